@@ -1,0 +1,102 @@
+"""ctypes binding of include/gridmm_b200.h -- the only door from Python into the CUDA kernels.
+
+There is deliberately no fallback: if the shared library is missing it is built with nvcc, and if that fails
+(or a kernel call returns non-zero) a GridmmError is raised.
+"""
+import ctypes
+import os
+import re
+
+from . import build as _build
+
+c_int, c_float, c_void_p, c_longlong = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
+
+
+class GridmmError(RuntimeError):
+    pass
+
+
+_ERR = {-1: "GRIDMM_ERR_SHAPE (unsupported size or alignment)", -2: "GRIDMM_ERR_DRIVER (tensor-map encode failed)",
+        -3: "GRIDMM_ERR_ARG (null pointer / inconsistent arguments)"}
+
+# name -> argument ctypes, in the order of include/gridmm_b200.h
+_SIGS = {
+    "gridmm_grid_update": [c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p],
+    "gridmm_cell_sort": [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "gridmm_pool": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                    c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "gridmm_linear_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                          c_void_p, c_int, c_int, c_void_p],
+    "gridmm_attention_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_float,
+                             c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "gridmm_layernorm": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    "gridmm_copy_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                         c_void_p],
+    "gridmm_pos_embed": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "gridmm_grid_assemble": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int, c_int, c_int, c_int, c_void_p],
+    "gridmm_cls_tail": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "gridmm_nav_logits": [c_void_p] * 16 + [c_int, c_int, c_int, c_void_p],
+}
+
+_lib = None
+
+
+def header_symbols():
+    """Every function name include/gridmm_b200.h declares (used by the CPU test-suite)."""
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gridmm_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"^\s*(?:int|long long|void)\s+(gridmm_\w+)\s*\(", txt, flags=re.M)))
+
+
+def load():
+    """Build (if needed) and dlopen the library; idempotent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.lib_path()
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = ctypes.CDLL(path)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    lib.gridmm_abi_version.restype = c_int
+    lib.gridmm_launch_count.restype = c_longlong
+    lib.gridmm_launch_count_reset.restype = None
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = _ERR.get(rc)
+        if msg is None:
+            msg = "cudaError %d" % rc
+        raise GridmmError("%s failed: %s" % (name, msg))
+
+
+def launch_count():
+    return int(load().gridmm_launch_count())
+
+
+def launch_count_reset():
+    load().gridmm_launch_count_reset()

@@ -1,0 +1,207 @@
+// Multi-head attention core for the small sequences of the navigation step:
+//   O = softmax(Q K^T / sqrt(64) + key_mask) V,   12 heads x 64, Sq <= ~300, Sk <= ~700.
+// Reference: BertSelfAttention / BertOutAttention (map_nav_src/models/vilmodel.py:95-153, 317-368, additive
+// -10000 mask from extend_neg_masks, models/ops.py:25-34) and nn.MultiheadAttention with key_padding_mask
+// (-inf) inside TransformerEncoderLayer.forward_pre (models/transformer.py:170-182).
+//
+// One CTA per (64-query tile, head, episode): K, V of that (episode, head) are staged once in shared memory
+// with cp.async, each warp owns 16 query rows and runs a flash-style online softmax over 64-key tiles with
+// mma.sync.m16n8k16 (fp16 in, fp32 accumulate).  The projections around this core -- where the FLOPs are --
+// run on tcgen05 (gemm_tc.cu); this core is softmax/latency bound at these sizes.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace gmm {
+
+constexpr int ATT_DH = 64;
+constexpr int ATT_LD = 72;          // padded smem row (halves): 144 B, 16-byte aligned, conflict-free ldmatrix
+constexpr int ATT_QT = 64;
+constexpr int ATT_THREADS = 128;
+
+struct AttnParams {
+    const __half* q; const __half* k; const __half* v; __half* o;
+    int ldq, ldk, ldv, ldo;            // row pitches in halves
+    int q_rows, k_rows;                // rows per episode in the q / kv buffers (batch stride)
+    const uint8_t* kmask;              // [B, Sk] 1 = valid key
+    float mask_neg;                    // -10000 (BERT additive) or -inf (key_padding_mask)
+    int sq, sk;
+    float scale;
+};
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS) attn_kernel(AttnParams p) {
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    const int sk_pad = (p.sk + 63) & ~63;
+    __half* sK = reinterpret_cast<__half*>(att_smem);
+    __half* sV = sK + static_cast<size_t>(sk_pad) * ATT_LD;
+    __half* sQ = sV + static_cast<size_t>(sk_pad) * ATT_LD;
+    float* sM = reinterpret_cast<float*>(sQ + ATT_QT * ATT_LD);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * ATT_QT, h = blockIdx.y, b = blockIdx.z;
+    const __half* gq = p.q + (static_cast<size_t>(b) * p.q_rows) * p.ldq + h * ATT_DH;
+    const __half* gk = p.k + (static_cast<size_t>(b) * p.k_rows) * p.ldk + h * ATT_DH;
+    const __half* gv = p.v + (static_cast<size_t>(b) * p.k_rows) * p.ldv + h * ATT_DH;
+
+    // stage K, V (all keys) and the Q tile; rows past the end are zero-filled
+    for (int i = tid; i < sk_pad * 8; i += ATT_THREADS) {
+        const int r = i >> 3, u = i & 7;
+        const uint32_t dk = smem_u32(sK + r * ATT_LD + u * 8), dv = smem_u32(sV + r * ATT_LD + u * 8);
+        if (r < p.sk) {
+            cp_async_16(dk, gk + static_cast<size_t>(r) * p.ldk + u * 8);
+            cp_async_16(dv, gv + static_cast<size_t>(r) * p.ldv + u * 8);
+        } else {
+            *reinterpret_cast<uint4*>(sK + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(sV + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    for (int i = tid; i < ATT_QT * 8; i += ATT_THREADS) {
+        const int r = i >> 3, u = i & 7;
+        if (q0 + r < p.sq) cp_async_16(smem_u32(sQ + r * ATT_LD + u * 8), gq + static_cast<size_t>(q0 + r) * p.ldq + u * 8);
+        else *reinterpret_cast<uint4*>(sQ + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+    for (int j = tid; j < sk_pad; j += ATT_THREADS) {
+        float m = -INFINITY;                                   // keys past Sk never contribute
+        if (j < p.sk) m = p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg;
+        sM[j] = m;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    // Q fragments: 16 rows x 64 dims = 4 k-steps
+    uint32_t qf[4][4];
+    {
+        const int m = lane >> 3, rr = lane & 7;
+        const int row = warp * 16 + (m & 1) * 8 + rr;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            ldsm_x4(smem_u32(sQ + row * ATT_LD + ks * 16 + (m >> 1) * 8), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    for (int kt = 0; kt < sk_pad; kt += 64) {
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+            const int key = kt + nt * 8 + (lane & 7);
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {   // two k-steps per ldmatrix.x4
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(smem_u32(sK + key * ATT_LD + kp * 32 + (lane >> 3) * 8), b0, b1, b2, b3);
+                mma_16816(s[nt], qf[2 * kp], b0, b1);
+                mma_16816(s[nt], qf[2 * kp + 1], b2, b3);
+            }
+        }
+        // scale + mask, row maxima (rows g and g+8)
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float ma = sM[kt + nt * 8 + 2 * t], mb = sM[kt + nt * 8 + 2 * t + 1];
+            s[nt][0] = s[nt][0] * p.scale + ma; s[nt][1] = s[nt][1] * p.scale + mb;
+            s[nt][2] = s[nt][2] * p.scale + ma; s[nt][3] = s[nt][3] * p.scale + mb;
+            mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+        }
+        float corr[2], m_use[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);
+            m_use[r] = (m_new == -INFINITY) ? 0.0f : m_new;
+            corr[r] = exp2f((m_run[r] - m_use[r]) * LOG2E);      // m_run = -inf -> 0
+            m_run[r] = m_new;
+            l_run[r] *= corr[r];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float p0 = exp2f((s[nt][0] - m_use[0]) * LOG2E), p1 = exp2f((s[nt][1] - m_use[0]) * LOG2E);
+            const float p2 = exp2f((s[nt][2] - m_use[1]) * LOG2E), p3 = exp2f((s[nt][3] - m_use[1]) * LOG2E);
+            l_run[0] += p0 + p1;
+            l_run[1] += p2 + p3;
+            // C fragments of n-tiles 2j, 2j+1 form the A fragment of key step j
+            pf[nt >> 1][(nt & 1) * 2 + 0] = pack_h2(p0, p1);
+            pf[nt >> 1][(nt & 1) * 2 + 1] = pack_h2(p2, p3);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int m = lane >> 3, rr = lane & 7;
+            const int key = kt + ks * 16 + (m & 1) * 8 + rr;
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {   // two 8-wide dim tiles per ldmatrix.x4.trans
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(smem_u32(sV + key * ATT_LD + (dp * 2 + (m >> 1)) * 8), b0, b1, b2, b3);
+                mma_16816(o[dp * 2], pf[ks], b0, b1);
+                mma_16816(o[dp * 2 + 1], pf[ks], b2, b3);
+            }
+        }
+    }
+    // finalize: quad-reduce the row sums, normalise, store fp16
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = l_run[0] > 0.0f ? 1.0f / l_run[0] : 0.0f;
+    const float inv1 = l_run[1] > 0.0f ? 1.0f / l_run[1] : 0.0f;
+    const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
+    __half* go = p.o + (static_cast<size_t>(b) * p.q_rows) * p.ldo + h * ATT_DH;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (row0 < p.sq)
+            *reinterpret_cast<uint32_t*>(go + static_cast<size_t>(row0) * p.ldo + i * 8 + 2 * t) = pack_h2(o[i][0] * inv0, o[i][1] * inv0);
+        if (row1 < p.sq)
+            *reinterpret_cast<uint32_t*>(go + static_cast<size_t>(row1) * p.ldo + i * 8 + 2 * t) = pack_h2(o[i][2] * inv1, o[i][3] * inv1);
+    }
+}
+
+}  // namespace gmm
+
+extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
+                                    int k_rows, void* o, int ldo, const unsigned char* kmask, float mask_neg, int batch,
+                                    int heads, int sq, int sk, float scale, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0 || sq <= 0) return 0;
+    if (!q || !k || !v || !o || !kmask) return GRIDMM_ERR_ARG;
+    if (sk <= 0 || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return GRIDMM_ERR_SHAPE;
+    AttnParams p;
+    p.q = reinterpret_cast<const __half*>(q); p.k = reinterpret_cast<const __half*>(k);
+    p.v = reinterpret_cast<const __half*>(v); p.o = reinterpret_cast<__half*>(o);
+    p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.q_rows = q_rows; p.k_rows = k_rows;
+    p.kmask = kmask; p.mask_neg = mask_neg; p.sq = sq; p.sk = sk; p.scale = scale;
+    const int sk_pad = (sk + 63) & ~63;
+    const int smem = (2 * sk_pad + ATT_QT) * ATT_LD * 2 + sk_pad * 4;
+    if (smem > 227 * 1024) return GRIDMM_ERR_SHAPE;
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid((sq + ATT_QT - 1) / ATT_QT, heads, batch);
+    attn_kernel<<<grid, ATT_THREADS, smem, stream>>>(p);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}

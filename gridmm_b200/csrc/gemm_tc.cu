@@ -1,0 +1,199 @@
+// tcgen05 GEMM for the cross-modal encoder blocks:
+//   C[M,N] = epilogue( A[M,K] (fp16, K contiguous) x W[N,K]^T (fp16, K contiguous) ),  fp32 accumulation in TMEM.
+// This is nn.Linear: the reference's BertSelfAttention/BertOutAttention projections
+// (map_nav_src/models/vilmodel.py:95-153, 317-368), BertIntermediate/BertOutput (:184-209),
+// nn.MultiheadAttention in/out projections + linear1/linear2 (map_nav_src/models/transformer.py:133-182),
+// ClsPrediction first layer (vilmodel.py:663-674), text_proj/grid_proj (:702-703).
+//
+// Structure (one 128 x BN output tile per CTA, 6 warps):
+//   warp 0      TMA producer: 128x64 A tile + BNx64 W tile per stage, SWIZZLE_128B, mbarrier complete_tx
+//   warp 1      allocates TMEM, issues tcgen05.mma (one thread), commits stages back to the producer
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns, bias / GELU / ReLU / residual, fp32 and/or fp16 stores
+#include "common.cuh"
+#include "host_util.h"
+
+namespace gmm {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmEpilogue {
+    const float* bias;       // [N] or null
+    const float* residual;   // [M, ld_res] fp32 or null (added after the activation)
+    float* out_f32;          // [M, ld_f32] or null
+    __half* out_f16;         // [M, ld_f16] or null
+    int ld_res, ld_f32, ld_f16;
+    int act;                 // 0 none, 1 GELU(erf), 2 ReLU
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem slot + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
+                   GemmEpilogue ep) {
+    using L = GemmSmem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * GEMM_BM;
+    const int num_kb = K / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + L::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                tma_load_2d(a_dst, &tmA, kb * GEMM_BK, m0, &full_bar[s]);
+                tma_load_2d(b_dst, &tmW, kb * GEMM_BK, n0, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint64_t da = umma_desc_sw128_kmajor(a_addr);
+                const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
+                    umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // epilogue warps: TMEM lane quadrant is fixed by warp id % 4
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const bool row_ok = row < M;
+#pragma unroll 1
+        for (int c = 0; c < BN / 16; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 16, v);
+            tmem_ld_wait();
+            if (!row_ok) continue;
+            const int col = n0 + c * 16;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (ep.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+                    f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                }
+            }
+            if (ep.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752440f));
+            } else if (ep.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+            if (ep.residual) {
+                const float* r = ep.residual + static_cast<size_t>(row) * ep.ld_res + col;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(r + j);
+                    f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                }
+            }
+            if (ep.out_f32) {
+                float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+            if (ep.out_f16) {
+                __half* o = ep.out_f16 + static_cast<size_t>(row) * ep.ld_f16 + col;
+                uint32_t p[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                    p[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
+                *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+}  // namespace gmm
+
+// ----------------------------------------------------------------------------- C ABI
+extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                                 const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
+                                 int act, cudaStream_t stream) {
+    using namespace gmm;
+    if (M <= 0) return 0;
+    if (N % 128 != 0 || K % GEMM_BK != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
+    if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
+    constexpr int BN = 128, STAGES = 4;
+    CUtensorMap tmA, tmW;
+    int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2,
+                              GEMM_BK, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, GEMM_BK,
+                          BN);
+    if (rc) return rc;
+    GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act};
+    auto kern = gemm_f16_tn_kernel<BN, STAGES>;
+    constexpr int smem = GemmSmem<BN, STAGES>::TOTAL;
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(N / BN, (M + GEMM_BM - 1) / GEMM_BM);
+    kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmW, M, N, K, ep);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,47 @@
+#include "host_util.h"
+
+#include <atomic>
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        // resolved through the runtime so the library has no link-time dependency on libcuda
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+std::atomic<long long> g_launches{0};
+}  // namespace
+
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
+                     uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return GRIDMM_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_pitch_bytes & 15)) return GRIDMM_ERR_SHAPE;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : GRIDMM_ERR_DRIVER;
+}
+
+void gridmm_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" long long gridmm_launch_count() { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void gridmm_launch_count_reset() { g_launches.store(0, std::memory_order_relaxed); }
+extern "C" int gridmm_abi_version() { return 1; }

@@ -1,0 +1,388 @@
+// Row-wise kernels around the GEMMs of the navigation step (all hidden size 768, one warp per row):
+//   layer norm (BertLayerNorm eps 1e-12 / nn.LayerNorm eps 1e-5), the small position-feature embeddings
+//   (Linear(5|7|14 -> 768) + LayerNorm, map_nav_src/models/vilmodel.py:697-700, 563-566, 534-537),
+//   grid-cell assembly incl. the reference's mask-compaction quirk (vilmodel.py:813-823),
+//   ClsPrediction tails and the action-logit fusion (vilmodel.py:859-907).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace gmm {
+
+constexpr int HID = 768;
+constexpr int HV = HID / 128;   // float4 per lane
+
+__device__ __forceinline__ void ln_row(float4 (&x)[HV], const float* gamma, const float* beta, float eps, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < HV; ++i) s += x[i].x + x[i].y + x[i].z + x[i].w;
+    const float mean = warp_sum(s) * (1.0f / HID);
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+        const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+        v += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(v) * (1.0f / HID) + eps);
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+        const float4 bb = *reinterpret_cast<const float4*>(beta + col);
+        x[i].x = (x[i].x - mean) * rstd * g.x + bb.x;
+        x[i].y = (x[i].y - mean) * rstd * g.y + bb.y;
+        x[i].z = (x[i].z - mean) * rstd * g.z + bb.z;
+        x[i].w = (x[i].w - mean) * rstd * g.w + bb.w;
+    }
+}
+
+__device__ __forceinline__ void store_row(float4 (&x)[HV], float* o32, __half* o16, int lane) {
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        if (o32) *reinterpret_cast<float4*>(o32 + col) = x[i];
+        if (o16) {
+            const __half2 a = __floats2half2_rn(x[i].x, x[i].y), b = __floats2half2_rn(x[i].z, x[i].w);
+            uint2 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&a);
+            u.y = *reinterpret_cast<const uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(o16 + col) = u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- layer norm
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx, const float* gamma, const float* beta,
+                                                        float eps, float* o32, int ld32, __half* o16, int ld16, int rows) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4 v[HV];
+#pragma unroll
+    for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx + (i * 32 + lane) * 4);
+    ln_row(v, gamma, beta, eps, lane);
+    store_row(v, o32 ? o32 + static_cast<size_t>(row) * ld32 : nullptr, o16 ? o16 + static_cast<size_t>(row) * ld16 : nullptr, lane);
+}
+
+// ------------------------------------------------------------------------------------------- row copies / casts
+// out[b, out_off + r] = in[b, in_off + r] for r < rows_per_b  (fp32 in; fp32 and/or fp16 out): builds the
+// [map; txt] and [gmap; vp] sequences (vilmodel.py:843-850) and the head inputs without torch.cat.
+__global__ void __launch_bounds__(256) copy_rows_kernel(const float* x, int ldx, int in_rows_per_b, int in_off, float* o32,
+                                                        int ld32, __half* o16, int ld16, int out_rows_per_b, int out_off,
+                                                        int rows_per_b, int rows) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int b = row / rows_per_b, r = row - b * rows_per_b;
+    const size_t irow = static_cast<size_t>(b) * in_rows_per_b + in_off + r;
+    const size_t orow = static_cast<size_t>(b) * out_rows_per_b + out_off + r;
+    float4 v[HV];
+#pragma unroll
+    for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(x + irow * ldx + (i * 32 + lane) * 4);
+    store_row(v, o32 ? o32 + orow * ld32 : nullptr, o16 ? o16 + orow * ld16 : nullptr, lane);
+}
+
+// ------------------------------------------------------------------------------------------- position embeddings
+// out[b, off + r] = base[b, r] + table[idx[b, r]] + LN(W f[b, r] + bias)      (base / table optional)
+struct EmbedParams {
+    const float* feat; int kin;                 // [rows, kin]
+    const float* w; const float* bias;          // [768, kin], [768]
+    const float* gamma; const float* beta; float eps;
+    const float* base;                          // [rows, 768] or null
+    const float* table; const long long* idx;   // [n, 768], [rows] or null
+    float* o32; __half* o16;                    // [B, out_rows_per_b, 768]
+    int in_rows_per_b, out_rows_per_b, out_row_off, rows;
+};
+
+__global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= p.rows) return;
+    float f[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = (k < p.kin) ? p.feat[static_cast<size_t>(row) * p.kin + k] : 0.0f;
+    float4 v[HV];
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        float a[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float s = p.bias[col + c];
+            const float* wr = p.w + static_cast<size_t>(col + c) * p.kin;
+            for (int k = 0; k < p.kin; ++k) s = fmaf(f[k], wr[k], s);
+            a[c] = s;
+        }
+        v[i] = make_float4(a[0], a[1], a[2], a[3]);
+    }
+    ln_row(v, p.gamma, p.beta, p.eps, lane);
+    if (p.base) {
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(p.base + static_cast<size_t>(row) * HID + (i * 32 + lane) * 4);
+            v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+        }
+    }
+    if (p.table) {
+        const float* tr = p.table + static_cast<size_t>(p.idx[row]) * HID;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(tr + (i * 32 + lane) * 4);
+            v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+        }
+    }
+    const int b = row / p.in_rows_per_b, r = row - b * p.in_rows_per_b;
+    const size_t orow = static_cast<size_t>(b) * p.out_rows_per_b + p.out_row_off + r;
+    store_row(v, p.o32 ? p.o32 + orow * HID : nullptr, p.o16 ? p.o16 + orow * HID : nullptr, lane);
+}
+
+// ------------------------------------------------------------------------------------------- grid-cell assembly
+// Rows [0, n_cells) of every episode's map sequence (vilmodel.py:813-823):
+//   r <  k_b : grid_proj(pooled)[b, r] + grid_pos_embeddings(pos_fts[b, cell of rank r])
+//   r >= k_b : 0
+// and the validity mask WITH the reference's aliasing quirk: grid_mask is a view of grid_masks[b], so after
+// `grid_masks[b,:k] = 1` the second `.sum()` is re-read: k' = k + |S n [k, n_cells)| (S = non-empty cells) and the
+// row ends as [0,k) u (S n [k,k')), finally truncated to C = max_b k_b columns.
+struct AssembleParams {
+    const float* proj;        // [B, n_cells, 768] grid_proj output in rank order (rows >= k_b undefined)
+    const float* pos_fts;     // [B, n_cells, 5]
+    const int* cell_rank;     // [B, n_cells]
+    const int* n_nonempty;    // [B]
+    const float* w; const float* bias; const float* gamma; const float* beta;   // grid_pos_embeddings
+    float* map32;             // [B, seq, 768]
+    uint8_t* map_mask;        // [B, seq]
+    int batch, n_cells, seq;
+};
+
+__global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
+    __shared__ int s_inv[256];
+    __shared__ int s_red[8];
+    __shared__ int s_c, s_k2;
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = p.n_nonempty[b];
+    // C = max over the batch; k' for this episode
+    int mx = 0;
+    for (int i = tid; i < p.batch; i += 256) mx = max(mx, p.n_nonempty[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    int above = 0;
+    for (int c = tid; c < p.n_cells; c += 256) {
+        const int r = p.cell_rank[b * p.n_cells + c];
+        if (r >= 0) { s_inv[r] = c; above += (c >= k) ? 1 : 0; }
+    }
+    // block-sum of `above`
+    for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+    __shared__ int s_sum[8];
+    if (lane == 0) s_sum[warp] = above;
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0, s = 0;
+        for (int i = 0; i < 8; ++i) { m = max(m, s_red[i]); s += s_sum[i]; }
+        s_c = m; s_k2 = k + s;
+    }
+    __syncthreads();
+    const int C = s_c, k2 = s_k2;
+    const int rows_per_cta = (p.n_cells + gridDim.x - 1) / gridDim.x;
+    const int r_lo = blockIdx.x * rows_per_cta, r_hi = min(r_lo + rows_per_cta, p.n_cells);
+    for (int r = r_lo + warp; r < r_hi; r += 8) {
+        float4 v[HV];
+        if (r < k) {
+            const int cellid = s_inv[r];
+            float f[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) f[j] = p.pos_fts[(static_cast<size_t>(b) * p.n_cells + cellid) * 5 + j];
+#pragma unroll
+            for (int i = 0; i < HV; ++i) {
+                const int col = (i * 32 + lane) * 4;
+                float a[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float s = p.bias[col + c];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) s = fmaf(f[j], p.w[(col + c) * 5 + j], s);
+                    a[c] = s;
+                }
+                v[i] = make_float4(a[0], a[1], a[2], a[3]);
+            }
+            ln_row(v, p.gamma, p.beta, 1e-12f, lane);
+#pragma unroll
+            for (int i = 0; i < HV; ++i) {
+                const float4 t = *reinterpret_cast<const float4*>(p.proj + (static_cast<size_t>(b) * p.n_cells + r) * HID + (i * 32 + lane) * 4);
+                v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < HV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        store_row(v, p.map32 + (static_cast<size_t>(b) * p.seq + r) * HID, nullptr, lane);
+        if (lane == 0) {
+            const bool in_s = p.cell_rank[b * p.n_cells + r] >= 0;
+            const bool valid = (r < C) && ((r < k) || (r < k2 && in_s));
+            p.map_mask[static_cast<size_t>(b) * p.seq + r] = valid ? 1 : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- ClsPrediction tail
+// logit[row] = w2 . LN(h[row]) + b2      (h = ReLU(Linear(x)) comes from the GEMM epilogue)
+__global__ void __launch_bounds__(256) cls_tail_kernel(const float* h, const float* gamma, const float* beta, const float* w2,
+                                                       const float* b2, float* logit, int rows) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4 v[HV];
+#pragma unroll
+    for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(h + static_cast<size_t>(row) * HID + (i * 32 + lane) * 4);
+    ln_row(v, gamma, beta, 1e-12f, lane);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(w2 + (i * 32 + lane) * 4);
+        s += v[i].x * w.x + v[i].y * w.y + v[i].z * w.z + v[i].w * w.w;
+    }
+    s = warp_sum(s);
+    if (lane == 0) logit[row] = s + b2[0];
+}
+
+// ------------------------------------------------------------------------------------------- action logits
+// vilmodel.py:859-907.  One CTA per episode.
+struct LogitParams {
+    const float* raw_global;   // [B, G]
+    const float* raw_grid;     // [B, G]
+    const float* raw_local;    // [B, V]
+    const float* raw_obj;      // [B, V] or null
+    const float* raw_fuse;     // [B] or null (fuse weight 0.5)
+    const uint8_t* gmap_masks; const uint8_t* gmap_visited;   // [B, G]
+    const uint8_t* vp_nav_masks; const uint8_t* vp_obj_masks; // [B, V]
+    const int* fuse_src;       // [B, G]  >=0: add local[src]; -2: add the back-track sum; -1: nothing
+    const uint8_t* bw_mask;    // [B, V]  candidates that are already visited (their local logits are summed)
+    float* global_logits; float* grid_logits; float* local_logits; float* fused_logits; float* obj_logits;
+    int G, V;
+};
+
+__global__ void __launch_bounds__(128) nav_logits_kernel(LogitParams p) {
+    extern __shared__ float s_local[];
+    __shared__ float s_bw;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float ninf = -INFINITY;
+    float fw = 0.5f;
+    if (p.raw_fuse) fw = 1.0f / (1.0f + expf(-p.raw_fuse[b]));
+    for (int v = tid; v < p.V; v += blockDim.x) {
+        float l = p.raw_local[b * p.V + v] * (1.0f - fw);
+        if (!p.vp_nav_masks[b * p.V + v]) l = ninf;
+        s_local[v] = l;
+        p.local_logits[b * p.V + v] = l;
+        if (p.raw_obj) {
+            float o = p.raw_obj[b * p.V + v];
+            if (!p.vp_obj_masks[b * p.V + v]) o = ninf;
+            p.obj_logits[b * p.V + v] = o;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float bw = 0.0f;   // sequential, candidate order (the reference accumulates with `+=` in a Python loop)
+        for (int v = 1; v < p.V; ++v)
+            if (p.bw_mask[b * p.V + v]) bw += s_local[v];
+        s_bw = bw;
+    }
+    __syncthreads();
+    for (int g = tid; g < p.G; g += blockDim.x) {
+        const bool masked = p.gmap_visited[b * p.G + g] || !p.gmap_masks[b * p.G + g];
+        float gl = p.raw_global[b * p.G + g] * fw;
+        float gr = p.raw_grid[b * p.G + g];
+        if (masked) { gl = ninf; gr = ninf; }
+        p.global_logits[b * p.G + g] = gl;
+        p.grid_logits[b * p.G + g] = gr;
+        float f = gl;
+        if (g == 0) f += s_local[0];
+        else {
+            const int src = p.fuse_src[b * p.G + g];
+            if (src >= 0) f += s_local[src];
+            else if (src == -2) f += s_bw;
+        }
+        p.fused_logits[b * p.G + g] = f;
+    }
+}
+
+}  // namespace gmm
+
+// ----------------------------------------------------------------------------- C ABI
+extern "C" int gridmm_layernorm(const float* x, int ldx, const float* gamma, const float* beta, float eps, float* out_f32,
+                                int ld_f32, void* out_f16, int ld_f16, int rows, int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    if (rows <= 0) return 0;
+    if (hidden != HID || (ldx % 4) || (out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 4))) return GRIDMM_ERR_SHAPE;
+    if (!x || !gamma || !beta) return GRIDMM_ERR_ARG;
+    layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, gamma, beta, eps, out_f32, ld_f32,
+                                                         reinterpret_cast<__half*>(out_f16), ld_f16, rows);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int in_off, float* out_f32, int ld_f32,
+                                void* out_f16, int ld_f16, int out_rows_per_b, int out_off, int rows_per_b, int batch,
+                                int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    const int rows = rows_per_b * batch;
+    if (rows <= 0) return 0;
+    if (hidden != HID || (ldx % 4) || (out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 4))) return GRIDMM_ERR_SHAPE;
+    if (!x || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
+    copy_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, in_rows_per_b, in_off, out_f32, ld_f32,
+                                                         reinterpret_cast<__half*>(out_f16), ld_f16, out_rows_per_b, out_off,
+                                                         rows_per_b, rows);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int gridmm_pos_embed(const float* feat, int kin, const float* w, const float* bias, const float* gamma,
+                                const float* beta, float eps, const float* base, const float* table, const long long* idx,
+                                float* out_f32, void* out_f16, int in_rows_per_b, int out_rows_per_b, int out_row_off,
+                                int rows, int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    if (rows <= 0) return 0;
+    if (hidden != HID || kin < 1 || kin > 16 || in_rows_per_b <= 0) return GRIDMM_ERR_SHAPE;
+    if (!feat || !w || !bias || !gamma || !beta || (table && !idx) || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
+    EmbedParams p{feat, kin, w, bias, gamma, beta, eps, base, table, idx, out_f32, reinterpret_cast<__half*>(out_f16),
+                  in_rows_per_b, out_rows_per_b, out_row_off, rows};
+    embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(p);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int gridmm_grid_assemble(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty,
+                                    const float* w, const float* bias, const float* gamma, const float* beta, float* map_f32,
+                                    unsigned char* map_mask, int batch, int n_cells, int seq, int hidden,
+                                    cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (hidden != HID || n_cells > 256 || seq < n_cells) return GRIDMM_ERR_SHAPE;
+    if (!proj || !pos_fts || !cell_rank || !n_nonempty || !w || !bias || !gamma || !beta || !map_f32 || !map_mask)
+        return GRIDMM_ERR_ARG;
+    AssembleParams p{proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq};
+    grid_assemble_kernel<<<dim3(4, batch), 256, 0, stream>>>(p);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int gridmm_cls_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2,
+                               float* logit, int rows, int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    if (rows <= 0) return 0;
+    if (hidden != HID) return GRIDMM_ERR_SHAPE;
+    if (!h || !gamma || !beta || !w2 || !b2 || !logit) return GRIDMM_ERR_ARG;
+    cls_tail_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(h, gamma, beta, w2, b2, logit, rows);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int gridmm_nav_logits(const float* raw_global, const float* raw_grid, const float* raw_local, const float* raw_obj,
+                                 const float* raw_fuse, const unsigned char* gmap_masks, const unsigned char* gmap_visited,
+                                 const unsigned char* vp_nav_masks, const unsigned char* vp_obj_masks, const int* fuse_src,
+                                 const unsigned char* bw_mask, float* global_logits, float* grid_logits, float* local_logits,
+                                 float* fused_logits, float* obj_logits, int batch, int G, int V, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (!raw_global || !raw_grid || !raw_local || !gmap_masks || !gmap_visited || !vp_nav_masks || !fuse_src || !bw_mask ||
+        !global_logits || !grid_logits || !local_logits || !fused_logits || (raw_obj && (!vp_obj_masks || !obj_logits)))
+        return GRIDMM_ERR_ARG;
+    LogitParams p{raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_masks, gmap_visited, vp_nav_masks, vp_obj_masks,
+                  fuse_src, bw_mask, global_logits, grid_logits, local_logits, fused_logits, obj_logits, G, V};
+    nav_logits_kernel<<<batch, 128, V * sizeof(float), stream>>>(p);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,224 @@
+"""Device-resident grid-map state: the B200 counterpart of the grid half of the reference's `EnvBatch`
+(map_nav_src/r2r/env.py:125-400 -- `newEpisodes` :177-193, `getGlobalMap` :267-374, `getStates` :377-400).
+
+The reference keeps, per episode, Python lists of numpy arrays, re-concatenates the whole [N,768] feature map every
+step, rebuilds `grid_map` with a 196-iteration compare loop on the CPU and re-uploads everything to the GPU
+(map_nav_src/r2r/agent.py:168).  Here the state lives in HBM for the whole episode:
+
+    slab      fp16 [t_cap, B, 12*50, D]   the CLIP patch tokens of every visited viewpoint, written ONCE (one H2D copy of
+                                          the step's B viewpoints); the CLS token stays in place and is skipped by indexing
+    wx, wy    f32  [B, cap]               world coordinates of every accumulated point (cap = t_cap * 588)
+    valid     u8   [B, cap]               depth != 0
+    bounds    f32  [B, 4]                 running max_x, min_x, max_y, min_y
+
+and one kernel launch per step (gridmm_grid_update) appends the new viewpoint, re-assigns all points to cells
+(bit-exact with the reference arithmetic) and sorts them by cell for the pooling kernel.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+PTS = 588            # 12 horizon views x 49 patch centres (env.py:279-289)
+VIEW_TOKENS = 50     # CLS + 49 patches (env.py:100)
+_OFF7 = [-6 / 7, -4 / 7, -2 / 7, 0., 2 / 7, 4 / 7, 6 / 7]
+PATCH_CENTRES = np.array([9 + 18 * i for i in range(7)])          # env.py:279
+PATCH_CENTRES_CE = np.array([19 + 36 * i for i in range(7)])      # Policy_ViewSelection_GridMap.py (256x256 depth)
+
+
+class Geometry:
+    """Camera / rotation conventions."""
+
+    def __init__(self, name, depth_scale, tan_half_fov, flip_y, angle_offset, negate_map_x, view_minus_heading, depth_is_f32):
+        self.name = name
+        self.depth_scale = depth_scale
+        self.tan_half_fov = tan_half_fov
+        self.flip_y = flip_y
+        self.angle_offset = angle_offset
+        self.negate_map_x = negate_map_x
+        self.view_minus_heading = view_minus_heading
+        self.depth_is_f32 = depth_is_f32
+        # env.py:118: np.array(o, np.float32) * math.tan(...)  ->  f32(o_k) * f32(tan) in fp32
+        self.off7 = (np.array(_OFF7, np.float32) * np.float32(tan_half_fov)).astype(np.float32)
+
+
+GEOMETRIES = {
+    # discrete envs: map_nav_src/{r2r,reverie,rxr}/env.py, pretrain_src/data/dataset.py
+    "r2r": Geometry("r2r", 4000.0, math.tan(math.pi / 6), False, 0.0, False, False, False),
+    # VLN_CE/vlnce_baselines/models/Policy_ViewSelection_GridMap.py:632-641, 689-825 (R2R-CE, hfov 90)
+    "r2r_ce": Geometry("r2r_ce", 1.0, math.tan(math.pi / 4), True, math.pi, True, True, True),
+    # RxR-CE, hfov 79
+    "rxr_ce": Geometry("rxr_ce", 1.0, math.tan(79 * math.pi / 360), True, math.pi, True, True, True),
+}
+
+
+class GridBatch:
+    """Handle to the device-resident grid map of a batch of episodes after a step (what the model's 'navigation' mode
+    consumes instead of the reference's grid_fts / grid_map lists)."""
+
+    def __init__(self, builder):
+        b = builder
+        self.batch = b.batch
+        self.feat_dim = b.feat_dim
+        self.grid_w = b.grid_w
+        self.n_cells = b.grid_w * b.grid_w
+        self.slab, self.slots, self.t_cap = b.slab, b.slots, b.t_cap
+        self.slot_rows, self.view_rows, self.tok_off = 12 * VIEW_TOKENS, VIEW_TOKENS, 1
+        self.cap = b.cap
+        self.perm, self.cell_start, self.cell_rank, self.n_nonempty = b.perm, b.cell_start, b.cell_rank, b.n_nonempty
+        self.cell, self.pos_fts, self.half_len, self.n_pts = b.cell, b.pos_fts, b.half_len, b.n_pts
+        self.n_steps = b.n_steps
+
+    # ---- views in the reference's formats (tests / drop-in consumers; these DO copy) ----
+    def grid_map_numpy(self):
+        """list of float64[N] with values in {-1, 0..n_cells-1} -- env.py:300-306,366-369."""
+        n = self.n_pts.cpu().numpy()
+        cell = self.cell.cpu().numpy()
+        return [cell[i, :n[i]].astype(np.float64) for i in range(self.batch)]
+
+    def grid_fts_torch(self):
+        """list of fp16[N, D] device tensors in point order (env.py:299-304)."""
+        out = []
+        slab = self.slab.view(-1, 12, VIEW_TOKENS, self.feat_dim)
+        slots = self.slots.view(self.batch, self.t_cap).cpu().numpy()
+        for i in range(self.batch):
+            t = int(self.n_steps[i])
+            rows = slab[torch.as_tensor(slots[i, :t].astype(np.int64), device=slab.device)]   # [t,12,50,D]
+            out.append(rows[:, :, 1:, :].reshape(-1, self.feat_dim))
+        return out
+
+
+class GridMapBuilder:
+    """`EnvBatch`-side replacement: persistent device buffers + one launch per step for the whole batch."""
+
+    def __init__(self, batch_size, feat_dim=768, grid_w=14, geometry="r2r", max_steps=16, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gridmm_b200.GridMapBuilder needs a CUDA device (there is no CPU path)")
+        self.batch = int(batch_size)
+        self.feat_dim = int(feat_dim)
+        self.grid_w = int(grid_w)
+        self.geom = GEOMETRIES[geometry] if isinstance(geometry, str) else geometry
+        self.device = torch.device(device)
+        self.t_cap = 0
+        self._alloc(int(max_steps))
+        B, nc = self.batch, self.grid_w * self.grid_w
+        dev = self.device
+        self.bounds = torch.empty(B, 4, dtype=torch.float32, device=dev)
+        self.n_pts = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.half_len = torch.zeros(B, dtype=torch.float32, device=dev)
+        self.cell_start = torch.zeros(B, nc + 1, dtype=torch.int32, device=dev)
+        self.cell_rank = torch.zeros(B, nc, dtype=torch.int32, device=dev)
+        self.n_nonempty = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.pos_fts = torch.zeros(B, nc, 5, dtype=torch.float32, device=dev)
+        # per-step staging (pinned host -> device)
+        self.h_depth_u16 = torch.empty(B, PTS, dtype=torch.int16).pin_memory()
+        self.h_depth_f32 = torch.empty(B, PTS, dtype=torch.float32).pin_memory()
+        self.h_pose = torch.empty(B, 4 + 24, dtype=torch.float32).pin_memory()     # pose[4] ++ view_cs[12*2]
+        self.h_clip = torch.empty(B, 12, VIEW_TOKENS, self.feat_dim, dtype=torch.float16).pin_memory()
+        self.d_depth_u16 = torch.empty(B, PTS, dtype=torch.int16, device=dev)
+        self.d_depth_f32 = torch.empty(B, PTS, dtype=torch.float32, device=dev)
+        self.d_pose = torch.empty(B, 4 + 24, dtype=torch.float32, device=dev)
+        self.new_episodes()
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, t_cap):
+        B, D, dev = self.batch, self.feat_dim, self.device
+        old = self.t_cap
+        cap = t_cap * PTS
+        if cap > 65535:
+            raise ValueError("at most 111 viewpoints per episode (cell sort uses 16-bit cursors)")
+        slab = torch.empty(t_cap, B, 12 * VIEW_TOKENS, D, dtype=torch.float16, device=dev)
+        wx = torch.zeros(B, cap, dtype=torch.float32, device=dev)
+        wy = torch.zeros(B, cap, dtype=torch.float32, device=dev)
+        valid = torch.zeros(B, cap, dtype=torch.uint8, device=dev)
+        if old:
+            slab[:old].copy_(self.slab)
+            wx[:, :old * PTS].copy_(self.wx); wy[:, :old * PTS].copy_(self.wy); valid[:, :old * PTS].copy_(self.valid)
+        self.slab, self.wx, self.wy, self.valid = slab, wx, wy, valid
+        self.cell = torch.full((B, cap), -1, dtype=torch.int16, device=dev)
+        self.perm = torch.zeros(B, cap, dtype=torch.int32, device=dev)
+        # slot of (episode b, step t) = t * B + b  -> the B viewpoints of one step are one contiguous H2D copy
+        slots = (torch.arange(t_cap, dtype=torch.int32)[None, :] * B + torch.arange(B, dtype=torch.int32)[:, None])
+        self.slots = slots.contiguous().to(dev)
+        self.t_cap, self.cap = t_cap, cap
+
+    def new_episodes(self):
+        """env.py:183-193."""
+        self.bounds.copy_(torch.tensor([-10000.0, 10000.0, -10000.0, 10000.0]).repeat(self.batch, 1))
+        self.n_pts.zero_()
+        self.n_steps = np.zeros(self.batch, dtype=np.int64)
+
+    # ------------------------------------------------------------------ one navigation step
+    @staticmethod
+    def subsample_depth(depth_full, ce=False):
+        """[..,36|12,H,W] depth map -> [..,12,49] patch-centre samples (env.py:279-285)."""
+        c = PATCH_CENTRES_CE if ce else PATCH_CENTRES
+        d = depth_full
+        if d.shape[-3] == 36:
+            d = d[..., 12:24, :, :]
+        return d[..., c[:, None], c[None, :]].reshape(d.shape[:-2] + (49,))
+
+    def host_pose(self, pos_xy, heading):
+        """pose / view trigonometry, evaluated in double and rounded to fp32 like the reference
+        (python float x np.float32 array, env.py:119-120, 290, 337, 347-348)."""
+        B, g = self.batch, self.geom
+        pos_xy = np.asarray(pos_xy, dtype=np.float64).reshape(B, 2)
+        heading = np.asarray(heading, dtype=np.float64).reshape(B)
+        out = np.empty((B, 28), dtype=np.float32)
+        out[:, 0:2] = pos_xy.astype(np.float32)
+        ang = -heading + g.angle_offset
+        out[:, 2] = np.cos(ang).astype(np.float32)
+        out[:, 3] = np.sin(ang).astype(np.float32)
+        v = np.arange(12, dtype=np.float64) * math.pi / 6
+        va = v[None, :] - heading[:, None] if g.view_minus_heading else np.broadcast_to(v[None, :], (B, 12))
+        out[:, 4::2] = np.cos(va).astype(np.float32)
+        out[:, 5::2] = np.sin(va).astype(np.float32)
+        return out
+
+    def step(self, depth_sub, clip, pos_xy, heading, active=None):
+        """Append one viewpoint per episode and rebuild the grid assignment (getStates' grid half, env.py:392-398).
+
+        depth_sub : [B,12,49] uint16 (0.25 mm) or float32 metres (CE); numpy (host) or a device tensor
+        clip      : [B,12,50,D] fp16 CLIP tokens incl. CLS; numpy / host tensor (copied H2D) or a device tensor
+        pos_xy    : [B,2] viewpoint x,y (python floats / float64);  heading : [B] radians
+        Returns a GridBatch.
+        """
+        B, g = self.batch, self.geom
+        if int(self.n_steps.max()) + 1 > self.t_cap:
+            self._alloc(self.t_cap * 2)
+        if active is not None and not bool(np.all(active)):
+            raise NotImplementedError("per-episode `active` masks need per-episode step counters on the slab; "
+                                      "the reference re-adds the last viewpoint of ended episodes, so do that")
+        t = int(self.n_steps[0])
+        # features: one contiguous copy into slab[t]
+        if isinstance(clip, torch.Tensor) and clip.is_cuda:
+            self.slab[t].copy_(clip.reshape(B, 12 * VIEW_TOKENS, self.feat_dim))
+        else:
+            self.h_clip.copy_(torch.as_tensor(clip).reshape(self.h_clip.shape))
+            self.slab[t].copy_(self.h_clip.view(B, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
+        # depth
+        if isinstance(depth_sub, torch.Tensor) and depth_sub.is_cuda:
+            d_depth = depth_sub.reshape(B, PTS).contiguous()
+        elif g.depth_is_f32:
+            self.h_depth_f32.copy_(torch.as_tensor(np.ascontiguousarray(depth_sub, dtype=np.float32)).reshape(B, PTS))
+            self.d_depth_f32.copy_(self.h_depth_f32, non_blocking=True)
+            d_depth = self.d_depth_f32
+        else:
+            arr = np.ascontiguousarray(depth_sub).astype(np.uint16, copy=False).reshape(B, PTS)
+            self.h_depth_u16.copy_(torch.from_numpy(arr.view(np.int16)))
+            self.d_depth_u16.copy_(self.h_depth_u16, non_blocking=True)
+            d_depth = self.d_depth_u16
+        self.h_pose.copy_(torch.from_numpy(self.host_pose(pos_xy, heading)))
+        self.d_pose.copy_(self.h_pose, non_blocking=True)
+        pose = self.d_pose[:, :4]
+        view_cs = self.d_pose[:, 4:]
+        # gridmm_grid_update reads pose with row pitch 4 and view_cs with pitch 24: hand it packed copies
+        self._pose4 = pose.contiguous()
+        self._view24 = view_cs.contiguous()
+        ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self._pose4, self._view24, None, g.off7, g.flip_y,
+                        g.negate_map_x, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
+                        self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
+        self.n_steps += 1
+        return GridBatch(self)

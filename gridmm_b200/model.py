@@ -1,0 +1,578 @@
+"""`GlocalTextPathNavCMT` / `VLNBert` with the reference's constructor config, `forward(mode, batch)` signature and
+state_dict keys (map_nav_src/models/vilmodel.py:676-939, map_nav_src/models/model.py:12-40), whose 'navigation' mode
+(vilmodel.py:782-918) runs entirely on the sm_100a kernels of this package.
+
+Parameters are ordinary nn.Parameters with the reference's names, so reference checkpoints load with
+`load_state_dict` (after the key remap of models/vlnbert_init.py:19-27, see `remap_pretrained_keys`) and DDP /
+optimizers / `agent.save()` keep working; the kernels borrow fp16 copies of the weights that are refreshed whenever a
+parameter's version counter changes.
+
+The forward here is inference (eval-mode semantics: dropout = identity), which is what SURVEY 8(b) pins for parity.
+"""
+import collections
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .env import GridBatch
+
+HID = 768
+HEADS = 12
+NEG_BERT = -10000.0          # extend_neg_masks, models/ops.py:25-34
+NEG_INF = float("-inf")      # key_padding_mask, models/transformer.py:176-177
+
+
+class NavConfig:
+    """The attributes models/vlnbert_init.py:29-56 puts on the BertConfig."""
+
+    def __init__(self, **kw):
+        self.vocab_size = 30522
+        self.hidden_size = HID
+        self.num_attention_heads = HEADS
+        self.intermediate_size = 3072
+        self.max_position_embeddings = 512
+        self.type_vocab_size = 2
+        self.max_action_steps = 100
+        self.image_feat_size = 768
+        self.angle_feat_size = 4
+        self.obj_feat_size = 0
+        self.obj_loc_size = 3
+        self.num_l_layers = 9
+        self.num_pano_layers = 2
+        self.num_x_layers = 4
+        self.graph_sprels = True
+        self.glocal_fuse = True
+        self.grid_w = 14             # GLOBAL_WIDTH / GLOBAL_HEIGHT, map_nav_src/r2r/env.py:43-44 (hard-coded there)
+        for k, v in kw.items():
+            setattr(self, k, v)
+        if self.hidden_size != HID or self.num_attention_heads != HEADS:
+            raise ValueError("the sm_100a kernels are specialised for hidden 768 / 12 heads (BERT-base, as the reference)")
+
+
+def _attn_self(p, pre, spec):
+    for n in ("query", "key", "value"):
+        spec[pre + ".self.%s.weight" % n] = ((HID, HID), "w")
+        spec[pre + ".self.%s.bias" % n] = ((HID,), "b")
+    spec[pre + ".output.dense.weight"] = ((HID, HID), "w")
+    spec[pre + ".output.dense.bias"] = ((HID,), "b")
+    spec[pre + ".output.LayerNorm.weight"] = ((HID,), "g")
+    spec[pre + ".output.LayerNorm.bias"] = ((HID,), "b")
+
+
+def _ffn(pre_i, pre_o, inter, spec):
+    spec[pre_i + ".dense.weight"] = ((inter, HID), "w")
+    spec[pre_i + ".dense.bias"] = ((inter,), "b")
+    spec[pre_o + ".dense.weight"] = ((HID, inter), "w")
+    spec[pre_o + ".dense.bias"] = ((HID,), "b")
+    spec[pre_o + ".LayerNorm.weight"] = ((HID,), "g")
+    spec[pre_o + ".LayerNorm.bias"] = ((HID,), "b")
+
+
+def _lxrt(pre, inter, spec):
+    """GraphLXRTXLayer parameters in the reference's registration order (vilmodel.py:381-397)."""
+    _attn_self(None, pre + ".visn_self_att", spec)
+    _ffn(pre + ".visn_inter", pre + ".visn_output", inter, spec)
+    q = pre + ".visual_attention"
+    for n in ("query", "key", "value"):
+        spec[q + ".att.%s.weight" % n] = ((HID, HID), "w")
+        spec[q + ".att.%s.bias" % n] = ((HID,), "b")
+    spec[q + ".output.dense.weight"] = ((HID, HID), "w")
+    spec[q + ".output.dense.bias"] = ((HID,), "b")
+    spec[q + ".output.LayerNorm.weight"] = ((HID,), "g")
+    spec[q + ".output.LayerNorm.bias"] = ((HID,), "b")
+
+
+def _prenorm(pre, n_layers, inter, spec):
+    """create_transformer_encoder(config, n, norm=True) (models/ops.py:11-23)."""
+    for i in range(n_layers):
+        q = "%s.layers.%d" % (pre, i)
+        spec[q + ".self_attn.in_proj_weight"] = ((3 * HID, HID), "w")
+        spec[q + ".self_attn.in_proj_bias"] = ((3 * HID,), "b")
+        spec[q + ".self_attn.out_proj.weight"] = ((HID, HID), "w")
+        spec[q + ".self_attn.out_proj.bias"] = ((HID,), "b")
+        spec[q + ".linear1.weight"] = ((inter, HID), "w")
+        spec[q + ".linear1.bias"] = ((inter,), "b")
+        spec[q + ".linear2.weight"] = ((HID, inter), "w")
+        spec[q + ".linear2.bias"] = ((HID,), "b")
+        for n in ("norm1", "norm2"):
+            spec[q + ".%s.weight" % n] = ((HID,), "g")
+            spec[q + ".%s.bias" % n] = ((HID,), "b")
+    spec[pre + ".norm.weight"] = ((HID,), "g")
+    spec[pre + ".norm.bias"] = ((HID,), "b")
+
+
+def _lin_ln(pre, kin, spec):
+    spec[pre + ".0.weight"] = ((HID, kin), "w")
+    spec[pre + ".0.bias"] = ((HID,), "b")
+    spec[pre + ".1.weight"] = ((HID,), "g")
+    spec[pre + ".1.bias"] = ((HID,), "b")
+
+
+def _cls(pre, kin, spec):
+    spec[pre + ".net.0.weight"] = ((HID, kin), "w")
+    spec[pre + ".net.0.bias"] = ((HID,), "b")
+    spec[pre + ".net.2.weight"] = ((HID,), "g")
+    spec[pre + ".net.2.bias"] = ((HID,), "b")
+    spec[pre + ".net.3.weight"] = ((1, HID), "w")
+    spec[pre + ".net.3.bias"] = ((1,), "b")
+
+
+def param_spec(cfg):
+    """name -> (shape, kind) for every parameter of the reference GlocalTextPathNavCMT, in its state_dict order."""
+    s = collections.OrderedDict()
+    inter = cfg.intermediate_size
+    s["embeddings.word_embeddings.weight"] = ((cfg.vocab_size, HID), "w")
+    s["embeddings.position_embeddings.weight"] = ((cfg.max_position_embeddings, HID), "w")
+    s["embeddings.token_type_embeddings.weight"] = ((cfg.type_vocab_size, HID), "w")
+    s["embeddings.LayerNorm.weight"] = ((HID,), "g")
+    s["embeddings.LayerNorm.bias"] = ((HID,), "b")
+    for i in range(cfg.num_l_layers):
+        p = "lang_encoder.layer.%d" % i
+        _attn_self(None, p + ".attention", s)
+        _ffn(p + ".intermediate", p + ".output", inter, s)
+    p = "img_embeddings"
+    s[p + ".img_linear.weight"] = ((HID, cfg.image_feat_size), "w")
+    s[p + ".img_linear.bias"] = ((HID,), "b")
+    s[p + ".img_layer_norm.weight"] = ((HID,), "g")
+    s[p + ".img_layer_norm.bias"] = ((HID,), "b")
+    s[p + ".loc_linear.weight"] = ((HID, cfg.angle_feat_size + 3), "w")
+    s[p + ".loc_linear.bias"] = ((HID,), "b")
+    s[p + ".loc_layer_norm.weight"] = ((HID,), "g")
+    s[p + ".loc_layer_norm.bias"] = ((HID,), "b")
+    if cfg.obj_feat_size > 0 and cfg.obj_feat_size != cfg.image_feat_size:
+        s[p + ".obj_linear.weight"] = ((HID, cfg.obj_feat_size), "w")
+        s[p + ".obj_linear.bias"] = ((HID,), "b")
+        s[p + ".obj_layer_norm.weight"] = ((HID,), "g")
+        s[p + ".obj_layer_norm.bias"] = ((HID,), "b")
+    s[p + ".nav_type_embedding.weight"] = ((3, HID), "w")
+    s[p + ".layer_norm.weight"] = ((HID,), "g")
+    s[p + ".layer_norm.bias"] = ((HID,), "b")
+    if cfg.num_pano_layers > 0:
+        _prenorm(p + ".pano_encoder", cfg.num_pano_layers, inter, s)
+    _lin_ln("local_encoder.vp_pos_embeddings", cfg.angle_feat_size * 2 + 6, s)
+    for i in range(cfg.num_x_layers):
+        _lxrt("local_encoder.encoder.x_layers.%d" % i, inter, s)
+    _lin_ln("global_encoder.gmap_pos_embeddings", cfg.angle_feat_size + 3, s)
+    s["global_encoder.gmap_step_embeddings.weight"] = ((cfg.max_action_steps, HID), "w")
+    if cfg.graph_sprels:
+        s["global_encoder.sprel_linear.weight"] = ((1, 1), "w")
+        s["global_encoder.sprel_linear.bias"] = ((1,), "b")
+    _cls("global_sap_head", HID, s)
+    _cls("local_sap_head", HID, s)
+    _cls("grid_sap_head", HID, s)
+    _prenorm("grid_encoder", 1, inter, s)
+    _lxrt("grid_txt_encoder.x_layers.0", inter, s)
+    _lin_ln("grid_pos_embeddings", 5, s)
+    s["text_proj.weight"] = ((HID, HID), "w"); s["text_proj.bias"] = ((HID,), "b")
+    s["grid_proj.weight"] = ((HID, HID), "w"); s["grid_proj.bias"] = ((HID,), "b")
+    if cfg.glocal_fuse:
+        _cls("sap_fuse_linear", 2 * HID, s)
+    if cfg.obj_feat_size > 0:
+        _cls("og_head", HID, s)
+    return s
+
+
+def remap_pretrained_keys(state_dict):
+    """Key remap applied when a pretraining checkpoint initialises fine-tuning (models/vlnbert_init.py:19-27):
+    strip `module.`, and `bert.` prefixes; pretrain heads `next_action`/`sap_fuse` live under `bert.` there."""
+    out = {}
+    for k, v in state_dict.items():
+        if k.startswith("module."):
+            k = k[7:]
+        if k.startswith("bert."):
+            k = k[5:]
+        out[k] = v
+    return out
+
+
+def build_fuse_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, G, V):
+    """Integer form of the vpid loops of vilmodel.py:884-899.
+
+    fuse_src[i,j]: >=0 -> fused[i,j] += local[i, src];  -2 -> += sum of local logits of already-visited candidates;
+    -1 -> unchanged.  bw_mask[i,v] marks those visited candidates.  (j = 0, the [stop] slot, is handled by the kernel.)
+    """
+    B = len(gmap_vpids)
+    fuse_src = np.full((B, G), -1, dtype=np.int32)
+    bw_mask = np.zeros((B, V), dtype=np.uint8)
+    vis = gmap_visited_masks
+    if isinstance(vis, torch.Tensor):
+        vis = vis.cpu().numpy()
+    for i in range(B):
+        vp_i = gmap_vpids[i]
+        visited = set(vp for vp, m in zip(vp_i, vis[i]) if m)
+        tmp = {}
+        for j, cand in enumerate(vp_cand_vpids[i]):
+            if j > 0:
+                if cand in visited:
+                    bw_mask[i, j] = 1
+                else:
+                    tmp[cand] = j
+        for j, vp in enumerate(vp_i):
+            if j > 0 and vp not in visited:
+                fuse_src[i, j] = tmp.get(vp, -2)
+    return fuse_src, bw_mask
+
+
+class _Holder(nn.Module):
+    """Empty module: a node of the parameter tree."""
+
+
+class GlocalTextPathNavCMT(nn.Module):
+    def __init__(self, config=None, **kw):
+        super().__init__()
+        self.config = config if config is not None else NavConfig(**kw)
+        self._spec = param_spec(self.config)
+        for name, (shape, kind) in self._spec.items():
+            if kind == "w":
+                t = torch.empty(shape).normal_(0.0, 0.02)     # BertPreTrainedModel.init_weights
+            elif kind == "g":
+                t = torch.ones(shape)
+            else:
+                t = torch.zeros(shape)
+            self._register(name, nn.Parameter(t))
+        self._w16 = {}
+        self._w16_versions = None
+        self._ws = {}
+
+    def _register(self, dotted, param):
+        mod = self
+        parts = dotted.split(".")
+        for p in parts[:-1]:
+            if not hasattr(mod, p):
+                mod.add_module(p, _Holder())
+            mod = getattr(mod, p)
+        mod.register_parameter(parts[-1], param)
+
+    # ------------------------------------------------------------------ weight plumbing
+    def P(self, name):
+        mod = self
+        for p in name.split("."):
+            mod = getattr(mod, p)
+        return mod
+
+    def _refresh_w16(self):
+        vers = tuple(p._version for p in self.parameters())
+        dev = next(self.parameters()).device
+        if self._w16_versions == (vers, dev):
+            return
+        self._w16 = {}
+        self._w16_versions = (vers, dev)
+
+    def W16(self, *names):
+        """fp16 copy of a weight, or of several weights concatenated along the output dimension (fused QKV etc.)."""
+        key = names
+        w = self._w16.get(key)
+        if w is None:
+            with torch.no_grad():
+                parts = [self.P(n).detach() for n in names]
+                w = (parts[0] if len(parts) == 1 else torch.cat(parts, 0)).to(torch.float16).contiguous()
+            self._w16[key] = w
+        return w
+
+    def B32(self, *names):
+        key = ("bias",) + names
+        b = self._w16.get(key)
+        if b is None:
+            with torch.no_grad():
+                parts = [self.P(n).detach().float() for n in names]
+                b = (parts[0] if len(parts) == 1 else torch.cat(parts, 0)).contiguous()
+            self._w16[key] = b
+        return b
+
+    def buf(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            dev = next(self.parameters()).device
+            t = torch.zeros(shape, dtype=dtype, device=dev) if zero else torch.empty(shape, dtype=dtype, device=dev)
+            self._ws[key] = t
+        return t
+
+    # ------------------------------------------------------------------ encoder blocks
+    def _attention(self, q, k, v, kmask, neg, B, Sq, Sk, name):
+        out = self.buf(name, (B * Sq, HID), torch.float16)
+        ops.attention(q, k, v, out, kmask, neg, B, HEADS, Sq, Sk)
+        return out
+
+    def _ln(self, x32, pre, eps, out32, out16):
+        ops.layernorm(x32, self.P(pre + ".weight"), self.P(pre + ".bias"), eps, out_f32=out32, out_f16=out16)
+
+    def _ffn_post(self, x32, x16, pre_i, pre_o, rows, tag):
+        """BertIntermediate + BertOutput (vilmodel.py:184-209): x = LN(W2 gelu(W1 x) + x)."""
+        h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16)
+        ops.linear(x16, self.W16(pre_i + ".dense.weight"), self.B32(pre_i + ".dense.bias"), out_f16=h, act=ops.ACT_GELU)
+        ops.linear(h, self.W16(pre_o + ".dense.weight"), self.B32(pre_o + ".dense.bias"), residual=x32, out_f32=x32)
+        self._ln(x32, pre_o + ".LayerNorm", 1e-12, x32, x16)
+
+    def _self_post(self, x32, x16, pre, kmask, B, S, tag):
+        """BertAttention (vilmodel.py:172-182): x = LN(Wo attn(x) + x), additive -10000 mask."""
+        qkv = self.buf("qkv16_" + tag, (B * S, 3 * HID), torch.float16)
+        ops.linear(x16, self.W16(pre + ".self.query.weight", pre + ".self.key.weight", pre + ".self.value.weight"),
+                   self.B32(pre + ".self.query.bias", pre + ".self.key.bias", pre + ".self.value.bias"), out_f16=qkv)
+        a = self._attention(qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:], kmask, NEG_BERT, B, S, S, "att16_" + tag)
+        ops.linear(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), residual=x32, out_f32=x32)
+        self._ln(x32, pre + ".output.LayerNorm", 1e-12, x32, x16)
+
+    def _cross_post(self, x32, x16, pre, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag):
+        """BertXAttention (vilmodel.py:317-379): x = LN(Wo attn(q = x, kv = ctx) + x)."""
+        q = self.buf("q16_" + tag, (B * S, HID), torch.float16)
+        ops.linear(x16, self.W16(pre + ".att.query.weight"), self.B32(pre + ".att.query.bias"), out_f16=q)
+        a = self._attention(q, ctx_k, ctx_v, ctx_mask, NEG_BERT, B, S, Sk, "att16_" + tag)
+        ops.linear(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), residual=x32, out_f32=x32)
+        self._ln(x32, pre + ".output.LayerNorm", 1e-12, x32, x16)
+
+    def _lxrt_layer(self, pre, x32, x16, x_mask, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag):
+        """GraphLXRTXLayer.forward (vilmodel.py:399-414): cross-attention, self-attention, FFN (all post-norm)."""
+        self._cross_post(x32, x16, pre + ".visual_attention", ctx_k, ctx_v, ctx_mask, B, S, Sk, tag)
+        self._self_post(x32, x16, pre + ".visn_self_att", x_mask, B, S, tag)
+        self._ffn_post(x32, x16, pre + ".visn_inter", pre + ".visn_output", B * S, tag)
+
+    def _prenorm_encoder(self, pre, n_layers, x32, x16, kmask, B, S, tag):
+        """TransformerEncoder of forward_pre layers + final norm (models/transformer.py:60-87, 170-182)."""
+        rows = B * S
+        for i in range(n_layers):
+            q = "%s.layers.%d" % (pre, i)
+            self._ln(x32, q + ".norm1", 1e-5, None, x16)
+            qkv = self.buf("qkv16_" + tag, (rows, 3 * HID), torch.float16)
+            ops.linear(x16, self.W16(q + ".self_attn.in_proj_weight"), self.B32(q + ".self_attn.in_proj_bias"), out_f16=qkv)
+            a = self._attention(qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:], kmask, NEG_INF, B, S, S, "att16_" + tag)
+            ops.linear(a, self.W16(q + ".self_attn.out_proj.weight"), self.B32(q + ".self_attn.out_proj.bias"),
+                       residual=x32, out_f32=x32)
+            self._ln(x32, q + ".norm2", 1e-5, None, x16)
+            h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16)
+            ops.linear(x16, self.W16(q + ".linear1.weight"), self.B32(q + ".linear1.bias"), out_f16=h, act=ops.ACT_GELU)
+            ops.linear(h, self.W16(q + ".linear2.weight"), self.B32(q + ".linear2.bias"), residual=x32, out_f32=x32)
+        self._ln(x32, pre + ".norm", 1e-12, x32, x16)
+
+    def _cls_head(self, pre, x16, rows, tag):
+        """ClsPrediction (vilmodel.py:663-674) -> raw logit per row."""
+        h = self.buf("cls32_" + tag, (rows, HID), torch.float32)
+        ops.linear(x16, self.W16(pre + ".net.0.weight"), self.B32(pre + ".net.0.bias"), out_f32=h, act=ops.ACT_RELU)
+        out = self.buf("cls_out_" + tag, (rows,), torch.float32)
+        ops.cls_tail(h, self.P(pre + ".net.2.weight"), self.P(pre + ".net.2.bias"), self.P(pre + ".net.3.weight"),
+                     self.P(pre + ".net.3.bias"), out)
+        return out
+
+    # ------------------------------------------------------------------ grid inputs
+    def _grid_from_reference_lists(self, grid_fts, grid_map, gridmap_pos_fts):
+        """Drop-in path: the reference's per-episode lists (r2r/agent.py:163-169) -> the device layout of GridBatch.
+        Copies the whole accumulated map (as the reference's `.cuda()` does every step)."""
+        B = len(grid_fts)
+        dev = next(self.parameters()).device
+        n = [int(x.shape[0]) for x in grid_fts]
+        if any(v % 588 for v in n):
+            raise ValueError("grid_fts rows must be a multiple of 588 (12 views x 49 patches, r2r/env.py:299)")
+        t_cap = max(max(n) // 588, 1)
+        cap = t_cap * 588
+        D = int(grid_fts[0].shape[1])
+        slab = self.buf("compat_slab", (B * t_cap * 588, D), torch.float16)
+        cell = self.buf("compat_cell", (B, cap), torch.int16)
+        cell.fill_(-1)
+        for b in range(B):
+            slab[b * cap: b * cap + n[b]].copy_(torch.as_tensor(grid_fts[b]).to(dev, torch.float16), non_blocking=True)
+            cell[b, :n[b]].copy_(torch.as_tensor(grid_map[b]).to(dev).to(torch.int16), non_blocking=True)
+        n_pts = torch.tensor(n, dtype=torch.int32).to(dev)
+        slots = (torch.arange(B, dtype=torch.int32)[:, None] * t_cap + torch.arange(t_cap, dtype=torch.int32)[None, :])
+        nc = self.config.grid_w ** 2
+        gb = GridBatch.__new__(GridBatch)
+        gb.batch, gb.feat_dim, gb.grid_w, gb.n_cells = B, D, self.config.grid_w, nc
+        gb.slab, gb.slots, gb.t_cap = slab, slots.contiguous().to(dev), t_cap
+        gb.slot_rows, gb.view_rows, gb.tok_off = 588, 49, 0
+        gb.cap = cap
+        gb.perm = self.buf("compat_perm", (B, cap), torch.int32)
+        gb.cell_start = self.buf("compat_cs", (B, nc + 1), torch.int32)
+        gb.cell_rank = self.buf("compat_cr", (B, nc), torch.int32)
+        gb.n_nonempty = self.buf("compat_ne", (B,), torch.int32)
+        gb.cell, gb.n_pts = cell, n_pts
+        gb.pos_fts = torch.as_tensor(gridmap_pos_fts).to(dev, torch.float32).contiguous()
+        ops.cell_sort(B, cell, n_pts, self.config.grid_w, cap, gb.perm, gb.cell_start, gb.cell_rank, gb.n_nonempty)
+        return gb
+
+    # ------------------------------------------------------------------ navigation
+    @torch.no_grad()
+    def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
+                                    gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
+                                    vp_nav_masks, vp_obj_masks, vp_cand_vpids, grid_fts, grid_map, gridmap_pos_fts,
+                                    grid=None, return_intermediates=False):
+        """vilmodel.py:782-918.  `grid` (a gridmm_b200.env.GridBatch) replaces grid_fts/grid_map/gridmap_pos_fts when the
+        grid was built on the device; otherwise the reference-format lists are uploaded and sorted first."""
+        self._refresh_w16()
+        cfg = self.config
+        if grid is None:
+            grid = self._grid_from_reference_lists(grid_fts, grid_map, gridmap_pos_fts)
+        B, L = txt_embeds.shape[0], txt_embeds.shape[1]
+        G, V = gmap_img_embeds.shape[1], vp_img_embeds.shape[1]
+        NC = grid.n_cells
+        S, Q, KC = NC + G, G + V, NC + G + L
+        f16, f32, u8 = torch.float16, torch.float32, torch.uint8
+        txt_embeds = txt_embeds.contiguous().float()
+        txt_mask_u8 = txt_masks.contiguous().view(u8) if txt_masks.dtype == torch.bool else txt_masks.to(u8)
+        gmap_mask_u8 = gmap_masks.contiguous().view(u8) if gmap_masks.dtype == torch.bool else gmap_masks.to(u8)
+        vp_mask_u8 = vp_masks.contiguous().view(u8) if vp_masks.dtype == torch.bool else vp_masks.to(u8)
+
+        # ---- text_proj + relevance pooling + grid_proj (vilmodel.py:793-807)
+        txt16 = self.buf("txt16", (B * L, HID), f16)
+        ops.copy_rows(txt_embeds.view(B * L, HID), L, 0, L, B, L, 0, out_f16=txt16)
+        l_pad = (L + 7) // 8 * 8
+        tp16 = self.buf("tp16", (B * l_pad, HID), f16)
+        if l_pad == L:
+            ops.linear(txt16, self.W16("text_proj.weight"), self.B32("text_proj.bias"), out_f16=tp16)
+        else:
+            tmp = self.buf("tp16_tmp", (B * L, HID), f16)
+            ops.linear(txt16, self.W16("text_proj.weight"), self.B32("text_proj.bias"), out_f16=tmp)
+            t3 = tp16.view(B, l_pad, HID)
+            t3[:, :L].copy_(tmp.view(B, L, HID))
+            t3[:, L:].copy_(tmp.view(B, L, HID)[:, :1].expand(B, l_pad - L, HID))   # duplicates never change the max
+        pooled16 = self.buf("pooled16", (B * NC, HID), f16, zero=True)
+        w_out = self.buf("w_out", (B, grid.cap), f32, zero=True) if return_intermediates else None
+        ops.pool(grid.slab, grid.feat_dim, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm,
+                 grid.cap, grid.cell_start, grid.cell_rank, NC, tp16, l_pad, B, pooled16, w_out=w_out)
+        proj32 = self.buf("proj32", (B * NC, HID), f32)
+        ops.linear(pooled16, self.W16("grid_proj.weight"), self.B32("grid_proj.bias"), out_f32=proj32)
+
+        # ---- map sequence = [grid cells ; gmap nodes]  (vilmodel.py:813-838)
+        map32 = self.buf("map32", (B * S, HID), f32)
+        map16 = self.buf("map16", (B * S, HID), f16)
+        map_mask = self.buf("map_mask", (B, S), u8)
+        ops.grid_assemble(proj32, grid.pos_fts, grid.cell_rank, grid.n_nonempty, self.P("grid_pos_embeddings.0.weight"),
+                          self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
+                          self.P("grid_pos_embeddings.1.bias"), map32, map_mask, B, NC, S)
+        map_mask[:, NC:].copy_(gmap_mask_u8)
+        ge = "global_encoder.gmap_pos_embeddings"
+        ops.pos_embed(gmap_pos_fts.contiguous().view(B * G, -1).float(), self.P(ge + ".0.weight"), self.P(ge + ".0.bias"),
+                      self.P(ge + ".1.weight"), self.P(ge + ".1.bias"), 1e-12, map32, None, G, S, NC,
+                      base=gmap_img_embeds.contiguous().view(B * G, HID).float(),
+                      table=self.P("global_encoder.gmap_step_embeddings.weight"), idx=gmap_step_ids.contiguous().view(-1))
+        x32 = torch.empty(B * Q, HID, dtype=f32, device=map32.device)     # escapes as gmap_embeds / vp_embeds
+        x16 = self.buf("x16", (B * Q, HID), f16)
+        ve = "local_encoder.vp_pos_embeddings"
+        ops.pos_embed(vp_pos_fts.contiguous().view(B * V, -1).float(), self.P(ve + ".0.weight"), self.P(ve + ".0.bias"),
+                      self.P(ve + ".1.weight"), self.P(ve + ".1.bias"), 1e-12, x32, x16, V, Q, G,
+                      base=vp_img_embeds.contiguous().view(B * V, HID).float())
+
+        # ---- grid_encoder (pre-norm, key_padding_mask) and grid_txt_encoder (vilmodel.py:840-841)
+        self._prenorm_encoder("grid_encoder", 1, map32, map16, map_mask, B, S, "map")
+        gt = "grid_txt_encoder.x_layers.0"
+        kv_txt = self.buf("kv_txt16", (B * L, 2 * HID), f16)
+        ops.linear(txt16, self.W16(gt + ".visual_attention.att.key.weight", gt + ".visual_attention.att.value.weight"),
+                   self.B32(gt + ".visual_attention.att.key.bias", gt + ".visual_attention.att.value.bias"), out_f16=kv_txt)
+        self._lxrt_layer(gt, map32, map16, map_mask, kv_txt[:, :HID], kv_txt[:, HID:], txt_mask_u8, B, S, L, "map")
+        inter = {}
+        if return_intermediates:
+            inter["map_embeds"] = map32.view(B, S, HID).clone()
+            inter["map_masks"] = map_mask.clone()
+
+        # ---- fusion encoder: queries [gmap'; vp], context [map; txt]  (vilmodel.py:843-856)
+        ops.copy_rows(map32, S, NC, G, B, Q, 0, out_f32=x32, out_f16=x16)
+        kv16 = self.buf("kv16", (B * KC, HID), f16)
+        ops.copy_rows(map32, S, 0, S, B, KC, 0, out_f16=kv16)
+        ops.copy_rows(txt_embeds.view(B * L, HID), L, 0, L, B, KC, S, out_f16=kv16)
+        kv_mask = self.buf("kv_mask", (B, KC), u8)
+        kv_mask[:, :S].copy_(map_mask)
+        kv_mask[:, S:].copy_(txt_mask_u8)
+        q_mask = self.buf("q_mask", (B, Q), u8)
+        q_mask[:, :G].copy_(gmap_mask_u8)
+        q_mask[:, G:].copy_(vp_mask_u8)
+        nx = cfg.num_x_layers
+        le = "local_encoder.encoder.x_layers.%d"
+        names_w, names_b = [], []
+        for i in range(nx):
+            names_w += [(le % i) + ".visual_attention.att.key.weight", (le % i) + ".visual_attention.att.value.weight"]
+            names_b += [(le % i) + ".visual_attention.att.key.bias", (le % i) + ".visual_attention.att.value.bias"]
+        kvp = self.buf("kvp16", (B * KC, 2 * HID * nx), f16)
+        ops.linear(kv16, self.W16(*names_w), self.B32(*names_b), out_f16=kvp)
+        for i in range(nx):
+            self._lxrt_layer(le % i, x32, x16, q_mask, kvp[:, 2 * HID * i: 2 * HID * i + HID],
+                             kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], kv_mask, B, Q, KC, "x")
+
+        # ---- heads and logit fusion (vilmodel.py:859-907)
+        hg16 = self.buf("hg16", (B * G, HID), f16)
+        hv16 = self.buf("hv16", (B * V, HID), f16)
+        hm16 = self.buf("hm16", (B * G, HID), f16)
+        ops.copy_rows(x32, Q, 0, G, B, G, 0, out_f16=hg16)
+        ops.copy_rows(x32, Q, G, V, B, V, 0, out_f16=hv16)
+        ops.copy_rows(map32, S, NC, G, B, G, 0, out_f16=hm16)
+        raw_global = self._cls_head("global_sap_head", hg16, B * G, "g")
+        raw_local = self._cls_head("local_sap_head", hv16, B * V, "l")
+        raw_grid = self._cls_head("grid_sap_head", hm16, B * G, "m")
+        raw_fuse = None
+        if cfg.glocal_fuse:
+            hf16 = self.buf("hf16", (B, 2 * HID), f16)
+            ops.copy_rows(x32, Q, 0, 1, B, 1, 0, out_f16=hf16)
+            ops.copy_rows(x32, Q, G, 1, B, 1, 0, out_f16=hf16[:, HID:])
+            raw_fuse = self._cls_head("sap_fuse_linear", hf16, B, "f")
+        has_obj = vp_obj_masks is not None
+        raw_obj = self._cls_head("og_head", hv16, B * V, "o") if has_obj else None
+        fuse_src, bw_mask = build_fuse_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, G, V)
+        dev = map32.device
+        fuse_src_d = torch.from_numpy(fuse_src).to(dev, non_blocking=True)
+        bw_mask_d = torch.from_numpy(bw_mask).to(dev, non_blocking=True)
+        vis_u8 = gmap_visited_masks.contiguous().view(u8) if gmap_visited_masks.dtype == torch.bool else gmap_visited_masks.to(u8)
+        nav_u8 = vp_nav_masks.contiguous().view(u8) if vp_nav_masks.dtype == torch.bool else vp_nav_masks.to(u8)
+        obj_u8 = None
+        if has_obj:
+            obj_u8 = vp_obj_masks.contiguous().view(u8) if vp_obj_masks.dtype == torch.bool else vp_obj_masks.to(u8)
+        global_logits = torch.empty(B, G, dtype=f32, device=dev)
+        grid_logits = torch.empty(B, G, dtype=f32, device=dev)
+        local_logits = torch.empty(B, V, dtype=f32, device=dev)
+        fused_logits = torch.empty(B, G, dtype=f32, device=dev)
+        obj_logits = torch.empty(B, V, dtype=f32, device=dev) if has_obj else None
+        ops.nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_mask_u8, vis_u8, nav_u8, obj_u8, fuse_src_d,
+                       bw_mask_d, global_logits, grid_logits, local_logits, fused_logits, obj_logits, B, G, V)
+        x3 = x32.view(B, Q, HID)
+        outs = {
+            "gmap_embeds": x3[:, :G], "vp_embeds": x3[:, G:],
+            "global_logits": global_logits, "local_logits": local_logits, "fused_logits": fused_logits,
+            "obj_logits": obj_logits, "grid_logits": grid_logits,
+        }
+        if return_intermediates:
+            inter["pooled"] = pooled16.view(B, NC, HID).clone()
+            inter["grid_proj"] = proj32.view(B, NC, HID).clone()
+            inter["w_sorted"] = w_out.clone()
+            outs.update(inter)
+        return outs
+
+    def forward(self, mode, batch, **kwargs):
+        """vilmodel.py:920-939."""
+        if mode == "navigation":
+            g = batch.get("grid") if hasattr(batch, "get") else None
+            return self.forward_navigation_per_step(
+                batch["txt_embeds"], batch["txt_masks"], batch["gmap_img_embeds"], batch["gmap_step_ids"],
+                batch["gmap_pos_fts"], batch["gmap_masks"], batch["gmap_pair_dists"], batch["gmap_visited_masks"],
+                batch["gmap_vpids"], batch["vp_img_embeds"], batch["vp_pos_fts"], batch["vp_masks"], batch["vp_nav_masks"],
+                batch["vp_obj_masks"], batch["vp_cand_vpids"], batch["grid_fts"], batch["grid_map"],
+                batch["gridmap_pos_fts"], grid=g, **kwargs)
+        if mode in ("language", "panorama"):
+            raise NotImplementedError(
+                "mode %r (vilmodel.py:730-780) is outside the accelerated hot path in this round (SURVEY 8f rank 1/3)" % mode)
+        raise NotImplementedError("wrong mode: %s" % mode)
+
+
+class VLNBert(nn.Module):
+    """map_nav_src/models/model.py:12-40 -- the object the agents hold (`self.vln_bert`)."""
+
+    def __init__(self, args=None, config=None):
+        super().__init__()
+        if config is None:
+            kw = {}
+            if args is not None:
+                for a, c in (("image_feat_size", "image_feat_size"), ("angle_feat_size", "angle_feat_size"),
+                             ("obj_feat_size", "obj_feat_size"), ("num_l_layers", "num_l_layers"),
+                             ("num_pano_layers", "num_pano_layers"), ("num_x_layers", "num_x_layers"),
+                             ("graph_sprels", "graph_sprels"), ("max_action_len", None)):
+                    if c and hasattr(args, a):
+                        kw[c] = getattr(args, a)
+                if hasattr(args, "fusion"):
+                    kw["glocal_fuse"] = args.fusion == "dynamic"
+            config = NavConfig(**kw)
+        self.args = args
+        self.vln_bert = GlocalTextPathNavCMT(config)
+
+    def forward(self, mode, batch):
+        batch = collections.defaultdict(lambda: None, batch)
+        if mode in ("language", "panorama", "navigation"):
+            return self.vln_bert(mode, batch)
+        raise NotImplementedError("wrong mode: %s" % mode)

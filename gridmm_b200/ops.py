@@ -1,0 +1,129 @@
+"""Tensor-level wrappers over the C ABI (include/gridmm_b200.h).  torch is used only for device memory and
+streams; every function here launches hand-written sm_100a kernels and raises if that is impossible."""
+import math
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+HID = 768
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.GridmmError("%s must be a CUDA tensor (gridmm_b200 has no CPU path)" % name)
+    if t.dtype != dtype:
+        raise _lib.GridmmError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.stride(-1) != 1:
+        raise _lib.GridmmError("%s must be contiguous in its last dimension" % name)
+
+
+def linear(a16, w16, bias=None, residual=None, out_f32=None, out_f16=None, act=ACT_NONE):
+    """act(a16 @ w16.T + bias) + residual.  a16 [M,K] fp16 (row pitch = stride(0)), w16 [N,K] fp16."""
+    _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w")
+    _chk(bias, torch.float32, "bias"); _chk(residual, torch.float32, "residual")
+    _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
+    M, K = a16.shape
+    N = w16.shape[0]
+    assert w16.shape[1] == K
+    _lib.call("gridmm_linear_f16", a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, N, K,
+              _lib.ptr(bias), _lib.ptr(residual), residual.stride(0) if residual is not None else 0,
+              _lib.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, act, _lib.stream_ptr())
+
+
+def attention(q, k, v, out, kmask, mask_neg, batch, heads, sq, sk, q_rows=None, k_rows=None):
+    """q [batch*q_rows, >=heads*64] fp16 views (column offset folded into the view), likewise k, v; out fp16."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t, torch.float16, n)
+    _chk(kmask, torch.uint8, "kmask")
+    _lib.call("gridmm_attention_f16", q.data_ptr(), q.stride(0), q_rows or sq, k.data_ptr(), k.stride(0), v.data_ptr(),
+              v.stride(0), k_rows or sk, out.data_ptr(), out.stride(0), kmask.data_ptr(), float(mask_neg), batch, heads, sq,
+              sk, 1.0 / math.sqrt(64.0), _lib.stream_ptr())
+
+
+def layernorm(x, gamma, beta, eps, out_f32=None, out_f16=None):
+    _chk(x, torch.float32, "x"); _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
+    rows = x.shape[0]
+    _lib.call("gridmm_layernorm", x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), float(eps),
+              _lib.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, rows, x.shape[1], _lib.stream_ptr())
+
+
+def copy_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_rows_per_b, out_off, out_f32=None, out_f16=None):
+    """out[b, out_off + r] = x[b, in_off + r] for r < rows_per_b; x fp32 [batch*in_rows_per_b, 768]."""
+    _chk(x, torch.float32, "x"); _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
+    _lib.call("gridmm_copy_rows", x.data_ptr(), x.stride(0), in_rows_per_b, in_off,
+              _lib.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0,
+              out_rows_per_b, out_off, rows_per_b, batch, x.shape[1], _lib.stream_ptr())
+
+
+def pos_embed(feat, w, bias, gamma, beta, eps, out_f32, out_f16, in_rows_per_b, out_rows_per_b, out_row_off,
+              base=None, table=None, idx=None):
+    _chk(feat, torch.float32, "feat"); _chk(base, torch.float32, "base"); _chk(table, torch.float32, "table")
+    _chk(idx, torch.int64, "idx"); _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
+    rows, kin = feat.shape
+    if base is not None:
+        assert base.is_contiguous()
+    assert feat.is_contiguous() and w.is_contiguous()
+    _lib.call("gridmm_pos_embed", feat.data_ptr(), kin, w.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+              float(eps), _lib.ptr(base), _lib.ptr(table), _lib.ptr(idx), _lib.ptr(out_f32), _lib.ptr(out_f16),
+              in_rows_per_b, out_rows_per_b, out_row_off, rows, HID, _lib.stream_ptr())
+
+
+def grid_assemble(proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq):
+    _chk(proj, torch.float32, "proj"); _chk(pos_fts, torch.float32, "pos_fts"); _chk(cell_rank, torch.int32, "cell_rank")
+    _chk(n_nonempty, torch.int32, "n_nonempty"); _chk(map_f32, torch.float32, "map_f32"); _chk(map_mask, torch.uint8, "map_mask")
+    _lib.call("gridmm_grid_assemble", proj.data_ptr(), pos_fts.data_ptr(), cell_rank.data_ptr(), n_nonempty.data_ptr(),
+              w.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), map_f32.data_ptr(), map_mask.data_ptr(),
+              batch, n_cells, seq, HID, _lib.stream_ptr())
+
+
+def cls_tail(h, gamma, beta, w2, b2, logit):
+    _chk(h, torch.float32, "h"); _chk(logit, torch.float32, "logit")
+    assert h.is_contiguous()
+    _lib.call("gridmm_cls_tail", h.data_ptr(), gamma.data_ptr(), beta.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+              logit.data_ptr(), h.shape[0], h.shape[1], _lib.stream_ptr())
+
+
+def nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_masks, gmap_visited, vp_nav_masks, vp_obj_masks,
+               fuse_src, bw_mask, global_logits, grid_logits, local_logits, fused_logits, obj_logits, batch, G, V):
+    for t, n in ((gmap_masks, "gmap_masks"), (gmap_visited, "gmap_visited"), (vp_nav_masks, "vp_nav_masks"),
+                 (vp_obj_masks, "vp_obj_masks"), (bw_mask, "bw_mask")):
+        _chk(t, torch.uint8, n)
+    _chk(fuse_src, torch.int32, "fuse_src")
+    _lib.call("gridmm_nav_logits", raw_global.data_ptr(), raw_grid.data_ptr(), raw_local.data_ptr(), _lib.ptr(raw_obj),
+              _lib.ptr(raw_fuse), gmap_masks.data_ptr(), gmap_visited.data_ptr(), vp_nav_masks.data_ptr(),
+              _lib.ptr(vp_obj_masks), fuse_src.data_ptr(), bw_mask.data_ptr(), global_logits.data_ptr(),
+              grid_logits.data_ptr(), local_logits.data_ptr(), fused_logits.data_ptr(), _lib.ptr(obj_logits), batch, G, V,
+              _lib.stream_ptr())
+
+
+def grid_update(batch, depth, depth_is_f32, depth_scale, pose, view_cs, active, off7_host, flip_y, negate_map_x, grid_w, cap,
+                wx, wy, valid, bounds, n_pts, cell, half_len, perm, cell_start, cell_rank, n_nonempty, pos_fts):
+    import ctypes
+    off = (ctypes.c_float * 7)(*[float(x) for x in off7_host])
+    _lib.call("gridmm_grid_update", batch, depth.data_ptr(), int(depth_is_f32), float(depth_scale), pose.data_ptr(),
+              view_cs.data_ptr(), _lib.ptr(active), ctypes.cast(off, ctypes.c_void_p), int(flip_y), int(negate_map_x), grid_w,
+              cap, wx.data_ptr(), wy.data_ptr(), valid.data_ptr(), bounds.data_ptr(), n_pts.data_ptr(), cell.data_ptr(),
+              half_len.data_ptr(), perm.data_ptr(), cell_start.data_ptr(), cell_rank.data_ptr(), n_nonempty.data_ptr(),
+              pos_fts.data_ptr(), _lib.stream_ptr())
+
+
+def pool(fts, feat_dim, slots, t_cap, slot_rows, view_rows, tok_off, perm, cap, cell_start, cell_rank, n_cells, text_fts, l_pad,
+         batch, pooled, w_out=None, num_ctas=0):
+    _chk(fts, torch.float16, "fts"); _chk(text_fts, torch.float16, "text_fts"); _chk(pooled, torch.float16, "pooled")
+    _chk(slots, torch.int32, "slots"); _chk(perm, torch.int32, "perm")
+    _lib.call("gridmm_pool", fts.data_ptr(), feat_dim, slots.data_ptr(), t_cap, slot_rows, view_rows, tok_off, perm.data_ptr(),
+              cap, cell_start.data_ptr(), cell_rank.data_ptr(), n_cells, text_fts.data_ptr(), l_pad, batch, pooled.data_ptr(),
+              _lib.ptr(w_out), num_ctas, _lib.stream_ptr())
+
+
+def cell_sort(batch, cell, n_pts, grid_w, cap, perm, cell_start, cell_rank, n_nonempty):
+    _chk(cell, torch.int16, "cell"); _chk(n_pts, torch.int32, "n_pts")
+    _lib.call("gridmm_cell_sort", batch, cell.data_ptr(), n_pts.data_ptr(), grid_w, cap, perm.data_ptr(), cell_start.data_ptr(),
+              cell_rank.data_ptr(), n_nonempty.data_ptr(), _lib.stream_ptr())

@@ -1,0 +1,154 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json names.
+
+There is no Matterport data and no checkpoint in this environment, so every
+test and the bench run on these.  The same generator feeds the reference (in the
+authoring container, to produce tests/golden/*), the oracle and the CUDA path,
+so all three see bit-identical inputs.
+
+Shapes follow the reference's on-disk formats:
+  depth     uint16[36,128,128], 0.25 mm units, 0 = invalid
+            (map_nav_src/r2r/env.py:80-95, 278-285) -- only views 12..23 and the
+            7x7 patch-centre pixels 9+18*i are read, so the generator draws the
+            sub-sampled uint16[12,49] and `expand_depth` scatters it into a full map.
+  clip      float16[12,50,768] CLIP ViT patch tokens, token 0 = CLS
+            (map_nav_src/r2r/env.py:98-113, 296-304)
+  pose      viewpoint x,y (python floats, viewpoint_info.json) and heading (rad).
+"""
+import math
+
+import numpy as np
+
+N_VIEWS = 12            # horizon views 12..23 of the 36 (env.py:289)
+N_PATCH = 49            # 7x7 patch centres per view (env.py:279-281)
+PTS_PER_VP = N_VIEWS * N_PATCH   # 588
+PATCH_CENTRES = np.array([9 + 18 * i for i in range(7)])
+
+
+def make_episodes(batch, steps, seed=0, dim=768, zero_frac=0.10):
+    """Per-episode, per-step viewpoint observations.
+
+    Returns a dict of numpy arrays:
+      depth_sub u16[B,T,12,49]   clip f16[B,T,12,50,dim]
+      pos f64[B,T,2]             heading f64[B,T]
+    """
+    rng = np.random.default_rng(seed)
+    depth = rng.integers(2000, 20001, size=(batch, steps, N_VIEWS, N_PATCH)).astype(np.uint16)
+    depth[rng.random(depth.shape) < zero_frac] = 0
+    clip = rng.standard_normal((batch, steps, N_VIEWS, N_PATCH + 1, dim), dtype=np.float32).astype(np.float16)
+    step_xy = rng.uniform(1.0, 3.0, size=(batch, steps, 2)) * rng.choice([-1.0, 1.0], size=(batch, steps, 2))
+    start = rng.uniform(-10.0, 10.0, size=(batch, 1, 2))
+    pos = start + np.cumsum(step_xy, axis=1)
+    heading = rng.uniform(0.0, 2.0 * math.pi, size=(batch, steps))
+    return {"depth_sub": depth, "clip": clip, "pos": pos, "heading": heading}
+
+
+def expand_depth(depth_sub):
+    """uint16[12,49] -> the reference's uint16[36,128,128] map (zeros elsewhere)."""
+    full = np.zeros((36, 128, 128), dtype=np.uint16)
+    sub = depth_sub.reshape(N_VIEWS, 7, 7)
+    full[12:24][:, PATCH_CENTRES[:, None], PATCH_CENTRES[None, :]] = sub
+    return full
+
+
+def make_nav_inputs(batch, seed=0, txt_len=80, gmap_len=20, n_views=36, n_objs=0,
+                    dim=768, min_txt=20, ragged=True):
+    """Everything `forward('navigation')` needs except the grid tensors
+    (map_nav_src/r2r/agent.py:96-205, map_nav_src/models/vilmodel.py:782-786).
+
+    Returns a dict of numpy arrays / python lists (reference batch keys).
+    """
+    rng = np.random.default_rng(seed + 7919)
+    B, L, G = batch, txt_len, gmap_len
+    V = 1 + n_views + n_objs
+    f32 = np.float32
+    txt_embeds = rng.standard_normal((B, L, dim), dtype=f32)
+    txt_lens = rng.integers(min_txt, L + 1, size=B) if ragged else np.full(B, L)
+    txt_lens[0] = L
+    txt_masks = np.arange(L)[None, :] < txt_lens[:, None]
+
+    gmap_lens = rng.integers(max(4, G // 2), G + 1, size=B) if ragged else np.full(B, G)
+    gmap_lens[0] = G
+    gmap_masks = np.arange(G)[None, :] < gmap_lens[:, None]
+    gmap_img_embeds = rng.standard_normal((B, G, dim), dtype=f32)
+    gmap_img_embeds[:, 0] = 0.0                     # [stop] token (agent.py:129-131)
+    gmap_img_embeds *= gmap_masks[:, :, None]       # pad_tensors_wgrad zero padding
+    gmap_step_ids = rng.integers(0, 16, size=(B, G)).astype(np.int64) * gmap_masks
+    gmap_step_ids[:, 0] = 0
+    gmap_pos_fts = rng.standard_normal((B, G, 7), dtype=f32) * gmap_masks[:, :, None]
+    gmap_visited = np.zeros((B, G), dtype=bool)
+    gmap_vpids, vp_cand_vpids = [], []
+    n_cands = rng.integers(2, 6, size=B)
+    vp_lens = np.full(B, V)
+    if ragged and n_objs > 0:
+        vp_lens = 1 + n_views + rng.integers(0, n_objs + 1, size=B)
+        vp_lens[0] = V
+    vp_masks = np.arange(V)[None, :] < vp_lens[:, None]
+    vp_nav_masks = np.zeros((B, V), dtype=bool)
+    vp_nav_masks[:, 0] = True
+    vp_obj_masks = np.zeros((B, V), dtype=bool) if n_objs > 0 else None
+    for b in range(B):
+        g = int(gmap_lens[b])
+        n_vis = int(rng.integers(1, max(2, g // 2)))
+        gmap_visited[b, 1:1 + n_vis] = True       # enc_full_graph order: [stop]+visited+unvisited
+        ids = [None] + ["vp%d_%d" % (b, j) for j in range(1, g)] + [None] * (G - g)
+        gmap_vpids.append(ids[:g])
+        nc = int(n_cands[b])
+        vp_nav_masks[b, 1:1 + nc] = True
+        # candidates: a mix of unvisited gmap nodes, visited nodes and (rarely) nodes absent from gmap
+        pool_unvis = ids[1 + n_vis:g]
+        pool_vis = ids[1:1 + n_vis]
+        cands = []
+        for j in range(nc):
+            r = rng.random()
+            if r < 0.6 and len(pool_unvis) > 0:
+                cands.append(pool_unvis[int(rng.integers(len(pool_unvis)))])
+            elif len(pool_vis) > 0:
+                cands.append(pool_vis[int(rng.integers(len(pool_vis)))])
+            else:
+                cands.append("ghost%d_%d" % (b, j))
+        vp_cand_vpids.append([None] + cands)
+        if vp_obj_masks is not None:
+            vp_obj_masks[b, 1 + n_views:int(vp_lens[b])] = True
+    vp_img_embeds = rng.standard_normal((B, V, dim), dtype=f32)
+    vp_img_embeds[:, 0] = 0.0                       # [stop] (agent.py:176-178)
+    vp_img_embeds *= vp_masks[:, :, None]
+    vp_pos_fts = rng.standard_normal((B, V, 14), dtype=f32) * vp_masks[:, :, None]
+    return {
+        "txt_embeds": txt_embeds, "txt_masks": txt_masks,
+        "gmap_img_embeds": gmap_img_embeds, "gmap_step_ids": gmap_step_ids,
+        "gmap_pos_fts": gmap_pos_fts, "gmap_masks": gmap_masks,
+        "gmap_pair_dists": np.zeros((B, G, G), dtype=f32),
+        "gmap_visited_masks": gmap_visited, "gmap_vpids": gmap_vpids,
+        "vp_img_embeds": vp_img_embeds, "vp_pos_fts": vp_pos_fts, "vp_masks": vp_masks,
+        "vp_nav_masks": vp_nav_masks, "vp_obj_masks": vp_obj_masks,
+        "vp_cand_vpids": vp_cand_vpids,
+    }
+
+
+def to_torch(nav, device="cpu"):
+    """numpy nav-input dict -> torch tensors with the reference's dtypes."""
+    import torch
+    out = {}
+    for k, v in nav.items():
+        if isinstance(v, np.ndarray):
+            out[k] = torch.from_numpy(v).to(device)
+        else:
+            out[k] = v
+    return out
+
+
+def make_weights(shapes, seed=0):
+    """Deterministic N(0,0.02) weights (LayerNorm gammas 1 + N(0,0.05)) for a
+    {name: shape} spec, drawn in sorted-name order from numpy's PCG64 so that the
+    authoring container (reference + golden vectors) and the GPU box build
+    bit-identical state_dicts without shipping a 640 MB checkpoint."""
+    rng = np.random.default_rng(seed + 104729)
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        w = rng.standard_normal(shape, dtype=np.float32)
+        if len(shape) == 1 and name.endswith(".weight"):
+            out[name] = (1.0 + 0.05 * w).astype(np.float32)
+        else:
+            out[name] = (0.02 * w).astype(np.float32)
+    return out

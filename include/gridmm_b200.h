@@ -1,0 +1,130 @@
+/* gridmm_b200 -- C ABI of the B200 (sm_100a) implementation of GridMM's per-navigation-step hot path.
+ *
+ * The reference (MrZihan/GridMM) is pure Python/PyTorch: there is no FFI to bind.  These entry points are
+ * what a ctypes/cffi stub on the reference side binds instead of the Python code cited at each function;
+ * gridmm_b200/_lib.py is that stub, INTEGRATION.md shows the three call sites a maintainer changes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the comment says "host";
+ *   - every function is asynchronous on `stream` (pass torch's current stream), re-entrant per device,
+ *     keeps no global state besides a launch counter, allocates nothing;
+ *   - return value: 0 = ok, > 0 = cudaError_t of the failed runtime call / launch,
+ *     GRIDMM_ERR_* (< 0) = rejected arguments.  No entry point has a CPU fallback.
+ *   - fp16 = IEEE binary16 ("half"); matrices are row-major with an explicit pitch in ELEMENTS.
+ */
+#ifndef GRIDMM_B200_H
+#define GRIDMM_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRIDMM_OK 0
+#define GRIDMM_ERR_SHAPE (-1)  /* unsupported size or alignment */
+#define GRIDMM_ERR_DRIVER (-2) /* cuTensorMapEncodeTiled unavailable or failed */
+#define GRIDMM_ERR_ARG (-3)    /* null pointer / inconsistent arguments */
+
+int gridmm_abi_version(void);
+long long gridmm_launch_count(void);      /* kernels launched through this library since the last reset */
+void gridmm_launch_count_reset(void);
+
+/* ---- stage 1: grid build ------------------------------------------------------------------------------
+ * Replaces EnvBatch.getGlobalMap + get_rel_position + get_gridmap_pos_fts
+ * (map_nav_src/r2r/env.py:115-121, 242-265, 267-374; same code in reverie/env.py, rxr/env.py,
+ * pretrain_src/data/dataset.py:351-473; CE geometry VLN_CE/.../Policy_ViewSelection_GridMap.py:632-641, 689-825)
+ * for ALL `batch` episodes in one launch.  Appends the 588 points (12 horizon views x 7x7 patch centres) of the
+ * current viewpoint to the per-episode state, then re-assigns every accumulated point to a cell of the
+ * egocentric grid_w x grid_w window (bit-exact with the reference's fp32 numpy arithmetic), and sorts the valid
+ * points by cell (stable) for gridmm_pool.
+ *   depth        [batch,588] uint16 (depth_is_f32=0; value/depth_scale = metres) or float32 (depth_is_f32=1)
+ *   pose         [batch,4]   px, py, cos(angle), sin(angle); angle = -heading (+pi for CE), evaluated in double on the
+ *                            host and rounded to fp32 exactly like `python float * np.float32 array`
+ *   view_cs      [batch,12,2] cos/sin of each view's angle (R2R: v*pi/6; CE: v*pi/6 - heading), host double -> fp32
+ *   active       [batch] or NULL; 0 = no new viewpoint for this episode (NULL = all active, the reference's behaviour)
+ *   off7         HOST pointer, 7 floats: f32(o_k) * f32(tan(hfov/2)), o = -6/7..6/7 (env.py:118)
+ *   state        wx, wy [batch,cap] f32; valid [batch,cap] u8; bounds [batch,4] = max_x,min_x,max_y,min_y
+ *                (initialise to -10000,10000,-10000,10000: env.py:187-190); n_pts [batch] int32 (initialise to 0)
+ *   outputs      cell [batch,cap] int16 (-1 = masked: env.py:306,366-369); half_len [batch];
+ *                perm [batch,cap] int32; cell_start [batch,grid_w^2+1]; cell_rank [batch,grid_w^2]; n_nonempty [batch];
+ *                pos_fts [batch,grid_w^2,5]
+ * An episode whose n_pts + 588 would exceed cap is left unchanged (the host wrapper grows the buffers first). */
+int gridmm_grid_update(int batch, const void* depth, int depth_is_f32, float depth_scale, const float* pose,
+                       const float* view_cs, const unsigned char* active, const float* off7, int flip_y, int negate_map_x,
+                       int grid_w, int cap, float* wx, float* wy, unsigned char* valid, float* bounds, int* n_pts,
+                       short* cell, float* half_len, int* perm, int* cell_start, int* cell_rank, int* n_nonempty,
+                       float* pos_fts, cudaStream_t stream);
+
+/* Sort-only variant for callers that already hold the reference's `grid_map` tensors (cell id per point, -1 = masked,
+ * r2r/env.py:611): cell [batch,cap] int16 and n_pts [batch] are INPUTS; outputs as above. */
+int gridmm_cell_sort(int batch, const short* cell, const int* n_pts, int grid_w, int cap, int* perm, int* cell_start,
+                     int* cell_rank, int* n_nonempty, cudaStream_t stream);
+
+/* ---- stage 2: instruction-relevance pooling --------------------------------------------------------------
+ * Replaces the B x 196 Python loop of GlocalTextPathNavCMT.forward_navigation_per_step
+ * (map_nav_src/models/vilmodel.py:796-807; pretrain_src/model/vilmodel.py:688-700;
+ * VLN_CE/.../gridmap/vilmodel.py:720-735).  For every episode b and non-empty cell c:
+ *     w_j = max_l <x_j, text_fts[b,l]>      over ALL l in [0,l_pad)  (padding positions included, vilmodel.py:798)
+ *     pooled[b, rank(c)] = sum_{j in c} softmax_c(w)_j * x_j          (fp32 accumulate, fp16 result)
+ * grid_proj is applied afterwards with gridmm_linear_f16 (it commutes with the convex combination).
+ *   fts          fp16 feature slab, row r at fts + r*feat_dim; point (step t, view v, patch k) of episode b is row
+ *                slots[b*t_cap+t]*slot_rows + v*view_rows + tok_off + k   (CLS token skipped via tok_off, env.py:299)
+ *   text_fts     fp16 [batch, l_pad, feat_dim] = text_proj(txt_embeds); l_pad % 8 == 0, l_pad*feat_dim*2 + 64*feat_dim*2
+ *                must fit in shared memory (l_pad <= 80 at feat_dim 768); pad with copies of a real row
+ *   pooled       fp16 [batch, n_cells, feat_dim], rows >= n_nonempty[b] are not written
+ *   w_out        optional f32 [batch,cap]: w per sorted position (tests), or NULL
+ *   num_ctas     0 = one CTA per SM */
+int gridmm_pool(const void* fts, int feat_dim, const int* slots, int t_cap, int slot_rows, int view_rows, int tok_off,
+                const int* perm, int cap, const int* cell_start, const int* cell_rank, int n_cells, const void* text_fts,
+                int l_pad, int batch, void* pooled, float* w_out, int num_ctas, cudaStream_t stream);
+
+/* ---- stage 3: cross-modal encoder blocks ------------------------------------------------------------------
+ * nn.Linear on tcgen05: out = act(a[M,K] . w[N,K]^T + bias) + residual; fp16 operands, fp32 accumulate.
+ * Replaces every nn.Linear of vilmodel.py:95-209, 317-379, 663-674, 702-703 and transformer.py:133-182.
+ * N % 128 == 0, K % 64 == 0; act: 0 none, 1 GELU(erf), 2 ReLU; either output may be NULL. */
+int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                      const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16, int act,
+                      cudaStream_t stream);
+
+/* softmax(q k^T * scale + mask) v per (episode, head); head dim 64; q/k/v/o fp16 with pitches; kmask [batch,sk] u8,
+ * masked keys get `mask_neg` added (-10000: models/ops.py:25-34; -inf: key_padding_mask, transformer.py:176). */
+int gridmm_attention_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv, int k_rows,
+                         void* o, int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk,
+                         float scale, cudaStream_t stream);
+
+/* LayerNorm over 768 (BertLayerNorm eps 1e-12 / nn.LayerNorm eps 1e-5); fp32 and/or fp16 output. */
+int gridmm_layernorm(const float* x, int ldx, const float* gamma, const float* beta, float eps, float* out_f32, int ld_f32,
+                     void* out_f16, int ld_f16, int rows, int hidden, cudaStream_t stream);
+
+/* out[b, out_off + r] = in[b, in_off + r], r < rows_per_b: fp32 rows to fp32 and/or fp16 rows of another per-episode
+ * sequence (builds [map; txt], [gmap; vp] and the head inputs, vilmodel.py:843-850, 855-856, 863). */
+int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int in_off, float* out_f32, int ld_f32, void* out_f16,
+                     int ld_f16, int out_rows_per_b, int out_off, int rows_per_b, int batch, int hidden, cudaStream_t stream);
+
+/* out[b, off + r] = base + table[idx] + LayerNorm(Linear(kin -> 768)(feat))   (vilmodel.py:828-833) */
+int gridmm_pos_embed(const float* feat, int kin, const float* w, const float* bias, const float* gamma, const float* beta,
+                     float eps, const float* base, const float* table, const long long* idx, float* out_f32, void* out_f16,
+                     int in_rows_per_b, int out_rows_per_b, int out_row_off, int rows, int hidden, cudaStream_t stream);
+
+/* grid cells of the map sequence + validity mask incl. the reference's compaction quirk (vilmodel.py:813-823) */
+int gridmm_grid_assemble(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty, const float* w,
+                         const float* bias, const float* gamma, const float* beta, float* map_f32, unsigned char* map_mask,
+                         int batch, int n_cells, int seq, int hidden, cudaStream_t stream);
+
+/* ClsPrediction tail: logit = w2 . LayerNorm(h) + b2 (vilmodel.py:663-674; h = ReLU(Linear(x)) from gridmm_linear_f16) */
+int gridmm_cls_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2, float* logit,
+                    int rows, int hidden, cudaStream_t stream);
+
+/* fuse weight, masking and global/local logit fusion (vilmodel.py:859-907); fuse_src/bw_mask are the integer form of the
+ * reference's vpid-string loops (built on the host by gridmm_b200.model.build_fuse_index). */
+int gridmm_nav_logits(const float* raw_global, const float* raw_grid, const float* raw_local, const float* raw_obj,
+                      const float* raw_fuse, const unsigned char* gmap_masks, const unsigned char* gmap_visited,
+                      const unsigned char* vp_nav_masks, const unsigned char* vp_obj_masks, const int* fuse_src,
+                      const unsigned char* bw_mask, float* global_logits, float* grid_logits, float* local_logits,
+                      float* fused_logits, float* obj_logits, int batch, int G, int V, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDMM_B200_H */

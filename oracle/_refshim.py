@@ -1,0 +1,199 @@
+"""Import the UNMODIFIED reference (MrZihan/GridMM) in-process, CPU only.
+
+TEST INFRASTRUCTURE -- only `oracle/make_golden.py` and tests that are skipped
+when `/root/reference` is absent may use this.  Nothing on the product path, in
+`-m gpu` tests, `smoke()` or `bench.py` imports it: `/root/reference` does not
+exist on the GPU box.
+
+The reference needs four harness-side shims and zero source edits:
+  1. stub modules for imports that are absent here and unused by the hot path
+     (`easydict`, `MatterSim`, `h5py`, `imutils`, `jsonlines`, `line_profiler`,
+     `cv2`/`PIL` are real);
+  2. `GlocalTextPathNavCMT.init_weights` replaced by a no-op, because
+     transformers 5.x expects `post_init()` (map_nav_src/models/vilmodel.py:712);
+     the config is built from `transformers.BertConfig()` + the attributes that
+     map_nav_src/models/vlnbert_init.py:38-56 sets;
+  3. `EnvBatch` is created with `object.__new__` and fed fake simulator state,
+     depth DB, semantic DB and viewpoint_info (all that
+     map_nav_src/r2r/env.py:267-374 touches);
+  4. after each `getGlobalMap` the accumulated feature array is re-viewed as an
+     ndarray subclass whose `== []` is False, because
+     `if self.global_semantic[i] == []` (env.py:298) raises under numpy >= 2.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REF_ROOT = os.environ.get("GRIDMM_REFERENCE", "/root/reference")
+REF_SRC = os.path.join(REF_ROOT, "map_nav_src")
+
+
+def available():
+    return os.path.isdir(REF_SRC)
+
+
+class _AttrDict(dict):
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def _stub(name, **attrs):
+    if name in sys.modules:
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def _install_stubs():
+    try:
+        import easydict  # noqa: F401
+    except ImportError:
+        _stub("easydict", EasyDict=_AttrDict)
+    for name in ("MatterSim", "h5py", "imutils", "jsonlines", "line_profiler"):
+        try:
+            __import__(name)
+        except ImportError:
+            _stub(name)
+    if REF_SRC not in sys.path:
+        sys.path.insert(0, REF_SRC)
+
+
+_MODEL_CACHE = {}
+
+
+def make_config(obj_feat_size=0, num_l_layers=9, num_pano_layers=2, num_x_layers=4,
+                image_feat_size=768, angle_feat_size=4, glocal_fuse=True, graph_sprels=True):
+    """BertConfig + the attributes of map_nav_src/models/vlnbert_init.py:38-56."""
+    from transformers import BertConfig
+    c = BertConfig()
+    c.max_action_steps = 100
+    c.image_feat_size = image_feat_size
+    c.angle_feat_size = angle_feat_size
+    c.obj_feat_size = obj_feat_size
+    c.obj_loc_size = 3
+    c.num_l_layers = num_l_layers
+    c.num_pano_layers = num_pano_layers
+    c.num_x_layers = num_x_layers
+    c.graph_sprels = graph_sprels
+    c.glocal_fuse = glocal_fuse
+    c.fix_lang_embedding = False
+    c.fix_pano_embedding = False
+    c.fix_local_branch = False
+    c.update_lang_bert = True
+    c.output_attentions = True
+    c.pred_head_dropout_prob = 0.1
+    c.use_lang2visn_attn = False
+    return c
+
+
+def load_reference_model(seed=0, **cfg):
+    """Build the reference GlocalTextPathNavCMT with deterministic N(0,0.02) weights."""
+    import torch
+    _install_stubs()
+    from models import vilmodel as ref_vilmodel  # noqa: E402  (reference module)
+    cls = ref_vilmodel.GlocalTextPathNavCMT
+    cls.init_weights = lambda self: None
+    config = make_config(**cfg)
+    model = cls(config)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 1 and name.endswith(".weight"):
+                # LayerNorm gamma: 1 + jitter so a gamma bug cannot hide
+                p.copy_(1.0 + 0.05 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+    model.eval()
+    return model
+
+
+class _NeverEqList(np.ndarray):
+    """ndarray whose comparison with a list is a plain False (shim 4)."""
+
+    def __eq__(self, other):
+        if isinstance(other, list):
+            return False
+        return np.ndarray.__eq__(self, other)
+
+    __hash__ = None
+
+
+class _FakeLoc:
+    def __init__(self, vp):
+        self.viewpointId = vp
+
+
+class _FakeState:
+    def __init__(self, scan, vp, heading):
+        self.scanId = scan
+        self.location = _FakeLoc(vp)
+        self.heading = heading
+
+
+class _FakeSim:
+    def __init__(self):
+        self.state = None
+
+    def getState(self):
+        return [self.state]
+
+
+class _DictDB:
+    def __init__(self):
+        self.store = {}
+
+    def get_image_feature(self, scan, vp):
+        return self.store["%s_%s" % (scan, vp)]
+
+
+def load_reference_env(batch_size):
+    """A reference EnvBatch (map_nav_src/r2r/env.py:125) without MatterSim/h5py."""
+    _install_stubs()
+    import importlib
+    # r2r/env.py imports `utils.data` and `r2r.eval_utils`; both import cleanly with stubs
+    env_mod = importlib.import_module("r2r.env")
+    EnvBatch = env_mod.EnvBatch
+    env = object.__new__(EnvBatch)
+    env.batch_size = batch_size
+    env.sims = [_FakeSim() for _ in range(batch_size)]
+    env.DepthDB = _DictDB()
+    env.SemanticDB = _DictDB()
+    env.viewpoint_info = {}
+    env.feature_states = [None] * batch_size
+    # the state lists of EnvBatch.__init__/newEpisodes (env.py:142-151, 183-193)
+    env.global_semantic = [[] for _ in range(batch_size)]
+    env.global_position_x = [[] for _ in range(batch_size)]
+    env.global_position_y = [[] for _ in range(batch_size)]
+    env.global_mask = [[] for _ in range(batch_size)]
+    env.max_x = [-10000 for _ in range(batch_size)]
+    env.min_x = [10000 for _ in range(batch_size)]
+    env.max_y = [-10000 for _ in range(batch_size)]
+    env.min_y = [10000 for _ in range(batch_size)]
+    env.heading = [0 for _ in range(batch_size)]
+    env.global_map = [[] for _ in range(batch_size)]
+    return env, env_mod
+
+
+def ref_step(env, i, scan, vp, heading, depth_u16, clip_fp16, pos_xy):
+    """Feed one viewpoint to the reference getGlobalMap(i) and return its outputs.
+
+    depth_u16: uint16[36,128,128]; clip_fp16: float16[12, 50, 768]; pos_xy: python floats.
+    Returns (grid_fts fp16[N,768], grid_map f64[N], gridmap_pos_fts f32[196,5]).
+    """
+    key = "%s_%s" % (scan, vp)
+    env.DepthDB.store[key] = depth_u16
+    env.SemanticDB.store[key] = clip_fp16
+    env.viewpoint_info[key] = {"x": float(pos_xy[0]), "y": float(pos_xy[1]), "z": 0.0}
+    env.sims[i].state = _FakeState(scan, vp, heading)
+    out = env.getGlobalMap(i)
+    # mirror getStates (env.py:397): write the returned state back, then shim 4
+    (_, env.global_semantic[i], env.global_position_x[i], env.global_position_y[i],
+     env.global_mask[i], env.global_map[i], env.max_x[i], env.min_x[i], env.max_y[i],
+     env.min_y[i], gridmap_pos_fts) = out
+    env.global_semantic[i] = np.asarray(env.global_semantic[i]).view(_NeverEqList)
+    return np.asarray(env.global_semantic[i]), np.array(env.global_map[i]), gridmap_pos_fts

@@ -1,0 +1,99 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (MrZihan/GridMM, /root/reference) in-process.
+
+TEST INFRASTRUCTURE.  Run in the authoring container only (`python -m oracle.make_golden`); the fixtures are committed
+because /root/reference does not exist on the GPU box.  Inputs and weights are NOT stored: they are regenerated from
+seeds by gridmm_b200/synth.py (numpy PCG64 streams are platform independent), only the reference's outputs are.
+
+  grid_r2r_s{seed}.npz   EnvBatch.getGlobalMap (map_nav_src/r2r/env.py:267-374) over T consecutive steps:
+                         cell ids per step (int16, -1 masked) and gridmap_pos_fts of the last step
+  nav_{name}.npz         GlocalTextPathNavCMT.forward('navigation', ...) (map_nav_src/models/vilmodel.py:782-918):
+                         all five logit tensors + gmap/vp embeddings
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from gridmm_b200 import synth  # noqa: E402
+from oracle import _refshim    # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+GRID_CASES = [dict(seed=11, batch=3, steps=6), dict(seed=12, batch=2, steps=15)]
+NAV_CASES = {
+    # name: (episode kwargs, nav-input kwargs, model kwargs)
+    "r2r_small": (dict(batch=2, steps=3, seed=21), dict(txt_len=32, gmap_len=12, n_views=36, n_objs=0), dict(obj_feat_size=0)),
+    "reverie_small": (dict(batch=2, steps=2, seed=22), dict(txt_len=24, gmap_len=10, n_views=36, n_objs=8), dict(obj_feat_size=768)),
+}
+MODEL_KW = dict(num_l_layers=1, num_pano_layers=1, num_x_layers=4)
+
+
+def reference_grid(ep):
+    """Run the reference getGlobalMap for every episode/step of `ep`; returns per-step cell arrays etc."""
+    B, T = ep["pos"].shape[:2]
+    env, _ = _refshim.load_reference_env(B)
+    cells = [[None] * T for _ in range(B)]
+    fts, pos_fts = [None] * B, [None] * B
+    for t in range(T):
+        for b in range(B):
+            f, gm, pf = _refshim.ref_step(env, b, "scan%d" % b, "vp%d" % t, float(ep["heading"][b, t]),
+                                          synth.expand_depth(ep["depth_sub"][b, t]), ep["clip"][b, t], ep["pos"][b, t])
+            cells[b][t] = gm.astype(np.int16)
+            fts[b], pos_fts[b] = f, pf
+    return cells, fts, pos_fts
+
+
+def make_grid():
+    for case in GRID_CASES:
+        ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+        cells, _, pos_fts = reference_grid(ep)
+        out = {"pos_fts_last": np.stack(pos_fts).astype(np.float32)}
+        for b in range(case["batch"]):
+            for t in range(case["steps"]):
+                out["cell_b%d_t%d" % (b, t)] = cells[b][t]
+        path = os.path.join(GOLD, "grid_r2r_s%d.npz" % case["seed"])
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path))
+
+
+def reference_nav(ep_kw, nav_kw, model_kw):
+    from gridmm_b200.model import NavConfig, param_spec
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, pos_fts = reference_grid(ep)
+    B, T = ep["pos"].shape[:2]
+    kw = dict(MODEL_KW); kw.update(model_kw)
+    model = _refshim.load_reference_model(seed=0, **kw)
+    spec = param_spec(NavConfig(**kw))
+    ref_keys = list(model.state_dict().keys())
+    assert ref_keys == list(spec.keys()), "param_spec order/keys differ from the reference state_dict"
+    w = synth.make_weights({k: v[0] for k, v in spec.items()}, seed=ep_kw["seed"])
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    nav = synth.to_torch(synth.make_nav_inputs(ep_kw["batch"], seed=ep_kw["seed"], **nav_kw))
+    nav["grid_fts"] = [torch.from_numpy(np.ascontiguousarray(f)) for f in fts]
+    nav["grid_map"] = [torch.from_numpy(cells[b][T - 1].astype(np.float64)) for b in range(B)]
+    nav["gridmap_pos_fts"] = torch.from_numpy(np.stack(pos_fts).astype(np.float32))
+    with torch.no_grad():
+        outs = model("navigation", nav)
+    return outs
+
+
+def make_nav():
+    for name, (ep_kw, nav_kw, model_kw) in NAV_CASES.items():
+        outs = reference_nav(ep_kw, nav_kw, model_kw)
+        save = {k: v.numpy() for k, v in outs.items() if v is not None}
+        path = os.path.join(GOLD, "nav_%s.npz" % name)
+        np.savez_compressed(path, **save)
+        print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()})
+
+
+if __name__ == "__main__":
+    if not _refshim.available():
+        raise SystemExit("reference not available at %s" % _refshim.REF_ROOT)
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    make_grid()
+    make_nav()

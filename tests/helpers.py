@@ -1,0 +1,69 @@
+"""Shared builders for the parity tests: seeded inputs (gridmm_b200/synth.py), weights, oracle runs."""
+import os
+
+import numpy as np
+import torch
+
+from gridmm_b200 import synth
+from gridmm_b200.model import NavConfig, param_spec
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODEL_KW = dict(num_l_layers=1, num_pano_layers=1, num_x_layers=4)     # the nav path never touches lang/pano encoders
+
+# must mirror oracle/make_golden.py
+GRID_CASES = [dict(seed=11, batch=3, steps=6), dict(seed=12, batch=2, steps=15)]
+NAV_CASES = {
+    "r2r_small": (dict(batch=2, steps=3, seed=21), dict(txt_len=32, gmap_len=12, n_views=36, n_objs=0), dict(obj_feat_size=0)),
+    "reverie_small": (dict(batch=2, steps=2, seed=22), dict(txt_len=24, gmap_len=10, n_views=36, n_objs=8), dict(obj_feat_size=768)),
+}
+
+
+def make_config(**model_kw):
+    kw = dict(MODEL_KW)
+    kw.update(model_kw)
+    return NavConfig(**kw)
+
+
+def make_weights(cfg, seed):
+    spec = param_spec(cfg)
+    return synth.make_weights({k: v[0] for k, v in spec.items()}, seed=seed)
+
+
+def oracle_grid(ep, grid_w=14, geom=None):
+    """oracle.grid_oracle over all episodes/steps -> (cells[b][t] int32, fts[b] f16[N,D], half[b], pos_fts[b])."""
+    from oracle import grid_oracle as go
+    geom = geom or go.R2RGeometry
+    B, T = ep["pos"].shape[:2]
+    cells = [[None] * T for _ in range(B)]
+    fts, halfs, pos = [None] * B, [None] * B, [None] * B
+    for b in range(B):
+        st = go.GridState()
+        for t in range(T):
+            f, c, h = go.grid_step(st, ep["depth_sub"][b, t], ep["clip"][b, t], ep["pos"][b, t], float(ep["heading"][b, t]),
+                                   grid_w=grid_w, geom=geom)
+            cells[b][t] = c
+        fts[b], halfs[b] = f, h
+        pos[b] = go.gridmap_pos_fts(h, grid_w)
+    return cells, fts, halfs, pos
+
+
+def nav_batch(ep_kw, nav_kw, cells, fts, pos, device="cpu"):
+    """Reference-format 'navigation' batch (map_nav_src/r2r/agent.py:163-205)."""
+    nav = synth.to_torch(synth.make_nav_inputs(ep_kw["batch"], seed=ep_kw["seed"], **nav_kw), device)
+    T = ep_kw["steps"]
+    nav["grid_fts"] = [torch.from_numpy(np.ascontiguousarray(f)).to(device) for f in fts]
+    nav["grid_map"] = [torch.from_numpy(cells[b][T - 1].astype(np.float64)).to(device) for b in range(len(fts))]
+    nav["gridmap_pos_fts"] = torch.from_numpy(np.stack(pos).astype(np.float32)).to(device)
+    return nav
+
+
+def finite_close(a, b, atol):
+    """same -inf pattern and |a-b| <= atol on finite entries; returns max abs error."""
+    a = torch.as_tensor(a).float().cpu()
+    b = torch.as_tensor(b).float().cpu()
+    fa, fb = torch.isfinite(a), torch.isfinite(b)
+    assert torch.equal(fa, fb), "finite/-inf pattern differs"
+    assert torch.equal(a[~fa], b[~fb]), "non-finite entries differ"
+    err = (a[fa] - b[fb]).abs().max().item() if fa.any() else 0.0
+    assert err <= atol, "max abs error %.3e > %.1e" % (err, atol)
+    return err

@@ -1,0 +1,103 @@
+"""CPU: host-side logic, the C-ABI surface, and the 'no CPU fallback' contract."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gridmm_b200 import synth
+from tests import helpers as H
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from gridmm_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = _lib.header_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), "include/gridmm_b200.h declares %s but the library does not export it" % n
+    assert set(_lib._SIGS) <= set(names)
+    assert _lib.load().gridmm_abi_version() == 1
+
+
+def test_param_spec_matches_reference_layout():
+    from gridmm_b200.model import GlocalTextPathNavCMT, NavConfig, param_spec
+    cfg = NavConfig(num_l_layers=1, num_pano_layers=1, obj_feat_size=768)
+    m = GlocalTextPathNavCMT(cfg)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(param_spec(cfg).keys())
+    # the keys SURVEY 8(b) lists as the drop-in contract
+    for k in ("text_proj.weight", "grid_proj.bias", "grid_pos_embeddings.0.weight", "grid_pos_embeddings.1.bias",
+              "grid_encoder.layers.0.self_attn.in_proj_weight", "grid_encoder.norm.weight",
+              "grid_txt_encoder.x_layers.0.visual_attention.att.query.weight",
+              "grid_txt_encoder.x_layers.0.visn_self_att.self.key.bias", "local_encoder.encoder.x_layers.3.visn_output.dense.weight",
+              "local_encoder.vp_pos_embeddings.0.weight", "global_encoder.gmap_step_embeddings.weight",
+              "global_encoder.sprel_linear.weight", "global_sap_head.net.3.weight", "sap_fuse_linear.net.0.weight",
+              "og_head.net.2.bias"):
+        assert k in sd, k
+    assert tuple(sd["grid_encoder.layers.0.self_attn.in_proj_weight"].shape) == (2304, 768)
+    assert tuple(sd["sap_fuse_linear.net.0.weight"].shape) == (768, 1536)
+    total = sum(v.numel() for v in GlocalTextPathNavCMT(NavConfig(obj_feat_size=768)).state_dict().values())
+    assert total == 161596423          # parameter count of the reference model (probed in the authoring container)
+
+
+def test_fuse_index_equals_reference_loops():
+    """build_fuse_index + the kernel's arithmetic (restated in numpy) == the reference's vpid loops (oracle.fuse_logits)."""
+    from gridmm_b200.model import build_fuse_index
+    from oracle import model_oracle as mo
+    for seed in range(5):
+        nav = synth.to_torch(synth.make_nav_inputs(16, seed=seed, gmap_len=14, n_views=36))
+        B, G = nav["gmap_masks"].shape
+        V = nav["vp_masks"].shape[1]
+        g = torch.Generator().manual_seed(seed)
+        gl = torch.randn(B, G, generator=g).masked_fill(nav["gmap_visited_masks"] | ~nav["gmap_masks"], float("-inf"))
+        ll = torch.randn(B, V, generator=g).masked_fill(~nav["vp_nav_masks"], float("-inf"))
+        ref = mo.fuse_logits(gl, ll, nav["gmap_vpids"], nav["gmap_visited_masks"], nav["vp_cand_vpids"])
+        src, bw = build_fuse_index(nav["gmap_vpids"], nav["gmap_visited_masks"], nav["vp_cand_vpids"], G, V)
+        got = gl.clone()
+        got[:, 0] += ll[:, 0]
+        for i in range(B):
+            s = torch.zeros(())
+            for v in range(1, V):
+                if bw[i, v]:
+                    s = s + ll[i, v]
+            for j in range(1, G):
+                if src[i, j] >= 0:
+                    got[i, j] += ll[i, src[i, j]]
+                elif src[i, j] == -2:
+                    got[i, j] += s
+        assert torch.equal(got, ref)
+
+
+def test_host_pose_rounding_contract():
+    """trig evaluated in double then rounded to fp32 (python float x np.float32 array, env.py:119-120,347-348)."""
+    import math
+    from gridmm_b200.env import GEOMETRIES
+    g = GEOMETRIES["r2r"]
+    off = np.array([-6 / 7, -4 / 7, -2 / 7, 0., 2 / 7, 4 / 7, 6 / 7] * 7, np.float32) * math.tan(math.pi / 6)
+    assert off.dtype == np.float32 and np.array_equal(off[:7], g.off7)
+
+
+def test_no_cpu_path():
+    """The product path must fail loudly without a GPU instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from gridmm_b200 import ops, _lib
+    from gridmm_b200.env import GridMapBuilder
+    with pytest.raises(RuntimeError):
+        GridMapBuilder(2)
+    with pytest.raises(_lib.GridmmError):
+        ops.linear(torch.zeros(128, 64, dtype=torch.float16), torch.zeros(128, 64, dtype=torch.float16),
+                   out_f16=torch.zeros(128, 128, dtype=torch.float16))
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "gridmm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

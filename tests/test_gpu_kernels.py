@@ -1,0 +1,239 @@
+"""GPU: each sm_100a kernel, called through the C ABI (gridmm_b200/_lib.py -> include/gridmm_b200.h), against a plain
+torch fp32 reference of the same op (floating point) or the oracle (integer grid work, bit-exact)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from gridmm_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (6912, 2304, 768), (1000, 768, 3072), (32, 768, 1536)])
+def test_linear_tcgen05_plain(M, N, K):
+    from gridmm_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).half().to(_dev())
+    w = (torch.randn(N, K, generator=g) * 0.05).half().to(_dev())
+    bias = torch.randn(N, generator=g).to(_dev())
+    o32 = torch.empty(M, N, device=_dev())
+    o16 = torch.empty(M, N, device=_dev(), dtype=torch.float16)
+    ops.linear(a, w, bias=bias, out_f32=o32, out_f16=o16)
+    ref = a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    err = (o32 - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err      # fp32 accumulate, order differs from cuBLAS only
+    assert (o16.float() - ref).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_linear_epilogues(act):
+    from gridmm_b200 import ops
+    M, N, K = 517, 256, 192
+    g = torch.Generator().manual_seed(act)
+    a = torch.randn(M, K, generator=g).half().to(_dev())
+    w = (torch.randn(N, K, generator=g) * 0.1).half().to(_dev())
+    bias = torch.randn(N, generator=g).to(_dev())
+    res = torch.randn(M, N, generator=g).to(_dev())
+    out = res.clone()
+    ops.linear(a, w, bias=bias, residual=out, out_f32=out, act=act)       # in-place residual, as the model uses it
+    y = a.float() @ w.float().t() + bias
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    elif act == 2:
+        y = torch.relu(y)
+    ref = y + res
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() < 2e-3
+
+
+def test_linear_strided_views():
+    """A operand / outputs addressed through row pitches (fused QKV buffers)."""
+    from gridmm_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    big = torch.randn(260, 3 * 768, generator=g).half().to(_dev())
+    w = (torch.randn(768, 768, generator=g) * 0.05).half().to(_dev())
+    out = torch.zeros(260, 1536, device=_dev(), dtype=torch.float16)
+    ops.linear(big[:, 768:1536], w, out_f16=out[:, 768:])
+    ref = big[:, 768:1536].float() @ w.float().t()
+    torch.cuda.synchronize()
+    assert (out[:, 768:].float() - ref).abs().max().item() < 2e-2
+    assert out[:, :768].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,Sq,Sk,neg", [(2, 216, 216, float("-inf")), (3, 57, 296, -10000.0), (2, 64, 80, -10000.0), (1, 5, 7, -10000.0)])
+def test_attention(B, Sq, Sk, neg):
+    from gridmm_b200 import ops
+    g = torch.Generator().manual_seed(Sq * 7 + Sk)
+    q = torch.randn(B * Sq, 768, generator=g).half().to(_dev())
+    kv = torch.randn(B * Sk, 1536, generator=g).half().to(_dev())
+    lens = torch.randint(1, Sk + 1, (B,), generator=g)
+    lens[0] = Sk
+    kmask = (torch.arange(Sk)[None, :] < lens[:, None]).to(torch.uint8).to(_dev())
+    out = torch.empty(B * Sq, 768, device=_dev(), dtype=torch.float16)
+    ops.attention(q, kv[:, :768], kv[:, 768:], out, kmask, neg, B, 12, Sq, Sk)
+    qh = q.float().view(B, Sq, 12, 64).permute(0, 2, 1, 3)
+    kh = kv[:, :768].float().view(B, Sk, 12, 64).permute(0, 2, 1, 3)
+    vh = kv[:, 768:].float().view(B, Sk, 12, 64).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / 8.0
+    add = torch.zeros(B, Sk, device=_dev()).masked_fill(kmask == 0, neg)[:, None, None, :]
+    ref = (torch.softmax(s + add, -1) @ vh).permute(0, 2, 1, 3).reshape(B * Sq, 768)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() < 6e-3      # P and the output are rounded to fp16
+
+
+def test_layernorm_and_rows():
+    from gridmm_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(1001, 768, generator=g) * 3 + 1).to(_dev())
+    gamma = torch.randn(768, generator=g).to(_dev())
+    beta = torch.randn(768, generator=g).to(_dev())
+    for eps in (1e-12, 1e-5):
+        o32 = torch.empty_like(x)
+        o16 = torch.empty(1001, 768, device=_dev(), dtype=torch.float16)
+        ops.layernorm(x, gamma, beta, eps, out_f32=o32, out_f16=o16)
+        ref = torch.nn.functional.layer_norm(x, (768,), gamma, beta, eps)
+        torch.cuda.synchronize()
+        assert (o32 - ref).abs().max().item() < 2e-5
+        assert (o16.float() - ref).abs().max().item() < 1e-2
+    # copy_rows: x viewed as [7, 143] rows per episode -> rows 3..12 of each to offset 20 of a 40-row sequence
+    o32 = torch.zeros(7 * 40, 768, device=_dev())
+    ops.copy_rows(x, 143, 3, 10, 7, 40, 20, out_f32=o32)
+    torch.cuda.synchronize()
+    assert torch.equal(o32.view(7, 40, 768)[:, 20:30], x.view(7, 143, 768)[:, 3:13])
+    assert o32.view(7, 40, 768)[:, :20].abs().max().item() == 0
+
+
+def test_pos_embed():
+    from gridmm_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, G, S = 3, 11, 30
+    feat = torch.randn(B * G, 7, generator=g).to(_dev())
+    w = torch.randn(768, 7, generator=g).to(_dev()); b = torch.randn(768, generator=g).to(_dev())
+    gamma = torch.randn(768, generator=g).to(_dev()); beta = torch.randn(768, generator=g).to(_dev())
+    base = torch.randn(B * G, 768, generator=g).to(_dev())
+    table = torch.randn(100, 768, generator=g).to(_dev())
+    idx = torch.randint(0, 100, (B * G,), generator=g).to(_dev())
+    out = torch.zeros(B * S, 768, device=_dev())
+    ops.pos_embed(feat, w, b, gamma, beta, 1e-12, out, None, G, S, 19, base=base, table=table, idx=idx)
+    ref = base + table[idx] + torch.nn.functional.layer_norm(feat @ w.t() + b, (768,), gamma, beta, 1e-12)
+    torch.cuda.synchronize()
+    assert (out.view(B, S, 768)[:, 19:] - ref.view(B, G, 768)).abs().max().item() < 2e-5
+
+
+def _run_builder(ep, grid_w=14, geometry="r2r"):
+    from gridmm_b200.env import GridMapBuilder
+    B, T = ep["pos"].shape[:2]
+    gb = GridMapBuilder(B, feat_dim=ep["clip"].shape[-1], grid_w=grid_w, geometry=geometry, max_steps=4)   # forces a regrow
+    per_step = []
+    for t in range(T):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+        torch.cuda.synchronize()
+        per_step.append(grid.grid_map_numpy())
+    return gb, grid, per_step
+
+
+@pytest.mark.parametrize("case", H.GRID_CASES + [dict(seed=13, batch=8, steps=15)], ids=lambda c: "s%d" % c["seed"])
+def test_grid_update_bit_exact(case):
+    """cell ids bit-exact vs the oracle at every step (and, through tests/golden, vs the reference itself)."""
+    import os
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    cells, fts, halfs, pos = H.oracle_grid(ep)
+    gb, grid, per_step = _run_builder(ep)
+    gold_path = os.path.join(H.GOLD, "grid_r2r_s%d.npz" % case["seed"])
+    gold = np.load(gold_path) if os.path.exists(gold_path) else None
+    B, T = case["batch"], case["steps"]
+    for t in range(T):
+        for b in range(B):
+            got = per_step[t][b]
+            assert got.dtype == np.float64 and got.shape == (588 * (t + 1),)
+            assert np.array_equal(got.astype(np.int32), cells[b][t]), "b=%d t=%d" % (b, t)
+            if gold is not None:
+                assert np.array_equal(got.astype(np.int16), gold["cell_b%d_t%d" % (b, t)])
+    # window + polar features
+    np.testing.assert_array_equal(grid.half_len.cpu().numpy(), np.array(halfs, dtype=np.float32))
+    np.testing.assert_allclose(grid.pos_fts.cpu().numpy(), np.stack(pos), atol=2e-6, rtol=0)
+    # sorted layout: perm is a stable sort of the valid points by cell
+    perm = grid.perm.cpu().numpy(); cs = grid.cell_start.cpu().numpy(); cr = grid.cell_rank.cpu().numpy()
+    ne = grid.n_nonempty.cpu().numpy()
+    for b in range(B):
+        c = cells[b][T - 1]
+        valid = np.nonzero(c >= 0)[0]
+        order = valid[np.argsort(c[valid], kind="stable")]
+        assert np.array_equal(perm[b, :len(order)], order)
+        counts = np.bincount(c[valid], minlength=196)
+        assert np.array_equal(cs[b], np.concatenate([[0], np.cumsum(counts)]))
+        rank = np.where(counts > 0, np.cumsum(counts > 0) - 1, -1)
+        assert np.array_equal(cr[b], rank) and ne[b] == (counts > 0).sum()
+    # features in the reference's row order
+    got_fts = grid.grid_fts_torch()
+    for b in range(B):
+        assert torch.equal(got_fts[b].cpu(), torch.from_numpy(np.ascontiguousarray(fts[b])))
+
+
+def test_grid_update_8x8_config1():
+    """BASELINE config 1: 8x8 grid, 512-d features, one viewpoint (the reference hard-codes 14/768; oracle is parametric)."""
+    ep = synth.make_episodes(1, 1, seed=1, dim=512)
+    cells, fts, halfs, pos = H.oracle_grid(ep, grid_w=8)
+    gb, grid, per_step = _run_builder(ep, grid_w=8)
+    assert np.array_equal(per_step[0][0].astype(np.int32), cells[0][0])
+    assert per_step[0][0].max() <= 63
+    np.testing.assert_allclose(grid.pos_fts.cpu().numpy()[0], pos[0], atol=2e-6, rtol=0)
+
+
+def test_grid_update_ce_geometry():
+    from oracle import grid_oracle as go
+    ep = synth.make_episodes(4, 5, seed=4, dim=768)
+    ep["depth_sub"] = (ep["depth_sub"].astype(np.float32) / 4000.0).astype(np.float32)       # CE depth is metres
+    cells, fts, halfs, pos = H.oracle_grid(ep, geom=go.CEGeometry)
+    gb, grid, per_step = _run_builder(ep, geometry="r2r_ce")
+    for t in range(5):
+        for b in range(4):
+            assert np.array_equal(per_step[t][b].astype(np.int32), cells[b][t]), "b=%d t=%d" % (b, t)
+
+
+def _oracle_pool(fts, cell, tp16, n_cells=196):
+    """float64 statement of vilmodel.py:797-807 in feature space, with the SAME fp16-rounded text_fts the kernel sees."""
+    x = torch.from_numpy(np.ascontiguousarray(fts)).double()
+    w = (x @ tp16.double().t()).max(-1)[0]
+    out = torch.zeros(n_cells, x.shape[1], dtype=torch.float64)
+    cell = torch.from_numpy(cell.astype(np.int64))
+    for c in range(n_cells):
+        sel = cell == c
+        if sel.any():
+            out[c] = (torch.softmax(w[sel], 0)[:, None] * x[sel]).sum(0)
+    return out, w
+
+
+@pytest.mark.parametrize("B,T,L,D,gw", [(3, 2, 80, 768, 14), (8, 8, 80, 768, 14), (2, 15, 40, 768, 14), (1, 1, 16, 512, 8), (37, 3, 24, 768, 14)])
+def test_pool_vs_oracle(B, T, L, D, gw):
+    from gridmm_b200 import ops
+    ep = synth.make_episodes(B, T, seed=B * 100 + T, dim=D)
+    cells, fts, halfs, pos = H.oracle_grid(ep, grid_w=gw)
+    gb, grid, _ = _run_builder(ep, grid_w=gw)
+    nc = gw * gw
+    g = torch.Generator().manual_seed(L)
+    tp = (torch.randn(B, L, D, generator=g) * 0.55).half()
+    pooled = torch.zeros(B * nc, D, device=_dev(), dtype=torch.float16)
+    w_out = torch.zeros(B, grid.cap, device=_dev())
+    ops.pool(grid.slab, D, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
+             grid.cell_start, grid.cell_rank, nc, tp.to(_dev()).view(B * L, D), L, B, pooled, w_out=w_out)
+    torch.cuda.synchronize()
+    pooled = pooled.view(B, nc, D).float().cpu(); w_out = w_out.cpu()
+    perm = grid.perm.cpu().numpy(); cr = grid.cell_rank.cpu().numpy(); cs = grid.cell_start.cpu().numpy()
+    for b in range(B):
+        ref, w = _oracle_pool(fts[b], cells[b][T - 1], tp[b], nc)
+        nv = cs[b, nc]
+        werr = (w_out[b, :nv].double() - w[perm[b, :nv]]).abs().max().item()
+        assert werr < 2e-3, "relevance max differs: %.3e" % werr          # fp32 tensor-core accumulate vs float64
+        for c in range(nc):
+            if cr[b, c] >= 0:
+                err = (pooled[b, cr[b, c]].double() - ref[c]).abs().max().item()
+                assert err < 6e-3, "b=%d cell=%d err=%.3e" % (b, c, err)   # fp16 output (ulp 4e-3 at |x|~4) + exp rounding

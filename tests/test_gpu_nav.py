@@ -1,0 +1,157 @@
+"""GPU: forward('navigation') of gridmm_b200.model (CUDA kernels through the C ABI) against
+  (a) golden outputs of the reference's own forward (tests/golden/nav_*.npz, made by oracle/make_golden.py),
+  (b) the CPU oracle (oracle/model_oracle.py) on the same seeded inputs, up to BASELINE config 2's full size,
+  (c) size-independent properties at full size (batch-order equivariance, list path == device-built path).
+Tolerance for action logits: 1e-3 absolute (BASELINE.json north_star); fp16 tensor-core operands, fp32 accumulate."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gridmm_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-3
+EMBED_TOL = 2e-2          # 768-d hidden states with |x| up to ~6 after LayerNorm
+LOGITS = ("global_logits", "local_logits", "fused_logits", "grid_logits", "obj_logits")
+
+
+def _model(cfg, seed):
+    from gridmm_b200.model import GlocalTextPathNavCMT
+    m = GlocalTextPathNavCMT(cfg)
+    w = H.make_weights(cfg, seed)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    return m.cuda().eval(), w
+
+
+def _to_cuda(nav):
+    out = {}
+    for k, v in nav.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.cuda()
+        elif isinstance(v, list) and len(v) and isinstance(v[0], torch.Tensor):
+            out[k] = [t.cuda() for t in v]
+        else:
+            out[k] = v
+    return out
+
+
+def _check(out, ref, keys=None):
+    errs = {}
+    for k in (keys or ref.keys()):
+        r = ref[k]
+        if r is None:
+            assert out[k] is None
+            continue
+        tol = LOGIT_TOL if k in LOGITS else EMBED_TOL
+        errs[k] = H.finite_close(out[k], r, atol=tol)
+    return errs
+
+
+@pytest.mark.parametrize("name", sorted(H.NAV_CASES))
+def test_nav_matches_reference_golden(name):
+    ep_kw, nav_kw, model_kw = H.NAV_CASES[name]
+    gold = np.load(os.path.join(H.GOLD, "nav_%s.npz" % name))
+    cfg = H.make_config(**model_kw)
+    model, _ = _model(cfg, ep_kw["seed"])
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, _, pos = H.oracle_grid(ep)
+    nav = _to_cuda(H.nav_batch(ep_kw, nav_kw, cells, fts, pos))
+    out = model("navigation", nav)
+    torch.cuda.synchronize()
+    errs = _check(out, {k: gold[k] for k in gold.files})
+    print(name, errs)
+    if "obj_logits" not in gold.files:
+        assert out["obj_logits"] is None
+
+
+def _oracle_nav(cfg, w, nav):
+    from oracle import model_oracle as mo
+    sd = {k: torch.from_numpy(v) for k, v in w.items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        return mo.navigation(sd, nav, n_x_layers=cfg.num_x_layers, return_intermediates=True)
+
+
+@pytest.mark.parametrize("B,T,L,G,objs", [(4, 2, 37, 9, 0), (32, 8, 80, 20, 0), (32, 4, 80, 20, 20), (5, 15, 80, 20, 0)],
+                         ids=["ragged_L37", "cfg2_b32_t8", "cfg3_reverie_b32", "t15"])
+def test_nav_matches_oracle(B, T, L, G, objs):
+    ep_kw = dict(batch=B, steps=T, seed=1000 + B + T)
+    nav_kw = dict(txt_len=L, gmap_len=G, n_views=36, n_objs=objs)
+    cfg = H.make_config(obj_feat_size=768 if objs else 0)
+    model, w = _model(cfg, ep_kw["seed"])
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, _, pos = H.oracle_grid(ep)
+    nav = H.nav_batch(ep_kw, nav_kw, cells, fts, pos)
+    ref = _oracle_nav(cfg, w, nav)
+    out = model("navigation", _to_cuda(nav), return_intermediates=True)
+    torch.cuda.synchronize()
+    # intermediate: map sequence after grid_encoder + grid_txt_encoder, on the rows the reference has (C = max cells)
+    C = ref["grid_masks"].shape[1]
+    got_map = out["map_embeds"].cpu()
+    got = torch.cat([got_map[:, :C], got_map[:, 196:]], 1)
+    valid = torch.cat([ref["grid_masks"], nav["gmap_masks"]], 1)
+    assert torch.equal(torch.cat([out["map_masks"].cpu()[:, :C], out["map_masks"].cpu()[:, 196:]], 1).bool(), valid)
+    assert out["map_masks"].cpu()[:, C:196].sum() == 0
+    err_map = (got - ref["map_embeds"])[valid].abs().max().item()
+    assert err_map < EMBED_TOL, err_map
+    errs = _check(out, ref, keys=("gmap_embeds", "vp_embeds") + LOGITS)
+    print("B=%d T=%d" % (B, T), "map", err_map, errs)
+    # argmax of the action distribution (what the agent acts on), ties within tolerance excepted
+    a, r = out["fused_logits"].cpu(), ref["fused_logits"]
+    same = a.argmax(1) == r.argmax(1)
+    if not same.all():
+        top2 = r.topk(2, 1).values
+        assert ((top2[:, 0] - top2[:, 1])[~same] < 2 * LOGIT_TOL).all()
+
+
+def test_device_built_grid_equals_list_path_and_batch_order():
+    """(1) GridBatch from GridMapBuilder == the reference-format lists uploaded per step (same kernels, same sorted order);
+    (2) episodes are independent: reversing the batch order permutes the outputs and changes nothing else."""
+    from gridmm_b200.env import GridMapBuilder
+    B, T, L, G = 32, 8, 80, 20
+    ep_kw = dict(batch=B, steps=T, seed=77)
+    nav_kw = dict(txt_len=L, gmap_len=G, n_views=36, n_objs=0)
+    cfg = H.make_config()
+    model, _ = _model(cfg, 77)
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    gb = GridMapBuilder(B, max_steps=T)
+    for t in range(T):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+    nav = _to_cuda(synth.to_torch(synth.make_nav_inputs(B, seed=77, **nav_kw)))
+    nav_dev = dict(nav); nav_dev.update(grid=grid, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+    out_dev = model("navigation", nav_dev)
+    out_dev = {k: (v.clone() if v is not None else None) for k, v in out_dev.items()}
+    nav_list = dict(nav)
+    nav_list.update(grid_fts=grid.grid_fts_torch(), grid_map=[torch.from_numpy(c).cuda() for c in grid.grid_map_numpy()],
+                    gridmap_pos_fts=grid.pos_fts.clone())
+    out_list = model("navigation", nav_list)
+    torch.cuda.synchronize()
+    for k in LOGITS[:4] + ("gmap_embeds", "vp_embeds"):
+        assert torch.equal(out_dev[k], out_list[k]), k
+    # batch-order equivariance
+    rev = list(range(B - 1, -1, -1))
+    nav_rev = {}
+    for k, v in nav_list.items():
+        if isinstance(v, torch.Tensor):
+            nav_rev[k] = v[rev].contiguous()
+        elif isinstance(v, list):
+            nav_rev[k] = [v[i] for i in rev]
+        else:
+            nav_rev[k] = v
+    out_rev = model("navigation", nav_rev)
+    torch.cuda.synchronize()
+    for k in LOGITS[:4]:
+        H.finite_close(out_rev[k][rev], out_list[k], atol=2e-5)     # only the pooling kernel's CTA split moves
+
+
+def test_missing_cuda_inputs_fail_loudly():
+    from gridmm_b200 import ops, _lib
+    with pytest.raises(_lib.GridmmError):
+        ops.linear(torch.zeros(128, 64, dtype=torch.float16), torch.zeros(128, 64, dtype=torch.float16).cuda(),
+                   out_f16=torch.zeros(128, 128, dtype=torch.float16).cuda())
+    with pytest.raises(_lib.GridmmError):
+        ops.linear(torch.zeros(128, 72, dtype=torch.float16).cuda(), torch.zeros(128, 72, dtype=torch.float16).cuda(),
+                   out_f16=torch.zeros(128, 128, dtype=torch.float16).cuda())     # K % 64 != 0 -> GRIDMM_ERR_SHAPE

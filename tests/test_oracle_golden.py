@@ -1,0 +1,60 @@
+"""CPU: the oracle (oracle/*.py, a restatement) against golden vectors produced by the reference itself
+(oracle/make_golden.py ran MrZihan/GridMM's own EnvBatch.getGlobalMap and forward('navigation') in the authoring
+container).  This is what pins the oracle; the GPU tests then compare the CUDA path with the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gridmm_b200 import synth
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("case", H.GRID_CASES, ids=lambda c: "s%d" % c["seed"])
+def test_grid_oracle_matches_reference_cells(case):
+    gold = np.load(os.path.join(H.GOLD, "grid_r2r_s%d.npz" % case["seed"]))
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    cells, _, _, pos = H.oracle_grid(ep)
+    n = 0
+    for b in range(case["batch"]):
+        for t in range(case["steps"]):
+            ref = gold["cell_b%d_t%d" % (b, t)]
+            assert ref.shape == cells[b][t].shape
+            assert np.array_equal(ref.astype(np.int32), cells[b][t]), "cell ids differ at b=%d t=%d" % (b, t)   # bit-exact
+            n += ref.size
+    assert n == case["batch"] * 588 * case["steps"] * (case["steps"] + 1) // 2
+    np.testing.assert_allclose(np.stack(pos), gold["pos_fts_last"], atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("name", sorted(H.NAV_CASES))
+def test_nav_oracle_matches_reference_forward(name):
+    from oracle import model_oracle as mo
+    ep_kw, nav_kw, model_kw = H.NAV_CASES[name]
+    gold = np.load(os.path.join(H.GOLD, "nav_%s.npz" % name))
+    cfg = H.make_config(**model_kw)
+    sd = {k: torch.from_numpy(v) for k, v in H.make_weights(cfg, ep_kw["seed"]).items()}
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, _, pos = H.oracle_grid(ep)
+    nav = H.nav_batch(ep_kw, nav_kw, cells, fts, pos)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        out = mo.navigation(sd, nav, n_x_layers=cfg.num_x_layers)
+    for k in gold.files:
+        H.finite_close(out[k], gold[k], atol=2e-5)     # fp32 CPU vs fp32 CPU: summation order only
+    if "obj_logits" not in gold.files:
+        assert out["obj_logits"] is None
+
+
+def test_compaction_quirk_is_reproduced():
+    """vilmodel.py:813-823: the mask row ends as [0,k) u (S n [k,k')), k' = k + |S n [k,196)|."""
+    from oracle import model_oracle as mo
+    nonempty = torch.zeros(2, 196, dtype=torch.long)
+    nonempty[0, [0, 3, 5, 7, 100]] = 1            # k = 5, S n [5,196) = {5,7,100} -> k' = 8, valid = [0,5) u {5,7}
+    nonempty[1, :9] = 1                            # k = 9 = C
+    gmi = torch.randn(2, 196, 8)
+    embeds, masks, C = mo.compact_cells(gmi, nonempty)
+    assert C == 9
+    assert masks[0].tolist() == [True] * 5 + [True, False, True, False]
+    assert masks[1].all()
+    assert torch.equal(embeds[0, :5], gmi[0, [0, 3, 5, 7, 100]]) and embeds[0, 5:].abs().sum() == 0
