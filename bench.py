@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- nav-steps/sec of the GridMM per-navigation-step hot path (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic R2R-shaped input (BASELINE config 2:
+batch 32, 14x14 grid, 36-view pano, 80-token instruction, the 8th viewpoint of every episode, i.e. N = 4704
+accumulated patch points per episode):
+    grid build  (gridmm_grid_update: append the viewpoint, re-assign all points, sort by cell)
+  + forward('navigation')  (relevance pooling, grid/text/pano cross-modal encoders, action logits).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the reference algorithm on the host CPU
+                                                                    # (oracle/ port; /root/reference cannot travel)
+N > 1: launched by torchrun, one rank per GPU, episodes sharded (weak scaling, no data-path collective).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gridmm_b200 import synth  # noqa: E402
+
+B, T, L, G, VIEWS = 32, 8, 80, 20, 36
+METRIC = "nav-steps/sec (grid build + cross-modal encode) R2R batch"
+CONFIG = {"workload": "configs[1]: R2R fine-tune forward, batch 32/GPU, 14x14 grid, 36-view pano, 80-tok instr, step T=8 "
+                      "(N=4704 points/episode), eval mode",
+          "batch_per_gpu": B, "T": T, "txt_len": L, "gmap_len": G, "views": VIEWS,
+          "l2": "inputs > L2: the pooling kernel streams ~208 MB of fp16 patch features per step; activations are L2-resident by nature"}
+
+
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _inputs(seed):
+    ep = synth.make_episodes(B, T, seed=seed, dim=768)
+    nav = synth.make_nav_inputs(B, seed=seed, txt_len=L, gmap_len=G, n_views=VIEWS)
+    return ep, nav
+
+
+def _weights(seed=0, obj=False):
+    from gridmm_b200.model import NavConfig, param_spec
+    cfg = NavConfig(num_l_layers=1, num_pano_layers=1, obj_feat_size=768 if obj else 0)   # lang/pano encoders are not on the path
+    w = synth.make_weights({k: v[0] for k, v in param_spec(cfg).items()}, seed=seed)
+    return cfg, w
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_steps(ep, nav_np, cfg, w, n_steps, threads):
+    """The reference algorithm on host cores: per-episode serial grid build (r2r/env.py:392-398) + forward('navigation')
+    (vilmodel.py:782-918) through the oracle port.  Returns seconds per step (best of n_steps after one warm-up)."""
+    from oracle import grid_oracle as go
+    from oracle import model_oracle as mo
+    torch.set_num_threads(threads)
+    sd = {k: torch.from_numpy(v) for k, v in w.items()}
+    nav = synth.to_torch(nav_np)
+    # state after T-1 viewpoints (not timed)
+    states = []
+    for b in range(B):
+        st = go.GridState()
+        for t in range(T - 1):
+            go.grid_step(st, ep["depth_sub"][b, t], ep["clip"][b, t], ep["pos"][b, t], float(ep["heading"][b, t]))
+        states.append(st)
+    times = []
+    for it in range(n_steps + 1):
+        t0 = time.perf_counter()
+        fts, cells, pos = [], [], []
+        for b in range(B):
+            st = states[b]
+            keep = (len(st.wx), st.max_x, st.min_x, st.max_y, st.min_y)
+            f, c, h = go.grid_step(st, ep["depth_sub"][b, T - 1], ep["clip"][b, T - 1], ep["pos"][b, T - 1],
+                                   float(ep["heading"][b, T - 1]))
+            pos.append(go.gridmap_pos_fts(h))
+            fts.append(torch.from_numpy(f)); cells.append(torch.from_numpy(c.astype(np.float64)))
+            # roll the state back so every timed step is the same T-th step
+            del st.wx[keep[0]:], st.wy[keep[0]:], st.mask[keep[0]:], st.fts[keep[0]:]
+            st.max_x, st.min_x, st.max_y, st.min_y = keep[1:]
+        nav["grid_fts"], nav["grid_map"] = fts, cells
+        nav["gridmap_pos_fts"] = torch.from_numpy(np.stack(pos).astype(np.float32))
+        with torch.no_grad():
+            out = mo.navigation(sd, nav, n_x_layers=cfg.num_x_layers)
+        float(out["fused_logits"][0, 0])
+        dt = time.perf_counter() - t0
+        if it > 0:
+            times.append(dt)
+    return min(times), statistics.mean(times)
+
+
+def run_reference(args):
+    rank, world, _ = _dist_env()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ep, nav = _inputs(0)
+    cfg, w = _weights()
+    n = max(1, min(args.steps, 3))
+    best, mean = cpu_reference_steps(ep, nav, cfg, w, n, threads)
+    value = B / mean
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "nav-steps/s", "n_gpus": args.gpus, "steps": n,
+            "warmup": 1, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {"value": value, "unit": "nav-steps/s", "cores": threads, "kind": "port",
+                             "sample": "%d step(s) of the B=32, T=8 workload (oracle/ port of the reference algorithm)" % n},
+            "e2e": {"value": value, "unit": "nav-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- CUDA path
+class ClockSampler:
+    """nvidia-smi sampling (the recipe's clocks line) started early; samples are attributed to a window by timestamp."""
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self, t0, t1):
+        """Summary over samples with t0 <= timestamp <= t1 (epoch seconds)."""
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if ts < t0 or ts > t1:
+                    continue
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                   "power_w_max": max(pw)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+class Step:
+    """Holds the device state of one rank and runs one hot-path step."""
+
+    def __init__(self, device, seed):
+        from gridmm_b200.env import GridMapBuilder
+        from gridmm_b200.model import GlocalTextPathNavCMT
+        self.dev = device
+        self.ep, self.nav_np = _inputs(seed)
+        self.cfg, w = _weights()
+        self.model = GlocalTextPathNavCMT(self.cfg)
+        self.model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+        self.model.to(device).eval()
+        self.model.enable_cuda_graph(True)      # the device part of forward('navigation') replays from a CUDA graph
+        self.builder = GridMapBuilder(B, max_steps=T, device=device)
+        ep = self.ep
+        for t in range(T - 1):
+            self.builder.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+        # saved state of step T-1, restored before every step so each timed step is the same 8th step
+        self.saved_bounds = self.builder.bounds.clone()
+        self.saved_npts = self.builder.n_pts.clone()
+        self.saved_steps = self.builder.n_steps.copy()
+        self.nav = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in synth.to_torch(self.nav_np).items()}
+        # host (pinned) and device copies of the step's new observation
+        self.h_depth = torch.from_numpy(ep["depth_sub"][:, T - 1].astype(np.int16)).pin_memory()
+        self.h_clip = torch.from_numpy(np.ascontiguousarray(ep["clip"][:, T - 1])).pin_memory()
+        self.d_depth = self.h_depth.to(device)
+        self.d_clip = self.h_clip.to(device)
+        # per-step host-originating nav inputs (ids, position features, masks); embeddings stay on the device, where the
+        # reference's 'language' / 'panorama' modes leave them
+        self.host_keys = ["gmap_step_ids", "gmap_pos_fts", "gmap_masks", "gmap_visited_masks", "vp_pos_fts", "vp_masks",
+                          "vp_nav_masks"]
+        self.h_nav = {k: synth.to_torch(self.nav_np)[k].pin_memory() for k in self.host_keys}
+
+    def restore(self):
+        self.builder.bounds.copy_(self.saved_bounds)
+        self.builder.n_pts.copy_(self.saved_npts)
+        self.builder.n_steps = self.saved_steps.copy()
+
+    def run_resident(self):
+        """inputs already in HBM"""
+        self.restore()
+        ep = self.ep
+        grid = self.builder.step(self.d_depth, self.d_clip, ep["pos"][:, T - 1], ep["heading"][:, T - 1])
+        batch = dict(self.nav); batch["grid"] = grid
+        batch.update(grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        return self.model("navigation", batch)
+
+    def run_e2e(self):
+        """host buffers in, logits out: H2D of the new viewpoint (depth + CLIP tokens) and of the step's nav inputs,
+        D2H of the fused logits."""
+        self.restore()
+        ep = self.ep
+        grid = self.builder.step(self.h_depth.numpy().view(np.uint16), self.h_clip, ep["pos"][:, T - 1], ep["heading"][:, T - 1])
+        batch = dict(self.nav); batch["grid"] = grid
+        batch.update(grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        for k in self.host_keys:
+            batch[k] = self.h_nav[k].to(self.dev, non_blocking=True)
+        out = self.model("navigation", batch)
+        return out["fused_logits"].cpu()
+
+    def e2e_bytes(self):
+        h2d = self.h_depth.numel() * 2 + self.h_clip.numel() * 2 + B * 28 * 4
+        h2d += sum(v.numel() * v.element_size() for v in self.h_nav.values()) + B * (G * 4 + (1 + VIEWS) * 1)
+        return int(h2d), int(B * G * 4)
+
+
+def timed(fn, steps, warmup, world):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    return ms
+
+
+def kernel_breakdown(step, n=5):
+    """Device time per C-ABI entry point over `n` steps, CUDA events around every launch (instrumented pass, not the timed
+    region).  Returns {name: (ms per step, launches per step)}."""
+    from gridmm_b200 import _lib
+    orig = _lib.call
+    rec = []
+
+    def call(name, *a):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(name, *a)
+        e.record()
+        rec.append((name, s, e))
+
+    _lib.call = call
+    graphed = step.model.use_cuda_graph
+    step.model.use_cuda_graph = False          # per-launch events need eager launches
+    try:
+        step.run_resident()
+        torch.cuda.synchronize()
+        del rec[:]
+        for _ in range(n):
+            step.run_resident()
+        torch.cuda.synchronize()
+    finally:
+        _lib.call = orig
+        step.model.use_cuda_graph = graphed
+    agg = {}
+    for name, s, e in rec:
+        t, c = agg.get(name, (0.0, 0))
+        agg[name] = (t + s.elapsed_time(e), c + 1)
+    return {k: (t / n, c / n) for k, (t, c) in agg.items()}
+
+
+def gemm_flops_per_step():
+    """Algorithmic FLOPs (2mnk) of every gridmm_linear_f16 launch of one step (padded shapes as launched: S = 196 + G)."""
+    H, I = 768, 3072
+    S, Q, KC = 196 + G, G + 1 + VIEWS, 196 + G + L
+    mm = lambda m, n, k: 2.0 * m * n * k   # noqa: E731
+    f = mm(B * L, H, H) + mm(B * 196, H, H)                                            # text_proj, grid_proj
+    f += mm(B * S, 3 * H, H) + mm(B * S, H, H) + mm(B * S, I, H) + mm(B * S, H, I)      # grid_encoder
+    f += mm(B * L, 2 * H, H) + mm(B * S, H, H) * 2 + mm(B * S, 3 * H, H) + mm(B * S, H, H) + mm(B * S, I, H) + mm(B * S, H, I)
+    f += mm(B * KC, 8 * H, H)                                                            # fusion K/V of 4 layers
+    f += 4 * (mm(B * Q, H, H) * 2 + mm(B * Q, 3 * H, H) + mm(B * Q, H, H) + mm(B * Q, I, H) + mm(B * Q, H, I))
+    f += mm(B * G, H, H) * 2 + mm(B * (1 + VIEWS), H, H) + mm(B, H, 2 * H)               # heads
+    return f
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gridmm_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    from gridmm_b200 import _lib
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to produce samples
+    step = Step(dev, seed=rank)
+    step.run_resident()
+    torch.cuda.synchronize()
+
+    # kernels per step, counted on one eager step (graph replays do not pass through the C-ABI launch counter)
+    step.model.use_cuda_graph = False
+    _lib.launch_count_reset()
+    step.run_resident()
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count()
+    step.model.use_cuda_graph = True
+    step.run_resident()
+    torch.cuda.synchronize()
+
+    t_w0 = time.time()
+    ms = timed(step.run_resident, args.steps, warmup, world)
+    t_w1 = time.time()
+    launches = launches_per_step * args.steps
+    ms_e2e = timed(step.run_e2e, args.steps, warmup, world)
+    clocks = None
+    if sampler:
+        window = "timed region"
+        if t_w1 - t_w0 < 0.5:
+            # the timed region is shorter than nvidia-smi's sampling period: keep the same loop running for 1.5 s more
+            t_c0 = time.time()
+            while time.time() - t_c0 < 1.5:
+                step.run_resident()
+            torch.cuda.synchronize()
+            t_w1 = time.time()
+            window = "timed region + 1.5 s continuation of the same loop (region shorter than the sampling period)"
+        clocks = sampler.stop(t_w0, t_w1)
+        clocks["window"] = window
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d, d2h = step.e2e_bytes()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        br = kernel_breakdown(step)
+        total_k = sum(t for t, _ in br.values())
+        # dominant kernel by share of the step: the tcgen05 GEMM
+        g_ms, g_n = br.get("gridmm_linear_f16", (0.0, 0))
+        flops = gemm_flops_per_step()
+        tf = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        roofline = {"kernel": "gemm_f16_tn_kernel (gridmm_linear_f16, %d launches/step)" % round(g_n), "bound": "tensor",
+                    "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
+                    "peak_source": peak_src + ", sustained bf16/fp16 dense", "share_of_step": g_ms / total_k if total_k else None}
+        # the HBM-bound pooling kernel (north_star's "grid scatter/pool"): bytes that must move / its duration
+        p_ms, _ = br.get("gridmm_pool", (0.0, 0))
+        gridb = step.builder
+        nv = int(gridb.cell_start[:, -1].sum().item()); ne = int(gridb.n_nonempty.sum().item())
+        pbytes = nv * 768 * 2 + B * L * 768 * 2 + ne * 768 * 2 + nv * 4
+        gbs = pbytes / (p_ms * 1e-3) / 1e9 if p_ms > 0 else 0.0
+        roofline_pool = {"kernel": "pool_kernel<768> (gridmm_pool)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "algorithmic_bytes": pbytes,
+                         "valid_rows": nv, "ms": p_ms, "peak_source": peak_src}
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            best, mean = cpu_reference_steps(step.ep, step.nav_np, step.cfg, _weights()[1], 2, threads)
+            cpu = {"value": B / mean, "unit": "nav-steps/s", "cores": threads, "kind": "port",
+                   "sample": "2 steps of the same B=32, T=8 workload after 1 warm-up (oracle/ port of the reference algorithm)"}
+        line = {"metric": METRIC, "value": value, "unit": "nav-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate (grid cell ids: f32 + int, bit-exact)", "data": "synthetic",
+                "config": CONFIG, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "nav-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_pool": roofline_pool, "cpu_baseline": cpu,
+                "kernel_ms_per_step": {k: round(t, 4) for k, (t, _) in sorted(br.items(), key=lambda kv: -kv[1][0])}}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,34 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const float* x, int ldx,
     store_row(v, o32 ? o32 + orow * ld32 : nullptr, o16 ? o16 + orow * ld16 : nullptr, lane);
 }
 
+// ------------------------------------------------------------------------------------------- fp32 -> (hi, lo) fp16 split
+// out[b, r] = [ hi | lo | hi ] at column blocks 0, k_total, 2*k_total (each 768 wide at the given column offset), where
+// hi = fp16(x), lo = fp16(x - hi).  Against weights laid out [Wh | Wh | Wl] a single K-concatenated GEMM then computes
+// xh.Wh + xl.Wh + xh.Wl = x.W to ~2^-22 -- used for the tiny ClsPrediction GEMMs, whose fp16 rounding would otherwise
+// dominate the logit error (numerics).
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* x, int ldx, int in_rows_per_b, int in_off, __half* o16,
+                                                         int ld16, int k_total, int rows_per_b, int rows) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int b = row / rows_per_b, r = row - b * rows_per_b;
+    const size_t irow = static_cast<size_t>(b) * in_rows_per_b + in_off + r;
+    __half* o = o16 + static_cast<size_t>(row) * ld16;
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + irow * ldx + col);
+        const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+        uint2 hi, lo;
+        hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(o + col) = hi;
+        *reinterpret_cast<uint2*>(o + k_total + col) = lo;
+        *reinterpret_cast<uint2*>(o + 2 * k_total + col) = hi;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- position embeddings
 // out[b, off + r] = base[b, r] + table[idx[b, r]] + LN(W f[b, r] + bias)      (base / table optional)
 struct EmbedParams {
@@ -325,6 +353,19 @@ extern "C" int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int 
     copy_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, in_rows_per_b, in_off, out_f32, ld_f32,
                                                          reinterpret_cast<__half*>(out_f16), ld_f16, out_rows_per_b, out_off,
                                                          rows_per_b, rows);
+    gridmm_count_launch(1);
+    return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int gridmm_split_rows(const float* x, int ldx, int in_rows_per_b, int in_off, void* out_f16, int ld_f16,
+                                 int k_total, int rows_per_b, int batch, int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    const int rows = rows_per_b * batch;
+    if (rows <= 0) return 0;
+    if (hidden != HID || (ldx % 4) || (ld_f16 % 4) || (k_total % 4) || ld_f16 < 3 * k_total) return GRIDMM_ERR_SHAPE;
+    if (!x || !out_f16) return GRIDMM_ERR_ARG;
+    split_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, in_rows_per_b, in_off, reinterpret_cast<__half*>(out_f16),
+                                                          ld_f16, k_total, rows_per_b, rows);
     gridmm_count_launch(1);
     return static_cast<int>(cudaGetLastError());
 }

@@ -115,11 +115,13 @@ class GridMapBuilder:
         # per-step staging (pinned host -> device)
         self.h_depth_u16 = torch.empty(B, PTS, dtype=torch.int16).pin_memory()
         self.h_depth_f32 = torch.empty(B, PTS, dtype=torch.float32).pin_memory()
-        self.h_pose = torch.empty(B, 4 + 24, dtype=torch.float32).pin_memory()     # pose[4] ++ view_cs[12*2]
+        self.h_pose = torch.empty(B, 4, dtype=torch.float32).pin_memory()
+        self.h_view = torch.empty(B, 24, dtype=torch.float32).pin_memory()         # view_cs[12*2]
         self.h_clip = torch.empty(B, 12, VIEW_TOKENS, self.feat_dim, dtype=torch.float16).pin_memory()
         self.d_depth_u16 = torch.empty(B, PTS, dtype=torch.int16, device=dev)
         self.d_depth_f32 = torch.empty(B, PTS, dtype=torch.float32, device=dev)
-        self.d_pose = torch.empty(B, 4 + 24, dtype=torch.float32, device=dev)
+        self.d_pose = torch.empty(B, 4, dtype=torch.float32, device=dev)
+        self.d_view = torch.empty(B, 24, dtype=torch.float32, device=dev)
         self.new_episodes()
 
     # ------------------------------------------------------------------ buffers
@@ -193,8 +195,8 @@ class GridMapBuilder:
                                       "the reference re-adds the last viewpoint of ended episodes, so do that")
         t = int(self.n_steps[0])
         # features: one contiguous copy into slab[t]
-        if isinstance(clip, torch.Tensor) and clip.is_cuda:
-            self.slab[t].copy_(clip.reshape(B, 12 * VIEW_TOKENS, self.feat_dim))
+        if isinstance(clip, torch.Tensor) and (clip.is_cuda or clip.is_pinned()):
+            self.slab[t].copy_(clip.reshape(B, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
         else:
             self.h_clip.copy_(torch.as_tensor(clip).reshape(self.h_clip.shape))
             self.slab[t].copy_(self.h_clip.view(B, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
@@ -210,14 +212,12 @@ class GridMapBuilder:
             self.h_depth_u16.copy_(torch.from_numpy(arr.view(np.int16)))
             self.d_depth_u16.copy_(self.h_depth_u16, non_blocking=True)
             d_depth = self.d_depth_u16
-        self.h_pose.copy_(torch.from_numpy(self.host_pose(pos_xy, heading)))
+        hp = self.host_pose(pos_xy, heading)
+        self.h_pose.copy_(torch.from_numpy(hp[:, :4]))
+        self.h_view.copy_(torch.from_numpy(hp[:, 4:]))
         self.d_pose.copy_(self.h_pose, non_blocking=True)
-        pose = self.d_pose[:, :4]
-        view_cs = self.d_pose[:, 4:]
-        # gridmm_grid_update reads pose with row pitch 4 and view_cs with pitch 24: hand it packed copies
-        self._pose4 = pose.contiguous()
-        self._view24 = view_cs.contiguous()
-        ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self._pose4, self._view24, None, g.off7, g.flip_y,
+        self.d_view.copy_(self.h_view, non_blocking=True)
+        ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, None, g.off7, g.flip_y,
                         g.negate_map_x, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
                         self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
         self.n_steps += 1

@@ -236,6 +236,8 @@ class GlocalTextPathNavCMT(nn.Module):
         self._w16 = {}
         self._w16_versions = None
         self._ws = {}
+        self._graphs = {}
+        self.use_cuda_graph = False
 
     def _register(self, dotted, param):
         mod = self
@@ -260,6 +262,7 @@ class GlocalTextPathNavCMT(nn.Module):
             return
         self._w16 = {}
         self._w16_versions = (vers, dev)
+        self._graphs = {}          # captured graphs hold pointers into the old fp16 weight copies
 
     def W16(self, *names):
         """fp16 copy of a weight, or of several weights concatenated along the output dimension (fused QKV etc.)."""
@@ -269,6 +272,19 @@ class GlocalTextPathNavCMT(nn.Module):
             with torch.no_grad():
                 parts = [self.P(n).detach() for n in names]
                 w = (parts[0] if len(parts) == 1 else torch.cat(parts, 0)).to(torch.float16).contiguous()
+            self._w16[key] = w
+        return w
+
+    def W16split(self, name):
+        """[Wh | Wh | Wl] along K (Wh = fp16(W), Wl = fp16(W - Wh)): the weight side of the split-precision head GEMMs."""
+        key = ("split", name)
+        w = self._w16.get(key)
+        if w is None:
+            with torch.no_grad():
+                w32 = self.P(name).detach().float()
+                hi = w32.to(torch.float16)
+                lo = (w32 - hi.float()).to(torch.float16)
+                w = torch.cat([hi, hi, lo], 1).contiguous()
             self._w16[key] = w
         return w
 
@@ -347,19 +363,30 @@ class GlocalTextPathNavCMT(nn.Module):
             ops.linear(h, self.W16(q + ".linear2.weight"), self.B32(q + ".linear2.bias"), residual=x32, out_f32=x32)
         self._ln(x32, pre + ".norm", 1e-12, x32, x16)
 
-    def _cls_head(self, pre, x16, rows, tag):
-        """ClsPrediction (vilmodel.py:663-674) -> raw logit per row."""
+    def _cls_head(self, pre, xs16, rows, tag):
+        """ClsPrediction (vilmodel.py:663-674) -> raw logit per row.  `xs16` is the [hi | lo | hi] split of the fp32 input
+        (ops.split_rows), so the first Linear is evaluated to ~fp32 accuracy on the fp16 tensor cores."""
         h = self.buf("cls32_" + tag, (rows, HID), torch.float32)
-        ops.linear(x16, self.W16(pre + ".net.0.weight"), self.B32(pre + ".net.0.bias"), out_f32=h, act=ops.ACT_RELU)
+        ops.linear(xs16, self.W16split(pre + ".net.0.weight"), self.B32(pre + ".net.0.bias"), out_f32=h, act=ops.ACT_RELU)
         out = self.buf("cls_out_" + tag, (rows,), torch.float32)
         ops.cls_tail(h, self.P(pre + ".net.2.weight"), self.P(pre + ".net.2.bias"), self.P(pre + ".net.3.weight"),
                      self.P(pre + ".net.3.bias"), out)
         return out
 
-    # ------------------------------------------------------------------ grid inputs
+    # ------------------------------------------------------------------ inputs -> persistent device buffers
+    def _stage(self, name, src, shape, dtype):
+        """Copy one input into a persistent device buffer (H2D from pinned memory or D2D; dtype conversion included), so
+        that the device part of the forward only ever sees static addresses (CUDA-graph capturable)."""
+        dst = self.buf("in_" + name, shape, dtype)
+        src = torch.as_tensor(src)
+        if src.dtype == torch.bool:
+            src = src.view(torch.uint8) if src.is_contiguous() else src.to(torch.uint8)
+        dst.copy_(src.reshape(shape), non_blocking=True)
+        return dst
+
     def _grid_from_reference_lists(self, grid_fts, grid_map, gridmap_pos_fts):
         """Drop-in path: the reference's per-episode lists (r2r/agent.py:163-169) -> the device layout of GridBatch.
-        Copies the whole accumulated map (as the reference's `.cuda()` does every step)."""
+        Copies the whole accumulated map (as the reference's `.cuda()` does every step), then sorts by cell."""
         B = len(grid_fts)
         dev = next(self.parameters()).device
         n = [int(x.shape[0]) for x in grid_fts]
@@ -368,18 +395,20 @@ class GlocalTextPathNavCMT(nn.Module):
         t_cap = max(max(n) // 588, 1)
         cap = t_cap * 588
         D = int(grid_fts[0].shape[1])
+        nc = self.config.grid_w ** 2
         slab = self.buf("compat_slab", (B * t_cap * 588, D), torch.float16)
         cell = self.buf("compat_cell", (B, cap), torch.int16)
         cell.fill_(-1)
         for b in range(B):
-            slab[b * cap: b * cap + n[b]].copy_(torch.as_tensor(grid_fts[b]).to(dev, torch.float16), non_blocking=True)
-            cell[b, :n[b]].copy_(torch.as_tensor(grid_map[b]).to(dev).to(torch.int16), non_blocking=True)
-        n_pts = torch.tensor(n, dtype=torch.int32).to(dev)
-        slots = (torch.arange(B, dtype=torch.int32)[:, None] * t_cap + torch.arange(t_cap, dtype=torch.int32)[None, :])
-        nc = self.config.grid_w ** 2
+            slab[b * cap: b * cap + n[b]].copy_(torch.as_tensor(grid_fts[b]), non_blocking=True)
+            cell[b, :n[b]].copy_(torch.as_tensor(grid_map[b]), non_blocking=True)      # float64 ids -> int16
+        n_pts = self.buf("compat_npts", (B,), torch.int32)
+        n_pts.copy_(torch.tensor(n, dtype=torch.int32), non_blocking=True)
+        slots = self.buf("compat_slots", (B, t_cap), torch.int32)
+        slots.copy_(torch.arange(B, dtype=torch.int32)[:, None] * t_cap + torch.arange(t_cap, dtype=torch.int32)[None, :])
         gb = GridBatch.__new__(GridBatch)
         gb.batch, gb.feat_dim, gb.grid_w, gb.n_cells = B, D, self.config.grid_w, nc
-        gb.slab, gb.slots, gb.t_cap = slab, slots.contiguous().to(dev), t_cap
+        gb.slab, gb.slots, gb.t_cap = slab, slots, t_cap
         gb.slot_rows, gb.view_rows, gb.tok_off = 588, 49, 0
         gb.cap = cap
         gb.perm = self.buf("compat_perm", (B, cap), torch.int32)
@@ -387,35 +416,85 @@ class GlocalTextPathNavCMT(nn.Module):
         gb.cell_rank = self.buf("compat_cr", (B, nc), torch.int32)
         gb.n_nonempty = self.buf("compat_ne", (B,), torch.int32)
         gb.cell, gb.n_pts = cell, n_pts
-        gb.pos_fts = torch.as_tensor(gridmap_pos_fts).to(dev, torch.float32).contiguous()
+        gb.pos_fts = self._stage("compat_pos_fts", gridmap_pos_fts, (B, nc, 5), torch.float32)
         ops.cell_sort(B, cell, n_pts, self.config.grid_w, cap, gb.perm, gb.cell_start, gb.cell_rank, gb.n_nonempty)
         return gb
 
     # ------------------------------------------------------------------ navigation
+    def enable_cuda_graph(self, flag=True):
+        """Replay the device part of forward('navigation') from a CUDA graph (one per input-shape signature).  Outputs then
+        live in persistent buffers that the next call overwrites."""
+        self.use_cuda_graph = bool(flag)
+        self._graphs = {}
+        return self
+
     @torch.no_grad()
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                     gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
                                     vp_nav_masks, vp_obj_masks, vp_cand_vpids, grid_fts, grid_map, gridmap_pos_fts,
                                     grid=None, return_intermediates=False):
         """vilmodel.py:782-918.  `grid` (a gridmm_b200.env.GridBatch) replaces grid_fts/grid_map/gridmap_pos_fts when the
-        grid was built on the device; otherwise the reference-format lists are uploaded and sorted first."""
+        grid was built on the device; otherwise the reference-format lists are uploaded and sorted first.
+        (`gmap_pair_dists` is accepted and ignored, as in the reference's navigation forward.)"""
         self._refresh_w16()
-        cfg = self.config
         if grid is None:
             grid = self._grid_from_reference_lists(grid_fts, grid_map, gridmap_pos_fts)
-        B, L = txt_embeds.shape[0], txt_embeds.shape[1]
-        G, V = gmap_img_embeds.shape[1], vp_img_embeds.shape[1]
+        B, L = int(txt_embeds.shape[0]), int(txt_embeds.shape[1])
+        G, V = int(gmap_img_embeds.shape[1]), int(vp_img_embeds.shape[1])
+        has_obj = vp_obj_masks is not None
+        f32, u8 = torch.float32, torch.uint8
+        # host part of the logit fusion (the reference's vpid-string loops) -> small int arrays
+        fuse_src, bw_mask = build_fuse_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, G, V)
+        st = {
+            "txt": self._stage("txt", txt_embeds, (B * L, HID), f32),
+            "txt_mask": self._stage("txt_mask", txt_masks, (B, L), u8),
+            "gmap_img": self._stage("gmap_img", gmap_img_embeds, (B * G, HID), f32),
+            "gmap_step": self._stage("gmap_step", gmap_step_ids, (B * G,), torch.int64),
+            "gmap_pos": self._stage("gmap_pos", gmap_pos_fts, (B * G, int(gmap_pos_fts.shape[-1])), f32),
+            "gmap_mask": self._stage("gmap_mask", gmap_masks, (B, G), u8),
+            "gmap_visited": self._stage("gmap_visited", gmap_visited_masks, (B, G), u8),
+            "vp_img": self._stage("vp_img", vp_img_embeds, (B * V, HID), f32),
+            "vp_pos": self._stage("vp_pos", vp_pos_fts, (B * V, int(vp_pos_fts.shape[-1])), f32),
+            "vp_mask": self._stage("vp_mask", vp_masks, (B, V), u8),
+            "vp_nav": self._stage("vp_nav", vp_nav_masks, (B, V), u8),
+            "vp_obj": self._stage("vp_obj", vp_obj_masks, (B, V), u8) if has_obj else None,
+            "fuse_src": self._stage("fuse_src", torch.from_numpy(fuse_src), (B, G), torch.int32),
+            "bw_mask": self._stage("bw_mask", torch.from_numpy(bw_mask), (B, V), u8),
+        }
+        dims = (B, L, G, V, has_obj)
+        if getattr(self, "use_cuda_graph", False) and not return_intermediates:
+            sig = dims + (st["gmap_pos"].shape[1], st["vp_pos"].shape[1], grid.n_cells, grid.t_cap, grid.cap, grid.feat_dim,
+                          grid.slot_rows, grid.view_rows, grid.tok_off, grid.slab.data_ptr(), grid.slots.data_ptr(),
+                          grid.perm.data_ptr(), grid.cell_start.data_ptr(), grid.pos_fts.data_ptr())
+            entry = self._graphs.get(sig)
+            if entry is None:
+                self._device_forward(st, grid, dims, False, True)          # warm-up: allocates every workspace
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    outs = self._device_forward(st, grid, dims, False, True)
+                entry = (g, outs)
+                self._graphs[sig] = entry
+            entry[0].replay()
+            return dict(entry[1])
+        return self._device_forward(st, grid, dims, return_intermediates, False)
+
+    def _out(self, name, shape, static):
+        dev = next(self.parameters()).device
+        return self.buf("out_" + name, shape, torch.float32) if static else torch.empty(shape, dtype=torch.float32, device=dev)
+
+    def _device_forward(self, st, grid, dims, return_intermediates, static_out):
+        """Everything below launches only gridmm_* kernels (plus a few tiny mask copies) on persistent buffers."""
+        cfg = self.config
+        B, L, G, V, has_obj = dims
         NC = grid.n_cells
         S, Q, KC = NC + G, G + V, NC + G + L
         f16, f32, u8 = torch.float16, torch.float32, torch.uint8
-        txt_embeds = txt_embeds.contiguous().float()
-        txt_mask_u8 = txt_masks.contiguous().view(u8) if txt_masks.dtype == torch.bool else txt_masks.to(u8)
-        gmap_mask_u8 = gmap_masks.contiguous().view(u8) if gmap_masks.dtype == torch.bool else gmap_masks.to(u8)
-        vp_mask_u8 = vp_masks.contiguous().view(u8) if vp_masks.dtype == torch.bool else vp_masks.to(u8)
+        txt32, txt_mask_u8, gmap_mask_u8, vp_mask_u8 = st["txt"], st["txt_mask"], st["gmap_mask"], st["vp_mask"]
 
         # ---- text_proj + relevance pooling + grid_proj (vilmodel.py:793-807)
         txt16 = self.buf("txt16", (B * L, HID), f16)
-        ops.copy_rows(txt_embeds.view(B * L, HID), L, 0, L, B, L, 0, out_f16=txt16)
+        ops.copy_rows(txt32, L, 0, L, B, L, 0, out_f16=txt16)
         l_pad = (L + 7) // 8 * 8
         tp16 = self.buf("tp16", (B * l_pad, HID), f16)
         if l_pad == L:
@@ -442,16 +521,14 @@ class GlocalTextPathNavCMT(nn.Module):
                           self.P("grid_pos_embeddings.1.bias"), map32, map_mask, B, NC, S)
         map_mask[:, NC:].copy_(gmap_mask_u8)
         ge = "global_encoder.gmap_pos_embeddings"
-        ops.pos_embed(gmap_pos_fts.contiguous().view(B * G, -1).float(), self.P(ge + ".0.weight"), self.P(ge + ".0.bias"),
-                      self.P(ge + ".1.weight"), self.P(ge + ".1.bias"), 1e-12, map32, None, G, S, NC,
-                      base=gmap_img_embeds.contiguous().view(B * G, HID).float(),
-                      table=self.P("global_encoder.gmap_step_embeddings.weight"), idx=gmap_step_ids.contiguous().view(-1))
-        x32 = torch.empty(B * Q, HID, dtype=f32, device=map32.device)     # escapes as gmap_embeds / vp_embeds
+        ops.pos_embed(st["gmap_pos"], self.P(ge + ".0.weight"), self.P(ge + ".0.bias"), self.P(ge + ".1.weight"),
+                      self.P(ge + ".1.bias"), 1e-12, map32, None, G, S, NC, base=st["gmap_img"],
+                      table=self.P("global_encoder.gmap_step_embeddings.weight"), idx=st["gmap_step"])
+        x32 = self._out("x32", (B * Q, HID), static_out)       # escapes as gmap_embeds / vp_embeds
         x16 = self.buf("x16", (B * Q, HID), f16)
         ve = "local_encoder.vp_pos_embeddings"
-        ops.pos_embed(vp_pos_fts.contiguous().view(B * V, -1).float(), self.P(ve + ".0.weight"), self.P(ve + ".0.bias"),
-                      self.P(ve + ".1.weight"), self.P(ve + ".1.bias"), 1e-12, x32, x16, V, Q, G,
-                      base=vp_img_embeds.contiguous().view(B * V, HID).float())
+        ops.pos_embed(st["vp_pos"], self.P(ve + ".0.weight"), self.P(ve + ".0.bias"), self.P(ve + ".1.weight"),
+                      self.P(ve + ".1.bias"), 1e-12, x32, x16, V, Q, G, base=st["vp_img"])
 
         # ---- grid_encoder (pre-norm, key_padding_mask) and grid_txt_encoder (vilmodel.py:840-841)
         self._prenorm_encoder("grid_encoder", 1, map32, map16, map_mask, B, S, "map")
@@ -469,7 +546,7 @@ class GlocalTextPathNavCMT(nn.Module):
         ops.copy_rows(map32, S, NC, G, B, Q, 0, out_f32=x32, out_f16=x16)
         kv16 = self.buf("kv16", (B * KC, HID), f16)
         ops.copy_rows(map32, S, 0, S, B, KC, 0, out_f16=kv16)
-        ops.copy_rows(txt_embeds.view(B * L, HID), L, 0, L, B, KC, S, out_f16=kv16)
+        ops.copy_rows(txt32, L, 0, L, B, KC, S, out_f16=kv16)
         kv_mask = self.buf("kv_mask", (B, KC), u8)
         kv_mask[:, :S].copy_(map_mask)
         kv_mask[:, S:].copy_(txt_mask_u8)
@@ -489,39 +566,30 @@ class GlocalTextPathNavCMT(nn.Module):
                              kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], kv_mask, B, Q, KC, "x")
 
         # ---- heads and logit fusion (vilmodel.py:859-907)
-        hg16 = self.buf("hg16", (B * G, HID), f16)
-        hv16 = self.buf("hv16", (B * V, HID), f16)
-        hm16 = self.buf("hm16", (B * G, HID), f16)
-        ops.copy_rows(x32, Q, 0, G, B, G, 0, out_f16=hg16)
-        ops.copy_rows(x32, Q, G, V, B, V, 0, out_f16=hv16)
-        ops.copy_rows(map32, S, NC, G, B, G, 0, out_f16=hm16)
+        hg16 = self.buf("hg16", (B * G, 3 * HID), f16)
+        hv16 = self.buf("hv16", (B * V, 3 * HID), f16)
+        hm16 = self.buf("hm16", (B * G, 3 * HID), f16)
+        ops.split_rows(x32, Q, 0, G, B, hg16, HID)
+        ops.split_rows(x32, Q, G, V, B, hv16, HID)
+        ops.split_rows(map32, S, NC, G, B, hm16, HID)
         raw_global = self._cls_head("global_sap_head", hg16, B * G, "g")
         raw_local = self._cls_head("local_sap_head", hv16, B * V, "l")
         raw_grid = self._cls_head("grid_sap_head", hm16, B * G, "m")
         raw_fuse = None
         if cfg.glocal_fuse:
-            hf16 = self.buf("hf16", (B, 2 * HID), f16)
-            ops.copy_rows(x32, Q, 0, 1, B, 1, 0, out_f16=hf16)
-            ops.copy_rows(x32, Q, G, 1, B, 1, 0, out_f16=hf16[:, HID:])
+            hf16 = self.buf("hf16", (B, 6 * HID), f16)             # [gmap0; vp0] -> K = 1536, split -> 3 * 1536
+            ops.split_rows(x32, Q, 0, 1, B, hf16, 2 * HID)
+            ops.split_rows(x32, Q, G, 1, B, hf16[:, HID:], 2 * HID)
             raw_fuse = self._cls_head("sap_fuse_linear", hf16, B, "f")
-        has_obj = vp_obj_masks is not None
         raw_obj = self._cls_head("og_head", hv16, B * V, "o") if has_obj else None
-        fuse_src, bw_mask = build_fuse_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, G, V)
-        dev = map32.device
-        fuse_src_d = torch.from_numpy(fuse_src).to(dev, non_blocking=True)
-        bw_mask_d = torch.from_numpy(bw_mask).to(dev, non_blocking=True)
-        vis_u8 = gmap_visited_masks.contiguous().view(u8) if gmap_visited_masks.dtype == torch.bool else gmap_visited_masks.to(u8)
-        nav_u8 = vp_nav_masks.contiguous().view(u8) if vp_nav_masks.dtype == torch.bool else vp_nav_masks.to(u8)
-        obj_u8 = None
-        if has_obj:
-            obj_u8 = vp_obj_masks.contiguous().view(u8) if vp_obj_masks.dtype == torch.bool else vp_obj_masks.to(u8)
-        global_logits = torch.empty(B, G, dtype=f32, device=dev)
-        grid_logits = torch.empty(B, G, dtype=f32, device=dev)
-        local_logits = torch.empty(B, V, dtype=f32, device=dev)
-        fused_logits = torch.empty(B, G, dtype=f32, device=dev)
-        obj_logits = torch.empty(B, V, dtype=f32, device=dev) if has_obj else None
-        ops.nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_mask_u8, vis_u8, nav_u8, obj_u8, fuse_src_d,
-                       bw_mask_d, global_logits, grid_logits, local_logits, fused_logits, obj_logits, B, G, V)
+        global_logits = self._out("global_logits", (B, G), static_out)
+        grid_logits = self._out("grid_logits", (B, G), static_out)
+        local_logits = self._out("local_logits", (B, V), static_out)
+        fused_logits = self._out("fused_logits", (B, G), static_out)
+        obj_logits = self._out("obj_logits", (B, V), static_out) if has_obj else None
+        ops.nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_mask_u8, st["gmap_visited"], st["vp_nav"],
+                       st["vp_obj"], st["fuse_src"], st["bw_mask"], global_logits, grid_logits, local_logits, fused_logits,
+                       obj_logits, B, G, V)
         x3 = x32.view(B, Q, HID)
         outs = {
             "gmap_embeds": x3[:, :G], "vp_embeds": x3[:, G:],

@@ -62,6 +62,13 @@ def copy_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_rows_per_b, out_o
               out_rows_per_b, out_off, rows_per_b, batch, x.shape[1], _lib.stream_ptr())
 
 
+def split_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_f16, k_total):
+    """out_f16[b*rows_per_b + r] = [hi | lo | hi](x[b, in_off + r]) at column blocks 0, k_total, 2*k_total."""
+    _chk(x, torch.float32, "x"); _chk(out_f16, torch.float16, "out_f16")
+    _lib.call("gridmm_split_rows", x.data_ptr(), x.stride(0), in_rows_per_b, in_off, out_f16.data_ptr(), out_f16.stride(0),
+              k_total, rows_per_b, batch, x.shape[1], _lib.stream_ptr())
+
+
 def pos_embed(feat, w, bias, gamma, beta, eps, out_f32, out_f16, in_rows_per_b, out_rows_per_b, out_row_off,
               base=None, table=None, idx=None):
     _chk(feat, torch.float32, "feat"); _chk(base, torch.float32, "base"); _chk(table, torch.float32, "table")

@@ -102,6 +102,12 @@ int gridmm_layernorm(const float* x, int ldx, const float* gamma, const float* b
 int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int in_off, float* out_f32, int ld_f32, void* out_f16,
                      int ld_f16, int out_rows_per_b, int out_off, int rows_per_b, int batch, int hidden, cudaStream_t stream);
 
+/* out[b*rows_per_b + r] = [hi | lo | hi] of in[b, in_off + r] at column blocks 0, k_total, 2*k_total (hi = fp16(x),
+ * lo = fp16(x - hi)): with weights [Wh | Wh | Wl] one K-concatenated gridmm_linear_f16 evaluates x.W to ~2^-22.
+ * Used for the ClsPrediction GEMMs (vilmodel.py:663-674), where plain fp16 rounding dominates the logit error. */
+int gridmm_split_rows(const float* x, int ldx, int in_rows_per_b, int in_off, void* out_f16, int ld_f16, int k_total,
+                      int rows_per_b, int batch, int hidden, cudaStream_t stream);
+
 /* out[b, off + r] = base + table[idx] + LayerNorm(Linear(kin -> 768)(feat))   (vilmodel.py:828-833) */
 int gridmm_pos_embed(const float* feat, int kin, const float* w, const float* bias, const float* gamma, const float* beta,
                      float eps, const float* base, const float* table, const long long* idx, float* out_f32, void* out_f16,
