@@ -281,8 +281,11 @@ def kernel_breakdown(step, n=5):
         torch.cuda.synchronize()
         del rec[:]
         for _ in range(n):
+            # park the GPU behind a ~3 ms spin so the host runs ahead and every launch is already queued: the event
+            # deltas are then device execution times, not host launch latencies
+            torch.cuda._sleep(6_000_000)
             step.run_resident()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
     finally:
         _lib.call = orig
         step.model.use_cuda_graph = graphed

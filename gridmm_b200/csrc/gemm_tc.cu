@@ -5,10 +5,15 @@
 // nn.MultiheadAttention in/out projections + linear1/linear2 (map_nav_src/models/transformer.py:133-182),
 // ClsPrediction first layer (vilmodel.py:663-674), text_proj/grid_proj (:702-703).
 //
-// Structure (one 128 x BN output tile per CTA, 6 warps):
-//   warp 0      TMA producer: 128x64 A tile + BNx64 W tile per stage, SWIZZLE_128B, mbarrier complete_tx
-//   warp 1      allocates TMEM, issues tcgen05.mma (one thread), commits stages back to the producer
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns, bias / GELU / ReLU / residual, fp32 and/or fp16 stores
+// Structure: persistent CTAs (one per SM), 128 x BN output tiles (BN = 128 or 256) handed out round-robin, 6 warps:
+//   warp 0      TMA producer: 128x64 A tile + BNx64 W tile per stage, SWIZZLE_128B, mbarrier complete_tx; the stage ring
+//               runs straight across tile boundaries
+//   warp 1      allocates TMEM (2 accumulators of BN columns), issues tcgen05.mma (one thread), commits smem stages back
+//               to the producer and finished accumulators to the epilogue
+//   warps 2..9  epilogue (two warps per TMEM lane quadrant, half of the columns each): the tile's bias slice is staged in
+//               shared memory and the first residual chunks are already in flight BEFORE the accumulator is ready;
+//               tcgen05.ld 32 lanes x 16 columns, bias / GELU / ReLU / residual (register-pipelined 4 chunks deep),
+//               fp32 and/or fp16 stores; accumulator t is drained while the MMA warp is already filling t+1
 #include "common.cuh"
 #include "host_util.h"
 
@@ -16,7 +21,9 @@ namespace gmm {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;       // 2 per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
+constexpr int GEMM_RES_PREFETCH = 4;    // residual chunks (16 columns each) kept in flight per epilogue thread
 
 struct GemmEpilogue {
     const float* bias;       // [N] or null
@@ -33,8 +40,13 @@ struct GemmSmem {
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem slot + alignment slack
+    static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;   // [2][BN] floats
+    static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;  // barriers + tmem slot + bias + alignment slack
 };
+
+__device__ __forceinline__ void named_bar_sync_epi() {
+    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -45,14 +57,16 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * GEMM_BM;
     const int num_kb = K / GEMM_BK;
+    const int tiles_n = N / BN;
+    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int num_tiles = tiles_m * tiles_n;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -61,10 +75,13 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);
+        }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -72,93 +89,134 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* a_dst = smem + s * L::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + L::A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-                tma_load_2d(a_dst, &tmA, kb * GEMM_BK, m0, &full_bar[s]);
-                tma_load_2d(b_dst, &tmW, kb * GEMM_BK, n0, &full_bar[s]);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + L::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                    tma_load_2d(a_dst, &tmA, kb * GEMM_BK, m0, &full_bar[s]);
+                    tma_load_2d(b_dst, &tmW, kb * GEMM_BK, n0, &full_bar[s]);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const int acc = t & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-                const uint64_t da = umma_desc_sw128_kmajor(a_addr);
-                const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES);
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                    const uint64_t da = umma_desc_sw128_kmajor(a_addr);
+                    const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k) {
-                    // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
-                    umma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
+                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&empty_bar[s]);
+                umma_commit(&tmem_full_bar[acc]);
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
-        // epilogue warps: TMEM lane quadrant is fixed by warp id % 4
+        // epilogue warps: TMEM lane quadrant is fixed by warp id % 4; warps 2..5 take columns [0, BN/2), 6..9 the rest
+        constexpr int HALF = BN / 2, NCH = HALF / 16, PD = GEMM_RES_PREFETCH;
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const bool row_ok = row < M;
-#pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 16, v);
-            tmem_ld_wait();
-            if (!row_ok) continue;
-            const int col = n0 + c * 16;
-            float f[16];
+        const int half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;                  // 0..255
+        float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+        int t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            const int acc = t & 1;
+            const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < M;
+            // stage this tile's bias slice (the slot of tile t-2 is free: all warps passed the barrier of tile t-1)
+            float* sb = s_bias + acc * BN;
+            for (int i = et; i < BN; i += GEMM_EPI_WARPS * 32) sb[i] = ep.bias ? __ldg(ep.bias + n0 + i) : 0.0f;
+            // residual chunks in flight before the accumulator is even ready
+            const int col0 = n0 + half * HALF;
+            const float* rrow = ep.residual ? ep.residual + static_cast<size_t>(row_ok ? row : 0) * ep.ld_res + col0 : nullptr;
+            float4 res[PD][4];
+            if (rrow) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            if (ep.bias) {
+                for (int c = 0; c < PD && c < NCH; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[c][j] = *reinterpret_cast<const float4*>(rrow + c * 16 + j * 4);
+            }
+            named_bar_sync_epi();
+            mbar_wait(&tmem_full_bar[acc], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * HALF;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(t_addr + c * 16, v);
+                tmem_ld_wait();
+                const int col = col0 + c * 16;
+                float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-                    f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    const float4 b4 = *reinterpret_cast<const float4*>(sb + half * HALF + c * 16 + j);
+                    f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+                }
+                if (ep.act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752440f));
+                } else if (ep.act == 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                if (rrow) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 r4 = res[c % PD][j];
+                        f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+                    }
+                    if (c + PD < NCH) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            res[c % PD][j] = *reinterpret_cast<const float4*>(rrow + (c + PD) * 16 + j * 4);
+                    }
+                }
+                if (row_ok) {
+                    if (ep.out_f32) {
+                        float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    }
+                    if (ep.out_f16) {
+                        __half* o = ep.out_f16 + static_cast<size_t>(row) * ep.ld_f16 + col;
+                        uint32_t p[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                            p[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
+                        *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+                    }
                 }
             }
-            if (ep.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752440f));
-            } else if (ep.act == 2) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
-            }
-            if (ep.residual) {
-                const float* r = ep.residual + static_cast<size_t>(row) * ep.ld_res + col;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(r + j);
-                    f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-                }
-            }
-            if (ep.out_f32) {
-                float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            }
-            if (ep.out_f16) {
-                __half* o = ep.out_f16 + static_cast<size_t>(row) * ep.ld_f16 + col;
-                uint32_t p[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                    p[j] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
-                *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
-            }
+            // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
     }
     tc_fence_before();
@@ -166,8 +224,26 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, 2 * BN);
     }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const GemmEpilogue& ep, int sms,
+                       cudaStream_t stream) {
+    CUtensorMap tmA, tmW;
+    int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2,
+                              GEMM_BK, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, GEMM_BK,
+                          BN);
+    if (rc) return rc;
+    auto kern = gemm_f16_tn_kernel<BN, STAGES>;
+    constexpr int smem = GemmSmem<BN, STAGES>::TOTAL;
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
+    kern<<<tiles < sms ? tiles : sms, GEMM_THREADS, smem, stream>>>(tmA, tmW, M, N, K, ep);
+    return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace gmm
@@ -180,20 +256,24 @@ extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw,
     if (M <= 0) return 0;
     if (N % 128 != 0 || K % GEMM_BK != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
     if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
-    constexpr int BN = 128, STAGES = 4;
-    CUtensorMap tmA, tmW;
-    int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2,
-                              GEMM_BK, GEMM_BM);
-    if (rc) return rc;
-    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, GEMM_BK,
-                          BN);
-    if (rc) return rc;
+    if (!a || !w || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        GMM_CUDA_CHECK(cudaGetDevice(&dev));
+        GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
     GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act};
-    auto kern = gemm_f16_tn_kernel<BN, STAGES>;
-    constexpr int smem = GemmSmem<BN, STAGES>::TOTAL;
-    GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    dim3 grid(N / BN, (M + GEMM_BM - 1) / GEMM_BM);
-    kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmW, M, N, K, ep);
+    // tile width: 256 halves the A re-reads, 128 quantises better over the SMs; pick the cheaper schedule
+    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    bool wide = false;
+    if (N % 256 == 0) {
+        const long long r256 = (static_cast<long long>(tiles_m) * (N / 256) + sms - 1) / sms;
+        const long long r128 = (static_cast<long long>(tiles_m) * (N / 128) + sms - 1) / sms;
+        wide = r256 * 18 <= r128 * 10;
+    }
+    const int rc = wide ? launch_gemm<256, 4>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+                        : launch_gemm<128, 6>(a, lda, w, ldw, M, N, K, ep, sms, stream);
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return rc;
 }

@@ -3,18 +3,21 @@
 //   for i in range(196): softmax over the points of cell i, weighted sum   vilmodel.py:801-807
 // as ONE persistent kernel that reads every valid patch-feature row from HBM exactly once.
 //
-//   * rows are streamed in cell-sorted order (gridmm_grid_update produced `perm`), 64 rows per tile,
-//     gathered with 16-byte cp.async into a SWIZZLE_128B K-major tile (12 chunks of 64 x 128 B);
-//     the next tile's rows are pulled into L2 with cp.async.bulk.prefetch (one 1536-byte request per row);
-//   * relevance  S[64, L] = X_tile . text_fts^T  on tcgen05 (UMMA M=64, N=L, K=16 x 48), text_fts of the
-//     current episode resident in shared memory (TMA, 12 chunks of L x 128 B), accumulator in TMEM
-//     (double buffered), w = max_l S  (over ALL L positions, padding included -- vilmodel.py:798);
-//   * per-cell softmax + weighted sum on CUDA cores straight from the resident tile: cells are contiguous
-//     row segments; a cell that straddles tiles is carried in registers with the usual online-softmax
-//     rescale.  CTA ranges are cut at cell boundaries, so no atomics and no cross-CTA merge exist.
-//   * grid_proj is applied AFTER pooling by the GEMM kernel (sum_j p_j (W x_j + b) = W (sum_j p_j x_j) + b),
-//     so this kernel emits the pooled raw feature per non-empty cell, compacted in ascending cell order
-//     (the order vilmodel.py:819 gathers them in), as fp16 GEMM input.
+//   * rows are streamed in cell-sorted order (gridmm_grid_update produced `perm`), 64 rows per tile, gathered with
+//     16-byte cp.async into a SWIZZLE_128B K-major tile (D/64 chunks of 64 x 128 B); two tile buffers, so tile i+1 is
+//     in flight while tile i is multiplied, reduced and pooled; rows of tile i+2 are pulled into L2 with
+//     cp.async.bulk.prefetch (one request per 1536-byte row) so DRAM sees whole rows;
+//   * relevance  S^T[L, 64] = text_fts[L, D] . X_tile^T  on tcgen05 with the A operand (text_fts of the current
+//     episode, up to 128 positions) held in TENSOR MEMORY for the whole episode (tcgen05.st once per episode, 3 KB per
+//     lane), B operand = the feature tile in shared memory, accumulator in TMEM (double buffered);
+//     w = max over ALL text positions (padding included -- vilmodel.py:798) = max over TMEM lanes, taken with a
+//     warp butterfly (62 shuffles per thread) + one shared-memory hop across the four lane quadrants;
+//   * per-cell softmax + weighted sum on CUDA cores straight from the resident tile: cells are contiguous row segments;
+//     a cell that straddles tiles is carried in registers with the usual online-softmax rescale.  CTA ranges are cut at
+//     cell boundaries, so no atomics and no cross-CTA merge exist and the result is deterministic;
+//   * grid_proj is applied AFTER pooling by the GEMM kernel (sum_j p_j (W x_j + b) = W (sum_j p_j x_j) + b), so this
+//     kernel emits the pooled raw feature per non-empty cell, compacted in ascending cell order (the order
+//     vilmodel.py:819 gathers them in), as fp16 GEMM input.
 //
 // HBM roofline: algorithmic bytes = valid_rows * D * 2 (+ L*D*2 per episode + outputs); see DESIGN.md.
 #include "common.cuh"
@@ -23,14 +26,13 @@
 namespace gmm {
 
 constexpr int POOL_ROWS = 64;
-constexpr int POOL_GATHER_WARPS = 4;
-constexpr int POOL_MMA_WARP = 4;
-constexpr int POOL_TMA_WARP = 5;
-constexpr int POOL_EPI_WARP0 = 6;      // warps 6..9  (TMEM lane quadrant = warp & 3)
-constexpr int POOL_POOL_WARP0 = 10;    // warps 10..  (D / 128 of them)
+constexpr int POOL_GATHER_WARP0 = 4;   // warps 0..3: epilogue (TMEM lane quadrant = warp); warps 4..7: gather
+constexpr int POOL_MMA_WARP = 8;
+constexpr int POOL_POOL_WARP0 = 9;     // warps 9..  (D / 128 of them)
+constexpr int POOL_FIXED_THREADS = 9 * 32;
 constexpr int POOL_MAX_BATCH = 1024;
 constexpr int POOL_MAX_CELLS = 256;
-constexpr int POOL_LAG = 4;            // cp.async groups in flight per gather thread
+constexpr int POOL_TMEM_COLS = 512;
 
 struct PoolParams {
     const __half* fts;       // feature slab; row r at fts + r * D
@@ -38,10 +40,11 @@ struct PoolParams {
     const int* perm;         // [B, cap]     valid point indices sorted by cell
     const int* cell_start;   // [B, n_cells + 1]
     const int* cell_rank;    // [B, n_cells]
+    const __half* text;      // [B, l_pad, D] text_fts
     __half* pooled;          // [B, n_cells, D]  compacted by cell rank
     float* w_out;            // [B, cap] relevance weight per sorted position, or null (tests)
     int batch, t_cap, cap, n_cells;
-    int l_pad;               // text positions (multiple of 8, <= 80 for D = 768)
+    int l_pad;               // text positions (<= 128)
     int slot_rows, view_rows, tok_off;   // row = slot*slot_rows + view*view_rows + tok_off + patch
 };
 
@@ -80,7 +83,14 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
         case 1: cp_async_wait<1>(); break;
         case 2: cp_async_wait<2>(); break;
         case 3: cp_async_wait<3>(); break;
-        default: cp_async_wait<4>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        case 7: cp_async_wait<7>(); break;
+        case 8: cp_async_wait<8>(); break;
+        case 9: cp_async_wait<9>(); break;
+        case 10: cp_async_wait<10>(); break;
+        default: cp_async_wait<11>(); break;
     }
 }
 
@@ -92,45 +102,58 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One butterfly level of the lane-max: every lane keeps the half of its N columns selected by `bit` of its lane id and
+// merges in the partner's copy of that half.  After the 64 -> 2 levels lane l holds the warp-wide max of columns 2l, 2l+1.
+template <int N>
+__device__ __forceinline__ void lane_max_level(float (&v)[64], int lane, int bit) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+        const float keep = up ? v[N / 2 + j] : v[j];
+        const float send = up ? v[j] : v[N / 2 + j];
+        v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, bit));
+    }
+}
+
 template <int D>
 struct PoolSmem {
     static constexpr int CH = D / 64;
     static constexpr int A_CHUNK = POOL_ROWS * 128;
-    static constexpr int A_BYTES = CH * A_CHUNK;
-    static constexpr int b_bytes(int l_pad) { return CH * l_pad * 128; }
-    // after A and B: barriers and small arrays
-    static constexpr int MISC_BYTES = 64 * 8                          // barriers
-                                      + 2 * POOL_ROWS * 4 * 4         // w, p, fin, rank (double buffered)
-                                      + 64                            // scalars
-                                      + (POOL_MAX_CELLS + 1) * 4 + POOL_MAX_CELLS * 4   // cell_start, cell_rank of current episode
-                                      + (POOL_MAX_BATCH + 1) * 4;     // vbase
-    static constexpr int total(int l_pad) { return 1024 + b_bytes(l_pad) + A_BYTES + MISC_BYTES; }
+    static constexpr int A_BYTES = CH * A_CHUNK;                  // one feature tile
+    static constexpr int MISC_BYTES = 64 * 8                      // barriers + tmem slot
+                                      + 2 * POOL_ROWS * 4 * 4     // w, p, fin, rank (double buffered)
+                                      + 4 * POOL_ROWS * 4         // per-quadrant partial maxima
+                                      + 64                        // scalars
+                                      + (POOL_MAX_CELLS + 1) * 4 + POOL_MAX_CELLS * 4   // cell_start, cell_rank of the episode
+                                      + (POOL_MAX_BATCH + 1) * 4; // vbase
+    static constexpr int TOTAL = 1024 + 2 * A_BYTES + MISC_BYTES;
 };
 
 template <int D>
-__global__ void __launch_bounds__(320 + D / 4, 1)
-pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
+__global__ void __launch_bounds__(POOL_FIXED_THREADS + D / 4, 1)
+pool_kernel(PoolParams p) {
     using L = PoolSmem<D>;
     constexpr int CH = L::CH;
+    constexpr int A_COLS = D / 2;                 // TMEM columns of the text operand (two fp16 per column)
+    constexpr int D_COL0 = A_COLS;                // accumulators behind it: 2 x 64 columns
+    static_assert(A_COLS + 2 * POOL_ROWS <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_chunk = p.l_pad * 128;
-    uint8_t* sB = smem;
-    uint8_t* sA = smem + CH * b_chunk;
-    uint8_t* misc = sA + L::A_BYTES;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);        // [CH]
-    uint64_t* a_empty = a_full + 12;                               // [CH]
-    uint64_t* d_full = a_empty + 12;                               // [2]
+    uint8_t* sA = smem;                            // [2][CH][64 x 128 B]
+    uint8_t* misc = sA + 2 * L::A_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);          // [2][12]
+    uint64_t* a_empty = a_full + 24;                               // [2][12]
+    uint64_t* d_full = a_empty + 24;                               // [2]
     uint64_t* d_empty = d_full + 2;                                // [2]
     uint64_t* p_full = d_empty + 2;                                // [2]
-    uint64_t* b_full = p_full + 2;                                 // [1]
-    uint64_t* b_empty = b_full + 1;                                // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + 1);
+    uint64_t* t_ready = p_full + 2;                                // [1] text operand of the episode is in TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 60);
     float* s_w = reinterpret_cast<float*>(misc + 64 * 8);          // [2][64]
     float* s_p = s_w + 2 * POOL_ROWS;                              // [2][64]
     float* s_fin = s_p + 2 * POOL_ROWS;                            // [2][64]  1/sum at the last row of a finished cell, else 0
     int* s_rank = reinterpret_cast<int*>(s_fin + 2 * POOL_ROWS);   // [2][64]
-    float* s_scal = reinterpret_cast<float*>(s_rank + 2 * POOL_ROWS);   // [0..1] carry scale per buffer, [2] m_carry, [3] s_carry
+    float* s_part = reinterpret_cast<float*>(s_rank + 2 * POOL_ROWS);   // [4][64]
+    float* s_scal = s_part + 4 * POOL_ROWS;                        // [0..1] carry scale per buffer, [2] m_carry, [3] s_carry
     int* s_range = reinterpret_cast<int*>(s_scal + 8);             // [0] g_start, [1] g_end
     int* s_cs = s_range + 8;                                       // [n_cells + 1]
     int* s_cr = s_cs + POOL_MAX_CELLS + 1;                         // [n_cells]
@@ -142,8 +165,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
 
     // ---------------------------------------------------------------- setup: barriers, TMEM, schedule
     if (tid == 0) {
-        for (int k = 0; k < CH; ++k) {
-            mbar_init(&a_full[k], POOL_GATHER_WARPS * 32);
+        for (int k = 0; k < 24; ++k) {
+            mbar_init(&a_full[k], 64);
             mbar_init(&a_empty[k], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -151,12 +174,10 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
             mbar_init(&d_empty[i], 4);
             mbar_init(&p_full[i], 128);
         }
-        mbar_init(b_full, 1);
-        mbar_init(b_empty, 1);
+        mbar_init(t_ready, 128);
         fence_mbar_init();
-        tma_prefetch_desc(&tmT);
     }
-    if (warp == POOL_MMA_WARP) tmem_alloc(tmem_slot, 256);
+    if (warp == POOL_MMA_WARP) tmem_alloc(tmem_slot, POOL_TMEM_COLS);
     // exclusive prefix of the valid-point counts: vbase[b] = sum_{b' < b} cell_start[b'][n_cells]
     for (int i = tid; i < p.batch; i += blockDim.x) s_vbase[i + 1] = p.cell_start[i * (n_cells + 1) + n_cells];
     if (tid == 0) s_vbase[0] = 0;
@@ -209,21 +230,26 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
     wk.init(s_vbase, p.batch, g0, g1);
     Tile t;
 
-    if (warp < POOL_GATHER_WARPS) {
+    if (warp >= POOL_GATHER_WARP0 && warp < POOL_MMA_WARP) {
         // ------------------------------------------------------------ gather producers
-        const int u = tid & 7;            // 16-byte unit inside the 128-byte chunk row
-        const int r0 = tid >> 3;          // rows r0 + 16*i
-        Walker ahead = wk;
+        // Two independent groups of 64 threads: group g fills tile buffer g with the tiles of parity g.  A group issues
+        // the WHOLE tile (96 x 16 B per thread, one cp.async group per 128-byte chunk column) before it waits for
+        // anything, so ~96 KB per buffer are in flight -- HBM latency x bandwidth needs ~80 KB per SM.
+        const int grp = (warp - POOL_GATHER_WARP0) >> 1;
+        const int gt = (tid - POOL_GATHER_WARP0 * 32) & 63;   // 0..63 within the group
+        const int u = gt & 7;             // 16-byte unit inside the 128-byte chunk row
+        const int r0 = gt >> 3;           // rows r0 + 8*i
+        uint8_t* tile_base = sA + grp * L::A_BYTES;
         Tile tn;
-        bool have_next = ahead.next(tn);
-        int it = 0;
-        while (wk.next(t)) {
-            have_next = ahead.next(tn);   // `ahead` runs one tile in front of `wk`
+        bool have = wk.next(t);
+        if (grp == 1 && have) have = wk.next(t);           // group 1 starts at tile 1
+        int n = 0;                                          // tiles this group has filled
+        while (have) {
             const int* perm_b = p.perm + static_cast<size_t>(t.b) * p.cap + t.pos;
-            const __half* src[4];
+            const __half* src[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + 16 * i;
+            for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 8 * i;
                 src[i] = nullptr;
                 if (r < t.nrows) {
                     const int j = perm_b[r];
@@ -234,117 +260,122 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
                     src[i] = p.fts + row * D + u * 8;
                 }
             }
-            // pull the NEXT tile's rows into L2 with one bulk request per row
-            if (have_next && tid < tn.nrows) {
-                const int j = p.perm[static_cast<size_t>(tn.b) * p.cap + tn.pos + tid];
+            const uint32_t ph = n & 1;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                mbar_wait(&a_empty[grp * 12 + k], ph ^ 1);
+                const uint32_t dst = smem_u32(tile_base + k * L::A_CHUNK);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (src[i]) cp_async_16(dst + sw128_offset(r0 + 8 * i, u), src[i] + k * 64);
+                cp_async_commit();
+            }
+            // this group's next tile (two tiles ahead in the CTA's sequence): pull its rows into L2, one bulk request per row
+            have = wk.next(tn) && wk.next(tn);
+            if (have && gt < tn.nrows) {
+                const int j = p.perm[static_cast<size_t>(tn.b) * p.cap + tn.pos + gt];
                 const int step = j / 588, q = j - step * 588;
                 const int v = q / 49, k = q - v * 49;
                 const long long row = static_cast<long long>(p.slots[tn.b * p.t_cap + step]) * p.slot_rows +
                                       v * p.view_rows + p.tok_off + k;
                 l2_prefetch_bulk(p.fts + row * D, D * 2);
             }
-            const uint32_t ph = it & 1;
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
-                mbar_wait(&a_empty[k], ph ^ 1);
-                const uint32_t dst = smem_u32(sA + k * L::A_CHUNK);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (src[i]) cp_async_16(dst + sw128_offset(r0 + 16 * i, u), src[i] + k * 64);
-                cp_async_commit();
-                if (k >= POOL_LAG) {
-                    cp_async_wait<POOL_LAG>();
-                    fence_proxy_async_smem();
-                    mbar_arrive(&a_full[k - POOL_LAG]);
-                }
-            }
-#pragma unroll
-            for (int k = CH - POOL_LAG; k < CH; ++k) {
                 cp_async_wait_dyn(CH - 1 - k);
                 fence_proxy_async_smem();
-                mbar_arrive(&a_full[k]);
+                mbar_arrive(&a_full[grp * 12 + k]);
             }
-            ++it;
+            t = tn;
+            ++n;
         }
     } else if (warp == POOL_MMA_WARP) {
-        // ------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------ MMA issuer: S^T = text (TMEM) x tile^T (smem)
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(POOL_ROWS, p.l_pad);
+            constexpr uint32_t idesc = umma_idesc_f16(128, POOL_ROWS);
             int it = 0, cur_b = -1, visits = 0;
-            bool more = wk.next(t);
-            while (more) {
-                Tile tnext;
-                const bool more_next = wk.next(tnext);
+            while (wk.next(t)) {
                 const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
                 if (t.b != cur_b) {
-                    mbar_wait(b_full, visits & 1);
+                    mbar_wait(t_ready, visits & 1);
                     cur_b = t.b;
                     ++visits;
                 }
-                mbar_wait(&d_empty[buf], ((it >> 1) & 1) ^ 1);
+                mbar_wait(&d_empty[buf], ph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * 128;
+                const uint32_t d_tmem = tmem_base + D_COL0 + buf * POOL_ROWS;
+                const uint8_t* tile_base = sA + buf * L::A_BYTES;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) {
-                    mbar_wait(&a_full[k], it & 1);
+                    mbar_wait(&a_full[buf * 12 + k], ph);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128_kmajor(smem_u32(sA + k * L::A_CHUNK));
-                    const uint64_t db = umma_desc_sw128_kmajor(smem_u32(sB + k * b_chunk));
+                    const uint64_t db = umma_desc_sw128_kmajor(smem_u32(tile_base + k * L::A_CHUNK));
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) umma_f16_ss(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk)   // K = 16 per instruction = 8 TMEM columns of A, 32 bytes of B
+                        umma_f16_ts(d_tmem, tmem_base + k * 32 + kk * 8, db + 2 * kk, idesc, (k | kk) ? 1u : 0u);
                 }
                 umma_commit(&d_full[buf]);
-                if (!more_next || tnext.b != cur_b) umma_commit(b_empty);   // text_fts of this episode may be replaced
-                t = tnext;
-                more = more_next;
                 ++it;
             }
         }
-    } else if (warp == POOL_TMA_WARP) {
-        // ------------------------------------------------------------ text_fts loader (one episode resident)
-        if (lane == 0) {
-            int cur_b = -1, visits = 0;
-            while (wk.next(t)) {
-                if (t.b == cur_b) continue;
-                cur_b = t.b;
-                mbar_wait(b_empty, (visits & 1) ^ 1);
-                mbar_arrive_expect_tx(b_full, CH * b_chunk);
-                for (int k = 0; k < CH; ++k) tma_load_2d(sB + k * b_chunk, &tmT, k * 64, t.b * p.l_pad, b_full);
-                ++visits;
-            }
-        }
-    } else if (warp < POOL_POOL_WARP0) {
-        // ------------------------------------------------------------ relevance max + per-cell softmax weights
-        const int q = warp & 3;
-        const int e = tid - POOL_EPI_WARP0 * 32;       // 0..127
+    } else if (warp < POOL_GATHER_WARP0) {
+        // ------------------------------------------------------------ text operand -> TMEM, relevance max, softmax weights
+        const int q = warp;                         // TMEM lane quadrant
+        const int e = tid;                          // 0..127 = TMEM lane = text position
         int it = 0, cur_b = -1;
         if (e == 0) { s_scal[2] = 0.0f; s_scal[3] = 0.0f; }
         while (wk.next(t)) {
             const int buf = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
             if (t.b != cur_b) {
-                // all 128 threads are past the previous tile's reads of s_cs/s_cr (barrier 2 below)
+                // Every MMA that read the previous episode's text has retired: this warp waited on d_full of the previous
+                // tile below.  Lanes past l_pad replicate position 0 -- duplicates never change a maximum.
                 cur_b = t.b;
+                const int tok = (e < p.l_pad) ? e : 0;
+                const uint4* src = reinterpret_cast<const uint4*>(p.text + (static_cast<size_t>(t.b) * p.l_pad + tok) * D);
+                const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 4
+                for (int c = 0; c < D / 16; ++c) {
+                    const uint4 lo = __ldg(src + 2 * c), hi = __ldg(src + 2 * c + 1);
+                    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+                    tmem_st_32x32b_x8(ta + c * 8, v);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(t_ready);
                 for (int i = e; i <= n_cells; i += 128) s_cs[i] = p.cell_start[t.b * (n_cells + 1) + i];
                 for (int i = e; i < n_cells; i += 128) s_cr[i] = p.cell_rank[t.b * n_cells + i];
             }
-            mbar_wait(&d_full[buf], (it >> 1) & 1);
+            mbar_wait(&d_full[buf], ph);
             tc_fence_after();
-            float mx = -INFINITY;
-            for (int c = 0; c < p.l_pad; c += 16) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128 + c, v);
-                tmem_ld_wait();
-                const int lim = min(16, p.l_pad - c);
+            float v[64];
+            {
+                const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + D_COL0 + buf * POOL_ROWS;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[16];
+                    tmem_ld_32x32b_x16(ta + c * 16, r);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c * 16 + j] = __uint_as_float(r[j]);
+                }
+                tmem_ld_wait();
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&d_empty[buf]);
-            // UMMA M=64: accumulator row 16*q + i lives in TMEM lane 32*q + i (i < 16)
-            if (lane < 16) s_w[buf * POOL_ROWS + q * 16 + lane] = mx;
+            lane_max_level<64>(v, lane, 16);
+            lane_max_level<32>(v, lane, 8);
+            lane_max_level<16>(v, lane, 4);
+            lane_max_level<8>(v, lane, 2);
+            lane_max_level<4>(v, lane, 1);
+            s_part[q * POOL_ROWS + 2 * lane] = v[0];
+            s_part[q * POOL_ROWS + 2 * lane + 1] = v[1];
             named_bar_sync(1, 128);
+            if (e < POOL_ROWS)
+                s_w[buf * POOL_ROWS + e] = fmaxf(fmaxf(s_part[e], s_part[POOL_ROWS + e]),
+                                                 fmaxf(s_part[2 * POOL_ROWS + e], s_part[3 * POOL_ROWS + e]));
+            named_bar_sync(2, 128);
             // --- softmax weights of this tile's rows; one thread per row
             float m_carry = s_scal[2], s_carry = s_scal[3];
             float my_p = 0.0f, my_fin = 0.0f, new_m = 0.0f, new_s = 0.0f, cscale = 1.0f;
@@ -387,7 +418,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
                 s_fin[buf * POOL_ROWS + e] = my_fin;
                 s_rank[buf * POOL_ROWS + e] = my_rank;
             }
-            named_bar_sync(2, 128);             // everyone has read the old carry / s_cs
+            named_bar_sync(3, 128);             // everyone has read the old carry / s_cs / s_part
             if (writes_carry) { s_scal[2] = new_m; s_scal[3] = new_s; }
             mbar_arrive(&p_full[buf]);          // release: s_p / s_fin / s_rank / s_scal[buf] are visible to the pooling warps
             ++it;
@@ -399,13 +430,14 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
         const int k = pt >> 4;
         const int u = (pt & 15) >> 1;
         const int sub = (pt & 1) * 8;
-        const uint8_t* chunk = sA + k * L::A_CHUNK;
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         int it = 0;
         while (wk.next(t)) {
             const int buf = it & 1;
-            mbar_wait(&p_full[buf], (it >> 1) & 1);
-            mbar_wait(&a_full[k], it & 1);
+            const uint32_t ph = (it >> 1) & 1;
+            mbar_wait(&p_full[buf], ph);
+            mbar_wait(&a_full[buf * 12 + k], ph);
+            const uint8_t* chunk = sA + buf * L::A_BYTES + k * L::A_CHUNK;
             const float cs = s_scal[buf];
             acc0 *= cs; acc1 *= cs; acc2 *= cs; acc3 *= cs;
             const float* pp = s_p + buf * POOL_ROWS;
@@ -432,8 +464,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
             }
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(&a_empty[2 * pw]);
-                mbar_arrive(&a_empty[2 * pw + 1]);
+                mbar_arrive(&a_empty[buf * 12 + 2 * pw]);
+                mbar_arrive(&a_empty[buf * 12 + 2 * pw + 1]);
             }
             ++it;
         }
@@ -444,7 +476,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tmT, PoolParams p) {
     if (warp == POOL_MMA_WARP) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, POOL_TMEM_COLS);
     }
 }
 
@@ -457,32 +489,27 @@ extern "C" int gridmm_pool(const void* fts, int feat_dim, const int* slots, int 
     using namespace gmm;
     if (batch <= 0) return 0;
     if (!fts || !slots || !perm || !cell_start || !cell_rank || !text_fts || !pooled) return GRIDMM_ERR_ARG;
-    if (batch > POOL_MAX_BATCH || n_cells > POOL_MAX_CELLS || l_pad < 8 || (l_pad % 8) || l_pad > 128) return GRIDMM_ERR_SHAPE;
+    if (batch > POOL_MAX_BATCH || n_cells > POOL_MAX_CELLS || l_pad < 1 || l_pad > 128) return GRIDMM_ERR_SHAPE;
     if (feat_dim != 768 && feat_dim != 512) return GRIDMM_ERR_SHAPE;
-    CUtensorMap tmT;
-    int rc = make_tmap_f16_2d(&tmT, text_fts, static_cast<uint64_t>(feat_dim), static_cast<uint64_t>(batch) * l_pad,
-                              static_cast<uint64_t>(feat_dim) * 2, 64, static_cast<uint32_t>(l_pad));
-    if (rc) return rc;
+    if (reinterpret_cast<uintptr_t>(text_fts) & 15) return GRIDMM_ERR_SHAPE;
     PoolParams p;
     p.fts = reinterpret_cast<const __half*>(fts); p.slots = slots; p.perm = perm; p.cell_start = cell_start;
-    p.cell_rank = cell_rank; p.pooled = reinterpret_cast<__half*>(pooled); p.w_out = w_out;
+    p.cell_rank = cell_rank; p.text = reinterpret_cast<const __half*>(text_fts);
+    p.pooled = reinterpret_cast<__half*>(pooled); p.w_out = w_out;
     p.batch = batch; p.t_cap = t_cap; p.cap = cap; p.n_cells = n_cells; p.l_pad = l_pad;
     p.slot_rows = slot_rows; p.view_rows = view_rows; p.tok_off = tok_off;
-    int dev = 0, sms = 0, max_smem = 0;
+    int dev = 0, sms = 0;
     GMM_CUDA_CHECK(cudaGetDevice(&dev));
     GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GMM_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int grid = num_ctas > 0 ? num_ctas : sms;
     if (feat_dim == 768) {
-        const int smem = PoolSmem<768>::total(l_pad);
-        if (smem > max_smem) return GRIDMM_ERR_SHAPE;
+        constexpr int smem = PoolSmem<768>::TOTAL;
         GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        pool_kernel<768><<<grid, 320 + 768 / 4, smem, stream>>>(tmT, p);
+        pool_kernel<768><<<grid, POOL_FIXED_THREADS + 768 / 4, smem, stream>>>(p);
     } else {
-        const int smem = PoolSmem<512>::total(l_pad);
-        if (smem > max_smem) return GRIDMM_ERR_SHAPE;
+        constexpr int smem = PoolSmem<512>::TOTAL;
         GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        pool_kernel<512><<<grid, 320 + 512 / 4, smem, stream>>>(tmT, p);
+        pool_kernel<512><<<grid, POOL_FIXED_THREADS + 512 / 4, smem, stream>>>(p);
     }
     gridmm_count_launch(1);
     return static_cast<int>(cudaGetLastError());

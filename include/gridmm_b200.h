@@ -70,8 +70,8 @@ int gridmm_cell_sort(int batch, const short* cell, const int* n_pts, int grid_w,
  * grid_proj is applied afterwards with gridmm_linear_f16 (it commutes with the convex combination).
  *   fts          fp16 feature slab, row r at fts + r*feat_dim; point (step t, view v, patch k) of episode b is row
  *                slots[b*t_cap+t]*slot_rows + v*view_rows + tok_off + k   (CLS token skipped via tok_off, env.py:299)
- *   text_fts     fp16 [batch, l_pad, feat_dim] = text_proj(txt_embeds); l_pad % 8 == 0, l_pad*feat_dim*2 + 64*feat_dim*2
- *                must fit in shared memory (l_pad <= 80 at feat_dim 768); pad with copies of a real row
+ *   text_fts     fp16 [batch, l_pad, feat_dim] = text_proj(txt_embeds), 16-byte aligned; l_pad <= 128 (the operand lives in
+ *                tensor memory, one text position per TMEM lane; unused lanes replicate position 0)
  *   pooled       fp16 [batch, n_cells, feat_dim], rows >= n_nonempty[b] are not written
  *   w_out        optional f32 [batch,cap]: w per sorted position (tests), or NULL
  *   num_ctas     0 = one CTA per SM */
