@@ -26,7 +26,7 @@ _SIGS = {
                            c_void_p, c_void_p, c_void_p],
     "gridmm_cell_sort": [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_pool": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
-                    c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                           c_void_p, c_int, c_int, c_void_p],
     "gridmm_attention_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_float,

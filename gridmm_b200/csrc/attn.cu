@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(AttnParams p) {
     __half* sQ = sV + static_cast<size_t>(sk_pad) * ATT_LD;
     float* sM = reinterpret_cast<float*>(sQ + ATT_QT * ATT_LD);
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * ATT_QT, h = blockIdx.y, b = blockIdx.z;
     const __half* gq = p.q + (static_cast<size_t>(b) * p.q_rows) * p.ldq + h * ATT_DH;
@@ -201,7 +203,7 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     if (smem > 227 * 1024) return GRIDMM_ERR_SHAPE;
     GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((sq + ATT_QT - 1) / ATT_QT, heads, batch);
-    attn_kernel<<<grid, ATT_THREADS, smem, stream>>>(p);
+    GMM_CUDA_CHECK(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), smem, stream, p));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }

@@ -28,14 +28,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint expires)
+// instead of burning issue slots in a polling loop -- it is woken by the arrival, so the hint adds no latency.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
@@ -155,6 +157,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
 __device__ __forceinline__ uint32_t sw128_offset(int r, int u) {
     return static_cast<uint32_t>(r * 128 + ((u ^ (r & 7)) << 4));
 }
+
+// ----------------------------------------------------------------------------- programmatic dependent launch
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {

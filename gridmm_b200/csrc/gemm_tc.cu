@@ -20,7 +20,7 @@
 namespace gmm {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;
+constexpr int GEMM_KATOM = 64;         // one SWIZZLE_128B atom = 64 fp16 along K
 constexpr int GEMM_EPI_WARPS = 8;       // 2 per TMEM lane quadrant, each takes half of the tile's columns
 constexpr int GEMM_THREADS = 64 + GEMM_EPI_WARPS * 32;
 constexpr int GEMM_RES_PREFETCH = 4;    // residual chunks (16 columns each) kept in flight per epilogue thread
@@ -32,27 +32,50 @@ struct GemmEpilogue {
     __half* out_f16;         // [M, ld_f16] or null
     int ld_res, ld_f32, ld_f16;
     int act;                 // 0 none, 1 GELU(erf), 2 ReLU
+    long long* dbg;          // optional [grid][8] cycle counters (tools/microbench.py), null in production
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK>
 struct GemmSmem {
-    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int A_ATOM = GEMM_BM * GEMM_KATOM * 2;     // 128 rows x 128 B
+    static constexpr int B_ATOM = BN * GEMM_KATOM * 2;
+    static constexpr int A_BYTES = A_ATOM * (BK / GEMM_KATOM);
+    static constexpr int B_BYTES = B_ATOM * (BK / GEMM_KATOM);
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;   // [2][BN] floats
-    static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;  // barriers + tmem slot + bias + alignment slack
+    static constexpr int STG_OFFSET = BIAS_OFFSET + 2 * BN * 4;     // per epilogue warp: 32 rows x 20 floats (16 + pad)
+    static constexpr int STG_WARP_BYTES = 32 * 20 * 4;
+    static constexpr int TOTAL = STG_OFFSET + GEMM_EPI_WARPS * STG_WARP_BYTES + 1024;
 };
+
+// erf-GELU (BertIntermediate / F.gelu: 0.5 x (1 + erf(x / sqrt 2))).  erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7,
+// MUFU rcp + MUFU ex2 + 7 FMA instead of erff's ~30 instructions): the epilogue of the FFN1 GEMM applies it to every element.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.4426950408889634f));
+    const float e = poly * t * ex;                                        // 1 - erf(z)
+    const float erf_abs = 1.0f - e;
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ void named_bar_sync_epi() {
     asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK, bool DBG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
                    GemmEpilogue ep) {
-    using L = GemmSmem<BN, STAGES>;
+    using L = GemmSmem<BN, STAGES, BK>;
+    constexpr int ATOMS = BK / GEMM_KATOM;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -63,11 +86,12 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_kb = K / GEMM_BK;
+    const int num_kb = K / BK;
     const int tiles_n = N / BN;
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     const int num_tiles = tiles_m * tiles_n;
 
+    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
@@ -86,49 +110,71 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
+            long long w_empty = 0;
+            const long long t_begin = DBG ? clock64() : 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const long long c0 = DBG ? clock64() : 0;
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (DBG) w_empty += clock64() - c0;
                     uint8_t* a_dst = smem + s * L::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + L::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-                    tma_load_2d(a_dst, &tmA, kb * GEMM_BK, m0, &full_bar[s]);
-                    tma_load_2d(b_dst, &tmW, kb * GEMM_BK, n0, &full_bar[s]);
+#pragma unroll
+                    for (int a = 0; a < ATOMS; ++a) {
+                        tma_load_2d(a_dst + a * L::A_ATOM, &tmA, kb * BK + a * GEMM_KATOM, m0, &full_bar[s]);
+                        tma_load_2d(b_dst + a * L::B_ATOM, &tmW, kb * BK + a * GEMM_KATOM, n0, &full_bar[s]);
+                    }
                 }
             }
+            if (DBG && ep.dbg) { ep.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 1] = w_empty; }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN);
             int it = 0, t = 0;
+            long long w_full = 0, w_acc = 0;
+            const long long t_begin = DBG ? clock64() : 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int acc = t & 1;
+                const long long c1 = DBG ? clock64() : 0;
                 mbar_wait(&tmem_empty_bar[acc], ((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+                if (DBG) w_acc += clock64() - c1;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const long long c0 = DBG ? clock64() : 0;
                     mbar_wait(&full_bar[s], ph);
+                    if (DBG) w_full += clock64() - c0;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-                    const uint64_t da = umma_desc_sw128_kmajor(a_addr);
-                    const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
-                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int a = 0; a < ATOMS; ++a) {
+                        const uint64_t da = umma_desc_sw128_kmajor(a_addr + a * L::A_ATOM);
+                        const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES + a * L::B_ATOM);
+#pragma unroll
+                        for (int k = 0; k < GEMM_KATOM / 16; ++k) {
+                            // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
+                            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&tmem_full_bar[acc]);
+            }
+            if (DBG && ep.dbg) {
+                ep.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 3] = w_full;
+                ep.dbg[blockIdx.x * 8 + 4] = w_acc;
             }
         }
     } else {
@@ -139,34 +185,44 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int et = threadIdx.x - 64;                  // 0..255
         float* s_bias = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
         int t = 0;
+        long long w_tfull = 0;
+        const long long t_begin = DBG ? clock64() : 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
             const int acc = t & 1;
             const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
             // stage this tile's bias slice (the slot of tile t-2 is free: all warps passed the barrier of tile t-1)
             float* sb = s_bias + acc * BN;
             for (int i = et; i < BN; i += GEMM_EPI_WARPS * 32) sb[i] = ep.bias ? __ldg(ep.bias + n0 + i) : 0.0f;
-            // residual chunks in flight before the accumulator is even ready
+            // Global accesses use a coalesced mapping: in pass i a lane owns row 8*i + lane/4 of the warp's 32 rows and 4
+            // of the chunk's 16 columns, so one warp instruction covers 8 rows x 64 contiguous bytes (the TMEM layout --
+            // one row per lane -- would touch 32 different lines per instruction).  Accumulator chunks cross over through
+            // a per-warp shared-memory tile.
             const int col0 = n0 + half * HALF;
-            const float* rrow = ep.residual ? ep.residual + static_cast<size_t>(row_ok ? row : 0) * ep.ld_res + col0 : nullptr;
+            const int rsub = lane >> 2, csub = (lane & 3) * 4;
+            const int row_base = m0 + q * 32 + rsub;
             float4 res[PD][4];
-            if (rrow) {
+            if (ep.residual) {
 #pragma unroll
                 for (int c = 0; c < PD && c < NCH; ++c)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) res[c][j] = *reinterpret_cast<const float4*>(rrow + c * 16 + j * 4);
+                    for (int i = 0; i < 4; ++i) {
+                        const int rg = row_base + 8 * i;
+                        res[c][i] = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rg < M ? rg : 0) * ep.ld_res +
+                                                                     col0 + c * 16 + csub);
+                    }
             }
             named_bar_sync_epi();
+            const long long c0 = DBG ? clock64() : 0;
             mbar_wait(&tmem_full_bar[acc], (t >> 1) & 1);
+            if (DBG) w_tfull += clock64() - c0;
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * HALF;
+            float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + (warp - 2) * L::STG_WARP_BYTES);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[16];
                 tmem_ld_32x32b_x16(t_addr + c * 16, v);
                 tmem_ld_wait();
-                const int col = col0 + c * 16;
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
@@ -176,48 +232,46 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 if (ep.act == 1) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752440f));
+                    for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
                 } else if (ep.act == 2) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
                 }
-                if (rrow) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 r4 = res[c % PD][j];
-                        f[4 * j] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * 20 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                __syncwarp();
+                const int col = col0 + c * 16 + csub;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 x = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * 20 + csub);
+                    const int rg = row_base + 8 * i;
+                    if (ep.residual) {
+                        const float4 r4 = res[c % PD][i];
+                        x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
+                        if (c + PD < NCH)
+                            res[c % PD][i] = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rg < M ? rg : 0) * ep.ld_res +
+                                                                              col + PD * 16);
                     }
-                    if (c + PD < NCH) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            res[c % PD][j] = *reinterpret_cast<const float4*>(rrow + (c + PD) * 16 + j * 4);
-                    }
-                }
-                if (row_ok) {
-                    if (ep.out_f32) {
-                        float* o = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    }
-                    if (ep.out_f16) {
-                        __half* o = ep.out_f16 + static_cast<size_t>(row) * ep.ld_f16 + col;
-                        uint32_t p[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                            p[j] = *reinterpret_cast<const uint32_t*>(&h);
+                    if (rg < M) {
+                        if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(rg) * ep.ld_f32 + col) = x;
+                        if (ep.out_f16) {
+                            const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+                            uint2 o;
+                            o.x = *reinterpret_cast<const uint32_t*>(&h01);
+                            o.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            *reinterpret_cast<uint2*>(ep.out_f16 + static_cast<size_t>(rg) * ep.ld_f16 + col) = o;
                         }
-                        *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
-                        *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
                     }
                 }
+                __syncwarp();
             }
             // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (DBG && ep.dbg && et == 0) { ep.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 6] = w_tfull; }
     }
     tc_fence_before();
     __syncthreads();
@@ -228,33 +282,36 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK, bool DBG>
 static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const GemmEpilogue& ep, int sms,
                        cudaStream_t stream) {
     CUtensorMap tmA, tmW;
     int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2,
-                              GEMM_BK, GEMM_BM);
+                              GEMM_KATOM, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2, GEMM_BK,
-                          BN);
+    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2,
+                          GEMM_KATOM, BN);
     if (rc) return rc;
-    auto kern = gemm_f16_tn_kernel<BN, STAGES>;
-    constexpr int smem = GemmSmem<BN, STAGES>::TOTAL;
+    auto kern = gemm_f16_tn_kernel<BN, STAGES, BK, DBG>;
+    constexpr int smem = GemmSmem<BN, STAGES, BK>::TOTAL;
     GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
-    kern<<<tiles < sms ? tiles : sms, GEMM_THREADS, smem, stream>>>(tmA, tmW, M, N, K, ep);
-    return static_cast<int>(cudaGetLastError());
+    return static_cast<int>(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(GEMM_THREADS), smem, stream, tmA, tmW, M, N, K, ep));
 }
 
 }  // namespace gmm
 
 // ----------------------------------------------------------------------------- C ABI
+static long long* g_gemm_dbg = nullptr;
+// Debug hook (tools/microbench.py): per-CTA cycle counters [grid][8] written by the next GEMM launches; null disables.
+extern "C" void gridmm_debug_set_gemm_counters(long long* dbg) { g_gemm_dbg = dbg; }
+
 extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                                  const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
                                  int act, cudaStream_t stream) {
     using namespace gmm;
     if (M <= 0) return 0;
-    if (N % 128 != 0 || K % GEMM_BK != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
+    if (N % 128 != 0 || K % GEMM_KATOM != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
     if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
     if (!a || !w || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
     static int sms = 0;
@@ -263,7 +320,7 @@ extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw,
         GMM_CUDA_CHECK(cudaGetDevice(&dev));
         GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act};
+    GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act, g_gemm_dbg};
     // tile width: 256 halves the A re-reads, 128 quantises better over the SMs; pick the cheaper schedule
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     bool wide = false;
@@ -272,8 +329,18 @@ extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw,
         const long long r128 = (static_cast<long long>(tiles_m) * (N / 128) + sms - 1) / sms;
         wide = r256 * 18 <= r128 * 10;
     }
-    const int rc = wide ? launch_gemm<256, 4>(a, lda, w, ldw, M, N, K, ep, sms, stream)
-                        : launch_gemm<128, 6>(a, lda, w, ldw, M, N, K, ep, sms, stream);
+    // 128-wide tiles: 128 K-columns per stage (8 MMAs per barrier round trip) when K allows, the single-thread issue loop
+    // is otherwise slower than the 4 x 64-cycle MMAs of a 64-column stage
+    const bool deep = (K % 128 == 0);
+    int rc;
+    if (g_gemm_dbg)
+        rc = wide ? launch_gemm<256, 4, 64, true>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : deep ? launch_gemm<128, 3, 128, true>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+                  : launch_gemm<128, 6, 64, true>(a, lda, w, ldw, M, N, K, ep, sms, stream);
+    else
+        rc = wide ? launch_gemm<256, 4, 64, false>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : deep ? launch_gemm<128, 3, 128, false>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+                  : launch_gemm<128, 6, 64, false>(a, lda, w, ldw, M, N, K, ep, sms, stream);
     gridmm_count_launch(1);
     return rc;
 }

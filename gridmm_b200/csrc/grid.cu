@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_update_kernel(GridParams
     __shared__ uint16_t warp_hist[32][MAX_CELLS];   // per-warp counts, then per-warp write cursors
     __shared__ int s_cell_start[MAX_CELLS + 1];
 
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -268,9 +270,9 @@ extern "C" int gridmm_grid_update(int batch, const void* depth, int depth_is_f32
     p.cap = cap; p.grid_w = grid_w; p.depth_is_f32 = depth_is_f32; p.depth_scale = depth_scale;
     for (int i = 0; i < 7; ++i) p.off[i] = off7[i];
     p.flip_y = flip_y; p.negate_map_x = negate_map_x; p.sort_only = 0;
-    grid_update_kernel<<<batch, GRID_THREADS, 0, stream>>>(p);
+    GMM_CUDA_CHECK(launch_pdl(grid_update_kernel, dim3(batch), dim3(GRID_THREADS), 0, stream, p));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }
 
 // Sort-only entry for callers that already hold the reference's `grid_map` (cell id per point, -1 = masked):
@@ -286,7 +288,7 @@ extern "C" int gridmm_cell_sort(int batch, const short* cell, const int* n_pts, 
     p.cell = const_cast<short*>(cell);
     p.perm = perm; p.cell_start = cell_start; p.cell_rank = cell_rank; p.n_nonempty = n_nonempty;
     p.cap = cap; p.grid_w = grid_w; p.depth_scale = 1.0f; p.sort_only = 1;
-    grid_update_kernel<<<batch, GRID_THREADS, 0, stream>>>(p);
+    GMM_CUDA_CHECK(launch_pdl(grid_update_kernel, dim3(batch), dim3(GRID_THREADS), 0, stream, p));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }

@@ -1,6 +1,7 @@
 #include "host_util.h"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -38,6 +39,15 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : GRIDMM_ERR_DRIVER;
+}
+
+bool gridmm_use_pdl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GRIDMM_PDL");      // off by default: measured slightly slower under CUDA-graph replay
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 void gridmm_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -15,3 +15,28 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 
 // counts kernel launches issued through the C ABI (bench.py reports it as gpu_launches)
 void gridmm_count_launch(int n);
+
+// Programmatic dependent launch (PDL): every kernel of this library calls griddepcontrol.launch_dependents at its start and
+// griddepcontrol.wait before its first global-memory access, and is launched with programmatic stream serialization, so
+// the launch latency and prologue (barrier init, TMEM allocation, descriptor prefetch) of kernel N+1 overlap the tail of
+// kernel N.  Opt-in with GRIDMM_PDL=1: under CUDA-graph replay it measured ~4% slower on the navigation step (early
+// dependents compete for SM slots), so the launch attribute is off by default and the device-side instructions are no-ops.
+bool gridmm_use_pdl();
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gridmm_use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif

@@ -53,6 +53,8 @@ __device__ __forceinline__ void store_row(float4 (&x)[HV], float* o32, __half* o
 // ------------------------------------------------------------------------------------------- layer norm
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx, const float* gamma, const float* beta,
                                                         float eps, float* o32, int ld32, __half* o16, int ld16, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     float4 v[HV];
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
 __global__ void __launch_bounds__(256) copy_rows_kernel(const float* x, int ldx, int in_rows_per_b, int in_off, float* o32,
                                                         int ld32, __half* o16, int ld16, int out_rows_per_b, int out_off,
                                                         int rows_per_b, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const int b = row / rows_per_b, r = row - b * rows_per_b;
@@ -86,6 +90,8 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const float* x, int ldx,
 // dominate the logit error (numerics).
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* x, int ldx, int in_rows_per_b, int in_off, __half* o16,
                                                          int ld16, int k_total, int rows_per_b, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const int b = row / rows_per_b, r = row - b * rows_per_b;
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* x, int ldx
 // out[b, off + r] = base[b, r] + table[idx[b, r]] + LN(W f[b, r] + bias)      (base / table optional)
 struct EmbedParams {
     const float* feat; int kin;                 // [rows, kin]
-    const float* w; const float* bias;          // [768, kin], [768]
+    const float* w; const float* bias;          // TRANSPOSED weight [kin, 768], [768]
     const float* gamma; const float* beta; float eps;
     const float* base;                          // [rows, 768] or null
     const float* table; const long long* idx;   // [n, 768], [rows] or null
@@ -120,6 +126,8 @@ struct EmbedParams {
 };
 
 __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= p.rows) return;
     float f[16];
@@ -129,15 +137,12 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
 #pragma unroll
     for (int i = 0; i < HV; ++i) {
         const int col = (i * 32 + lane) * 4;
-        float a[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float s = p.bias[col + c];
-            const float* wr = p.w + static_cast<size_t>(col + c) * p.kin;
-            for (int k = 0; k < p.kin; ++k) s = fmaf(f[k], wr[k], s);
-            a[c] = s;
+        float4 a = *reinterpret_cast<const float4*>(p.bias + col);
+        for (int k = 0; k < p.kin; ++k) {      // transposed weight [kin, 768]: coalesced float4 per lane
+            const float4 w4 = *reinterpret_cast<const float4*>(p.w + static_cast<size_t>(k) * HID + col);
+            a.x = fmaf(f[k], w4.x, a.x); a.y = fmaf(f[k], w4.y, a.y); a.z = fmaf(f[k], w4.z, a.z); a.w = fmaf(f[k], w4.w, a.w);
         }
-        v[i] = make_float4(a[0], a[1], a[2], a[3]);
+        v[i] = a;
     }
     ln_row(v, p.gamma, p.beta, p.eps, lane);
     if (p.base) {
@@ -172,7 +177,7 @@ struct AssembleParams {
     const float* pos_fts;     // [B, n_cells, 5]
     const int* cell_rank;     // [B, n_cells]
     const int* n_nonempty;    // [B]
-    const float* w; const float* bias; const float* gamma; const float* beta;   // grid_pos_embeddings
+    const float* w; const float* bias; const float* gamma; const float* beta;   // grid_pos_embeddings (w TRANSPOSED: [5, 768])
     float* map32;             // [B, seq, 768]
     uint8_t* map_mask;        // [B, seq]
     int batch, n_cells, seq;
@@ -182,6 +187,8 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
     __shared__ int s_inv[256];
     __shared__ int s_red[8];
     __shared__ int s_c, s_k2;
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = p.n_nonempty[b];
     // C = max over the batch; k' for this episode
@@ -218,15 +225,13 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
 #pragma unroll
             for (int i = 0; i < HV; ++i) {
                 const int col = (i * 32 + lane) * 4;
-                float a[4];
+                float4 a = *reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float s = p.bias[col + c];
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) s = fmaf(f[j], p.w[(col + c) * 5 + j], s);
-                    a[c] = s;
+                for (int j = 0; j < 5; ++j) {      // transposed weight [5, 768]
+                    const float4 w4 = *reinterpret_cast<const float4*>(p.w + j * HID + col);
+                    a.x = fmaf(f[j], w4.x, a.x); a.y = fmaf(f[j], w4.y, a.y); a.z = fmaf(f[j], w4.z, a.z); a.w = fmaf(f[j], w4.w, a.w);
                 }
-                v[i] = make_float4(a[0], a[1], a[2], a[3]);
+                v[i] = a;
             }
             ln_row(v, p.gamma, p.beta, 1e-12f, lane);
 #pragma unroll
@@ -251,6 +256,8 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
 // logit[row] = w2 . LN(h[row]) + b2      (h = ReLU(Linear(x)) comes from the GEMM epilogue)
 __global__ void __launch_bounds__(256) cls_tail_kernel(const float* h, const float* gamma, const float* beta, const float* w2,
                                                        const float* b2, float* logit, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     float4 v[HV];
@@ -286,6 +293,8 @@ struct LogitParams {
 __global__ void __launch_bounds__(128) nav_logits_kernel(LogitParams p) {
     extern __shared__ float s_local[];
     __shared__ float s_bw;
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x;
     const float ninf = -INFINITY;
     float fw = 0.5f;
@@ -336,10 +345,10 @@ extern "C" int gridmm_layernorm(const float* x, int ldx, const float* gamma, con
     if (rows <= 0) return 0;
     if (hidden != HID || (ldx % 4) || (out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 4))) return GRIDMM_ERR_SHAPE;
     if (!x || !gamma || !beta) return GRIDMM_ERR_ARG;
-    layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, gamma, beta, eps, out_f32, ld_f32,
-                                                         reinterpret_cast<__half*>(out_f16), ld_f16, rows);
+    GMM_CUDA_CHECK(launch_pdl(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, ldx, gamma, beta, eps, out_f32, ld_f32,
+                                                         reinterpret_cast<__half*>(out_f16), ld_f16, rows));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int in_off, float* out_f32, int ld_f32,
@@ -350,11 +359,11 @@ extern "C" int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int 
     if (rows <= 0) return 0;
     if (hidden != HID || (ldx % 4) || (out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 4))) return GRIDMM_ERR_SHAPE;
     if (!x || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
-    copy_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, in_rows_per_b, in_off, out_f32, ld_f32,
+    GMM_CUDA_CHECK(launch_pdl(copy_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, ldx, in_rows_per_b, in_off, out_f32, ld_f32,
                                                          reinterpret_cast<__half*>(out_f16), ld_f16, out_rows_per_b, out_off,
-                                                         rows_per_b, rows);
+                                                         rows_per_b, rows));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int gridmm_split_rows(const float* x, int ldx, int in_rows_per_b, int in_off, void* out_f16, int ld_f16,
@@ -364,10 +373,10 @@ extern "C" int gridmm_split_rows(const float* x, int ldx, int in_rows_per_b, int
     if (rows <= 0) return 0;
     if (hidden != HID || (ldx % 4) || (ld_f16 % 4) || (k_total % 4) || ld_f16 < 3 * k_total) return GRIDMM_ERR_SHAPE;
     if (!x || !out_f16) return GRIDMM_ERR_ARG;
-    split_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, ldx, in_rows_per_b, in_off, reinterpret_cast<__half*>(out_f16),
-                                                          ld_f16, k_total, rows_per_b, rows);
+    GMM_CUDA_CHECK(launch_pdl(split_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, ldx, in_rows_per_b, in_off, reinterpret_cast<__half*>(out_f16),
+                                                          ld_f16, k_total, rows_per_b, rows));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int gridmm_pos_embed(const float* feat, int kin, const float* w, const float* bias, const float* gamma,
@@ -380,9 +389,9 @@ extern "C" int gridmm_pos_embed(const float* feat, int kin, const float* w, cons
     if (!feat || !w || !bias || !gamma || !beta || (table && !idx) || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
     EmbedParams p{feat, kin, w, bias, gamma, beta, eps, base, table, idx, out_f32, reinterpret_cast<__half*>(out_f16),
                   in_rows_per_b, out_rows_per_b, out_row_off, rows};
-    embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(p);
+    GMM_CUDA_CHECK(launch_pdl(embed_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, p));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int gridmm_grid_assemble(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty,
@@ -395,9 +404,9 @@ extern "C" int gridmm_grid_assemble(const float* proj, const float* pos_fts, con
     if (!proj || !pos_fts || !cell_rank || !n_nonempty || !w || !bias || !gamma || !beta || !map_f32 || !map_mask)
         return GRIDMM_ERR_ARG;
     AssembleParams p{proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq};
-    grid_assemble_kernel<<<dim3(4, batch), 256, 0, stream>>>(p);
+    GMM_CUDA_CHECK(launch_pdl(grid_assemble_kernel, dim3(dim3(4, batch)), dim3(256), 0, stream, p));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int gridmm_cls_tail(const float* h, const float* gamma, const float* beta, const float* w2, const float* b2,
@@ -406,9 +415,9 @@ extern "C" int gridmm_cls_tail(const float* h, const float* gamma, const float* 
     if (rows <= 0) return 0;
     if (hidden != HID) return GRIDMM_ERR_SHAPE;
     if (!h || !gamma || !beta || !w2 || !b2 || !logit) return GRIDMM_ERR_ARG;
-    cls_tail_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(h, gamma, beta, w2, b2, logit, rows);
+    GMM_CUDA_CHECK(launch_pdl(cls_tail_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, h, gamma, beta, w2, b2, logit, rows));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int gridmm_nav_logits(const float* raw_global, const float* raw_grid, const float* raw_local, const float* raw_obj,
@@ -423,7 +432,7 @@ extern "C" int gridmm_nav_logits(const float* raw_global, const float* raw_grid,
         return GRIDMM_ERR_ARG;
     LogitParams p{raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_masks, gmap_visited, vp_nav_masks, vp_obj_masks,
                   fuse_src, bw_mask, global_logits, grid_logits, local_logits, fused_logits, obj_logits, G, V};
-    nav_logits_kernel<<<batch, 128, V * sizeof(float), stream>>>(p);
+    GMM_CUDA_CHECK(launch_pdl(nav_logits_kernel, dim3(batch), dim3(128), V * sizeof(float), stream, p));
     gridmm_count_launch(1);
-    return static_cast<int>(cudaGetLastError());
+    return 0;
 }

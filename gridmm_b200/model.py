@@ -288,6 +288,16 @@ class GlocalTextPathNavCMT(nn.Module):
             self._w16[key] = w
         return w
 
+    def Wt32(self, name):
+        """fp32 transposed copy [in, out] of a small nn.Linear weight (position-feature embeddings)."""
+        key = ("t32", name)
+        w = self._w16.get(key)
+        if w is None:
+            with torch.no_grad():
+                w = self.P(name).detach().float().t().contiguous()
+            self._w16[key] = w
+        return w
+
     def B32(self, *names):
         key = ("bias",) + names
         b = self._w16.get(key)
@@ -516,18 +526,18 @@ class GlocalTextPathNavCMT(nn.Module):
         map32 = self.buf("map32", (B * S, HID), f32)
         map16 = self.buf("map16", (B * S, HID), f16)
         map_mask = self.buf("map_mask", (B, S), u8)
-        ops.grid_assemble(proj32, grid.pos_fts, grid.cell_rank, grid.n_nonempty, self.P("grid_pos_embeddings.0.weight"),
+        ops.grid_assemble(proj32, grid.pos_fts, grid.cell_rank, grid.n_nonempty, self.Wt32("grid_pos_embeddings.0.weight"),
                           self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
                           self.P("grid_pos_embeddings.1.bias"), map32, map_mask, B, NC, S)
         map_mask[:, NC:].copy_(gmap_mask_u8)
         ge = "global_encoder.gmap_pos_embeddings"
-        ops.pos_embed(st["gmap_pos"], self.P(ge + ".0.weight"), self.P(ge + ".0.bias"), self.P(ge + ".1.weight"),
+        ops.pos_embed(st["gmap_pos"], self.Wt32(ge + ".0.weight"), self.P(ge + ".0.bias"), self.P(ge + ".1.weight"),
                       self.P(ge + ".1.bias"), 1e-12, map32, None, G, S, NC, base=st["gmap_img"],
                       table=self.P("global_encoder.gmap_step_embeddings.weight"), idx=st["gmap_step"])
         x32 = self._out("x32", (B * Q, HID), static_out)       # escapes as gmap_embeds / vp_embeds
         x16 = self.buf("x16", (B * Q, HID), f16)
         ve = "local_encoder.vp_pos_embeddings"
-        ops.pos_embed(st["vp_pos"], self.P(ve + ".0.weight"), self.P(ve + ".0.bias"), self.P(ve + ".1.weight"),
+        ops.pos_embed(st["vp_pos"], self.Wt32(ve + ".0.weight"), self.P(ve + ".0.bias"), self.P(ve + ".1.weight"),
                       self.P(ve + ".1.bias"), 1e-12, x32, x16, V, Q, G, base=st["vp_img"])
 
         # ---- grid_encoder (pre-norm, key_padding_mask) and grid_txt_encoder (vilmodel.py:840-841)

@@ -121,13 +121,21 @@ def grid_update(batch, depth, depth_is_f32, depth_scale, pose, view_cs, active, 
               pos_fts.data_ptr(), _lib.stream_ptr())
 
 
+_POOL_WS = {}
+
+
 def pool(fts, feat_dim, slots, t_cap, slot_rows, view_rows, tok_off, perm, cap, cell_start, cell_rank, n_cells, text_fts, l_pad,
-         batch, pooled, w_out=None, num_ctas=0):
+         batch, pooled, w_out=None, num_ctas=0, text_ws=None):
     _chk(fts, torch.float16, "fts"); _chk(text_fts, torch.float16, "text_fts"); _chk(pooled, torch.float16, "pooled")
     _chk(slots, torch.int32, "slots"); _chk(perm, torch.int32, "perm")
+    if text_ws is None:      # persistent per (device, size): CUDA-graph safe
+        key = (fts.device, batch, feat_dim)
+        text_ws = _POOL_WS.get(key)
+        if text_ws is None:
+            text_ws = _POOL_WS[key] = torch.empty(batch * 128 * feat_dim, dtype=torch.float16, device=fts.device)
     _lib.call("gridmm_pool", fts.data_ptr(), feat_dim, slots.data_ptr(), t_cap, slot_rows, view_rows, tok_off, perm.data_ptr(),
-              cap, cell_start.data_ptr(), cell_rank.data_ptr(), n_cells, text_fts.data_ptr(), l_pad, batch, pooled.data_ptr(),
-              _lib.ptr(w_out), num_ctas, _lib.stream_ptr())
+              cap, cell_start.data_ptr(), cell_rank.data_ptr(), n_cells, text_fts.data_ptr(), l_pad, batch, text_ws.data_ptr(),
+              pooled.data_ptr(), _lib.ptr(w_out), num_ctas, _lib.stream_ptr())
 
 
 def cell_sort(batch, cell, n_pts, grid_w, cap, perm, cell_start, cell_rank, n_nonempty):

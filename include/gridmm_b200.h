@@ -72,12 +72,13 @@ int gridmm_cell_sort(int batch, const short* cell, const int* n_pts, int grid_w,
  *                slots[b*t_cap+t]*slot_rows + v*view_rows + tok_off + k   (CLS token skipped via tok_off, env.py:299)
  *   text_fts     fp16 [batch, l_pad, feat_dim] = text_proj(txt_embeds), 16-byte aligned; l_pad <= 128 (the operand lives in
  *                tensor memory, one text position per TMEM lane; unused lanes replicate position 0)
+ *   text_ws      workspace, batch * 128 * feat_dim * 2 bytes, 16-byte aligned: lane-major copy of text_fts (written here)
  *   pooled       fp16 [batch, n_cells, feat_dim], rows >= n_nonempty[b] are not written
  *   w_out        optional f32 [batch,cap]: w per sorted position (tests), or NULL
  *   num_ctas     0 = one CTA per SM */
 int gridmm_pool(const void* fts, int feat_dim, const int* slots, int t_cap, int slot_rows, int view_rows, int tok_off,
                 const int* perm, int cap, const int* cell_start, const int* cell_rank, int n_cells, const void* text_fts,
-                int l_pad, int batch, void* pooled, float* w_out, int num_ctas, cudaStream_t stream);
+                int l_pad, int batch, void* text_ws, void* pooled, float* w_out, int num_ctas, cudaStream_t stream);
 
 /* ---- stage 3: cross-modal encoder blocks ------------------------------------------------------------------
  * nn.Linear on tcgen05: out = act(a[M,K] . w[N,K]^T + bias) + residual; fp16 operands, fp32 accumulate.
@@ -108,12 +109,14 @@ int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int in_off, flo
 int gridmm_split_rows(const float* x, int ldx, int in_rows_per_b, int in_off, void* out_f16, int ld_f16, int k_total,
                       int rows_per_b, int batch, int hidden, cudaStream_t stream);
 
-/* out[b, off + r] = base + table[idx] + LayerNorm(Linear(kin -> 768)(feat))   (vilmodel.py:828-833) */
+/* out[b, off + r] = base + table[idx] + LayerNorm(Linear(kin -> 768)(feat))   (vilmodel.py:828-833)
+ * w is the TRANSPOSED nn.Linear weight, [kin, 768] (coalesced reads). */
 int gridmm_pos_embed(const float* feat, int kin, const float* w, const float* bias, const float* gamma, const float* beta,
                      float eps, const float* base, const float* table, const long long* idx, float* out_f32, void* out_f16,
                      int in_rows_per_b, int out_rows_per_b, int out_row_off, int rows, int hidden, cudaStream_t stream);
 
-/* grid cells of the map sequence + validity mask incl. the reference's compaction quirk (vilmodel.py:813-823) */
+/* grid cells of the map sequence + validity mask incl. the reference's compaction quirk (vilmodel.py:813-823);
+ * w is the TRANSPOSED grid_pos_embeddings.0 weight, [5, 768]. */
 int gridmm_grid_assemble(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty, const float* w,
                          const float* bias, const float* gamma, const float* beta, float* map_f32, unsigned char* map_mask,
                          int batch, int n_cells, int seq, int hidden, cudaStream_t stream);
@@ -129,6 +132,12 @@ int gridmm_nav_logits(const float* raw_global, const float* raw_grid, const floa
                       const unsigned char* vp_nav_masks, const unsigned char* vp_obj_masks, const int* fuse_src,
                       const unsigned char* bw_mask, float* global_logits, float* grid_logits, float* local_logits,
                       float* fused_logits, float* obj_logits, int batch, int G, int V, cudaStream_t stream);
+
+/* Debug hooks (tools/microbench.py only): per-CTA clock64 counters written by the following launches ([grid][8] for the
+ * GEMM, [grid][16] for the pooling kernel: role totals and time spent waiting on each mbarrier).  NULL disables. */
+void gridmm_debug_set_gemm_counters(long long* dbg);
+void gridmm_debug_set_pool_counters(long long* dbg);
+void gridmm_debug_set_pool_mode(int mode);   /* bit0: skip the pooling loop, bit1: skip the softmax weights (timing experiments) */
 
 #ifdef __cplusplus
 }

@@ -122,7 +122,7 @@ def test_pos_embed():
     table = torch.randn(100, 768, generator=g).to(_dev())
     idx = torch.randint(0, 100, (B * G,), generator=g).to(_dev())
     out = torch.zeros(B * S, 768, device=_dev())
-    ops.pos_embed(feat, w, b, gamma, beta, 1e-12, out, None, G, S, 19, base=base, table=table, idx=idx)
+    ops.pos_embed(feat, w.t().contiguous(), b, gamma, beta, 1e-12, out, None, G, S, 19, base=base, table=table, idx=idx)
     ref = base + table[idx] + torch.nn.functional.layer_norm(feat @ w.t() + b, (768,), gamma, beta, 1e-12)
     torch.cuda.synchronize()
     assert (out.view(B, S, 768)[:, 19:] - ref.view(B, G, 768)).abs().max().item() < 2e-5

@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q -x --timeout 150 --timeout-method=thread -p no:cacheprovider > gpurun_out/test_all12.log 2>&1; echo "all gpu tests exit=$?"; tail -4 gpurun_out/test_all12.log
+timeout 600 python tools/microbench.py > gpurun_out/microbench12.log 2>&1; echo "micro exit=$?"; grep -E "^GEMM|^pool|^mode 0" gpurun_out/microbench12.log | cut -c1-110
+for pdl in 1 0; do
+GRIDMM_NO_PDL=$pdl timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench7_nopdl$pdl.json 2> gpurun_out/bench7.err; echo "bench NO_PDL=$pdl exit=$?"; python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench7_nopdl$pdl.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'])
+print(d['roofline']['achieved'], d['roofline']['frac'], d['roofline_pool']['achieved'], d['roofline_pool']['frac']); print(d['kernel_ms_per_step'])
+PY
+done
+tail -5 gpurun_out/bench7.err
