@@ -21,7 +21,8 @@ _ERR = {-1: "GRIDMM_ERR_SHAPE (unsupported size or alignment)", -2: "GRIDMM_ERR_
 
 # name -> argument ctypes, in the order of include/gridmm_b200.h
 _SIGS = {
-    "gridmm_grid_update": [c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+    "gridmm_grid_update": [c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                           c_int, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p],
     "gridmm_cell_sort": [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -37,9 +38,11 @@ _SIGS = {
     "gridmm_split_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "gridmm_pos_embed": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "gridmm_text_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "gridmm_grid_assemble": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_int, c_int, c_int, c_void_p],
     "gridmm_cls_tail": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "gridmm_ce_logits": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "gridmm_nav_logits": [c_void_p] * 16 + [c_int, c_int, c_int, c_void_p],
 }
 

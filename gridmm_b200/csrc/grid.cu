@@ -52,6 +52,8 @@ struct GridParams {
     int flip_y;                // CE: world_y = -rel_y + py
     int negate_map_x;          // CE: map_x = -(...)
     int sort_only;             // 1: `cell` and `n_pts` are inputs (reference-format grid_map); only steps 3-4 run
+    int pos_mode;              // 0: discrete-env polar features (env.py:242-265); 1: the CE code's (x, z, y) convention
+    float max_dist;            // distance normaliser: 30 (env.py:47), 25 / 40 (R2R-CE / RxR-CE)
 };
 
 __device__ __forceinline__ float block_reduce_max(float v, float* red, int tid) {
@@ -238,14 +240,25 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_update_kernel(GridParams
         const float x = __fadd_rn(__fsub_rn(__fmul_rn(static_cast<float>(i), cell_len), half), hc);
         const float y = __fadd_rn(__fsub_rn(__fmul_rn(static_cast<float>(jj), cell_len), half), hc);
         const float r = fmaxf(sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))), 1e-8f);
-        float h = asinf(__fdiv_rn(x, r));
-        if (y < 0.0f) h = 3.14159265358979323846f - h;
         float* o = p.pos_fts + (static_cast<size_t>(b) * n_cells + tid) * 5;
-        o[0] = sinf(h);
-        o[1] = cosf(h);
-        o[2] = 0.0f;   // elevation = asin(0 / r) = 0
-        o[3] = 1.0f;
-        o[4] = r / 30.0f;
+        if (p.pos_mode == 0) {
+            float h = asinf(__fdiv_rn(x, r));
+            if (y < 0.0f) h = 3.14159265358979323846f - h;
+            o[0] = sinf(h);
+            o[1] = cosf(h);
+            o[2] = 0.0f;   // elevation = asin(0 / r) = 0
+            o[3] = 1.0f;
+        } else {
+            // VLN_CE/vlnce_baselines/models/utils.py:125-144 reads (x, z, y): the cell's second coordinate is taken as the
+            // HEIGHT, so heading = asin(x / |x|) = +-pi/2 and elevation = asin(y / r)  (Policy_ViewSelection_GridMap.py:661-684)
+            const float h = asinf(__fdiv_rn(x, fmaxf(fabsf(x), 1e-8f)));
+            const float e = asinf(__fdiv_rn(y, r));
+            o[0] = sinf(h);
+            o[1] = cosf(h);
+            o[2] = sinf(e);
+            o[3] = cosf(e);
+        }
+        o[4] = r / p.max_dist;
     }
 }
 
@@ -253,7 +266,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_update_kernel(GridParams
 
 extern "C" int gridmm_grid_update(int batch, const void* depth, int depth_is_f32, float depth_scale, const float* pose,
                                   const float* view_cs, const unsigned char* active, const float* off7, int flip_y,
-                                  int negate_map_x, int grid_w, int cap, float* wx, float* wy, unsigned char* valid,
+                                  int negate_map_x, int pos_mode, float max_dist, int grid_w, int cap, float* wx, float* wy, unsigned char* valid,
                                   float* bounds, int* n_pts, short* cell, float* half_len, int* perm, int* cell_start,
                                   int* cell_rank, int* n_nonempty, float* pos_fts, cudaStream_t stream) {
     using namespace gmm;
@@ -269,7 +282,7 @@ extern "C" int gridmm_grid_update(int batch, const void* depth, int depth_is_f32
     p.n_nonempty = n_nonempty; p.pos_fts = pos_fts;
     p.cap = cap; p.grid_w = grid_w; p.depth_is_f32 = depth_is_f32; p.depth_scale = depth_scale;
     for (int i = 0; i < 7; ++i) p.off[i] = off7[i];
-    p.flip_y = flip_y; p.negate_map_x = negate_map_x; p.sort_only = 0;
+    p.flip_y = flip_y; p.negate_map_x = negate_map_x; p.sort_only = 0; p.pos_mode = pos_mode; p.max_dist = max_dist;
     GMM_CUDA_CHECK(launch_pdl(grid_update_kernel, dim3(batch), dim3(GRID_THREADS), 0, stream, p));
     gridmm_count_launch(1);
     return 0;

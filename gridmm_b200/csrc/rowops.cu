@@ -165,6 +165,29 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
     store_row(v, p.o32 ? p.o32 + orow * HID : nullptr, p.o16 ? p.o16 + orow * HID : nullptr, lane);
 }
 
+// ------------------------------------------------------------------------------------------- BERT text embeddings
+// LayerNorm(word[ids] + position[l] + token_type[0])   (BertEmbeddings.forward, vilmodel.py:77-93; one warp per token)
+__global__ void __launch_bounds__(256) text_embed_kernel(const long long* ids, const float* word, const float* pos,
+                                                         const float* type0, const float* gamma, const float* beta,
+                                                         float* o32, __half* o16, int L, int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* w = word + static_cast<size_t>(ids[row]) * HID;
+    const float* pe = pos + static_cast<size_t>(row % L) * HID;
+    float4 v[HV];
+#pragma unroll
+    for (int i = 0; i < HV; ++i) {
+        const int col = (i * 32 + lane) * 4;
+        const float4 a = *reinterpret_cast<const float4*>(w + col), b = *reinterpret_cast<const float4*>(pe + col);
+        const float4 c = *reinterpret_cast<const float4*>(type0 + col);
+        v[i] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
+    }
+    ln_row(v, gamma, beta, 1e-12f, lane);
+    store_row(v, o32 ? o32 + static_cast<size_t>(row) * HID : nullptr, o16 ? o16 + static_cast<size_t>(row) * HID : nullptr, lane);
+}
+
 // ------------------------------------------------------------------------------------------- grid-cell assembly
 // Rows [0, n_cells) of every episode's map sequence (vilmodel.py:813-823):
 //   r <  k_b : grid_proj(pooled)[b, r] + grid_pos_embeddings(pos_fts[b, cell of rank r])
@@ -336,6 +359,22 @@ __global__ void __launch_bounds__(128) nav_logits_kernel(LogitParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------- continuous-env action logits
+// VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:791-800: w = sigmoid(fuse); logits[b, j] = global[b, j] * w +
+// local[b, j] * (1 - w) for j < max(candidate_lengths), -inf where vp_nav_masks is false.
+__global__ void __launch_bounds__(128) ce_logits_kernel(const float* raw_global, const float* raw_local, const float* raw_fuse,
+                                                        const uint8_t* vp_nav_masks, float* fused, int G, int V, int maxc) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x;
+    const float fw = 1.0f / (1.0f + expf(-raw_fuse[b]));
+    for (int j = threadIdx.x; j < maxc; j += blockDim.x) {
+        const bool nav = vp_nav_masks[b * V + j] != 0;
+        // both terms are masked with -inf in the reference, so a masked slot is -inf + -inf = -inf
+        fused[b * maxc + j] = nav ? (raw_global[b * G + j] * fw + raw_local[b * V + j] * (1.0f - fw)) : -INFINITY;
+    }
+}
+
 }  // namespace gmm
 
 // ----------------------------------------------------------------------------- C ABI
@@ -394,6 +433,20 @@ extern "C" int gridmm_pos_embed(const float* feat, int kin, const float* w, cons
     return 0;
 }
 
+extern "C" int gridmm_text_embed(const long long* ids, const float* word, const float* pos, const float* type0,
+                                 const float* gamma, const float* beta, float* out_f32, void* out_f16, int batch, int L,
+                                 int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    const int rows = batch * L;
+    if (rows <= 0) return 0;
+    if (hidden != HID) return GRIDMM_ERR_SHAPE;
+    if (!ids || !word || !pos || !type0 || !gamma || !beta || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
+    GMM_CUDA_CHECK(launch_pdl(text_embed_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, ids, word, pos, type0, gamma, beta,
+                              out_f32, reinterpret_cast<__half*>(out_f16), L, rows));
+    gridmm_count_launch(1);
+    return 0;
+}
+
 extern "C" int gridmm_grid_assemble(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty,
                                     const float* w, const float* bias, const float* gamma, const float* beta, float* map_f32,
                                     unsigned char* map_mask, int batch, int n_cells, int seq, int hidden,
@@ -433,6 +486,19 @@ extern "C" int gridmm_nav_logits(const float* raw_global, const float* raw_grid,
     LogitParams p{raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_masks, gmap_visited, vp_nav_masks, vp_obj_masks,
                   fuse_src, bw_mask, global_logits, grid_logits, local_logits, fused_logits, obj_logits, G, V};
     GMM_CUDA_CHECK(launch_pdl(nav_logits_kernel, dim3(batch), dim3(128), V * sizeof(float), stream, p));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+extern "C" int gridmm_ce_logits(const float* raw_global, const float* raw_local, const float* raw_fuse,
+                                const unsigned char* vp_nav_masks, float* fused, int batch, int G, int V, int maxc,
+                                cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (maxc < 1 || maxc > G || maxc > V) return GRIDMM_ERR_SHAPE;
+    if (!raw_global || !raw_local || !raw_fuse || !vp_nav_masks || !fused) return GRIDMM_ERR_ARG;
+    GMM_CUDA_CHECK(launch_pdl(ce_logits_kernel, dim3(batch), dim3(128), 0, stream, raw_global, raw_local, raw_fuse, vp_nav_masks,
+                              fused, G, V, maxc));
     gridmm_count_launch(1);
     return 0;
 }

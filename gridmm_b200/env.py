@@ -31,7 +31,8 @@ PATCH_CENTRES_CE = np.array([19 + 36 * i for i in range(7)])      # Policy_ViewS
 class Geometry:
     """Camera / rotation conventions."""
 
-    def __init__(self, name, depth_scale, tan_half_fov, flip_y, angle_offset, negate_map_x, view_minus_heading, depth_is_f32):
+    def __init__(self, name, depth_scale, tan_half_fov, flip_y, angle_offset, negate_map_x, view_minus_heading, depth_is_f32,
+                 pos_mode=0, max_dist=30.0):
         self.name = name
         self.depth_scale = depth_scale
         self.tan_half_fov = tan_half_fov
@@ -40,6 +41,8 @@ class Geometry:
         self.negate_map_x = negate_map_x
         self.view_minus_heading = view_minus_heading
         self.depth_is_f32 = depth_is_f32
+        self.pos_mode = pos_mode          # 1: the CE code's cell-feature convention (see include/gridmm_b200.h)
+        self.max_dist = max_dist          # MAX_DIST: 30 (r2r/env.py:47), 25 / 40 (Policy_ViewSelection_GridMap.py:39, 269-285)
         # env.py:118: np.array(o, np.float32) * math.tan(...)  ->  f32(o_k) * f32(tan) in fp32
         self.off7 = (np.array(_OFF7, np.float32) * np.float32(tan_half_fov)).astype(np.float32)
 
@@ -48,9 +51,9 @@ GEOMETRIES = {
     # discrete envs: map_nav_src/{r2r,reverie,rxr}/env.py, pretrain_src/data/dataset.py
     "r2r": Geometry("r2r", 4000.0, math.tan(math.pi / 6), False, 0.0, False, False, False),
     # VLN_CE/vlnce_baselines/models/Policy_ViewSelection_GridMap.py:632-641, 689-825 (R2R-CE, hfov 90)
-    "r2r_ce": Geometry("r2r_ce", 1.0, math.tan(math.pi / 4), True, math.pi, True, True, True),
+    "r2r_ce": Geometry("r2r_ce", 1.0, math.tan(math.pi / 4), True, math.pi, True, True, True, pos_mode=1, max_dist=25.0),
     # RxR-CE, hfov 79
-    "rxr_ce": Geometry("rxr_ce", 1.0, math.tan(79 * math.pi / 360), True, math.pi, True, True, True),
+    "rxr_ce": Geometry("rxr_ce", 1.0, math.tan(79 * math.pi / 360), True, math.pi, True, True, True, pos_mode=1, max_dist=40.0),
 }
 
 
@@ -218,7 +221,7 @@ class GridMapBuilder:
         self.d_pose.copy_(self.h_pose, non_blocking=True)
         self.d_view.copy_(self.h_view, non_blocking=True)
         ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, None, g.off7, g.flip_y,
-                        g.negate_map_x, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
+                        g.negate_map_x, g.pos_mode, g.max_dist, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
                         self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
         self.n_steps += 1
         return GridBatch(self)

@@ -442,7 +442,7 @@ class GlocalTextPathNavCMT(nn.Module):
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                     gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
                                     vp_nav_masks, vp_obj_masks, vp_cand_vpids, grid_fts, grid_map, gridmap_pos_fts,
-                                    grid=None, return_intermediates=False):
+                                    grid=None, return_intermediates=False, ce_candidate_lengths=None):
         """vilmodel.py:782-918.  `grid` (a gridmm_b200.env.GridBatch) replaces grid_fts/grid_map/gridmap_pos_fts when the
         grid was built on the device; otherwise the reference-format lists are uploaded and sorted first.
         (`gmap_pair_dists` is accepted and ignored, as in the reference's navigation forward.)"""
@@ -453,8 +453,13 @@ class GlocalTextPathNavCMT(nn.Module):
         G, V = int(gmap_img_embeds.shape[1]), int(vp_img_embeds.shape[1])
         has_obj = vp_obj_masks is not None
         f32, u8 = torch.float32, torch.uint8
+        ce_maxc = int(max(ce_candidate_lengths)) if ce_candidate_lengths is not None else 0
         # host part of the logit fusion (the reference's vpid-string loops) -> small int arrays
-        fuse_src, bw_mask = build_fuse_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, G, V)
+        if ce_maxc:
+            fuse_src, bw_mask = np.zeros((B, G), np.int32), np.zeros((B, V), np.uint8)
+            gmap_visited_masks = torch.zeros(B, G, dtype=torch.uint8)
+        else:
+            fuse_src, bw_mask = build_fuse_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, G, V)
         st = {
             "txt": self._stage("txt", txt_embeds, (B * L, HID), f32),
             "txt_mask": self._stage("txt_mask", txt_masks, (B, L), u8),
@@ -471,7 +476,7 @@ class GlocalTextPathNavCMT(nn.Module):
             "fuse_src": self._stage("fuse_src", torch.from_numpy(fuse_src), (B, G), torch.int32),
             "bw_mask": self._stage("bw_mask", torch.from_numpy(bw_mask), (B, V), u8),
         }
-        dims = (B, L, G, V, has_obj)
+        dims = (B, L, G, V, has_obj, ce_maxc)
         if getattr(self, "use_cuda_graph", False) and not return_intermediates:
             sig = dims + (st["gmap_pos"].shape[1], st["vp_pos"].shape[1], grid.n_cells, grid.t_cap, grid.cap, grid.feat_dim,
                           grid.slot_rows, grid.view_rows, grid.tok_off, grid.slab.data_ptr(), grid.slots.data_ptr(),
@@ -486,7 +491,7 @@ class GlocalTextPathNavCMT(nn.Module):
                 entry = (g, outs)
                 self._graphs[sig] = entry
             entry[0].replay()
-            return dict(entry[1])
+            return dict(entry[1]) if isinstance(entry[1], dict) else entry[1]
         return self._device_forward(st, grid, dims, return_intermediates, False)
 
     def _out(self, name, shape, static):
@@ -496,7 +501,7 @@ class GlocalTextPathNavCMT(nn.Module):
     def _device_forward(self, st, grid, dims, return_intermediates, static_out):
         """Everything below launches only gridmm_* kernels (plus a few tiny mask copies) on persistent buffers."""
         cfg = self.config
-        B, L, G, V, has_obj = dims
+        B, L, G, V, has_obj, ce_maxc = dims
         NC = grid.n_cells
         S, Q, KC = NC + G, G + V, NC + G + L
         f16, f32, u8 = torch.float16, torch.float32, torch.uint8
@@ -584,6 +589,15 @@ class GlocalTextPathNavCMT(nn.Module):
         ops.split_rows(map32, S, NC, G, B, hm16, HID)
         raw_global = self._cls_head("global_sap_head", hg16, B * G, "g")
         raw_local = self._cls_head("local_sap_head", hv16, B * V, "l")
+        if ce_maxc:
+            # continuous-env head (VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:786-800)
+            hf16 = self.buf("hf16", (B, 6 * HID), f16)
+            ops.split_rows(x32, Q, 0, 1, B, hf16, 2 * HID)
+            ops.split_rows(x32, Q, G, 1, B, hf16[:, HID:], 2 * HID)
+            raw_fuse = self._cls_head("sap_fuse_linear", hf16, B, "f")
+            fused = self._out("ce_fused", (B, ce_maxc), static_out)
+            ops.ce_logits(raw_global, raw_local, raw_fuse, st["vp_nav"], fused, B, G, V, ce_maxc)
+            return fused
         raw_grid = self._cls_head("grid_sap_head", hm16, B * G, "m")
         raw_fuse = None
         if cfg.glocal_fuse:
@@ -613,8 +627,112 @@ class GlocalTextPathNavCMT(nn.Module):
             outs.update(inter)
         return outs
 
+    # ------------------------------------------------------------------ language / panorama
+    @torch.no_grad()
+    def forward_text(self, txt_ids, txt_masks):
+        """vilmodel.py:730-734: BertEmbeddings + num_l_layers BertLayer (self-attention + FFN, post-norm, -10000 mask)."""
+        self._refresh_w16()
+        dev = next(self.parameters()).device
+        B, L = int(txt_ids.shape[0]), int(txt_ids.shape[1])
+        ids = torch.as_tensor(txt_ids).to(dev, torch.int64).contiguous().view(-1)
+        mask = torch.as_tensor(txt_masks).to(dev)
+        mask_u8 = (mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)).contiguous()
+        x32 = torch.empty(B * L, HID, dtype=torch.float32, device=dev)
+        x16 = self.buf("lang_x16", (B * L, HID), torch.float16)
+        ops.text_embed(ids, self.P("embeddings.word_embeddings.weight"), self.P("embeddings.position_embeddings.weight"),
+                       self.P("embeddings.token_type_embeddings.weight"), self.P("embeddings.LayerNorm.weight"),
+                       self.P("embeddings.LayerNorm.bias"), x32, x16, B, L)
+        for i in range(self.config.num_l_layers):
+            p = "lang_encoder.layer.%d" % i
+            self._self_post(x32, x16, p + ".attention", mask_u8, B, L, "lang")
+            self._ffn_post(x32, x16, p + ".intermediate", p + ".output", B * L, "lang")
+        return x32.view(B, L, HID)
+
+    @torch.no_grad()
+    def forward_panorama_per_step(self, view_img_fts, obj_img_fts, loc_fts, nav_types, view_lens, obj_lens):
+        """vilmodel.py:736-780: image/object/location embeddings + the pre-norm panorama encoder."""
+        self._refresh_w16()
+        cfg = self.config
+        dev = next(self.parameters()).device
+        f16, f32 = torch.float16, torch.float32
+        ie = "img_embeddings"
+
+        def embed(fts, lin, ln, tag):
+            Bn, n, k = fts.shape
+            a16 = torch.as_tensor(fts).to(dev).reshape(Bn * n, k).to(f16)
+            h = self.buf("pano_h32_" + tag, (Bn * n, HID), f32)
+            ops.linear(a16, self.W16(lin + ".weight"), self.B32(lin + ".bias"), out_f32=h)
+            out = self.buf("pano_e32_" + tag, (Bn * n, HID), f32)
+            self._ln(h, ln, 1e-12, out, None)
+            return out.view(Bn, n, HID)
+
+        view = embed(view_img_fts, ie + ".img_linear", ie + ".img_layer_norm", "v")
+        B = view.shape[0]
+        view_lens = torch.as_tensor(view_lens).to(dev)
+        if obj_img_fts is not None:
+            has_own = (ie + ".obj_linear.weight") in self._spec
+            obj = embed(obj_img_fts, ie + (".obj_linear" if has_own else ".img_linear"),
+                        ie + (".obj_layer_norm" if has_own else ".img_layer_norm"), "o")
+            obj_lens = torch.as_tensor(obj_lens).to(dev)
+            lens = view_lens + obj_lens
+            vl, ol = view_lens.tolist(), obj_lens.tolist()          # host sync, as in the reference's zip loop (:755-761)
+            n = max(a + b for a, b in zip(vl, ol))
+            img = torch.zeros(B, n, HID, dtype=f32, device=dev)
+            for b in range(B):
+                img[b, :vl[b]] = view[b, :vl[b]]
+                if ol[b] > 0:
+                    img[b, vl[b]:vl[b] + ol[b]] = obj[b, :ol[b]]
+        else:
+            img, lens, n = view, view_lens, view.shape[1]
+        base = (img + self.P("embeddings.token_type_embeddings.weight")[1]).reshape(B * n, HID).contiguous()
+        loc = torch.as_tensor(loc_fts).to(dev, f32).reshape(B * n, -1).contiguous()
+        nav = torch.as_tensor(nav_types).to(dev, torch.int64).reshape(-1).contiguous()
+        tmp = self.buf("pano_tmp32", (B * n, HID), f32)
+        ops.pos_embed(loc, self.Wt32(ie + ".loc_linear.weight"), self.P(ie + ".loc_linear.bias"), self.P(ie + ".loc_layer_norm.weight"),
+                      self.P(ie + ".loc_layer_norm.bias"), 1e-12, tmp, None, n, n, 0, base=base,
+                      table=self.P(ie + ".nav_type_embedding.weight"), idx=nav)
+        x32 = torch.empty(B * n, HID, dtype=f32, device=dev)
+        x16 = self.buf("pano_x16", (B * n, HID), f16)
+        self._ln(tmp, ie + ".layer_norm", 1e-12, x32, x16)
+        masks = torch.arange(n, device=dev)[None, :] < lens[:, None]
+        if cfg.num_pano_layers > 0:
+            self._prenorm_encoder(ie + ".pano_encoder", cfg.num_pano_layers, x32, x16, masks.view(torch.uint8).contiguous(), B, n, "pano")
+        return x32.view(B, n, HID), masks
+
+    def forward_navigation_ce(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
+                              vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, grid_fts, grid_map_indexs, gridmap_pos_fts,
+                              candidate_lengths, grid=None):
+        """Continuous-env signature (VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:710-800, the 14-tuple of
+        Policy_ViewSelection_GridMap.py:622-623).  Returns fused logits [B, max(candidate_lengths)]; the policy's rotation of the
+        [stop] slot to the end (:625-626) is `roll_stop_last`."""
+        return self.forward_navigation_per_step(
+            txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks, None, None, None,
+            vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, None, None, grid_fts, grid_map_indexs, gridmap_pos_fts,
+            grid=grid, ce_candidate_lengths=candidate_lengths)
+
+    @staticmethod
+    def roll_stop_last(logits, candidate_lengths):
+        """Policy_ViewSelection_GridMap.py:625-626."""
+        out = logits.clone()
+        for b, n in enumerate(candidate_lengths):
+            out[b, :n] = torch.cat((logits[b, 1:n], logits[b, 0:1]), 0)
+        return out
+
     def forward(self, mode, batch, **kwargs):
-        """vilmodel.py:920-939."""
+        """vilmodel.py:920-939.  A tuple batch selects the continuous-env calling convention (gridmap/vilmodel.py:802-817)."""
+        if isinstance(batch, (tuple, list)):
+            if mode == "language":
+                return self.forward_text(batch[0], batch[1])
+            if mode == "panorama":
+                return self.forward_panorama_per_step(batch[0], None, batch[1], batch[2], batch[3], None)
+            if mode == "navigation":
+                return self.forward_navigation_ce(*batch, **kwargs)
+            raise NotImplementedError("wrong mode: %s" % mode)
+        if mode == "language":
+            return self.forward_text(batch["txt_ids"], batch["txt_masks"])
+        if mode == "panorama":
+            return self.forward_panorama_per_step(batch["view_img_fts"], batch["obj_img_fts"], batch["loc_fts"],
+                                                  batch["nav_types"], batch["view_lens"], batch["obj_lens"])
         if mode == "navigation":
             g = batch.get("grid") if hasattr(batch, "get") else None
             return self.forward_navigation_per_step(
@@ -623,9 +741,6 @@ class GlocalTextPathNavCMT(nn.Module):
                 batch["gmap_vpids"], batch["vp_img_embeds"], batch["vp_pos_fts"], batch["vp_masks"], batch["vp_nav_masks"],
                 batch["vp_obj_masks"], batch["vp_cand_vpids"], batch["grid_fts"], batch["grid_map"],
                 batch["gridmap_pos_fts"], grid=g, **kwargs)
-        if mode in ("language", "panorama"):
-            raise NotImplementedError(
-                "mode %r (vilmodel.py:730-780) is outside the accelerated hot path in this round (SURVEY 8f rank 1/3)" % mode)
         raise NotImplementedError("wrong mode: %s" % mode)
 
 

@@ -82,6 +82,12 @@ def pos_embed(feat, w, bias, gamma, beta, eps, out_f32, out_f16, in_rows_per_b, 
               in_rows_per_b, out_rows_per_b, out_row_off, rows, HID, _lib.stream_ptr())
 
 
+def text_embed(ids, word, pos, type0, gamma, beta, out_f32, out_f16, batch, L):
+    _chk(ids, torch.int64, "ids"); _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
+    _lib.call("gridmm_text_embed", ids.data_ptr(), word.data_ptr(), pos.data_ptr(), type0.data_ptr(), gamma.data_ptr(),
+              beta.data_ptr(), _lib.ptr(out_f32), _lib.ptr(out_f16), batch, L, HID, _lib.stream_ptr())
+
+
 def grid_assemble(proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq):
     _chk(proj, torch.float32, "proj"); _chk(pos_fts, torch.float32, "pos_fts"); _chk(cell_rank, torch.int32, "cell_rank")
     _chk(n_nonempty, torch.int32, "n_nonempty"); _chk(map_f32, torch.float32, "map_f32"); _chk(map_mask, torch.uint8, "map_mask")
@@ -110,13 +116,20 @@ def nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_masks, g
               _lib.stream_ptr())
 
 
-def grid_update(batch, depth, depth_is_f32, depth_scale, pose, view_cs, active, off7_host, flip_y, negate_map_x, grid_w, cap,
+def ce_logits(raw_global, raw_local, raw_fuse, vp_nav_masks, fused, batch, G, V, maxc):
+    _chk(vp_nav_masks, torch.uint8, "vp_nav_masks"); _chk(fused, torch.float32, "fused")
+    _lib.call("gridmm_ce_logits", raw_global.data_ptr(), raw_local.data_ptr(), raw_fuse.data_ptr(), vp_nav_masks.data_ptr(),
+              fused.data_ptr(), batch, G, V, maxc, _lib.stream_ptr())
+
+
+def grid_update(batch, depth, depth_is_f32, depth_scale, pose, view_cs, active, off7_host, flip_y, negate_map_x, pos_mode,
+                max_dist, grid_w, cap,
                 wx, wy, valid, bounds, n_pts, cell, half_len, perm, cell_start, cell_rank, n_nonempty, pos_fts):
     import ctypes
     off = (ctypes.c_float * 7)(*[float(x) for x in off7_host])
     _lib.call("gridmm_grid_update", batch, depth.data_ptr(), int(depth_is_f32), float(depth_scale), pose.data_ptr(),
-              view_cs.data_ptr(), _lib.ptr(active), ctypes.cast(off, ctypes.c_void_p), int(flip_y), int(negate_map_x), grid_w,
-              cap, wx.data_ptr(), wy.data_ptr(), valid.data_ptr(), bounds.data_ptr(), n_pts.data_ptr(), cell.data_ptr(),
+              view_cs.data_ptr(), _lib.ptr(active), ctypes.cast(off, ctypes.c_void_p), int(flip_y), int(negate_map_x),
+              int(pos_mode), float(max_dist), grid_w, cap, wx.data_ptr(), wy.data_ptr(), valid.data_ptr(), bounds.data_ptr(), n_pts.data_ptr(), cell.data_ptr(),
               half_len.data_ptr(), perm.data_ptr(), cell_start.data_ptr(), cell_rank.data_ptr(), n_nonempty.data_ptr(),
               pos_fts.data_ptr(), _lib.stream_ptr())
 

@@ -50,6 +50,16 @@ def expand_depth(depth_sub):
     return full
 
 
+PATCH_CENTRES_CE = np.array([19 + 36 * i for i in range(7)])
+
+
+def expand_depth_ce(depth_sub_f32):
+    """float32[12,49] metres -> the CE policy's float32[12,256,256] depth stack (zeros elsewhere)."""
+    full = np.zeros((12, 256, 256), dtype=np.float32)
+    full[:, PATCH_CENTRES_CE[:, None], PATCH_CENTRES_CE[None, :]] = depth_sub_f32.reshape(N_VIEWS, 7, 7)
+    return full
+
+
 def make_nav_inputs(batch, seed=0, txt_len=80, gmap_len=20, n_views=36, n_objs=0,
                     dim=768, min_txt=20, ragged=True):
     """Everything `forward('navigation')` needs except the grid tensors
@@ -125,13 +135,50 @@ def make_nav_inputs(batch, seed=0, txt_len=80, gmap_len=20, n_views=36, n_objs=0
     }
 
 
+def make_lang_inputs(batch, seed=0, txt_len=80, vocab=30522, min_txt=8):
+    """`forward('language')` inputs (map_nav_src/r2r/agent.py:62-77): padded token ids + masks."""
+    rng = np.random.default_rng(seed + 31337)
+    lens = rng.integers(min_txt, txt_len + 1, size=batch)
+    lens[0] = txt_len
+    ids = rng.integers(1, vocab, size=(batch, txt_len)).astype(np.int64)
+    masks = np.arange(txt_len)[None, :] < lens[:, None]
+    ids = ids * masks                                   # pad id 0
+    return {"txt_ids": ids, "txt_masks": masks}
+
+
+def make_pano_inputs(batch, seed=0, n_views=36, n_objs=0, dim=768, loc_dim=7):
+    """`forward('panorama')` inputs (map_nav_src/r2r/agent.py:79-129; reverie/agent_obj.py adds object tokens)."""
+    rng = np.random.default_rng(seed + 4242)
+    f32 = np.float32
+    view_lens = np.full(batch, n_views, dtype=np.int64)
+    out = {"view_img_fts": rng.standard_normal((batch, n_views, dim), dtype=f32), "view_lens": view_lens}
+    if n_objs > 0:
+        obj_lens = rng.integers(0, n_objs + 1, size=batch).astype(np.int64)
+        obj_lens[0] = n_objs
+        obj = rng.standard_normal((batch, n_objs, dim), dtype=f32)
+        obj *= (np.arange(n_objs)[None, :] < obj_lens[:, None])[:, :, None]
+        out.update(obj_img_fts=obj, obj_lens=obj_lens)
+        n = int((view_lens + obj_lens).max())
+    else:
+        out.update(obj_img_fts=None, obj_lens=None)
+        n = n_views
+    out["loc_fts"] = rng.standard_normal((batch, n, loc_dim), dtype=f32)
+    nav_types = rng.integers(0, 2, size=(batch, n)).astype(np.int64)
+    if n_objs > 0:
+        for b in range(batch):
+            nav_types[b, n_views:n_views + int(out["obj_lens"][b])] = 2
+            nav_types[b, n_views + int(out["obj_lens"][b]):] = 0
+    out["nav_types"] = nav_types
+    return out
+
+
 def to_torch(nav, device="cpu"):
     """numpy nav-input dict -> torch tensors with the reference's dtypes."""
     import torch
     out = {}
     for k, v in nav.items():
         if isinstance(v, np.ndarray):
-            out[k] = torch.from_numpy(v).to(device)
+            out[k] = torch.from_numpy(np.ascontiguousarray(v)).to(device)
         else:
             out[k] = v
     return out

@@ -44,6 +44,9 @@ void gridmm_launch_count_reset(void);
  *   view_cs      [batch,12,2] cos/sin of each view's angle (R2R: v*pi/6; CE: v*pi/6 - heading), host double -> fp32
  *   active       [batch] or NULL; 0 = no new viewpoint for this episode (NULL = all active, the reference's behaviour)
  *   off7         HOST pointer, 7 floats: f32(o_k) * f32(tan(hfov/2)), o = -6/7..6/7 (env.py:118)
+ *   pos_mode     0: discrete-env cell features [sin h, cos h, 0, 1, dist/max_dist] (env.py:242-265); 1: the CE code's
+ *                (x, z, y) reading of the same call (VLN_CE/.../Policy_ViewSelection_GridMap.py:661-684, models/utils.py:125-144);
+ *                max_dist = 30 (env.py:47), 25 (R2R-CE), 40 (RxR-CE)
  *   state        wx, wy [batch,cap] f32; valid [batch,cap] u8; bounds [batch,4] = max_x,min_x,max_y,min_y
  *                (initialise to -10000,10000,-10000,10000: env.py:187-190); n_pts [batch] int32 (initialise to 0)
  *   outputs      cell [batch,cap] int16 (-1 = masked: env.py:306,366-369); half_len [batch];
@@ -52,7 +55,7 @@ void gridmm_launch_count_reset(void);
  * An episode whose n_pts + 588 would exceed cap is left unchanged (the host wrapper grows the buffers first). */
 int gridmm_grid_update(int batch, const void* depth, int depth_is_f32, float depth_scale, const float* pose,
                        const float* view_cs, const unsigned char* active, const float* off7, int flip_y, int negate_map_x,
-                       int grid_w, int cap, float* wx, float* wy, unsigned char* valid, float* bounds, int* n_pts,
+                       int pos_mode, float max_dist, int grid_w, int cap, float* wx, float* wy, unsigned char* valid, float* bounds, int* n_pts,
                        short* cell, float* half_len, int* perm, int* cell_start, int* cell_rank, int* n_nonempty,
                        float* pos_fts, cudaStream_t stream);
 
@@ -115,6 +118,11 @@ int gridmm_pos_embed(const float* feat, int kin, const float* w, const float* bi
                      float eps, const float* base, const float* table, const long long* idx, float* out_f32, void* out_f16,
                      int in_rows_per_b, int out_rows_per_b, int out_row_off, int rows, int hidden, cudaStream_t stream);
 
+/* BERT text embeddings: LayerNorm(word[ids] + position[0..L) + token_type[0]), eps 1e-12 (BertEmbeddings.forward,
+ * vilmodel.py:77-93); ids int64 [batch, L]. */
+int gridmm_text_embed(const long long* ids, const float* word, const float* pos, const float* type0, const float* gamma,
+                      const float* beta, float* out_f32, void* out_f16, int batch, int L, int hidden, cudaStream_t stream);
+
 /* grid cells of the map sequence + validity mask incl. the reference's compaction quirk (vilmodel.py:813-823);
  * w is the TRANSPOSED grid_pos_embeddings.0 weight, [5, 768]. */
 int gridmm_grid_assemble(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty, const float* w,
@@ -132,6 +140,11 @@ int gridmm_nav_logits(const float* raw_global, const float* raw_grid, const floa
                       const unsigned char* vp_nav_masks, const unsigned char* vp_obj_masks, const int* fuse_src,
                       const unsigned char* bw_mask, float* global_logits, float* grid_logits, float* local_logits,
                       float* fused_logits, float* obj_logits, int batch, int G, int V, cudaStream_t stream);
+
+/* continuous-env action logits (VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:791-800):
+ * fused[b, j] = global[b, j] * w + local[b, j] * (1 - w), w = sigmoid(raw_fuse[b]), j < maxc; -inf where vp_nav_masks = 0. */
+int gridmm_ce_logits(const float* raw_global, const float* raw_local, const float* raw_fuse, const unsigned char* vp_nav_masks,
+                     float* fused, int batch, int G, int V, int maxc, cudaStream_t stream);
 
 /* Debug hooks (tools/microbench.py only): per-CTA clock64 counters written by the following launches ([grid][8] for the
  * GEMM, [grid][16] for the pooling kernel: role totals and time spent waiting on each mbarrier).  NULL disables. */

@@ -42,7 +42,9 @@ class _AttrDict(dict):
 def _stub(name, **attrs):
     if name in sys.modules:
         return sys.modules[name]
+    import importlib.machinery
     m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
     for k, v in attrs.items():
         setattr(m, k, v)
     sys.modules[name] = m
@@ -197,3 +199,88 @@ def ref_step(env, i, scan, vp, heading, depth_u16, clip_fp16, pos_xy):
      env.min_y[i], gridmap_pos_fts) = out
     env.global_semantic[i] = np.asarray(env.global_semantic[i]).view(_NeverEqList)
     return np.asarray(env.global_semantic[i]), np.array(env.global_map[i]), gridmap_pos_fts
+
+
+# ----------------------------------------------------------------------------------------------- continuous-env variant
+CE_ROOT = os.path.join(REF_ROOT, "VLN_CE", "vlnce_baselines", "models")
+
+
+def _extract_functions(path, names, class_name=None):
+    """AST-extract function definitions (module level, or methods of `class_name`) from a reference file WITHOUT importing
+    the module (the CE policy file imports habitat / gym / timm, which are absent here).  Returns source-compiled objects."""
+    import ast
+    tree = ast.parse(open(path).read(), filename=path)
+    body = tree.body
+    if class_name is not None:
+        body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name).body
+    picked = [n for n in body if isinstance(n, ast.FunctionDef) and n.name in names]
+    missing = set(names) - {n.name for n in picked}
+    if missing:
+        raise RuntimeError("%s lacks %s" % (path, sorted(missing)))
+    return picked
+
+
+def load_reference_ce_grid(batch_size, dataset="R2R", max_dist=25):
+    """The reference's continuous-env grid builder: `get_rel_position`, `get_gridmap_pos_fts`, `getGlobalMap` of
+    VLN_CE/vlnce_baselines/models/Policy_ViewSelection_GridMap.py (:632-641, 661-684, 689-825) and the two helpers of
+    VLN_CE/vlnce_baselines/models/utils.py (:110-144), compiled from the reference's own source text into a bare class."""
+    import ast
+    import math
+    pol = os.path.join(CE_ROOT, "Policy_ViewSelection_GridMap.py")
+    utl = os.path.join(CE_ROOT, "utils.py")
+    helpers = _extract_functions(utl, ["calculate_vp_rel_pos_fts", "get_angle_fts"])
+    cls_name = next(n.name for n in ast.parse(open(pol).read()).body
+                    if isinstance(n, ast.ClassDef) and any(isinstance(m, ast.FunctionDef) and m.name == "getGlobalMap" for m in n.body))
+    methods = _extract_functions(pol, ["get_rel_position", "get_gridmap_pos_fts", "getGlobalMap"], class_name=cls_name)
+    holder = ast.ClassDef(name="RefCEGrid", bases=[], keywords=[], body=methods, decorator_list=[])
+    mod = ast.Module(body=helpers + [holder], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"np": np, "math": math, "DATASET": dataset, "MAX_DIST": max_dist}
+    exec(compile(mod, pol, "exec"), ns)
+    g = ns["RefCEGrid"]()
+    g.global_fts = [[] for _ in range(batch_size)]
+    g.global_position_x = [[] for _ in range(batch_size)]
+    g.global_position_y = [[] for _ in range(batch_size)]
+    g.global_mask = [[] for _ in range(batch_size)]
+    g.global_map_index = [[] for _ in range(batch_size)]
+    g.max_x = [-10000 for _ in range(batch_size)]
+    g.min_x = [10000 for _ in range(batch_size)]
+    g.max_y = [-10000 for _ in range(batch_size)]
+    g.min_y = [10000 for _ in range(batch_size)]
+    g.headings = [0.0 for _ in range(batch_size)]
+    return g
+
+
+def ref_ce_step(g, i, heading, depth_f32, clip_fp16, pos_xy):
+    """One reference CE getGlobalMap call.  depth_f32: float32[12,256,256] metres; clip_fp16: [12,50,768]."""
+    g.headings[i] = heading
+    out = g.getGlobalMap(i, {"x": float(pos_xy[0]), "y": float(pos_xy[1])}, heading, depth_f32, clip_fp16, None)
+    g.global_fts[i] = np.asarray(out[0]).view(_NeverEqList)          # shim 4 (`== []` under numpy >= 2)
+    return np.asarray(out[0]), np.array(out[4]), out[9]
+
+
+def load_reference_ce_model(**cfg):
+    """VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py GlocalTextPathNavCMT (the CE copy).  Its constructor builds an online
+    CLIP (pure torch, importable) and `timm.create_model(...)` (timm is absent: stubbed with an empty module -- neither is
+    touched by forward('navigation'))."""
+    import importlib
+    import torch
+    _install_stubs()
+    from transformers import BertConfig, BertPreTrainedModel  # noqa: F401  (resolve transformers' lazy imports BEFORE timm is stubbed)
+    if "timm" not in sys.modules:
+        t = _stub("timm", create_model=lambda *a, **k: torch.nn.Identity())
+        d = _stub("timm.data", resolve_data_config=lambda *a, **k: {})
+        tf = _stub("timm.data.transforms_factory", create_transform=lambda *a, **k: None)
+        t.data = d
+        d.transforms_factory = tf
+    pkg = types.ModuleType("ce_gridmap")
+    pkg.__path__ = [os.path.join(CE_ROOT, "gridmap")]
+    sys.modules["ce_gridmap"] = pkg
+    vil = importlib.import_module("ce_gridmap.vilmodel")
+    cls = vil.GlocalTextPathNavCMT
+    cls.init_weights = lambda self: None
+    kw = dict(obj_feat_size=0)
+    kw.update(cfg)
+    model = cls(make_config(**kw))
+    model.eval()
+    return model

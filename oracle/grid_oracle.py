@@ -41,6 +41,8 @@ class R2RGeometry:
     flip_y = False                            # global_y = rel_y + pos.y (env.py:292)
     angle_offset = 0.0                        # angle = -heading (env.py:337)
     negate_map_x = False
+    ce_pos_fts = False
+    max_dist = 30.0                           # env.py:47
 
     @staticmethod
     def view_angle(v, heading):
@@ -54,6 +56,8 @@ class CEGeometry:
     flip_y = True                             # global_y = -rel_y + pos.y (:735)
     angle_offset = math.pi                    # angle = -heading + pi (:781)
     negate_map_x = True                       # map_x = -(...) (:790)
+    ce_pos_fts = True                         # calculate_vp_rel_pos_fts reads (x, z, y): VLN_CE/.../models/utils.py:125-144
+    max_dist = 25.0                           # MAX_DIST (:39; 40 for RxR-CE :282-285)
 
     @staticmethod
     def view_angle(v, heading):
@@ -143,7 +147,7 @@ def grid_step(state, depth_sub, clip, pos_xy, heading, grid_w=14, geom=R2RGeomet
     return fts, cell, half
 
 
-def gridmap_pos_fts(half_len, grid_w=14):
+def gridmap_pos_fts(half_len, grid_w=14, geom=R2RGeometry):
     """env.py:242-265 + :60-77 + :52-58 -> f32[grid_w^2, 5] = [sin h, cos h, sin e, cos e, dist/30].
 
     The reference evaluates this in numpy scalar arithmetic whose width follows
@@ -157,13 +161,21 @@ def gridmap_pos_fts(half_len, grid_w=14):
         for j in range(grid_w):
             x = f32(i) * cell_len - half_len + cell_len / f32(2)
             y = f32(j) * cell_len - half_len + cell_len / f32(2)
+            if geom.ce_pos_fts:
+                # Policy_ViewSelection_GridMap.py:661-684 passes (x, y, 0) to a helper that reads (x, z, y): dz = y, dy = 0
+                xy = max(np.sqrt(x * x), 1e-8)
+                xyz = max(np.sqrt(x * x + y * y), 1e-8)
+                hs.append(np.arcsin(x / xy))
+                es.append(np.arcsin(y / xyz))
+                ds.append(xyz / geom.max_dist)
+                continue
             xy = max(np.sqrt(x * x + y * y), 1e-8)
             heading = np.arcsin(x / xy)
             if y < 0:
                 heading = np.pi - heading
             hs.append(heading)
             es.append(np.arcsin(f32(0) / xy))
-            ds.append(xy / MAX_DIST)
+            ds.append(xy / geom.max_dist)
     hs = np.array(hs).astype(f32)
     es = np.array(es).astype(f32)
     ds = np.array(ds).astype(f32)

@@ -81,6 +81,94 @@ def reference_nav(ep_kw, nav_kw, model_kw):
     return outs
 
 
+AUX_CASES = {
+    # forward('language') and forward('panorama'): name -> (seed, model kwargs, input kwargs)
+    "lang_small": (31, dict(num_l_layers=2), dict(batch=3, txt_len=24)),
+    "pano_r2r": (32, dict(num_pano_layers=2), dict(batch=3, n_views=36, n_objs=0)),
+    "pano_reverie": (33, dict(num_pano_layers=2, obj_feat_size=768), dict(batch=3, n_views=36, n_objs=8)),
+}
+
+
+def make_aux():
+    from gridmm_b200.model import NavConfig, param_spec
+    for name, (seed, model_kw, in_kw) in AUX_CASES.items():
+        kw = dict(MODEL_KW); kw.update(model_kw)
+        model = _refshim.load_reference_model(seed=0, **kw)
+        spec = param_spec(NavConfig(**kw))
+        assert list(model.state_dict().keys()) == list(spec.keys())
+        w = synth.make_weights({k: v[0] for k, v in spec.items()}, seed=seed)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+        with torch.no_grad():
+            if name.startswith("lang"):
+                out = model("language", synth.to_torch(synth.make_lang_inputs(seed=seed, **in_kw)))
+                save = {"txt_embeds": out.numpy()}
+            else:
+                embeds, masks = model("panorama", synth.to_torch(synth.make_pano_inputs(seed=seed, **in_kw)))
+                save = {"pano_embeds": embeds.numpy(), "pano_masks": masks.numpy()}
+        path = os.path.join(GOLD, "aux_%s.npz" % name)
+        np.savez_compressed(path, **save)
+        print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()})
+
+
+CE_GRID_CASE = dict(seed=41, batch=3, steps=6)
+CE_NAV_CASE = (dict(batch=3, steps=3, seed=42), dict(txt_len=24, gmap_len=10, n_views=12, n_objs=0))
+
+
+def reference_ce_grid(ep):
+    B, T = ep["pos"].shape[:2]
+    g = _refshim.load_reference_ce_grid(B)
+    dep = (ep["depth_sub"].astype(np.float32) / 4000.0).astype(np.float32)          # CE depth is float32 metres
+    cells = [[None] * T for _ in range(B)]
+    fts, pos_fts = [None] * B, [None] * B
+    for t in range(T):
+        for b in range(B):
+            f, gm, pf = _refshim.ref_ce_step(g, b, float(ep["heading"][b, t]), synth.expand_depth_ce(dep[b, t]),
+                                             ep["clip"][b, t], ep["pos"][b, t])
+            cells[b][t] = gm.astype(np.int16)
+            fts[b], pos_fts[b] = f, pf
+    return cells, fts, pos_fts
+
+
+def make_ce():
+    """Continuous-env variant: the reference's CE getGlobalMap (compiled from its source text) and the CE
+    copy of GlocalTextPathNavCMT.forward('navigation', 14-tuple)."""
+    from gridmm_b200.model import NavConfig, param_spec
+    case = CE_GRID_CASE
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    cells, _, pos_fts = reference_ce_grid(ep)
+    out = {"pos_fts_last": np.stack(pos_fts).astype(np.float32)}
+    for b in range(case["batch"]):
+        for t in range(case["steps"]):
+            out["cell_b%d_t%d" % (b, t)] = cells[b][t]
+    path = os.path.join(GOLD, "grid_ce_s%d.npz" % case["seed"])
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path))
+
+    ep_kw, nav_kw = CE_NAV_CASE
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, pos_fts = reference_ce_grid(ep)
+    B, T = ep["pos"].shape[:2]
+    kw = dict(MODEL_KW, graph_sprels=False)            # the CE copy of GlobalMapEncoder has no sprel_linear
+    model = _refshim.load_reference_ce_model(**kw)
+    spec = param_spec(NavConfig(**kw))
+    w = synth.make_weights({k: v[0] for k, v in spec.items()}, seed=ep_kw["seed"])
+    res = model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith(("clip.", "visual_encoder.")) for k in res.missing_keys), res.missing_keys
+    nav = synth.to_torch(synth.make_nav_inputs(ep_kw["batch"], seed=ep_kw["seed"], **nav_kw))
+    cand = [int(x) for x in nav["vp_nav_masks"].sum(1)]
+    tup = (nav["txt_embeds"], nav["txt_masks"], nav["gmap_img_embeds"], nav["gmap_step_ids"], nav["gmap_pos_fts"],
+           nav["gmap_masks"], nav["vp_img_embeds"], nav["vp_pos_fts"], nav["vp_masks"], nav["vp_nav_masks"],
+           [torch.from_numpy(np.ascontiguousarray(f)) for f in fts],
+           [torch.from_numpy(cells[b][T - 1].astype(np.float64)) for b in range(B)],
+           torch.from_numpy(np.stack(pos_fts).astype(np.float32)), cand)
+    with torch.no_grad():
+        logits = model("navigation", tup)
+    path = os.path.join(GOLD, "nav_ce_small.npz")
+    np.savez_compressed(path, fused_logits=logits.numpy(), candidate_lengths=np.array(cand))
+    print("wrote", path, os.path.getsize(path), tuple(logits.shape))
+
+
 def make_nav():
     for name, (ep_kw, nav_kw, model_kw) in NAV_CASES.items():
         outs = reference_nav(ep_kw, nav_kw, model_kw)
@@ -95,5 +183,12 @@ if __name__ == "__main__":
         raise SystemExit("reference not available at %s" % _refshim.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    make_grid()
-    make_nav()
+    which = sys.argv[1:] or ["grid", "nav", "aux", "ce"]
+    if "grid" in which:
+        make_grid()
+    if "nav" in which:
+        make_nav()
+    if "aux" in which:
+        make_aux()
+    if "ce" in which:
+        make_ce()

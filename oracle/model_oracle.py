@@ -172,8 +172,9 @@ def fuse_logits(global_logits, local_logits, gmap_vpids, gmap_visited_masks, vp_
     return fused
 
 
-def navigation(sd, batch, n_x_layers=4, n_cells=196, return_intermediates=False):
-    """forward_navigation_per_step (vilmodel.py:782-918), eval mode (dropout = identity)."""
+def _nav_trunk(sd, batch, n_x_layers, n_cells):
+    """Everything of forward_navigation_per_step up to the fused [gmap; vp] embeddings (vilmodel.py:788-856; identical
+    in VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:714-789)."""
     txt, txt_masks = batch["txt_embeds"], batch["txt_masks"]
     gmap_masks = batch["gmap_masks"]
     gmi, nonempty = grid_pool(sd, txt, batch["grid_fts"], batch["grid_map"], n_cells)
@@ -196,7 +197,14 @@ def navigation(sd, batch, n_x_layers=4, n_cells=196, return_intermediates=False)
     qm = torch.cat([gmap_masks, batch["vp_masks"]], 1)
     q = crossmodal_encoder(sd, "local_encoder.encoder", n_x_layers, kv, kvm, q, qm)     # :853
     G = gmap_masks.shape[1]
-    gm_e, vp_e = q[:, :G], q[:, G:]
+    inter = {"grid_map_input": gmi, "nonempty": nonempty, "grid_map_embeds": cells, "grid_masks": cell_masks, "map_embeds": m}
+    return q[:, :G], q[:, G:], gmap2, inter
+
+
+def navigation(sd, batch, n_x_layers=4, n_cells=196, return_intermediates=False):
+    """forward_navigation_per_step (vilmodel.py:782-918), eval mode (dropout = identity)."""
+    gmap_masks = batch["gmap_masks"]
+    gm_e, vp_e, gmap2, inter = _nav_trunk(sd, batch, n_x_layers, n_cells)
     if "sap_fuse_linear.net.0.weight" in sd:
         fw = torch.sigmoid(cls_head(sd, "sap_fuse_linear", torch.cat([gm_e[:, 0], vp_e[:, 0]], 1)))
     else:
@@ -216,9 +224,21 @@ def navigation(sd, batch, n_x_layers=4, n_cells=196, return_intermediates=False)
     outs = {"gmap_embeds": gm_e, "vp_embeds": vp_e, "global_logits": gl, "local_logits": ll,
             "fused_logits": fused, "obj_logits": ol, "grid_logits": gr}
     if return_intermediates:
-        outs.update({"grid_map_input": gmi, "nonempty": nonempty, "grid_map_embeds": cells,
-                     "grid_masks": cell_masks, "map_embeds": m})
+        outs.update(inter)
     return outs
+
+
+def navigation_ce(sd, batch, n_x_layers=4, n_cells=196):
+    """Continuous-env head: VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:710-800.  Same trunk; the action logits are
+    `global * w + local * (1 - w)` on the first max(candidate_lengths) slots, masked by vp_nav_masks (:791-800)."""
+    gm_e, vp_e, _, _ = _nav_trunk(sd, batch, n_x_layers, n_cells)
+    fw = torch.sigmoid(cls_head(sd, "sap_fuse_linear", torch.cat([gm_e[:, 0], vp_e[:, 0]], 1)))
+    maxc = int(max(batch["candidate_lengths"]))
+    ninf = float("-inf")
+    nav = ~batch["vp_nav_masks"][:, :maxc]
+    gl = (cls_head(sd, "global_sap_head", gm_e).squeeze(2) * fw)[:, :maxc].masked_fill(nav, ninf)
+    ll = (cls_head(sd, "local_sap_head", vp_e).squeeze(2) * (1 - fw))[:, :maxc].masked_fill(nav, ninf)
+    return gl + ll
 
 
 def panorama(sd, batch, n_layers=2):

@@ -18,6 +18,36 @@ NAV_CASES = {
 }
 
 
+AUX_CASES = {
+    "lang_small": (31, dict(num_l_layers=2), dict(batch=3, txt_len=24)),
+    "pano_r2r": (32, dict(num_pano_layers=2), dict(batch=3, n_views=36, n_objs=0)),
+    "pano_reverie": (33, dict(num_pano_layers=2, obj_feat_size=768), dict(batch=3, n_views=36, n_objs=8)),
+}
+
+
+CE_GRID_CASE = dict(seed=41, batch=3, steps=6)
+CE_NAV_CASE = (dict(batch=3, steps=3, seed=42), dict(txt_len=24, gmap_len=10, n_views=12, n_objs=0))
+
+
+def ce_episodes(ep_kw):
+    """CE episodes: same generator, depth converted to float32 metres (the CE policy's depth sensor)."""
+    ep = synth.make_episodes(ep_kw["batch"], ep_kw["steps"], seed=ep_kw["seed"], dim=768)
+    ep["depth_sub"] = (ep["depth_sub"].astype(np.float32) / 4000.0).astype(np.float32)
+    return ep
+
+
+def ce_nav_tuple(ep_kw, nav_kw, cells, fts, pos, device="cpu"):
+    """The 14-tuple of Policy_ViewSelection_GridMap.py:622-623."""
+    nav = synth.to_torch(synth.make_nav_inputs(ep_kw["batch"], seed=ep_kw["seed"], **nav_kw), device)
+    T = ep_kw["steps"]
+    cand = [int(x) for x in nav["vp_nav_masks"].sum(1)]
+    return (nav["txt_embeds"], nav["txt_masks"], nav["gmap_img_embeds"], nav["gmap_step_ids"], nav["gmap_pos_fts"],
+            nav["gmap_masks"], nav["vp_img_embeds"], nav["vp_pos_fts"], nav["vp_masks"], nav["vp_nav_masks"],
+            [torch.from_numpy(np.ascontiguousarray(f)).to(device) for f in fts],
+            [torch.from_numpy(cells[b][T - 1].astype(np.float64)).to(device) for b in range(len(fts))],
+            torch.from_numpy(np.stack(pos).astype(np.float32)).to(device), cand)
+
+
 def make_config(**model_kw):
     kw = dict(MODEL_KW)
     kw.update(model_kw)
@@ -43,7 +73,7 @@ def oracle_grid(ep, grid_w=14, geom=None):
                                    grid_w=grid_w, geom=geom)
             cells[b][t] = c
         fts[b], halfs[b] = f, h
-        pos[b] = go.gridmap_pos_fts(h, grid_w)
+        pos[b] = go.gridmap_pos_fts(h, grid_w, geom)
     return cells, fts, halfs, pos
 
 

@@ -159,3 +159,78 @@ def test_missing_cuda_inputs_fail_loudly():
     with pytest.raises(_lib.GridmmError):
         ops.linear(torch.zeros(128, 72, dtype=torch.float16).cuda(), torch.zeros(128, 72, dtype=torch.float16).cuda(),
                    out_f16=torch.zeros(128, 128, dtype=torch.float16).cuda())     # K % 64 != 0 -> GRIDMM_ERR_SHAPE
+
+
+@pytest.mark.parametrize("name", sorted(H.AUX_CASES))
+def test_language_panorama_match_reference_golden(name):
+    """forward('language') / forward('panorama') on the CUDA kernels vs the reference's own outputs."""
+    seed, model_kw, in_kw = H.AUX_CASES[name]
+    gold = np.load(os.path.join(H.GOLD, "aux_%s.npz" % name))
+    cfg = H.make_config(**model_kw)
+    model, _ = _model(cfg, seed)
+    if name.startswith("lang"):
+        out = model("language", _to_cuda(synth.to_torch(synth.make_lang_inputs(seed=seed, **in_kw))))
+        torch.cuda.synchronize()
+        valid = torch.from_numpy(synth.make_lang_inputs(seed=seed, **in_kw)["txt_masks"])
+        err = (out.cpu() - torch.from_numpy(gold["txt_embeds"]))[valid].abs().max().item()
+        assert err < EMBED_TOL, err
+    else:
+        emb, masks = model("panorama", _to_cuda(synth.to_torch(synth.make_pano_inputs(seed=seed, **in_kw))))
+        torch.cuda.synchronize()
+        assert np.array_equal(masks.cpu().numpy(), gold["pano_masks"])
+        valid = torch.from_numpy(gold["pano_masks"])
+        err = (emb.cpu() - torch.from_numpy(gold["pano_embeds"]))[valid].abs().max().item()
+        assert err < EMBED_TOL, err
+
+
+def test_cuda_graph_replay_matches_eager():
+    B, T, L, G = 8, 3, 40, 12
+    from gridmm_b200.env import GridMapBuilder
+    cfg = H.make_config()
+    model, _ = _model(cfg, 5)
+    ep = synth.make_episodes(B, T, seed=5)
+    gb = GridMapBuilder(B, max_steps=T)
+    for t in range(T):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+    nav = _to_cuda(synth.to_torch(synth.make_nav_inputs(B, seed=5, txt_len=L, gmap_len=G)))
+    nav.update(grid=grid, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+    eager = {k: (v.clone() if v is not None else None) for k, v in model("navigation", nav).items()}
+    model.enable_cuda_graph(True)
+    for _ in range(2):
+        replay = model("navigation", nav)
+    torch.cuda.synchronize()
+    for k in LOGITS[:4] + ("gmap_embeds", "vp_embeds"):
+        assert torch.equal(eager[k], replay[k]), k
+
+
+def test_ce_variant_matches_reference_golden():
+    """R2R-CE (config 4): device-built grid with the CE geometry (bit-exact) + the CE head, vs the reference's own outputs."""
+    from gridmm_b200.env import GridMapBuilder
+    ep_kw, nav_kw = H.CE_NAV_CASE
+    gold_nav = np.load(os.path.join(H.GOLD, "nav_ce_small.npz"))
+    gold_grid = np.load(os.path.join(H.GOLD, "grid_ce_s%d.npz" % H.CE_GRID_CASE["seed"]))
+    # grid: every step bit-exact vs the reference
+    ep = H.ce_episodes(H.CE_GRID_CASE)
+    gb = GridMapBuilder(H.CE_GRID_CASE["batch"], geometry="r2r_ce", max_steps=8)
+    for t in range(H.CE_GRID_CASE["steps"]):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+        got = grid.grid_map_numpy()
+        for b in range(H.CE_GRID_CASE["batch"]):
+            assert np.array_equal(got[b].astype(np.int16), gold_grid["cell_b%d_t%d" % (b, t)])
+    np.testing.assert_allclose(grid.pos_fts.cpu().numpy(), gold_grid["pos_fts_last"], atol=2e-6, rtol=0)
+    # model
+    cfg = H.make_config(graph_sprels=False)
+    model, _ = _model(cfg, ep_kw["seed"])
+    ep = H.ce_episodes(ep_kw)
+    gb = GridMapBuilder(ep_kw["batch"], geometry="r2r_ce", max_steps=4)
+    for t in range(ep_kw["steps"]):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+    nav = synth.to_torch(synth.make_nav_inputs(ep_kw["batch"], seed=ep_kw["seed"], **nav_kw), "cuda")
+    cand = [int(x) for x in nav["vp_nav_masks"].sum(1)]
+    tup = (nav["txt_embeds"], nav["txt_masks"], nav["gmap_img_embeds"], nav["gmap_step_ids"], nav["gmap_pos_fts"],
+           nav["gmap_masks"], nav["vp_img_embeds"], nav["vp_pos_fts"], nav["vp_masks"], nav["vp_nav_masks"], None, None, None, cand)
+    out = model("navigation", tup, grid=grid)
+    torch.cuda.synchronize()
+    H.finite_close(out, gold_nav["fused_logits"], atol=LOGIT_TOL)
+    rolled = model.roll_stop_last(out, cand)
+    assert torch.equal(rolled[0, cand[0] - 1], out[0, 0])

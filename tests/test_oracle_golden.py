@@ -58,3 +58,48 @@ def test_compaction_quirk_is_reproduced():
     assert masks[0].tolist() == [True] * 5 + [True, False, True, False]
     assert masks[1].all()
     assert torch.equal(embeds[0, :5], gmi[0, [0, 3, 5, 7, 100]]) and embeds[0, 5:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("name", sorted(H.AUX_CASES))
+def test_language_panorama_oracle_matches_reference(name):
+    """forward('language') / forward('panorama') of the oracle vs the reference's own outputs."""
+    from oracle import model_oracle as mo
+    seed, model_kw, in_kw = H.AUX_CASES[name]
+    gold = np.load(os.path.join(H.GOLD, "aux_%s.npz" % name))
+    cfg = H.make_config(**model_kw)
+    sd = {k: torch.from_numpy(v) for k, v in H.make_weights(cfg, seed).items()}
+    with torch.no_grad():
+        if name.startswith("lang"):
+            out = mo.language(sd, synth.to_torch(synth.make_lang_inputs(seed=seed, **in_kw)), n_layers=cfg.num_l_layers)
+            H.finite_close(out, gold["txt_embeds"], atol=2e-5)
+        else:
+            emb, masks = mo.panorama(sd, synth.to_torch(synth.make_pano_inputs(seed=seed, **in_kw)), n_layers=cfg.num_pano_layers)
+            assert np.array_equal(masks.numpy(), gold["pano_masks"])
+            H.finite_close(emb, gold["pano_embeds"], atol=2e-5)
+
+
+def test_ce_oracle_matches_reference():
+    """Continuous-env variant: grid cells bit-exact vs the reference's CE getGlobalMap, action logits vs
+    the CE copy of the model (both produced by oracle/make_golden.py from the reference's own code)."""
+    from oracle import grid_oracle as go
+    from oracle import model_oracle as mo
+    case = H.CE_GRID_CASE
+    gold = np.load(os.path.join(H.GOLD, "grid_ce_s%d.npz" % case["seed"]))
+    ep = H.ce_episodes(case)
+    cells, _, _, pos = H.oracle_grid(ep, geom=go.CEGeometry)
+    for b in range(case["batch"]):
+        for t in range(case["steps"]):
+            assert np.array_equal(gold["cell_b%d_t%d" % (b, t)].astype(np.int32), cells[b][t])
+    np.testing.assert_allclose(np.stack(pos), gold["pos_fts_last"], atol=1e-6, rtol=0)
+    ep_kw, nav_kw = H.CE_NAV_CASE
+    gold = np.load(os.path.join(H.GOLD, "nav_ce_small.npz"))
+    cfg = H.make_config(graph_sprels=False)
+    sd = {k: torch.from_numpy(v) for k, v in H.make_weights(cfg, ep_kw["seed"]).items()}
+    cells, fts, _, pos = H.oracle_grid(H.ce_episodes(ep_kw), geom=go.CEGeometry)
+    tup = H.ce_nav_tuple(ep_kw, nav_kw, cells, fts, pos)
+    keys = ("txt_embeds", "txt_masks", "gmap_img_embeds", "gmap_step_ids", "gmap_pos_fts", "gmap_masks", "vp_img_embeds",
+            "vp_pos_fts", "vp_masks", "vp_nav_masks", "grid_fts", "grid_map", "gridmap_pos_fts", "candidate_lengths")
+    with torch.no_grad():
+        out = mo.navigation_ce(sd, dict(zip(keys, tup)), n_x_layers=cfg.num_x_layers)
+    assert list(gold["candidate_lengths"]) == tup[-1]
+    H.finite_close(out, gold["fused_logits"], atol=2e-5)
