@@ -45,6 +45,23 @@ def _dist_env():
     return rank, world, local
 
 
+def shard_seed(rank):
+    """Weak scaling: rank r owns its own batch of B episodes, generated from seed r (episodes are independent, SURVEY 8e;
+    the reference shards the same way per process: map_nav_src/main_nav.py:32-45, 79)."""
+    return int(rank)
+
+
+def aggregate(ms_local, steps, world, device=None):
+    """(max-over-ranks time in ms, whole-job nav-steps/s).  The only collective on the path: one MAX all-reduce of the timing."""
+    import torch.distributed as dist
+    ms = float(ms_local)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, world * B * steps / (ms * 1e-3)
+
+
 def _inputs(seed):
     ep = synth.make_episodes(B, T, seed=seed, dim=768)
     nav = synth.make_nav_inputs(B, seed=seed, txt_len=L, gmap_len=G, n_views=VIEWS)
@@ -250,11 +267,8 @@ def timed(fn, steps, warmup, world):
         fn()
     e.record()
     torch.cuda.synchronize()
-    ms = s.elapsed_time(e)
+    ms, _ = aggregate(s.elapsed_time(e), steps, world, device="cuda")
     if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         dist.barrier()
     return ms
 
@@ -332,7 +346,7 @@ def main():
     warmup = max(args.warmup, 3)
     from gridmm_b200 import _lib
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to produce samples
-    step = Step(dev, seed=rank)
+    step = Step(dev, seed=shard_seed(rank))
     step.run_resident()
     torch.cuda.synchronize()
 

@@ -4,9 +4,9 @@
 // -10000 mask from extend_neg_masks, models/ops.py:25-34) and nn.MultiheadAttention with key_padding_mask
 // (-inf) inside TransformerEncoderLayer.forward_pre (models/transformer.py:170-182).
 //
-// One CTA per (64-query tile, head, episode): K, V of that (episode, head) are staged once in shared memory
-// with cp.async, each warp owns 16 query rows and runs a flash-style online softmax over 64-key tiles with
-// mma.sync.m16n8k16 (fp16 in, fp32 accumulate).  The projections around this core -- where the FLOPs are --
+// One CTA per (query tile of 64 or 128 rows, head, episode), one warp per 16 query rows: K, V of that (episode, head)
+// stream into shared memory in 64-key cp.async groups and the flash-style online softmax (mma.sync.m16n8k16, fp16 in,
+// fp32 accumulate) starts on the first group while the later ones are still in flight.  The projections around this core -- where the FLOPs are --
 // run on tcgen05 (gemm_tc.cu); this core is softmax/latency bound at these sizes.
 #include "common.cuh"
 #include "host_util.h"
@@ -15,8 +15,7 @@ namespace gmm {
 
 constexpr int ATT_DH = 64;
 constexpr int ATT_LD = 72;          // padded smem row (halves): 144 B, 16-byte aligned, conflict-free ldmatrix
-constexpr int ATT_QT = 64;
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_KT = 64;           // keys per pipeline step (one cp.async group)
 
 struct AttnParams {
     const __half* q; const __half* k; const __half* v; __half* o;
@@ -41,12 +40,28 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// wait until at most `n` of this thread's cp.async groups are still pending (n is clamped to 7: older groups first)
+__device__ __forceinline__ void cp_async_wait_upto(int n) {
+    switch (n) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        default: cp_async_wait<7>(); break;
+    }
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS) attn_kernel(AttnParams p) {
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
+    constexpr int ATT_QT = NW * 16;
+    constexpr int ATT_THREADS = NW * 32;
     extern __shared__ __align__(16) uint8_t att_smem[];
     const int sk_pad = (p.sk + 63) & ~63;
     __half* sK = reinterpret_cast<__half*>(att_smem);
@@ -62,30 +77,34 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(AttnParams p) {
     const __half* gk = p.k + (static_cast<size_t>(b) * p.k_rows) * p.ldk + h * ATT_DH;
     const __half* gv = p.v + (static_cast<size_t>(b) * p.k_rows) * p.ldv + h * ATT_DH;
 
-    // stage K, V (all keys) and the Q tile; rows past the end are zero-filled
-    for (int i = tid; i < sk_pad * 8; i += ATT_THREADS) {
-        const int r = i >> 3, u = i & 7;
-        const uint32_t dk = smem_u32(sK + r * ATT_LD + u * 8), dv = smem_u32(sV + r * ATT_LD + u * 8);
-        if (r < p.sk) {
-            cp_async_16(dk, gk + static_cast<size_t>(r) * p.ldk + u * 8);
-            cp_async_16(dv, gv + static_cast<size_t>(r) * p.ldv + u * 8);
-        } else {
-            *reinterpret_cast<uint4*>(sK + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(sV + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
-        }
-    }
+    // stage the Q tile with the first key tile, then K, V in 64-key cp.async groups; rows past the end are zero-filled
     for (int i = tid; i < ATT_QT * 8; i += ATT_THREADS) {
         const int r = i >> 3, u = i & 7;
         if (q0 + r < p.sq) cp_async_16(smem_u32(sQ + r * ATT_LD + u * 8), gq + static_cast<size_t>(q0 + r) * p.ldq + u * 8);
         else *reinterpret_cast<uint4*>(sQ + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
     }
-    cp_async_commit();
+    const int n_kt = sk_pad / ATT_KT;
+    for (int kt = 0; kt < n_kt; ++kt) {
+        for (int i = tid; i < ATT_KT * 8; i += ATT_THREADS) {
+            const int r = kt * ATT_KT + (i >> 3), u = i & 7;
+            const uint32_t dk = smem_u32(sK + r * ATT_LD + u * 8), dv = smem_u32(sV + r * ATT_LD + u * 8);
+            if (r < p.sk) {
+                cp_async_16(dk, gk + static_cast<size_t>(r) * p.ldk + u * 8);
+                cp_async_16(dv, gv + static_cast<size_t>(r) * p.ldv + u * 8);
+            } else {
+                *reinterpret_cast<uint4*>(sK + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(sV + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        cp_async_commit();
+    }
     for (int j = tid; j < sk_pad; j += ATT_THREADS) {
         float m = -INFINITY;                                   // keys past Sk never contribute
         if (j < p.sk) m = p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg;
         sM[j] = m;
     }
-    cp_async_wait<0>();
+    // first group (Q + key tile 0) must have landed before the Q fragments are read
+    if (n_kt > 1) cp_async_wait_upto(n_kt - 1); else cp_async_wait<0>();
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
@@ -105,6 +124,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_kernel(AttnParams p) {
     constexpr float LOG2E = 1.4426950408889634f;
 
     for (int kt = 0; kt < sk_pad; kt += 64) {
+        if (kt > 0) {      // key tile kt/64: all but the (n_kt - 1 - kt/64) newest groups are complete
+            cp_async_wait_upto(n_kt - 1 - kt / 64);
+            __syncthreads();
+        }
         float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -199,11 +222,19 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.q_rows = q_rows; p.k_rows = k_rows;
     p.kmask = kmask; p.mask_neg = mask_neg; p.sq = sq; p.sk = sk; p.scale = scale;
     const int sk_pad = (sk + 63) & ~63;
-    const int smem = (2 * sk_pad + ATT_QT) * ATT_LD * 2 + sk_pad * 4;
+    // 8 warps (128 query rows per CTA) halve the K/V re-reads of long query sequences; 4 warps otherwise
+    const int nw = (sq > 64) ? 8 : 4;
+    const int qt = nw * 16;
+    const int smem = (2 * sk_pad + qt) * ATT_LD * 2 + sk_pad * 4;
     if (smem > 227 * 1024) return GRIDMM_ERR_SHAPE;
-    GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    dim3 grid((sq + ATT_QT - 1) / ATT_QT, heads, batch);
-    GMM_CUDA_CHECK(launch_pdl(attn_kernel, grid, dim3(ATT_THREADS), smem, stream, p));
+    dim3 grid((sq + qt - 1) / qt, heads, batch);
+    if (nw == 8) {
+        GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GMM_CUDA_CHECK(launch_pdl(attn_kernel<8>, grid, dim3(256), smem, stream, p));
+    } else {
+        GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GMM_CUDA_CHECK(launch_pdl(attn_kernel<4>, grid, dim3(128), smem, stream, p));
+    }
     gridmm_count_launch(1);
     return 0;
 }

@@ -234,3 +234,52 @@ def test_ce_variant_matches_reference_golden():
     H.finite_close(out, gold_nav["fused_logits"], atol=LOGIT_TOL)
     rolled = model.roll_stop_last(out, cand)
     assert torch.equal(rolled[0, cand[0] - 1], out[0, 0])
+
+
+@pytest.mark.parametrize("case", ["one_empty_episode", "all_empty", "batch1"])
+def test_edge_cases_vs_oracle(case):
+    """Erasures: a viewpoint whose depth is all zero contributes only masked points (r2r/env.py:283-285) -- an episode can
+    reach the model with no valid point at all; and the smallest batch."""
+    from gridmm_b200.env import GridMapBuilder
+    B, T = (1, 2) if case == "batch1" else (3, 2)
+    ep_kw = dict(batch=B, steps=T, seed=900 + B)
+    nav_kw = dict(txt_len=24, gmap_len=8, n_views=36, n_objs=0)
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    if case == "one_empty_episode":
+        ep["depth_sub"][1] = 0
+    elif case == "all_empty":
+        ep["depth_sub"][:] = 0
+    cfg = H.make_config()
+    model, w = _model(cfg, ep_kw["seed"])
+    cells, fts, _, pos = H.oracle_grid(ep)
+    nav = H.nav_batch(ep_kw, nav_kw, cells, fts, pos)
+    ref = _oracle_nav(cfg, w, nav)
+    gb = GridMapBuilder(B, max_steps=T)
+    for t in range(T):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+    got_cells = grid.grid_map_numpy()
+    for b in range(B):
+        assert np.array_equal(got_cells[b].astype(np.int32), cells[b][T - 1])
+    dev_nav = _to_cuda(nav)
+    dev_nav.update(grid=grid, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+    out = model("navigation", dev_nav)
+    torch.cuda.synchronize()
+    _check(out, ref, keys=LOGITS)
+    out2 = model("navigation", _to_cuda(nav))          # reference-format lists, same result
+    torch.cuda.synchronize()
+    for k in LOGITS[:4]:
+        assert torch.equal(out[k], out2[k])
+
+
+def test_unsupported_shapes_are_rejected():
+    from gridmm_b200 import _lib
+    cfg = H.make_config()
+    model, _ = _model(cfg, 1)
+    ep_kw = dict(batch=2, steps=1, seed=3)
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, _, pos = H.oracle_grid(ep)
+    nav = _to_cuda(H.nav_batch(ep_kw, dict(txt_len=136, gmap_len=6, n_views=36, n_objs=0), cells, fts, pos))
+    with pytest.raises(_lib.GridmmError):            # the pooling kernel keeps one text position per TMEM lane: L <= 128
+        model("navigation", nav)
+    with pytest.raises(NotImplementedError):
+        model("nonsense", nav)
