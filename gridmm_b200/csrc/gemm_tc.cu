@@ -35,10 +35,10 @@ struct GemmEpilogue {
     long long* dbg;          // optional [grid][8] cycle counters (tools/microbench.py), null in production
 };
 
-template <int BN, int STAGES, int BK>
+template <int BN, int STAGES, int BK, int CG = 1>
 struct GemmSmem {
     static constexpr int A_ATOM = GEMM_BM * GEMM_KATOM * 2;     // 128 rows x 128 B
-    static constexpr int B_ATOM = BN * GEMM_KATOM * 2;
+    static constexpr int B_ATOM = (BN / CG) * GEMM_KATOM * 2;   // a CTA pair splits the W tile: BN / 2 rows each
     static constexpr int A_BYTES = A_ATOM * (BK / GEMM_KATOM);
     static constexpr int B_BYTES = B_ATOM * (BK / GEMM_KATOM);
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -70,14 +70,17 @@ __device__ __forceinline__ void named_bar_sync_epi() {
     asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");
 }
 
-template <int BN, int STAGES, int BK, bool DBG>
+template <int BN, int STAGES, int BK, bool DBG, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int N, int K,
                    GemmEpilogue ep) {
-    using L = GemmSmem<BN, STAGES, BK>;
+    using L = GemmSmem<BN, STAGES, BK, CG>;
     constexpr int ATOMS = BK / GEMM_KATOM;
+    constexpr int TILE_M = GEMM_BM * CG;          // CG = 2: a CTA pair owns a 256 x BN tile (tcgen05 cta_group::2)
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access below to a
+    // generic LD/ST instead of LDS/STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
@@ -88,8 +91,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int lane = threadIdx.x & 31;
     const int num_kb = K / BK;
     const int tiles_n = N / BN;
-    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    const int tiles_m = (M + TILE_M - 1) / TILE_M;
     const int num_tiles = tiles_m * tiles_n;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader: owns the full barriers and issues the MMAs
+    const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
@@ -101,13 +106,16 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);
+            mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS * CG);
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 1) {
+        if (CG == 2) tmem_alloc_2sm(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();     // the peer's barriers must be initialised before anything is signalled across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
@@ -117,8 +125,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             int it = 0;
             long long w_empty = 0;
             const long long t_begin = DBG ? clock64() : 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+                // pair mode: this CTA loads its own 128 rows of A and its half of the W tile
+                const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * GEMM_BM;
+                const int n0 = (tile % tiles_n) * BN + static_cast<int>(rank) * (BN / CG);
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -127,23 +137,34 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (DBG) w_empty += clock64() - c0;
                     uint8_t* a_dst = smem + s * L::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + L::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                    if (CG == 1) {
+                        mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
 #pragma unroll
-                    for (int a = 0; a < ATOMS; ++a) {
-                        tma_load_2d(a_dst + a * L::A_ATOM, &tmA, kb * BK + a * GEMM_KATOM, m0, &full_bar[s]);
-                        tma_load_2d(b_dst + a * L::B_ATOM, &tmW, kb * BK + a * GEMM_KATOM, n0, &full_bar[s]);
+                        for (int a = 0; a < ATOMS; ++a) {
+                            tma_load_2d(a_dst + a * L::A_ATOM, &tmA, kb * BK + a * GEMM_KATOM, m0, &full_bar[s]);
+                            tma_load_2d(b_dst + a * L::B_ATOM, &tmW, kb * BK + a * GEMM_KATOM, n0, &full_bar[s]);
+                        }
+                    } else {
+                        // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the pair
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+                        const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+#pragma unroll
+                        for (int a = 0; a < ATOMS; ++a) {
+                            tma_load_2d_2sm(a_dst + a * L::A_ATOM, &tmA, kb * BK + a * GEMM_KATOM, m0, lead_bar);
+                            tma_load_2d_2sm(b_dst + a * L::B_ATOM, &tmW, kb * BK + a * GEMM_KATOM, n0, lead_bar);
+                        }
                     }
                 }
             }
             if (DBG && ep.dbg) { ep.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 1] = w_empty; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(TILE_M, BN);
             int it = 0, t = 0;
             long long w_full = 0, w_acc = 0;
             const long long t_begin = DBG ? clock64() : 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
                 const int acc = t & 1;
                 const long long c1 = DBG ? clock64() : 0;
                 mbar_wait(&tmem_empty_bar[acc], ((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
@@ -165,12 +186,13 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < GEMM_KATOM / 16; ++k) {
                             // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
-                            umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
+                            if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
+                            else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty_bar[s]);
+                    if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);     // frees the stage in both CTAs
                 }
-                umma_commit(&tmem_full_bar[acc]);
+                if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
             }
             if (DBG && ep.dbg) {
                 ep.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 3] = w_full;
@@ -187,9 +209,9 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         int t = 0;
         long long w_tfull = 0;
         const long long t_begin = DBG ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
             const int acc = t & 1;
-            const int m0 = (tile / tiles_n) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+            const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * GEMM_BM, n0 = (tile % tiles_n) * BN;
             // stage this tile's bias slice (the slot of tile t-2 is free: all warps passed the barrier of tile t-1)
             float* sb = s_bias + acc * BN;
             for (int i = et; i < BN; i += GEMM_EPI_WARPS * 32) sb[i] = ep.bias ? __ldg(ep.bias + n0 + i) : 0.0f;
@@ -269,20 +291,24 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) {
+                if (CG == 2 && rank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // leader's barrier
+                else mbar_arrive(&tmem_empty_bar[acc]);
+            }
         }
         if (DBG && ep.dbg && et == 0) { ep.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 6] = w_tfull; }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();     // neither CTA may exit / free TMEM while its peer can still signal it
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
-template <int BN, int STAGES, int BK, bool DBG>
+template <int BN, int STAGES, int BK, bool DBG, int CG>
 static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const GemmEpilogue& ep, int sms,
                        cudaStream_t stream) {
     CUtensorMap tmA, tmW;
@@ -290,19 +316,42 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, in
                               GEMM_KATOM, GEMM_BM);
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2,
-                          GEMM_KATOM, BN);
+                          GEMM_KATOM, BN / CG);
     if (rc) return rc;
-    auto kern = gemm_f16_tn_kernel<BN, STAGES, BK, DBG>;
-    constexpr int smem = GemmSmem<BN, STAGES, BK>::TOTAL;
+    auto kern = gemm_f16_tn_kernel<BN, STAGES, BK, DBG, CG>;
+    constexpr int smem = GemmSmem<BN, STAGES, BK, CG>::TOTAL;
     GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * (N / BN);
-    return static_cast<int>(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(GEMM_THREADS), smem, stream, tmA, tmW, M, N, K, ep));
+    const int tiles = ((M + GEMM_BM * CG - 1) / (GEMM_BM * CG)) * (N / BN);
+    int ctas = tiles * CG < sms ? tiles * CG : (sms / CG) * CG;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (gridmm_use_pdl()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, M, N, K, ep));
 }
 
 }  // namespace gmm
 
 // ----------------------------------------------------------------------------- C ABI
 static long long* g_gemm_dbg = nullptr;
+static int g_gemm_pairs = 1;
+// Debug hook: 0 disables the CTA-pair (cta_group::2) path (A/B comparisons in tools/microbench.py).
+extern "C" void gridmm_debug_set_gemm_pairs(int on) { g_gemm_pairs = on; }
 // Debug hook (tools/microbench.py): per-CTA cycle counters [grid][8] written by the next GEMM launches; null disables.
 extern "C" void gridmm_debug_set_gemm_counters(long long* dbg) { g_gemm_dbg = dbg; }
 
@@ -321,26 +370,32 @@ extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw,
         GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act, g_gemm_dbg};
-    // tile width: 256 halves the A re-reads, 128 quantises better over the SMs; pick the cheaper schedule
+    // tile width: a 128x256 tile does twice the work of a 128x128 one in ~1.45x the time (shared-memory bandwidth: both
+    // re-read their operands for every MMA, the wide tile reads 96 B/clk + fills 96 B/clk against 128 + 128 for the narrow
+    // one), the narrow tile quantises better over the SMs; pick the cheaper schedule
     const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     bool wide = false;
     if (N % 256 == 0) {
         const long long r256 = (static_cast<long long>(tiles_m) * (N / 256) + sms - 1) / sms;
         const long long r128 = (static_cast<long long>(tiles_m) * (N / 128) + sms - 1) / sms;
-        wide = r256 * 18 <= r128 * 10;
+        wide = r256 * 145 <= r128 * 100;
     }
-    // 128-wide tiles: 128 K-columns per stage (8 MMAs per barrier round trip) when K allows, the single-thread issue loop
-    // is otherwise slower than the 4 x 64-cycle MMAs of a 64-column stage
+    // Large problems run on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles): each SM then reads only half of the W tile
+    // per MMA and fills half per stage, which is what lifts the shared-memory-bandwidth cap of the single-CTA tiles.
+    // 128-wide single-CTA tiles take 128 K-columns per stage (8 MMAs per barrier round trip) when K allows.
+    const bool pair = g_gemm_pairs && (N % 256 == 0) && (static_cast<long long>(tiles_m / 2) * (N / 256) * 2 >= sms);
     const bool deep = (K % 128 == 0);
     int rc;
     if (g_gemm_dbg)
-        rc = wide ? launch_gemm<256, 4, 64, true>(a, lda, w, ldw, M, N, K, ep, sms, stream)
-           : deep ? launch_gemm<128, 3, 128, true>(a, lda, w, ldw, M, N, K, ep, sms, stream)
-                  : launch_gemm<128, 6, 64, true>(a, lda, w, ldw, M, N, K, ep, sms, stream);
+        rc = pair ? launch_gemm<256, 6, 64, true, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : wide ? launch_gemm<256, 4, 64, true, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : deep ? launch_gemm<128, 3, 128, true, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+                  : launch_gemm<128, 6, 64, true, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream);
     else
-        rc = wide ? launch_gemm<256, 4, 64, false>(a, lda, w, ldw, M, N, K, ep, sms, stream)
-           : deep ? launch_gemm<128, 3, 128, false>(a, lda, w, ldw, M, N, K, ep, sms, stream)
-                  : launch_gemm<128, 6, 64, false>(a, lda, w, ldw, M, N, K, ep, sms, stream);
+        rc = pair ? launch_gemm<256, 6, 64, false, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : wide ? launch_gemm<256, 4, 64, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : deep ? launch_gemm<128, 3, 128, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+                  : launch_gemm<128, 6, 64, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream);
     gridmm_count_launch(1);
     return rc;
 }

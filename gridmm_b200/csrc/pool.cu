@@ -155,7 +155,9 @@ pool_kernel(PoolParams p) {
     constexpr int D_COL0 = A_COLS;                // accumulators behind it: 2 x 64 columns
     static_assert(A_COLS + 2 * POOL_ROWS <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access below to a
+    // generic LD/ST instead of LDS/STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;                            // [2][CH][64 x 128 B]
     uint8_t* misc = sA + 2 * L::A_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);          // [2] tile buffer filled

@@ -150,6 +150,7 @@ int gridmm_ce_logits(const float* raw_global, const float* raw_local, const floa
  * GEMM, [grid][16] for the pooling kernel: role totals and time spent waiting on each mbarrier).  NULL disables. */
 void gridmm_debug_set_gemm_counters(long long* dbg);
 void gridmm_debug_set_pool_counters(long long* dbg);
+void gridmm_debug_set_gemm_pairs(int on);    /* 0: disable the cta_group::2 GEMM path (A/B timing) */
 void gridmm_debug_set_pool_mode(int mode);   /* bit0: skip the pooling loop, bit1: skip the softmax weights (timing experiments) */
 
 #ifdef __cplusplus

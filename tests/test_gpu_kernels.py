@@ -16,7 +16,8 @@ def _dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (6912, 2304, 768), (1000, 768, 3072), (32, 768, 1536)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (6912, 2304, 768), (1000, 768, 3072), (32, 768, 1536),
+                                   (6272, 768, 768), (9472, 6144, 768), (6913, 768, 3072), (12801, 256, 192)])
 def test_linear_tcgen05_plain(M, N, K):
     from gridmm_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)

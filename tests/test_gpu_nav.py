@@ -265,10 +265,11 @@ def test_edge_cases_vs_oracle(case):
     out = model("navigation", dev_nav)
     torch.cuda.synchronize()
     _check(out, ref, keys=LOGITS)
-    out2 = model("navigation", _to_cuda(nav))          # reference-format lists, same result
+    # reference-format lists: same kernels, but gridmap_pos_fts now comes from the oracle (numpy) instead of the grid kernel;
+    # the ~1e-7 difference can flip an fp16 rounding downstream, so this is a tolerance check, not a bitwise one
+    out2 = model("navigation", _to_cuda(nav))
     torch.cuda.synchronize()
-    for k in LOGITS[:4]:
-        assert torch.equal(out[k], out2[k])
+    _check(out2, ref, keys=LOGITS)
 
 
 def test_unsupported_shapes_are_rejected():

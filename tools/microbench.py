@@ -44,7 +44,19 @@ def gemm_case(M, N, K, act=0, res=False, f32=False):
           % (M, N, K, act, res, us, tf, d[0], d[1], d[2], d[3], d[4], d[5], d[6]), flush=True)
 
 
+lib.gridmm_debug_set_gemm_pairs.argtypes = [ctypes.c_int]
 if "gemm" in sys.argv or len(sys.argv) == 1:
+    for pairs in (0, 1):
+        lib.gridmm_debug_set_gemm_pairs(pairs)
+        print("--- CTA pairs (cta_group::2):", "on" if pairs else "off", flush=True)
+        gemm_case(6912, 2304, 768)
+        gemm_case(6912, 3072, 768, act=1)
+        gemm_case(6912, 768, 3072, res=True)
+        gemm_case(6912, 768, 768, res=True)
+        gemm_case(9472, 6144, 768)
+        gemm_case(8192, 8192, 8192)
+    lib.gridmm_debug_set_gemm_pairs(1)
+if "gemm_all" in sys.argv:
     gemm_case(6912, 2304, 768)
     gemm_case(6912, 3072, 768, act=1)
     gemm_case(6912, 768, 3072, res=True)
