@@ -212,6 +212,21 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------- warp-uniform issue
+// One lane of a CONVERGED warp.  The single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) are issued as
+//     whole warp runs the loop;  values made warp-uniform with uniform_u32();  if (elect_one()) { issue }
+// rather than from an `if (lane == 0)` region: with provably uniform operands ptxas keeps addresses / descriptors in
+// uniform registers and emits the UTMALDG / UTCHMMA back to back, whereas operands living in one thread's vector
+// registers cost an ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" of ~90 cycles per instruction (measured: the
+// tcgen05.mma issue rate of the pooling kernel was 87 cycles per instruction before this).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int uniform_i32(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -32,6 +32,8 @@ struct GemmEpilogue {
     __half* out_f16;         // [M, ld_f16] or null
     int ld_res, ld_f32, ld_f16;
     int act;                 // 0 none, 1 GELU(erf), 2 ReLU
+    __half* out_lanes;       // optional lane-major fp16 output [M / lanes_rows, N / 8, 128] of 16-byte units (gridmm_pool's
+    int lanes_rows;          // text operand layout): row = b * lanes_rows + t  ->  unit u of it at ((b * N/8 + u) * 128 + t)
     long long* dbg;          // optional [grid][8] cycle counters (tools/microbench.py), null in production
 };
 
@@ -64,6 +66,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
     const float e = poly * t * ex;                                        // 1 - erf(z)
     const float erf_abs = 1.0f - e;
     return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 __device__ __forceinline__ void named_bar_sync_epi() {
@@ -117,11 +124,11 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __syncthreads();
     if (CG == 2) cluster_sync_all();     // the peer's barriers must be initialised before anything is signalled across the pair
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
     pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // the whole (converged) warp runs the schedule, one elected lane issues: see elect_one() in common.cuh
             int it = 0;
             long long w_empty = 0;
             const long long t_begin = DBG ? clock64() : 0;
@@ -137,6 +144,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (DBG) w_empty += clock64() - c0;
                     uint8_t* a_dst = smem + s * L::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + L::A_BYTES;
+                    if (!elect_one()) continue;
                     if (CG == 1) {
                         mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
 #pragma unroll
@@ -156,10 +164,10 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
-            if (DBG && ep.dbg) { ep.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 1] = w_empty; }
+            if (DBG && ep.dbg && lane == 0) { ep.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 1] = w_empty; }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(TILE_M, BN);
             int it = 0, t = 0;
             long long w_full = 0, w_acc = 0;
@@ -179,6 +187,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (DBG) w_full += clock64() - c0;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
                     for (int a = 0; a < ATOMS; ++a) {
                         const uint64_t da = umma_desc_sw128_kmajor(a_addr + a * L::A_ATOM);
@@ -191,10 +200,15 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         }
                     }
                     if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);     // frees the stage in both CTAs
+                    }
+                    __syncwarp();
                 }
-                if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+                if (elect_one()) {
+                    if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
+                }
+                __syncwarp();
             }
-            if (DBG && ep.dbg) {
+            if (DBG && ep.dbg && lane == 0) {
                 ep.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 3] = w_full;
                 ep.dbg[blockIdx.x * 8 + 4] = w_acc;
             }
@@ -258,6 +272,22 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 } else if (ep.act == 2) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                if (ep.out_lanes) {
+                    // the TMEM layout (one row per lane) IS the coalesced mapping for the lane-major layout: consecutive
+                    // lanes = consecutive text positions = consecutive 16-byte units
+                    const int rg = m0 + q * 32 + lane;
+                    if (rg < M) {
+                        const int bb = rg / ep.lanes_rows, tt = rg - bb * ep.lanes_rows;
+                        const int unit = (col0 + c * 16) >> 3;
+                        uint4* dst = reinterpret_cast<uint4*>(ep.out_lanes) + (static_cast<size_t>(bb) * (N >> 3) + unit) * 128 + tt;
+                        uint4 o0, o1;
+                        o0.x = pack_half2(f[0], f[1]); o0.y = pack_half2(f[2], f[3]); o0.z = pack_half2(f[4], f[5]); o0.w = pack_half2(f[6], f[7]);
+                        o1.x = pack_half2(f[8], f[9]); o1.y = pack_half2(f[10], f[11]); o1.z = pack_half2(f[12], f[13]); o1.w = pack_half2(f[14], f[15]);
+                        dst[0] = o0;
+                        dst[128] = o1;
+                    }
+                    continue;
                 }
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
@@ -355,21 +385,22 @@ extern "C" void gridmm_debug_set_gemm_pairs(int on) { g_gemm_pairs = on; }
 // Debug hook (tools/microbench.py): per-CTA cycle counters [grid][8] written by the next GEMM launches; null disables.
 extern "C" void gridmm_debug_set_gemm_counters(long long* dbg) { g_gemm_dbg = dbg; }
 
-extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
-                                 const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
-                                 int act, cudaStream_t stream) {
+static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                         const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
+                         int act, void* out_lanes, int lanes_rows, cudaStream_t stream) {
     using namespace gmm;
     if (M <= 0) return 0;
     if (N % 128 != 0 || K % GEMM_KATOM != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
     if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
-    if (!a || !w || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
+    if (!a || !w || (!out_f32 && !out_f16 && !out_lanes)) return GRIDMM_ERR_ARG;
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;
         GMM_CUDA_CHECK(cudaGetDevice(&dev));
         GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act, g_gemm_dbg};
+    GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act,
+                    reinterpret_cast<__half*>(out_lanes), lanes_rows, g_gemm_dbg};
     // tile width: a 128x256 tile does twice the work of a 128x128 one in ~1.45x the time (shared-memory bandwidth: both
     // re-read their operands for every MMA, the wide tile reads 96 B/clk + fills 96 B/clk against 128 + 128 for the narrow
     // one), the narrow tile quantises better over the SMs; pick the cheaper schedule
@@ -398,4 +429,17 @@ extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw,
                   : launch_gemm<128, 6, 64, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream);
     gridmm_count_launch(1);
     return rc;
+}
+
+extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                                 const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
+                                 int act, cudaStream_t stream) {
+    return gemm_dispatch(a, lda, w, ldw, M, N, K, bias, residual, ld_res, out_f32, ld_f32, out_f16, ld_f16, act, nullptr, 0, stream);
+}
+
+// text_proj for gridmm_pool: out_lanes[b, N/8, 128] (16-byte units, lane-major) = a[M = batch*rows_per_b, K] . w[N, K]^T + bias
+extern "C" int gridmm_linear_f16_lanes(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                                       void* out_lanes, int rows_per_b, cudaStream_t stream) {
+    if (!out_lanes || rows_per_b < 1 || rows_per_b > 128 || (M % rows_per_b)) return GRIDMM_ERR_SHAPE;
+    return gemm_dispatch(a, lda, w, ldw, M, N, K, bias, nullptr, 0, nullptr, 0, nullptr, 0, 0, out_lanes, rows_per_b, stream);
 }

@@ -3,18 +3,22 @@
 //   for i in range(196): softmax over the points of cell i, weighted sum   vilmodel.py:801-807
 // as ONE persistent kernel that reads every valid patch-feature row from HBM exactly once.
 //
-//   * rows are streamed in cell-sorted order (gridmm_grid_update produced `perm`), 64 rows per tile, gathered with
-//     16-byte cp.async into a SWIZZLE_128B K-major tile (D/64 chunks of 64 x 128 B); two tile buffers, so tile i+1 is
-//     in flight while tile i is multiplied, reduced and pooled; rows of tile i+2 are pulled into L2 with
-//     cp.async.bulk.prefetch (one request per 1536-byte row) so DRAM sees whole rows;
+//   * rows are streamed in cell-sorted order (gridmm_grid_update produced `perm`), 64 rows per tile.  Four producer warps
+//     resolve the tile's 64 slab rows (perm -> slot -> row) and fetch them with TMA tile::gather4
+//     (cp.async.bulk.tensor.2d...tile::gather4: four arbitrary rows x 64 fp16 columns per instruction, hardware
+//     SWIZZLE_128B, completion on an mbarrier) straight into a K-major operand tile (D/64 chunks of 64 x 128 B).  Two
+//     tile buffers: up to 192 KB per SM are in flight, no registers or wait_group stalls are spent on the copy
+//     (four warps because a gather4 with per-lane row indices costs ~70 issue cycles: R2UR waterfall per lane);
 //   * relevance  S^T[L, 64] = text_fts[L, D] . X_tile^T  on tcgen05 with the A operand (text_fts of the current
-//     episode, up to 128 positions) held in TENSOR MEMORY for the whole episode (tcgen05.st once per episode, 3 KB per
-//     lane), B operand = the feature tile in shared memory, accumulator in TMEM (double buffered);
+//     episode, up to 128 positions) held in TENSOR MEMORY for the whole episode (tcgen05.st, 8 warps, software
+//     pipelined), B operand = the feature tile in shared memory, accumulator in TMEM (double buffered);
 //     w = max over ALL text positions (padding included -- vilmodel.py:798) = max over TMEM lanes, taken with a
 //     warp butterfly (62 shuffles per thread) + one shared-memory hop across the four lane quadrants;
-//   * per-cell softmax + weighted sum on CUDA cores straight from the resident tile: cells are contiguous row segments;
-//     a cell that straddles tiles is carried in registers with the usual online-softmax rescale.  CTA ranges are cut at
-//     cell boundaries, so no atomics and no cross-CTA merge exist and the result is deterministic;
+//   * per-cell softmax numerators exp(w - cell max) by the same warps that reduced w (cell max = match.any + redux.max
+//     inside a warp, running max carried across tiles), weighted sums on CUDA cores straight from the resident tile:
+//     cells are contiguous row segments, every pooling thread owns 4 feature columns and carries (sum, acc) of the
+//     open cell in registers across tiles (rescaled when a later tile raises the max).  CTA ranges are cut at cell
+//     boundaries, so no atomics and no cross-CTA merge exist and the result is deterministic;
 //   * grid_proj is applied AFTER pooling by the GEMM kernel (sum_j p_j (W x_j + b) = W (sum_j p_j x_j) + b), so this
 //     kernel emits the pooled raw feature per non-empty cell, compacted in ascending cell order (the order
 //     vilmodel.py:819 gathers them in), as fp16 GEMM input.
@@ -25,30 +29,30 @@
 
 namespace gmm {
 
-constexpr int POOL_ROWS = 64;
-constexpr int POOL_GATHER_WARP0 = 4;   // warps 0..3: epilogue (TMEM lane quadrant = warp); warps 4..7: gather
-constexpr int POOL_MMA_WARP = 8;
-constexpr int POOL_POOL_WARP0 = 9;     // warps 9..  (D / 128 of them)
-constexpr int POOL_FIXED_THREADS = 9 * 32;
+constexpr int POOL_ROWS = 32;          // rows per tile (= N of the relevance MMA)
+constexpr int POOL_NBUF = 4;           // tile buffers / TMEM accumulators in flight
+constexpr int POOL_PROD_WARPS = 4;     // warps 0..3: TMA gather producers (8 rows of every tile each) + text staging, first half
+constexpr int POOL_RED_WARP0 = 4;      // warps 4..7: relevance max (TMEM lane quadrant = warp % 4), softmax weights, text staging
+constexpr int POOL_MMA_WARP = 8;       // tcgen05.mma issuer, owns the TMEM allocation
+constexpr int POOL_POOL_WARP0 = 9;     // warps 9.. (D / 128 of them): weighted sums
+constexpr int POOL_FIXED_THREADS = POOL_POOL_WARP0 * 32;
 constexpr int POOL_MAX_BATCH = 1024;
 constexpr int POOL_MAX_CELLS = 256;
 constexpr int POOL_TMEM_COLS = 512;
+constexpr int POOL_PTS = 588, POOL_VIEW_PTS = 49;   // points per viewpoint / per view (r2r/env.py:279-289)
 
 struct PoolParams {
-    const __half* fts;       // feature slab; row r at fts + r * D
     const int* slots;        // [B, t_cap]   slab slot of (episode, step)
     const int* perm;         // [B, cap]     valid point indices sorted by cell
     const int* cell_start;   // [B, n_cells + 1]
     const int* cell_rank;    // [B, n_cells]
-    const __half* text;      // [B, l_pad, D] text_fts
-    const uint4* text_ws;    // [B, D/8, 128] lane-major copy of text_fts (written by text_to_lanes_kernel)
+    const uint4* text_ws;    // [B, D/8, 128] lane-major copy of text_fts (16-byte units; positions < l_pad are read)
     __half* pooled;          // [B, n_cells, D]  compacted by cell rank
     float* w_out;            // [B, cap] relevance weight per sorted position, or null (tests)
     int batch, t_cap, cap, n_cells;
     int l_pad;               // text positions (<= 128)
     int slot_rows, view_rows, tok_off;   // row = slot*slot_rows + view*view_rows + tok_off + patch
-    long long* dbg;          // optional [grid][16] cycle counters (tools/microbench.py), null in production
-    int mode;                // debug experiments (tools/microbench.py): bit0 skip the pooling loop, bit1 skip softmax weights
+    long long* dbg;          // optional [grid][16] cycle counters (tools/microbench2.py), null in production
 };
 
 struct Tile {
@@ -80,35 +84,50 @@ struct Walker {
     }
 };
 
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-    switch (n) {
-        case 0: cp_async_wait<0>(); break;
-        case 1: cp_async_wait<1>(); break;
-        case 2: cp_async_wait<2>(); break;
-        case 3: cp_async_wait<3>(); break;
-        case 4: cp_async_wait<4>(); break;
-        case 5: cp_async_wait<5>(); break;
-        case 6: cp_async_wait<6>(); break;
-        case 7: cp_async_wait<7>(); break;
-        case 8: cp_async_wait<8>(); break;
-        case 9: cp_async_wait<9>(); break;
-        case 10: cp_async_wait<10>(); break;
-        default: cp_async_wait<11>(); break;
+// TMA tile::gather4: rows r0..r3 (arbitrary), columns [c0, c0 + box) of a 2D tensor -> 4 consecutive 128-byte rows at
+// smem_dst (hardware SWIZZLE_128B on the shared-memory address), completion counted on `bar`.
+__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const CUtensorMap* tm, int c0, int r0, int r1, int r2, int r3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
+
+// mbarrier wait that traps instead of hanging the GPU if a phase never completes (a wrong transaction count would
+// otherwise spin forever): each failed try_wait parks the thread for up to the suspend-time hint
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1 << 22)) __trap();
     }
 }
 
-__device__ __forceinline__ void l2_prefetch_bulk(const void* g, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+// same, with a sleep between polls: for waiters with slack (the gather producers run several tiles ahead), so that their
+// polling does not take issue slots from the pooling warps
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(128);
+        if (++spins > (1 << 22)) __trap();
+    }
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // One butterfly level of the lane-max: every lane keeps the half of its N columns selected by `bit` of its lane id and
-// merges in the partner's copy of that half.  After the 64 -> 2 levels lane l holds the warp-wide max of columns 2l, 2l+1.
+// merges in the partner's copy of that half.  After the 32 -> 1 levels lane l holds the warp-wide max of column l.
 template <int N>
-__device__ __forceinline__ void lane_max_level(float (&v)[64], int lane, int bit) {
+__device__ __forceinline__ void lane_max_level(float (&v)[32], int lane, int bit) {
     const bool up = (lane & bit) != 0;
 #pragma unroll
     for (int j = 0; j < N / 2; ++j) {
@@ -118,66 +137,110 @@ __device__ __forceinline__ void lane_max_level(float (&v)[64], int lane, int bit
     }
 }
 
+// order-preserving float <-> uint32 map (for redux.sync max over the rows of one cell)
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 template <int D>
 struct PoolSmem {
     static constexpr int CH = D / 64;
     static constexpr int A_CHUNK = POOL_ROWS * 128;
     static constexpr int A_BYTES = CH * A_CHUNK;                  // one feature tile
     static constexpr int MISC_BYTES = 64 * 8                      // barriers + tmem slot
-                                      + 2 * POOL_ROWS * 4 * 5     // w, p, seg_end, seg_fin, seg_rank (double buffered)
-                                      + 4 * POOL_ROWS * 4         // per-quadrant partial maxima
-                                      + 64                        // scalars
-                                      + (POOL_MAX_CELLS + 1) * 4 + POOL_MAX_CELLS * 4   // cell_start, cell_rank of the episode
+                                      + POOL_NBUF * POOL_ROWS * 4 // softmax numerator per row (per buffer)
+                                      + POOL_NBUF * POOL_ROWS * 4 // cell id per row (per buffer)
+                                      + POOL_NBUF * 4 * POOL_ROWS * 4   // per-quadrant partial maxima (per buffer)
+                                      + 128                       // scalars
+                                      + 2 * (POOL_MAX_CELLS + 1) * 4 + POOL_MAX_CELLS * 4   // cell_start (reducers / poolers), cell_rank
                                       + (POOL_MAX_BATCH + 1) * 4; // vbase
-    static constexpr int TOTAL = 1024 + 2 * A_BYTES + MISC_BYTES;
+    static constexpr int TOTAL = 1024 + POOL_NBUF * A_BYTES + MISC_BYTES;
 };
 
 // text_fts [B, l_pad, D] -> lane-major copy [B, D/8, 128] of 16-byte units: unit c of text position t sits at
 // ((b * D/8 + c) * 128 + t) * 16 bytes, so the 32 lanes of a warp (32 consecutive positions) read 512 contiguous bytes
-// when the operand is moved into tensor memory.  Positions >= l_pad replicate position 0.
+// when the operand is moved into tensor memory.  (The navigation forward skips this kernel: the text_proj GEMM writes
+// this layout directly from its epilogue, gridmm_linear_f16_lanes.)
 template <int D>
 __global__ void __launch_bounds__(128) text_to_lanes_kernel(const __half* text, uint4* ws, int l_pad) {
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
-    const int tok = (t < l_pad) ? t : 0;
-    const uint4 v = *reinterpret_cast<const uint4*>(text + (static_cast<size_t>(b) * l_pad + tok) * D + c * 8);
+    if (t >= l_pad) return;
+    const uint4 v = *reinterpret_cast<const uint4*>(text + (static_cast<size_t>(b) * l_pad + t) * D + c * 8);
     ws[(static_cast<size_t>(b) * (D / 8) + c) * 128 + t] = v;
+}
+
+// Move this thread's share of the episode's text operand into tensor memory: TMEM lane `tlane` (= text position, lanes
+// >= l_pad replicate position 0 so that they never change the max), 16-byte units [u0, u0 + 8 * BU), software pipelined
+// two batches deep.
+template <int D, int BU>
+__device__ __forceinline__ void stage_text(const uint4* ws_b, int tlane, int l_pad, uint32_t taddr_lane, int u0) {
+    const uint4* src = ws_b + (tlane < l_pad ? tlane : 0);
+    uint4 cur[BU], nxt[BU];
+#pragma unroll
+    for (int c = 0; c < BU; ++c) cur[c] = __ldg(src + static_cast<size_t>(u0 + c) * 128);
+#pragma unroll
+    for (int bi = 0; bi < 8; ++bi) {
+        if (bi + 1 < 8) {
+#pragma unroll
+            for (int c = 0; c < BU; ++c) nxt[c] = __ldg(src + static_cast<size_t>(u0 + (bi + 1) * BU + c) * 128);
+        }
+#pragma unroll
+        for (int c = 0; c < BU / 2; ++c) {
+            const uint32_t v8[8] = {cur[2 * c].x, cur[2 * c].y, cur[2 * c].z, cur[2 * c].w,
+                                    cur[2 * c + 1].x, cur[2 * c + 1].y, cur[2 * c + 1].z, cur[2 * c + 1].w};
+            // unit u holds fp16 elements 8u..8u+7 = TMEM columns 4u..4u+3
+            tmem_st_32x32b_x8(taddr_lane + (u0 + bi * BU + 2 * c) * 4, v8);
+        }
+#pragma unroll
+        for (int c = 0; c < BU; ++c) cur[c] = nxt[c];
+    }
+    tmem_st_wait();
 }
 
 template <int D>
 __global__ void __launch_bounds__(POOL_FIXED_THREADS + D / 4, 1)
-pool_kernel(PoolParams p) {
+pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     using L = PoolSmem<D>;
     constexpr int CH = L::CH;
     constexpr int NPW = D / 128;                  // pooling warps
     constexpr int A_COLS = D / 2;                 // TMEM columns of the text operand (two fp16 per column)
-    constexpr int D_COL0 = A_COLS;                // accumulators behind it: 2 x 64 columns
-    static_assert(A_COLS + 2 * POOL_ROWS <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
+    constexpr int D_COL0 = A_COLS;                // accumulators behind it: one of 32 columns per tile buffer
+    constexpr int UNITS = D / 8;                  // 16-byte units per text position
+    constexpr int BU = UNITS / 16;                // units per staging batch (16 batches: 8 per half)
+    constexpr float LOG2E = 1.4426950408889634f;
+    static_assert(A_COLS + POOL_NBUF * POOL_ROWS <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
+    static_assert(BU % 2 == 0 && CH <= 32 && POOL_ROWS == 8 * POOL_PROD_WARPS && (D == 512 || D == 768), "unsupported feature width");
     extern __shared__ uint8_t smem_raw[];
     // align by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access below to a
     // generic LD/ST instead of LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sA = smem;                            // [2][CH][64 x 128 B]
-    uint8_t* misc = sA + 2 * L::A_BYTES;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);          // [2] tile buffer filled
-    uint64_t* a_empty = a_full + 2;                                // [2] tile buffer drained by the pooling warps
-    uint64_t* d_full = a_empty + 2;                                // [2]
-    uint64_t* d_empty = d_full + 2;                                // [2]
-    uint64_t* p_full = d_empty + 2;                                // [2]
-    uint64_t* t_ready = p_full + 2;                                // [1] text operand of the episode is in TMEM
+    uint8_t* sA = smem;                            // [NBUF][CH][32 x 128 B]
+    uint8_t* misc = sA + POOL_NBUF * L::A_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);          // [NBUF] tile landed (producer arrivals + TMA transaction bytes)
+    uint64_t* a_empty = a_full + POOL_NBUF;                        // [NBUF] tile buffer drained by the pooling warps
+    uint64_t* d_full = a_empty + POOL_NBUF;                        // [NBUF] accumulator written (tcgen05.commit)
+    uint64_t* d_empty = d_full + POOL_NBUF;                        // [NBUF] accumulator read back
+    uint64_t* p_full = d_empty + POOL_NBUF;                        // [NBUF] softmax numerators of the tile are in s_p
+    uint64_t* m_full = p_full + POOL_NBUF;                         // [NBUF] partial maxima of reducer warps 1..3 are in s_part
+    uint64_t* t_ready = m_full + POOL_NBUF;                              // [1] text operand of the episode is in TMEM
+    uint64_t* ep_done = t_ready + 1;                               // [1] every MMA of the previous episode has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 60);
-    float* s_w = reinterpret_cast<float*>(misc + 64 * 8);          // [2][64] relevance weight per row
-    float* s_p = s_w + 2 * POOL_ROWS;                              // [2][64] exp(w - m) per row
-    int* s_send = reinterpret_cast<int*>(s_p + 2 * POOL_ROWS);     // [2][64] exclusive end row of the k-th cell segment
-    float* s_sfin = reinterpret_cast<float*>(s_send + 2 * POOL_ROWS);   // [2][64] 1/sum if the segment closes its cell, else 0
-    int* s_srank = reinterpret_cast<int*>(s_sfin + 2 * POOL_ROWS); // [2][64] compact output slot of the segment's cell
-    float* s_part = reinterpret_cast<float*>(s_srank + 2 * POOL_ROWS);  // [4][64]
-    float* s_scal = s_part + 4 * POOL_ROWS;                        // [0..1] carry scale per buffer, [2] m_carry, [3] s_carry
-    int* s_nseg = reinterpret_cast<int*>(s_scal + 4);              // [2] segments in the tile
-    int* s_range = s_nseg + 4;                                     // [0] g_start, [1] g_end
-    int* s_cs = s_range + 8;                                       // [n_cells + 1]
-    int* s_cr = s_cs + POOL_MAX_CELLS + 1;                         // [n_cells]
+    float* s_p = reinterpret_cast<float*>(misc + 64 * 8);          // [NBUF][32] exp(w - cell max) per row
+    int* s_cid = reinterpret_cast<int*>(s_p + POOL_NBUF * POOL_ROWS);      // [NBUF][32] compact cell rank (+ last-row flag) of every row
+    float* s_part = reinterpret_cast<float*>(s_cid + POOL_NBUF * POOL_ROWS);   // [2][4][32]
+    float* s_scal = s_part + POOL_NBUF * 4 * POOL_ROWS;            // [NBUF] rescale of the open cell per buffer
+    float* s_carry_m = s_scal + POOL_NBUF;         // [1] running max of the cell left open by the previous tile
+    int* s_carry_c = reinterpret_cast<int*>(s_carry_m + 1);        // [1] its (episode << 16 | cell) key (-1: none)
+    int* s_range = s_carry_c + 1;                                  // [0] g_start, [1] g_end
+    int* s_csr = reinterpret_cast<int*>(misc + 64 * 8 + 2 * POOL_NBUF * POOL_ROWS * 4 + POOL_NBUF * 4 * POOL_ROWS * 4 + 128);   // reducers' cell_start
+    int* s_cs = s_csr + POOL_MAX_CELLS + 1;                        // (unused)
+    int* s_cr = s_cs + POOL_MAX_CELLS + 1;                         // reducers' cell_rank [n_cells]
     int* s_vbase = s_cr + POOL_MAX_CELLS;                          // [batch + 1]
 
     const int tid = threadIdx.x;
@@ -186,19 +249,26 @@ pool_kernel(PoolParams p) {
 
     // ---------------------------------------------------------------- setup: barriers, TMEM, schedule
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 64);
+        tma_prefetch_desc(&tm_fts);
+        for (int i = 0; i < POOL_NBUF; ++i) {
+            mbar_init(&a_full[i], POOL_PROD_WARPS);
             mbar_init(&a_empty[i], NPW);
             mbar_init(&d_full[i], 1);
             mbar_init(&d_empty[i], 4);
-            mbar_init(&p_full[i], 128);
+            mbar_init(&p_full[i], 32);
+            mbar_init(&m_full[i], 3);
         }
-        mbar_init(t_ready, 128);
+        mbar_init(t_ready, 256);
+        mbar_init(ep_done, 1);
+        *s_carry_c = -1;
         fence_mbar_init();
     }
     pdl_launch_dependents();
     if (warp == POOL_MMA_WARP) tmem_alloc(tmem_slot, POOL_TMEM_COLS);
     pdl_wait();      // barrier init / TMEM allocation above overlap the previous kernel's tail
+    // the tile buffers start as zeros: rows past a partial tile's end are never fetched, only multiplied by weight 0
+    for (int i = tid; i < POOL_NBUF * L::A_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
     // exclusive prefix of the valid-point counts: vbase[b] = sum_{b' < b} cell_start[b'][n_cells]
     for (int i = tid; i < p.batch; i += blockDim.x) s_vbase[i + 1] = p.cell_start[i * (n_cells + 1) + n_cells];
     if (tid == 0) s_vbase[0] = 0;
@@ -218,10 +288,11 @@ pool_kernel(PoolParams p) {
         for (int i = lo; i < hi; ++i) { run += s_vbase[i + 1]; s_vbase[i + 1] = run; }
     }
     __syncthreads();
-    if (tid < 2) {
-        // CTA range [g0, g1) in global sorted-valid coordinates, snapped up to a cell boundary
+    if (warp < 2) {
+        // CTA range [g0, g1) in global sorted-valid coordinates, snapped up to a cell boundary: warp w resolves boundary
+        // blockIdx.x + w with ONE round trip to global memory (every lane loads a slice of the episode's cell_start row)
         const int total = s_vbase[p.batch];
-        const long long tgt = (static_cast<long long>(blockIdx.x + tid) * total) / gridDim.x;
+        const long long tgt = (static_cast<long long>(blockIdx.x + warp) * total) / gridDim.x;
         int g = static_cast<int>(tgt);
         if (g >= total) g = total;
         else if (g > 0) {
@@ -232,371 +303,375 @@ pool_kernel(PoolParams p) {
             }
             const int local = g - s_vbase[lo];
             const int* cs = p.cell_start + lo * (n_cells + 1);
-            int a = 0, c = n_cells;    // first boundary index with cs[idx] >= local
-            while (a < c) {
-                const int mid = (a + c) >> 1;
-                if (cs[mid] >= local) c = mid; else a = mid + 1;
+            int best = 0x7fffffff;     // smallest boundary value >= local (cell_start is non-decreasing)
+            for (int i = lane; i <= n_cells; i += 32) {
+                const int v = cs[i];
+                if (v >= local) best = min(best, v);
             }
-            g = s_vbase[lo] + cs[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            g = s_vbase[lo] + best;
         }
-        s_range[tid] = g;
+        if (lane == 0) s_range[warp] = g;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
     const int g0 = s_range[0], g1 = s_range[1];
 
     Walker wk;
     wk.init(s_vbase, p.batch, g0, g1);
     Tile t;
+    const long long t_begin = p.dbg ? clock64() : 0;
+    long long w_a = 0, w_b = 0;
 
-    if (warp >= POOL_GATHER_WARP0 && warp < POOL_MMA_WARP) {
-        // ------------------------------------------------------------ gather producers
-        // Two independent groups of 64 threads: group g fills tile buffer g with the tiles of parity g.  The row
-        // addresses of a group's NEXT tile are resolved (perm -> slot -> row, two dependent global loads) and its rows
-        // pulled into L2 while the group still waits for its buffer; once the buffer is free the WHOLE tile is issued
-        // (96 x 16 B per thread) before anything is waited for, so ~96 KB per buffer are in flight.
-        const int grp = (warp - POOL_GATHER_WARP0) >> 1;
-        const int gt = (tid - POOL_GATHER_WARP0 * 32) & 63;   // 0..63 within the group
-        const int u = gt & 7;             // 16-byte unit inside the 128-byte chunk row
-        const int r0 = gt >> 3;           // rows r0 + 8*i
-        uint8_t* tile_base = sA + grp * L::A_BYTES;
-        auto resolve = [&](const Tile& tt, const __half* (&src)[8]) {
-            const int* perm_b = p.perm + static_cast<size_t>(tt.b) * p.cap + tt.pos;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = r0 + 8 * i;
-                src[i] = nullptr;
-                if (r < tt.nrows) {
-                    const int j = perm_b[r];
-                    const int step = j / 588, q = j - step * 588;
-                    const int v = q / 49, k = q - v * 49;
-                    const long long row = static_cast<long long>(p.slots[tt.b * p.t_cap + step]) * p.slot_rows +
-                                          v * p.view_rows + p.tok_off + k;
-                    src[i] = p.fts + row * D + u * 8;
-                }
-            }
+    if (warp < POOL_PROD_WARPS) {
+        // ------------------------------------------------------------ TMA gather producers (+ first half of the text operand)
+        // Warp w owns rows 8w .. 8w+7 of every tile (two gather4 row groups): lanes 0..7 resolve one slab row each (perm -> slot ->
+        // row, two dependent global loads, done for the NEXT tile while this tile's buffer is still busy), then one gather4 copy
+        // (4 rows x 128 B) per row group and 64-column chunk is issued.
+        const int q = warp & 3;
+        const int tlane = q * 32 + lane;
+        const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        int myrow = 0;
+        auto resolve = [&](const Tile& tt) {
+            const int r = min(8 * warp + (lane & 7), tt.nrows - 1);            // rows past the tile's end duplicate its last row
+            const int j = p.perm[static_cast<size_t>(tt.b) * p.cap + tt.pos + r];
+            const int step = j / POOL_PTS, qq = j - step * POOL_PTS;
+            const int v = qq / POOL_VIEW_PTS, k = qq - v * POOL_VIEW_PTS;
+            myrow = p.slots[tt.b * p.t_cap + step] * p.slot_rows + v * p.view_rows + p.tok_off + k;
         };
         bool have = wk.next(t);
-        if (grp == 1 && have) have = wk.next(t);           // group 1 starts at tile 1
-        const __half* src[8];
-        if (have) resolve(t, src);
-        int n = 0;                                          // tiles this group has filled
-        long long w_empty = 0, w_land = 0;
-        const long long t_begin = clock64();
+        if (have) resolve(t);
+        int it = 0, cur_b = -1, visits = 0;
+        long long c_text = 0;
         while (have) {
-            const long long c0 = clock64();
-            mbar_wait(&a_empty[grp], (n & 1) ^ 1);
-            w_empty += clock64() - c0;
+            const int buf = it % POOL_NBUF;
+            const uint32_t ph = (it / POOL_NBUF) & 1;
+            const long long c0 = p.dbg ? clock64() : 0;
+            mbar_wait_relaxed(&a_empty[buf], ph ^ 1);
+            if (p.dbg) w_a += clock64() - c0;
+            // this warp's row group is present if it holds at least one row of the tile.  Everything the copies need is made
+            // warp-uniform (shuffle broadcasts) and ONE elected lane issues the CH copies back to back (elect_one(), common.cuh).
+            const int ngroups = min(2, max(0, ((uniform_i32(t.nrows) + 3) >> 2) - 2 * warp));
+            int rr[8];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const uint32_t dst = smem_u32(tile_base + k * L::A_CHUNK);
+            for (int i = 0; i < 8; ++i) rr[i] = __shfl_sync(0xffffffffu, myrow, i);
+            const int ubuf = uniform_i32(buf);
+            const uint32_t dst = smem_u32(sA) + ubuf * L::A_BYTES + warp * 1024;
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&a_full[ubuf], static_cast<uint32_t>(ngroups) * 4u * D * 2u);
+                if (ngroups > 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (src[i]) cp_async_16(dst + sw128_offset(r0 + 8 * i, u), src[i] + k * 64);
-            }
-            cp_async_commit();
-            const long long c1 = clock64();
-            cp_async_wait<0>();
-            fence_proxy_async_smem();
-            mbar_arrive(&a_full[grp]);
-            w_land += clock64() - c1;
-            // this group's next tile (two tiles ahead in the CTA's sequence): resolve its rows and prefetch them into L2
-            // while the consumers work on the tile just published
-            Tile tn;
-            have = wk.next(tn) && wk.next(tn);
-            const __half* nsrc[8];
-            if (have) {
-                resolve(tn, nsrc);
-                if (u == 0) {
+                    for (int ck = 0; ck < CH; ++ck)
+                        tma_gather4(dst + ck * L::A_CHUNK, &tm_fts, ck * 64, rr[0], rr[1], rr[2], rr[3], &a_full[ubuf]);
+                }
+                if (ngroups > 1) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (nsrc[i]) l2_prefetch_bulk(nsrc[i], D * 2);
+                    for (int ck = 0; ck < CH; ++ck)
+                        tma_gather4(dst + 512 + ck * L::A_CHUNK, &tm_fts, ck * 64, rr[4], rr[5], rr[6], rr[7], &a_full[ubuf]);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) src[i] = nsrc[i];
-            t = tn;
-            ++n;
+            __syncwarp();
+            if (t.b != cur_b) {
+                // first tile of an episode: once the tensor core is done with the previous episode, move this warp's half of
+                // the new text operand into TMEM (the tile just issued lands meanwhile)
+                const long long c1 = p.dbg ? clock64() : 0;
+                if (visits > 0) mbar_wait_guard(ep_done, (visits - 1) & 1);
+                tc_fence_after();
+                cur_b = t.b; ++visits;
+                stage_text<D, BU>(p.text_ws + static_cast<size_t>(t.b) * UNITS * 128, tlane, p.l_pad, taddr_lane, 0);
+                tc_fence_before();
+                mbar_arrive(t_ready);
+                if (p.dbg) c_text += clock64() - c1;
+            }
+            have = wk.next(t);
+            if (have) resolve(t);
+            ++it;
         }
-        if (p.dbg && gt == 0) {
-            long long* d = p.dbg + blockIdx.x * 16 + grp * 3;
-            d[0] = clock64() - t_begin; d[1] = w_empty; d[2] = w_land;
-        }
+        if (p.dbg && tid == 0) { p.dbg[blockIdx.x * 16 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 16 + 1] = w_a; p.dbg[blockIdx.x * 16 + 2] = c_text; }
     } else if (warp == POOL_MMA_WARP) {
         // ------------------------------------------------------------ MMA issuer: S^T = text (TMEM) x tile^T (smem)
-        if (lane == 0) {
+        {   // the whole (converged) warp walks the tiles and waits; one elected lane issues (elect_one(), common.cuh)
             constexpr uint32_t idesc = umma_idesc_f16(128, POOL_ROWS);
             int it = 0, cur_b = -1, visits = 0;
-            long long w_afull = 0, w_dempty = 0;
-            const long long t_begin = clock64();
             while (wk.next(t)) {
-                const int buf = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
+                const int buf = uniform_i32(it % POOL_NBUF);
+                const uint32_t ph = (it / POOL_NBUF) & 1;
                 if (t.b != cur_b) {
-                    mbar_wait(t_ready, visits & 1);
+                    if (visits > 0 && elect_one()) umma_commit(ep_done);      // arrives when every MMA issued so far has retired
+                    __syncwarp();
+                    mbar_wait_guard(t_ready, visits & 1);
                     cur_b = t.b;
                     ++visits;
                 }
-                const long long c0 = clock64();
-                mbar_wait(&d_empty[buf], ph ^ 1);
-                const long long c1 = clock64();
-                mbar_wait(&a_full[buf], ph);
-                w_dempty += c1 - c0;
-                w_afull += clock64() - c1;
+                const long long c0 = p.dbg ? clock64() : 0;
+                mbar_wait_guard(&d_empty[buf], ph ^ 1);
+                const long long c1 = p.dbg ? clock64() : 0;
+                mbar_wait_relaxed(&a_full[buf], ph);
+                if (p.dbg) { w_b += c1 - c0; w_a += clock64() - c1; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + D_COL0 + buf * POOL_ROWS;
-                const uint32_t tile_s = smem_u32(sA + buf * L::A_BYTES);
+                const uint32_t tile_s = smem_u32(sA) + buf * L::A_BYTES;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const uint64_t db = umma_desc_sw128_kmajor(tile_s + k * L::A_CHUNK);
+                    for (int k = 0; k < CH; ++k) {
+                        const uint64_t db = umma_desc_sw128_kmajor(tile_s + k * L::A_CHUNK);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)   // K = 16 per instruction = 8 TMEM columns of A, 32 bytes of B
-                        umma_f16_ts(d_tmem, tmem_base + k * 32 + kk * 8, db + 2 * kk, idesc, (k | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk)   // K = 16 per instruction = 8 TMEM columns of A, 32 bytes of B
+                            umma_f16_ts(d_tmem, tmem_base + k * 32 + kk * 8, db + 2 * kk, idesc, (k | kk) ? 1u : 0u);
+                    }
+                    umma_commit(&d_full[buf]);
                 }
-                umma_commit(&d_full[buf]);
+                __syncwarp();
                 ++it;
             }
-            if (p.dbg) {
-                long long* d = p.dbg + blockIdx.x * 16 + 6;
-                d[0] = clock64() - t_begin; d[1] = w_afull; d[2] = w_dempty;
+            if (p.dbg && lane == 0) {
+                long long* d = p.dbg + blockIdx.x * 16 + 3;
+                d[0] = clock64() - t_begin; d[1] = w_a; d[2] = w_b;
             }
         }
-    } else if (warp < POOL_GATHER_WARP0) {
-        // ------------------------------------------------------------ text operand -> TMEM, relevance max, softmax weights
-        const int q = warp;                         // TMEM lane quadrant
-        const int e = tid;                          // 0..127 = TMEM lane = text position
+    } else if (warp < POOL_MMA_WARP) {
+        // ------------------------------------------------------------ relevance max + softmax numerators (+ second half of the text)
+        const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+        const int tlane = q * 32 + lane;            // TMEM lane = text position
+        const uint32_t taddr_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int e = tid - POOL_RED_WARP0 * 32;    // 0..127; threads 0..63 own one tile row each in the softmax part
         int it = 0, cur_b = -1;
-        if (e == 0) { s_scal[2] = 0.0f; s_scal[3] = 0.0f; }
-        long long w_dfull = 0, c_text = 0, c_red = 0;
-        const long long t_begin = clock64();
+        long long c_text = 0, c_soft = 0;
         while (wk.next(t)) {
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            const long long c0 = clock64();
+            const int buf = it % POOL_NBUF;
+            const uint32_t ph = (it / POOL_NBUF) & 1;
             if (t.b != cur_b) {
-                // Every MMA that read the previous episode's text has retired: this warp waited on d_full of the previous
-                // tile below.  Lane-major workspace: unit c of this lane's text position at ((b*D/8 + c)*128 + lane)*16.
+                // every MMA that read the previous episode's text has retired: this warp waited on d_full of the previous tile
+                const long long c0 = p.dbg ? clock64() : 0;
                 cur_b = t.b;
-                const uint4* src = p.text_ws + static_cast<size_t>(t.b) * (D / 8) * 128 + e;
-                const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-                for (int c0u = 0; c0u < D / 8; c0u += 16) {     // 16 coalesced 16-byte loads in flight, then 8 stores of 32 B
-                    uint4 vv[16];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) vv[c] = __ldg(src + static_cast<size_t>(c0u + c) * 128);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t v8[8] = {vv[2 * c].x, vv[2 * c].y, vv[2 * c].z, vv[2 * c].w,
-                                                vv[2 * c + 1].x, vv[2 * c + 1].y, vv[2 * c + 1].z, vv[2 * c + 1].w};
-                        tmem_st_32x32b_x8(ta + (c0u / 2 + c) * 8, v8);
-                    }
-                }
-                tmem_st_wait();
+                named_bar_sync(4, 128);             // every reducer is done with the previous episode's table
+                for (int i = e; i <= n_cells; i += 128) s_csr[i] = p.cell_start[t.b * (n_cells + 1) + i];
+                for (int i = e; i < n_cells; i += 128) s_cr[i] = p.cell_rank[t.b * n_cells + i];
+                stage_text<D, BU>(p.text_ws + static_cast<size_t>(t.b) * UNITS * 128, tlane, p.l_pad, taddr_lane, UNITS / 2);
                 tc_fence_before();
                 mbar_arrive(t_ready);
-                for (int i = e; i <= n_cells; i += 128) s_cs[i] = p.cell_start[t.b * (n_cells + 1) + i];
-                for (int i = e; i < n_cells; i += 128) s_cr[i] = p.cell_rank[t.b * n_cells + i];
+                if (p.dbg) c_text += clock64() - c0;
             }
-            const long long c1 = clock64();
-            c_text += c1 - c0;
-            mbar_wait(&d_full[buf], ph);
-            const long long c2 = clock64();
-            w_dfull += c2 - c1;
+            const long long c1 = p.dbg ? clock64() : 0;
+            mbar_wait_guard(&d_full[buf], ph);
+            const long long c2 = p.dbg ? clock64() : 0;
             tc_fence_after();
-            float v[64];
-            {
-                const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + D_COL0 + buf * POOL_ROWS;
+            float* part = s_part + buf * 4 * POOL_ROWS;
+            float wmax = -INFINITY;                 // this warp's quadrant: max over its 32 text positions for tile row `lane`
+            const bool has_text = q * 32 < p.l_pad; // a quadrant of padding lanes only (replicas of position 0) adds nothing to the max
+            if (!has_text) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[buf]);
+            } else {
+                float v[32];
+                const uint32_t ta = taddr_lane + D_COL0 + buf * POOL_ROWS;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t r[16];
-                    tmem_ld_32x32b_x16(ta + c * 16, r);
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r0[16];
+                    tmem_ld_32x32b_x16(ta + c * 16, r0);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[c * 16 + j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; ++j) v[c * 16 + j] = __uint_as_float(r0[j]);
                 }
                 tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[buf]);      // the accumulator may be overwritten
+                lane_max_level<32>(v, lane, 16);
+                lane_max_level<16>(v, lane, 8);
+                lane_max_level<8>(v, lane, 4);
+                lane_max_level<4>(v, lane, 2);
+                lane_max_level<2>(v, lane, 1);
+                wmax = v[0];
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d_empty[buf]);
-            lane_max_level<64>(v, lane, 16);
-            lane_max_level<32>(v, lane, 8);
-            lane_max_level<16>(v, lane, 4);
-            lane_max_level<8>(v, lane, 2);
-            lane_max_level<4>(v, lane, 1);
-            s_part[q * POOL_ROWS + 2 * lane] = v[0];
-            s_part[q * POOL_ROWS + 2 * lane + 1] = v[1];
-            named_bar_sync(1, 128);
-            if (e < POOL_ROWS)
-                s_w[buf * POOL_ROWS + e] = fmaxf(fmaxf(s_part[e], s_part[POOL_ROWS + e]),
-                                                 fmaxf(s_part[2 * POOL_ROWS + e], s_part[3 * POOL_ROWS + e]));
-            named_bar_sync(2, 128);
-            c_red += clock64() - c2;
-            // --- softmax weights of this tile's rows: one thread per row (warps 0 and 1), per-cell max and sum by
-            //     warp-segmented scans (cells are contiguous row segments), one shared-memory hop for a cell that
-            //     straddles rows 31|32; the cells of the tile are emitted as a compact segment list for the pooling warps
-            float m_carry = s_scal[2], s_carry = s_scal[3];
-            float new_m = 0.0f, new_s = 0.0f;
-            bool writes_carry = false;
-            if (warp < 2 && !(p.mode & 2)) {
-                const bool valid = e < t.nrows;
-                const float* wrow = s_w + buf * POOL_ROWS;
-                int c_lo = 0, c_hi = 0, cellid = 0, seg_lo = e, seg_hi = e + 1;
+            if (warp != POOL_RED_WARP0 + 3) {
+                // reducer warps 0..2 hand their partial maxima to warp 3 through shared memory + an mbarrier and move on to the next
+                // tile; warp 3 owns TMEM lanes 96..127 (padding whenever the instruction has <= 96 tokens), so the softmax part
+                // below runs in parallel with the others' butterflies
+                part[(warp - POOL_RED_WARP0) * POOL_ROWS + lane] = wmax;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&m_full[buf]);
+            } else {
+                mbar_wait_guard(&m_full[buf], ph);  // (at an episode switch this also publishes the other warps' s_csr / s_cr loads)
+                // ---- softmax numerator of row e (one warp: 32 rows): exp(w - max over its cell), the cell max taken with
+                //      match.any + redux.max, merged with the carried max of a cell that an earlier tile opened (the pooling
+                //      warps rescale their accumulators by s_scal)
+                const float w = fmaxf(fmaxf(wmax, part[lane]), fmaxf(part[POOL_ROWS + lane], part[2 * POOL_ROWS + lane]));
+                const bool valid = lane < t.nrows;
+                int cid = -1;
                 if (valid) {
-                    const int P = t.pos + e;
+                    const int P = t.pos + lane;
                     int a = 0, c = n_cells;        // last cell with cs[cell] <= P
                     while (c - a > 1) {
                         const int mid = (a + c) >> 1;
-                        if (s_cs[mid] <= P) a = mid; else c = mid;
+                        if (s_csr[mid] <= P) a = mid; else c = mid;
                     }
-                    cellid = a;
-                    c_lo = s_cs[cellid]; c_hi = s_cs[cellid + 1];
-                    seg_lo = max(c_lo, t.pos) - t.pos;
-                    seg_hi = min(c_hi, t.pos + t.nrows) - t.pos;
+                    cid = a;
+                    if (p.w_out) p.w_out[static_cast<size_t>(t.b) * p.cap + P] = w;
                 }
-                const int w0 = warp * 32;
-                const int lo_w = max(seg_lo, w0) - w0, hi_w = min(seg_hi, w0 + 32) - w0;     // this warp's part, in lanes
-                const bool spans = valid && seg_lo < 32 && seg_hi > 32;
-                const float wr = valid ? wrow[e] : -INFINITY;
-                // segment max
-                float m = wr;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float v2 = __shfl_up_sync(0xffffffffu, m, o);
-                    if (lane - o >= lo_w) m = fmaxf(m, v2);
-                }
-                m = __shfl_sync(0xffffffffu, m, hi_w - 1);
-                // index of this row's segment inside the tile = number of segment heads before it
-                const bool head = valid && (e == seg_lo);
-                const unsigned heads = __ballot_sync(0xffffffffu, head);
-                if (lane == (warp == 0 ? 31 : 0)) s_part[warp] = m;          // s_part is free again after barrier 2
-                if (lane == 0) reinterpret_cast<int*>(s_part)[8 + warp] = __popc(heads);
-                named_bar_sync(4, 64);
-                if (spans) m = fmaxf(s_part[0], s_part[1]);
-                // (rows of a cell that started in warp 0 see no head before them in warp 1 and land on warp 0's last segment)
-                const int seg_idx = __popc(heads & ((2u << lane) - 1u)) - 1 + (warp == 1 ? reinterpret_cast<int*>(s_part)[8] : 0);
-                const bool continues = valid && (c_lo < t.pos);
-                float cscale = 1.0f, s0 = 0.0f;
-                if (continues) {
-                    const float mn = fmaxf(m, m_carry);
-                    cscale = expf(m_carry - mn);
-                    s0 = s_carry * cscale;
-                    m = mn;
-                }
-                const float my_p = valid ? expf(wr - m) : 0.0f;
-                // segment sum
-                float sm = my_p;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float v2 = __shfl_up_sync(0xffffffffu, sm, o);
-                    if (lane - o >= lo_w) sm += v2;
-                }
-                sm = __shfl_sync(0xffffffffu, sm, hi_w - 1);
-                if (lane == (warp == 0 ? 31 : 0)) s_part[2 + warp] = sm;
-                named_bar_sync(5, 64);
-                if (spans) sm = s_part[2] + s_part[3];
-                const float ssum = s0 + sm;
-                if (valid) {
-                    if (e == seg_hi - 1) {       // last row of the segment publishes it
-                        const int k = seg_idx;
-                        float fin = 0.0f;
-                        int rank = 0;
-                        if (c_hi <= t.pos + t.nrows) { fin = 1.0f / ssum; rank = s_cr[cellid]; }
-                        else { writes_carry = true; new_m = m; new_s = ssum; }
-                        s_send[buf * POOL_ROWS + k] = seg_hi;
-                        s_sfin[buf * POOL_ROWS + k] = fin;
-                        s_srank[buf * POOL_ROWS + k] = rank;
-                        if (seg_hi == t.nrows) s_nseg[buf] = k + 1;
-                    }
-                    if (e == 0) s_scal[buf] = continues ? cscale : 1.0f;
-                    if (p.w_out) p.w_out[static_cast<size_t>(t.b) * p.cap + t.pos + e] = wr;
-                }
-                s_p[buf * POOL_ROWS + e] = my_p;
-            } else if (warp < 2) {
-                if (e == 0) { s_nseg[buf] = 0; s_scal[buf] = 1.0f; }
+                const unsigned same = __match_any_sync(0xffffffffu, cid);
+                float m = ord2f(__reduce_max_sync(same, f2ord(w)));
+                const float carry_m = *s_carry_m;
+                const int carry_c = *s_carry_c;     // (episode << 16 | cell) of the cell the previous tile left open
+                const int key = (t.b << 16) | (cid & 0xffff);
+                __syncwarp();                       // every lane has read the carry before the last row's lane replaces it
+                const bool cont = valid && (key == carry_c);
+                if (cont) m = fmaxf(m, carry_m);
+                s_p[buf * POOL_ROWS + lane] = valid ? ex2_approx((w - m) * LOG2E) : 0.0f;
+                // compact rank of the row's cell (= its row in `pooled`), flagged when this is the cell's last row
+                s_cid[buf * POOL_ROWS + lane] = valid ? (s_cr[cid] | ((t.pos + lane + 1 == s_csr[cid + 1]) ? 0x10000 : 0)) : -1;
+                if (lane == 0) s_scal[buf] = cont ? ex2_approx((carry_m - m) * LOG2E) : 1.0f;
+                if (lane == t.nrows - 1) { *s_carry_m = m; *s_carry_c = key; }
+                mbar_arrive(&p_full[buf]);          // release: s_p[buf] / s_scal[buf] are visible to the pooling warps
             }
-            named_bar_sync(3, 128);             // everyone has read the old carry / s_cs / s_part
-            if (writes_carry) { s_scal[2] = new_m; s_scal[3] = new_s; }
-            mbar_arrive(&p_full[buf]);          // release: s_p / segment list / s_scal[buf] are visible to the pooling warps
+            if (p.dbg) { w_a += c2 - c1; c_soft += clock64() - c2; }
             ++it;
         }
-        if (p.dbg && e == 0) {
-            long long* d = p.dbg + blockIdx.x * 16 + 10;
-            d[0] = clock64() - t_begin; d[1] = w_dfull; d[2] = c_text; p.dbg[blockIdx.x * 16 + 9] = c_red;
+        if (p.dbg && e == 96) {
+            long long* d = p.dbg + blockIdx.x * 16 + 6;
+            d[0] = clock64() - t_begin; d[1] = w_a; d[2] = c_text; d[3] = c_soft;
         }
     } else {
-        // ------------------------------------------------------------ weighted sums from the resident tile
-        const int pt = tid - POOL_POOL_WARP0 * 32;     // owns columns 4*pt .. 4*pt+3
-        const int k = pt >> 4;                         // chunk of those columns
-        const int u = (pt & 15) >> 1;
-        const int sub = (pt & 1) * 8;
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        // ------------------------------------------------------------ weighted sums from the resident tile (warp-level HMMA)
+        // out[cell, :] = sum_r p[r] x[r, :] is a matrix product  X^T[D, 32 rows] . W[32 rows, 8 cell slots]  with W[r, slot] = p[r]
+        // when row r belongs to the cell in that slot (slot = compact cell rank & 7; ranks are consecutive along the sorted
+        // rows, so an open cell keeps its slot from tile to tile).  Each warp owns 128 columns: 8 column tiles x 2 row steps of
+        // mma.sync.m16n8k16 per tile (A = the resident tile through ldmatrix.trans, B = weights built in registers from
+        // s_p / s_cid, fp32 accumulators in registers across tiles) instead of ~570 scalar instructions.  Each weight enters
+        // as fp16 value + fp16 rounding residual (two MMAs on the same A fragment), i.e. to ~2^-22: with one fp16 weight the
+        // action logits drifted to 1.08e-3.
+        const int pw = warp - POOL_POOL_WARP0;         // columns [128 pw, 128 pw + 128)
+        const int g = lane >> 2, tq = lane & 3;
+        float cacc[8][4];                              // [column tile][(col g, slot 2tq), (g, 2tq+1), (g+8, 2tq), (g+8, 2tq+1)]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cacc[i][0] = cacc[i][1] = cacc[i][2] = cacc[i][3] = 0.f;
+        float s_slot = 0.f;                            // sum of weights of the cell in slot g (replicated over tq)
         int it = 0;
-        long long w_pfull = 0, c_loop = 0;
-        const long long t_begin = clock64();
+        long long c_loop = 0;
         while (wk.next(t)) {
-            const int buf = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            const long long c0 = clock64();
-            mbar_wait(&p_full[buf], ph);
-            w_pfull += clock64() - c0;
-            mbar_wait(&a_full[buf], ph);               // already complete; orders the cp.async writes before our reads
-            const uint32_t chunk_s = smem_u32(sA + buf * L::A_BYTES + k * L::A_CHUNK) + sub;
-            const float cs = s_scal[buf];
-            acc0 *= cs; acc1 *= cs; acc2 *= cs; acc3 *= cs;
+            const int buf = it % POOL_NBUF;
+            const uint32_t ph = (it / POOL_NBUF) & 1;
+            const long long c0 = p.dbg ? clock64() : 0;
+            mbar_wait_guard(&p_full[buf], ph);
+            mbar_wait_guard(&a_full[buf], ph);         // already complete; makes the TMA-written tile visible to this thread
+            const long long c1 = p.dbg ? clock64() : 0;
+            const uint32_t tile_s = smem_u32(sA) + buf * L::A_BYTES;
             const float* pp = s_p + buf * POOL_ROWS;
-            __half* out_b = p.pooled + static_cast<size_t>(t.b) * n_cells * D + pt * 4;
-            const long long c_loop0 = clock64();
-            const int nseg = (p.mode & 1) ? 0 : s_nseg[buf];
-            int r = 0;
-            for (int sg = 0; sg < nseg; ++sg) {
-                const int end = s_send[buf * POOL_ROWS + sg];
-                // rows of one cell: branch-free inner loop, 4 rows per round (loads first, then the FMA chain)
-                for (; r + 4 <= end; r += 4) {
-                    uint2 raw[4];
-                    float w4[4];
+            const int* rk = s_cid + buf * POOL_ROWS;    // compact cell rank | (last row of its cell ? 0x10000 : 0); -1 = no row
+            const int my_rk = rk[lane];
+            const int rank0 = __shfl_sync(0xffffffffu, my_rk, 0) & 0xffff;
+            const int rank_last = __shfl_sync(0xffffffffu, my_rk, t.nrows - 1) & 0xffff;
+            {
+                const float sc = s_scal[buf];          // a later tile raised the open cell's max (1 otherwise): its slot is rank0 & 7
+                if (sc != 1.0f) {
+                    const int s0 = rank0 & 7;
+                    if (g == s0) s_slot *= sc;
+                    if (2 * tq == s0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(raw[i].x), "=r"(raw[i].y) : "r"(chunk_s + sw128_offset(r + i, u)));
-                        w4[i] = pp[r + i];
-                    }
+                        for (int i = 0; i < 8; ++i) { cacc[i][0] *= sc; cacc[i][2] *= sc; }
+                    } else if (2 * tq + 1 == s0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].x));
-                        const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].y));
-                        acc0 = fmaf(w4[i], x01.x, acc0); acc1 = fmaf(w4[i], x01.y, acc1);
-                        acc2 = fmaf(w4[i], x23.x, acc2); acc3 = fmaf(w4[i], x23.y, acc3);
+                        for (int i = 0; i < 8; ++i) { cacc[i][1] *= sc; cacc[i][3] *= sc; }
                     }
-                }
-                for (; r < end; ++r) {
-                    uint2 raw;
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(raw.x), "=r"(raw.y) : "r"(chunk_s + sw128_offset(r, u)));
-                    const float w = pp[r];
-                    const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-                    const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-                    acc0 = fmaf(w, x01.x, acc0); acc1 = fmaf(w, x01.y, acc1);
-                    acc2 = fmaf(w, x23.x, acc2); acc3 = fmaf(w, x23.y, acc3);
-                }
-                const float fin = s_sfin[buf * POOL_ROWS + sg];
-                if (fin != 0.0f) {      // the cell is complete: normalise, store, reset (else it is carried into the next tile)
-                    const __half2 h01 = __floats2half2_rn(acc0 * fin, acc1 * fin);
-                    const __half2 h23 = __floats2half2_rn(acc2 * fin, acc3 * fin);
-                    uint2 o;
-                    o.x = *reinterpret_cast<const uint32_t*>(&h01);
-                    o.y = *reinterpret_cast<const uint32_t*>(&h23);
-                    *reinterpret_cast<uint2*>(out_b + static_cast<size_t>(s_srank[buf * POOL_ROWS + sg]) * D) = o;
-                    acc0 = acc1 = acc2 = acc3 = 0.f;
                 }
             }
-            c_loop += clock64() - c_loop0;
+            // rows this thread feeds into the B fragments: row step ks covers rows 16 ks + {2tq, 2tq+1, 2tq+8, 2tq+9}
+            float2 pv[2][2];
+            int2 rv[2][2];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    pv[ks][h] = *reinterpret_cast<const float2*>(pp + 16 * ks + 8 * h + 2 * tq);
+                    rv[ks][h] = *reinterpret_cast<const int2*>(rk + 16 * ks + 8 * h + 2 * tq);
+                }
+            for (int base = rank0; base <= rank_last; base += 8) {       // one pass per 8 consecutive cells (normally one)
+                uint32_t bh[2][2], bl[2][2];           // fp16 weights of slot g and their fp16 rounding residuals
+                float add = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int ra = (rv[ks][h].x & 0xffff) - base, rb = (rv[ks][h].y & 0xffff) - base;
+                        const bool va = rv[ks][h].x >= 0 && ra >= 0 && ra < 8 && (((ra + base) & 7) == g);
+                        const bool vb = rv[ks][h].y >= 0 && rb >= 0 && rb < 8 && (((rb + base) & 7) == g);
+                        const float2 w = make_float2(va ? pv[ks][h].x : 0.f, vb ? pv[ks][h].y : 0.f);
+                        const __half2 hi = __floats2half2_rn(w.x, w.y);
+                        const float2 fhi = __half22float2(hi);
+                        const __half2 lo = __floats2half2_rn(w.x - fhi.x, w.y - fhi.y);
+                        bh[ks][h] = *reinterpret_cast<const uint32_t*>(&hi);
+                        bl[ks][h] = *reinterpret_cast<const uint32_t*>(&lo);
+                        add += w.x + w.y;
+                    }
+                add += __shfl_xor_sync(0xffffffffu, add, 1);
+                add += __shfl_xor_sync(0xffffffffu, add, 2);
+                s_slot += add;
+                {
+                    const int mi = lane >> 3, rr = lane & 7;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const int r = 16 * ks + (mi >> 1) * 8 + rr;
+#pragma unroll
+                        for (int ct = 0; ct < 8; ++ct) {       // 16 columns per tile: units 2ct, 2ct+1 of the warp's 16
+                            const int chunk = 2 * pw + (ct >> 2), u = (ct & 3) * 2 + (mi & 1);
+                            uint32_t a0, a1, a2, a3;
+                            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                                         : "r"(tile_s + chunk * L::A_CHUNK + r * 128 + ((u ^ rr) << 4)));
+                            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(cacc[ct][0]), "+f"(cacc[ct][1]), "+f"(cacc[ct][2]), "+f"(cacc[ct][3])
+                                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bh[ks][0]), "r"(bh[ks][1]));
+                            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(cacc[ct][0]), "+f"(cacc[ct][1]), "+f"(cacc[ct][2]), "+f"(cacc[ct][3])
+                                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bl[ks][0]), "r"(bl[ks][1]));
+                        }
+                    }
+                }
+                // cells of this pass whose last row lies in this tile: normalise, store (rows of `pooled` are the compact ranks), reset
+                unsigned done = 0;
+                {
+                    const int rel = (my_rk & 0xffff) - base;
+                    if (my_rk >= 0 && (my_rk & 0x10000) && rel >= 0 && rel < 8) done = 1u << ((rel + base) & 7);
+                    done = __reduce_or_sync(0xffffffffu, done);
+                }
+                if (done) {
+                    // weight sums of slots 2tq and 2tq+1 live in the lanes with g = 2tq, 2tq+1
+                    const float sa = __shfl_sync(0xffffffffu, s_slot, (2 * tq) * 4), sb = __shfl_sync(0xffffffffu, s_slot, (2 * tq + 1) * 4);
+                    __half* out_b = p.pooled + static_cast<size_t>(t.b) * n_cells * D + pw * 128 + g;
+                    if ((done >> (2 * tq)) & 1u) {
+                        const float fin = 1.0f / sa;
+                        __half* orow = out_b + static_cast<size_t>(base + ((2 * tq - base) & 7)) * D;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            orow[i * 16] = __float2half_rn(cacc[i][0] * fin);
+                            orow[i * 16 + 8] = __float2half_rn(cacc[i][2] * fin);
+                            cacc[i][0] = cacc[i][2] = 0.f;
+                        }
+                    }
+                    if ((done >> (2 * tq + 1)) & 1u) {
+                        const float fin = 1.0f / sb;
+                        __half* orow = out_b + static_cast<size_t>(base + ((2 * tq + 1 - base) & 7)) * D;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            orow[i * 16] = __float2half_rn(cacc[i][1] * fin);
+                            orow[i * 16 + 8] = __float2half_rn(cacc[i][3] * fin);
+                            cacc[i][1] = cacc[i][3] = 0.f;
+                        }
+                    }
+                    if ((done >> g) & 1u) s_slot = 0.f;
+                }
+            }
+            if (p.dbg) { w_a += c1 - c0; c_loop += clock64() - c1; }
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_empty[buf]);
             ++it;
         }
-        if (p.dbg && pt == 0) {
-            long long* d = p.dbg + blockIdx.x * 16 + 13;
-            d[0] = clock64() - t_begin; d[1] = w_pfull; d[2] = c_loop;
+        if (p.dbg && tid == POOL_FIXED_THREADS) {
+            long long* d = p.dbg + blockIdx.x * 16 + 10;
+            d[0] = clock64() - t_begin; d[1] = w_a; d[2] = c_loop;
         }
     }
 
@@ -609,48 +684,52 @@ pool_kernel(PoolParams p) {
     }
 }
 
+template <int D>
+static int launch_pool(const void* fts, long long fts_rows, const void* text_fts, void* text_ws, int text_ws_ready, int grid,
+                       PoolParams& p, cudaStream_t stream) {
+    // gather4 tensor map: the slab as [fts_rows, D] fp16, box = 64 columns x 1 row (the instruction names 4 rows)
+    CUtensorMap tm;
+    const int rc = make_tmap_f16_2d(&tm, fts, static_cast<uint64_t>(D), static_cast<uint64_t>(fts_rows), static_cast<uint64_t>(D) * 2, 64, 1);
+    if (rc) return rc;
+    constexpr int smem = PoolSmem<D>::TOTAL;
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (!text_ws_ready) {
+        GMM_CUDA_CHECK(launch_pdl(text_to_lanes_kernel<D>, dim3(D / 8, p.batch), dim3(128), 0, stream,
+                                  reinterpret_cast<const __half*>(text_fts), reinterpret_cast<uint4*>(text_ws), p.l_pad));
+        gridmm_count_launch(1);
+    }
+    GMM_CUDA_CHECK(launch_pdl(pool_kernel<D>, dim3(grid), dim3(POOL_FIXED_THREADS + D / 4), smem, stream, tm, p));
+    gridmm_count_launch(1);
+    return 0;
+}
+
 }  // namespace gmm
 
 static long long* g_pool_dbg = nullptr;
-static int g_pool_mode = 0;
-extern "C" void gridmm_debug_set_pool_mode(int mode) { g_pool_mode = mode; }
-// Debug hook (tools/microbench.py): per-CTA cycle counters [grid][16] written by the next pool launches; null disables.
+// Debug hook (tools/microbench2.py): per-CTA cycle counters [grid][16] written by the next pool launches; null disables.
 extern "C" void gridmm_debug_set_pool_counters(long long* dbg) { g_pool_dbg = dbg; }
 
-extern "C" int gridmm_pool(const void* fts, int feat_dim, const int* slots, int t_cap, int slot_rows, int view_rows,
-                           int tok_off, const int* perm, int cap, const int* cell_start, const int* cell_rank, int n_cells,
-                           const void* text_fts, int l_pad, int batch, void* text_ws, void* pooled, float* w_out, int num_ctas,
-                           cudaStream_t stream) {
+extern "C" int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, const int* slots, int t_cap, int slot_rows,
+                           int view_rows, int tok_off, const int* perm, int cap, const int* cell_start, const int* cell_rank,
+                           int n_cells, const void* text_fts, int l_pad, int batch, void* text_ws, int text_ws_ready,
+                           void* pooled, float* w_out, int num_ctas, cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0) return 0;
-    if (!fts || !slots || !perm || !cell_start || !cell_rank || !text_fts || !text_ws || !pooled) return GRIDMM_ERR_ARG;
-    if (batch > POOL_MAX_BATCH || n_cells > POOL_MAX_CELLS || l_pad < 1 || l_pad > 128) return GRIDMM_ERR_SHAPE;
+    if (!fts || !slots || !perm || !cell_start || !cell_rank || !text_ws || !pooled) return GRIDMM_ERR_ARG;
+    if (!text_ws_ready && !text_fts) return GRIDMM_ERR_ARG;
+    if (batch > POOL_MAX_BATCH || n_cells > POOL_MAX_CELLS || l_pad < 1 || l_pad > 128 || fts_rows <= 0) return GRIDMM_ERR_SHAPE;
     if (feat_dim != 768 && feat_dim != 512) return GRIDMM_ERR_SHAPE;
     if ((reinterpret_cast<uintptr_t>(text_fts) & 15) || (reinterpret_cast<uintptr_t>(text_ws) & 15)) return GRIDMM_ERR_SHAPE;
     PoolParams p;
-    p.fts = reinterpret_cast<const __half*>(fts); p.slots = slots; p.perm = perm; p.cell_start = cell_start;
-    p.cell_rank = cell_rank; p.text = reinterpret_cast<const __half*>(text_fts);
+    p.slots = slots; p.perm = perm; p.cell_start = cell_start; p.cell_rank = cell_rank;
     p.text_ws = reinterpret_cast<const uint4*>(text_ws);
     p.pooled = reinterpret_cast<__half*>(pooled); p.w_out = w_out;
     p.batch = batch; p.t_cap = t_cap; p.cap = cap; p.n_cells = n_cells; p.l_pad = l_pad;
-    p.slot_rows = slot_rows; p.view_rows = view_rows; p.tok_off = tok_off; p.dbg = g_pool_dbg; p.mode = g_pool_mode;
+    p.slot_rows = slot_rows; p.view_rows = view_rows; p.tok_off = tok_off; p.dbg = g_pool_dbg;
     int dev = 0, sms = 0;
     GMM_CUDA_CHECK(cudaGetDevice(&dev));
     GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = num_ctas > 0 ? num_ctas : sms;
-    if (feat_dim == 768) {
-        constexpr int smem = PoolSmem<768>::TOTAL;
-        GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        GMM_CUDA_CHECK(launch_pdl(text_to_lanes_kernel<768>, dim3(768 / 8, batch), dim3(128), 0, stream, p.text,
-                                  reinterpret_cast<uint4*>(text_ws), l_pad));
-        GMM_CUDA_CHECK(launch_pdl(pool_kernel<768>, dim3(grid), dim3(POOL_FIXED_THREADS + 768 / 4), smem, stream, p));
-    } else {
-        constexpr int smem = PoolSmem<512>::TOTAL;
-        GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        GMM_CUDA_CHECK(launch_pdl(text_to_lanes_kernel<512>, dim3(512 / 8, batch), dim3(128), 0, stream, p.text,
-                                  reinterpret_cast<uint4*>(text_ws), l_pad));
-        GMM_CUDA_CHECK(launch_pdl(pool_kernel<512>, dim3(grid), dim3(POOL_FIXED_THREADS + 512 / 4), smem, stream, p));
-    }
-    gridmm_count_launch(2);
-    return 0;
+    if (feat_dim == 768) return launch_pool<768>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, stream);
+    return launch_pool<512>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, stream);
 }

@@ -510,20 +510,16 @@ class GlocalTextPathNavCMT(nn.Module):
         # ---- text_proj + relevance pooling + grid_proj (vilmodel.py:793-807)
         txt16 = self.buf("txt16", (B * L, HID), f16)
         ops.copy_rows(txt32, L, 0, L, B, L, 0, out_f16=txt16)
-        l_pad = (L + 7) // 8 * 8
-        tp16 = self.buf("tp16", (B * l_pad, HID), f16)
-        if l_pad == L:
-            ops.linear(txt16, self.W16("text_proj.weight"), self.B32("text_proj.bias"), out_f16=tp16)
-        else:
-            tmp = self.buf("tp16_tmp", (B * L, HID), f16)
-            ops.linear(txt16, self.W16("text_proj.weight"), self.B32("text_proj.bias"), out_f16=tmp)
-            t3 = tp16.view(B, l_pad, HID)
-            t3[:, :L].copy_(tmp.view(B, L, HID))
-            t3[:, L:].copy_(tmp.view(B, L, HID)[:, :1].expand(B, l_pad - L, HID))   # duplicates never change the max
+        # text_proj lands directly in the pooling kernel's lane-major operand layout (no fp16 [B, L, 768] round trip)
+        if L > 128:
+            raise ops._lib.GridmmError("gridmm_pool keeps one text position per TMEM lane: at most 128 text positions")
+        text_ws = ops.pool_text_ws(txt16.device, B, HID)
+        ops.linear_lanes(txt16, self.W16("text_proj.weight"), self.B32("text_proj.bias"), text_ws, L)
         pooled16 = self.buf("pooled16", (B * NC, HID), f16, zero=True)
         w_out = self.buf("w_out", (B, grid.cap), f32, zero=True) if return_intermediates else None
         ops.pool(grid.slab, grid.feat_dim, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm,
-                 grid.cap, grid.cell_start, grid.cell_rank, NC, tp16, l_pad, B, pooled16, w_out=w_out)
+                 grid.cap, grid.cell_start, grid.cell_rank, NC, None, L, B, pooled16, w_out=w_out, text_ws=text_ws,
+                 text_ws_ready=True)
         proj32 = self.buf("proj32", (B * NC, HID), f32)
         ops.linear(pooled16, self.W16("grid_proj.weight"), self.B32("grid_proj.bias"), out_f32=proj32)
 

@@ -137,18 +137,37 @@ def grid_update(batch, depth, depth_is_f32, depth_scale, pose, view_cs, active, 
 _POOL_WS = {}
 
 
+def pool_text_ws(device, batch, feat_dim):
+    """Persistent (CUDA-graph safe) lane-major text workspace of gridmm_pool: [batch, feat_dim/8, 128] 16-byte units."""
+    key = (device, batch, feat_dim)
+    ws = _POOL_WS.get(key)
+    if ws is None:
+        ws = _POOL_WS[key] = torch.zeros(batch * 128 * feat_dim, dtype=torch.float16, device=device)
+    return ws
+
+
+def linear_lanes(a16, w16, bias, out_lanes, rows_per_b):
+    """text_proj written directly in gridmm_pool's lane-major layout (see include/gridmm_b200.h)."""
+    _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w"); _chk(bias, torch.float32, "bias")
+    _chk(out_lanes, torch.float16, "out_lanes")
+    M, K = a16.shape
+    _lib.call("gridmm_linear_f16_lanes", a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, w16.shape[0], K,
+              _lib.ptr(bias), out_lanes.data_ptr(), rows_per_b, _lib.stream_ptr())
+
+
 def pool(fts, feat_dim, slots, t_cap, slot_rows, view_rows, tok_off, perm, cap, cell_start, cell_rank, n_cells, text_fts, l_pad,
-         batch, pooled, w_out=None, num_ctas=0, text_ws=None):
+         batch, pooled, w_out=None, num_ctas=0, text_ws=None, text_ws_ready=False):
+    """text_fts [batch*l_pad, D] fp16, or None with text_ws_ready=True when `text_ws` was filled by linear_lanes."""
     _chk(fts, torch.float16, "fts"); _chk(text_fts, torch.float16, "text_fts"); _chk(pooled, torch.float16, "pooled")
     _chk(slots, torch.int32, "slots"); _chk(perm, torch.int32, "perm")
-    if text_ws is None:      # persistent per (device, size): CUDA-graph safe
-        key = (fts.device, batch, feat_dim)
-        text_ws = _POOL_WS.get(key)
-        if text_ws is None:
-            text_ws = _POOL_WS[key] = torch.empty(batch * 128 * feat_dim, dtype=torch.float16, device=fts.device)
-    _lib.call("gridmm_pool", fts.data_ptr(), feat_dim, slots.data_ptr(), t_cap, slot_rows, view_rows, tok_off, perm.data_ptr(),
-              cap, cell_start.data_ptr(), cell_rank.data_ptr(), n_cells, text_fts.data_ptr(), l_pad, batch, text_ws.data_ptr(),
-              pooled.data_ptr(), _lib.ptr(w_out), num_ctas, _lib.stream_ptr())
+    if text_ws is None:
+        if text_ws_ready:
+            raise _lib.GridmmError("text_ws_ready needs the workspace that linear_lanes filled")
+        text_ws = pool_text_ws(fts.device, batch, feat_dim)
+    fts_rows = fts.numel() // feat_dim
+    _lib.call("gridmm_pool", fts.data_ptr(), fts_rows, feat_dim, slots.data_ptr(), t_cap, slot_rows, view_rows, tok_off,
+              perm.data_ptr(), cap, cell_start.data_ptr(), cell_rank.data_ptr(), n_cells, _lib.ptr(text_fts), l_pad, batch,
+              text_ws.data_ptr(), int(bool(text_ws_ready)), pooled.data_ptr(), _lib.ptr(w_out), num_ctas, _lib.stream_ptr())
 
 
 def cell_sort(batch, cell, n_pts, grid_w, cap, perm, cell_start, cell_rank, n_nonempty):

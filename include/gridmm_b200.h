@@ -71,17 +71,21 @@ int gridmm_cell_sort(int batch, const short* cell, const int* n_pts, int grid_w,
  *     w_j = max_l <x_j, text_fts[b,l]>      over ALL l in [0,l_pad)  (padding positions included, vilmodel.py:798)
  *     pooled[b, rank(c)] = sum_{j in c} softmax_c(w)_j * x_j          (fp32 accumulate, fp16 result)
  * grid_proj is applied afterwards with gridmm_linear_f16 (it commutes with the convex combination).
- *   fts          fp16 feature slab, row r at fts + r*feat_dim; point (step t, view v, patch k) of episode b is row
- *                slots[b*t_cap+t]*slot_rows + v*view_rows + tok_off + k   (CLS token skipped via tok_off, env.py:299)
+ *   fts          fp16 feature slab [fts_rows, feat_dim], row r at fts + r*feat_dim; point (step t, view v, patch k) of episode
+ *                b is row slots[b*t_cap+t]*slot_rows + v*view_rows + tok_off + k (CLS token skipped via tok_off,
+ *                env.py:299); rows are fetched with TMA tile::gather4 through a tensor map over the whole slab
  *   text_fts     fp16 [batch, l_pad, feat_dim] = text_proj(txt_embeds), 16-byte aligned; l_pad <= 128 (the operand lives in
- *                tensor memory, one text position per TMEM lane; unused lanes replicate position 0)
- *   text_ws      workspace, batch * 128 * feat_dim * 2 bytes, 16-byte aligned: lane-major copy of text_fts (written here)
+ *                tensor memory, one text position per TMEM lane; unused lanes replicate position 0); may be NULL when
+ *                text_ws_ready != 0
+ *   text_ws      workspace, batch * 128 * feat_dim * 2 bytes, 16-byte aligned: lane-major copy of text_fts -- written here
+ *                (text_ws_ready = 0) or already produced by gridmm_linear_f16_lanes (text_ws_ready = 1)
  *   pooled       fp16 [batch, n_cells, feat_dim], rows >= n_nonempty[b] are not written
  *   w_out        optional f32 [batch,cap]: w per sorted position (tests), or NULL
  *   num_ctas     0 = one CTA per SM */
-int gridmm_pool(const void* fts, int feat_dim, const int* slots, int t_cap, int slot_rows, int view_rows, int tok_off,
-                const int* perm, int cap, const int* cell_start, const int* cell_rank, int n_cells, const void* text_fts,
-                int l_pad, int batch, void* text_ws, void* pooled, float* w_out, int num_ctas, cudaStream_t stream);
+int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, const int* slots, int t_cap, int slot_rows, int view_rows,
+                int tok_off, const int* perm, int cap, const int* cell_start, const int* cell_rank, int n_cells,
+                const void* text_fts, int l_pad, int batch, void* text_ws, int text_ws_ready, void* pooled, float* w_out,
+                int num_ctas, cudaStream_t stream);
 
 /* ---- stage 3: cross-modal encoder blocks ------------------------------------------------------------------
  * nn.Linear on tcgen05: out = act(a[M,K] . w[N,K]^T + bias) + residual; fp16 operands, fp32 accumulate.
@@ -90,6 +94,12 @@ int gridmm_pool(const void* fts, int feat_dim, const int* slots, int t_cap, int 
 int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                       const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16, int act,
                       cudaStream_t stream);
+
+/* text_proj (vilmodel.py:702, 793-795) written straight into gridmm_pool's lane-major operand layout:
+ * out_lanes[b][u][t] (16-byte units, 128 slots per unit row) = (a[b*rows_per_b + t, :] . w^T + bias)[8u .. 8u+7];
+ * M = batch*rows_per_b, rows_per_b <= 128. */
+int gridmm_linear_f16_lanes(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                            void* out_lanes, int rows_per_b, cudaStream_t stream);
 
 /* softmax(q k^T * scale + mask) v per (episode, head); head dim 64; q/k/v/o fp16 with pitches; kmask [batch,sk] u8,
  * masked keys get `mask_neg` added (-10000: models/ops.py:25-34; -inf: key_padding_mask, transformer.py:176). */
@@ -151,7 +161,6 @@ int gridmm_ce_logits(const float* raw_global, const float* raw_local, const floa
 void gridmm_debug_set_gemm_counters(long long* dbg);
 void gridmm_debug_set_pool_counters(long long* dbg);
 void gridmm_debug_set_gemm_pairs(int on);    /* 0: disable the cta_group::2 GEMM path (A/B timing) */
-void gridmm_debug_set_pool_mode(int mode);   /* bit0: skip the pooling loop, bit1: skip the softmax weights (timing experiments) */
 
 #ifdef __cplusplus
 }

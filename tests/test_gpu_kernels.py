@@ -55,6 +55,26 @@ def test_linear_epilogues(act):
     assert (out - ref).abs().max().item() < 2e-3
 
 
+@pytest.mark.parametrize("B,L", [(32, 80), (3, 37), (1, 128)])
+def test_linear_lanes_layout(B, L):
+    """text_proj epilogue that writes gridmm_pool's lane-major operand: unit u of (b, t) at ((b*96 + u)*128 + t) * 8 halves."""
+    from gridmm_b200 import ops
+    g = torch.Generator().manual_seed(B * 131 + L)
+    a = torch.randn(B * L, 768, generator=g).half().to(_dev())
+    w = (torch.randn(768, 768, generator=g) * 0.05).half().to(_dev())
+    bias = torch.randn(768, generator=g).to(_dev())
+    ws = torch.zeros(B * 128 * 768, dtype=torch.float16, device=_dev())
+    ops.linear_lanes(a, w, bias, ws, L)
+    ref16 = torch.empty(B * L, 768, device=_dev(), dtype=torch.float16)
+    ops.linear(a, w, bias=bias, out_f16=ref16)
+    torch.cuda.synchronize()
+    got = ws.view(B, 96, 128, 8)[:, :, :L].permute(0, 2, 1, 3).reshape(B * L, 768)
+    assert torch.equal(got, ref16)                                   # same kernel, same rounding: bitwise
+    assert ws.view(B, 96, 128, 8)[:, :, L:].abs().max().item() == 0 if L < 128 else True
+    ref = a.float() @ w.float().t() + bias
+    assert (got.float() - ref).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
+
+
 def test_linear_strided_views():
     """A operand / outputs addressed through row pitches (fused QKV buffers)."""
     from gridmm_b200 import ops

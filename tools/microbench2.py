@@ -15,7 +15,6 @@ torch.cuda.set_device(0)
 lib = _lib.load()
 lib.gridmm_debug_set_gemm_counters.argtypes = [ctypes.c_void_p]
 lib.gridmm_debug_set_pool_counters.argtypes = [ctypes.c_void_p]
-lib.gridmm_debug_set_pool_mode.argtypes = [ctypes.c_int]
 want = set(sys.argv[1:]) or {"gemm", "attn", "ln", "pool"}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -105,26 +104,23 @@ if "pool" in want:
     m = step.model; g = step.builder
     from gridmm_b200.env import GridBatch
     grid = GridBatch(g)
-    tp16 = m.buf("tp16", (B * 80, 768), torch.float16)
     pooled = m.buf("pooled16", (B * 196, 768), torch.float16, zero=True)
+    text_ws = ops.pool_text_ws(dev, B, 768)          # filled by the step above (text_proj epilogue)
     fn = lambda: ops.pool(grid.slab, 768, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
-                          grid.cell_start, grid.cell_rank, 196, tp16, 80, B, pooled)
+                          grid.cell_start, grid.cell_rank, 196, None, 80, B, pooled, text_ws=text_ws, text_ws_ready=True)
     nv = int(grid.cell_start[:, -1].sum().item())
     cs = grid.cell_start.cpu()
     sizes = (cs[:, 1:] - cs[:, :-1]).flatten()
     print("pool: valid rows %d; cell sizes: max %d, mean(nonempty) %.1f, cells>256 rows: %d" %
           (nv, int(sizes.max()), float(sizes[sizes > 0].float().mean()), int((sizes > 256).sum())), flush=True)
-    for mode in (0, 1, 3):
-        lib.gridmm_debug_set_pool_mode(mode)
-        us_w = graph_time(fn, n=1, reps=5, cold=False)
-        us_c = graph_time(fn, n=1, reps=5, cold=True)
-        dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
-        lib.gridmm_debug_set_pool_counters(dbg.data_ptr())
-        fn(); torch.cuda.synchronize()
-        lib.gridmm_debug_set_pool_counters(None)
-        d = dbg.float()
-        names = ["g0 tot", "g0 wait_empty", "g0 land", "g1 tot", "g1 wait_empty", "g1 land", "mma tot", "mma wait_afull", "mma wait_dempty",
-                 "epi red", "epi tot", "epi wait_dfull", "epi text", "pool tot", "pool wait_pfull", "pool loop"]
-        print("mode %d: %.1f us L2-warm, %.1f us after L2 flush (%.0f GB/s feature bytes)" % (mode, us_w, us_c, nv * 1536 / us_c / 1e3), flush=True)
-        print("   " + " | ".join("%s mean %.0f max %.0f" % (n_, d[:, i].mean().item(), d[:, i].max().item()) for i, n_ in enumerate(names)), flush=True)
-    lib.gridmm_debug_set_pool_mode(0)
+    us_w = graph_time(fn, n=1, reps=5, cold=False)
+    us_c = graph_time(fn, n=1, reps=5, cold=True)
+    dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    lib.gridmm_debug_set_pool_counters(dbg.data_ptr())
+    fn(); torch.cuda.synchronize()
+    lib.gridmm_debug_set_pool_counters(None)
+    d = dbg.float()
+    names = ["prod tot", "prod wait_empty", "prod text", "mma tot", "mma wait_afull", "mma wait_dempty", "red tot", "red wait_dfull",
+             "red text", "red max+softmax", "pool tot", "pool wait", "pool loop"]
+    print("pool: %.1f us L2-warm, %.1f us after L2 flush (%.0f GB/s feature bytes)" % (us_w, us_c, nv * 1536 / us_c / 1e3), flush=True)
+    print("   " + " | ".join("%s mean %.0f max %.0f" % (n_, d[:, i].mean().item(), d[:, i].max().item()) for i, n_ in enumerate(names)), flush=True)
