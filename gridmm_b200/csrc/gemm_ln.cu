@@ -1,0 +1,386 @@
+// tcgen05 GEMM with the residual add AND the LayerNorm fused into the epilogue, for the 768-wide projections that close
+// every attention / FFN sub-block of the cross-modal encoders:
+//     v = A[M,K] . W[768,K]^T + bias + residual        y = LayerNorm(v) * gamma + beta
+//   BertSelfOutput / BertOutput / BertOutAttention's output (map_nav_src/models/vilmodel.py:155-170, 196-209, 370-379):
+//     x <- LN(dense(h) + x)                       -> out_f32 = y, out_f16 = y
+//   TransformerEncoderLayer.forward_pre (map_nav_src/models/transformer.py:170-182):
+//     x <- x + out_proj(a); norm2(x) feeds linear1 -> out_f32 = v (raw residual stream), out_f16 = y
+// The un-fused sequence (GEMM epilogue: read residual, write fp32; LayerNorm kernel: read fp32, write fp32 + fp16) moves
+// 18 B per element through L2 and costs two launches; this kernel moves 10 B and one.
+//
+// A LayerNorm row needs all 768 output columns, which is more fp32 accumulator columns than one SM's tensor memory holds
+// (512).  A CLUSTER of CL CTAs therefore shares one 128-row tile: CTA r accumulates columns [r*768/CL, (r+1)*768/CL) in its
+// own TMEM (CL = 2: 384 columns, two N=192 MMAs per K step; CL = 6: 128 columns -- picked by problem size so that
+// small-M problems still spread over ~90 SMs).  In the epilogue every thread owns one row of its CTA's slice:
+//   pass 1  v = acc + bias + residual (the residual arrives coalesced through a per-warp shared-memory transpose), written
+//           back into TMEM; per-thread mean and M2 over its columns
+//   merge   (mean, M2) partials of the 2*CL column slices of a row are exchanged through DISTRIBUTED SHARED MEMORY
+//           (mapa + ld.shared::cluster) around one cluster barrier and merged with Chan's formula
+//   pass 2  v is read back from TMEM, normalised, and stored coalesced (fp32 and/or fp16)
+// Warp roles as in gemm_tc.cu: warp 0 TMA producer, warp 1 MMA issuer (both issue from a converged warp through
+// elect_one()), warps 2..9 epilogue.
+#include "common.cuh"
+#include "host_util.h"
+
+namespace gmm {
+
+constexpr int LN_N = 768;
+constexpr int LN_BM = 128;
+constexpr int LN_EPI_WARPS = 8;
+constexpr int LN_THREADS = 64 + LN_EPI_WARPS * 32;
+constexpr int LN_PD = 4;                 // residual chunks (16 columns) in flight per epilogue thread
+
+struct LnEpilogue {
+    const float* bias;       // [768] or null
+    const float* residual;   // [M, ld_res] fp32 or null
+    const float* gamma;      // [768]
+    const float* beta;       // [768]
+    float eps;
+    float* out_f32;          // [M, ld_f32] or null
+    __half* out_f16;         // [M, ld_f16] or null
+    int ld_res, ld_f32, ld_f16;
+    int f32_raw;             // 1: out_f32 receives v (pre-norm residual stream), 0: the normalised y
+};
+
+template <int CL>
+struct LnSmem {
+    static constexpr int BN = LN_N / CL;
+    static constexpr int STAGES = (CL == 2) ? 3 : 6;
+    static constexpr int A_BYTES = LN_BM * 128;                 // 128 rows x 64 fp16
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;     // full[STAGES], empty[STAGES], tmem_full, tmem slot
+    static constexpr int VEC_OFFSET = BAR_OFFSET + 256;         // bias, gamma, beta slices: 3 x BN floats
+    static constexpr int STAT_OFFSET = VEC_OFFSET + 3 * BN * 4; // [2 halves][128 rows] float2 (mean, M2): read by the peers
+    static constexpr int FIN_OFFSET = STAT_OFFSET + 2 * LN_BM * 8;   // [2 halves][128 rows] float2 (mean, rstd)
+    static constexpr int STG_OFFSET = FIN_OFFSET + 2 * LN_BM * 8;    // per epilogue warp: 32 rows x 20 floats
+    static constexpr int STG_WARP_BYTES = 32 * 20 * 4;
+    static constexpr int TOTAL = STG_OFFSET + LN_EPI_WARPS * STG_WARP_BYTES + 1024;
+    static constexpr int TMEM_COLS = (BN <= 128) ? 128 : (BN <= 256 ? 256 : 512);
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const float (&f)[16]) {
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = __float_as_uint(f[j]); b[j] = __float_as_uint(f[8 + j]); }
+    tmem_st_32x32b_x8(taddr, a);
+    tmem_st_32x32b_x8(taddr + 8, b);
+}
+__device__ __forceinline__ float2 ld_cluster_f2(uint32_t cluster_addr) {
+    float2 v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr));
+    return v;
+}
+
+template <int CL>
+__global__ void __launch_bounds__(LN_THREADS, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int K, LnEpilogue ep) {
+    using L = LnSmem<CL>;
+    constexpr int BN = L::BN, STAGES = L::STAGES;
+    constexpr int NMMA = (BN > 256) ? 2 : 1;          // UMMA N <= 256
+    constexpr int MMA_N = BN / NMMA;
+    constexpr int HALF = BN / 2, NCH = HALF / 16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(smem + L::VEC_OFFSET);
+    float* s_gamma = s_bias + BN;
+    float* s_beta = s_gamma + BN;
+    float2* s_stat = reinterpret_cast<float2*>(smem + L::STAT_OFFSET);
+    float2* s_fin = reinterpret_cast<float2*>(smem + L::FIN_OFFSET);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int m0 = (blockIdx.x / CL) * LN_BM;
+    const int n0 = static_cast<int>(rank) * BN;
+    const int num_kb = K / 64;
+
+    pdl_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    pdl_wait();
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer (converged warp, elected issue)
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+            if (elect_one()) {
+                uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+                uint8_t* b_dst = a_dst + L::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                tma_load_2d(a_dst, &tmA, kb * 64, m0, &full_bar[s]);
+#pragma unroll
+                for (int j = 0; j < NMMA; ++j)
+                    tma_load_2d(b_dst + j * MMA_N * 128, &tmW, kb * 64, n0 + j * MMA_N, &full_bar[s]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        constexpr uint32_t idesc = umma_idesc_f16(LN_BM, MMA_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem) + s * L::STAGE_BYTES;
+            if (elect_one()) {
+                const uint64_t da = umma_desc_sw128_kmajor(a_addr);
+#pragma unroll
+                for (int j = 0; j < NMMA; ++j) {
+                    const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES + j * MMA_N * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_ss(tmem_base + j * MMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue: TMEM lane quadrant = warp % 4, column half
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64;
+        for (int i = et; i < BN; i += LN_EPI_WARPS * 32) {
+            s_bias[i] = ep.bias ? __ldg(ep.bias + n0 + i) : 0.0f;
+            s_gamma[i] = __ldg(ep.gamma + n0 + i);
+            s_beta[i] = __ldg(ep.beta + n0 + i);
+        }
+        // coalesced global mapping: in pass i a lane owns row 8*i + lane/4 of the warp's 32 rows and 4 of a chunk's 16 columns
+        const int rsub = lane >> 2, csub = (lane & 3) * 4;
+        const int row_base = m0 + q * 32 + rsub;
+        const int colh = half * HALF;                 // first column of this thread's half inside the CTA slice
+        float4 res[LN_PD][4];
+        if (ep.residual) {
+#pragma unroll
+            for (int c = 0; c < LN_PD && c < NCH; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rg = row_base + 8 * i;
+                    res[c][i] = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rg < M ? rg : 0) * ep.ld_res +
+                                                                 n0 + colh + c * 16 + csub);
+                }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(LN_EPI_WARPS * 32) : "memory");      // bias / gamma / beta slices are staged
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + colh;
+        float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + (warp - 2) * L::STG_WARP_BYTES);
+        const int trow = q * 32 + lane;               // this thread's row of the tile (TMEM lane)
+
+        // ---- pass 1: v = acc + bias + residual -> back to TMEM; running sum
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_addr + c * 16, v);
+            if (ep.residual) {
+                // residual chunk: coalesced registers -> [row][col] staging tile -> this thread's row
+#pragma unroll
+                for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + (rsub + 8 * i) * 20 + csub) = res[c % LN_PD][i];
+                if (c + LN_PD < NCH) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rg = row_base + 8 * i;
+                        res[c % LN_PD][i] = *reinterpret_cast<const float4*>(ep.residual + static_cast<size_t>(rg < M ? rg : 0) * ep.ld_res +
+                                                                              n0 + colh + (c + LN_PD) * 16 + csub);
+                    }
+                }
+                __syncwarp();
+            }
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + colh + c * 16 + j);
+                f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
+            if (ep.residual) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * 20 + j);
+                    f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum += f[j];
+            tmem_st_32x32b_x16(t_addr + c * 16, f);
+        }
+        tmem_st_wait();
+        const float mean_i = sum * (1.0f / HALF);
+        // ---- pass 1b: M2 = sum (v - mean_i)^2 over this thread's columns
+        float m2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_addr + c * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float d = __uint_as_float(v[j]) - mean_i; m2 = fmaf(d, d, m2); }
+        }
+        s_stat[half * LN_BM + trow] = make_float2(mean_i, m2);
+    }
+
+    // ---- every column slice of the tile has published its partial statistics
+    cluster_sync_all();
+
+    if (warp >= 2) {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int trow = q * 32 + lane;
+        const int rsub = lane >> 2, csub = (lane & 3) * 4;
+        const int row_base = m0 + q * 32 + rsub;
+        const int colh = half * HALF;
+        // merge the 2*CL partials of this row (equal counts): mean = avg of means, M2 = sum M2_i + HALF * sum (mean_i - mean)^2
+        float2 part[2 * CL];
+        const uint32_t my_stat = smem_u32(s_stat + trow);
+#pragma unroll
+        for (int r = 0; r < CL; ++r) {
+            const uint32_t base = mapa_u32(my_stat, static_cast<uint32_t>(r));
+            part[2 * r] = ld_cluster_f2(base);
+            part[2 * r + 1] = ld_cluster_f2(base + LN_BM * 8);
+        }
+        float mean = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2 * CL; ++i) mean += part[i].x;
+        mean *= 1.0f / (2 * CL);
+        float m2 = 0.f, dev = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2 * CL; ++i) { m2 += part[i].y; const float d = part[i].x - mean; dev = fmaf(d, d, dev); }
+        const float var = (m2 + HALF * dev) * (1.0f / LN_N);
+        s_fin[half * LN_BM + trow] = make_float2(mean, rsqrtf(var + ep.eps));
+        __syncwarp();      // the 32 rows of this warp's quadrant are final (each half keeps its own copy)
+        float2 fin[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fin[i] = s_fin[half * LN_BM + q * 32 + rsub + 8 * i];
+
+        // ---- pass 2: v from TMEM -> staging tile -> coalesced normalise + store
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + colh;
+        float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + (warp - 2) * L::STG_WARP_BYTES);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_addr + c * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(stg + lane * 20 + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            __syncwarp();
+            const int cl = colh + c * 16 + csub;          // column inside the CTA slice
+            const float4 g4 = *reinterpret_cast<const float4*>(s_gamma + cl);
+            const float4 b4 = *reinterpret_cast<const float4*>(s_beta + cl);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 x = *reinterpret_cast<const float4*>(stg + (rsub + 8 * i) * 20 + csub);
+                const int rg = row_base + 8 * i;
+                float4 y;
+                y.x = (x.x - fin[i].x) * fin[i].y * g4.x + b4.x; y.y = (x.y - fin[i].x) * fin[i].y * g4.y + b4.y;
+                y.z = (x.z - fin[i].x) * fin[i].y * g4.z + b4.z; y.w = (x.w - fin[i].x) * fin[i].y * g4.w + b4.w;
+                if (rg < M) {
+                    const int col = n0 + cl;
+                    if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(rg) * ep.ld_f32 + col) = ep.f32_raw ? x : y;
+                    if (ep.out_f16) {
+                        const __half2 h01 = __floats2half2_rn(y.x, y.y), h23 = __floats2half2_rn(y.z, y.w);
+                        uint2 o;
+                        o.x = *reinterpret_cast<const uint32_t*>(&h01);
+                        o.y = *reinterpret_cast<const uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(ep.out_f16 + static_cast<size_t>(rg) * ep.ld_f16 + col) = o;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();      // no CTA may exit while a peer can still read its statistics
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, L::TMEM_COLS);
+    }
+}
+
+template <int CL>
+static int launch_gemm_ln(const void* a, int lda, const void* w, int ldw, int M, int K, const LnEpilogue& ep, cudaStream_t stream) {
+    using L = LnSmem<CL>;
+    constexpr int BOXN = (L::BN > 256) ? L::BN / 2 : L::BN;
+    CUtensorMap tmA, tmW;
+    int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2, 64, LN_BM);
+    if (rc) return rc;
+    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(LN_N), static_cast<uint64_t>(ldw) * 2, 64, BOXN);
+    if (rc) return rc;
+    auto kern = gemm_ln_kernel<CL>;
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const int tiles_m = (M + LN_BM - 1) / LN_BM;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles_m * CL);
+    cfg.blockDim = dim3(LN_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (gridmm_use_pdl()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, M, K, ep));
+}
+
+}  // namespace gmm
+
+static int g_ln_cluster = 0;
+// Debug hook: force the cluster size (2 or 6) of gridmm_linear_ln_f16; 0 = automatic.
+extern "C" void gridmm_debug_set_ln_cluster(int cl) { g_ln_cluster = cl; }
+
+extern "C" int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                                    const float* residual, int ld_res, const float* gamma, const float* beta, float eps,
+                                    float* out_f32, int ld_f32, void* out_f16, int ld_f16, int f32_raw, cudaStream_t stream) {
+    using namespace gmm;
+    if (M <= 0) return 0;
+    if (N != LN_N || K % 64 != 0 || K <= 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
+    if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
+    if (!a || !w || !gamma || !beta || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        GMM_CUDA_CHECK(cudaGetDevice(&dev));
+        GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    LnEpilogue ep{bias, residual, gamma, beta, eps, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, f32_raw};
+    // cluster size: waves x (per-CTA work ~ slice width + fixed epilogue/launch part)
+    const int tiles_m = (M + LN_BM - 1) / LN_BM;
+    const long long t2 = static_cast<long long>((tiles_m * 2 + sms - 1) / sms) * (384 + 128);
+    const long long t6 = static_cast<long long>((tiles_m * 6 + sms - 1) / sms) * (128 + 128);
+    int cl = (t2 <= t6) ? 2 : 6;
+    if (g_ln_cluster == 2 || g_ln_cluster == 6) cl = g_ln_cluster;
+    const int rc = (cl == 2) ? launch_gemm_ln<2>(a, lda, w, ldw, M, K, ep, stream) : launch_gemm_ln<6>(a, lda, w, ldw, M, K, ep, stream);
+    gridmm_count_launch(1);
+    return rc;
+}

@@ -330,8 +330,8 @@ class GlocalTextPathNavCMT(nn.Module):
         """BertIntermediate + BertOutput (vilmodel.py:184-209): x = LN(W2 gelu(W1 x) + x)."""
         h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16)
         ops.linear(x16, self.W16(pre_i + ".dense.weight"), self.B32(pre_i + ".dense.bias"), out_f16=h, act=ops.ACT_GELU)
-        ops.linear(h, self.W16(pre_o + ".dense.weight"), self.B32(pre_o + ".dense.bias"), residual=x32, out_f32=x32)
-        self._ln(x32, pre_o + ".LayerNorm", 1e-12, x32, x16)
+        ops.linear_ln(h, self.W16(pre_o + ".dense.weight"), self.B32(pre_o + ".dense.bias"), x32, self.P(pre_o + ".LayerNorm.weight"),
+                      self.P(pre_o + ".LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
 
     def _self_post(self, x32, x16, pre, kmask, B, S, tag):
         """BertAttention (vilmodel.py:172-182): x = LN(Wo attn(x) + x), additive -10000 mask."""
@@ -339,16 +339,16 @@ class GlocalTextPathNavCMT(nn.Module):
         ops.linear(x16, self.W16(pre + ".self.query.weight", pre + ".self.key.weight", pre + ".self.value.weight"),
                    self.B32(pre + ".self.query.bias", pre + ".self.key.bias", pre + ".self.value.bias"), out_f16=qkv)
         a = self._attention(qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:], kmask, NEG_BERT, B, S, S, "att16_" + tag)
-        ops.linear(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), residual=x32, out_f32=x32)
-        self._ln(x32, pre + ".output.LayerNorm", 1e-12, x32, x16)
+        ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
+                      self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
 
     def _cross_post(self, x32, x16, pre, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag):
         """BertXAttention (vilmodel.py:317-379): x = LN(Wo attn(q = x, kv = ctx) + x)."""
         q = self.buf("q16_" + tag, (B * S, HID), torch.float16)
         ops.linear(x16, self.W16(pre + ".att.query.weight"), self.B32(pre + ".att.query.bias"), out_f16=q)
         a = self._attention(q, ctx_k, ctx_v, ctx_mask, NEG_BERT, B, S, Sk, "att16_" + tag)
-        ops.linear(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), residual=x32, out_f32=x32)
-        self._ln(x32, pre + ".output.LayerNorm", 1e-12, x32, x16)
+        ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
+                      self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
 
     def _lxrt_layer(self, pre, x32, x16, x_mask, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag):
         """GraphLXRTXLayer.forward (vilmodel.py:399-414): cross-attention, self-attention, FFN (all post-norm)."""
@@ -359,19 +359,24 @@ class GlocalTextPathNavCMT(nn.Module):
     def _prenorm_encoder(self, pre, n_layers, x32, x16, kmask, B, S, tag):
         """TransformerEncoder of forward_pre layers + final norm (models/transformer.py:60-87, 170-182)."""
         rows = B * S
+        self._ln(x32, "%s.layers.0.norm1" % pre, 1e-5, None, x16)
         for i in range(n_layers):
             q = "%s.layers.%d" % (pre, i)
-            self._ln(x32, q + ".norm1", 1e-5, None, x16)
             qkv = self.buf("qkv16_" + tag, (rows, 3 * HID), torch.float16)
             ops.linear(x16, self.W16(q + ".self_attn.in_proj_weight"), self.B32(q + ".self_attn.in_proj_bias"), out_f16=qkv)
             a = self._attention(qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:], kmask, NEG_INF, B, S, S, "att16_" + tag)
-            ops.linear(a, self.W16(q + ".self_attn.out_proj.weight"), self.B32(q + ".self_attn.out_proj.bias"),
-                       residual=x32, out_f32=x32)
-            self._ln(x32, q + ".norm2", 1e-5, None, x16)
+            # x += out_proj(a); x16 = norm2(x)   (residual stream stays un-normalised: f32_raw)
+            ops.linear_ln(a, self.W16(q + ".self_attn.out_proj.weight"), self.B32(q + ".self_attn.out_proj.bias"), x32,
+                          self.P(q + ".norm2.weight"), self.P(q + ".norm2.bias"), 1e-5, out_f32=x32, out_f16=x16, f32_raw=True)
             h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16)
             ops.linear(x16, self.W16(q + ".linear1.weight"), self.B32(q + ".linear1.bias"), out_f16=h, act=ops.ACT_GELU)
-            ops.linear(h, self.W16(q + ".linear2.weight"), self.B32(q + ".linear2.bias"), residual=x32, out_f32=x32)
-        self._ln(x32, pre + ".norm", 1e-12, x32, x16)
+            if i + 1 < n_layers:      # x += linear2(h); x16 = norm1 of the next layer
+                nq = "%s.layers.%d" % (pre, i + 1)
+                ops.linear_ln(h, self.W16(q + ".linear2.weight"), self.B32(q + ".linear2.bias"), x32, self.P(nq + ".norm1.weight"),
+                              self.P(nq + ".norm1.bias"), 1e-5, out_f32=x32, out_f16=x16, f32_raw=True)
+            else:                     # x = norm(x + linear2(h))  (the encoder's final LayerNorm, eps 1e-12)
+                ops.linear_ln(h, self.W16(q + ".linear2.weight"), self.B32(q + ".linear2.bias"), x32, self.P(pre + ".norm.weight"),
+                              self.P(pre + ".norm.bias"), 1e-12, out_f32=x32, out_f16=x16)
 
     def _cls_head(self, pre, xs16, rows, tag):
         """ClsPrediction (vilmodel.py:663-674) -> raw logit per row.  `xs16` is the [hi | lo | hi] split of the fp32 input

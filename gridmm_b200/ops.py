@@ -35,6 +35,20 @@ def linear(a16, w16, bias=None, residual=None, out_f32=None, out_f16=None, act=A
               _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, act, _lib.stream_ptr())
 
 
+def linear_ln(a16, w16, bias, residual, gamma, beta, eps, out_f32=None, out_f16=None, f32_raw=False):
+    """LayerNorm(a16 @ w16.T + bias + residual) in one kernel; out_f32 gets the un-normalised sum when f32_raw (pre-norm blocks)."""
+    _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w"); _chk(bias, torch.float32, "bias")
+    _chk(residual, torch.float32, "residual"); _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
+    _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
+    M, K = a16.shape
+    N = w16.shape[0]
+    assert w16.shape[1] == K
+    _lib.call("gridmm_linear_ln_f16", a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, N, K, _lib.ptr(bias),
+              _lib.ptr(residual), residual.stride(0) if residual is not None else 0, gamma.data_ptr(), beta.data_ptr(), float(eps),
+              _lib.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, int(bool(f32_raw)), _lib.stream_ptr())
+
+
 def attention(q, k, v, out, kmask, mask_neg, batch, heads, sq, sk, q_rows=None, k_rows=None):
     """q [batch*q_rows, >=heads*64] fp16 views (column offset folded into the view), likewise k, v; out fp16."""
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):

@@ -95,6 +95,15 @@ int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int
                       const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16, int act,
                       cudaStream_t stream);
 
+/* nn.Linear(K -> 768) + residual + LayerNorm in one kernel (a cluster of 2 or 6 CTAs per 128-row tile, row statistics merged
+ * through distributed shared memory):  v = a . w^T + bias + residual;  y = LayerNorm(v; gamma, beta, eps).
+ * Replaces BertSelfOutput / BertOutput / BertOutAttention.output (vilmodel.py:155-170, 196-209, 370-379: out_f32 = out_f16 = y)
+ * and `x = x + out_proj(a); norm2(x)` of TransformerEncoderLayer.forward_pre (transformer.py:170-182: f32_raw = 1, out_f32 = v,
+ * out_f16 = y).  N must be 768, K % 64 == 0; out_f32 may alias residual. */
+int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                         const float* residual, int ld_res, const float* gamma, const float* beta, float eps, float* out_f32,
+                         int ld_f32, void* out_f16, int ld_f16, int f32_raw, cudaStream_t stream);
+
 /* text_proj (vilmodel.py:702, 793-795) written straight into gridmm_pool's lane-major operand layout:
  * out_lanes[b][u][t] (16-byte units, 128 slots per unit row) = (a[b*rows_per_b + t, :] . w^T + bias)[8u .. 8u+7];
  * M = batch*rows_per_b, rows_per_b <= 128. */
@@ -160,6 +169,7 @@ int gridmm_ce_logits(const float* raw_global, const float* raw_local, const floa
  * GEMM, [grid][16] for the pooling kernel: role totals and time spent waiting on each mbarrier).  NULL disables. */
 void gridmm_debug_set_gemm_counters(long long* dbg);
 void gridmm_debug_set_pool_counters(long long* dbg);
+void gridmm_debug_set_ln_cluster(int cl);     /* force the cluster size (2 / 6) of gridmm_linear_ln_f16; 0 = automatic */
 void gridmm_debug_set_gemm_pairs(int on);    /* 0: disable the cta_group::2 GEMM path (A/B timing) */
 
 #ifdef __cplusplus

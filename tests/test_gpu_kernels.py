@@ -75,6 +75,34 @@ def test_linear_lanes_layout(B, L):
     assert (got.float() - ref).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("M,K,cl,raw", [(6912, 768, 2, False), (6912, 3072, 2, False), (1824, 768, 6, False), (1824, 3072, 6, True),
+                                        (300, 768, 0, True), (2560, 768, 0, False), (6913, 768, 0, False), (57, 3072, 2, True)])
+def test_linear_ln_fused(M, K, cl, raw):
+    """GEMM + bias + residual + LayerNorm in one cluster kernel vs torch fp32 (in-place residual stream, as the model uses it)."""
+    import ctypes
+    from gridmm_b200 import ops, _lib
+    lib = _lib.load()
+    lib.gridmm_debug_set_ln_cluster.argtypes = [ctypes.c_int]
+    g = torch.Generator().manual_seed(M + K + cl)
+    a = torch.randn(M, K, generator=g).half().to(_dev())
+    w = (torch.randn(768, K, generator=g) * 0.03).half().to(_dev())
+    bias = torch.randn(768, generator=g).to(_dev())
+    res = (torch.randn(M, 768, generator=g) * 2 + 0.5).to(_dev())
+    gamma = (1 + 0.1 * torch.randn(768, generator=g)).to(_dev()); beta = (0.1 * torch.randn(768, generator=g)).to(_dev())
+    x32 = res.clone()
+    x16 = torch.empty(M, 768, device=_dev(), dtype=torch.float16)
+    lib.gridmm_debug_set_ln_cluster(cl)
+    try:
+        ops.linear_ln(a, w, bias, x32, gamma, beta, 1e-12, out_f32=x32, out_f16=x16, f32_raw=raw)
+    finally:
+        lib.gridmm_debug_set_ln_cluster(0)
+    v = a.float() @ w.float().t() + bias + res
+    y = torch.nn.functional.layer_norm(v, (768,), gamma, beta, 1e-12)
+    torch.cuda.synchronize()
+    assert (x32 - (v if raw else y)).abs().max().item() < (4e-3 if raw else 2e-3)
+    assert (x16.float() - y).abs().max().item() < 6e-3
+
+
 def test_linear_strided_views():
     """A operand / outputs addressed through row pitches (fused QKV buffers)."""
     from gridmm_b200 import ops

@@ -15,7 +15,7 @@ torch.cuda.set_device(0)
 lib = _lib.load()
 lib.gridmm_debug_set_gemm_counters.argtypes = [ctypes.c_void_p]
 lib.gridmm_debug_set_pool_counters.argtypes = [ctypes.c_void_p]
-want = set(sys.argv[1:]) or {"gemm", "attn", "ln", "pool"}
+want = set(sys.argv[1:]) or {"gemm", "gemmln", "attn", "ln", "pool"}
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
@@ -76,6 +76,17 @@ if "gemm" in want:
     tot += gemm_case(B * 37, 768, 2304, act=2, f32=True, tag="cls head V")
     tot += gemm_case(B, 768, 4608, act=2, f32=True, tag="cls fuse")
     print("GEMM sum over the step's 42 launches: %.1f us" % tot, flush=True)
+
+if "gemmln" in want:
+    def ln_case(M, K, tag):
+        a = torch.randn(M, K, device=dev).half(); w = (torch.randn(768, K, device=dev) * 0.02).half()
+        bias = torch.zeros(768, device=dev); g_ = torch.ones(768, device=dev); b_ = torch.zeros(768, device=dev)
+        x32 = torch.randn(M, 768, device=dev); x16 = torch.empty(M, 768, device=dev, dtype=torch.float16)
+        us = graph_time(lambda: ops.linear_ln(a, w, bias, x32, g_, b_, 1e-12, out_f32=x32, out_f16=x16))
+        print("GEMM+LN %-14s M=%5d K=%5d: %6.1f us  %6.1f TF" % (tag, M, K, us, 2.0 * M * 768 * K / us / 1e6), flush=True)
+        return us
+    tot = ln_case(B * 216, 768, "map out-proj") * 3 + ln_case(B * 216, 3072, "map ffn2") * 2 + ln_case(B * 57, 768, "x out-proj") * 8 + ln_case(B * 57, 3072, "x ffn2") * 4
+    print("GEMM+LN sum over the step's 17 launches: %.1f us" % tot, flush=True)
 
 if "attn" in want:
     def attn_case(Sq, Sk, tag):
