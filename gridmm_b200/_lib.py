@@ -30,6 +30,11 @@ _SIGS = {
                     c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_ln_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                              c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+    "gridmm_head_rows": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+    "gridmm_cls_heads_f16": [c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p],
+    "gridmm_nav_logits2": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 11 +
+                          [c_int, c_int, c_int, c_void_p],
     "gridmm_linear_f16_lanes": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                           c_void_p, c_int, c_int, c_void_p],

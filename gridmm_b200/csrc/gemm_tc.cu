@@ -34,6 +34,12 @@ struct GemmEpilogue {
     int act;                 // 0 none, 1 GELU(erf), 2 ReLU
     __half* out_lanes;       // optional lane-major fp16 output [M / lanes_rows, N / 8, 128] of 16-byte units (gridmm_pool's
     int lanes_rows;          // text operand layout): row = b * lanes_rows + t  ->  unit u of it at ((b * N/8 + u) * 128 + t)
+    // grouped ClsPrediction mode (gridmm_cls_heads_f16): per 128-row tile {first A row, first W / bias row, first output row};
+    // the epilogue keeps only three sums per row and 64-column slice (see cls_part) instead of storing the activations
+    const int* grp;          // [tiles_m][4] or null: first A row, first W row, first output row, mode (0: ReLU + sums, 1: raw fp32)
+    const float* gw2;        // [groups * N] gamma * w2 of every head (indexed like bias), cls mode only
+    float* cls_part;         // [rows][N / 64][3]: sum r, sum r^2, sum r * gw2 with r = act(acc + bias), or null
+    float* cls_raw;          // [rows][N] plain products of the mode-1 tiles (K-split halves of sap_fuse_linear), or null
     long long* dbg;          // optional [grid][8] cycle counters (tools/microbench.py), null in production
 };
 
@@ -46,7 +52,8 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;   // [2][BN] floats
-    static constexpr int STG_OFFSET = BIAS_OFFSET + 2 * BN * 4;     // per epilogue warp: 32 rows x 20 floats (16 + pad)
+    static constexpr int GW2_OFFSET = BIAS_OFFSET + 2 * BN * 4;    // [2][BN] floats (cls mode)
+    static constexpr int STG_OFFSET = GW2_OFFSET + 2 * BN * 4;      // per epilogue warp: 32 rows x 20 floats (16 + pad)
     static constexpr int STG_WARP_BYTES = 32 * 20 * 4;
     static constexpr int TOTAL = STG_OFFSET + GEMM_EPI_WARPS * STG_WARP_BYTES + 1024;
 };
@@ -134,8 +141,13 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const long long t_begin = DBG ? clock64() : 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 // pair mode: this CTA loads its own 128 rows of A and its half of the W tile
-                const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * GEMM_BM;
-                const int n0 = (tile % tiles_n) * BN + static_cast<int>(rank) * (BN / CG);
+                int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * GEMM_BM;
+                int n0 = (tile % tiles_n) * BN + static_cast<int>(rank) * (BN / CG);
+                if (ep.grp) {      // grouped heads: this row tile reads its own A rows and its head's weight rows
+                    const int* gt = ep.grp + (tile / tiles_n) * 4;
+                    m0 = __ldg(gt + 0);
+                    n0 += __ldg(gt + 1);
+                }
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -225,10 +237,23 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const long long t_begin = DBG ? clock64() : 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
             const int acc = t & 1;
-            const int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * GEMM_BM, n0 = (tile % tiles_n) * BN;
+            int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * GEMM_BM;
+            const int n0 = (tile % tiles_n) * BN;
+            int wrow0 = n0;                                // row of W / index of bias for column n0 of this tile
+            bool raw_tile = false;
+            if (ep.grp) {
+                const int* gt = ep.grp + (tile / tiles_n) * 4;
+                wrow0 += __ldg(gt + 1);
+                m0 = __ldg(gt + 2);                        // output rows of this tile
+                raw_tile = __ldg(gt + 3) != 0;
+            }
             // stage this tile's bias slice (the slot of tile t-2 is free: all warps passed the barrier of tile t-1)
             float* sb = s_bias + acc * BN;
-            for (int i = et; i < BN; i += GEMM_EPI_WARPS * 32) sb[i] = ep.bias ? __ldg(ep.bias + n0 + i) : 0.0f;
+            float* sg = reinterpret_cast<float*>(smem + L::GW2_OFFSET) + acc * BN;
+            for (int i = et; i < BN; i += GEMM_EPI_WARPS * 32) {
+                sb[i] = ep.bias ? __ldg(ep.bias + wrow0 + i) : 0.0f;
+                if (ep.cls_part) sg[i] = __ldg(ep.gw2 + wrow0 + i);
+            }
             // Global accesses use a coalesced mapping: in pass i a lane owns row 8*i + lane/4 of the warp's 32 rows and 4
             // of the chunk's 16 columns, so one warp instruction covers 8 rows x 64 contiguous bytes (the TMEM layout --
             // one row per lane -- would touch 32 different lines per instruction).  Accumulator chunks cross over through
@@ -254,6 +279,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * HALF;
             float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + (warp - 2) * L::STG_WARP_BYTES);
+            float cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;          // cls mode: this row's sums over the warp's column half
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 uint32_t v[16];
@@ -266,12 +292,32 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
                     f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
                 }
+                if (raw_tile) {
+                    // plain product rows (no activation): 64 contiguous bytes per lane, a handful of rows per launch
+                    const int rg = m0 + q * 32 + lane;
+                    float4* dst = reinterpret_cast<float4*>(ep.cls_raw + static_cast<size_t>(rg) * N + col0 + c * 16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    continue;
+                }
                 if (ep.act == 1) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
                 } else if (ep.act == 2) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+                }
+                if (ep.cls_part) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(sg + half * HALF + c * 16 + j);
+                        cs1 += (f[j] + f[j + 1]) + (f[j + 2] + f[j + 3]);
+                        cs2 = fmaf(f[j], f[j], cs2); cs2 = fmaf(f[j + 1], f[j + 1], cs2);
+                        cs2 = fmaf(f[j + 2], f[j + 2], cs2); cs2 = fmaf(f[j + 3], f[j + 3], cs2);
+                        cs3 = fmaf(f[j], g4.x, cs3); cs3 = fmaf(f[j + 1], g4.y, cs3);
+                        cs3 = fmaf(f[j + 2], g4.z, cs3); cs3 = fmaf(f[j + 3], g4.w, cs3);
+                    }
+                    continue;
                 }
                 if (ep.out_lanes) {
                     // the TMEM layout (one row per lane) IS the coalesced mapping for the lane-major layout: consecutive
@@ -318,6 +364,13 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 __syncwarp();
             }
+            if (ep.cls_part && !raw_tile) {
+                const int rg = m0 + q * 32 + lane;
+                if (rg < M) {
+                    float* dst = ep.cls_part + (static_cast<size_t>(rg) * (N / 64) + (n0 + half * HALF) / 64) * 3;
+                    dst[0] = cs1; dst[1] = cs2; dst[2] = cs3;
+                }
+            }
             // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -340,13 +393,13 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
 template <int BN, int STAGES, int BK, bool DBG, int CG>
 static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const GemmEpilogue& ep, int sms,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, long long a_rows = 0, long long w_rows = 0) {
     CUtensorMap tmA, tmW;
-    int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2,
-                              GEMM_KATOM, GEMM_BM);
+    int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(a_rows > 0 ? a_rows : M),
+                              static_cast<uint64_t>(lda) * 2, GEMM_KATOM, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(ldw) * 2,
-                          GEMM_KATOM, BN / CG);
+    rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(w_rows > 0 ? w_rows : N),
+                          static_cast<uint64_t>(ldw) * 2, GEMM_KATOM, BN / CG);
     if (rc) return rc;
     auto kern = gemm_f16_tn_kernel<BN, STAGES, BK, DBG, CG>;
     constexpr int smem = GemmSmem<BN, STAGES, BK, CG>::TOTAL;
@@ -387,12 +440,14 @@ extern "C" void gridmm_debug_set_gemm_counters(long long* dbg) { g_gemm_dbg = db
 
 static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                          const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
-                         int act, void* out_lanes, int lanes_rows, cudaStream_t stream) {
+                         int act, void* out_lanes, int lanes_rows, cudaStream_t stream, const int* grp = nullptr,
+                         const float* gw2 = nullptr, float* cls_part = nullptr, long long a_rows = 0, long long w_rows = 0,
+                         float* cls_raw = nullptr) {
     using namespace gmm;
     if (M <= 0) return 0;
     if (N % 128 != 0 || K % GEMM_KATOM != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
     if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
-    if (!a || !w || (!out_f32 && !out_f16 && !out_lanes)) return GRIDMM_ERR_ARG;
+    if (!a || !w || (!out_f32 && !out_f16 && !out_lanes && !cls_part)) return GRIDMM_ERR_ARG;
     static int sms = 0;
     if (sms == 0) {
         int dev = 0;
@@ -400,7 +455,14 @@ static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, 
         GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act,
-                    reinterpret_cast<__half*>(out_lanes), lanes_rows, g_gemm_dbg};
+                    reinterpret_cast<__half*>(out_lanes), lanes_rows, grp, gw2, cls_part, cls_raw, g_gemm_dbg};
+    if (grp) {
+        // grouped heads: 128 x 128 tiles, one CTA each (row tiles address A / W / outputs through the table; the tensor maps
+        // span all A rows and all stacked weight rows)
+        if (K % 128 != 0 || (N % 128 != 0)) return GRIDMM_ERR_SHAPE;
+        gridmm_count_launch(1);
+        return launch_gemm<128, 3, 128, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream, a_rows, w_rows);
+    }
     // tile width: a 128x256 tile does twice the work of a 128x128 one in ~1.45x the time (shared-memory bandwidth: both
     // re-read their operands for every MMA, the wide tile reads 96 B/clk + fills 96 B/clk against 128 + 128 for the narrow
     // one), the narrow tile quantises better over the SMs; pick the cheaper schedule
@@ -442,4 +504,22 @@ extern "C" int gridmm_linear_f16_lanes(const void* a, int lda, const void* w, in
                                        void* out_lanes, int rows_per_b, cudaStream_t stream) {
     if (!out_lanes || rows_per_b < 1 || rows_per_b > 128 || (M % rows_per_b)) return GRIDMM_ERR_SHAPE;
     return gemm_dispatch(a, lda, w, ldw, M, N, K, bias, nullptr, 0, nullptr, 0, nullptr, 0, 0, out_lanes, rows_per_b, stream);
+}
+
+// All ClsPrediction heads of a navigation step in ONE grouped launch (vilmodel.py:663-674, 859-878, 903-907):
+//   r = ReLU(x . W_h^T + b_h) for every row of every head h, reduced on the fly to the three sums the head's tail needs
+//   (LayerNorm + Linear(768 -> 1) = rstd * (sum r*gamma*w2 - mean * sum gamma*w2) + const): cls_part[row][N/64][3].
+//   a         fp16 [a_rows, K] (K = 3 x 768: the [hi | lo | hi] split of the fp32 inputs, see gridmm_split_rows)
+//   w         fp16 [groups * N, K] stacked [Wh | Wh | Wl] weights; bias, gw2 fp32 [groups * N]
+//   grp       device int [tiles_m][4]: first A row, first W row (group * N), first output row of every 128-row tile, mode
+//   cls_part  fp32 [out_rows, N / 64, 3]
+//   cls_raw   fp32 [out_rows, N]: mode-1 tiles store x . W^T itself (bias-free, no activation) -- the two K halves of
+//             sap_fuse_linear's first layer ([gmap'_0 ; vp_0] . [Wg | Wv]^T), which gridmm_nav_logits2 adds and finishes
+extern "C" int gridmm_cls_heads_f16(const void* a, int lda, long long a_rows, const void* w, int ldw, int groups, int tiles_m,
+                                    int N, int K, const float* bias, const float* gw2, const int* grp, float* cls_part,
+                                    float* cls_raw, cudaStream_t stream) {
+    if (tiles_m <= 0) return 0;
+    if (!grp || !gw2 || !cls_part || !cls_raw || groups < 1) return GRIDMM_ERR_ARG;
+    return gemm_dispatch(a, lda, w, ldw, tiles_m * 128, N, K, bias, nullptr, 0, nullptr, 0, nullptr, 0, 2, nullptr, 0, stream, grp, gw2,
+                         cls_part, a_rows, static_cast<long long>(groups) * N, cls_raw);
 }

@@ -308,6 +308,79 @@ class GlocalTextPathNavCMT(nn.Module):
             self._w16[key] = b
         return b
 
+    def head_pack(self, has_obj):
+        """Stacked operands of the grouped ClsPrediction launch: [Wh | Wh | Wl] weights, biases, gamma*w2 of the global, local,
+        grid (and object) heads, and the (c1, c0) constants of all five heads incl. sap_fuse_linear."""
+        key = ("heads", bool(has_obj))
+        pk = self._w16.get(key)
+        if pk is None:
+            with torch.no_grad():
+                names = ["global_sap_head", "local_sap_head", "grid_sap_head"] + (["og_head"] if has_obj else [])
+                ws = [self.W16split(n + ".net.0.weight") for n in names]
+                bs = [self.P(n + ".net.0.bias").detach().float() for n in names]
+                gs = [(self.P(n + ".net.2.weight") * self.P(n + ".net.3.weight")[0]).detach().float() for n in names]
+                if self.config.glocal_fuse:
+                    # sap_fuse_linear.net[0] = [Wg | Wv] over [gmap'_0 ; vp_0]: two K = 768 halves, each as one more (bias-free,
+                    # raw-product) group of the same launch
+                    wf = self.P("sap_fuse_linear.net.0.weight").detach().float()
+                    for part_w in (wf[:, :HID], wf[:, HID:]):
+                        hi = part_w.to(torch.float16)
+                        lo = (part_w - hi.float()).to(torch.float16)
+                        ws.append(torch.cat([hi, hi, lo], 1))
+                        bs.append(torch.zeros(HID, device=wf.device))
+                        gs.append(torch.zeros(HID, device=wf.device))
+                w = torch.cat(ws, 0).contiguous()
+                bias = torch.cat(bs, 0).contiguous()
+                gw2 = torch.cat(gs, 0)
+                consts = torch.zeros(5, 2, dtype=torch.float32, device=w.device)
+                order = ["global_sap_head", "local_sap_head", "grid_sap_head", "og_head", "sap_fuse_linear"]
+                for i, n in enumerate(order):
+                    if (n + ".net.0.weight") not in self._spec:
+                        continue
+                    g_, b_ = self.P(n + ".net.2.weight").detach().double(), self.P(n + ".net.2.bias").detach().double()
+                    w2, b2 = self.P(n + ".net.3.weight").detach().double()[0], self.P(n + ".net.3.bias").detach().double()[0]
+                    consts[i, 0] = float((g_ * w2).sum())
+                    consts[i, 1] = float((b_ * w2).sum() + b2)
+                fuse_gw2 = None
+                if self.config.glocal_fuse:
+                    fuse_gw2 = (self.P("sap_fuse_linear.net.2.weight") * self.P("sap_fuse_linear.net.3.weight")[0]).detach().float().contiguous()
+                pk = (w, bias, gw2.contiguous(), consts, fuse_gw2, len(ws), len(names))
+            self._w16[key] = pk
+        return pk
+
+    def head_table(self, B, G, V, has_obj, dev):
+        """Row layout of the grouped head launch: per 128-row tile (first A row, first W row, first output row, mode)."""
+        key = ("head_table", B, G, V, bool(has_obj), bool(self.config.glocal_fuse), str(dev))
+        tb = self._ws.get(key)
+        if tb is None:
+            pad = lambda r: (r + 127) // 128 * 128      # noqa: E731
+            rg, rl = B * G, B * V
+            a0 = {"global": 0, "local": pad(rg), "grid": pad(rg) + pad(rl)}
+            a_rows = 2 * pad(rg) + pad(rl)
+            n_names = 4 if has_obj else 3
+            if self.config.glocal_fuse:
+                a0["fuse_g"], a0["fuse_v"] = a_rows, a_rows + pad(B)
+                a_rows += 2 * pad(B)
+            rows = []
+            for gi, (name, n) in enumerate((("global", rg), ("local", rl), ("grid", rg))):
+                for i in range(pad(n) // 128):
+                    rows.append((a0[name] + 128 * i, gi * HID, a0[name] + 128 * i, 0))
+            if self.config.glocal_fuse:
+                for j, name in enumerate(("fuse_g", "fuse_v")):
+                    for i in range(pad(B) // 128):
+                        rows.append((a0[name] + 128 * i, (n_names + j) * HID, a0[name] + 128 * i, 1))
+            o_obj = -1
+            out_rows = a_rows
+            if has_obj:
+                o_obj = a_rows
+                for i in range(pad(rl) // 128):
+                    rows.append((a0["local"] + 128 * i, 3 * HID, o_obj + 128 * i, 0))
+                out_rows += pad(rl)
+            grp = torch.tensor(rows, dtype=torch.int32).to(dev)
+            tb = (grp, len(rows), a0, a_rows, o_obj, out_rows)
+            self._ws[key] = tb
+        return tb
+
     def buf(self, name, shape, dtype, zero=False):
         key = (name, tuple(shape), dtype)
         t = self._ws.get(key)
@@ -582,15 +655,13 @@ class GlocalTextPathNavCMT(nn.Module):
                              kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], kv_mask, B, Q, KC, "x")
 
         # ---- heads and logit fusion (vilmodel.py:859-907)
-        hg16 = self.buf("hg16", (B * G, 3 * HID), f16)
-        hv16 = self.buf("hv16", (B * V, 3 * HID), f16)
-        hm16 = self.buf("hm16", (B * G, 3 * HID), f16)
-        ops.split_rows(x32, Q, 0, G, B, hg16, HID)
-        ops.split_rows(x32, Q, G, V, B, hv16, HID)
-        ops.split_rows(map32, S, NC, G, B, hm16, HID)
-        raw_global = self._cls_head("global_sap_head", hg16, B * G, "g")
-        raw_local = self._cls_head("local_sap_head", hv16, B * V, "l")
         if ce_maxc:
+            hg16 = self.buf("hg16", (B * G, 3 * HID), f16)
+            hv16 = self.buf("hv16", (B * V, 3 * HID), f16)
+            ops.split_rows(x32, Q, 0, G, B, hg16, HID)
+            ops.split_rows(x32, Q, G, V, B, hv16, HID)
+            raw_global = self._cls_head("global_sap_head", hg16, B * G, "g")
+            raw_local = self._cls_head("local_sap_head", hv16, B * V, "l")
             # continuous-env head (VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:786-800)
             hf16 = self.buf("hf16", (B, 6 * HID), f16)
             ops.split_rows(x32, Q, 0, 1, B, hf16, 2 * HID)
@@ -599,22 +670,27 @@ class GlocalTextPathNavCMT(nn.Module):
             fused = self._out("ce_fused", (B, ce_maxc), static_out)
             ops.ce_logits(raw_global, raw_local, raw_fuse, st["vp_nav"], fused, B, G, V, ce_maxc)
             return fused
-        raw_grid = self._cls_head("grid_sap_head", hm16, B * G, "m")
-        raw_fuse = None
+        # ---- discrete-env heads: one operand build, one grouped GEMM, the fuse head, one finishing kernel
+        w_h, b_h, gw2_h, consts, fuse_gw2, n_groups, _ = self.head_pack(has_obj)
+        grp, tiles_m, a0, a_rows, o_obj, out_rows = self.head_table(B, G, V, has_obj, x32.device)
+        hA = self.buf("heads_a16", (a_rows, 3 * HID), f16, zero=True)
+        part = self.buf("heads_part", (out_rows, 36), f32)
+        raw = self.buf("heads_raw", (out_rows, HID), f32)
+        segs = [(x32, Q, 0, G, a0["global"]), (x32, Q, G, V, a0["local"]), (map32, S, NC, G, a0["grid"])]
         if cfg.glocal_fuse:
-            hf16 = self.buf("hf16", (B, 6 * HID), f16)             # [gmap0; vp0] -> K = 1536, split -> 3 * 1536
-            ops.split_rows(x32, Q, 0, 1, B, hf16, 2 * HID)
-            ops.split_rows(x32, Q, G, 1, B, hf16[:, HID:], 2 * HID)
-            raw_fuse = self._cls_head("sap_fuse_linear", hf16, B, "f")
-        raw_obj = self._cls_head("og_head", hv16, B * V, "o") if has_obj else None
+            segs += [(x32, Q, 0, 1, a0["fuse_g"]), (x32, Q, G, 1, a0["fuse_v"])]
+        ops.head_rows(segs, B, hA)
+        ops.cls_heads(hA, w_h, n_groups, tiles_m, b_h, gw2_h, grp, part, raw)
         global_logits = self._out("global_logits", (B, G), static_out)
         grid_logits = self._out("grid_logits", (B, G), static_out)
         local_logits = self._out("local_logits", (B, V), static_out)
         fused_logits = self._out("fused_logits", (B, G), static_out)
         obj_logits = self._out("obj_logits", (B, V), static_out) if has_obj else None
-        ops.nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_mask_u8, st["gmap_visited"], st["vp_nav"],
-                       st["vp_obj"], st["fuse_src"], st["bw_mask"], global_logits, grid_logits, local_logits, fused_logits,
-                       obj_logits, B, G, V)
+        fuse = cfg.glocal_fuse
+        ops.nav_logits2(part, raw if fuse else None, self.P("sap_fuse_linear.net.0.bias") if fuse else None, fuse_gw2,
+                        a0.get("fuse_g", 0), a0.get("fuse_v", 0), consts, a0["global"], a0["local"], a0["grid"], o_obj,
+                        gmap_mask_u8, st["gmap_visited"], st["vp_nav"], st["vp_obj"], st["fuse_src"], st["bw_mask"], global_logits,
+                        grid_logits, local_logits, fused_logits, obj_logits, B, G, V)
         x3 = x32.view(B, Q, HID)
         outs = {
             "gmap_embeds": x3[:, :G], "vp_embeds": x3[:, G:],

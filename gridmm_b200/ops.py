@@ -130,6 +130,43 @@ def nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_masks, g
               _lib.stream_ptr())
 
 
+def head_rows(segs, batch, out_f16):
+    """segs: list of (x fp32 [*, 768], in_rows_per_b, in_off, rows_per_b, out_row0) -> [hi | lo | hi] rows of out_f16 [*, 2304]."""
+    import ctypes
+    n = len(segs)
+    _chk(out_f16, torch.float16, "out_f16")
+    for sgm in segs:
+        _chk(sgm[0], torch.float32, "x")
+    xs = (ctypes.c_void_p * n)(*[sgm[0].data_ptr() for sgm in segs])
+    mk = lambda vals: (ctypes.c_int * n)(*[int(v) for v in vals])      # noqa: E731
+    ldx, irb, ioff, rpb, or0 = (mk([sgm[0].stride(0) for sgm in segs]), mk([sgm[1] for sgm in segs]), mk([sgm[2] for sgm in segs]),
+                                mk([sgm[3] for sgm in segs]), mk([sgm[4] for sgm in segs]))
+    cast = lambda a: ctypes.cast(a, ctypes.c_void_p)                   # noqa: E731
+    _lib.call("gridmm_head_rows", n, cast(xs), cast(ldx), cast(irb), cast(ioff), cast(rpb), cast(or0), batch, out_f16.data_ptr(),
+              out_f16.stride(0), HID, _lib.stream_ptr())
+
+
+def cls_heads(a16, w16, groups, tiles_m, bias, gw2, grp, part, raw):
+    _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w"); _chk(bias, torch.float32, "bias"); _chk(gw2, torch.float32, "gw2")
+    _chk(grp, torch.int32, "grp"); _chk(part, torch.float32, "part"); _chk(raw, torch.float32, "raw")
+    _lib.call("gridmm_cls_heads_f16", a16.data_ptr(), a16.stride(0), a16.shape[0], w16.data_ptr(), w16.stride(0), groups, tiles_m,
+              HID, a16.shape[1], bias.data_ptr(), gw2.data_ptr(), grp.data_ptr(), part.data_ptr(), raw.data_ptr(), _lib.stream_ptr())
+
+
+def nav_logits2(part, fuse_raw, fuse_bias, fuse_gw2, row_fuse_g, row_fuse_v, consts, row_global, row_local, row_grid, row_obj,
+                gmap_masks, gmap_visited, vp_nav_masks, vp_obj_masks, fuse_src, bw_mask, global_logits, grid_logits, local_logits,
+                fused_logits, obj_logits, batch, G, V):
+    for t, n in ((gmap_masks, "gmap_masks"), (gmap_visited, "gmap_visited"), (vp_nav_masks, "vp_nav_masks"),
+                 (vp_obj_masks, "vp_obj_masks"), (bw_mask, "bw_mask")):
+        _chk(t, torch.uint8, n)
+    _chk(fuse_src, torch.int32, "fuse_src"); _chk(part, torch.float32, "part"); _chk(consts, torch.float32, "consts")
+    _lib.call("gridmm_nav_logits2", part.data_ptr(), _lib.ptr(fuse_raw), _lib.ptr(fuse_bias), _lib.ptr(fuse_gw2), row_fuse_g, row_fuse_v,
+              consts.data_ptr(), row_global, row_local, row_grid, row_obj,
+              gmap_masks.data_ptr(), gmap_visited.data_ptr(), vp_nav_masks.data_ptr(), _lib.ptr(vp_obj_masks), fuse_src.data_ptr(),
+              bw_mask.data_ptr(), global_logits.data_ptr(), grid_logits.data_ptr(), local_logits.data_ptr(),
+              fused_logits.data_ptr(), _lib.ptr(obj_logits), batch, G, V, _lib.stream_ptr())
+
+
 def ce_logits(raw_global, raw_local, raw_fuse, vp_nav_masks, fused, batch, G, V, maxc):
     _chk(vp_nav_masks, torch.uint8, "vp_nav_masks"); _chk(fused, torch.float32, "fused")
     _lib.call("gridmm_ce_logits", raw_global.data_ptr(), raw_local.data_ptr(), raw_fuse.data_ptr(), vp_nav_masks.data_ptr(),

@@ -104,6 +104,30 @@ int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, 
                          const float* residual, int ld_res, const float* gamma, const float* beta, float eps, float* out_f32,
                          int ld_f32, void* out_f16, int ld_f16, int f32_raw, cudaStream_t stream);
 
+/* ---- action heads (vilmodel.py:663-674, 859-907) in three launches ------------------------------------------
+ * ClsPrediction = Linear, ReLU, LayerNorm(1e-12), Linear(768 -> 1):  logit = rstd * (S3 - mean * c1) + c0 with r = ReLU(xW + b),
+ * S1 = sum r, S2 = sum r^2, S3 = sum r * gamma * w2, c1 = sum gamma * w2, c0 = sum beta * w2 + b2.
+ * gridmm_head_rows: up to 6 row segments of fp32 matrices (host arrays of device pointers / ints) -> one [hi | lo | hi] fp16
+ *   operand matrix (row = out_row0[i] + b * rows_per_b[i] + r  <-  x[i][b * in_rows_per_b[i] + in_off[i] + r]).
+ * gridmm_cls_heads_f16: grouped tcgen05 GEMM over `tiles_m` 128-row tiles; grp (device) = per tile {first A row, first W row,
+ *   first output row, mode}; w = stacked [groups * N, K] split weights; mode 0: cls_part[out_row][N / 64][3] = (S1, S2, S3) per
+ *   64 columns; mode 1: cls_raw[out_row][N] = x . W^T (the two K halves of sap_fuse_linear's first layer, vilmodel.py:859-862).
+ * gridmm_nav_logits2: finishes every head from its sums (consts [5][2] = (c1, c0) of global, local, grid, obj, fuse; the fuse
+ *   head from fuse_raw rows row_fuse_g + b, row_fuse_v + b) and fuses the logits exactly like gridmm_nav_logits;
+ *   row_obj < 0 / fuse_raw NULL disable the object head / dynamic fusion. */
+int gridmm_head_rows(int nseg, const float* const* x, const int* ldx, const int* in_rows_per_b, const int* in_off,
+                     const int* rows_per_b, const int* out_row0, int batch, void* out_f16, int ld_f16, int hidden,
+                     cudaStream_t stream);
+int gridmm_cls_heads_f16(const void* a, int lda, long long a_rows, const void* w, int ldw, int groups, int tiles_m, int N, int K,
+                         const float* bias, const float* gw2, const int* grp, float* cls_part, float* cls_raw,
+                         cudaStream_t stream);
+int gridmm_nav_logits2(const float* part, const float* fuse_raw, const float* fuse_bias, const float* fuse_gw2, int row_fuse_g,
+                       int row_fuse_v, const float* consts, int row_global, int row_local, int row_grid, int row_obj,
+                       const unsigned char* gmap_masks, const unsigned char* gmap_visited, const unsigned char* vp_nav_masks,
+                       const unsigned char* vp_obj_masks, const int* fuse_src, const unsigned char* bw_mask, float* global_logits,
+                       float* grid_logits, float* local_logits, float* fused_logits, float* obj_logits, int batch, int G, int V,
+                       cudaStream_t stream);
+
 /* text_proj (vilmodel.py:702, 793-795) written straight into gridmm_pool's lane-major operand layout:
  * out_lanes[b][u][t] (16-byte units, 128 slots per unit row) = (a[b*rows_per_b + t, :] . w^T + bias)[8u .. 8u+7];
  * M = batch*rows_per_b, rows_per_b <= 128. */
