@@ -83,6 +83,47 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const float* x, int ldx,
     store_row(v, o32 ? o32 + orow * ld32 : nullptr, o16 ? o16 + orow * ld16 : nullptr, lane);
 }
 
+// ------------------------------------------------------------------------------------------- fusion-encoder inputs
+// vilmodel.py:843-850 in one launch: queries x = [gmap' ; vp] get their gmap' rows from the map sequence (fp32 + fp16), the
+// context kv = [map ; txt] is assembled as fp16, and both masks are concatenated.  One warp per row of (kv rows, then gmap' rows).
+struct FusionInParams {
+    const float* map32; const float* txt32;     // [B, S, 768], [B, L, 768]
+    const uint8_t* map_mask; const uint8_t* txt_mask; const uint8_t* gmap_mask; const uint8_t* vp_mask;   // [B,S] [B,L] [B,G] [B,V]
+    float* x32; __half* x16; __half* kv16;      // [B, Q, 768] x2, [B, KC, 768]
+    uint8_t* kv_mask; uint8_t* q_mask;          // [B, KC], [B, Q]
+    int B, S, L, G, V;
+};
+
+__global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int KC = p.S + p.L, Q = p.G + p.V;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= p.B * (KC + p.G)) return;
+    float4 v[HV];
+    if (row < p.B * KC) {
+        const int b = row / KC, r = row - b * KC;
+        const float* src = (r < p.S) ? p.map32 + (static_cast<size_t>(b) * p.S + r) * HID
+                                     : p.txt32 + (static_cast<size_t>(b) * p.L + (r - p.S)) * HID;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+        store_row(v, nullptr, p.kv16 + static_cast<size_t>(row) * HID, lane);
+        if (lane == 0) {
+            p.kv_mask[row] = (r < p.S) ? p.map_mask[b * p.S + r] : p.txt_mask[b * p.L + (r - p.S)];
+            for (int j = r; j < p.V; j += KC) p.q_mask[b * Q + p.G + j] = p.vp_mask[b * p.V + j];
+        }
+    } else {
+        const int rr = row - p.B * KC;
+        const int b = rr / p.G, g = rr - b * p.G;
+        const float* src = p.map32 + (static_cast<size_t>(b) * p.S + (p.S - p.G) + g) * HID;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+        const size_t orow = static_cast<size_t>(b) * Q + g;
+        store_row(v, p.x32 + orow * HID, p.x16 + orow * HID, lane);
+        if (lane == 0) p.q_mask[b * Q + g] = p.gmap_mask[b * p.G + g];
+    }
+}
+
 // ------------------------------------------------------------------------------------------- fp32 -> (hi, lo) fp16 split
 // out[b, r] = [ hi | lo | hi ] at column blocks 0, k_total, 2*k_total (each 768 wide at the given column offset), where
 // hi = fp16(x), lo = fp16(x - hi).  Against weights laid out [Wh | Wh | Wl] a single K-concatenated GEMM then computes
@@ -138,9 +179,15 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
     for (int i = 0; i < HV; ++i) {
         const int col = (i * 32 + lane) * 4;
         float4 a = *reinterpret_cast<const float4*>(p.bias + col);
-        for (int k = 0; k < p.kin; ++k) {      // transposed weight [kin, 768]: coalesced float4 per lane
-            const float4 w4 = *reinterpret_cast<const float4*>(p.w + static_cast<size_t>(k) * HID + col);
-            a.x = fmaf(f[k], w4.x, a.x); a.y = fmaf(f[k], w4.y, a.y); a.z = fmaf(f[k], w4.z, a.z); a.w = fmaf(f[k], w4.w, a.w);
+        // transposed weight [kin, 768]: coalesced float4 per lane; fully unrolled with predicated loads so that all kin x 6 loads of
+        // a row are in flight together (a runtime trip count serialised them: 36 us for 1184 rows)
+        float4 w4[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            w4[k] = (k < p.kin) ? __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(k) * HID + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {         // f[k] = 0 beyond kin
+            a.x = fmaf(f[k], w4[k].x, a.x); a.y = fmaf(f[k], w4[k].y, a.y); a.z = fmaf(f[k], w4[k].z, a.z); a.w = fmaf(f[k], w4[k].w, a.w);
         }
         v[i] = a;
     }
@@ -401,6 +448,23 @@ extern "C" int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int 
     GMM_CUDA_CHECK(launch_pdl(copy_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, x, ldx, in_rows_per_b, in_off, out_f32, ld_f32,
                                                          reinterpret_cast<__half*>(out_f16), ld_f16, out_rows_per_b, out_off,
                                                          rows_per_b, rows));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+extern "C" int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned char* map_mask,
+                                    const unsigned char* txt_mask, const unsigned char* gmap_mask, const unsigned char* vp_mask,
+                                    float* x32, void* x16, void* kv16, unsigned char* kv_mask, unsigned char* q_mask, int batch,
+                                    int S, int L, int G, int V, int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (hidden != HID || S < G || L < 1 || G < 1 || V < 1) return GRIDMM_ERR_SHAPE;
+    if (!map32 || !txt32 || !map_mask || !txt_mask || !gmap_mask || !vp_mask || !x32 || !x16 || !kv16 || !kv_mask || !q_mask)
+        return GRIDMM_ERR_ARG;
+    FusionInParams p{map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, reinterpret_cast<__half*>(x16),
+                     reinterpret_cast<__half*>(kv16), kv_mask, q_mask, batch, S, L, G, V};
+    const int rows = batch * (S + L + G);
+    GMM_CUDA_CHECK(launch_pdl(fusion_inputs_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, p));
     gridmm_count_launch(1);
     return 0;
 }

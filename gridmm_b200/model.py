@@ -632,16 +632,10 @@ class GlocalTextPathNavCMT(nn.Module):
             inter["map_masks"] = map_mask.clone()
 
         # ---- fusion encoder: queries [gmap'; vp], context [map; txt]  (vilmodel.py:843-856)
-        ops.copy_rows(map32, S, NC, G, B, Q, 0, out_f32=x32, out_f16=x16)
         kv16 = self.buf("kv16", (B * KC, HID), f16)
-        ops.copy_rows(map32, S, 0, S, B, KC, 0, out_f16=kv16)
-        ops.copy_rows(txt32, L, 0, L, B, KC, S, out_f16=kv16)
         kv_mask = self.buf("kv_mask", (B, KC), u8)
-        kv_mask[:, :S].copy_(map_mask)
-        kv_mask[:, S:].copy_(txt_mask_u8)
         q_mask = self.buf("q_mask", (B, Q), u8)
-        q_mask[:, :G].copy_(gmap_mask_u8)
-        q_mask[:, G:].copy_(vp_mask_u8)
+        ops.fusion_inputs(map32, txt32, map_mask, txt_mask_u8, gmap_mask_u8, vp_mask_u8, x32, x16, kv16, kv_mask, q_mask, B, S, L, G, V)
         nx = cfg.num_x_layers
         le = "local_encoder.encoder.x_layers.%d"
         names_w, names_b = [], []

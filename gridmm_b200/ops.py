@@ -76,6 +76,19 @@ def copy_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_rows_per_b, out_o
               out_rows_per_b, out_off, rows_per_b, batch, x.shape[1], _lib.stream_ptr())
 
 
+def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16, kv16, kv_mask, q_mask, batch, S, L, G, V):
+    for t_, n in ((map_mask, "map_mask"), (txt_mask, "txt_mask"), (gmap_mask, "gmap_mask"), (vp_mask, "vp_mask"), (kv_mask, "kv_mask"),
+                  (q_mask, "q_mask")):
+        _chk(t_, torch.uint8, n)
+    _chk(map32, torch.float32, "map32"); _chk(txt32, torch.float32, "txt32"); _chk(x32, torch.float32, "x32")
+    _chk(x16, torch.float16, "x16"); _chk(kv16, torch.float16, "kv16")
+    for t_ in (map32, txt32, x32, x16, kv16, map_mask, txt_mask, gmap_mask, vp_mask, kv_mask, q_mask):
+        assert t_.is_contiguous()
+    _lib.call("gridmm_fusion_inputs", map32.data_ptr(), txt32.data_ptr(), map_mask.data_ptr(), txt_mask.data_ptr(), gmap_mask.data_ptr(),
+              vp_mask.data_ptr(), x32.data_ptr(), x16.data_ptr(), kv16.data_ptr(), kv_mask.data_ptr(), q_mask.data_ptr(), batch, S, L, G, V,
+              HID, _lib.stream_ptr())
+
+
 def split_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_f16, k_total):
     """out_f16[b*rows_per_b + r] = [hi | lo | hi](x[b, in_off + r]) at column blocks 0, k_total, 2*k_total."""
     _chk(x, torch.float32, "x"); _chk(out_f16, torch.float16, "out_f16")

@@ -104,6 +104,13 @@ int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, 
                          const float* residual, int ld_res, const float* gamma, const float* beta, float eps, float* out_f32,
                          int ld_f32, void* out_f16, int ld_f16, int f32_raw, cudaStream_t stream);
 
+/* Inputs of the fusion encoder (vilmodel.py:843-850) in one launch: x[b, :G] = map[b, S-G:] (fp32 + fp16; rows G.. of x hold the
+ * vp tokens already), kv16[b] = fp16([map[b] ; txt[b]]), kv_mask = [map_mask ; txt_mask], q_mask = [gmap_mask ; vp_mask]. */
+int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned char* map_mask, const unsigned char* txt_mask,
+                         const unsigned char* gmap_mask, const unsigned char* vp_mask, float* x32, void* x16, void* kv16,
+                         unsigned char* kv_mask, unsigned char* q_mask, int batch, int S, int L, int G, int V, int hidden,
+                         cudaStream_t stream);
+
 /* ---- action heads (vilmodel.py:663-674, 859-907) in three launches ------------------------------------------
  * ClsPrediction = Linear, ReLU, LayerNorm(1e-12), Linear(768 -> 1):  logit = rstd * (S3 - mean * c1) + c0 with r = ReLU(xW + b),
  * S1 = sum r, S2 = sum r^2, S3 = sum r * gamma * w2, c1 = sum gamma * w2, c0 = sum beta * w2 + b2.
