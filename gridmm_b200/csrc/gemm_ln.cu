@@ -98,7 +98,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = static_cast<int>(rank) * BN;
     const int num_kb = K / 64;
 
-    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
@@ -129,6 +128,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             __syncwarp();
         }
+        pdl_launch_dependents();      // all loads issued: the next kernel's prologue may overlap our MMA tail and epilogue
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         constexpr uint32_t idesc = umma_idesc_f16(LN_BM, MMA_N);

@@ -110,7 +110,6 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader: owns the full barriers and issues the MMAs
     const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
-    pdl_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
@@ -176,6 +175,9 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
+            // every load of this CTA is in flight: let the next kernel's CTAs be scheduled (their prologue overlaps our tail; they
+            // still wait for this grid to complete in griddepcontrol.wait before touching global memory)
+            pdl_launch_dependents();
             if (DBG && ep.dbg && lane == 0) { ep.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; ep.dbg[blockIdx.x * 8 + 1] = w_empty; }
         }
     } else if (warp == 1) {
