@@ -209,6 +209,13 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
 
 }  // namespace gmm
 
+int gridmm_attention_tc(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv, int k_rows, void* o,
+                        int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk, float scale,
+                        cudaStream_t stream);      // attn_tc.cu
+static int g_attn_legacy = 0;
+// Debug hook: 1 forces the mma.sync kernel, 2 the tcgen05 kernel (A/B timing and parity of the two paths); 0 = by shape.
+extern "C" void gridmm_debug_set_attn_legacy(int on) { g_attn_legacy = on; }
+
 extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
                                     int k_rows, void* o, int ldo, const unsigned char* kmask, float mask_neg, int batch,
                                     int heads, int sq, int sk, float scale, cudaStream_t stream) {
@@ -216,6 +223,18 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     if (batch <= 0 || sq <= 0) return 0;
     if (!q || !k || !v || !o || !kmask) return GRIDMM_ERR_ARG;
     if (sk <= 0 || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return GRIDMM_ERR_SHAPE;
+    // Query tiles are 128 rows on the tcgen05 path: with <= 64 queries per (episode, head) half of every MMA and of the softmax
+    // threads is padding and the mma.sync kernel (64-row tiles, 4 warps) is faster -- measured at B=32: Sq=57/Sk=296 18.4 vs
+    // 22.5 us, Sq=57/Sk=57 5.3 vs 6.8 us; Sq=216/Sk=216 35.8 vs 24.6 us, Sq=216/Sk=80 21.6 vs 13.6 us.  g_attn_legacy: 1 forces
+    // mma.sync, 2 forces tcgen05 (tests).
+    if (g_attn_legacy != 1 && (sq > 64 || g_attn_legacy == 2) && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
+        // tcgen05 path (attn_tc.cu); shapes it does not cover (Sk > 320, unaligned output) fall through to mma.sync
+        const int rc = gridmm_attention_tc(q, ldq, q_rows, k, ldk, v, ldv, k_rows, o, ldo, kmask, mask_neg, batch, heads, sq, sk, scale, stream);
+        if (rc != GRIDMM_ERR_SHAPE) {
+            if (rc == 0) gridmm_count_launch(1);
+            return rc;
+        }
+    }
     AttnParams p;
     p.q = reinterpret_cast<const __half*>(q); p.k = reinterpret_cast<const __half*>(k);
     p.v = reinterpret_cast<const __half*>(v); p.o = reinterpret_cast<__half*>(o);

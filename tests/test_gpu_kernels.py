@@ -117,9 +117,16 @@ def test_linear_strided_views():
     assert out[:, :768].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("B,Sq,Sk,neg", [(2, 216, 216, float("-inf")), (3, 57, 296, -10000.0), (2, 64, 80, -10000.0), (1, 5, 7, -10000.0)])
-def test_attention(B, Sq, Sk, neg):
-    from gridmm_b200 import ops
+@pytest.mark.parametrize("legacy", [2, 1, 0])
+@pytest.mark.parametrize("B,Sq,Sk,neg", [(2, 216, 216, float("-inf")), (3, 57, 296, -10000.0), (2, 64, 80, -10000.0), (1, 5, 7, -10000.0),
+                                         (2, 130, 320, -10000.0), (1, 40, 400, float("-inf"))])
+def test_attention(B, Sq, Sk, neg, legacy):
+    """legacy = 2: the tcgen05 kernel (Sk <= 320; Sk = 400 exercises its fall-back), 1: the mma.sync kernel, 0: dispatch by shape."""
+    import ctypes
+    from gridmm_b200 import ops, _lib
+    lib = _lib.load()
+    lib.gridmm_debug_set_attn_legacy.argtypes = [ctypes.c_int]
+    lib.gridmm_debug_set_attn_legacy(legacy)
     g = torch.Generator().manual_seed(Sq * 7 + Sk)
     q = torch.randn(B * Sq, 768, generator=g).half().to(_dev())
     kv = torch.randn(B * Sk, 1536, generator=g).half().to(_dev())
@@ -127,7 +134,10 @@ def test_attention(B, Sq, Sk, neg):
     lens[0] = Sk
     kmask = (torch.arange(Sk)[None, :] < lens[:, None]).to(torch.uint8).to(_dev())
     out = torch.empty(B * Sq, 768, device=_dev(), dtype=torch.float16)
-    ops.attention(q, kv[:, :768], kv[:, 768:], out, kmask, neg, B, 12, Sq, Sk)
+    try:
+        ops.attention(q, kv[:, :768], kv[:, 768:], out, kmask, neg, B, 12, Sq, Sk)
+    finally:
+        lib.gridmm_debug_set_attn_legacy(0)
     qh = q.float().view(B, Sq, 12, 64).permute(0, 2, 1, 3)
     kh = kv[:, :768].float().view(B, Sk, 12, 64).permute(0, 2, 1, 3)
     vh = kv[:, 768:].float().view(B, Sk, 12, 64).permute(0, 2, 1, 3)

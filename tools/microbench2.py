@@ -98,8 +98,12 @@ if "attn" in want:
         fl = 4.0 * B * 12 * Sq * Sk * 64
         print("ATTN %-14s Sq=%3d Sk=%3d: %6.1f us  %6.1f TF" % (tag, Sq, Sk, us, fl / us / 1e6), flush=True)
         return us
-    tot = attn_case(216, 216, "map self") * 2 + attn_case(216, 80, "map x txt") + attn_case(57, 296, "x cross") * 4 + attn_case(57, 57, "x self") * 4
-    print("ATTN sum over the step's 11 launches: %.1f us" % tot, flush=True)
+    lib.gridmm_debug_set_attn_legacy.argtypes = [ctypes.c_int]
+    for legacy in (1, 2, 0):
+        lib.gridmm_debug_set_attn_legacy(legacy)
+        print("--- attention kernel:", {1: "mma.sync", 2: "tcgen05", 0: "dispatch by shape"}[legacy], flush=True)
+        tot = attn_case(216, 216, "map self") * 2 + attn_case(216, 80, "map x txt") + attn_case(57, 296, "x cross") * 4 + attn_case(57, 57, "x self") * 4
+        print("ATTN sum over the step's 11 launches: %.1f us" % tot, flush=True)
 
 if "ln" in want:
     for rows in (B * 216, B * 57):
