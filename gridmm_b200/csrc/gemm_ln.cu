@@ -49,7 +49,7 @@ struct LnSmem {
     static constexpr int A_BYTES = LN_BM * 128;                 // 128 rows x 64 fp16
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;     // full[STAGES], empty[STAGES], tmem_full, tmem slot
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;     // full, empty, a_empty [STAGES each], tmem_full, tmem slot
     static constexpr int VEC_OFFSET = BAR_OFFSET + 256;         // bias, gamma, beta slices: 3 x BN floats
     static constexpr int STAT_OFFSET = VEC_OFFSET + 3 * BN * 4; // [2 halves][128 rows] float2 (mean, M2): read by the peers
     static constexpr int FIN_OFFSET = STAT_OFFSET + 2 * LN_BM * 8;   // [2 halves][128 rows] float2 (mean, rstd)
@@ -65,6 +65,18 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const float (
     for (int j = 0; j < 8; ++j) { a[j] = __float_as_uint(f[j]); b[j] = __float_as_uint(f[8 + j]); }
     tmem_st_32x32b_x8(taddr, a);
     tmem_st_32x32b_x8(taddr + 8, b);
+}
+// TMA load delivered to the same shared-memory offset (and signalled on the same mbarrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this shared-memory offset in the CTAs of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ float2 ld_cluster_f2(uint32_t cluster_addr) {
     float2 v;
@@ -84,7 +96,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* a_empty_bar = empty_bar + STAGES;       // rank 0 only: stage s of EVERY CTA of the cluster has been consumed
+    uint64_t* tmem_full_bar = a_empty_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     float* s_bias = reinterpret_cast<float*>(smem + L::VEC_OFFSET);
     float* s_gamma = s_bias + BN;
@@ -101,13 +114,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmW);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&a_empty_bar[s], CL); }
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();      // every CTA's barriers exist before a peer's multicast load / commit can signal them
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     pdl_wait();
@@ -118,15 +132,21 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int s = kb % STAGES;
             mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
             if (elect_one()) {
-                uint8_t* a_dst = smem + s * L::STAGE_BYTES;
-                uint8_t* b_dst = a_dst + L::A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-                tma_load_2d(a_dst, &tmA, kb * 64, m0, &full_bar[s]);
+                uint8_t* b_dst = smem + s * L::STAGE_BYTES + L::A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);       // own W slice + the multicast A tile
 #pragma unroll
                 for (int j = 0; j < NMMA; ++j)
                     tma_load_2d(b_dst + j * MMA_N * 128, &tmW, kb * 64, n0 + j * MMA_N, &full_bar[s]);
             }
             __syncwarp();
+            if (rank == 0) {
+                // the A tile is the same for the whole cluster: rank 0 fetches it once and TMA multicasts it into every CTA's
+                // stage (per-CTA L2 -> SM traffic drops from A + W/CL to A/CL + W/CL per k-block: 1.7x at CL = 6)
+                mbar_wait(&a_empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                if (elect_one())
+                    tma_load_2d_mc(smem + s * L::STAGE_BYTES, &tmA, kb * 64, m0, &full_bar[s], static_cast<uint16_t>((1u << CL) - 1));
+                __syncwarp();
+            }
         }
         pdl_launch_dependents();      // all loads issued: the next kernel's prologue may overlap our MMA tail and epilogue
     } else if (warp == 1) {
@@ -147,6 +167,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         umma_f16_ss(tmem_base + j * MMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[s]);
+                umma_commit_mc(&a_empty_bar[s], 1);         // tell rank 0 (the A multicaster) that this CTA is done with the stage
                 if (kb == num_kb - 1) umma_commit(tmem_full_bar);
             }
             __syncwarp();
