@@ -296,3 +296,60 @@ def test_pool_vs_oracle(B, T, L, D, gw):
             if cr[b, c] >= 0:
                 err = (pooled[b, cr[b, c]].double() - ref[c]).abs().max().item()
                 assert err < 6e-3, "b=%d cell=%d err=%.3e" % (b, c, err)   # fp16 output (ulp 4e-3 at |x|~4) + exp rounding
+
+
+@pytest.mark.parametrize("sizes", ["tiny", "mixed", "one_big"])
+def test_pool_handmade_cells(sizes):
+    """gridmm_pool on a hand-made layout (no grid builder): tiny cells (> 8 cells per 32-row tile -> several passes of the
+    8-slot HMMA pooling), a cell spanning many tiles, an episode without any valid point, ragged text length."""
+    from gridmm_b200 import ops
+    rng = np.random.default_rng({"tiny": 1, "mixed": 2, "one_big": 3}[sizes])
+    B, nc, D, L, t_cap = 3, 196, 768, 37, 2
+    cap = t_cap * 588
+    slab = torch.randn(B * t_cap * 588, D, generator=torch.Generator().manual_seed(7)).half()
+    slots = (torch.arange(B, dtype=torch.int32)[:, None] * t_cap + torch.arange(t_cap, dtype=torch.int32)[None, :]).contiguous()
+    perm = torch.zeros(B, cap, dtype=torch.int32)
+    cell_start = torch.zeros(B, nc + 1, dtype=torch.int32)
+    cell_rank = torch.full((B, nc), -1, dtype=torch.int32)
+    members = []
+    for b in range(B):
+        if b == 1:                                   # no valid point at all
+            members.append({})
+            continue
+        pts = rng.permutation(cap)
+        if sizes == "tiny":
+            counts = rng.integers(0, 3, nc)          # 0..2 rows per cell
+        elif sizes == "mixed":
+            counts = rng.integers(0, 12, nc)
+        else:
+            counts = np.zeros(nc, dtype=np.int64); counts[77] = 700; counts[3] = 1; counts[190] = 2
+        mem, pos, rank = {}, 0, 0
+        for c in range(nc):
+            n = int(counts[c])
+            cell_start[b, c] = pos
+            if n:
+                mem[c] = np.sort(pts[pos:pos + n])
+                perm[b, pos:pos + n] = torch.from_numpy(mem[c].astype(np.int32))
+                cell_rank[b, c] = rank
+                rank += 1
+            pos += n
+        cell_start[b, nc] = pos
+        members.append(mem)
+    tp = (torch.randn(B, L, D, generator=torch.Generator().manual_seed(11)) * 0.3).half()
+    dev = _dev()
+    pooled = torch.zeros(B * nc, D, device=dev, dtype=torch.float16)
+    w_out = torch.zeros(B, cap, device=dev)
+    ops.pool(slab.to(dev), D, slots.to(dev), t_cap, 588, 49, 0, perm.to(dev), cap, cell_start.to(dev), cell_rank.to(dev), nc,
+             tp.to(dev).view(B * L, D), L, B, pooled, w_out=w_out)
+    torch.cuda.synchronize()
+    pooled = pooled.view(B, nc, D).float().cpu()
+    for b in range(B):
+        x_b = slab[b * cap:(b + 1) * cap].double()
+        for c, idx in members[b].items():
+            x = x_b[torch.from_numpy(idx)]
+            w = (x @ tp[b].double().t()).max(-1)[0]
+            ref = (torch.softmax(w, 0)[:, None] * x).sum(0)
+            err = (pooled[b, int(cell_rank[b, c])].double() - ref).abs().max().item()
+            assert err < 6e-3, "b=%d cell=%d n=%d err=%.3e" % (b, c, len(idx), err)
+    assert pooled[1].abs().max().item() == 0
+
