@@ -5,8 +5,9 @@
 // (-inf) inside TransformerEncoderLayer.forward_pre (models/transformer.py:170-182).
 //
 // One CTA per (query tile of 64 or 128 rows, head, episode), one warp per 16 query rows: K, V of that (episode, head)
-// stream into shared memory in 64-key cp.async groups and the flash-style online softmax (mma.sync.m16n8k16, fp16 in,
-// fp32 accumulate) starts on the first group while the later ones are still in flight.  The projections around this core -- where the FLOPs are --
+// stream through a ring of three 64-key shared-memory tiles (cp.async groups; 64 KB per CTA, so three CTAs share an SM and
+// the 384 CTAs of a 57-query launch run in one wave) and the flash-style online softmax (mma.sync.m16n8k16, fp16 in,
+// fp32 accumulate) works on one tile while the next ones are in flight.  The projections around this core -- where the FLOPs are --
 // run on tcgen05 (gemm_tc.cu); this core is softmax/latency bound at these sizes.
 #include "common.cuh"
 #include "host_util.h"
@@ -16,6 +17,7 @@ namespace gmm {
 constexpr int ATT_DH = 64;
 constexpr int ATT_LD = 72;          // padded smem row (halves): 144 B, 16-byte aligned, conflict-free ldmatrix
 constexpr int ATT_KT = 64;           // keys per pipeline step (one cp.async group)
+constexpr int ATT_NSTG = 3;          // key tiles resident at a time (ring): 64 KB of shared memory per CTA -> 3 CTAs per SM
 
 struct AttnParams {
     const __half* q; const __half* k; const __half* v; __half* o;
@@ -65,11 +67,10 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
     extern __shared__ __align__(16) uint8_t att_smem[];
     const int sk_pad = (p.sk + 63) & ~63;
     __half* sK = reinterpret_cast<__half*>(att_smem);
-    __half* sV = sK + static_cast<size_t>(sk_pad) * ATT_LD;
-    __half* sQ = sV + static_cast<size_t>(sk_pad) * ATT_LD;
+    __half* sV = sK + static_cast<size_t>(ATT_NSTG * ATT_KT) * ATT_LD;
+    __half* sQ = sV + static_cast<size_t>(ATT_NSTG * ATT_KT) * ATT_LD;
     float* sM = reinterpret_cast<float*>(sQ + ATT_QT * ATT_LD);
 
-    pdl_launch_dependents();
     pdl_wait();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * ATT_QT, h = blockIdx.y, b = blockIdx.z;
@@ -84,27 +85,31 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
         else *reinterpret_cast<uint4*>(sQ + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
     }
     const int n_kt = sk_pad / ATT_KT;
-    for (int kt = 0; kt < n_kt; ++kt) {
+    // key tile kt lives in ring slot kt % ATT_NSTG; one cp.async group per tile
+    auto issue_tile = [&](int kt) {
+        const int slot = kt % ATT_NSTG;
         for (int i = tid; i < ATT_KT * 8; i += ATT_THREADS) {
             const int r = kt * ATT_KT + (i >> 3), u = i & 7;
-            const uint32_t dk = smem_u32(sK + r * ATT_LD + u * 8), dv = smem_u32(sV + r * ATT_LD + u * 8);
+            __half* dk = sK + (slot * ATT_KT + (i >> 3)) * ATT_LD + u * 8;
+            __half* dv = sV + (slot * ATT_KT + (i >> 3)) * ATT_LD + u * 8;
             if (r < p.sk) {
-                cp_async_16(dk, gk + static_cast<size_t>(r) * p.ldk + u * 8);
-                cp_async_16(dv, gv + static_cast<size_t>(r) * p.ldv + u * 8);
+                cp_async_16(smem_u32(dk), gk + static_cast<size_t>(r) * p.ldk + u * 8);
+                cp_async_16(smem_u32(dv), gv + static_cast<size_t>(r) * p.ldv + u * 8);
             } else {
-                *reinterpret_cast<uint4*>(sK + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(sV + r * ATT_LD + u * 8) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(dk) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(dv) = make_uint4(0, 0, 0, 0);
             }
         }
         cp_async_commit();
-    }
+    };
+    for (int kt = 0; kt < n_kt && kt < ATT_NSTG; ++kt) issue_tile(kt);
     for (int j = tid; j < sk_pad; j += ATT_THREADS) {
         float m = -INFINITY;                                   // keys past Sk never contribute
         if (j < p.sk) m = p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg;
         sM[j] = m;
     }
     // first group (Q + key tile 0) must have landed before the Q fragments are read
-    if (n_kt > 1) cp_async_wait_upto(n_kt - 1); else cp_async_wait<0>();
+    cp_async_wait_upto(min(ATT_NSTG, n_kt) - 1);
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
@@ -124,15 +129,17 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
     constexpr float LOG2E = 1.4426950408889634f;
 
     for (int kt = 0; kt < sk_pad; kt += 64) {
-        if (kt > 0) {      // key tile kt/64: all but the (n_kt - 1 - kt/64) newest groups are complete
-            cp_async_wait_upto(n_kt - 1 - kt / 64);
+        const int ti = kt / 64;
+        const int soff = (ti % ATT_NSTG) * ATT_KT - kt;      // ring-slot row of key `kt + j` is soff + kt + j
+        if (kt > 0) {      // the groups issued after tile ti's are those of tiles ti+1 .. min(ti + NSTG - 1, n_kt - 1)
+            cp_async_wait_upto(min(ti + ATT_NSTG - 1, n_kt - 1) - ti);
             __syncthreads();
         }
         float s[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-            const int key = kt + nt * 8 + (lane & 7);
+            const int key = soff + kt + nt * 8 + (lane & 7);
 #pragma unroll
             for (int kp = 0; kp < 2; ++kp) {   // two k-steps per ldmatrix.x4
                 uint32_t b0, b1, b2, b3;
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const int m = lane >> 3, rr = lane & 7;
-            const int key = kt + ks * 16 + (m & 1) * 8 + rr;
+            const int key = soff + kt + ks * 16 + (m & 1) * 8 + rr;
 #pragma unroll
             for (int dp = 0; dp < 4; ++dp) {   // two 8-wide dim tiles per ldmatrix.x4.trans
                 uint32_t b0, b1, b2, b3;
@@ -186,6 +193,10 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
                 mma_16816(o[dp * 2], pf[ks], b0, b1);
                 mma_16816(o[dp * 2 + 1], pf[ks], b2, b3);
             }
+        }
+        if (ti + ATT_NSTG < n_kt) {      // every warp is done with this ring slot: refill it with tile ti + NSTG
+            __syncthreads();
+            issue_tile(ti + ATT_NSTG);
         }
     }
     // finalize: quad-reduce the row sums, normalise, store fp16
@@ -205,6 +216,7 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
         if (row1 < p.sq)
             *reinterpret_cast<uint32_t*>(go + static_cast<size_t>(row1) * p.ldo + i * 8 + 2 * t) = pack_h2(o[i][2] * inv1, o[i][3] * inv1);
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 }  // namespace gmm
@@ -244,7 +256,7 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     // 8 warps (128 query rows per CTA) halve the K/V re-reads of long query sequences; 4 warps otherwise
     const int nw = (sq > 64) ? 8 : 4;
     const int qt = nw * 16;
-    const int smem = (2 * sk_pad + qt) * ATT_LD * 2 + sk_pad * 4;
+    const int smem = (2 * ATT_NSTG * ATT_KT + qt) * ATT_LD * 2 + sk_pad * 4;
     if (smem > 227 * 1024) return GRIDMM_ERR_SHAPE;
     dim3 grid((sq + qt - 1) / qt, heads, batch);
     if (nw == 8) {

@@ -72,7 +72,6 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
         fence_mbar_init();
     }
     if (warp == 4) tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-    pdl_launch_dependents();
     pdl_wait();
     for (int j = threadIdx.x; j < p.nkey; j += blockDim.x) {
         float m = -INFINITY;                               // keys past Sk never contribute
@@ -193,6 +192,7 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
         tc_fence_after();
         tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 }  // namespace gmm

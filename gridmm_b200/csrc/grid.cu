@@ -77,7 +77,6 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_update_kernel(GridParams
     __shared__ uint16_t warp_hist[32][MAX_CELLS];   // per-warp counts, then per-warp write cursors
     __shared__ int s_cell_start[MAX_CELLS + 1];
 
-    pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -260,6 +259,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_update_kernel(GridParams
         }
         o[4] = r / p.max_dist;
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 }  // namespace gmm

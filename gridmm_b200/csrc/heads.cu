@@ -23,7 +23,6 @@ struct HeadRowsParams {
 };
 
 __global__ void __launch_bounds__(256) head_rows_kernel(HeadRowsParams p) {
-    pdl_launch_dependents();
     pdl_wait();
     int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -50,6 +49,7 @@ __global__ void __launch_bounds__(256) head_rows_kernel(HeadRowsParams p) {
         *reinterpret_cast<uint2*>(o + HD + col) = lo;
         *reinterpret_cast<uint2*>(o + 2 * HD + col) = hi;
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // vilmodel.py:859-907.  One CTA per episode; every head's logit is finished from its partial sums first.
@@ -79,7 +79,6 @@ __device__ __forceinline__ float finish_head(const float* pr, int nparts, float 
 __global__ void __launch_bounds__(128) nav_logits2_kernel(Logit2Params p) {
     extern __shared__ float s_local[];
     __shared__ float s_bw, s_fw;
-    pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x;
     const float ninf = -INFINITY;
@@ -142,6 +141,7 @@ __global__ void __launch_bounds__(128) nav_logits2_kernel(Logit2Params p) {
         }
         p.fused_logits[b * p.G + g] = f;
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 }  // namespace gmm

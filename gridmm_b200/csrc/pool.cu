@@ -167,12 +167,12 @@ struct PoolSmem {
 // this layout directly from its epilogue, gridmm_linear_f16_lanes.)
 template <int D>
 __global__ void __launch_bounds__(128) text_to_lanes_kernel(const __half* text, uint4* ws, int l_pad) {
-    pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
     if (t >= l_pad) return;
     const uint4 v = *reinterpret_cast<const uint4*>(text + (static_cast<size_t>(b) * l_pad + t) * D + c * 8);
     ws[(static_cast<size_t>(b) * (D / 8) + c) * 128 + t] = v;
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // Move this thread's share of the episode's text operand into tensor memory: TMEM lane `tlane` (= text position, lanes
@@ -263,7 +263,6 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
         *s_carry_c = -1;
         fence_mbar_init();
     }
-    pdl_launch_dependents();
     if (warp == POOL_MMA_WARP) tmem_alloc(tmem_slot, POOL_TMEM_COLS);
     pdl_wait();      // barrier init / TMEM allocation above overlap the previous kernel's tail
     // the tile buffers start as zeros: rows past a partial tile's end are never fetched, only multiplied by weight 0
@@ -682,6 +681,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
         tc_fence_after();
         tmem_dealloc(tmem_base, POOL_TMEM_COLS);
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 template <int D>

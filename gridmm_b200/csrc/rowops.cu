@@ -53,7 +53,6 @@ __device__ __forceinline__ void store_row(float4 (&x)[HV], float* o32, __half* o
 // ------------------------------------------------------------------------------------------- layer norm
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx, const float* gamma, const float* beta,
                                                         float eps, float* o32, int ld32, __half* o16, int ld16, int rows) {
-    pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -62,6 +61,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
     for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx + (i * 32 + lane) * 4);
     ln_row(v, gamma, beta, eps, lane);
     store_row(v, o32 ? o32 + static_cast<size_t>(row) * ld32 : nullptr, o16 ? o16 + static_cast<size_t>(row) * ld16 : nullptr, lane);
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- row copies / casts
@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx,
 __global__ void __launch_bounds__(256) copy_rows_kernel(const float* x, int ldx, int in_rows_per_b, int in_off, float* o32,
                                                         int ld32, __half* o16, int ld16, int out_rows_per_b, int out_off,
                                                         int rows_per_b, int rows) {
-    pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -81,6 +80,7 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const float* x, int ldx,
 #pragma unroll
     for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(x + irow * ldx + (i * 32 + lane) * 4);
     store_row(v, o32 ? o32 + orow * ld32 : nullptr, o16 ? o16 + orow * ld16 : nullptr, lane);
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- fusion-encoder inputs
@@ -95,7 +95,6 @@ struct FusionInParams {
 };
 
 __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
-    pdl_launch_dependents();
     pdl_wait();
     const int KC = p.S + p.L, Q = p.G + p.V;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -122,6 +121,7 @@ __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
         store_row(v, p.x32 + orow * HID, p.x16 + orow * HID, lane);
         if (lane == 0) p.q_mask[b * Q + g] = p.gmap_mask[b * p.G + g];
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- fp32 -> (hi, lo) fp16 split
@@ -131,7 +131,6 @@ __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
 // dominate the logit error (numerics).
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* x, int ldx, int in_rows_per_b, int in_off, __half* o16,
                                                          int ld16, int k_total, int rows_per_b, int rows) {
-    pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -152,6 +151,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* x, int ldx
         *reinterpret_cast<uint2*>(o + k_total + col) = lo;
         *reinterpret_cast<uint2*>(o + 2 * k_total + col) = hi;
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- position embeddings
@@ -167,7 +167,6 @@ struct EmbedParams {
 };
 
 __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
-    pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= p.rows) return;
@@ -210,6 +209,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
     const int b = row / p.in_rows_per_b, r = row - b * p.in_rows_per_b;
     const size_t orow = static_cast<size_t>(b) * p.out_rows_per_b + p.out_row_off + r;
     store_row(v, p.o32 ? p.o32 + orow * HID : nullptr, p.o16 ? p.o16 + orow * HID : nullptr, lane);
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- BERT text embeddings
@@ -217,7 +217,6 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
 __global__ void __launch_bounds__(256) text_embed_kernel(const long long* ids, const float* word, const float* pos,
                                                          const float* type0, const float* gamma, const float* beta,
                                                          float* o32, __half* o16, int L, int rows) {
-    pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -233,6 +232,7 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const long long* ids, c
     }
     ln_row(v, gamma, beta, 1e-12f, lane);
     store_row(v, o32 ? o32 + static_cast<size_t>(row) * HID : nullptr, o16 ? o16 + static_cast<size_t>(row) * HID : nullptr, lane);
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- grid-cell assembly
@@ -257,7 +257,6 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
     __shared__ int s_inv[256];
     __shared__ int s_red[8];
     __shared__ int s_c, s_k2;
-    pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int k = p.n_nonempty[b];
@@ -320,13 +319,13 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
             p.map_mask[static_cast<size_t>(b) * p.seq + r] = valid ? 1 : 0;
         }
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- ClsPrediction tail
 // logit[row] = w2 . LN(h[row]) + b2      (h = ReLU(Linear(x)) comes from the GEMM epilogue)
 __global__ void __launch_bounds__(256) cls_tail_kernel(const float* h, const float* gamma, const float* beta, const float* w2,
                                                        const float* b2, float* logit, int rows) {
-    pdl_launch_dependents();
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -342,6 +341,7 @@ __global__ void __launch_bounds__(256) cls_tail_kernel(const float* h, const flo
     }
     s = warp_sum(s);
     if (lane == 0) logit[row] = s + b2[0];
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- action logits
@@ -363,7 +363,6 @@ struct LogitParams {
 __global__ void __launch_bounds__(128) nav_logits_kernel(LogitParams p) {
     extern __shared__ float s_local[];
     __shared__ float s_bw;
-    pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x;
     const float ninf = -INFINITY;
@@ -404,6 +403,7 @@ __global__ void __launch_bounds__(128) nav_logits_kernel(LogitParams p) {
         }
         p.fused_logits[b * p.G + g] = f;
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 // ------------------------------------------------------------------------------------------- continuous-env action logits
@@ -411,7 +411,6 @@ __global__ void __launch_bounds__(128) nav_logits_kernel(LogitParams p) {
 // local[b, j] * (1 - w) for j < max(candidate_lengths), -inf where vp_nav_masks is false.
 __global__ void __launch_bounds__(128) ce_logits_kernel(const float* raw_global, const float* raw_local, const float* raw_fuse,
                                                         const uint8_t* vp_nav_masks, float* fused, int G, int V, int maxc) {
-    pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x;
     const float fw = 1.0f / (1.0f + expf(-raw_fuse[b]));
@@ -420,6 +419,7 @@ __global__ void __launch_bounds__(128) ce_logits_kernel(const float* raw_global,
         // both terms are masked with -inf in the reference, so a masked slot is -inf + -inf = -inf
         fused[b * maxc + j] = nav ? (raw_global[b * G + j] * fw + raw_local[b * V + j] * (1.0f - fw)) : -INFINITY;
     }
+    pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
 }  // namespace gmm
