@@ -190,16 +190,18 @@ class ClockSampler:
 class Step:
     """Holds the device state of one rank and runs one hot-path step."""
 
-    def __init__(self, device, seed):
+    def __init__(self, device, seed, model=None):
         from gridmm_b200.env import GridMapBuilder
         from gridmm_b200.model import GlocalTextPathNavCMT
         self.dev = device
         self.ep, self.nav_np = _inputs(seed)
         self.cfg, w = _weights()
-        self.model = GlocalTextPathNavCMT(self.cfg)
-        self.model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
-        self.model.to(device).eval()
-        self.model.enable_cuda_graph(True)      # the device part of forward('navigation') replays from a CUDA graph
+        if model is None:
+            model = GlocalTextPathNavCMT(self.cfg)
+            model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+            model.to(device).eval()
+            model.enable_cuda_graph(True)       # the device part of forward('navigation') replays from a CUDA graph
+        self.model = model
         self.builder = GridMapBuilder(B, max_steps=T, device=device)
         ep = self.ep
         for t in range(T - 1):
@@ -246,6 +248,34 @@ class Step:
             batch[k] = self.h_nav[k].to(self.dev, non_blocking=True)
         out = self.model("navigation", batch)
         return out["fused_logits"].cpu()
+
+    # ---- pipelined end-to-end: two environment batches per GPU share one model; while one batch's kernels run, the other
+    #      batch's new viewpoint (29.5 MB of CLIP tokens) is copied on the builder's copy stream.  Every step still performs
+    #      its own H2D (from pinned memory) and its own D2H of the fused logits inside the timed region.
+    def e2e_begin(self):
+        """start this batch's H2D for its next step (returns immediately)"""
+        self.restore()
+        self.builder.stage_features(self.h_clip, after=getattr(self, "done_evt", None))
+
+    def e2e_compute(self):
+        """enqueue the step's kernels + the async D2H of the result"""
+        ep = self.ep
+        grid = self.builder.step(self.h_depth.numpy().view(np.uint16), None, ep["pos"][:, T - 1], ep["heading"][:, T - 1])
+        batch = dict(self.nav); batch["grid"] = grid
+        batch.update(grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        for k in self.host_keys:
+            batch[k] = self.h_nav[k].to(self.dev, non_blocking=True)
+        out = self.model("navigation", batch)
+        if not hasattr(self, "h_out"):
+            self.h_out = torch.empty(out["fused_logits"].shape, dtype=torch.float32).pin_memory()
+        self.h_out.copy_(out["fused_logits"], non_blocking=True)
+        self.done_evt = torch.cuda.Event()
+        self.done_evt.record()
+
+    def e2e_result(self):
+        """host-side read of the step's result (blocks until that step's D2H has landed)"""
+        self.done_evt.synchronize()
+        return float(self.h_out[0, 0])
 
     def e2e_bytes(self):
         h2d = self.h_depth.numel() * 2 + self.h_clip.numel() * 2 + B * 28 * 4
@@ -373,7 +403,27 @@ def main():
     ms = timed(step.run_resident, args.steps, warmup, world)
     t_w1 = time.time()
     launches = launches_per_step * args.steps
-    ms_e2e = timed(step.run_e2e, args.steps, warmup, world)
+    ms_e2e_serial = timed(step.run_e2e, args.steps, warmup, world)
+    # pipelined e2e: a second environment batch (own grid state, own host buffers) on the same model
+    step_b = Step(dev, seed=shard_seed(rank) + 1000, model=step.model)
+    pair = [step, step_b]
+    state = {"i": 0}
+    step.e2e_begin()
+
+    def e2e_step():
+        i = state["i"]; state["i"] = i + 1
+        cur, nxt = pair[i & 1], pair[(i + 1) & 1]
+        cur.e2e_compute()           # enqueue this step (its H2D was started one call ago)
+        if i >= 1:
+            nxt.e2e_result()        # host reads the other batch's previous result while this step runs
+        nxt.e2e_begin()             # the other batch's next H2D overlaps this step's kernels
+
+    def e2e_drain():
+        for sp in pair:
+            if hasattr(sp, "done_evt"):
+                sp.e2e_result()
+    ms_e2e = timed(e2e_step, args.steps, warmup, world)
+    e2e_drain()
     clocks = None
     if sampler:
         window = "timed region"
@@ -440,7 +490,11 @@ def main():
                 "dtype": "f16 operands / f32 accumulate (grid cell ids: f32 + int, bit-exact)", "data": "synthetic",
                 "config": CONFIG, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "nav-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps,
+                        "mode": "two environment batches per GPU ping-pong on one model: each step's H2D (pinned host -> HBM, copy "
+                                "stream) overlaps the other batch's kernels; every step copies its own inputs in and its logits out",
+                        "serial_value": world * B * args.steps / (ms_e2e_serial * 1e-3),
+                        "serial_ms_per_step": ms_e2e_serial / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_pool": roofline_pool, "cpu_baseline": cpu,
                 "kernel_ms_per_step": {k: round(t, 4) for k, (t, _) in sorted(br.items(), key=lambda kv: -kv[1][0])}}
         print(json.dumps(line))

@@ -125,6 +125,9 @@ class GridMapBuilder:
         self.d_depth_f32 = torch.empty(B, PTS, dtype=torch.float32, device=dev)
         self.d_pose = torch.empty(B, 4, dtype=torch.float32, device=dev)
         self.d_view = torch.empty(B, 24, dtype=torch.float32, device=dev)
+        self._copy_stream = None
+        self._staged_evt = None
+        self._staged_step = -1
         self.new_episodes()
 
     # ------------------------------------------------------------------ buffers
@@ -182,11 +185,41 @@ class GridMapBuilder:
         out[:, 5::2] = np.sin(va).astype(np.float32)
         return out
 
+    def stage_features(self, clip, after=None):
+        """Start the host->device copy of the NEXT viewpoint's CLIP tokens on this builder's copy stream and return at once.
+        `step(..., clip=None)` then only waits for that copy on the device.  With two environment batches per GPU (two
+        builders, one model) the 29.5 MB copy of one batch hides behind the other batch's kernels (bench.py's `e2e`).
+        clip: pinned host tensor [B,12,50,D] fp16 (a pageable array is first copied into this builder's pinned buffer);
+        after: optional CUDA event the copy must wait for (only needed when a slab slot is rewritten while an earlier step
+        may still read it -- never the case in a real episode, where every step writes a new slot)."""
+        grew = False
+        if int(self.n_steps.max()) + 1 > self.t_cap:
+            self._alloc(self.t_cap * 2)
+            grew = True
+        t = int(self.n_steps[0])
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            grew = True
+        if not (isinstance(clip, torch.Tensor) and clip.is_pinned()):
+            self.h_clip.copy_(torch.as_tensor(clip).reshape(self.h_clip.shape))
+            clip = self.h_clip
+        cs = self._copy_stream
+        if grew:      # the slab was (re)allocated on the compute stream: order that before the first copy into it
+            cs.wait_stream(torch.cuda.current_stream(self.device))
+        if after is not None:
+            cs.wait_event(after)
+        with torch.cuda.stream(cs):
+            self.slab[t].copy_(clip.reshape(self.batch, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
+            self._staged_evt = torch.cuda.Event()
+            self._staged_evt.record(cs)
+        self._staged_step = t
+
     def step(self, depth_sub, clip, pos_xy, heading, active=None):
         """Append one viewpoint per episode and rebuild the grid assignment (getStates' grid half, env.py:392-398).
 
         depth_sub : [B,12,49] uint16 (0.25 mm) or float32 metres (CE); numpy (host) or a device tensor
-        clip      : [B,12,50,D] fp16 CLIP tokens incl. CLS; numpy / host tensor (copied H2D) or a device tensor
+        clip      : [B,12,50,D] fp16 CLIP tokens incl. CLS; numpy / host tensor (copied H2D) or a device tensor; None when the
+                    copy was started earlier with stage_features()
         pos_xy    : [B,2] viewpoint x,y (python floats / float64);  heading : [B] radians
         Returns a GridBatch.
         """
@@ -198,7 +231,12 @@ class GridMapBuilder:
                                       "the reference re-adds the last viewpoint of ended episodes, so do that")
         t = int(self.n_steps[0])
         # features: one contiguous copy into slab[t]
-        if isinstance(clip, torch.Tensor) and (clip.is_cuda or clip.is_pinned()):
+        if clip is None:
+            if self._staged_step != t or self._staged_evt is None:
+                raise RuntimeError("step(clip=None) needs stage_features() for this step first")
+            torch.cuda.current_stream(self.device).wait_event(self._staged_evt)
+            self._staged_step = -1
+        elif isinstance(clip, torch.Tensor) and (clip.is_cuda or clip.is_pinned()):
             self.slab[t].copy_(clip.reshape(B, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
         else:
             self.h_clip.copy_(torch.as_tensor(clip).reshape(self.h_clip.shape))

@@ -284,3 +284,44 @@ def test_unsupported_shapes_are_rejected():
         model("navigation", nav)
     with pytest.raises(NotImplementedError):
         model("nonsense", nav)
+
+
+def test_staged_features_two_batches_ping_pong():
+    """GridMapBuilder.stage_features (async H2D on the builder's copy stream) + step(clip=None): two environment batches share one
+    CUDA-graphed model and alternate steps (bench.py's end-to-end mode).  Every step must give bitwise the logits of the plain
+    synchronous path for that batch."""
+    from gridmm_b200.env import GridMapBuilder
+    B, T, L, G = 8, 4, 40, 12
+    cfg = H.make_config()
+    model, _ = _model(cfg, 5)
+    eps = [synth.make_episodes(dim=768, batch=B, steps=T, seed=s) for s in (21, 22)]
+    navs = [_to_cuda(synth.to_torch(synth.make_nav_inputs(B, seed=s, txt_len=L, gmap_len=G, n_views=36, n_objs=0))) for s in (21, 22)]
+    # reference: synchronous, one batch after the other, no graph
+    want = []
+    for ep, nav in zip(eps, navs):
+        gb = GridMapBuilder(B, max_steps=T)
+        per_t = []
+        for t in range(T):
+            grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+            b = dict(nav); b.update(grid=grid, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+            per_t.append(model("navigation", b)["fused_logits"].clone())
+        want.append(per_t)
+    # staged + graphed + interleaved
+    model.enable_cuda_graph(True)
+    gbs = [GridMapBuilder(B, max_steps=2) for _ in range(2)]         # max_steps=2: the slab also has to grow while copies are staged
+    pinned = [[torch.from_numpy(np.ascontiguousarray(ep["clip"][:, t])).pin_memory() for t in range(T)] for ep in eps]
+    gbs[0].stage_features(pinned[0][0])
+    for t in range(T):
+        for i in range(2):
+            ep, nav, gb = eps[i], navs[i], gbs[i]
+            grid = gb.step(ep["depth_sub"][:, t], None, ep["pos"][:, t], ep["heading"][:, t])
+            nxt = (i + 1) % 2
+            nt = t if nxt == 1 else t + 1
+            if nt < T:
+                gbs[nxt].stage_features(pinned[nxt][nt])                # the other batch's copy overlaps this step's kernels
+            b = dict(nav); b.update(grid=grid, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+            got = model("navigation", b)["fused_logits"].clone()
+            torch.cuda.synchronize()
+            assert torch.equal(got, want[i][t]), "batch %d step %d" % (i, t)
+    with pytest.raises(RuntimeError):
+        gbs[0].step(eps[0]["depth_sub"][:, 0], None, eps[0]["pos"][:, 0], eps[0]["heading"][:, 0])     # nothing staged
