@@ -251,6 +251,11 @@ struct AssembleParams {
     float* map32;             // [B, seq, 768]
     uint8_t* map_mask;        // [B, seq]
     int batch, n_cells, seq;
+    // optional (gridmm_map_inputs): rows [n_cells, seq) = gmap tokens (vilmodel.py:828-831: img + step embedding +
+    // LN(Linear(pos))) and the first pre-norm LayerNorm of grid_encoder over every row -> map16
+    const float* g_feat; int g_kin; const float* g_w; const float* g_bias; const float* g_gamma; const float* g_beta;
+    const float* g_base; const float* g_table; const long long* g_idx; const uint8_t* g_mask;
+    const float* n_gamma; const float* n_beta; float n_eps; __half* map16;
 };
 
 __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
@@ -282,10 +287,48 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
     }
     __syncthreads();
     const int C = s_c, k2 = s_k2;
-    const int rows_per_cta = (p.n_cells + gridDim.x - 1) / gridDim.x;
-    const int r_lo = blockIdx.x * rows_per_cta, r_hi = min(r_lo + rows_per_cta, p.n_cells);
+    const int n_rows = p.g_feat ? p.seq : p.n_cells;
+    const int rows_per_cta = (n_rows + gridDim.x - 1) / gridDim.x;
+    const int r_lo = blockIdx.x * rows_per_cta, r_hi = min(r_lo + rows_per_cta, n_rows);
     for (int r = r_lo + warp; r < r_hi; r += 8) {
         float4 v[HV];
+        if (r >= p.n_cells) {
+            // gmap token r - n_cells of this episode
+            const int G = p.seq - p.n_cells;
+            const size_t gr = static_cast<size_t>(b) * G + (r - p.n_cells);
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = (j < p.g_kin) ? p.g_feat[gr * p.g_kin + j] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < HV; ++i) {
+                const int col = (i * 32 + lane) * 4;
+                float4 a = *reinterpret_cast<const float4*>(p.g_bias + col);
+                float4 w4[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    w4[j] = (j < p.g_kin) ? __ldg(reinterpret_cast<const float4*>(p.g_w + static_cast<size_t>(j) * HID + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    a.x = fmaf(f[j], w4[j].x, a.x); a.y = fmaf(f[j], w4[j].y, a.y); a.z = fmaf(f[j], w4[j].z, a.z); a.w = fmaf(f[j], w4[j].w, a.w);
+                }
+                v[i] = a;
+            }
+            ln_row(v, p.g_gamma, p.g_beta, 1e-12f, lane);
+            const float* tr = p.g_table + static_cast<size_t>(p.g_idx[gr]) * HID;
+#pragma unroll
+            for (int i = 0; i < HV; ++i) {
+                const float4 t1 = *reinterpret_cast<const float4*>(p.g_base + gr * HID + (i * 32 + lane) * 4);
+                const float4 t2 = *reinterpret_cast<const float4*>(tr + (i * 32 + lane) * 4);
+                v[i].x += t1.x + t2.x; v[i].y += t1.y + t2.y; v[i].z += t1.z + t2.z; v[i].w += t1.w + t2.w;
+            }
+            store_row(v, p.map32 + (static_cast<size_t>(b) * p.seq + r) * HID, nullptr, lane);
+            if (lane == 0) p.map_mask[static_cast<size_t>(b) * p.seq + r] = p.g_mask[gr];
+            if (p.map16) {
+                ln_row(v, p.n_gamma, p.n_beta, p.n_eps, lane);
+                store_row(v, nullptr, p.map16 + (static_cast<size_t>(b) * p.seq + r) * HID, lane);
+            }
+            continue;
+        }
         if (r < k) {
             const int cellid = s_inv[r];
             float f[5];
@@ -317,6 +360,10 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
             const bool in_s = p.cell_rank[b * p.n_cells + r] >= 0;
             const bool valid = (r < C) && ((r < k) || (r < k2 && in_s));
             p.map_mask[static_cast<size_t>(b) * p.seq + r] = valid ? 1 : 0;
+        }
+        if (p.map16) {
+            ln_row(v, p.n_gamma, p.n_beta, p.n_eps, lane);
+            store_row(v, nullptr, p.map16 + (static_cast<size_t>(b) * p.seq + r) * HID, lane);
         }
     }
     pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
@@ -520,8 +567,33 @@ extern "C" int gridmm_grid_assemble(const float* proj, const float* pos_fts, con
     if (hidden != HID || n_cells > 256 || seq < n_cells) return GRIDMM_ERR_SHAPE;
     if (!proj || !pos_fts || !cell_rank || !n_nonempty || !w || !bias || !gamma || !beta || !map_f32 || !map_mask)
         return GRIDMM_ERR_ARG;
-    AssembleParams p{proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq};
+    AssembleParams p{proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq,
+                     nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, nullptr};
     GMM_CUDA_CHECK(launch_pdl(grid_assemble_kernel, dim3(dim3(4, batch)), dim3(256), 0, stream, p));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+// grid_assemble + the gmap tokens (rows [n_cells, seq): gmap_img + step embedding + LN(Linear(gmap_pos)), vilmodel.py:828-831) +
+// the first pre-norm LayerNorm of grid_encoder (transformer.py:170-172) in one launch: map_f32 [B, seq, 768] and its mask are the
+// encoder input, map_f16 = LayerNorm(map_f32; norm_gamma, norm_beta, norm_eps) is the operand of the first QKV projection.
+extern "C" int gridmm_map_inputs(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty,
+                                 const float* w, const float* bias, const float* gamma, const float* beta, const float* gmap_pos,
+                                 int gmap_kin, const float* gw, const float* gbias, const float* ggamma, const float* gbeta,
+                                 const float* gmap_img, const float* step_table, const long long* step_ids,
+                                 const unsigned char* gmap_mask, const float* norm_gamma, const float* norm_beta, float norm_eps,
+                                 float* map_f32, void* map_f16, unsigned char* map_mask, int batch, int n_cells, int seq,
+                                 int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (hidden != HID || n_cells > 256 || seq <= n_cells || gmap_kin < 1 || gmap_kin > 16) return GRIDMM_ERR_SHAPE;
+    if (!proj || !pos_fts || !cell_rank || !n_nonempty || !w || !bias || !gamma || !beta || !gmap_pos || !gw || !gbias || !ggamma ||
+        !gbeta || !gmap_img || !step_table || !step_ids || !gmap_mask || !norm_gamma || !norm_beta || !map_f32 || !map_f16 || !map_mask)
+        return GRIDMM_ERR_ARG;
+    AssembleParams p{proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq,
+                     gmap_pos, gmap_kin, gw, gbias, ggamma, gbeta, gmap_img, step_table, step_ids, gmap_mask, norm_gamma, norm_beta,
+                     norm_eps, reinterpret_cast<__half*>(map_f16)};
+    GMM_CUDA_CHECK(launch_pdl(grid_assemble_kernel, dim3(dim3(5, batch)), dim3(256), 0, stream, p));
     gridmm_count_launch(1);
     return 0;
 }

@@ -435,10 +435,12 @@ class GlocalTextPathNavCMT(nn.Module):
         self._self_post(x32, x16, pre + ".visn_self_att", x_mask, B, S, tag)
         self._ffn_post(x32, x16, pre + ".visn_inter", pre + ".visn_output", B * S, tag)
 
-    def _prenorm_encoder(self, pre, n_layers, x32, x16, kmask, B, S, tag):
-        """TransformerEncoder of forward_pre layers + final norm (models/transformer.py:60-87, 170-182)."""
+    def _prenorm_encoder(self, pre, n_layers, x32, x16, kmask, B, S, tag, first_norm_done=False):
+        """TransformerEncoder of forward_pre layers + final norm (models/transformer.py:60-87, 170-182).
+        first_norm_done: x16 already holds layers.0.norm1(x32) (written by the kernel that produced x32)."""
         rows = B * S
-        self._ln(x32, "%s.layers.0.norm1" % pre, 1e-5, None, x16)
+        if not first_norm_done:
+            self._ln(x32, "%s.layers.0.norm1" % pre, 1e-5, None, x16)
         for i in range(n_layers):
             q = "%s.layers.%d" % (pre, i)
             qkv = self.buf("qkv16_" + tag, (rows, 3 * HID), torch.float16)
@@ -611,14 +613,16 @@ class GlocalTextPathNavCMT(nn.Module):
         map32 = self.buf("map32", (B * S, HID), f32)
         map16 = self.buf("map16", (B * S, HID), f16)
         map_mask = self.buf("map_mask", (B, S), u8)
-        ops.grid_assemble(proj32, grid.pos_fts, grid.cell_rank, grid.n_nonempty, self.Wt32("grid_pos_embeddings.0.weight"),
-                          self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
-                          self.P("grid_pos_embeddings.1.bias"), map32, map_mask, B, NC, S)
-        map_mask[:, NC:].copy_(gmap_mask_u8)
+        # one launch: grid-cell rows (+ position embedding, compaction quirk), gmap rows (img + step + position embedding), both
+        # masks, and grid_encoder's first pre-norm LayerNorm (-> map16)
         ge = "global_encoder.gmap_pos_embeddings"
-        ops.pos_embed(st["gmap_pos"], self.Wt32(ge + ".0.weight"), self.P(ge + ".0.bias"), self.P(ge + ".1.weight"),
-                      self.P(ge + ".1.bias"), 1e-12, map32, None, G, S, NC, base=st["gmap_img"],
-                      table=self.P("global_encoder.gmap_step_embeddings.weight"), idx=st["gmap_step"])
+        ops.map_inputs(proj32, grid.pos_fts, grid.cell_rank, grid.n_nonempty, self.Wt32("grid_pos_embeddings.0.weight"),
+                       self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
+                       self.P("grid_pos_embeddings.1.bias"), st["gmap_pos"], self.Wt32(ge + ".0.weight"), self.P(ge + ".0.bias"),
+                       self.P(ge + ".1.weight"), self.P(ge + ".1.bias"), st["gmap_img"],
+                       self.P("global_encoder.gmap_step_embeddings.weight"), st["gmap_step"], gmap_mask_u8,
+                       self.P("grid_encoder.layers.0.norm1.weight"), self.P("grid_encoder.layers.0.norm1.bias"), 1e-5,
+                       map32, map16, map_mask, B, NC, S)
         x32 = self._out("x32", (B * Q, HID), static_out)       # escapes as gmap_embeds / vp_embeds
         x16 = self.buf("x16", (B * Q, HID), f16)
         ve = "local_encoder.vp_pos_embeddings"
@@ -626,7 +630,7 @@ class GlocalTextPathNavCMT(nn.Module):
                       self.P(ve + ".1.bias"), 1e-12, x32, x16, V, Q, G, base=st["vp_img"])
 
         # ---- grid_encoder (pre-norm, key_padding_mask) and grid_txt_encoder (vilmodel.py:840-841)
-        self._prenorm_encoder("grid_encoder", 1, map32, map16, map_mask, B, S, "map")
+        self._prenorm_encoder("grid_encoder", 1, map32, map16, map_mask, B, S, "map", first_norm_done=True)
         gt = "grid_txt_encoder.x_layers.0"
         kv_txt = self.buf("kv_txt16", (B * L, 2 * HID), f16)
         ops.linear(txt16, self.W16(gt + ".visual_attention.att.key.weight", gt + ".visual_attention.att.value.weight"),

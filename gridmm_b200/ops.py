@@ -76,6 +76,21 @@ def copy_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_rows_per_b, out_o
               out_rows_per_b, out_off, rows_per_b, batch, x.shape[1], _lib.stream_ptr())
 
 
+def map_inputs(proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, gmap_pos, gw, gbias, ggamma, gbeta, gmap_img, step_table,
+               step_ids, gmap_mask, norm_gamma, norm_beta, norm_eps, map_f32, map_f16, map_mask, batch, n_cells, seq):
+    _chk(proj, torch.float32, "proj"); _chk(pos_fts, torch.float32, "pos_fts"); _chk(cell_rank, torch.int32, "cell_rank")
+    _chk(n_nonempty, torch.int32, "n_nonempty"); _chk(gmap_pos, torch.float32, "gmap_pos"); _chk(gmap_img, torch.float32, "gmap_img")
+    _chk(step_ids, torch.int64, "step_ids"); _chk(gmap_mask, torch.uint8, "gmap_mask"); _chk(map_f32, torch.float32, "map_f32")
+    _chk(map_f16, torch.float16, "map_f16"); _chk(map_mask, torch.uint8, "map_mask")
+    for t_ in (gmap_pos, gmap_img, gw, map_f32, map_f16):
+        assert t_.is_contiguous()
+    _lib.call("gridmm_map_inputs", proj.data_ptr(), pos_fts.data_ptr(), cell_rank.data_ptr(), n_nonempty.data_ptr(), w.data_ptr(),
+              bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), gmap_pos.data_ptr(), gmap_pos.shape[1], gw.data_ptr(),
+              gbias.data_ptr(), ggamma.data_ptr(), gbeta.data_ptr(), gmap_img.data_ptr(), step_table.data_ptr(), step_ids.data_ptr(),
+              gmap_mask.data_ptr(), norm_gamma.data_ptr(), norm_beta.data_ptr(), float(norm_eps), map_f32.data_ptr(),
+              map_f16.data_ptr(), map_mask.data_ptr(), batch, n_cells, seq, HID, _lib.stream_ptr())
+
+
 def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16, kv16, kv_mask, q_mask, batch, S, L, G, V):
     for t_, n in ((map_mask, "map_mask"), (txt_mask, "txt_mask"), (gmap_mask, "gmap_mask"), (vp_mask, "vp_mask"), (kv_mask, "kv_mask"),
                   (q_mask, "q_mask")):

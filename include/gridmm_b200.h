@@ -104,6 +104,17 @@ int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, 
                          const float* residual, int ld_res, const float* gamma, const float* beta, float eps, float* out_f32,
                          int ld_f32, void* out_f16, int ld_f16, int f32_raw, cudaStream_t stream);
 
+/* gridmm_grid_assemble + the gmap tokens (rows [n_cells, seq) of the map sequence: gmap_img + step_table[step_ids] +
+ * LN(Linear(gmap_pos)), vilmodel.py:828-831; mask from gmap_mask) + the first pre-norm LayerNorm of grid_encoder
+ * (transformer.py:170-172: map_f16 = LN(map_f32; norm_gamma, norm_beta, norm_eps)) in one launch.  gw is the TRANSPOSED weight
+ * [gmap_kin, 768] like w. */
+int gridmm_map_inputs(const float* proj, const float* pos_fts, const int* cell_rank, const int* n_nonempty, const float* w,
+                      const float* bias, const float* gamma, const float* beta, const float* gmap_pos, int gmap_kin,
+                      const float* gw, const float* gbias, const float* ggamma, const float* gbeta, const float* gmap_img,
+                      const float* step_table, const long long* step_ids, const unsigned char* gmap_mask,
+                      const float* norm_gamma, const float* norm_beta, float norm_eps, float* map_f32, void* map_f16,
+                      unsigned char* map_mask, int batch, int n_cells, int seq, int hidden, cudaStream_t stream);
+
 /* Inputs of the fusion encoder (vilmodel.py:843-850) in one launch: x[b, :G] = map[b, S-G:] (fp32 + fp16; rows G.. of x hold the
  * vp tokens already), kv16[b] = fp16([map[b] ; txt[b]]), kv_mask = [map_mask ; txt_mask], q_mask = [gmap_mask ; vp_mask]. */
 int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned char* map_mask, const unsigned char* txt_mask,
