@@ -27,6 +27,8 @@ struct AttnParams {
     float mask_neg;                    // -10000 (BERT additive) or -inf (key_padding_mask)
     int sq, sk;
     float scale;
+    const int* k_off;                  // optional packed context: keys of episode b are rows k_off[b] .. k_off[b] + k_cnt[b] - 1,
+    const int* k_cnt;                  // all valid (kmask unused); sk is then the maximum over the batch (shared-memory sizing)
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -65,18 +67,21 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
     constexpr int ATT_QT = NW * 16;
     constexpr int ATT_THREADS = NW * 32;
     extern __shared__ __align__(16) uint8_t att_smem[];
-    const int sk_pad = (p.sk + 63) & ~63;
+    const int b = blockIdx.z;
     __half* sK = reinterpret_cast<__half*>(att_smem);
     __half* sV = sK + static_cast<size_t>(ATT_NSTG * ATT_KT) * ATT_LD;
     __half* sQ = sV + static_cast<size_t>(ATT_NSTG * ATT_KT) * ATT_LD;
     float* sM = reinterpret_cast<float*>(sQ + ATT_QT * ATT_LD);
 
     pdl_wait();
+    const int sk = p.k_cnt ? p.k_cnt[b] : p.sk;               // keys of this episode
+    const int sk_pad = (sk + 63) & ~63;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * ATT_QT, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * ATT_QT, h = blockIdx.y;
     const __half* gq = p.q + (static_cast<size_t>(b) * p.q_rows) * p.ldq + h * ATT_DH;
-    const __half* gk = p.k + (static_cast<size_t>(b) * p.k_rows) * p.ldk + h * ATT_DH;
-    const __half* gv = p.v + (static_cast<size_t>(b) * p.k_rows) * p.ldv + h * ATT_DH;
+    const size_t krow0 = p.k_off ? static_cast<size_t>(p.k_off[b]) : static_cast<size_t>(b) * p.k_rows;
+    const __half* gk = p.k + krow0 * p.ldk + h * ATT_DH;
+    const __half* gv = p.v + krow0 * p.ldv + h * ATT_DH;
 
     // stage the Q tile with the first key tile, then K, V in 64-key cp.async groups; rows past the end are zero-filled
     for (int i = tid; i < ATT_QT * 8; i += ATT_THREADS) {
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
             const int r = kt * ATT_KT + (i >> 3), u = i & 7;
             __half* dk = sK + (slot * ATT_KT + (i >> 3)) * ATT_LD + u * 8;
             __half* dv = sV + (slot * ATT_KT + (i >> 3)) * ATT_LD + u * 8;
-            if (r < p.sk) {
+            if (r < sk) {
                 cp_async_16(smem_u32(dk), gk + static_cast<size_t>(r) * p.ldk + u * 8);
                 cp_async_16(smem_u32(dv), gv + static_cast<size_t>(r) * p.ldv + u * 8);
             } else {
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
     for (int kt = 0; kt < n_kt && kt < ATT_NSTG; ++kt) issue_tile(kt);
     for (int j = tid; j < sk_pad; j += ATT_THREADS) {
         float m = -INFINITY;                                   // keys past Sk never contribute
-        if (j < p.sk) m = p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg;
+        if (j < sk) m = p.k_off ? 0.0f : (p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg);
         sM[j] = m;
     }
     // first group (Q + key tile 0) must have landed before the Q fragments are read
@@ -251,13 +256,44 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     p.q = reinterpret_cast<const __half*>(q); p.k = reinterpret_cast<const __half*>(k);
     p.v = reinterpret_cast<const __half*>(v); p.o = reinterpret_cast<__half*>(o);
     p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.q_rows = q_rows; p.k_rows = k_rows;
-    p.kmask = kmask; p.mask_neg = mask_neg; p.sq = sq; p.sk = sk; p.scale = scale;
+    p.kmask = kmask; p.mask_neg = mask_neg; p.sq = sq; p.sk = sk; p.scale = scale; p.k_off = nullptr; p.k_cnt = nullptr;
     const int sk_pad = (sk + 63) & ~63;
     // 8 warps (128 query rows per CTA) halve the K/V re-reads of long query sequences; 4 warps otherwise
     const int nw = (sq > 64) ? 8 : 4;
     const int qt = nw * 16;
     const int smem = (2 * ATT_NSTG * ATT_KT + qt) * ATT_LD * 2 + sk_pad * 4;
     if (smem > 227 * 1024) return GRIDMM_ERR_SHAPE;
+    dim3 grid((sq + qt - 1) / qt, heads, batch);
+    if (nw == 8) {
+        GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GMM_CUDA_CHECK(launch_pdl(attn_kernel<8>, grid, dim3(256), smem, stream, p));
+    } else {
+        GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GMM_CUDA_CHECK(launch_pdl(attn_kernel<4>, grid, dim3(128), smem, stream, p));
+    }
+    gridmm_count_launch(1);
+    return 0;
+}
+
+// Attention over a PACKED context (gridmm_kv_index): the keys / values of episode b are rows k_off[b] .. k_off[b] + k_cnt[b] - 1 of
+// k / v and all of them are valid, so no key mask is applied (a masked key contributes exp(-10000) = 0 in fp32: dropping it is
+// exact).  max_sk >= max_b k_cnt[b] sizes the shared memory.  Always the mma.sync kernel (query tiles of 64 / 128 rows).
+extern "C" int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
+                                           const int* k_off, const int* k_cnt, int max_sk, void* o, int ldo, int batch, int heads,
+                                           int sq, float scale, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0 || sq <= 0) return 0;
+    if (!q || !k || !v || !o || !k_off || !k_cnt) return GRIDMM_ERR_ARG;
+    if (max_sk <= 0 || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return GRIDMM_ERR_SHAPE;
+    AttnParams p;
+    p.q = reinterpret_cast<const __half*>(q); p.k = reinterpret_cast<const __half*>(k);
+    p.v = reinterpret_cast<const __half*>(v); p.o = reinterpret_cast<__half*>(o);
+    p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.q_rows = q_rows; p.k_rows = 0;
+    p.kmask = nullptr; p.mask_neg = 0.0f; p.sq = sq; p.sk = max_sk; p.scale = scale; p.k_off = k_off; p.k_cnt = k_cnt;
+    const int sk_pad = (max_sk + 63) & ~63;
+    const int nw = (sq > 64) ? 8 : 4;
+    const int qt = nw * 16;
+    const int smem = (2 * ATT_NSTG * ATT_KT + qt) * ATT_LD * 2 + sk_pad * 4;
     dim3 grid((sq + qt - 1) / qt, heads, batch);
     if (nw == 8) {
         GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

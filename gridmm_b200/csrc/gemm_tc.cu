@@ -40,6 +40,7 @@ struct GemmEpilogue {
     const float* gw2;        // [groups * N] gamma * w2 of every head (indexed like bias), cls mode only
     float* cls_part;         // [rows][N / 64][3]: sum r, sum r^2, sum r * gw2 with r = act(acc + bias), or null
     float* cls_raw;          // [rows][N] plain products of the mode-1 tiles (K-split halves of sap_fuse_linear), or null
+    const int* m_dev;        // optional device-side row count (<= M): packed / ragged operands whose size only the GPU knows
     long long* dbg;          // optional [grid][8] cycle counters (tools/microbench.py), null in production
 };
 
@@ -108,8 +109,6 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int lane = threadIdx.x & 31;
     const int num_kb = K / BK;
     const int tiles_n = N / BN;
-    const int tiles_m = (M + TILE_M - 1) / TILE_M;
-    const int num_tiles = tiles_m * tiles_n;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader: owns the full barriers and issues the MMAs
     const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
@@ -135,6 +134,9 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched only below
+    if (ep.m_dev) M = min(M, __ldg(ep.m_dev));      // packed operand: the row count lives on the device
+    const int tiles_m = (M + TILE_M - 1) / TILE_M;
+    const int num_tiles = tiles_m * tiles_n;
 
     if (warp == 0) {
         {   // the whole (converged) warp runs the schedule, one elected lane issues: see elect_one() in common.cuh
@@ -447,7 +449,7 @@ static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, 
                          const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
                          int act, void* out_lanes, int lanes_rows, cudaStream_t stream, const int* grp = nullptr,
                          const float* gw2 = nullptr, float* cls_part = nullptr, long long a_rows = 0, long long w_rows = 0,
-                         float* cls_raw = nullptr) {
+                         float* cls_raw = nullptr, const int* m_dev = nullptr) {
     using namespace gmm;
     if (M <= 0) return 0;
     if (N % 128 != 0 || K % GEMM_KATOM != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
@@ -460,7 +462,7 @@ static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, 
         GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act,
-                    reinterpret_cast<__half*>(out_lanes), lanes_rows, grp, gw2, cls_part, cls_raw, g_gemm_dbg};
+                    reinterpret_cast<__half*>(out_lanes), lanes_rows, grp, gw2, cls_part, cls_raw, m_dev, g_gemm_dbg};
     if (grp) {
         // grouped heads: 128 x 128 tiles, one CTA each (row tiles address A / W / outputs through the table; the tensor maps
         // span all A rows and all stacked weight rows)
@@ -527,4 +529,14 @@ extern "C" int gridmm_cls_heads_f16(const void* a, int lda, long long a_rows, co
     if (!grp || !gw2 || !cls_part || !cls_raw || groups < 1) return GRIDMM_ERR_ARG;
     return gemm_dispatch(a, lda, w, ldw, tiles_m * 128, N, K, bias, nullptr, 0, nullptr, 0, nullptr, 0, 2, nullptr, 0, stream, grp, gw2,
                          cls_part, a_rows, static_cast<long long>(groups) * N, cls_raw);
+}
+
+// gridmm_linear_f16 over the first *m_dev rows only (m_dev: device int, <= M): for packed operands whose row count is computed on
+// the GPU (the fusion encoder's context without its masked rows, gridmm_kv_index).  The launch is sized for M; CTAs without
+// tiles exit at once.
+extern "C" int gridmm_linear_f16_rows(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
+                                      void* out_f16, int ld_f16, const int* m_dev, cudaStream_t stream) {
+    if (!m_dev) return GRIDMM_ERR_ARG;
+    return gemm_dispatch(a, lda, w, ldw, M, N, K, bias, nullptr, 0, nullptr, 0, out_f16, ld_f16, 0, nullptr, 0, stream, nullptr, nullptr,
+                         nullptr, 0, 0, nullptr, m_dev);
 }

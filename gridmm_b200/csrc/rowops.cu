@@ -92,7 +92,58 @@ struct FusionInParams {
     float* x32; __half* x16; __half* kv16;      // [B, Q, 768] x2, [B, KC, 768]
     uint8_t* kv_mask; uint8_t* q_mask;          // [B, KC], [B, Q]
     int B, S, L, G, V;
+    const int* kv_pos;                          // [B, KC] packed row of every VALID context row (-1: masked), or null = unpacked
 };
+
+// Packed ("ragged") context index for the fusion encoder: masked context rows (empty grid-cell slots, padded text) get no K/V
+// projection and no attention work.  kv_off[b] = number of valid rows of the episodes before b,
+// kv_cnt[b] = valid rows of b, kv_pos[b, r] = kv_off[b] + rank of row r among b's valid rows (or -1), kv_off[B] = total.
+__global__ void __launch_bounds__(1024) kv_index_kernel(const uint8_t* map_mask, const uint8_t* txt_mask, int S, int L, int B,
+                                                        int* kv_pos, int* kv_off, int* kv_cnt) {
+    // ONE CTA, one warp per episode (round-robin): count with ballots, scan the counts, then write the packed positions
+    extern __shared__ int s_cnt[];          // [B + 1]
+    pdl_wait();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    const int KC = S + L;
+    for (int b = warp; b < B; b += nwarps) {
+        int cnt = 0;
+        for (int r0 = 0; r0 < KC; r0 += 32) {
+            const int r = r0 + lane;
+            const bool valid = r < KC && ((r < S) ? map_mask[b * S + r] : txt_mask[b * L + (r - S)]) != 0;
+            cnt += __popc(__ballot_sync(0xffffffffu, valid));
+        }
+        if (lane == 0) s_cnt[b] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {                        // exclusive scan of the counts (B <= a few hundred)
+        int run = 0;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int b = b0 + lane;
+            const int c = b < B ? s_cnt[b] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (b < B) { kv_off[b] = run + incl - c; kv_cnt[b] = c; s_cnt[b] = run + incl - c; }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) kv_off[B] = run;
+    }
+    __syncthreads();
+    for (int b = warp; b < B; b += nwarps) {
+        int rank = s_cnt[b];
+        for (int r0 = 0; r0 < KC; r0 += 32) {
+            const int r = r0 + lane;
+            const bool valid = r < KC && ((r < S) ? map_mask[b * S + r] : txt_mask[b * L + (r - S)]) != 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (r < KC) kv_pos[b * KC + r] = valid ? rank + __popc(bal & ((1u << lane) - 1u)) : -1;
+            rank += __popc(bal);
+        }
+    }
+    pdl_launch_dependents();
+}
 
 __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
     pdl_wait();
@@ -106,7 +157,8 @@ __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
                                      : p.txt32 + (static_cast<size_t>(b) * p.L + (r - p.S)) * HID;
 #pragma unroll
         for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
-        store_row(v, nullptr, p.kv16 + static_cast<size_t>(row) * HID, lane);
+        const int prow = p.kv_pos ? p.kv_pos[row] : row;
+        if (prow >= 0) store_row(v, nullptr, p.kv16 + static_cast<size_t>(prow) * HID, lane);
         if (lane == 0) {
             p.kv_mask[row] = (r < p.S) ? p.map_mask[b * p.S + r] : p.txt_mask[b * p.L + (r - p.S)];
             for (int j = r; j < p.V; j += KC) p.q_mask[b * Q + p.G + j] = p.vp_mask[b * p.V + j];
@@ -499,17 +551,30 @@ extern "C" int gridmm_copy_rows(const float* x, int ldx, int in_rows_per_b, int 
     return 0;
 }
 
+extern "C" int gridmm_kv_index(const unsigned char* map_mask, const unsigned char* txt_mask, int batch, int S, int L, int* kv_pos,
+                               int* kv_off, int* kv_cnt, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (S < 1 || L < 1 || S + L > 1024) return GRIDMM_ERR_SHAPE;
+    if (!map_mask || !txt_mask || !kv_pos || !kv_off || !kv_cnt) return GRIDMM_ERR_ARG;
+    if (batch > 8192) return GRIDMM_ERR_SHAPE;
+    GMM_CUDA_CHECK(launch_pdl(kv_index_kernel, dim3(1), dim3(1024), (batch + 1) * sizeof(int), stream, map_mask, txt_mask, S, L, batch, kv_pos,
+                              kv_off, kv_cnt));
+    gridmm_count_launch(1);
+    return 0;
+}
+
 extern "C" int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned char* map_mask,
                                     const unsigned char* txt_mask, const unsigned char* gmap_mask, const unsigned char* vp_mask,
-                                    float* x32, void* x16, void* kv16, unsigned char* kv_mask, unsigned char* q_mask, int batch,
-                                    int S, int L, int G, int V, int hidden, cudaStream_t stream) {
+                                    float* x32, void* x16, void* kv16, unsigned char* kv_mask, unsigned char* q_mask,
+                                    const int* kv_pos, int batch, int S, int L, int G, int V, int hidden, cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0) return 0;
     if (hidden != HID || S < G || L < 1 || G < 1 || V < 1) return GRIDMM_ERR_SHAPE;
     if (!map32 || !txt32 || !map_mask || !txt_mask || !gmap_mask || !vp_mask || !x32 || !x16 || !kv16 || !kv_mask || !q_mask)
         return GRIDMM_ERR_ARG;
     FusionInParams p{map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, reinterpret_cast<__half*>(x16),
-                     reinterpret_cast<__half*>(kv16), kv_mask, q_mask, batch, S, L, G, V};
+                     reinterpret_cast<__half*>(kv16), kv_mask, q_mask, batch, S, L, G, V, kv_pos};
     const int rows = batch * (S + L + G);
     GMM_CUDA_CHECK(launch_pdl(fusion_inputs_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, p));
     gridmm_count_launch(1);

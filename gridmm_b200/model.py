@@ -421,17 +421,22 @@ class GlocalTextPathNavCMT(nn.Module):
         ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
                       self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
 
-    def _cross_post(self, x32, x16, pre, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag):
-        """BertXAttention (vilmodel.py:317-379): x = LN(Wo attn(q = x, kv = ctx) + x)."""
+    def _cross_post(self, x32, x16, pre, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None):
+        """BertXAttention (vilmodel.py:317-379): x = LN(Wo attn(q = x, kv = ctx) + x).
+        ctx_var = (k_off, k_cnt): the context is packed (masked rows removed, gridmm_kv_index), no key mask is needed."""
         q = self.buf("q16_" + tag, (B * S, HID), torch.float16)
         ops.linear(x16, self.W16(pre + ".att.query.weight"), self.B32(pre + ".att.query.bias"), out_f16=q)
-        a = self._attention(q, ctx_k, ctx_v, ctx_mask, NEG_BERT, B, S, Sk, "att16_" + tag)
+        if ctx_var is not None:
+            a = self.buf("att16_" + tag, (B * S, HID), torch.float16)
+            ops.attention_varlen(q, ctx_k, ctx_v, a, ctx_var[0], ctx_var[1], Sk, B, HEADS, S)
+        else:
+            a = self._attention(q, ctx_k, ctx_v, ctx_mask, NEG_BERT, B, S, Sk, "att16_" + tag)
         ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
                       self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
 
-    def _lxrt_layer(self, pre, x32, x16, x_mask, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag):
+    def _lxrt_layer(self, pre, x32, x16, x_mask, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None):
         """GraphLXRTXLayer.forward (vilmodel.py:399-414): cross-attention, self-attention, FFN (all post-norm)."""
-        self._cross_post(x32, x16, pre + ".visual_attention", ctx_k, ctx_v, ctx_mask, B, S, Sk, tag)
+        self._cross_post(x32, x16, pre + ".visual_attention", ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=ctx_var)
         self._self_post(x32, x16, pre + ".visn_self_att", x_mask, B, S, tag)
         self._ffn_post(x32, x16, pre + ".visn_inter", pre + ".visn_output", B * S, tag)
 
@@ -642,21 +647,28 @@ class GlocalTextPathNavCMT(nn.Module):
             inter["map_masks"] = map_mask.clone()
 
         # ---- fusion encoder: queries [gmap'; vp], context [map; txt]  (vilmodel.py:843-856)
-        kv16 = self.buf("kv16", (B * KC, HID), f16)
+        # The context is PACKED: masked rows (empty grid-cell slots, padded text: ~1/3 of the 296 rows per episode) get no K/V
+        # projection and no attention work; their attention weight would be exp(-10000) = 0 anyway.
+        kv16 = self.buf("kv16", (B * KC, HID), f16, zero=True)
         kv_mask = self.buf("kv_mask", (B, KC), u8)
         q_mask = self.buf("q_mask", (B, Q), u8)
-        ops.fusion_inputs(map32, txt32, map_mask, txt_mask_u8, gmap_mask_u8, vp_mask_u8, x32, x16, kv16, kv_mask, q_mask, B, S, L, G, V)
+        kv_pos = self.buf("kv_pos", (B * KC,), torch.int32)
+        kv_off = self.buf("kv_off", (B + 1,), torch.int32)
+        kv_cnt = self.buf("kv_cnt", (B,), torch.int32)
+        ops.kv_index(map_mask, txt_mask_u8, kv_pos, kv_off, kv_cnt, B, S, L)
+        ops.fusion_inputs(map32, txt32, map_mask, txt_mask_u8, gmap_mask_u8, vp_mask_u8, x32, x16, kv16, kv_mask, q_mask, B, S, L, G, V,
+                          kv_pos=kv_pos)
         nx = cfg.num_x_layers
         le = "local_encoder.encoder.x_layers.%d"
         names_w, names_b = [], []
         for i in range(nx):
             names_w += [(le % i) + ".visual_attention.att.key.weight", (le % i) + ".visual_attention.att.value.weight"]
             names_b += [(le % i) + ".visual_attention.att.key.bias", (le % i) + ".visual_attention.att.value.bias"]
-        kvp = self.buf("kvp16", (B * KC, 2 * HID * nx), f16)
-        ops.linear(kv16, self.W16(*names_w), self.B32(*names_b), out_f16=kvp)
+        kvp = self.buf("kvp16", (B * KC, 2 * HID * nx), f16, zero=True)
+        ops.linear_rows(kv16, self.W16(*names_w), self.B32(*names_b), kvp, kv_off[B:])
         for i in range(nx):
             self._lxrt_layer(le % i, x32, x16, q_mask, kvp[:, 2 * HID * i: 2 * HID * i + HID],
-                             kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], kv_mask, B, Q, KC, "x")
+                             kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], kv_mask, B, Q, KC, "x", ctx_var=(kv_off, kv_cnt))
 
         # ---- heads and logit fusion (vilmodel.py:859-907)
         if ce_maxc:

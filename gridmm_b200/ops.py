@@ -91,7 +91,33 @@ def map_inputs(proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, gmap_
               map_f16.data_ptr(), map_mask.data_ptr(), batch, n_cells, seq, HID, _lib.stream_ptr())
 
 
-def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16, kv16, kv_mask, q_mask, batch, S, L, G, V):
+def kv_index(map_mask, txt_mask, kv_pos, kv_off, kv_cnt, batch, S, L):
+    _chk(map_mask, torch.uint8, "map_mask"); _chk(txt_mask, torch.uint8, "txt_mask")
+    for t_ in (kv_pos, kv_off, kv_cnt):
+        _chk(t_, torch.int32, "kv index")
+    _lib.call("gridmm_kv_index", map_mask.data_ptr(), txt_mask.data_ptr(), batch, S, L, kv_pos.data_ptr(), kv_off.data_ptr(),
+              kv_cnt.data_ptr(), _lib.stream_ptr())
+
+
+def linear_rows(a16, w16, bias, out_f16, m_dev):
+    """linear() over the first m_dev[0] rows (device int32 tensor)."""
+    _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w"); _chk(bias, torch.float32, "bias"); _chk(out_f16, torch.float16, "out_f16")
+    _chk(m_dev, torch.int32, "m_dev")
+    M, K = a16.shape
+    _lib.call("gridmm_linear_f16_rows", a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, w16.shape[0], K, _lib.ptr(bias),
+              out_f16.data_ptr(), out_f16.stride(0), m_dev.data_ptr(), _lib.stream_ptr())
+
+
+def attention_varlen(q, k, v, out, k_off, k_cnt, max_sk, batch, heads, sq, q_rows=None):
+    for t_, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t_, torch.float16, n)
+    _chk(k_off, torch.int32, "k_off"); _chk(k_cnt, torch.int32, "k_cnt")
+    _lib.call("gridmm_attention_varlen_f16", q.data_ptr(), q.stride(0), q_rows or sq, k.data_ptr(), k.stride(0), v.data_ptr(),
+              v.stride(0), k_off.data_ptr(), k_cnt.data_ptr(), max_sk, out.data_ptr(), out.stride(0), batch, heads, sq,
+              1.0 / math.sqrt(64.0), _lib.stream_ptr())
+
+
+def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16, kv16, kv_mask, q_mask, batch, S, L, G, V, kv_pos=None):
     for t_, n in ((map_mask, "map_mask"), (txt_mask, "txt_mask"), (gmap_mask, "gmap_mask"), (vp_mask, "vp_mask"), (kv_mask, "kv_mask"),
                   (q_mask, "q_mask")):
         _chk(t_, torch.uint8, n)
@@ -100,8 +126,8 @@ def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16
     for t_ in (map32, txt32, x32, x16, kv16, map_mask, txt_mask, gmap_mask, vp_mask, kv_mask, q_mask):
         assert t_.is_contiguous()
     _lib.call("gridmm_fusion_inputs", map32.data_ptr(), txt32.data_ptr(), map_mask.data_ptr(), txt_mask.data_ptr(), gmap_mask.data_ptr(),
-              vp_mask.data_ptr(), x32.data_ptr(), x16.data_ptr(), kv16.data_ptr(), kv_mask.data_ptr(), q_mask.data_ptr(), batch, S, L, G, V,
-              HID, _lib.stream_ptr())
+              vp_mask.data_ptr(), x32.data_ptr(), x16.data_ptr(), kv16.data_ptr(), kv_mask.data_ptr(), q_mask.data_ptr(), _lib.ptr(kv_pos),
+              batch, S, L, G, V, HID, _lib.stream_ptr())
 
 
 def split_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_f16, k_total):

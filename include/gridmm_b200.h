@@ -115,12 +115,28 @@ int gridmm_map_inputs(const float* proj, const float* pos_fts, const int* cell_r
                       const float* norm_gamma, const float* norm_beta, float norm_eps, float* map_f32, void* map_f16,
                       unsigned char* map_mask, int batch, int n_cells, int seq, int hidden, cudaStream_t stream);
 
+/* ---- packed ("ragged") fusion-encoder context: masked context rows (empty grid-cell slots, padded text) are dropped before the
+ * K/V projection of the 4 fusion layers and before their cross-attention (vilmodel.py:843-853; a masked key has weight
+ * exp(-10000) = 0 in fp32, so the result is the same).
+ * gridmm_kv_index: kv_off[b] = valid rows of episodes < b (kv_off[batch] = total), kv_cnt[b], kv_pos[b, r] = packed row or -1,
+ *   for the context [map (S rows, map_mask) ; txt (L rows, txt_mask)]; S + L <= 1024.
+ * gridmm_linear_f16_rows: gridmm_linear_f16 (fp16 output) over the first *m_dev rows only (m_dev on the device, <= M).
+ * gridmm_attention_varlen_f16: attention whose keys / values of episode b are rows k_off[b] .. + k_cnt[b] of k / v, all valid. */
+int gridmm_kv_index(const unsigned char* map_mask, const unsigned char* txt_mask, int batch, int S, int L, int* kv_pos, int* kv_off,
+                    int* kv_cnt, cudaStream_t stream);
+int gridmm_linear_f16_rows(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, void* out_f16,
+                           int ld_f16, const int* m_dev, cudaStream_t stream);
+int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
+                                const int* k_off, const int* k_cnt, int max_sk, void* o, int ldo, int batch, int heads, int sq,
+                                float scale, cudaStream_t stream);
+
 /* Inputs of the fusion encoder (vilmodel.py:843-850) in one launch: x[b, :G] = map[b, S-G:] (fp32 + fp16; rows G.. of x hold the
- * vp tokens already), kv16[b] = fp16([map[b] ; txt[b]]), kv_mask = [map_mask ; txt_mask], q_mask = [gmap_mask ; vp_mask]. */
+ * vp tokens already), kv16[b] = fp16([map[b] ; txt[b]]) -- or, with kv_pos (gridmm_kv_index), only the valid rows at their packed
+ * positions --, kv_mask = [map_mask ; txt_mask], q_mask = [gmap_mask ; vp_mask]. */
 int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned char* map_mask, const unsigned char* txt_mask,
                          const unsigned char* gmap_mask, const unsigned char* vp_mask, float* x32, void* x16, void* kv16,
-                         unsigned char* kv_mask, unsigned char* q_mask, int batch, int S, int L, int G, int V, int hidden,
-                         cudaStream_t stream);
+                         unsigned char* kv_mask, unsigned char* q_mask, const int* kv_pos, int batch, int S, int L, int G, int V,
+                         int hidden, cudaStream_t stream);
 
 /* ---- action heads (vilmodel.py:663-674, 859-907) in three launches ------------------------------------------
  * ClsPrediction = Linear, ReLU, LayerNorm(1e-12), Linear(768 -> 1):  logit = rstd * (S3 - mean * c1) + c0 with r = ReLU(xW + b),

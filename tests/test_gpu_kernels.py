@@ -353,3 +353,46 @@ def test_pool_handmade_cells(sizes):
             assert err < 6e-3, "b=%d cell=%d n=%d err=%.3e" % (b, c, len(idx), err)
     assert pooled[1].abs().max().item() == 0
 
+
+
+def test_kv_index_and_varlen_attention():
+    """Packed fusion context: gridmm_kv_index positions, and attention over the packed keys == masked attention over the padded ones."""
+    from gridmm_b200 import ops
+    B, S, L, Sq = 5, 216, 80, 57
+    KC = S + L
+    g = torch.Generator().manual_seed(9)
+    map_mask = (torch.rand(B, S, generator=g) < 0.6).to(torch.uint8); map_mask[:, -3:] = 1
+    txt_mask = (torch.arange(L)[None, :] < torch.randint(20, L + 1, (B, 1), generator=g)).to(torch.uint8)
+    dev = _dev()
+    kv_pos = torch.zeros(B * KC, dtype=torch.int32, device=dev); kv_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    kv_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    ops.kv_index(map_mask.to(dev), txt_mask.to(dev), kv_pos, kv_off, kv_cnt, B, S, L)
+    full = torch.cat([map_mask, txt_mask], 1).flatten().bool()
+    want_pos = torch.where(full, torch.cumsum(full.int(), 0) - 1, torch.full_like(full.int(), -1))
+    assert torch.equal(kv_pos.cpu(), want_pos.int())
+    cnt = torch.cat([map_mask, txt_mask], 1).sum(1).int()
+    assert torch.equal(kv_cnt.cpu(), cnt) and int(kv_off[-1]) == int(cnt.sum())
+    assert torch.equal(kv_off[:-1].cpu(), (torch.cumsum(cnt, 0) - cnt).int())
+    # attention: padded + mask vs packed
+    q = torch.randn(B * Sq, 768, generator=g).half().to(dev)
+    kv = torch.randn(B * KC, 1536, generator=g).half().to(dev)
+    kmask = torch.cat([map_mask, txt_mask], 1).to(dev)
+    ref = torch.empty(B * Sq, 768, device=dev, dtype=torch.float16)
+    ops.attention(q, kv[:, :768], kv[:, 768:], ref, kmask, -10000.0, B, 12, Sq, KC)
+    packed = torch.zeros_like(kv)
+    packed[: int(cnt.sum())] = kv[full.to(dev)]
+    out = torch.empty_like(ref)
+    ops.attention_varlen(q, packed[:, :768], packed[:, 768:], out, kv_off, kv_cnt, KC, B, 12, Sq)
+    torch.cuda.synchronize()
+    assert (out.float() - ref.float()).abs().max().item() < 2e-3
+    # GEMM over the first kv_off[B] rows only
+    w = (torch.randn(256, 1536, generator=g) * 0.05).half().to(dev)
+    bias = torch.randn(256, generator=g).to(dev)
+    o = torch.full((B * KC, 256), 7.0, device=dev, dtype=torch.float16)
+    ops.linear_rows(packed, w, bias, o, kv_off[B:])
+    torch.cuda.synchronize()
+    n = int(cnt.sum())
+    want = packed[:n].float() @ w.float().t() + bias
+    assert (o[:n].float() - want).abs().max().item() < 4e-3 * max(1.0, want.abs().max().item())
+    tail = ((n + 255) // 256) * 256           # rows of tiles that hold no valid row stay untouched
+    assert (o[tail:] == 7.0).all()
