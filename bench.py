@@ -348,15 +348,16 @@ def kernel_breakdown(step, n=5):
     return {k: (t / n, c / n) for k, (t, c) in agg.items()}
 
 
-def gemm_flops_per_step():
-    """Algorithmic FLOPs (2mnk) of every gridmm_linear_f16 launch of one step (padded shapes as launched: S = 196 + G)."""
+def gemm_flops_per_step(kv_rows=None):
+    """Algorithmic FLOPs (2mnk) of every tcgen05 GEMM launch of one step (padded shapes as launched: S = 196 + G; the fusion
+    encoder's K/V projection over the `kv_rows` packed context rows it actually processes)."""
     H, I = 768, 3072
     S, Q, KC = 196 + G, G + 1 + VIEWS, 196 + G + L
     mm = lambda m, n, k: 2.0 * m * n * k   # noqa: E731
     f = mm(B * L, H, H) + mm(B * 196, H, H)                                            # text_proj, grid_proj
     f += mm(B * S, 3 * H, H) + mm(B * S, H, H) + mm(B * S, I, H) + mm(B * S, H, I)      # grid_encoder
     f += mm(B * L, 2 * H, H) + mm(B * S, H, H) * 2 + mm(B * S, 3 * H, H) + mm(B * S, H, H) + mm(B * S, I, H) + mm(B * S, H, I)
-    f += mm(B * KC, 8 * H, H)                                                            # fusion K/V of 4 layers
+    f += mm(kv_rows if kv_rows is not None else B * KC, 8 * H, H)                        # fusion K/V of 4 layers
     f += 4 * (mm(B * Q, H, H) * 2 + mm(B * Q, 3 * H, H) + mm(B * Q, H, H) + mm(B * Q, I, H) + mm(B * Q, H, I))
     f += mm(B * G, H, H) * 2 + mm(B * (1 + VIEWS), H, H) + mm(B, H, 2 * H)               # heads (algorithmic: the 3-term fp16 split
     #                                                                                      and the 128-row padding are not counted)
@@ -454,10 +455,12 @@ def main():
         total_k = sum(t for t, _ in br.values())
         # dominant kernel class by share of the step: the tcgen05 GEMMs (plain, + residual/LayerNorm epilogue, grouped heads,
         # text_proj into the pooling layout -- the same mainloop with different epilogues)
-        gemm_eps = ("gridmm_linear_f16", "gridmm_linear_ln_f16", "gridmm_cls_heads_f16", "gridmm_linear_f16_lanes")
+        gemm_eps = ("gridmm_linear_f16", "gridmm_linear_ln_f16", "gridmm_cls_heads_f16", "gridmm_linear_f16_lanes",
+                    "gridmm_linear_f16_rows")
         g_ms = sum(br.get(k, (0.0, 0))[0] for k in gemm_eps)
         g_n = sum(br.get(k, (0.0, 0))[1] for k in gemm_eps)
-        flops = gemm_flops_per_step()
+        kv_rows = int(step.model.buf("kv_off", (B + 1,), torch.int32)[B].item())      # packed context rows of this batch
+        flops = gemm_flops_per_step(kv_rows)
         tf = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         traffic = {}
         try:
@@ -468,7 +471,7 @@ def main():
                     "bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
                     "traffic": traffic.get("gemm_bytes_per_step"),
                     "peak_source": peak_src + ", sustained bf16/fp16 dense", "share_of_step": g_ms / total_k if total_k else None,
-                    "algorithmic_flops_per_step": flops, "ms": g_ms}
+                    "algorithmic_flops_per_step": flops, "ms": g_ms, "packed_context_rows": kv_rows}
         # the HBM-bound pooling kernel (north_star's "grid scatter/pool"): bytes that must move / its duration
         p_ms, _ = br.get("gridmm_pool", (0.0, 0))
         gridb = step.builder

@@ -8,6 +8,7 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 600 python tools/microbench2.py > gpurun_out/microbench29.log 2>&1; echo "micro exit=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1c.csv python tools/prof_pool.py > gpurun_out/ncu_l29.log 2>&1; echo "ncu launches exit=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"pool_kernel" -s 2 -c 1 -o gpurun_out/prof_r1c_pool -f python tools/prof_pool.py > gpurun_out/ncu_f29a.log 2>&1; echo "ncu pool exit=$?"
-timeout 900 ncu --set full --clock-control none -k regex:"gemm_f16|gemm_ln|attn_kernel|head_rows|nav_logits2|fusion_inputs|grid_update|embed_kernel|grid_assemble|layernorm" -s 124 -c 62 -o /tmp/prof_r1c_all -f python tools/prof_pool.py > gpurun_out/ncu_f29b.log 2>&1; echo "ncu all exit=$?"
+timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"gmm::" -s 125 -c 59 -o /tmp/prof_r1c_all -f python tools/prof_pool.py > gpurun_out/ncu_f29b.log 2>&1; echo "ncu all exit=$?"
 ncu -i /tmp/prof_r1c_all.ncu-rep --page raw --csv > gpurun_out/prof_r1c_all_raw.csv 2>/dev/null
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"attn_tc_kernel" -s 6 -c 2 -o gpurun_out/prof_r1c_attn_tc -f python tools/prof_pool.py > gpurun_out/ncu_f29c.log 2>&1; echo "ncu attn exit=$?"
 du -sh gpurun_out
