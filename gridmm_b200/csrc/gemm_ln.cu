@@ -11,7 +11,8 @@
 // A LayerNorm row needs all 768 output columns, which is more fp32 accumulator columns than one SM's tensor memory holds
 // (512).  A CLUSTER of CL CTAs therefore shares one 128-row tile: CTA r accumulates columns [r*768/CL, (r+1)*768/CL) in its
 // own TMEM (CL = 2: 384 columns, two N=192 MMAs per K step; CL = 6: 128 columns -- picked by problem size so that
-// small-M problems still spread over ~90 SMs).  In the epilogue every thread owns one row of its CTA's slice:
+// small-M problems still spread over ~90 SMs; CL = 4 = two cta_group::2 PAIRS, 256 rows x 384 columns per pair, for the
+// map-sized problems).  In the epilogue every thread owns one row of its CTA's slice:
 //   pass 1  v = acc + bias + residual (the residual arrives coalesced through a per-warp shared-memory transpose), written
 //           back into TMEM; per-thread mean and M2 over its columns
 //   merge   (mean, M2) partials of the 2*CL column slices of a row are exchanged through DISTRIBUTED SHARED MEMORY
@@ -42,12 +43,16 @@ struct LnEpilogue {
     int f32_raw;             // 1: out_f32 receives v (pre-norm residual stream), 0: the normalised y
 };
 
-template <int CL>
+// PAIR: the cluster is 4 CTAs = two cta_group::2 pairs.  A pair owns 256 rows x 384 columns (each CTA: its 128 rows of A, HALF of
+// the pair's W tile, 128 x 384 accumulators in its own TMEM); the two pairs hold the two column halves of the same 256 rows.
+// Per CTA and k-block 16 KB of A + 24 KB of W arrive instead of 16 + 48: 153 flop per delivered byte instead of 96.
+template <int CL, bool PAIR>
 struct LnSmem {
-    static constexpr int BN = LN_N / CL;
-    static constexpr int STAGES = (CL == 2) ? 3 : 6;
+    static constexpr int BN = PAIR ? 384 : LN_N / CL;           // accumulator columns per CTA
+    static constexpr int BROWS = PAIR ? BN / 2 : BN;            // W rows this CTA stages per k-block
+    static constexpr int STAGES = PAIR ? 4 : ((CL == 2) ? 3 : 6);
     static constexpr int A_BYTES = LN_BM * 128;                 // 128 rows x 64 fp16
-    static constexpr int B_BYTES = BN * 128;
+    static constexpr int B_BYTES = BROWS * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;     // full, empty, a_empty [STAGES each], tmem_full, tmem slot
     static constexpr int VEC_OFFSET = BAR_OFFSET + 256;         // bias, gamma, beta slices: 3 x BN floats
@@ -78,16 +83,22 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// cta_group::2 commit arriving on the mbarrier at this offset in the CTAs of `mask` (the two CTAs of the issuing pair)
+__device__ __forceinline__ void umma_commit_2sm_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ float2 ld_cluster_f2(uint32_t cluster_addr) {
     float2 v;
     asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr));
     return v;
 }
 
-template <int CL>
+template <int CL, bool PAIR>
 __global__ void __launch_bounds__(LN_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int M, int K, LnEpilogue ep) {
-    using L = LnSmem<CL>;
+    using L = LnSmem<CL, PAIR>;
+    static_assert(!PAIR || CL == 4, "pair mode: two CTA pairs per cluster");
     constexpr int BN = L::BN, STAGES = L::STAGES;
     constexpr int NMMA = (BN > 256) ? 2 : 1;          // UMMA N <= 256
     constexpr int MMA_N = BN / NMMA;
@@ -107,8 +118,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int m0 = (blockIdx.x / CL) * LN_BM;
-    const int n0 = static_cast<int>(rank) * BN;
+    const uint32_t lr = PAIR ? (rank & 1u) : 0u;                 // row half inside the pair's 256-row tile
+    const uint32_t leader = PAIR ? (rank & ~1u) : rank;          // CTA whose barriers collect the pair's loads and which issues the MMAs
+    const int m0 = (blockIdx.x / CL) * (PAIR ? 2 * LN_BM : LN_BM) + static_cast<int>(lr) * LN_BM;
+    const int n0 = static_cast<int>(PAIR ? (rank >> 1) : rank) * BN;
     const int num_kb = K / 64;
 
     if (warp == 0 && lane == 0) {
@@ -118,7 +131,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, L::TMEM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc_2sm(tmem_slot, L::TMEM_COLS); else tmem_alloc(tmem_slot, L::TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();      // every CTA's barriers exist before a peer's multicast load / commit can signal them
@@ -131,6 +144,22 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % STAGES;
             mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+            if (PAIR) {
+                // both CTAs of the pair load their own A rows and their half of every MMA's W rows; all bytes are counted on the
+                // LEADER's full barrier
+                if (elect_one()) {
+                    uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + L::A_BYTES;
+                    if (lr == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+                    const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[s]), leader);
+                    tma_load_2d_2sm(a_dst, &tmA, kb * 64, m0, lead_bar);
+#pragma unroll
+                    for (int j = 0; j < NMMA; ++j)
+                        tma_load_2d_2sm(b_dst + j * (MMA_N / 2) * 128, &tmW, kb * 64, n0 + j * MMA_N + static_cast<int>(lr) * (MMA_N / 2), lead_bar);
+                }
+                __syncwarp();
+                continue;
+            }
             if (elect_one()) {
                 uint8_t* b_dst = smem + s * L::STAGE_BYTES + L::A_BYTES;
                 mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);       // own W slice + the multicast A tile
@@ -151,8 +180,28 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         pdl_launch_dependents();      // all loads issued: the next kernel's prologue may overlap our MMA tail and epilogue
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
-        constexpr uint32_t idesc = umma_idesc_f16(LN_BM, MMA_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * LN_BM : LN_BM, MMA_N);
+        for (int kb = 0; PAIR && lr == 0 && kb < num_kb; ++kb) {      // pair mode: the leader issues for both CTAs
+            const int s = kb % STAGES;
+            mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem) + s * L::STAGE_BYTES;
+            if (elect_one()) {
+                const uint64_t da = umma_desc_sw128_kmajor(a_addr);
+                const uint16_t mask = static_cast<uint16_t>(3u << leader);
+#pragma unroll
+                for (int j = 0; j < NMMA; ++j) {
+                    const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES + j * (MMA_N / 2) * 128);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_ss_2sm(tmem_base + j * MMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit_2sm_mask(&empty_bar[s], mask);            // frees the stage in both CTAs of the pair
+                if (kb == num_kb - 1) umma_commit_2sm_mask(tmem_full_bar, mask);
+            }
+            __syncwarp();
+        }
+        for (int kb = 0; !PAIR && kb < num_kb; ++kb) {
             const int s = kb % STAGES;
             mbar_wait(&full_bar[s], (kb / STAGES) & 1);
             tc_fence_after();
@@ -269,22 +318,24 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int rsub = lane >> 2, csub = (lane & 3) * 4;
         const int row_base = m0 + q * 32 + rsub;
         const int colh = half * HALF;
-        // merge the 2*CL partials of this row (equal counts): mean = avg of means, M2 = sum M2_i + HALF * sum (mean_i - mean)^2
-        float2 part[2 * CL];
+        // merge the 2*NS partials of this row (equal counts): mean = avg of means, M2 = sum M2_i + HALF * sum (mean_i - mean)^2
+        // (NS column slices hold the row: every CTA of the cluster, or -- pair mode -- the CTAs with this CTA's row half)
+        constexpr int NS = PAIR ? 2 : CL;
+        float2 part[2 * NS];
         const uint32_t my_stat = smem_u32(s_stat + trow);
 #pragma unroll
-        for (int r = 0; r < CL; ++r) {
-            const uint32_t base = mapa_u32(my_stat, static_cast<uint32_t>(r));
+        for (int r = 0; r < NS; ++r) {
+            const uint32_t base = mapa_u32(my_stat, PAIR ? (lr + 2u * r) : static_cast<uint32_t>(r));
             part[2 * r] = ld_cluster_f2(base);
             part[2 * r + 1] = ld_cluster_f2(base + LN_BM * 8);
         }
         float mean = 0.f;
 #pragma unroll
-        for (int i = 0; i < 2 * CL; ++i) mean += part[i].x;
-        mean *= 1.0f / (2 * CL);
+        for (int i = 0; i < 2 * NS; ++i) mean += part[i].x;
+        mean *= 1.0f / (2 * NS);
         float m2 = 0.f, dev = 0.f;
 #pragma unroll
-        for (int i = 0; i < 2 * CL; ++i) { m2 += part[i].y; const float d = part[i].x - mean; dev = fmaf(d, d, dev); }
+        for (int i = 0; i < 2 * NS; ++i) { m2 += part[i].y; const float d = part[i].x - mean; dev = fmaf(d, d, dev); }
         const float var = (m2 + HALF * dev) * (1.0f / LN_N);
         s_fin[half * LN_BM + trow] = make_float2(mean, rsqrtf(var + ep.eps));
         __syncwarp();      // the 32 rows of this warp's quadrant are final (each half keeps its own copy)
@@ -337,23 +388,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, L::TMEM_COLS);
+        if (PAIR) tmem_dealloc_2sm(tmem_base, L::TMEM_COLS); else tmem_dealloc(tmem_base, L::TMEM_COLS);
     }
 }
 
-template <int CL>
+template <int CL, bool PAIR>
 static int launch_gemm_ln(const void* a, int lda, const void* w, int ldw, int M, int K, const LnEpilogue& ep, cudaStream_t stream) {
-    using L = LnSmem<CL>;
-    constexpr int BOXN = (L::BN > 256) ? L::BN / 2 : L::BN;
+    using L = LnSmem<CL, PAIR>;
+    constexpr int BOXN = PAIR ? L::BN / 4 : ((L::BN > 256) ? L::BN / 2 : L::BN);      // pair: half of an N = 192 MMA's W rows
     CUtensorMap tmA, tmW;
     int rc = make_tmap_f16_2d(&tmA, a, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda) * 2, 64, LN_BM);
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(LN_N), static_cast<uint64_t>(ldw) * 2, 64, BOXN);
     if (rc) return rc;
-    auto kern = gemm_ln_kernel<CL>;
+    auto kern = gemm_ln_kernel<CL, PAIR>;
     GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     GMM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    const int tiles_m = (M + LN_BM - 1) / LN_BM;
+    const int tiles_m = PAIR ? (M + 2 * LN_BM - 1) / (2 * LN_BM) : (M + LN_BM - 1) / LN_BM;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles_m * CL);
     cfg.blockDim = dim3(LN_THREADS);
@@ -377,7 +428,7 @@ static int launch_gemm_ln(const void* a, int lda, const void* w, int ldw, int M,
 }  // namespace gmm
 
 static int g_ln_cluster = 0;
-// Debug hook: force the cluster size (2 or 6) of gridmm_linear_ln_f16; 0 = automatic.
+// Debug hook: force the cluster size (2 or 6; 4 = two CTA pairs) of gridmm_linear_ln_f16; 0 = automatic.
 extern "C" void gridmm_debug_set_ln_cluster(int cl) { g_ln_cluster = cl; }
 
 extern "C" int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
@@ -399,9 +450,17 @@ extern "C" int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int l
     const int tiles_m = (M + LN_BM - 1) / LN_BM;
     const long long t2 = static_cast<long long>((tiles_m * 2 + sms - 1) / sms) * (384 + 128);
     const long long t6 = static_cast<long long>((tiles_m * 6 + sms - 1) / sms) * (128 + 128);
+    // two CTA pairs (cl = 4): same 384 accumulator columns per CTA as cl = 2, but 40 instead of 64 KB of operands per CTA and
+    // k-block (measured at M = 6912: K = 768 23.7 -> 22.9 us, K = 3072 42.9 -> 39.4 us; the rest of these kernels is the
+    // fp32 residual read + fp32/fp16 write of the epilogue, which is DRAM-bound)
+    const int tiles_m2 = (M + 2 * LN_BM - 1) / (2 * LN_BM);
+    const long long t4 = static_cast<long long>((tiles_m2 * 4 + sms - 1) / sms) * (346 + 128);
     int cl = (t2 <= t6) ? 2 : 6;
-    if (g_ln_cluster == 2 || g_ln_cluster == 6) cl = g_ln_cluster;
-    const int rc = (cl == 2) ? launch_gemm_ln<2>(a, lda, w, ldw, M, K, ep, stream) : launch_gemm_ln<6>(a, lda, w, ldw, M, K, ep, stream);
+    if (t4 < t2 && t4 < t6) cl = 4;
+    if (g_ln_cluster == 2 || g_ln_cluster == 6 || g_ln_cluster == 4) cl = g_ln_cluster;
+    const int rc = (cl == 4) ? launch_gemm_ln<4, true>(a, lda, w, ldw, M, K, ep, stream)
+                 : (cl == 2) ? launch_gemm_ln<2, false>(a, lda, w, ldw, M, K, ep, stream)
+                             : launch_gemm_ln<6, false>(a, lda, w, ldw, M, K, ep, stream);
     gridmm_count_launch(1);
     return rc;
 }

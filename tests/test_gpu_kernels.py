@@ -76,7 +76,8 @@ def test_linear_lanes_layout(B, L):
 
 
 @pytest.mark.parametrize("M,K,cl,raw", [(6912, 768, 2, False), (6912, 3072, 2, False), (1824, 768, 6, False), (1824, 3072, 6, True),
-                                        (300, 768, 0, True), (2560, 768, 0, False), (6913, 768, 0, False), (57, 3072, 2, True)])
+                                        (300, 768, 0, True), (2560, 768, 0, False), (6913, 768, 0, False), (57, 3072, 2, True),
+                                        (6912, 768, 4, False), (6912, 3072, 4, True), (300, 768, 4, False), (6913, 768, 4, True)])
 def test_linear_ln_fused(M, K, cl, raw):
     """GEMM + bias + residual + LayerNorm in one cluster kernel vs torch fp32 (in-place residual stream, as the model uses it)."""
     import ctypes

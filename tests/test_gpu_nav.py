@@ -325,3 +325,21 @@ def test_staged_features_two_batches_ping_pong():
             assert torch.equal(got, want[i][t]), "batch %d step %d" % (i, t)
     with pytest.raises(RuntimeError):
         gbs[0].step(eps[0]["depth_sub"][:, 0], None, eps[0]["pos"][:, 0], eps[0]["heading"][:, 0])     # nothing staged
+
+
+def test_nav_average_fusion():
+    """`--fusion avg` models have no sap_fuse_linear (vlnbert_init / vilmodel.py:859-866: fuse weight 0.5): the grouped head launch
+    then has no raw-product tiles and nav_logits2 gets no fuse inputs."""
+    B, T, L, G = 6, 3, 48, 14
+    ep_kw = dict(batch=B, steps=T, seed=314)
+    nav_kw = dict(txt_len=L, gmap_len=G, n_views=36, n_objs=0)
+    cfg = H.make_config(glocal_fuse=False)
+    model, w = _model(cfg, 314)
+    assert "sap_fuse_linear.net.0.weight" not in w
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, _, pos = H.oracle_grid(ep)
+    nav = H.nav_batch(ep_kw, nav_kw, cells, fts, pos)
+    ref = _oracle_nav(cfg, w, nav)
+    out = model("navigation", _to_cuda(nav))
+    torch.cuda.synchronize()
+    _check(out, ref, keys=("gmap_embeds", "vp_embeds") + LOGITS)

@@ -87,6 +87,12 @@ if "gemmln" in want:
         return us
     tot = ln_case(B * 216, 768, "map out-proj") * 3 + ln_case(B * 216, 3072, "map ffn2") * 2 + ln_case(B * 57, 768, "x out-proj") * 8 + ln_case(B * 57, 3072, "x ffn2") * 4
     print("GEMM+LN sum over the step's 17 launches: %.1f us" % tot, flush=True)
+    lib.gridmm_debug_set_ln_cluster.argtypes = [ctypes.c_int]
+    for cl in (2, 4, 6):
+        lib.gridmm_debug_set_ln_cluster(cl)
+        print("--- forced cluster %d%s" % (cl, " (two CTA pairs)" if cl == 4 else ""), flush=True)
+        ln_case(B * 216, 768, "map out-proj"); ln_case(B * 216, 3072, "map ffn2"); ln_case(B * 57, 768, "x out-proj"); ln_case(B * 57, 3072, "x ffn2")
+    lib.gridmm_debug_set_ln_cluster(0)
 
 if "attn" in want:
     def attn_case(Sq, Sk, tag):
