@@ -14,7 +14,7 @@
 // small-M problems still spread over ~90 SMs; CL = 4 = two cta_group::2 PAIRS, 256 rows x 384 columns per pair, for the
 // map-sized problems).  In the epilogue every thread owns one row of its CTA's slice:
 //   pass 1  v = acc + bias + residual (the residual arrives coalesced through a per-warp shared-memory transpose), written
-//           back into TMEM; per-thread mean and M2 over its columns
+//           back into TMEM; per-thread mean and M2 (from sum and sum of squares) over its columns
 //   merge   (mean, M2) partials of the 2*CL column slices of a row are exchanged through DISTRIBUTED SHARED MEMORY
 //           (mapa + ld.shared::cluster) around one cluster barrier and merged with Chan's formula
 //   pass 2  v is read back from TMEM, normalised, and stored coalesced (fp32 and/or fp16)
@@ -253,8 +253,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET + (warp - 2) * L::STG_WARP_BYTES);
         const int trow = q * 32 + lane;               // this thread's row of the tile (TMEM lane)
 
-        // ---- pass 1: v = acc + bias + residual -> back to TMEM; running sum
-        float sum = 0.f;
+        // ---- pass 1: v = acc + bias + residual -> back to TMEM; running sum and sum of squares over this thread's columns
+        //      (M2 = sum v^2 - n mean^2 inside one 64..192-column slice: v = O(1), the cancellation costs ~1e-7 relative; the
+        //      slices are then merged with Chan's formula, which is where the means can differ)
+        float sum = 0.f, sq = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             uint32_t v[16];
@@ -290,22 +292,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum += f[j];
+            for (int j = 0; j < 16; ++j) { sum += f[j]; sq = fmaf(f[j], f[j], sq); }
             tmem_st_32x32b_x16(t_addr + c * 16, f);
         }
         tmem_st_wait();
         const float mean_i = sum * (1.0f / HALF);
-        // ---- pass 1b: M2 = sum (v - mean_i)^2 over this thread's columns
-        float m2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_addr + c * 16, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { const float d = __uint_as_float(v[j]) - mean_i; m2 = fmaf(d, d, m2); }
-        }
-        s_stat[half * LN_BM + trow] = make_float2(mean_i, m2);
+        s_stat[half * LN_BM + trow] = make_float2(mean_i, fmaxf(sq - sum * mean_i, 0.0f));
     }
 
     // ---- every column slice of the tile has published its partial statistics
