@@ -2,6 +2,7 @@
 
     python tools/summarize_profiles.py launches gpurun_out/launches_r1.csv profiles/r1_launches.md
     python tools/summarize_profiles.py full gpurun_out/prof_r1.ncu-rep profiles/r1_ncu_full.md
+    python tools/summarize_profiles.py step gpurun_out/prof_r1c_all_raw.csv profiles/r1_ncu_full_v4_step.md profiles/r1_traffic.json gpurun_out/prof_r1c_pool.ncu-rep
 """
 import collections
 import csv
@@ -62,5 +63,46 @@ def full(src, dst):
                     f.write("| %s | %s | %s |\n" % (w, r[ix[w]], units[ix[w]]))
 
 
+def _bytes(v, u):
+    return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+
+
+def step(src_csv, dst, traffic_json=None, pool_rep=None):
+    """`ncu --page raw --csv` export of every launch of one step (tools/gpu_evidence.sh) -> per-launch tables + per-kernel
+    totals; optionally profiles/r1_traffic.json (DRAM bytes of the GEMM launches and of the pooling kernel)."""
+    import json
+    rows = list(csv.reader(open(src_csv)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    gem = 0.0
+    with open(dst, "w") as f:
+        f.write("# ncu --set full, every launch of this library in one navigation step (`ncu --page raw --csv` exported on the GPU box)\n")
+        for r in data:
+            name = r[ix["Kernel Name"]]
+            f.write("\n## %s  grid %s\n\n| metric | value | unit |\n|---|---:|---|\n" % (name[:100], r[ix["Grid Size"]]))
+            for w in WANT:
+                if w in ix:
+                    f.write("| %s | %s | %s |\n" % (w, r[ix[w]], units[ix[w]]))
+            b = _bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + \
+                _bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
+            key = re.sub(r"[<(].*", "", name).replace("void ", "").replace("gmm::", "")
+            t = float(r[ix["gpu__time_duration.sum"]].replace(",", ""))
+            tp = float(r[ix["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]].replace(",", ""))
+            agg[key][0] += 1; agg[key][1] += b; agg[key][2] += t; agg[key][3] += tp * t
+            if "gemm" in name:
+                gem += b
+        f.write("\n## totals per kernel (one step)\n\n| kernel | launches | DRAM bytes (MB) | ncu time (us) | tensor pipe active, time-weighted (%) |\n|---|---:|---:|---:|---:|\n")
+        for k, (n, b, t, tp) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
+            f.write("| `%s` | %d | %.1f | %.1f | %.1f |\n" % (k, n, b / 1e6, t, tp / t if t else 0))
+    if traffic_json and pool_rep:
+        raw = subprocess.run(["ncu", "-i", pool_rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+        pr = list(csv.reader(raw.splitlines()))
+        pix = {h: i for i, h in enumerate(pr[0])}
+        pb = sum(_bytes(pr[2][pix[m]], pr[1][pix[m]]) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        json.dump({"source": "ncu --set full --clock-control none (tools/gpu_evidence.sh, B=32 T=8 step): dram__bytes_read.sum + dram__bytes_write.sum",
+                   "pool_bytes_per_launch": pb, "gemm_bytes_per_step": gem}, open(traffic_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "step": step}[sys.argv[1]](*sys.argv[2:])
