@@ -3,22 +3,25 @@
 //   for i in range(196): softmax over the points of cell i, weighted sum   vilmodel.py:801-807
 // as ONE persistent kernel that reads every valid patch-feature row from HBM exactly once.
 //
-//   * rows are streamed in cell-sorted order (gridmm_grid_update produced `perm`), 64 rows per tile.  Four producer warps
-//     resolve the tile's 64 slab rows (perm -> slot -> row) and fetch them with TMA tile::gather4
-//     (cp.async.bulk.tensor.2d...tile::gather4: four arbitrary rows x 64 fp16 columns per instruction, hardware
-//     SWIZZLE_128B, completion on an mbarrier) straight into a K-major operand tile (D/64 chunks of 64 x 128 B).  Two
-//     tile buffers: up to 192 KB per SM are in flight, no registers or wait_group stalls are spent on the copy
-//     (four warps because a gather4 with per-lane row indices costs ~70 issue cycles: R2UR waterfall per lane);
-//   * relevance  S^T[L, 64] = text_fts[L, D] . X_tile^T  on tcgen05 with the A operand (text_fts of the current
-//     episode, up to 128 positions) held in TENSOR MEMORY for the whole episode (tcgen05.st, 8 warps, software
-//     pipelined), B operand = the feature tile in shared memory, accumulator in TMEM (double buffered);
+//   * rows are streamed in cell-sorted order (gridmm_grid_update produced `perm`), 32 rows per tile, through a ring of
+//     four 48 KB shared-memory tiles.  Four producer warps resolve the tile's slab rows (perm -> slot -> row) and fetch
+//     them with TMA tile::gather4 (cp.async.bulk.tensor.2d...tile::gather4: four arbitrary rows x 64 fp16 columns per
+//     instruction, hardware SWIZZLE_128B, completion on an mbarrier) straight into a K-major operand tile (D/64 chunks
+//     of 32 x 128 B).  Row indices are made warp-uniform with shuffles and one elected lane issues the copies back to back
+//     (elect_one(), common.cuh: per-lane operands cost a ~100-cycle R2UR waterfall per gather4);
+//   * relevance  S^T[L, 32] = text_fts[L, D] . X_tile^T  on tcgen05 with the A operand (text_fts of the current
+//     episode, up to 128 positions) held in TENSOR MEMORY for the whole episode (tcgen05.st by 8 warps, software
+//     pipelined), B operand = the feature tile in shared memory, one TMEM accumulator per ring slot;
 //     w = max over ALL text positions (padding included -- vilmodel.py:798) = max over TMEM lanes, taken with a
-//     warp butterfly (62 shuffles per thread) + one shared-memory hop across the four lane quadrants;
-//   * per-cell softmax numerators exp(w - cell max) by the same warps that reduced w (cell max = match.any + redux.max
-//     inside a warp, running max carried across tiles), weighted sums on CUDA cores straight from the resident tile:
-//     cells are contiguous row segments, every pooling thread owns 4 feature columns and carries (sum, acc) of the
-//     open cell in registers across tiles (rescaled when a later tile raises the max).  CTA ranges are cut at cell
-//     boundaries, so no atomics and no cross-CTA merge exist and the result is deterministic;
+//     warp butterfly (31 shuffles per thread) by the reducer warps whose lane quadrant holds real text positions, merged
+//     across quadrants through shared memory + an mbarrier by the reducer warp that owns the padding quadrant;
+//   * that warp also turns w into per-cell softmax numerators exp(w - cell max) (binary search of the row's cell,
+//     match.any + redux.max inside the warp, running max carried across tiles) and publishes each row's compact cell rank;
+//   * weighted sums as warp-level HMMA from the resident tile: out[cell, :] = sum_r p[r] x[r, :] is the product
+//     X^T[D, 32 rows] . W[32 rows, 8 cell slots] (slot = rank & 7; an open cell keeps its slot across tiles), A through
+//     ldmatrix.trans, weights as fp16 value + fp16 residual (two MMAs), fp32 accumulators in registers across tiles,
+//     rescaled when a later tile raises the open cell's max.  CTA ranges are cut at cell boundaries, so no atomics and no
+//     cross-CTA merge exist and the result is deterministic;
 //   * grid_proj is applied AFTER pooling by the GEMM kernel (sum_j p_j (W x_j + b) = W (sum_j p_j x_j) + b), so this
 //     kernel emits the pooled raw feature per non-empty cell, compacted in ascending cell order (the order
 //     vilmodel.py:819 gathers them in), as fp16 GEMM input.
@@ -239,7 +242,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     int* s_carry_c = reinterpret_cast<int*>(s_carry_m + 1);        // [1] its (episode << 16 | cell) key (-1: none)
     int* s_range = s_carry_c + 1;                                  // [0] g_start, [1] g_end
     int* s_csr = reinterpret_cast<int*>(misc + 64 * 8 + 2 * POOL_NBUF * POOL_ROWS * 4 + POOL_NBUF * 4 * POOL_ROWS * 4 + 128);   // reducers' cell_start
-    int* s_cs = s_csr + POOL_MAX_CELLS + 1;                        // (unused)
+    int* s_cs = s_csr + POOL_MAX_CELLS + 1;                        // (spare table slot)
     int* s_cr = s_cs + POOL_MAX_CELLS + 1;                         // reducers' cell_rank [n_cells]
     int* s_vbase = s_cr + POOL_MAX_CELLS;                          // [batch + 1]
 
