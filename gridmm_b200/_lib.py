@@ -44,7 +44,7 @@ _SIGS = {
     "gridmm_copy_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_void_p],
     "gridmm_map_inputs": [c_void_p] * 9 + [c_int] + [c_void_p] * 10 + [c_float] + [c_void_p] * 3 + [c_int] * 4 + [c_void_p],
-    "gridmm_fusion_inputs": [c_void_p] * 12 + [c_int] * 6 + [c_void_p],
+    "gridmm_fusion_inputs": [c_void_p] * 13 + [c_int] + [c_void_p] * 5 + [c_int] * 6 + [c_void_p],
     "gridmm_kv_index": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_linear_f16_rows": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "gridmm_attention_varlen_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,

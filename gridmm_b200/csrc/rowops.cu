@@ -93,6 +93,9 @@ struct FusionInParams {
     uint8_t* kv_mask; uint8_t* q_mask;          // [B, KC], [B, Q]
     int B, S, L, G, V;
     const int* kv_pos;                          // [B, KC] packed row of every VALID context row (-1: masked), or null = unpacked
+    // optional: the vp tokens of x (rows G.. of every episode) = vp_img + LN(Linear(vp_pos)) (vilmodel.py:832-833), else they must
+    // already be in x32 / x16
+    const float* v_feat; int v_kin; const float* v_w; const float* v_bias; const float* v_gamma; const float* v_beta; const float* v_base;
 };
 
 // Packed ("ragged") context index for the fusion encoder: masked context rows (empty grid-cell slots, padded text) get no K/V
@@ -149,9 +152,38 @@ __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
     pdl_wait();
     const int KC = p.S + p.L, Q = p.G + p.V;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= p.B * (KC + p.G)) return;
+    if (row >= p.B * (KC + p.G + (p.v_feat ? p.V : 0))) return;
     float4 v[HV];
-    if (row < p.B * KC) {
+    if (row >= p.B * (KC + p.G)) {
+        // vp token j of episode b
+        const int vr = row - p.B * (KC + p.G);
+        const int b = vr / p.V, j = vr - b * p.V;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = (k < p.v_kin) ? p.v_feat[static_cast<size_t>(vr) * p.v_kin + k] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const int col = (i * 32 + lane) * 4;
+            float4 a = *reinterpret_cast<const float4*>(p.v_bias + col);
+            float4 w4[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                w4[k] = (k < p.v_kin) ? __ldg(reinterpret_cast<const float4*>(p.v_w + static_cast<size_t>(k) * HID + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                a.x = fmaf(f[k], w4[k].x, a.x); a.y = fmaf(f[k], w4[k].y, a.y); a.z = fmaf(f[k], w4[k].z, a.z); a.w = fmaf(f[k], w4[k].w, a.w);
+            }
+            v[i] = a;
+        }
+        ln_row(v, p.v_gamma, p.v_beta, 1e-12f, lane);
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(p.v_base + static_cast<size_t>(vr) * HID + (i * 32 + lane) * 4);
+            v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+        }
+        const size_t orow = static_cast<size_t>(b) * Q + p.G + j;
+        store_row(v, p.x32 + orow * HID, p.x16 + orow * HID, lane);
+    } else if (row < p.B * KC) {
         const int b = row / KC, r = row - b * KC;
         const float* src = (r < p.S) ? p.map32 + (static_cast<size_t>(b) * p.S + r) * HID
                                      : p.txt32 + (static_cast<size_t>(b) * p.L + (r - p.S)) * HID;
@@ -567,15 +599,19 @@ extern "C" int gridmm_kv_index(const unsigned char* map_mask, const unsigned cha
 extern "C" int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned char* map_mask,
                                     const unsigned char* txt_mask, const unsigned char* gmap_mask, const unsigned char* vp_mask,
                                     float* x32, void* x16, void* kv16, unsigned char* kv_mask, unsigned char* q_mask,
-                                    const int* kv_pos, int batch, int S, int L, int G, int V, int hidden, cudaStream_t stream) {
+                                    const int* kv_pos, const float* vp_pos, int vp_kin, const float* vp_w, const float* vp_bias,
+                                    const float* vp_gamma, const float* vp_beta, const float* vp_img, int batch, int S, int L, int G,
+                                    int V, int hidden, cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0) return 0;
     if (hidden != HID || S < G || L < 1 || G < 1 || V < 1) return GRIDMM_ERR_SHAPE;
     if (!map32 || !txt32 || !map_mask || !txt_mask || !gmap_mask || !vp_mask || !x32 || !x16 || !kv16 || !kv_mask || !q_mask)
         return GRIDMM_ERR_ARG;
     FusionInParams p{map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, reinterpret_cast<__half*>(x16),
-                     reinterpret_cast<__half*>(kv16), kv_mask, q_mask, batch, S, L, G, V, kv_pos};
-    const int rows = batch * (S + L + G);
+                     reinterpret_cast<__half*>(kv16), kv_mask, q_mask, batch, S, L, G, V, kv_pos,
+                     vp_pos, vp_kin, vp_w, vp_bias, vp_gamma, vp_beta, vp_img};
+    if (vp_pos && (!vp_w || !vp_bias || !vp_gamma || !vp_beta || !vp_img || vp_kin < 1 || vp_kin > 16)) return GRIDMM_ERR_ARG;
+    const int rows = batch * (S + L + G + (vp_pos ? V : 0));
     GMM_CUDA_CHECK(launch_pdl(fusion_inputs_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, p));
     gridmm_count_launch(1);
     return 0;

@@ -630,9 +630,7 @@ class GlocalTextPathNavCMT(nn.Module):
                        map32, map16, map_mask, B, NC, S)
         x32 = self._out("x32", (B * Q, HID), static_out)       # escapes as gmap_embeds / vp_embeds
         x16 = self.buf("x16", (B * Q, HID), f16)
-        ve = "local_encoder.vp_pos_embeddings"
-        ops.pos_embed(st["vp_pos"], self.Wt32(ve + ".0.weight"), self.P(ve + ".0.bias"), self.P(ve + ".1.weight"),
-                      self.P(ve + ".1.bias"), 1e-12, x32, x16, V, Q, G, base=st["vp_img"])
+        ve = "local_encoder.vp_pos_embeddings"      # the vp tokens of x are computed by gridmm_fusion_inputs below
 
         # ---- grid_encoder (pre-norm, key_padding_mask) and grid_txt_encoder (vilmodel.py:840-841)
         self._prenorm_encoder("grid_encoder", 1, map32, map16, map_mask, B, S, "map", first_norm_done=True)
@@ -657,7 +655,8 @@ class GlocalTextPathNavCMT(nn.Module):
         kv_cnt = self.buf("kv_cnt", (B,), torch.int32)
         ops.kv_index(map_mask, txt_mask_u8, kv_pos, kv_off, kv_cnt, B, S, L)
         ops.fusion_inputs(map32, txt32, map_mask, txt_mask_u8, gmap_mask_u8, vp_mask_u8, x32, x16, kv16, kv_mask, q_mask, B, S, L, G, V,
-                          kv_pos=kv_pos)
+                          kv_pos=kv_pos, vp=(st["vp_pos"], self.Wt32(ve + ".0.weight"), self.P(ve + ".0.bias"),
+                                             self.P(ve + ".1.weight"), self.P(ve + ".1.bias"), st["vp_img"]))
         nx = cfg.num_x_layers
         le = "local_encoder.encoder.x_layers.%d"
         names_w, names_b = [], []

@@ -117,7 +117,9 @@ def attention_varlen(q, k, v, out, k_off, k_cnt, max_sk, batch, heads, sq, q_row
               1.0 / math.sqrt(64.0), _lib.stream_ptr())
 
 
-def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16, kv16, kv_mask, q_mask, batch, S, L, G, V, kv_pos=None):
+def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16, kv16, kv_mask, q_mask, batch, S, L, G, V, kv_pos=None,
+                  vp=None):
+    """vp = (vp_pos [B*V, kin], w_t [kin, 768], bias, gamma, beta, vp_img [B*V, 768]) computes the vp tokens of x in the same launch."""
     for t_, n in ((map_mask, "map_mask"), (txt_mask, "txt_mask"), (gmap_mask, "gmap_mask"), (vp_mask, "vp_mask"), (kv_mask, "kv_mask"),
                   (q_mask, "q_mask")):
         _chk(t_, torch.uint8, n)
@@ -127,7 +129,9 @@ def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16
         assert t_.is_contiguous()
     _lib.call("gridmm_fusion_inputs", map32.data_ptr(), txt32.data_ptr(), map_mask.data_ptr(), txt_mask.data_ptr(), gmap_mask.data_ptr(),
               vp_mask.data_ptr(), x32.data_ptr(), x16.data_ptr(), kv16.data_ptr(), kv_mask.data_ptr(), q_mask.data_ptr(), _lib.ptr(kv_pos),
-              batch, S, L, G, V, HID, _lib.stream_ptr())
+              _lib.ptr(vp[0]) if vp else None, vp[0].shape[1] if vp else 0, _lib.ptr(vp[1]) if vp else None,
+              _lib.ptr(vp[2]) if vp else None, _lib.ptr(vp[3]) if vp else None, _lib.ptr(vp[4]) if vp else None,
+              _lib.ptr(vp[5]) if vp else None, batch, S, L, G, V, HID, _lib.stream_ptr())
 
 
 def split_rows(x, in_rows_per_b, in_off, rows_per_b, batch, out_f16, k_total):

@@ -130,13 +130,15 @@ int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, const void* 
                                 const int* k_off, const int* k_cnt, int max_sk, void* o, int ldo, int batch, int heads, int sq,
                                 float scale, cudaStream_t stream);
 
-/* Inputs of the fusion encoder (vilmodel.py:843-850) in one launch: x[b, :G] = map[b, S-G:] (fp32 + fp16; rows G.. of x hold the
- * vp tokens already), kv16[b] = fp16([map[b] ; txt[b]]) -- or, with kv_pos (gridmm_kv_index), only the valid rows at their packed
- * positions --, kv_mask = [map_mask ; txt_mask], q_mask = [gmap_mask ; vp_mask]. */
+/* Inputs of the fusion encoder (vilmodel.py:828-833, 843-850) in one launch: x[b, :G] = map[b, S-G:] (fp32 + fp16),
+ * x[b, G:] = vp_img + LN(Linear(vp_pos)) when vp_pos is given (vp_w = TRANSPOSED weight [vp_kin, 768]; with vp_pos NULL rows G..
+ * of x must hold the vp tokens already), kv16[b] = fp16([map[b] ; txt[b]]) -- or, with kv_pos (gridmm_kv_index), only the valid
+ * rows at their packed positions --, kv_mask = [map_mask ; txt_mask], q_mask = [gmap_mask ; vp_mask]. */
 int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned char* map_mask, const unsigned char* txt_mask,
                          const unsigned char* gmap_mask, const unsigned char* vp_mask, float* x32, void* x16, void* kv16,
-                         unsigned char* kv_mask, unsigned char* q_mask, const int* kv_pos, int batch, int S, int L, int G, int V,
-                         int hidden, cudaStream_t stream);
+                         unsigned char* kv_mask, unsigned char* q_mask, const int* kv_pos, const float* vp_pos, int vp_kin,
+                         const float* vp_w, const float* vp_bias, const float* vp_gamma, const float* vp_beta, const float* vp_img,
+                         int batch, int S, int L, int G, int V, int hidden, cudaStream_t stream);
 
 /* ---- action heads (vilmodel.py:663-674, 859-907) in three launches ------------------------------------------
  * ClsPrediction = Linear, ReLU, LayerNorm(1e-12), Linear(768 -> 1):  logit = rstd * (S3 - mean * c1) + c0 with r = ReLU(xW + b),
