@@ -101,3 +101,47 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_head_pack_and_table_restate_cls_prediction():
+    """Host side of the grouped ClsPrediction launch: the stacked split weights / gamma*w2 / (c1, c0) constants and the per-tile
+    table reproduce ClsPrediction (vilmodel.py:663-674) when the kernel's arithmetic is restated in torch on the CPU:
+    logit = rstd * (S3 - mean * c1) + c0 over r = ReLU(x W^T + b)."""
+    from gridmm_b200.model import GlocalTextPathNavCMT, NavConfig
+    from oracle import model_oracle as mo
+    cfg = NavConfig(num_l_layers=1, num_pano_layers=1, obj_feat_size=768)
+    m = GlocalTextPathNavCMT(cfg).eval()
+    with torch.no_grad():
+        for p in m.parameters():          # non-trivial LayerNorm weights / biases
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    w, bias, gw2, consts, fuse_gw2, n_groups, n_names = m.head_pack(True)
+    assert n_names == 4 and n_groups == 6 and tuple(w.shape) == (6 * 768, 3 * 768) and tuple(gw2.shape) == (6 * 768,)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    x = torch.randn(9, 768)
+    hi = x.half(); lo = (x - hi.float()).half()
+    a = torch.cat([hi, lo, hi], 1).float()                      # what gridmm_head_rows writes
+    for gi, name in enumerate(["global_sap_head", "local_sap_head", "grid_sap_head", "og_head"]):
+        r = torch.relu(a @ w[gi * 768:(gi + 1) * 768].float().t() + bias[gi * 768:(gi + 1) * 768])
+        s1, s2, s3 = r.sum(1), (r * r).sum(1), (r * gw2[gi * 768:(gi + 1) * 768]).sum(1)
+        mean = s1 / 768
+        logit = torch.rsqrt(s2 / 768 - mean * mean + 1e-12) * (s3 - mean * consts[gi, 0]) + consts[gi, 1]
+        ref = mo.cls_head(sd, name, x).squeeze(-1)
+        assert (logit - ref).abs().max().item() < 2e-4, name
+    # fuse head: the two raw-product groups are the K halves of sap_fuse_linear.net.0
+    g0, v0 = torch.randn(5, 768), torch.randn(5, 768)
+    split = lambda t: torch.cat([t.half(), (t - t.half().float()).half(), t.half()], 1).float()      # noqa: E731
+    h = split(g0) @ w[4 * 768:5 * 768].float().t() + split(v0) @ w[5 * 768:6 * 768].float().t()
+    r = torch.relu(h + sd["sap_fuse_linear.net.0.bias"])
+    mean = r.mean(1)
+    logit = torch.rsqrt((r * r).mean(1) - mean * mean + 1e-12) * ((r * fuse_gw2).sum(1) - mean * consts[4, 0]) + consts[4, 1]
+    ref = mo.cls_head(sd, "sap_fuse_linear", torch.cat([g0, v0], 1)).squeeze(-1)
+    assert (logit - ref).abs().max().item() < 2e-4
+    # tile table: A rows / output rows are 128-aligned, groups do not overlap, the object head re-reads the local rows
+    grp, tiles, a0, a_rows, o_obj, out_rows = m.head_table(32, 20, 57, True, torch.device("cpu"))
+    t = grp.numpy()
+    assert tiles == t.shape[0] and (t[:, 0] % 128 == 0).all() and (t[:, 2] % 128 == 0).all() and t[:, 0].max() < a_rows
+    assert len(set(t[:, 2].tolist())) == tiles and t[:, 2].max() + 128 <= out_rows
+    obj = t[t[:, 1] == 3 * 768]
+    loc = t[t[:, 1] == 1 * 768]
+    assert (obj[:, 0] == loc[:, 0]).all() and (obj[:, 2] >= o_obj).all() and (t[t[:, 3] == 1][:, 1] >= 4 * 768).all()
