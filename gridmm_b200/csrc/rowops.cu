@@ -50,6 +50,32 @@ __device__ __forceinline__ void store_row(float4 (&x)[HV], float* o32, __half* o
     }
 }
 
+// v = bias + f[0..kin) . W^T[kin, 768] for this lane's 6 float4 column groups (position-feature embeddings: kin <= 16).  The
+// weight loads of TWO column groups (2 x 16 predicated LDG.128) are issued before their FMAs, so a row costs three global round
+// trips instead of six (one warp per row: these kernels are pure latency).
+__device__ __forceinline__ void small_linear(float4 (&v)[HV], const float (&f)[16], int kin, const float* w, const float* bias, int lane) {
+#pragma unroll
+    for (int i0 = 0; i0 < HV; i0 += 2) {
+        float4 w4[2][16];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col = ((i0 + j) * 32 + lane) * 4;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                w4[j][k] = (k < kin) ? __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(k) * HID + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float4 a = *reinterpret_cast<const float4*>(bias + ((i0 + j) * 32 + lane) * 4);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {         // f[k] = 0 beyond kin
+                a.x = fmaf(f[k], w4[j][k].x, a.x); a.y = fmaf(f[k], w4[j][k].y, a.y); a.z = fmaf(f[k], w4[j][k].z, a.z); a.w = fmaf(f[k], w4[j][k].w, a.w);
+            }
+            v[i0 + j] = a;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- layer norm
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, int ldx, const float* gamma, const float* beta,
                                                         float eps, float* o32, int ld32, __half* o16, int ld16, int rows) {
@@ -161,20 +187,7 @@ __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
         float f[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) f[k] = (k < p.v_kin) ? p.v_feat[static_cast<size_t>(vr) * p.v_kin + k] : 0.0f;
-#pragma unroll
-        for (int i = 0; i < HV; ++i) {
-            const int col = (i * 32 + lane) * 4;
-            float4 a = *reinterpret_cast<const float4*>(p.v_bias + col);
-            float4 w4[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                w4[k] = (k < p.v_kin) ? __ldg(reinterpret_cast<const float4*>(p.v_w + static_cast<size_t>(k) * HID + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                a.x = fmaf(f[k], w4[k].x, a.x); a.y = fmaf(f[k], w4[k].y, a.y); a.z = fmaf(f[k], w4[k].z, a.z); a.w = fmaf(f[k], w4[k].w, a.w);
-            }
-            v[i] = a;
-        }
+        small_linear(v, f, p.v_kin, p.v_w, p.v_bias, lane);
         ln_row(v, p.v_gamma, p.v_beta, 1e-12f, lane);
 #pragma unroll
         for (int i = 0; i < HV; ++i) {
@@ -258,22 +271,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
 #pragma unroll
     for (int k = 0; k < 16; ++k) f[k] = (k < p.kin) ? p.feat[static_cast<size_t>(row) * p.kin + k] : 0.0f;
     float4 v[HV];
-#pragma unroll
-    for (int i = 0; i < HV; ++i) {
-        const int col = (i * 32 + lane) * 4;
-        float4 a = *reinterpret_cast<const float4*>(p.bias + col);
-        // transposed weight [kin, 768]: coalesced float4 per lane; fully unrolled with predicated loads so that all kin x 6 loads of
-        // a row are in flight together (a runtime trip count serialised them: 36 us for 1184 rows)
-        float4 w4[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            w4[k] = (k < p.kin) ? __ldg(reinterpret_cast<const float4*>(p.w + static_cast<size_t>(k) * HID + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {         // f[k] = 0 beyond kin
-            a.x = fmaf(f[k], w4[k].x, a.x); a.y = fmaf(f[k], w4[k].y, a.y); a.z = fmaf(f[k], w4[k].z, a.z); a.w = fmaf(f[k], w4[k].w, a.w);
-        }
-        v[i] = a;
-    }
+    small_linear(v, f, p.kin, p.w, p.bias, lane);      // transposed weight [kin, 768]: coalesced float4 per lane
     ln_row(v, p.gamma, p.beta, p.eps, lane);
     if (p.base) {
 #pragma unroll
@@ -383,20 +381,7 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = (j < p.g_kin) ? p.g_feat[gr * p.g_kin + j] : 0.0f;
-#pragma unroll
-            for (int i = 0; i < HV; ++i) {
-                const int col = (i * 32 + lane) * 4;
-                float4 a = *reinterpret_cast<const float4*>(p.g_bias + col);
-                float4 w4[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    w4[j] = (j < p.g_kin) ? __ldg(reinterpret_cast<const float4*>(p.g_w + static_cast<size_t>(j) * HID + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    a.x = fmaf(f[j], w4[j].x, a.x); a.y = fmaf(f[j], w4[j].y, a.y); a.z = fmaf(f[j], w4[j].z, a.z); a.w = fmaf(f[j], w4[j].w, a.w);
-                }
-                v[i] = a;
-            }
+            small_linear(v, f, p.g_kin, p.g_w, p.g_bias, lane);
             ln_row(v, p.g_gamma, p.g_beta, 1e-12f, lane);
             const float* tr = p.g_table + static_cast<size_t>(p.g_idx[gr]) * HID;
 #pragma unroll
