@@ -76,6 +76,13 @@ if "gemm" in want:
     tot += gemm_case(B * 37, 768, 2304, act=2, f32=True, tag="cls head V")
     tot += gemm_case(B, 768, 4608, act=2, f32=True, tag="cls fuse")
     print("GEMM sum over the step's 42 launches: %.1f us" % tot, flush=True)
+    # CTA pairs (cta_group::2, 256x256 tiles) against single-CTA tiles on the shapes where the choice is close
+    lib.gridmm_debug_set_gemm_pairs.argtypes = [ctypes.c_int]
+    for on in (0, 1):
+        lib.gridmm_debug_set_gemm_pairs(on)
+        print("--- CTA pairs %s" % ("on" if on else "off"), flush=True)
+        gemm_case(B * Q, 3072, 768, act=1, tag="x ffn1"); gemm_case(B * Q, 2304, 768, tag="x qkv")
+        gemm_case(B * S, 768, 768, tag="map xattn q"); gemm_case(B * L, 1536, 768, tag="txt kv")
 
 if "gemmln" in want:
     def ln_case(M, K, tag):
