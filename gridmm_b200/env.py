@@ -57,6 +57,25 @@ GEOMETRIES = {
 }
 
 
+def target_patch_id(pos_xy, next_xy, heading, half_len, grid_w=14):
+    """Pretraining label: 1 + cell of the next ground-truth viewpoint in this step's window, 0 when the path ends here
+    (pretrain_src/data/dataset.py:361-368, 427-439; returned by the dataset next to the grid, not read by the model).
+    Host scalar arithmetic like the reference's: the offset to the next viewpoint and its rotation by -heading are python
+    floats, the fp32 window half-length then pulls the sum, the scale by grid_w (14 here, not grid_w - 1 as for the points) and
+    the floor division into fp32.  `half_len` is this step's GridBatch.half_len entry."""
+    if next_xy is None:
+        return 0
+    dx, dy = float(next_xy[0]) - float(pos_xy[0]), float(next_xy[1]) - float(pos_xy[1])
+    c, s = math.cos(-heading), math.sin(-heading)
+    h = np.float32(half_len)
+    span = np.float32(2) * h
+    idx = []
+    for r in (dx * c + dy * s, dy * c - dx * s):
+        q = np.floor_divide((np.float32(r) + h) * np.float32(grid_w), span)
+        idx.append(min(max(int(q), 0), grid_w - 1))
+    return 1 + idx[0] * grid_w + idx[1]
+
+
 class GridBatch:
     """Handle to the device-resident grid map of a batch of episodes after a step (what the model's 'navigation' mode
     consumes instead of the reference's grid_fts / grid_map lists)."""
@@ -128,6 +147,7 @@ class GridMapBuilder:
         self._copy_stream = None
         self._staged_evt = None
         self._staged_step = -1
+        self._h2d_evt = None          # last asynchronous copy out of the pinned staging buffers above
         self.new_episodes()
 
     # ------------------------------------------------------------------ buffers
@@ -201,6 +221,7 @@ class GridMapBuilder:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             grew = True
         if not (isinstance(clip, torch.Tensor) and clip.is_pinned()):
+            self._pinned_free()
             self.h_clip.copy_(torch.as_tensor(clip).reshape(self.h_clip.shape))
             clip = self.h_clip
         cs = self._copy_stream
@@ -213,6 +234,14 @@ class GridMapBuilder:
             self._staged_evt = torch.cuda.Event()
             self._staged_evt.record(cs)
         self._staged_step = t
+
+    def _pinned_free(self, clip_too=True):
+        """The pinned staging buffers are reused every step: before the host rewrites them, the asynchronous copies that read
+        them last step must have run (they have, unless the caller queued steps faster than the GPU drains them).
+        clip_too: also the last staged feature copy, which may have read h_clip."""
+        for evt in (self._h2d_evt, self._staged_evt if clip_too else None):
+            if evt is not None:
+                evt.synchronize()
 
     def step(self, depth_sub, clip, pos_xy, heading, active=None):
         """Append one viewpoint per episode and rebuild the grid assignment (getStates' grid half, env.py:392-398).
@@ -230,6 +259,7 @@ class GridMapBuilder:
             raise NotImplementedError("per-episode `active` masks need per-episode step counters on the slab; "
                                       "the reference re-adds the last viewpoint of ended episodes, so do that")
         t = int(self.n_steps[0])
+        self._pinned_free(clip_too=clip is not None)      # a staged copy of THIS step is waited for on the device, below
         # features: one contiguous copy into slab[t]
         if clip is None:
             if self._staged_step != t or self._staged_evt is None:
@@ -258,8 +288,21 @@ class GridMapBuilder:
         self.h_view.copy_(torch.from_numpy(hp[:, 4:]))
         self.d_pose.copy_(self.h_pose, non_blocking=True)
         self.d_view.copy_(self.h_view, non_blocking=True)
+        self._h2d_evt = torch.cuda.Event()
+        self._h2d_evt.record()
         ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, None, g.off7, g.flip_y,
                         g.negate_map_x, g.pos_mode, g.max_dist, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
                         self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
         self.n_steps += 1
         return GridBatch(self)
+
+    def run_trajectory(self, depth_sub, clip, pos_xy, heading):
+        """Whole ground-truth paths at once, as the pretraining dataset builds them (`get_traj_pano_fts`,
+        pretrain_src/data/dataset.py:482-507: reset, then one getGlobalMap per viewpoint): depth_sub [B,T,12,49],
+        clip [B,T,12,50,D], pos_xy [B,T,2], heading [B,T].  Returns the GridBatch after the last viewpoint; all T*588 points
+        per path are assigned to the last viewpoint's window, which is what the pretraining model consumes."""
+        self.new_episodes()
+        grid = None
+        for t in range(int(np.asarray(pos_xy).shape[1])):
+            grid = self.step(depth_sub[:, t], clip[:, t], np.asarray(pos_xy)[:, t], np.asarray(heading)[:, t])
+        return grid

@@ -42,6 +42,16 @@ def make_episodes(batch, steps, seed=0, dim=768, zero_frac=0.10):
     return {"depth_sub": depth, "clip": clip, "pos": pos, "heading": heading}
 
 
+def pretrain_headings(ep):
+    """Headings as the pretraining dataset sets them along a ground-truth path: (viewidx % 12) * 30 degrees of the candidate
+    view that led to each viewpoint (pretrain_src/data/dataset.py:497-499); the first viewpoint keeps the start heading."""
+    B, T = ep["pos"].shape[:2]
+    rng = np.random.default_rng(1000 + int(B) * 31 + int(T))
+    h = ep["heading"].astype(np.float64).copy()
+    h[:, 1:] = rng.integers(0, 12, size=(B, T - 1)) * math.radians(30)
+    return h
+
+
 def expand_depth(depth_sub):
     """uint16[12,49] -> the reference's uint16[36,128,128] map (zeros elsewhere)."""
     full = np.zeros((36, 128, 128), dtype=np.uint16)

@@ -201,6 +201,57 @@ def ref_step(env, i, scan, vp, heading, depth_u16, clip_fp16, pos_xy):
     return np.asarray(env.global_semantic[i]), np.array(env.global_map[i]), gridmap_pos_fts
 
 
+# ----------------------------------------------------------------------------------------------- pretraining dataset variant
+def load_reference_pretrain_data():
+    """The pretraining dataset object (pretrain_src/data/dataset.py:90 `ReverieTextPathData`, subclass `R2RTextPathData` :634)
+    created with `object.__new__` and fake depth / CLIP / viewpoint stores -- all that its `getGlobalMap` (:351-473) touches.
+    The module is imported under the alias package `pretrain_data` so that its `.common` import resolves and nothing in
+    map_nav_src is shadowed."""
+    import importlib
+    _install_stubs()
+    if "pretrain_data" not in sys.modules:
+        pkg = types.ModuleType("pretrain_data")
+        pkg.__path__ = [os.path.join(REF_ROOT, "pretrain_src", "data")]
+        sys.modules["pretrain_data"] = pkg
+    mod = importlib.import_module("pretrain_data.dataset")
+    ds = object.__new__(mod.R2RTextPathData)
+    ds.DepthDB = _DictDB()
+    ds.SemanticDB = _DictDB()
+    ds.viewpoint_info = {}
+    return ds
+
+
+def ref_pretrain_traj(ds, scan, headings, depth_u16, clip_f32, pos_xy):
+    """The grid half of `get_traj_pano_fts` (pretrain_src/data/dataset.py:482-507) over one ground-truth path of T viewpoints:
+    state reset, one `getGlobalMap` per viewpoint, features concatenated by the caller.  `headings[t]` is what :499 would have
+    set from the candidate view index ((viewidx % 12) * 30 degrees).
+    Returns per step: grid_map f64[588 (t+1)], gridmap_pos_fts f32[196,5], target_patch_id; and the final grid_fts [588 T, D]."""
+    T = len(headings)
+    path = ["vp%d" % t for t in range(T)]
+    for t in range(T):
+        key = "%s_%s" % (scan, path[t])
+        ds.DepthDB.store[key] = depth_u16[t]
+        ds.SemanticDB.store[key] = clip_f32[t]
+        ds.viewpoint_info[key] = {"x": float(pos_xy[t][0]), "y": float(pos_xy[t][1]), "z": 0.0}
+    ds.gt_path = path
+    ds.global_semantic, ds.global_position_x, ds.global_position_y, ds.global_mask = [], [], [], []   # :483-491
+    ds.max_x, ds.min_x, ds.max_y, ds.min_y = -10000, 10000, -10000, 10000
+    ds.global_map = None
+    cells, pos_fts, targets = [], [], []
+    grid_fts = np.array([])
+    for t in range(T):
+        ds.heading = headings[t]
+        out = ds.getGlobalMap(scan, path[t])
+        (sem, ds.global_position_x, ds.global_position_y, ds.global_mask, ds.global_map, ds.max_x, ds.min_x, ds.max_y, ds.min_y,
+         pf, target) = out
+        ds.global_semantic = np.asarray(sem).view(_NeverEqList)       # shim 4 (`== []` under numpy >= 2, dataset.py:388)
+        grid_fts = np.asarray(sem) if grid_fts.shape == (0,) else np.concatenate((grid_fts, np.asarray(sem)), axis=0)   # :503-506
+        cells.append(np.array(ds.global_map))
+        pos_fts.append(pf)
+        targets.append(int(target))
+    return cells, pos_fts, targets, grid_fts.reshape((-1, clip_f32[0].shape[-1]))
+
+
 # ----------------------------------------------------------------------------------------------- continuous-env variant
 CE_ROOT = os.path.join(REF_ROOT, "VLN_CE", "vlnce_baselines", "models")
 

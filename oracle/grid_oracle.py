@@ -16,6 +16,8 @@ Follows, line by line:
   EnvBatch.get_gridmap_pos_fts map_nav_src/r2r/env.py:242-265
   calculate_vp_rel_pos_fts    map_nav_src/r2r/env.py:60-77
   get_angle_fts               map_nav_src/r2r/env.py:52-58
+  target_patch_id (pretraining dataset only; its grid arithmetic is otherwise the R2R one)
+                              pretrain_src/data/dataset.py:361-368, 427-439
 Arithmetic contract: every op is an individually rounded IEEE fp32 op (numpy
 elementwise semantics, no FMA); trig of view angles / heading is evaluated in
 double on the host and rounded to fp32 (python float x fp32 array => fp32 under
@@ -180,3 +182,26 @@ def gridmap_pos_fts(half_len, grid_w=14, geom=R2RGeometry):
     es = np.array(es).astype(f32)
     ds = np.array(ds).astype(f32)
     return np.stack([np.sin(hs), np.cos(hs), np.sin(es), np.cos(es), ds], 1).astype(f32)
+
+
+def target_patch_id(pos_xy, next_xy, heading, half, is_last, grid_w=14):
+    """Cell (1-based; 0 = "stay") that holds the NEXT ground-truth viewpoint of a pretraining path -- an extra label the
+    pretraining dataset derives from the same window (pretrain_src/data/dataset.py:361-368, 427-439); the model does not read it.
+
+    pos_xy / next_xy: python floats (viewpoint_info); heading: python float; half: the fp32 half_len of this step's window.
+    The offset and its rotation are python-float (double) arithmetic; adding the fp32 `half` makes the rest fp32 (NEP 50), and
+    `//` is numpy's floor_divide on fp32 scalars.  Note the reference scales by 14 (GLOBAL_WIDTH) here, not by 13 as for points."""
+    if is_last:
+        return 0
+    tx = float(next_xy[0]) - float(pos_xy[0])
+    ty = float(next_xy[1]) - float(pos_xy[1])
+    ang = -heading
+    rx = tx * math.cos(ang) + ty * math.sin(ang)
+    ry = ty * math.cos(ang) - tx * math.sin(ang)
+    half = f32(half)
+    two_half = f32(f32(2) * half)
+    ix = int(np.floor_divide(f32(f32(f32(rx) + half) * f32(grid_w)), two_half))
+    iy = int(np.floor_divide(f32(f32(f32(ry) + half) * f32(grid_w)), two_half))
+    ix = min(max(ix, 0), grid_w - 1)
+    iy = min(max(iy, 0), grid_w - 1)
+    return 1 + ix * grid_w + iy

@@ -6,6 +6,8 @@ seeds by gridmm_b200/synth.py (numpy PCG64 streams are platform independent), on
 
   grid_r2r_s{seed}.npz   EnvBatch.getGlobalMap (map_nav_src/r2r/env.py:267-374) over T consecutive steps:
                          cell ids per step (int16, -1 masked) and gridmap_pos_fts of the last step
+  grid_pretrain_s{seed}.npz  the pretraining dataset's getGlobalMap (pretrain_src/data/dataset.py:351-473) over whole ground-truth
+                         paths (as get_traj_pano_fts :482-507 drives it): cell ids per step, gridmap_pos_fts and target_patch_id
   nav_{name}.npz         GlocalTextPathNavCMT.forward('navigation', ...) (map_nav_src/models/vilmodel.py:782-918):
                          all five logit tensors + gmap/vp embeddings
 """
@@ -58,6 +60,31 @@ def make_grid():
         path = os.path.join(GOLD, "grid_r2r_s%d.npz" % case["seed"])
         np.savez_compressed(path, **out)
         print("wrote", path, os.path.getsize(path))
+
+
+PRETRAIN_GRID_CASE = dict(seed=51, batch=3, steps=7)
+
+
+def make_pretrain_grid():
+    case = PRETRAIN_GRID_CASE
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    heads = synth.pretrain_headings(ep)
+    ds = _refshim.load_reference_pretrain_data()
+    out = {}
+    for b in range(case["batch"]):
+        T = case["steps"]
+        depth = [synth.expand_depth(ep["depth_sub"][b, t]) for t in range(T)]
+        clip = [ep["clip"][b, t].astype(np.float32) for t in range(T)]           # SemanticFeaturesDB returns float32 (dataset.py:78)
+        cells, pos_fts, targets, fts = _refshim.ref_pretrain_traj(ds, "scan%d" % b, [float(x) for x in heads[b]], depth, clip,
+                                                                   ep["pos"][b])
+        assert fts.shape == (588 * T, 768) and np.array_equal(fts.astype(np.float16)[:588], ep["clip"][b, 0][:, 1:].reshape(-1, 768))
+        for t in range(T):
+            out["cell_b%d_t%d" % (b, t)] = cells[t].astype(np.int16)
+        out["pos_fts_b%d" % b] = np.stack(pos_fts).astype(np.float32)            # [T,196,5]
+        out["target_b%d" % b] = np.array(targets, np.int32)
+    path = os.path.join(GOLD, "grid_pretrain_s%d.npz" % case["seed"])
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), {k: out[k].tolist() for k in out if k.startswith("target")})
 
 
 def reference_nav(ep_kw, nav_kw, model_kw):
@@ -183,7 +210,7 @@ if __name__ == "__main__":
         raise SystemExit("reference not available at %s" % _refshim.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["grid", "nav", "aux", "ce"]
+    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain"]
     if "grid" in which:
         make_grid()
     if "nav" in which:
@@ -192,3 +219,5 @@ if __name__ == "__main__":
         make_aux()
     if "ce" in which:
         make_ce()
+    if "pretrain" in which:
+        make_pretrain_grid()

@@ -25,6 +25,7 @@ AUX_CASES = {
 }
 
 
+PRETRAIN_GRID_CASE = dict(seed=51, batch=3, steps=7)      # mirrors oracle/make_golden.py
 CE_GRID_CASE = dict(seed=41, batch=3, steps=6)
 CE_NAV_CASE = (dict(batch=3, steps=3, seed=42), dict(txt_len=24, gmap_len=10, n_views=12, n_objs=0))
 

@@ -238,6 +238,40 @@ def test_grid_update_bit_exact(case):
         assert torch.equal(got_fts[b].cpu(), torch.from_numpy(np.ascontiguousarray(fts[b])))
 
 
+def test_grid_update_pretraining_paths_bit_exact():
+    """SURVEY 8a row 19, grid half: whole ground-truth paths with the pretraining dataset's headings, against the golden cell ids
+    its own getGlobalMap produced (tests/golden/grid_pretrain_s51.npz, pretrain_src/data/dataset.py:351-473) -- bit-exact at
+    every step, plus gridmap_pos_fts and the target_patch_id label computed from the device's half_len."""
+    import os
+    from gridmm_b200.env import GridMapBuilder, target_patch_id
+    case = H.PRETRAIN_GRID_CASE
+    gold = np.load(os.path.join(H.GOLD, "grid_pretrain_s%d.npz" % case["seed"]))
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    ep["heading"] = synth.pretrain_headings(ep)
+    B, T = case["batch"], case["steps"]
+    gb = GridMapBuilder(B, max_steps=4)
+    for t in range(T):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+        torch.cuda.synchronize()
+        cells = grid.grid_map_numpy()
+        half = grid.half_len.cpu().numpy()
+        pos_fts = grid.pos_fts.cpu().numpy()
+        for b in range(B):
+            assert np.array_equal(cells[b].astype(np.int16), gold["cell_b%d_t%d" % (b, t)]), "b=%d t=%d" % (b, t)
+            np.testing.assert_allclose(pos_fts[b], gold["pos_fts_b%d" % b][t], atol=2e-6, rtol=0)
+            nxt = ep["pos"][b, t + 1] if t + 1 < T else None
+            assert target_patch_id(ep["pos"][b, t], nxt, float(ep["heading"][b, t]), half[b]) == int(gold["target_b%d" % b][t])
+    # the one-call form the pretraining loader would use gives the same final state
+    last = [c.copy() for c in cells]
+    grid2 = gb.run_trajectory(ep["depth_sub"], ep["clip"], ep["pos"], ep["heading"])
+    torch.cuda.synchronize()
+    for b, c in enumerate(grid2.grid_map_numpy()):
+        assert np.array_equal(c, last[b])
+    fts = grid2.grid_fts_torch()
+    for b in range(B):
+        assert torch.equal(fts[b].cpu(), torch.from_numpy(np.ascontiguousarray(ep["clip"][b][:, :, 1:].reshape(-1, 768))))
+
+
 def test_grid_update_8x8_config1():
     """BASELINE config 1: 8x8 grid, 512-d features, one viewpoint (the reference hard-codes 14/768; oracle is parametric)."""
     ep = synth.make_episodes(1, 1, seed=1, dim=512)

@@ -27,6 +27,45 @@ def test_grid_oracle_matches_reference_cells(case):
     np.testing.assert_allclose(np.stack(pos), gold["pos_fts_last"], atol=1e-6, rtol=0)
 
 
+def test_grid_oracle_matches_pretraining_dataset():
+    """SURVEY 8a row 19, grid half: the pretraining dataset's own getGlobalMap (pretrain_src/data/dataset.py:351-473) run over
+    whole ground-truth paths gave tests/golden/grid_pretrain_s51.npz; the oracle's R2R arithmetic reproduces its cell ids bit
+    for bit at every step, its gridmap_pos_fts, and the extra target_patch_id label."""
+    from oracle import grid_oracle as go
+    case = H.PRETRAIN_GRID_CASE
+    gold = np.load(os.path.join(H.GOLD, "grid_pretrain_s%d.npz" % case["seed"]))
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    ep["heading"] = synth.pretrain_headings(ep)
+    T = case["steps"]
+    for b in range(case["batch"]):
+        st = go.GridState()
+        for t in range(T):
+            _, cell, half = go.grid_step(st, ep["depth_sub"][b, t], None, ep["pos"][b, t], float(ep["heading"][b, t]))
+            assert np.array_equal(cell, gold["cell_b%d_t%d" % (b, t)].astype(np.int32)), "b=%d t=%d" % (b, t)
+            np.testing.assert_allclose(go.gridmap_pos_fts(half), gold["pos_fts_b%d" % b][t], atol=1e-6, rtol=0)
+            nxt = ep["pos"][b, t + 1] if t + 1 < T else ep["pos"][b, t]
+            got = go.target_patch_id(ep["pos"][b, t], nxt, float(ep["heading"][b, t]), half, is_last=(t + 1 == T))
+            assert got == int(gold["target_b%d" % b][t]), "target b=%d t=%d" % (b, t)
+
+
+def test_host_target_patch_id_matches_pretraining_dataset():
+    """gridmm_b200.env.target_patch_id (host scalar code of the product) against the same golden labels, with the oracle's
+    half_len standing in for GridBatch.half_len (the GPU test checks that one bit-exactly)."""
+    from gridmm_b200.env import target_patch_id
+    case = H.PRETRAIN_GRID_CASE
+    gold = np.load(os.path.join(H.GOLD, "grid_pretrain_s%d.npz" % case["seed"]))
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    ep["heading"] = synth.pretrain_headings(ep)
+    from oracle import grid_oracle as go
+    T = case["steps"]
+    for b in range(case["batch"]):
+        st = go.GridState()
+        for t in range(T):
+            _, _, half = go.grid_step(st, ep["depth_sub"][b, t], None, ep["pos"][b, t], float(ep["heading"][b, t]))
+            nxt = ep["pos"][b, t + 1] if t + 1 < T else None
+            assert target_patch_id(ep["pos"][b, t], nxt, float(ep["heading"][b, t]), half) == int(gold["target_b%d" % b][t])
+
+
 @pytest.mark.parametrize("name", sorted(H.NAV_CASES))
 def test_nav_oracle_matches_reference_forward(name):
     from oracle import model_oracle as mo
