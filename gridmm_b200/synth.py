@@ -182,6 +182,63 @@ def make_pano_inputs(batch, seed=0, n_views=36, n_objs=0, dim=768, loc_dim=7):
     return out
 
 
+def make_pretrain_batch(batch, seed=0, txt_len=40, max_steps=4, n_views=36, n_cands=3, dim=768, vocab=30522, min_txt=8):
+    """One collated pretraining batch without objects, in the layout pretrain_src/data/tasks.py's collate functions hand to
+    `GlocalTextPathCMT.forward` / `forward_mlm` (pretrain_src/model/vilmodel.py:668-674, 767-771), minus the grid tensors
+    (those come from the grid build over the same paths).  Episode b walks steps[b] viewpoints "v{b}_{t}"; each panorama has
+    n_views views of which the first n_cands are navigable candidates: the next viewpoint of the path, the previous one, and
+    fresh unvisited nodes "u{b}_{t}_{j}".  gmap = [stop] + visited + unvisited (tasks.py order)."""
+    rng = np.random.default_rng(seed + 15485863)
+    f32 = np.float32
+    B, L = batch, txt_len
+    steps = rng.integers(2, max_steps + 1, size=B)
+    steps[0] = max_steps
+    txt_lens = rng.integers(min_txt, L + 1, size=B)
+    txt_lens[0] = L
+    txt_ids = rng.integers(1000, vocab, size=(B, L)).astype(np.int64) * (np.arange(L)[None, :] < txt_lens[:, None])
+    n_tot = int(steps.sum())
+    traj_view_img_fts = rng.standard_normal((n_tot, n_views, dim), dtype=f32)
+    traj_loc_fts = rng.standard_normal((n_tot, n_views, 7), dtype=f32)
+    traj_nav_types = np.zeros((n_tot, n_views), dtype=np.int64)
+    traj_nav_types[:, :n_cands] = 1
+    traj_vpids, traj_cand_vpids, gmap_vpids, gmap_step = [], [], [], []
+    for b in range(B):
+        T = int(steps[b])
+        vps = ["v%d_%d" % (b, t) for t in range(T)]
+        cands_b, unvisited = [], []
+        for t in range(T):
+            c = []
+            if t + 1 < T:
+                c.append(vps[t + 1])
+            if t > 0:
+                c.append(vps[t - 1])
+            j = 0
+            while len(c) < n_cands:
+                u = "u%d_%d_%d" % (b, t, j)
+                c.append(u); unvisited.append(u); j += 1
+            cands_b.append(c)
+        traj_vpids.append(vps)
+        traj_cand_vpids.append(cands_b)
+        gmap_vpids.append([None] + vps + unvisited)
+        gmap_step.append([0] + list(range(1, T + 1)) + [0] * len(unvisited))
+    gmap_lens = np.array([len(g) for g in gmap_vpids], dtype=np.int64)
+    G = int(gmap_lens.max())
+    gmap_masks = np.arange(G)[None, :] < gmap_lens[:, None]
+    gmap_step_ids = np.zeros((B, G), dtype=np.int64)
+    for b in range(B):
+        gmap_step_ids[b, :gmap_lens[b]] = gmap_step[b]
+    gmap_pos_fts = rng.standard_normal((B, G, 7), dtype=f32) * gmap_masks[:, :, None]
+    vp_pos_fts = rng.standard_normal((B, 1 + n_views, 14), dtype=f32)
+    return {
+        "txt_ids": txt_ids, "txt_lens": txt_lens.astype(np.int64),
+        "traj_view_img_fts": traj_view_img_fts, "traj_loc_fts": traj_loc_fts, "traj_nav_types": traj_nav_types,
+        "traj_step_lens": [int(x) for x in steps], "traj_vp_view_lens": np.full(n_tot, n_views, dtype=np.int64),
+        "traj_vpids": traj_vpids, "traj_cand_vpids": traj_cand_vpids,
+        "gmap_lens": gmap_lens, "gmap_step_ids": gmap_step_ids, "gmap_pos_fts": gmap_pos_fts,
+        "gmap_pair_dists": np.zeros((B, G, G), dtype=f32), "gmap_vpids": gmap_vpids, "vp_pos_fts": vp_pos_fts,
+    }
+
+
 def to_torch(nav, device="cpu"):
     """numpy nav-input dict -> torch tensors with the reference's dtypes."""
     import torch

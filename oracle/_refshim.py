@@ -252,6 +252,35 @@ def ref_pretrain_traj(ds, scan, headings, depth_u16, clip_f32, pos_xy):
     return cells, pos_fts, targets, grid_fts.reshape((-1, clip_f32[0].shape[-1]))
 
 
+def make_pretrain_config(num_l_layers=9, num_pano_layers=2, num_x_layers=4):
+    """BertConfig + the keys of pretrain_src/config/r2r_model_config.json."""
+    from transformers import BertConfig
+    c = BertConfig()
+    for k, v in dict(pred_head_dropout_prob=0.1, image_feat_size=768, image_prob_size=1000, angle_feat_size=4, obj_feat_size=0,
+                     obj_prob_size=0, num_l_layers=num_l_layers, num_x_layers=num_x_layers, num_pano_layers=num_pano_layers,
+                     max_action_steps=100, update_lang_bert=True, use_lang2visn_attn=True, graph_sprels=True,
+                     glocal_fuse=True).items():
+        setattr(c, k, v)
+    return c
+
+
+def load_reference_pretrain_model(**cfg):
+    """The pretraining trunk `GlocalTextPathCMT` (pretrain_src/model/vilmodel.py:640-855), eval mode, imported under the alias
+    package `pretrain_model`; `init_weights` is a no-op as for the navigation model (shim 2)."""
+    import importlib
+    _install_stubs()
+    if "pretrain_model" not in sys.modules:
+        pkg = types.ModuleType("pretrain_model")
+        pkg.__path__ = [os.path.join(REF_ROOT, "pretrain_src", "model")]
+        sys.modules["pretrain_model"] = pkg
+    vil = importlib.import_module("pretrain_model.vilmodel")
+    cls = vil.GlocalTextPathCMT
+    cls.init_weights = lambda self: None
+    model = cls(make_pretrain_config(**cfg))
+    model.eval()
+    return model
+
+
 # ----------------------------------------------------------------------------------------------- continuous-env variant
 CE_ROOT = os.path.join(REF_ROOT, "VLN_CE", "vlnce_baselines", "models")
 

@@ -8,6 +8,8 @@ seeds by gridmm_b200/synth.py (numpy PCG64 streams are platform independent), on
                          cell ids per step (int16, -1 masked) and gridmap_pos_fts of the last step
   grid_pretrain_s{seed}.npz  the pretraining dataset's getGlobalMap (pretrain_src/data/dataset.py:351-473) over whole ground-truth
                          paths (as get_traj_pano_fts :482-507 drives it): cell ids per step, gridmap_pos_fts and target_patch_id
+  pretrain_small.npz     the pretraining trunk GlocalTextPathCMT.forward / forward_mlm (pretrain_src/model/vilmodel.py:668-855,
+                         fp16 pooling) on one collated batch: gmap / vp embeddings, grid-encoded gmap rows, MLM text states
   nav_{name}.npz         GlocalTextPathNavCMT.forward('navigation', ...) (map_nav_src/models/vilmodel.py:782-918):
                          all five logit tensors + gmap/vp embeddings
 """
@@ -85,6 +87,49 @@ def make_pretrain_grid():
     path = os.path.join(GOLD, "grid_pretrain_s%d.npz" % case["seed"])
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), {k: out[k].tolist() for k in out if k.startswith("target")})
+
+
+PRETRAIN_MODEL_CASE = dict(seed=61, batch=3, max_steps=4, txt_len=40, model=dict(num_l_layers=2, num_pano_layers=2, num_x_layers=4))
+
+
+def make_pretrain_model():
+    """pretrain_small.npz: the pretraining trunk's `forward` and `forward_mlm` (pretrain_src/model/vilmodel.py:668-855) on a
+    collated batch whose grids come from the pretraining dataset's own getGlobalMap; pretrain_small_spec.json: parameter names
+    and shapes of that model (the weights themselves are regenerated from the seed by synth.make_weights)."""
+    import json
+    case = PRETRAIN_MODEL_CASE
+    B, seed = case["batch"], case["seed"]
+    model = _refshim.load_reference_pretrain_model(**case["model"])
+    shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
+    w = synth.make_weights(shapes, seed=seed)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    assert model.grid_proj.weight.dtype == torch.float16
+    pb = synth.make_pretrain_batch(B, seed=seed, txt_len=case["txt_len"], max_steps=case["max_steps"])
+    ep = synth.make_episodes(B, case["max_steps"], seed=seed, dim=768)
+    heads = synth.pretrain_headings(ep)
+    ds = _refshim.load_reference_pretrain_data()
+    gfts, gmap, gpos = [], [], []
+    for b in range(B):
+        T = pb["traj_step_lens"][b]
+        cells, pos_fts, _, fts = _refshim.ref_pretrain_traj(
+            ds, "scan%d" % b, [float(x) for x in heads[b, :T]], [synth.expand_depth(ep["depth_sub"][b, t]) for t in range(T)],
+            [ep["clip"][b, t].astype(np.float32) for t in range(T)], ep["pos"][b, :T])
+        gfts.append(torch.from_numpy(fts).to(torch.float16))                # tasks.py:95
+        gmap.append(torch.from_numpy(cells[-1]).to(torch.int64))             # tasks.py:96
+        gpos.append(pos_fts[-1])
+    t = lambda k: torch.from_numpy(pb[k])
+    args = (t("txt_ids"), t("txt_lens"), t("traj_view_img_fts"), None, t("traj_loc_fts"), t("traj_nav_types"), pb["traj_step_lens"],
+            t("traj_vp_view_lens"), None, pb["traj_vpids"], pb["traj_cand_vpids"], t("gmap_lens"), t("gmap_step_ids"),
+            t("gmap_pos_fts"), t("gmap_pair_dists"), pb["gmap_vpids"], t("vp_pos_fts"), gfts, gmap)
+    gp = torch.from_numpy(np.stack(gpos).astype(np.float32))
+    with torch.no_grad():
+        gmap_e, vp_e, grid_g = model.forward(*args, None, gp)
+        txt = model.forward_mlm(*args, gp)
+    save = {"gmap_embeds": gmap_e.numpy(), "vp_embeds": vp_e.numpy(), "grid_gmap_embeds": grid_g.numpy(), "mlm_txt_embeds": txt.numpy()}
+    path = os.path.join(GOLD, "pretrain_small.npz")
+    np.savez_compressed(path, **save)
+    json.dump(shapes, open(os.path.join(GOLD, "pretrain_small_spec.json"), "w"), indent=0)
+    print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()})
 
 
 def reference_nav(ep_kw, nav_kw, model_kw):
@@ -210,7 +255,7 @@ if __name__ == "__main__":
         raise SystemExit("reference not available at %s" % _refshim.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain"]
+    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain", "pretrain_model"]
     if "grid" in which:
         make_grid()
     if "nav" in which:
@@ -221,3 +266,5 @@ if __name__ == "__main__":
         make_ce()
     if "pretrain" in which:
         make_pretrain_grid()
+    if "pretrain_model" in which:
+        make_pretrain_model()

@@ -172,12 +172,12 @@ def fuse_logits(global_logits, local_logits, gmap_vpids, gmap_visited_masks, vp_
     return fused
 
 
-def _nav_trunk(sd, batch, n_x_layers, n_cells):
+def _nav_trunk(sd, batch, n_x_layers, n_cells, fts_dtype=torch.float32, stop_after_map=False):
     """Everything of forward_navigation_per_step up to the fused [gmap; vp] embeddings (vilmodel.py:788-856; identical
     in VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:714-789)."""
     txt, txt_masks = batch["txt_embeds"], batch["txt_masks"]
     gmap_masks = batch["gmap_masks"]
-    gmi, nonempty = grid_pool(sd, txt, batch["grid_fts"], batch["grid_map"], n_cells)
+    gmi, nonempty = grid_pool(sd, txt, batch["grid_fts"], batch["grid_map"], n_cells, fts_dtype=fts_dtype)
     pos = _ln(sd, "grid_pos_embeddings.1", _lin(sd, "grid_pos_embeddings.0", batch["gridmap_pos_fts"]), 1e-12)
     gmi = gmi + pos                                                                     # :816
     cells, cell_masks, C = compact_cells(gmi, nonempty)                                 # :813-823
@@ -191,6 +191,8 @@ def _nav_trunk(sd, batch, n_x_layers, n_cells):
     m = prenorm_encoder(sd, "grid_encoder", m, mm, 1)                                   # :840
     m = crossmodal_encoder(sd, "grid_txt_encoder", 1, txt, txt_masks, m, mm)            # :841
     gmap2 = m[:, C:]
+    if stop_after_map:          # the pretraining MLM path leaves the trunk here (pretrain_src/model/vilmodel.py:836-838)
+        return None, vp, gmap2, {"map_embeds": m}
     kv = torch.cat([m, txt], 1)
     kvm = torch.cat([mm, txt_masks], 1)
     q = torch.cat([gmap2, vp], 1)

@@ -26,6 +26,7 @@ AUX_CASES = {
 
 
 PRETRAIN_GRID_CASE = dict(seed=51, batch=3, steps=7)      # mirrors oracle/make_golden.py
+PRETRAIN_MODEL_CASE = dict(seed=61, batch=3, max_steps=4, txt_len=40, model=dict(num_l_layers=2, num_pano_layers=2, num_x_layers=4))
 CE_GRID_CASE = dict(seed=41, batch=3, steps=6)
 CE_NAV_CASE = (dict(batch=3, steps=3, seed=42), dict(txt_len=24, gmap_len=10, n_views=12, n_objs=0))
 
@@ -98,3 +99,24 @@ def finite_close(a, b, atol):
     err = (a[fa] - b[fb]).abs().max().item() if fa.any() else 0.0
     assert err <= atol, "max abs error %.3e > %.1e" % (err, atol)
     return err
+
+
+def pretrain_batch(case):
+    """The collated pretraining batch of oracle/make_golden.py's PRETRAIN_MODEL_CASE, with the grid tensors from the oracle's grid
+    build over each path (bit-identical to the pretraining dataset's, see test_grid_oracle_matches_pretraining_dataset)."""
+    from oracle import grid_oracle as go
+    B = case["batch"]
+    pb = synth.make_pretrain_batch(B, seed=case["seed"], txt_len=case["txt_len"], max_steps=case["max_steps"])
+    ep = synth.make_episodes(B, case["max_steps"], seed=case["seed"], dim=768)
+    heads = synth.pretrain_headings(ep)
+    batch = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in pb.items()}
+    gfts, gmap, gpos = [], [], []
+    for b in range(B):
+        st = go.GridState()
+        for t in range(pb["traj_step_lens"][b]):
+            f, c, h = go.grid_step(st, ep["depth_sub"][b, t], ep["clip"][b, t], ep["pos"][b, t], float(heads[b, t]))
+        gfts.append(torch.from_numpy(np.ascontiguousarray(f)))                       # fp16 [588 T_b, 768]
+        gmap.append(torch.from_numpy(c.astype(np.int64)))
+        gpos.append(go.gridmap_pos_fts(h))
+    batch.update(grid_fts=gfts, grid_map=gmap, gridmap_pos_fts=torch.from_numpy(np.stack(gpos).astype(np.float32)))
+    return batch

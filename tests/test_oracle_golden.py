@@ -66,6 +66,29 @@ def test_host_target_patch_id_matches_pretraining_dataset():
             assert target_patch_id(ep["pos"][b, t], nxt, float(ep["heading"][b, t]), half) == int(gold["target_b%d" % b][t])
 
 
+def test_pretrain_oracle_matches_reference_trunk():
+    """SURVEY 8a row 19, model half: oracle/pretrain_oracle.py against the outputs of the reference's own pretraining trunk
+    (`forward` and `forward_mlm`, fp16 pooling) on one collated batch -- tests/golden/pretrain_small.npz."""
+    import json
+    from oracle import pretrain_oracle as po
+    case = H.PRETRAIN_MODEL_CASE
+    gold = np.load(os.path.join(H.GOLD, "pretrain_small.npz"))
+    shapes = json.load(open(os.path.join(H.GOLD, "pretrain_small_spec.json")))
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_weights(shapes, seed=case["seed"]).items()}
+    batch = H.pretrain_batch(case)
+    torch.set_num_threads(os.cpu_count() or 1)
+    kw = dict(n_l_layers=case["model"]["num_l_layers"], n_pano_layers=case["model"]["num_pano_layers"],
+              n_x_layers=case["model"]["num_x_layers"])
+    with torch.no_grad():
+        gmap_e, vp_e, grid_g = po.forward(sd, batch, **kw)
+        txt = po.forward_mlm(sd, batch, **kw)
+    # fp32 CPU vs fp32 CPU except the fp16 pooling, where both sides call the same torch half kernels on the same values
+    for got, key in ((gmap_e, "gmap_embeds"), (vp_e, "vp_embeds"), (grid_g, "grid_gmap_embeds"), (txt, "mlm_txt_embeds")):
+        assert tuple(got.shape) == gold[key].shape, key
+        err = (got - torch.from_numpy(gold[key])).abs().max().item()
+        assert err <= 5e-5, "%s: max abs error %.3e" % (key, err)
+
+
 @pytest.mark.parametrize("name", sorted(H.NAV_CASES))
 def test_nav_oracle_matches_reference_forward(name):
     from oracle import model_oracle as mo
