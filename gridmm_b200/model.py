@@ -46,6 +46,10 @@ class NavConfig:
         self.graph_sprels = True
         self.glocal_fuse = True
         self.grid_w = 14             # GLOBAL_WIDTH / GLOBAL_HEIGHT, map_nav_src/r2r/env.py:43-44 (hard-coded there)
+        # pretraining trunk (pretrain_src/model/vilmodel.py:640-666): no action heads, no sprel_linear, and with
+        # use_lang2visn_attn every GraphLXRTXLayer also owns the lang_* blocks that forward_mlm runs (:369-385)
+        self.pretrain_trunk = False
+        self.use_lang2visn_attn = False
         for k, v in kw.items():
             setattr(self, k, v)
         if self.hidden_size != HID or self.num_attention_heads != HEADS:
@@ -71,8 +75,12 @@ def _ffn(pre_i, pre_o, inter, spec):
     spec[pre_o + ".LayerNorm.bias"] = ((HID,), "b")
 
 
-def _lxrt(pre, inter, spec):
-    """GraphLXRTXLayer parameters in the reference's registration order (vilmodel.py:381-397)."""
+def _lxrt(pre, inter, spec, lang=False):
+    """GraphLXRTXLayer parameters in the reference's registration order (vilmodel.py:381-397; with `lang` the
+    use_lang2visn_attn blocks of the pretraining model come first, pretrain_src/model/vilmodel.py:373-385)."""
+    if lang:
+        _attn_self(None, pre + ".lang_self_att", spec)
+        _ffn(pre + ".lang_inter", pre + ".lang_output", inter, spec)
     _attn_self(None, pre + ".visn_self_att", spec)
     _ffn(pre + ".visn_inter", pre + ".visn_output", inter, spec)
     q = pre + ".visual_attention"
@@ -153,21 +161,26 @@ def param_spec(cfg):
     if cfg.num_pano_layers > 0:
         _prenorm(p + ".pano_encoder", cfg.num_pano_layers, inter, s)
     _lin_ln("local_encoder.vp_pos_embeddings", cfg.angle_feat_size * 2 + 6, s)
+    trunk = getattr(cfg, "pretrain_trunk", False)
+    lang = trunk and getattr(cfg, "use_lang2visn_attn", False)
     for i in range(cfg.num_x_layers):
-        _lxrt("local_encoder.encoder.x_layers.%d" % i, inter, s)
+        _lxrt("local_encoder.encoder.x_layers.%d" % i, inter, s, lang)
     _lin_ln("global_encoder.gmap_pos_embeddings", cfg.angle_feat_size + 3, s)
     s["global_encoder.gmap_step_embeddings.weight"] = ((cfg.max_action_steps, HID), "w")
-    if cfg.graph_sprels:
+    if cfg.graph_sprels and not trunk:
         s["global_encoder.sprel_linear.weight"] = ((1, 1), "w")
         s["global_encoder.sprel_linear.bias"] = ((1,), "b")
-    _cls("global_sap_head", HID, s)
-    _cls("local_sap_head", HID, s)
-    _cls("grid_sap_head", HID, s)
+    if not trunk:
+        _cls("global_sap_head", HID, s)
+        _cls("local_sap_head", HID, s)
+        _cls("grid_sap_head", HID, s)
     _prenorm("grid_encoder", 1, inter, s)
-    _lxrt("grid_txt_encoder.x_layers.0", inter, s)
+    _lxrt("grid_txt_encoder.x_layers.0", inter, s, lang)
     _lin_ln("grid_pos_embeddings", 5, s)
     s["text_proj.weight"] = ((HID, HID), "w"); s["text_proj.bias"] = ((HID,), "b")
     s["grid_proj.weight"] = ((HID, HID), "w"); s["grid_proj.bias"] = ((HID,), "b")
+    if trunk:
+        return s
     if cfg.glocal_fuse:
         _cls("sap_fuse_linear", 2 * HID, s)
     if cfg.obj_feat_size > 0:
@@ -533,7 +546,7 @@ class GlocalTextPathNavCMT(nn.Module):
     def forward_navigation_per_step(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                                     gmap_pair_dists, gmap_visited_masks, gmap_vpids, vp_img_embeds, vp_pos_fts, vp_masks,
                                     vp_nav_masks, vp_obj_masks, vp_cand_vpids, grid_fts, grid_map, gridmap_pos_fts,
-                                    grid=None, return_intermediates=False, ce_candidate_lengths=None):
+                                    grid=None, return_intermediates=False, ce_candidate_lengths=None, _mode="nav"):
         """vilmodel.py:782-918.  `grid` (a gridmm_b200.env.GridBatch) replaces grid_fts/grid_map/gridmap_pos_fts when the
         grid was built on the device; otherwise the reference-format lists are uploaded and sorted first.
         (`gmap_pair_dists` is accepted and ignored, as in the reference's navigation forward.)"""
@@ -546,9 +559,11 @@ class GlocalTextPathNavCMT(nn.Module):
         f32, u8 = torch.float32, torch.uint8
         ce_maxc = int(max(ce_candidate_lengths)) if ce_candidate_lengths is not None else 0
         # host part of the logit fusion (the reference's vpid-string loops) -> small int arrays
-        if ce_maxc:
+        if ce_maxc or _mode != "nav":
             fuse_src, bw_mask = np.zeros((B, G), np.int32), np.zeros((B, V), np.uint8)
             gmap_visited_masks = torch.zeros(B, G, dtype=torch.uint8)
+            if vp_nav_masks is None:
+                vp_nav_masks = torch.zeros(B, V, dtype=torch.uint8)
         else:
             fuse_src, bw_mask = build_fuse_index(gmap_vpids, gmap_visited_masks, vp_cand_vpids, G, V)
         st = {
@@ -568,6 +583,8 @@ class GlocalTextPathNavCMT(nn.Module):
             "bw_mask": self._stage("bw_mask", torch.from_numpy(bw_mask), (B, V), u8),
         }
         dims = (B, L, G, V, has_obj, ce_maxc)
+        if _mode != "nav":
+            return self._device_forward(st, grid, dims, False, False, mode=_mode)
         if getattr(self, "use_cuda_graph", False) and not return_intermediates:
             sig = dims + (st["gmap_pos"].shape[1], st["vp_pos"].shape[1], grid.n_cells, grid.t_cap, grid.cap, grid.feat_dim,
                           grid.slot_rows, grid.view_rows, grid.tok_off, grid.slab.data_ptr(), grid.slots.data_ptr(),
@@ -589,8 +606,10 @@ class GlocalTextPathNavCMT(nn.Module):
         dev = next(self.parameters()).device
         return self.buf("out_" + name, shape, torch.float32) if static else torch.empty(shape, dtype=torch.float32, device=dev)
 
-    def _device_forward(self, st, grid, dims, return_intermediates, static_out):
-        """Everything below launches only gridmm_* kernels (plus a few tiny mask copies) on persistent buffers."""
+    def _device_forward(self, st, grid, dims, return_intermediates, static_out, mode="nav"):
+        """Everything below launches only gridmm_* kernels (plus a few tiny mask copies) on persistent buffers.
+        mode: "nav" (the navigation step), or the two pretraining exits: "mlm" leaves after the fusion inputs are built
+        (forward_mlm), "trunk" after the fusion encoder (GlocalTextPathCMT.forward), both before any action head."""
         cfg = self.config
         B, L, G, V, has_obj, ce_maxc = dims
         NC = grid.n_cells
@@ -659,6 +678,8 @@ class GlocalTextPathNavCMT(nn.Module):
                                              self.P(ve + ".1.weight"), self.P(ve + ".1.bias"), st["vp_img"]))
         nx = cfg.num_x_layers
         le = "local_encoder.encoder.x_layers.%d"
+        if mode == "mlm":
+            return {"ctx32": x32, "ctx16": x16, "ctx_mask": q_mask, "txt16": txt16}
         names_w, names_b = [], []
         for i in range(nx):
             names_w += [(le % i) + ".visual_attention.att.key.weight", (le % i) + ".visual_attention.att.value.weight"]
@@ -669,6 +690,9 @@ class GlocalTextPathNavCMT(nn.Module):
             self._lxrt_layer(le % i, x32, x16, q_mask, kvp[:, 2 * HID * i: 2 * HID * i + HID],
                              kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], kv_mask, B, Q, KC, "x", ctx_var=(kv_off, kv_cnt))
 
+        if mode == "trunk":
+            x3 = x32.view(B, Q, HID)
+            return {"gmap_embeds": x3[:, :G], "vp_embeds": x3[:, G:], "grid_gmap_embeds": map32.view(B, S, HID)[:, NC:].clone()}
         # ---- heads and logit fusion (vilmodel.py:859-907)
         if ce_maxc:
             hg16 = self.buf("hg16", (B * G, 3 * HID), f16)
@@ -790,6 +814,87 @@ class GlocalTextPathNavCMT(nn.Module):
         if cfg.num_pano_layers > 0:
             self._prenorm_encoder(ie + ".pano_encoder", cfg.num_pano_layers, x32, x16, masks.view(torch.uint8).contiguous(), B, n, "pano")
         return x32.view(B, n, HID), masks
+
+    # ------------------------------------------------------------------ pretraining trunk
+    def _aggregate_gmap(self, pano, lens, step_lens, traj_vpids, traj_cand_vpids, gmap_vpids):
+        """Node features of the global map from the panorama tokens of a whole path (GlobalMapEncoder._aggregate_gmap_features,
+        pretrain_src/model/vilmodel.py:578-612; the agent does the same per step in map_nav_src, r2r/agent.py:309-320):
+        visited node = mean of its own panorama, unvisited node = mean of the candidate-view tokens that pointed at it while it
+        was unvisited.  Host-driven gathers over device tensors, like the reference; [stop] row of zeros first."""
+        dev = pano.device
+        rows, row0 = [], 0
+        for i, T in enumerate(step_lens):
+            e, n = pano[row0:row0 + T], lens[row0:row0 + T]
+            row0 += T
+            keep = (torch.arange(e.shape[1], device=dev)[None, :] < n[:, None])
+            e = e * keep[:, :, None]
+            own, seen_from = {}, {}
+            for t in range(T):
+                own[traj_vpids[i][t]] = e[t].sum(0) / n[t]
+                for j, vp in enumerate(traj_cand_vpids[i][t]):
+                    if vp not in own:
+                        seen_from.setdefault(vp, []).append(e[t, j])
+            rows.append(torch.stack([own[vp] if vp in own else torch.stack(seen_from[vp], 0).mean(0) for vp in gmap_vpids[i][1:]], 0))
+        G = 1 + max(r.shape[0] for r in rows)
+        out = torch.zeros(len(rows), G, HID, dtype=torch.float32, device=dev)
+        for i, r in enumerate(rows):
+            out[i, 1:1 + r.shape[0]] = r
+        return out
+
+    @torch.no_grad()
+    def forward_pretrain(self, batch, task="sap"):
+        """The pretraining trunk on one collated batch (pretrain_src/model/vilmodel.py:668-764 `forward`, :767-855 `forward_mlm`):
+        text encoder, every panorama of every path through the image embeddings + pano encoder, gmap aggregation, then the same
+        grid pooling / grid encoders / fusion encoder kernels as the navigation step.
+          task "sap" (also mrc / og) -> (gmap_embeds, vp_embeds, grid-encoded gmap rows)
+          task "mlm"                 -> text states after the text-queries-[gmap'; vp] layers (forward_lang2visn, :404-415)
+        The reference pools in fp16 here (:685-699); this path keeps fp16 operands with fp32 accumulation, which is at least as
+        accurate.  `batch["grid"]` may hold a GridBatch (GridMapBuilder.run_trajectory) instead of the grid_fts / grid_map lists."""
+        cfg = self.config
+        dev = next(self.parameters()).device
+        txt_ids = torch.as_tensor(batch["txt_ids"]).to(dev)
+        txt_lens = torch.as_tensor(batch["txt_lens"]).to(dev)
+        B, L = int(txt_ids.shape[0]), int(txt_ids.shape[1])
+        txt_masks = torch.arange(L, device=dev)[None, :] < txt_lens[:, None]
+        txt = self.forward_text(txt_ids, txt_masks)
+        if batch.get("traj_obj_img_fts") is not None:
+            raise NotImplementedError("object tokens in pretraining batches (REVERIE / SOON) are not wired yet")
+        pano, _ = self.forward_panorama_per_step(batch["traj_view_img_fts"], None, batch["traj_loc_fts"], batch["traj_nav_types"],
+                                                 batch["traj_vp_view_lens"], None)
+        lens = torch.as_tensor(batch["traj_vp_view_lens"]).to(dev)
+        step_lens = [int(x) for x in batch["traj_step_lens"]]
+        gmap_img = self._aggregate_gmap(pano, lens, step_lens, batch["traj_vpids"], batch["traj_cand_vpids"], batch["gmap_vpids"])
+        gmap_lens = torch.as_tensor(batch["gmap_lens"]).to(dev)
+        G = int(gmap_img.shape[1])
+        gmap_masks = torch.arange(G, device=dev)[None, :] < gmap_lens[:, None]
+        # LocalVPEncoder.vp_input_embedding (:541-555): [stop] + the tokens of each path's last panorama
+        last = torch.tensor(np.cumsum(step_lens) - 1, device=dev)
+        vp_lens = lens[last] + 1
+        V = int(vp_lens.max())
+        vp_img = torch.cat([torch.zeros(B, 1, HID, device=dev), pano[last]], 1)[:, :V].contiguous()
+        vp_masks = torch.arange(V, device=dev)[None, :] < vp_lens[:, None]
+        mode = "mlm" if task.startswith("mlm") else "trunk"
+        out = self.forward_navigation_per_step(
+            txt, txt_masks, gmap_img, batch["gmap_step_ids"], batch["gmap_pos_fts"], gmap_masks, None, None, None, vp_img,
+            torch.as_tensor(batch["vp_pos_fts"])[:, :V], vp_masks, None, None, None, batch.get("grid_fts"), batch.get("grid_map"),
+            batch.get("gridmap_pos_fts"), grid=batch.get("grid"), _mode=mode)
+        if mode == "trunk":
+            return out["gmap_embeds"], out["vp_embeds"], out["grid_gmap_embeds"]
+        # ---- forward_mlm: text tokens are the queries, [gmap'; vp] (constant across layers) the context
+        Q = G + V
+        t32 = txt.reshape(B * L, HID).clone()
+        t16 = out["txt16"].clone()
+        txt_mask_u8 = txt_masks.to(torch.uint8).contiguous()
+        for i in range(cfg.num_x_layers):
+            pre = "local_encoder.encoder.x_layers.%d" % i
+            va = pre + ".visual_attention.att"
+            kv = self.buf("mlm_kv16", (B * Q, 2 * HID), torch.float16)
+            ops.linear(out["ctx16"], self.W16(va + ".key.weight", va + ".value.weight"), self.B32(va + ".key.bias", va + ".value.bias"),
+                       out_f16=kv)
+            self._cross_post(t32, t16, pre + ".visual_attention", kv[:, :HID], kv[:, HID:], out["ctx_mask"], B, L, Q, "mlm")
+            self._self_post(t32, t16, pre + ".lang_self_att", txt_mask_u8, B, L, "mlm")
+            self._ffn_post(t32, t16, pre + ".lang_inter", pre + ".lang_output", B * L, "mlm")
+        return t32.view(B, L, HID)
 
     def forward_navigation_ce(self, txt_embeds, txt_masks, gmap_img_embeds, gmap_step_ids, gmap_pos_fts, gmap_masks,
                               vp_img_embeds, vp_pos_fts, vp_masks, vp_nav_masks, grid_fts, grid_map_indexs, gridmap_pos_fts,
