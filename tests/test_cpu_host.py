@@ -145,3 +145,88 @@ def test_head_pack_and_table_restate_cls_prediction():
     obj = t[t[:, 1] == 3 * 768]
     loc = t[t[:, 1] == 1 * 768]
     assert (obj[:, 0] == loc[:, 0]).all() and (obj[:, 2] >= o_obj).all() and (t[t[:, 3] == 1][:, 1] >= 4 * 768).all()
+
+
+def test_pretraining_param_spec_equals_reference_state_dict():
+    """NavConfig(pretrain_trunk=True, use_lang2visn_attn=True): names, shapes and order of the parameter tree equal the reference
+    pretraining trunk's state_dict (pretrain_src/model/vilmodel.py:640-666), recorded by oracle/make_golden.py next to the golden
+    outputs -- so `load_state_dict(strict=True)` of a pretraining checkpoint's `bert.*` tensors works."""
+    import json
+    from gridmm_b200.model import GlocalTextPathNavCMT, NavConfig, param_spec
+    kw = H.PRETRAIN_MODEL_CASE["model"]
+    ref = json.load(open(os.path.join(H.GOLD, "pretrain_small_spec.json")))
+    cfg = NavConfig(pretrain_trunk=True, use_lang2visn_attn=True, **kw)
+    spec = param_spec(cfg)
+    assert list(spec.keys()) == list(ref.keys())
+    assert {k: list(v[0]) for k, v in spec.items()} == ref
+    m = GlocalTextPathNavCMT(cfg)
+    assert list(m.state_dict().keys()) == list(ref.keys())
+    for absent in ("global_sap_head.net.0.weight", "global_encoder.sprel_linear.weight", "sap_fuse_linear.net.0.weight"):
+        assert absent not in spec
+    # the navigation model's tree is untouched by the new flags
+    assert len(param_spec(NavConfig())) == 373
+
+
+def test_gmap_aggregation_glue_equals_oracle():
+    """GlocalTextPathNavCMT._aggregate_gmap (torch gathers, device-agnostic host glue of forward_pretrain) against the oracle's
+    restatement of GlobalMapEncoder._aggregate_gmap_features (pretrain_src/model/vilmodel.py:578-612)."""
+    from gridmm_b200.model import GlocalTextPathNavCMT
+    from oracle import pretrain_oracle as po
+    case = H.PRETRAIN_MODEL_CASE
+    pb = synth.make_pretrain_batch(case["batch"], seed=case["seed"], txt_len=case["txt_len"], max_steps=case["max_steps"])
+    n_tot = sum(pb["traj_step_lens"])
+    g = torch.Generator().manual_seed(5)
+    pano = torch.randn(n_tot, 36, 768, generator=g)
+    lens = torch.from_numpy(pb["traj_vp_view_lens"]).clone()
+    lens[1] = 30                                        # a shorter panorama exercises the validity mask
+    m = GlocalTextPathNavCMT(H.make_config(pretrain_trunk=True, use_lang2visn_attn=True, **case["model"]))
+    got = m._aggregate_gmap(pano, lens, pb["traj_step_lens"], pb["traj_vpids"], pb["traj_cand_vpids"], pb["gmap_vpids"])
+    ref = po.aggregate_gmap_features(list(torch.split(pano, pb["traj_step_lens"], 0)), list(torch.split(lens, pb["traj_step_lens"], 0)),
+                                     pb["traj_vpids"], pb["traj_cand_vpids"], pb["gmap_vpids"])
+    assert got.shape == ref.shape and got[:, 0].abs().max() == 0
+    assert (got - ref).abs().max().item() < 1e-6
+
+
+def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
+    """Host logic without a GPU: every `ops.*` kernel wrapper is replaced by a recorder, the model lives on the CPU, and the
+    Python glue of forward('navigation'), its intermediates path and forward_pretrain (both tasks) must run to the end with
+    consistent shapes.  Pins the launch budget of the navigation step: 58 kernel launches at one launch per wrapper call."""
+    import types
+    from gridmm_b200 import ops
+    from gridmm_b200.model import GlocalTextPathNavCMT
+    calls = []
+    for name in dir(ops):
+        fn = getattr(ops, name)
+        if isinstance(fn, types.FunctionType) and not name.startswith("_") and name != "pool_text_ws":
+            monkeypatch.setattr(ops, name, (lambda n: (lambda *a, **k: calls.append(n)))(name))
+    monkeypatch.setattr(ops, "pool_text_ws", lambda dev, B, D: torch.zeros(B * 128 * D, dtype=torch.float16))
+    ep_kw, nav_kw, model_kw = H.NAV_CASES["r2r_small"]
+    model = GlocalTextPathNavCMT(H.make_config(**model_kw)).eval()
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    cells, fts, _, pos = H.oracle_grid(ep)
+    nav = H.nav_batch(ep_kw, nav_kw, cells, fts, pos)
+    out = model("navigation", nav)
+    B, G, V = ep_kw["batch"], nav_kw["gmap_len"], 1 + nav_kw["n_views"]
+    assert out["fused_logits"].shape == (B, G) and out["local_logits"].shape == (B, V) and out["obj_logits"] is None
+    assert out["gmap_embeds"].shape == (B, G, 768) and out["vp_embeds"].shape == (B, V, 768)
+    # cell_sort (list path only) + the 57 launches after the grid build = the 58-launch step of bench.py, where grid_update replaces cell_sort
+    assert calls.count("cell_sort") == 1 and len(calls) == 58, (len(calls), calls)
+    assert calls.count("linear_ln") == 17 and calls.count("pool") == 1 and calls.count("cls_heads") == 1
+    calls.clear()
+    inter = model("navigation", nav, return_intermediates=True)
+    assert inter["map_embeds"].shape[0] == B and "pooled" in inter
+    # pretraining trunk, both exits
+    case = H.PRETRAIN_MODEL_CASE
+    pm = GlocalTextPathNavCMT(H.make_config(pretrain_trunk=True, use_lang2visn_attn=True, **case["model"])).eval()
+    batch = H.pretrain_batch(case)
+    calls.clear()
+    gmap_e, vp_e, grid_g = pm.forward_pretrain(batch, task="sap")
+    Gp = int(batch["gmap_lens"].max())
+    assert gmap_e.shape == (case["batch"], Gp, 768) and vp_e.shape == (case["batch"], 37, 768) and grid_g.shape == gmap_e.shape
+    assert "cls_heads" not in calls and "nav_logits2" not in calls          # the trunk stops before any action head
+    calls.clear()
+    txt = pm.forward_pretrain(batch, task="mlm")
+    assert txt.shape == (case["batch"], case["txt_len"], 768)
+    assert "linear_rows" not in calls                                       # the MLM exit leaves before the fusion encoder's K/V projection
+    with pytest.raises(NotImplementedError):
+        pm.forward_pretrain(dict(batch, traj_obj_img_fts=torch.zeros(1)), task="sap")
