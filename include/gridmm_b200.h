@@ -176,7 +176,8 @@ int gridmm_attention_f16(const void* q, int ldq, int q_rows, const void* k, int 
                          void* o, int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk,
                          float scale, cudaStream_t stream);
 
-/* LayerNorm over 768 (BertLayerNorm eps 1e-12 / nn.LayerNorm eps 1e-5); fp32 and/or fp16 output. */
+/* LayerNorm over 768 (BertLayerNorm = torch.nn.LayerNorm, eps 1e-12: map_nav_src/models/vilmodel.py:40-44, 163-169;
+ * nn.LayerNorm eps 1e-5 inside the pre-norm layers: models/transformer.py:144-145, 170-180); fp32 and/or fp16 output. */
 int gridmm_layernorm(const float* x, int ldx, const float* gamma, const float* beta, float eps, float* out_f32, int ld_f32,
                      void* out_f16, int ld_f16, int rows, int hidden, cudaStream_t stream);
 
