@@ -239,6 +239,26 @@ def make_pretrain_batch(batch, seed=0, txt_len=40, max_steps=4, n_views=36, n_ca
     }
 
 
+def make_pretrain_labels(pb, seed=0, n_masked=2):
+    """Task inputs that go with make_pretrain_batch: SAP (pretrain_src/data/tasks.py sap collate: gmap_visited_masks,
+    global / local action labels, here the first unvisited node and the first candidate view) and MLM (txt_labels: the original
+    id at n_masked masked positions per instruction, -1 elsewhere)."""
+    rng = np.random.default_rng(seed + 32452843)
+    B, G = pb["gmap_step_ids"].shape
+    visited = np.zeros((B, G), dtype=bool)
+    glob = np.zeros(B, dtype=np.int64)
+    for b in range(B):
+        T = pb["traj_step_lens"][b]
+        visited[b, 1:1 + T] = True
+        glob[b] = 1 + T
+    txt_labels = np.full(pb["txt_ids"].shape, -1, dtype=np.int64)
+    for b in range(B):
+        pos = rng.choice(int(pb["txt_lens"][b]), size=n_masked, replace=False)
+        txt_labels[b, pos] = pb["txt_ids"][b, pos]
+    return {"gmap_visited_masks": visited, "global_act_labels": glob, "local_act_labels": np.ones(B, dtype=np.int64),
+            "txt_labels": txt_labels}
+
+
 def to_torch(nav, device="cpu"):
     """numpy nav-input dict -> torch tensors with the reference's dtypes."""
     import torch

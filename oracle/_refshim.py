@@ -281,6 +281,23 @@ def load_reference_pretrain_model(**cfg):
     return model
 
 
+def load_reference_pretrain_wrapper(tasks=("mlm", "sap"), **cfg):
+    """`GlocalTextPathCMTPreTraining` (pretrain_src/model/pretrain_cmt.py:37-66): the trunk as `.bert` plus the task heads.
+    `init_weights` / `tie_weights` are no-ops under transformers 5.x (shim 2); the caller ties the MLM decoder to the word
+    embeddings by value, which is all `tie_weights` (:68-71) achieves for a forward pass."""
+    import importlib
+    load_reference_pretrain_model(num_l_layers=1, num_pano_layers=1, num_x_layers=1)      # installs the alias package
+    pc = importlib.import_module("pretrain_model.pretrain_cmt")
+    cls = pc.GlocalTextPathCMTPreTraining
+    cls.init_weights = lambda self: None
+    cls.tie_weights = lambda self, *a, **k: None
+    config = make_pretrain_config(**cfg)
+    config.pretrain_tasks = list(tasks)
+    model = cls(config)
+    model.eval()
+    return model
+
+
 # ----------------------------------------------------------------------------------------------- continuous-env variant
 CE_ROOT = os.path.join(REF_ROOT, "VLN_CE", "vlnce_baselines", "models")
 

@@ -132,6 +132,51 @@ def make_pretrain_model():
     print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()})
 
 
+def make_pretrain_heads():
+    """pretrain_heads_small.npz: `GlocalTextPathCMTPreTraining.forward_sap` (logits and per-sample losses) and `.forward_mlm`
+    (vocabulary scores at the masked positions) on the batch of pretrain_small.npz (pretrain_src/model/pretrain_cmt.py:128-292);
+    pretrain_heads_small_spec.json: the wrapper's parameter names and shapes."""
+    import json
+    case = PRETRAIN_MODEL_CASE
+    B, seed = case["batch"], case["seed"]
+    model = _refshim.load_reference_pretrain_wrapper(**case["model"])
+    shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
+    w = synth.make_weights(shapes, seed=seed)
+    w["mlm_head.predictions.decoder.weight"] = w["bert.embeddings.word_embeddings.weight"]       # tie_weights, pretrain_cmt.py:68-71
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    pb = synth.make_pretrain_batch(B, seed=seed, txt_len=case["txt_len"], max_steps=case["max_steps"])
+    lab = synth.make_pretrain_labels(pb, seed=seed)
+    ep = synth.make_episodes(B, case["max_steps"], seed=seed, dim=768)
+    heads = synth.pretrain_headings(ep)
+    ds = _refshim.load_reference_pretrain_data()
+    gfts, gmap, gpos = [], [], []
+    for b in range(B):
+        T = pb["traj_step_lens"][b]
+        cells, pos_fts, _, fts = _refshim.ref_pretrain_traj(
+            ds, "scan%d" % b, [float(x) for x in heads[b, :T]], [synth.expand_depth(ep["depth_sub"][b, t]) for t in range(T)],
+            [ep["clip"][b, t].astype(np.float32) for t in range(T)], ep["pos"][b, :T])
+        gfts.append(torch.from_numpy(fts).to(torch.float16))
+        gmap.append(torch.from_numpy(cells[-1]).to(torch.int64))
+        gpos.append(pos_fts[-1])
+    t = lambda k: torch.from_numpy(pb[k])
+    common = (t("txt_ids"), t("txt_lens"), t("traj_view_img_fts"), None, t("traj_loc_fts"), t("traj_nav_types"), pb["traj_step_lens"],
+              t("traj_vp_view_lens"), None, pb["traj_vpids"], pb["traj_cand_vpids"], t("gmap_lens"), t("gmap_step_ids"),
+              t("gmap_pos_fts"), t("gmap_pair_dists"), pb["gmap_vpids"], t("vp_pos_fts"))
+    gp = torch.from_numpy(np.stack(gpos).astype(np.float32))
+    lt = {k: torch.from_numpy(v) for k, v in lab.items()}
+    with torch.no_grad():
+        sap_args = common + (lt["gmap_visited_masks"], lt["global_act_labels"], lt["local_act_labels"], gfts, gmap, None, gp)
+        gl, ll, fused, _, _ = model.forward_sap(*sap_args, False)
+        losses = model.forward_sap(*sap_args, True)
+        scores = model.forward_mlm(*common, lt["txt_labels"], gfts, gmap, None, gp, False)
+    save = {"global_logits": gl.numpy(), "local_logits": ll.numpy(), "fused_logits": fused.numpy(), "sap_losses": losses.numpy(),
+            "mlm_scores": scores.numpy().astype(np.float32)}
+    path = os.path.join(GOLD, "pretrain_heads_small.npz")
+    np.savez_compressed(path, **save)
+    json.dump(shapes, open(os.path.join(GOLD, "pretrain_heads_small_spec.json"), "w"), indent=0)
+    print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()}, losses.tolist())
+
+
 def reference_nav(ep_kw, nav_kw, model_kw):
     from gridmm_b200.model import NavConfig, param_spec
     ep = synth.make_episodes(dim=768, **ep_kw)
@@ -255,7 +300,7 @@ if __name__ == "__main__":
         raise SystemExit("reference not available at %s" % _refshim.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain", "pretrain_model"]
+    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain", "pretrain_model", "pretrain_heads"]
     if "grid" in which:
         make_grid()
     if "nav" in which:
@@ -268,3 +313,5 @@ if __name__ == "__main__":
         make_pretrain_grid()
     if "pretrain_model" in which:
         make_pretrain_model()
+    if "pretrain_heads" in which:
+        make_pretrain_heads()

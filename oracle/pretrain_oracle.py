@@ -14,6 +14,9 @@ What differs from the navigation forward (oracle/model_oracle.py):
   * relevance, grid_proj, the per-cell softmax and the weighted sum run in fp16 (:685-699; grid_proj is an fp16 Linear, :664);
   * `forward_mlm` swaps the roles in the fusion encoder: text tokens are the queries, [gmap'; vp] the context, through the
     lang_* halves of GraphLXRTXLayer (forward_lang2visn, :404-415).
+The task heads on top of the trunk (`GlocalTextPathCMTPreTraining.forward_sap` / `.forward_mlm`,
+pretrain_src/model/pretrain_cmt.py:128-153, 214-292) are restated by `sap` and `mlm_scores`; they take the wrapper's state_dict
+(trunk under `bert.`) and are pinned by tests/golden/pretrain_heads_small.npz.
 Functional over a plain state_dict with the reference's key names.
 """
 import torch
@@ -93,3 +96,47 @@ def forward_mlm(sd, batch, n_l_layers=9, n_pano_layers=2, n_x_layers=4):
         txt = mo.bert_self_block(sd, p + ".lang_self_att", txt, txt_add)
         txt = mo.bert_ffn(sd, p + ".lang_inter", p + ".lang_output", txt)
     return txt
+
+
+def _trunk_sd(sd):
+    return {k[5:]: v for k, v in sd.items() if k.startswith("bert.")}
+
+
+def sap(sd, batch, labels, n_l_layers=9, n_pano_layers=2, n_x_layers=4):
+    """forward_sap (pretrain_cmt.py:214-292) -> (global_logits, local_logits, fused_logits, per-sample loss).
+    The heads, masks and the logit fusion are the navigation forward's (model_oracle.navigation); what differs is where the masks
+    come from: navigable = nav type 1 of the LAST panorama (:244-250), candidates = traj_cand_vpids[i][-1] (:259)."""
+    import torch.nn.functional as F
+    gmap_e, vp_e, gmap2 = forward(_trunk_sd(sd), batch, n_l_layers, n_pano_layers, n_x_layers)
+    ninf = float("-inf")
+    fw = torch.sigmoid(mo.cls_head(sd, "sap_fuse_linear", torch.cat([gmap_e[:, 0], vp_e[:, 0]], 1))) \
+        if "sap_fuse_linear.net.0.weight" in sd else 0.5
+    gmap_masks = torch.arange(gmap_e.shape[1])[None, :] < batch["gmap_lens"][:, None]
+    visited = labels["gmap_visited_masks"]
+    gl = (mo.cls_head(sd, "global_sap_head", gmap_e).squeeze(2) * fw).masked_fill(visited, ninf).masked_fill(~gmap_masks, ninf)
+    gr = mo.cls_head(sd, "grid_sap_head", gmap2).squeeze(2).masked_fill(visited, ninf).masked_fill(~gmap_masks, ninf)
+    ll = mo.cls_head(sd, "local_sap_head", vp_e).squeeze(2) * (1 - fw)
+    last_types = [t[-1] for t in torch.split(batch["traj_nav_types"], list(batch["traj_step_lens"]), 0)]
+    not_nav = torch.stack(last_types, 0)[:, :ll.shape[1] - 1] != 1
+    ll = ll.masked_fill(torch.cat([torch.zeros(len(last_types), 1, dtype=torch.bool), not_nav], 1), ninf)
+    cands = [[None] + list(c[-1]) for c in batch["traj_cand_vpids"]]
+    fused = mo.fuse_logits(gl, ll, batch["gmap_vpids"], visited, cands)
+    ga, la = labels["global_act_labels"], labels["local_act_labels"]
+    losses = [F.cross_entropy(x, y, reduction="none") for x, y in ((gl, ga), (ll, la), (fused, ga), (gr, ga))]
+    n_go = int((ga != 0).sum())
+    stop_rate = (int((ga == 0).sum()) / n_go) if n_go else 1.0                         # :279-287
+    for x, y in zip(losses, (ga, la, ga, ga)):
+        x[y == 0] = x[y == 0] / stop_rate if (y == 0).any() else x[y == 0]
+    return gl, ll, fused, sum(losses)
+
+
+def mlm_scores(sd, batch, txt_labels, n_l_layers=9, n_pano_layers=2, n_x_layers=4):
+    """forward_mlm of the wrapper (pretrain_cmt.py:128-153): vocabulary scores at the masked positions only
+    (BertOnlyMLMHead, pretrain_src/model/vilmodel.py:262-303; decoder weight tied to the word embeddings)."""
+    txt = forward_mlm(_trunk_sd(sd), batch, n_l_layers, n_pano_layers, n_x_layers)
+    h = txt[txt_labels != -1]
+    p = "mlm_head.predictions"
+    h = mo._lin(sd, p + ".transform.dense", h)
+    h = h * 0.5 * (1.0 + torch.erf(h / 2.0 ** 0.5))
+    h = mo._ln(sd, p + ".transform.LayerNorm", h, 1e-12)
+    return torch.nn.functional.linear(h, sd[p + ".decoder.weight"]) + sd[p + ".bias"]

@@ -89,6 +89,35 @@ def test_pretrain_oracle_matches_reference_trunk():
         assert err <= 5e-5, "%s: max abs error %.3e" % (key, err)
 
 
+def test_pretrain_oracle_matches_reference_task_heads():
+    """oracle/pretrain_oracle.py `sap` / `mlm_scores` against the reference's own GlocalTextPathCMTPreTraining.forward_sap
+    (logits + per-sample losses, which also cover the grid head) and .forward_mlm (scores at the masked positions) --
+    tests/golden/pretrain_heads_small.npz (pretrain_src/model/pretrain_cmt.py:128-153, 214-292)."""
+    import json
+    from oracle import pretrain_oracle as po
+    case = H.PRETRAIN_MODEL_CASE
+    gold = np.load(os.path.join(H.GOLD, "pretrain_heads_small.npz"))
+    shapes = json.load(open(os.path.join(H.GOLD, "pretrain_heads_small_spec.json")))
+    w = synth.make_weights(shapes, seed=case["seed"])
+    w["mlm_head.predictions.decoder.weight"] = w["bert.embeddings.word_embeddings.weight"]
+    sd = {k: torch.from_numpy(v) for k, v in w.items()}
+    batch = H.pretrain_batch(case)
+    pb = synth.make_pretrain_batch(case["batch"], seed=case["seed"], txt_len=case["txt_len"], max_steps=case["max_steps"])
+    labels = {k: torch.from_numpy(v) for k, v in synth.make_pretrain_labels(pb, seed=case["seed"]).items()}
+    torch.set_num_threads(os.cpu_count() or 1)
+    kw = dict(n_l_layers=case["model"]["num_l_layers"], n_pano_layers=case["model"]["num_pano_layers"],
+              n_x_layers=case["model"]["num_x_layers"])
+    with torch.no_grad():
+        gl, ll, fused, losses = po.sap(sd, batch, labels, **kw)
+        scores = po.mlm_scores(sd, batch, labels["txt_labels"], **kw)
+    H.finite_close(gl, gold["global_logits"], atol=5e-5)
+    H.finite_close(ll, gold["local_logits"], atol=5e-5)
+    H.finite_close(fused, gold["fused_logits"], atol=5e-5)
+    assert (losses - torch.from_numpy(gold["sap_losses"])).abs().max().item() < 2e-4
+    assert scores.shape == gold["mlm_scores"].shape
+    assert (scores - torch.from_numpy(gold["mlm_scores"])).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("name", sorted(H.NAV_CASES))
 def test_nav_oracle_matches_reference_forward(name):
     from oracle import model_oracle as mo
