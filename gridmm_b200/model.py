@@ -162,7 +162,7 @@ def param_spec(cfg):
         _prenorm(p + ".pano_encoder", cfg.num_pano_layers, inter, s)
     _lin_ln("local_encoder.vp_pos_embeddings", cfg.angle_feat_size * 2 + 6, s)
     trunk = getattr(cfg, "pretrain_trunk", False)
-    lang = trunk and getattr(cfg, "use_lang2visn_attn", False)
+    lang = getattr(cfg, "use_lang2visn_attn", False)
     for i in range(cfg.num_x_layers):
         _lxrt("local_encoder.encoder.x_layers.%d" % i, inter, s, lang)
     _lin_ln("global_encoder.gmap_pos_embeddings", cfg.angle_feat_size + 3, s)
@@ -842,12 +842,16 @@ class GlocalTextPathNavCMT(nn.Module):
         return out
 
     @torch.no_grad()
-    def forward_pretrain(self, batch, task="sap"):
+    def forward_pretrain(self, batch, task="sap", heads=False):
         """The pretraining trunk on one collated batch (pretrain_src/model/vilmodel.py:668-764 `forward`, :767-855 `forward_mlm`):
         text encoder, every panorama of every path through the image embeddings + pano encoder, gmap aggregation, then the same
         grid pooling / grid encoders / fusion encoder kernels as the navigation step.
           task "sap" (also mrc / og) -> (gmap_embeds, vp_embeds, grid-encoded gmap rows)
           task "mlm"                 -> text states after the text-queries-[gmap'; vp] layers (forward_lang2visn, :404-415)
+          task "sap", heads=True     -> the action logits of `forward_sap` (pretrain_src/model/pretrain_cmt.py:214-270) as the
+                                        navigation dict: needs a model WITH the action heads (NavConfig(use_lang2visn_attn=True,
+                                        graph_sprels=False), weights = remap_pretrained_keys(wrapper state_dict)) and
+                                        batch["gmap_visited_masks"]
         The reference pools in fp16 here (:685-699); this path keeps fp16 operands with fp32 accumulation, which is at least as
         accurate.  `batch["grid"]` may hold a GridBatch (GridMapBuilder.run_trajectory) instead of the grid_fts / grid_map lists."""
         cfg = self.config
@@ -874,6 +878,19 @@ class GlocalTextPathNavCMT(nn.Module):
         vp_img = torch.cat([torch.zeros(B, 1, HID, device=dev), pano[last]], 1)[:, :V].contiguous()
         vp_masks = torch.arange(V, device=dev)[None, :] < vp_lens[:, None]
         mode = "mlm" if task.startswith("mlm") else "trunk"
+        if heads:
+            if mode == "mlm" or "global_sap_head.net.0.weight" not in self._spec:
+                raise ValueError("heads=True is the SAP task on a model built with the action heads (pretrain_trunk=False)")
+            # forward_sap's masks (pretrain_cmt.py:244-259): navigable = [stop] + views of the LAST panorama with nav type 1,
+            # candidates of the logit fusion = that panorama's candidate viewpoints
+            types_last = torch.as_tensor(batch["traj_nav_types"]).to(dev)[last][:, :V - 1]
+            vp_nav = torch.cat([torch.ones(B, 1, dtype=torch.bool, device=dev), types_last == 1], 1)
+            cands = [[None] + list(c[-1]) for c in batch["traj_cand_vpids"]]
+            return self.forward_navigation_per_step(
+                txt, txt_masks, gmap_img, batch["gmap_step_ids"], batch["gmap_pos_fts"], gmap_masks, None,
+                torch.as_tensor(batch["gmap_visited_masks"]), batch["gmap_vpids"], vp_img, torch.as_tensor(batch["vp_pos_fts"])[:, :V],
+                vp_masks, vp_nav, None, cands, batch.get("grid_fts"), batch.get("grid_map"), batch.get("gridmap_pos_fts"),
+                grid=batch.get("grid"))
         out = self.forward_navigation_per_step(
             txt, txt_masks, gmap_img, batch["gmap_step_ids"], batch["gmap_pos_fts"], gmap_masks, None, None, None, vp_img,
             torch.as_tensor(batch["vp_pos_fts"])[:, :V], vp_masks, None, None, None, batch.get("grid_fts"), batch.get("grid_map"),

@@ -187,19 +187,61 @@ def test_gmap_aggregation_glue_equals_oracle():
     assert (got - ref).abs().max().item() < 1e-6
 
 
-def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
-    """Host logic without a GPU: every `ops.*` kernel wrapper is replaced by a recorder, the model lives on the CPU, and the
-    Python glue of forward('navigation'), its intermediates path and forward_pretrain (both tasks) must run to the end with
-    consistent shapes.  Pins the launch budget of the navigation step: 58 kernel launches at one launch per wrapper call."""
+def _stub_ops(monkeypatch):
+    """Replace every kernel wrapper of gridmm_b200.ops by a recorder (host-logic tests; nothing is computed)."""
     import types
     from gridmm_b200 import ops
-    from gridmm_b200.model import GlocalTextPathNavCMT
     calls = []
     for name in dir(ops):
         fn = getattr(ops, name)
         if isinstance(fn, types.FunctionType) and not name.startswith("_") and name != "pool_text_ws":
             monkeypatch.setattr(ops, name, (lambda n: (lambda *a, **k: calls.append(n)))(name))
     monkeypatch.setattr(ops, "pool_text_ws", lambda dev, B, D: torch.zeros(B * 128 * D, dtype=torch.float16))
+    return calls
+
+
+def test_pretrain_sap_heads_glue_masks_and_candidates(monkeypatch):
+    """forward_pretrain(task="sap", heads=True): the host side of forward_sap (pretrain_src/model/pretrain_cmt.py:244-269) --
+    navigable mask from the last panorama's nav types, candidates of the logit fusion from traj_cand_vpids[i][-1] -- must hand
+    the navigation kernels the same masks / index arrays as the oracle's restatement uses; and the wrapper's state_dict loads
+    after the reference's own key remap (vlnbert_init.py:19-27) with only the MLM head left over."""
+    import json
+    from gridmm_b200.model import GlocalTextPathNavCMT, build_fuse_index, remap_pretrained_keys
+    calls = _stub_ops(monkeypatch)
+    case = H.PRETRAIN_MODEL_CASE
+    cfg = H.make_config(use_lang2visn_attn=True, graph_sprels=False, **case["model"])
+    model = GlocalTextPathNavCMT(cfg).eval()
+    shapes = json.load(open(os.path.join(H.GOLD, "pretrain_heads_small_spec.json")))
+    sd = remap_pretrained_keys({k: torch.zeros(v) for k, v in shapes.items()})
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.missing_keys and all(k.startswith("mlm_head.") for k in res.unexpected_keys) and len(res.unexpected_keys) == 6
+    batch = H.pretrain_batch(case)
+    pb = synth.make_pretrain_batch(case["batch"], seed=case["seed"], txt_len=case["txt_len"], max_steps=case["max_steps"])
+    lab = synth.make_pretrain_labels(pb, seed=case["seed"])
+    batch["gmap_visited_masks"] = torch.from_numpy(lab["gmap_visited_masks"])
+    out = model.forward_pretrain(batch, task="sap", heads=True)
+    B, G, V = case["batch"], int(batch["gmap_lens"].max()), 37
+    assert out["fused_logits"].shape == (B, G) and out["local_logits"].shape == (B, V) and out["grid_logits"].shape == (B, G)
+    assert calls.count("cls_heads") == 1 and calls.count("nav_logits2") == 1
+    staged = {k[0]: v for k, v in model._ws.items() if k[0].startswith("in_")}
+    nav_types_last = torch.stack([t[-1] for t in torch.split(batch["traj_nav_types"], batch["traj_step_lens"], 0)], 0)
+    want_nav = torch.cat([torch.ones(B, 1, dtype=torch.bool), nav_types_last[:, :V - 1] == 1], 1)
+    assert torch.equal(staged["in_vp_nav"].bool(), want_nav)
+    assert torch.equal(staged["in_gmap_visited"].bool(), batch["gmap_visited_masks"])
+    cands = [[None] + list(c[-1]) for c in batch["traj_cand_vpids"]]
+    src, bw = build_fuse_index(batch["gmap_vpids"], batch["gmap_visited_masks"], cands, G, V)
+    assert np.array_equal(staged["in_fuse_src"].numpy(), src) and np.array_equal(staged["in_bw_mask"].numpy(), bw)
+    with pytest.raises(ValueError):
+        GlocalTextPathNavCMT(H.make_config(pretrain_trunk=True, use_lang2visn_attn=True, **case["model"])).forward_pretrain(
+            batch, task="sap", heads=True)
+
+
+def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
+    """Host logic without a GPU: every `ops.*` kernel wrapper is replaced by a recorder, the model lives on the CPU, and the
+    Python glue of forward('navigation'), its intermediates path and forward_pretrain (both tasks) must run to the end with
+    consistent shapes.  Pins the launch budget of the navigation step: 58 kernel launches at one launch per wrapper call."""
+    from gridmm_b200.model import GlocalTextPathNavCMT
+    calls = _stub_ops(monkeypatch)
     ep_kw, nav_kw, model_kw = H.NAV_CASES["r2r_small"]
     model = GlocalTextPathNavCMT(H.make_config(**model_kw)).eval()
     ep = synth.make_episodes(dim=768, **ep_kw)
