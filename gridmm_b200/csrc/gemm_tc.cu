@@ -5,11 +5,13 @@
 // nn.MultiheadAttention in/out projections + linear1/linear2 (map_nav_src/models/transformer.py:133-182),
 // ClsPrediction first layer (vilmodel.py:663-674), text_proj/grid_proj (:702-703).
 //
-// Structure: persistent CTAs (one per SM), 128 x BN output tiles (BN = 128 or 256) handed out round-robin, 6 warps:
-//   warp 0      TMA producer: 128x64 A tile + BNx64 W tile per stage, SWIZZLE_128B, mbarrier complete_tx; the stage ring
-//               runs straight across tile boundaries
-//   warp 1      allocates TMEM (2 accumulators of BN columns), issues tcgen05.mma (one thread), commits smem stages back
-//               to the producer and finished accumulators to the epilogue
+// Structure: persistent CTAs (one per SM), 128 x BN output tiles (BN = 128 or 256) handed out round-robin -- or, for large
+// problems, CTA pairs (tcgen05 cta_group::2) on 256 x 256 tiles, each CTA loading half of the W tile -- 10 warps:
+//   warp 0      TMA producer: 128 x BK A tile + (BN / CG) x BK W tile per stage (BK = 64 or 128), SWIZZLE_128B, mbarrier
+//               complete_tx; the stage ring runs straight across tile boundaries.  The loop runs warp-converged and issues under
+//               elect.sync (common.cuh: a divergent single-thread loop costs ~100 cycles per TMA / MMA instruction)
+//   warp 1      allocates TMEM (2 accumulators of BN columns), issues tcgen05.mma (one elected lane), commits smem stages
+//               back to the producer and finished accumulators to the epilogue
 //   warps 2..9  epilogue (two warps per TMEM lane quadrant, half of the columns each): the tile's bias slice is staged in
 //               shared memory and the first residual chunks are already in flight BEFORE the accumulator is ready;
 //               tcgen05.ld 32 lanes x 16 columns, bias / GELU / ReLU / residual (register-pipelined 4 chunks deep),
@@ -41,7 +43,7 @@ struct GemmEpilogue {
     float* cls_part;         // [rows][N / 64][3]: sum r, sum r^2, sum r * gw2 with r = act(acc + bias), or null
     float* cls_raw;          // [rows][N] plain products of the mode-1 tiles (K-split halves of sap_fuse_linear), or null
     const int* m_dev;        // optional device-side row count (<= M): packed / ragged operands whose size only the GPU knows
-    long long* dbg;          // optional [grid][8] cycle counters (tools/microbench.py), null in production
+    long long* dbg;          // optional [grid][8] cycle counters (tools/microbench2.py), null in production
 };
 
 template <int BN, int STAGES, int BK, int CG = 1>

@@ -1,8 +1,10 @@
 // Row-wise kernels around the GEMMs of the navigation step (all hidden size 768, one warp per row):
 //   layer norm (BertLayerNorm eps 1e-12 / nn.LayerNorm eps 1e-5), the small position-feature embeddings
 //   (Linear(5|7|14 -> 768) + LayerNorm, map_nav_src/models/vilmodel.py:697-700, 563-566, 534-537),
-//   grid-cell assembly incl. the reference's mask-compaction quirk (vilmodel.py:813-823),
-//   ClsPrediction tails and the action-logit fusion (vilmodel.py:859-907).
+//   grid-cell assembly incl. the reference's mask-compaction quirk (vilmodel.py:813-823) together with the gmap tokens and
+//   grid_encoder's first pre-norm LayerNorm (gridmm_map_inputs, vilmodel.py:828-838), the packed fusion context
+//   (gridmm_kv_index + gridmm_fusion_inputs: [map; txt] without its masked rows, queries [gmap'; vp], vilmodel.py:843-850),
+//   text / panorama input embeddings, ClsPrediction tails and the action-logit fusion (vilmodel.py:859-907).
 #include "common.cuh"
 #include "host_util.h"
 
