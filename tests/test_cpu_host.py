@@ -272,3 +272,37 @@ def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
     assert "linear_rows" not in calls                                       # the MLM exit leaves before the fusion encoder's K/V projection
     with pytest.raises(NotImplementedError):
         pm.forward_pretrain(dict(batch, traj_obj_img_fts=torch.zeros(1)), task="sap")
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): one JSON line with the contract's keys,
+    measured on the oracle port of the reference algorithm; and the CUDA arm refuses to run without a GPU instead of falling
+    back to anything."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "nav-steps/s" and line["higher_is_better"] is True
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["config"]["workload"].startswith("configs[1]")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert abs(line["cpu_baseline"]["value"] - line["value"]) < 1e-9
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode != 0 and "no CPU path" in (r.stdout + r.stderr)
+
+
+def test_bench_flop_model_matches_the_survey():
+    """bench.py's roofline numerator: 2mnk over the GEMM launches of one B=32 step.  SURVEY 8(d) puts the whole step at
+    ~14.4 GFLOP per episode-step including the attention cores (4 S^2 D etc., ~0.6 G) -- the GEMM share must sit just below."""
+    import bench
+    per_sample = bench.gemm_flops_per_step() / bench.B
+    assert 13.0e9 < per_sample < 14.4e9
+    packed = bench.gemm_flops_per_step(kv_rows=bench.B * 217)        # ~217 valid context rows per episode instead of 296
+    assert packed < bench.gemm_flops_per_step() and packed > 0.9 * bench.gemm_flops_per_step()
