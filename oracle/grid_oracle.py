@@ -95,8 +95,13 @@ class GridState:
         self.max_y, self.min_y = f32(-10000), f32(10000)
 
 
-def grid_step(state, depth_sub, clip, pos_xy, heading, grid_w=14, geom=R2RGeometry):
+def grid_step(state, depth_sub, clip, pos_xy, heading, grid_w=14, geom=R2RGeometry, legacy_half=False):
     """One getGlobalMap call (env.py:267-374).
+
+    legacy_half: evaluate the window half-length as the reference's PINNED numpy (1.20.3, value-based casting) would:
+    `position - np.float32` is float64 there, so half_len is computed in double and only rounded to fp32 when it meets the
+    fp32 point arrays.  Not the oracle of record (that is the reference run under this container's numpy 2, all fp32); kept to
+    COUNT how many cell ids the two conventions can disagree on (hard parts).
 
     depth_sub: [12,49] uint16 (R2R) or f32 metres (CE); clip: f16[12,50,D] (CLS first) or None;
     pos_xy: python floats; heading: python float.
@@ -127,6 +132,13 @@ def grid_step(state, depth_sub, clip, pos_xy, heading, grid_w=14, geom=R2RGeomet
     y_half = a if a > b else b
     half = x_half if x_half > y_half else y_half
     half = f32(f32(half * f32(2)) / f32(3))                         # half_len * 2/3
+    if legacy_half:
+        pxd, pyd = float(pos_xy[0]), float(pos_xy[1])
+        a, b = pxd - float(state.min_x), float(state.max_x) - pxd
+        xh = a if a > b else b
+        a, b = pyd - float(state.min_y), float(state.max_y) - pyd
+        yh = a if a > b else b
+        half = f32((xh if xh > yh else yh) * 2 / 3)
     # index assignment for every accumulated point (env.py:337-369)
     ang = -heading + geom.angle_offset
     c, s = f32(math.cos(ang)), f32(math.sin(ang))

@@ -27,6 +27,31 @@ def test_grid_oracle_matches_reference_cells(case):
     np.testing.assert_allclose(np.stack(pos), gold["pos_fts_last"], atol=1e-6, rtol=0)
 
 
+def test_numpy_legacy_half_len_variant_flip_count():
+    """SURVEY 7 (hard parts): under the reference's pinned numpy 1.20 the window half-length is computed in float64 and meets the
+    fp32 points only afterwards; under numpy 2 (the oracle of record, and what the goldens were produced with) it is fp32 all
+    the way.  The two half-lengths differ by at most 1 ulp, and over this sample no cell id changes (flips are possible in
+    principle -- a point within ~1e-7 of a cell boundary -- so the bound is loose)."""
+    from oracle import grid_oracle as go
+    total = flips = half_diff = 0
+    for seed in (12, 101):
+        B, T = 6, 15
+        ep = synth.make_episodes(B, T, seed=seed, dim=8)
+        for b in range(B):
+            s1, s2 = go.GridState(), go.GridState()
+            for t in range(T):
+                args = (ep["depth_sub"][b, t], None, ep["pos"][b, t], float(ep["heading"][b, t]))
+                _, c1, h1 = go.grid_step(s1, *args)
+                _, c2, h2 = go.grid_step(s2, *args, legacy_half=True)
+                assert abs(float(h1) - float(h2)) <= float(np.spacing(np.float32(h1)))
+                total += c1.size
+                flips += int((c1 != c2).sum())
+                half_diff += int(h1 != h2)
+    assert total == 2 * 6 * 588 * 15 * 16 // 2
+    assert half_diff > 0                       # the conventions really differ ...
+    assert flips <= 5, flips                   # ... but (almost) never move a point to another cell
+
+
 def test_grid_oracle_matches_pretraining_dataset():
     """SURVEY 8a row 19, grid half: the pretraining dataset's own getGlobalMap (pretrain_src/data/dataset.py:351-473) run over
     whole ground-truth paths gave tests/golden/grid_pretrain_s51.npz; the oracle's R2R arithmetic reproduces its cell ids bit
