@@ -210,6 +210,7 @@ class Step:
         self.saved_bounds = self.builder.bounds.clone()
         self.saved_npts = self.builder.n_pts.clone()
         self.saved_steps = self.builder.n_steps.copy()
+        self.saved_calls = self.builder.n_calls
         self.nav = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in synth.to_torch(self.nav_np).items()}
         # host (pinned) and device copies of the step's new observation
         self.h_depth = torch.from_numpy(ep["depth_sub"][:, T - 1].astype(np.int16)).pin_memory()
@@ -226,6 +227,7 @@ class Step:
         self.builder.bounds.copy_(self.saved_bounds)
         self.builder.n_pts.copy_(self.saved_npts)
         self.builder.n_steps = self.saved_steps.copy()
+        self.builder.n_calls = self.saved_calls
 
     def run_resident(self):
         """inputs already in HBM"""

@@ -27,7 +27,7 @@ _SIGS = {
                            c_void_p, c_void_p, c_void_p],
     "gridmm_cell_sort": [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_pool": [c_void_p, c_longlong, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
-                    c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
+                    c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_ln_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                              c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "gridmm_head_rows": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
@@ -52,7 +52,8 @@ _SIGS = {
     "gridmm_split_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "gridmm_pos_embed": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
-    "gridmm_text_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "gridmm_text_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                          c_void_p],
     "gridmm_grid_assemble": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_int, c_int, c_int, c_void_p],
     "gridmm_cls_tail": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
@@ -75,9 +76,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.lib_path()
-    if not os.path.exists(path):
-        path = _build.build()
+    # build() is a no-op when the source digest matches the stamp next to the library (a stale binary after an edit of
+    # csrc/*.cu would otherwise be loaded silently); concurrent ranks serialise on a file lock inside build()
+    path = _build.build()
     lib = ctypes.CDLL(path)
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
@@ -97,9 +98,10 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Raw cudaStream_t of torch's current stream on `device` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def call(name, *args):

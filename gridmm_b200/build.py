@@ -42,15 +42,34 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Build the library if the sources changed.  Returns the path of the .so."""
-    os.makedirs(LIBDIR, exist_ok=True)
+def _up_to_date(dig):
     stamp = os.path.join(LIBDIR, "build.sha256")
+    return os.path.exists(lib_path()) and os.path.exists(stamp) and open(stamp).read().strip() == dig
+
+
+def build(force=False, verbose=False):
+    """Build the library if the sources changed.  Returns the path of the .so.  Safe to call from several processes at once
+    (one rank per GPU): builders serialise on a file lock, compile into a per-process object directory and publish the library
+    with an atomic rename."""
+    import fcntl
+    os.makedirs(LIBDIR, exist_ok=True)
     dig = _digest()
-    if not force and os.path.exists(lib_path()) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+    if not force and _up_to_date(dig):
         return lib_path()
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(dig):      # another process built it while this one waited
+                return lib_path()
+            return _build_locked(dig, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(dig, verbose):
+    stamp = os.path.join(LIBDIR, "build.sha256")
     nvcc = _nvcc()
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj", "pid%d" % os.getpid())
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -67,7 +86,7 @@ def build(force=False, verbose=False):
         if verbose and out:
             sys.stderr.write(out)
         objs.append(obj)
-    tmp = lib_path() + ".tmp"
+    tmp = lib_path() + ".tmp%d" % os.getpid()
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
@@ -75,6 +94,7 @@ def build(force=False, verbose=False):
     os.replace(tmp, lib_path())
     with open(stamp, "w") as f:
         f.write(dig)
+    shutil.rmtree(objdir, ignore_errors=True)
     return lib_path()
 
 

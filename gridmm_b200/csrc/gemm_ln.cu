@@ -431,12 +431,8 @@ extern "C" int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int l
     if (N != LN_N || K % 64 != 0 || K <= 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
     if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
     if (!a || !w || !gamma || !beta || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        GMM_CUDA_CHECK(cudaGetDevice(&dev));
-        GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sms = gridmm_sm_count();
+    if (sms <= 0) return GRIDMM_ERR_DRIVER;
     LnEpilogue ep{bias, residual, gamma, beta, eps, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, f32_raw};
     // cluster size: waves x (per-CTA work ~ slice width + fixed epilogue/launch part)
     const int tiles_m = (M + LN_BM - 1) / LN_BM;

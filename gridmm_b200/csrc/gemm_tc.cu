@@ -34,7 +34,7 @@ struct GemmEpilogue {
     __half* out_f16;         // [M, ld_f16] or null
     int ld_res, ld_f32, ld_f16;
     int act;                 // 0 none, 1 GELU(erf), 2 ReLU
-    __half* out_lanes;       // optional lane-major fp16 output [M / lanes_rows, N / 8, 128] of 16-byte units (gridmm_pool's
+    __half* out_lanes;       // optional lane-major fp16 output [lanes_rows / 128 blocks][M / lanes_rows, N / 8, 128] of 16-byte units (gridmm_pool's
     int lanes_rows;          // text operand layout): row = b * lanes_rows + t  ->  unit u of it at ((b * N/8 + u) * 128 + t)
     // grouped ClsPrediction mode (gridmm_cls_heads_f16): per 128-row tile {first A row, first W / bias row, first output row};
     // the epilogue keeps only three sums per row and 64-column slice (see cls_part) instead of storing the activations
@@ -81,8 +81,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// fp16 outputs SATURATE at +-65504 instead of overflowing to inf: the reference computes these activations in fp32, where a
+// large QKV / FFN1 value is harmless; as an fp16 GEMM operand an inf would turn the next layer into NaN.  (With trained
+// BERT-size weights |QKV| and |GELU(FFN1)| stay below a few hundred; tests/test_gpu_nav.py::test_trained_scale_activations.)
+__device__ __forceinline__ float sat_f16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-    const __half2 h = __floats2half2_rn(a, b);
+    const __half2 h = __floats2half2_rn(sat_f16(a), sat_f16(b));
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
@@ -335,7 +339,9 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (rg < M) {
                         const int bb = rg / ep.lanes_rows, tt = rg - bb * ep.lanes_rows;
                         const int unit = (col0 + c * 16) >> 3;
-                        uint4* dst = reinterpret_cast<uint4*>(ep.out_lanes) + (static_cast<size_t>(bb) * (N >> 3) + unit) * 128 + tt;
+                        // positions >= 128 of a long text go to the second [batch][N/8][128] block
+                        const size_t blk = static_cast<size_t>(tt >> 7) * (M / ep.lanes_rows);
+                        uint4* dst = reinterpret_cast<uint4*>(ep.out_lanes) + ((blk + bb) * (N >> 3) + unit) * 128 + (tt & 127);
                         uint4 o0, o1;
                         o0.x = pack_half2(f[0], f[1]); o0.y = pack_half2(f[2], f[3]); o0.z = pack_half2(f[4], f[5]); o0.w = pack_half2(f[6], f[7]);
                         o1.x = pack_half2(f[8], f[9]); o1.y = pack_half2(f[10], f[11]); o1.z = pack_half2(f[12], f[13]); o1.w = pack_half2(f[14], f[15]);
@@ -363,10 +369,9 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (rg < M) {
                         if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + static_cast<size_t>(rg) * ep.ld_f32 + col) = x;
                         if (ep.out_f16) {
-                            const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
                             uint2 o;
-                            o.x = *reinterpret_cast<const uint32_t*>(&h01);
-                            o.y = *reinterpret_cast<const uint32_t*>(&h23);
+                            o.x = pack_half2(x.x, x.y);
+                            o.y = pack_half2(x.z, x.w);
                             *reinterpret_cast<uint2*>(ep.out_f16 + static_cast<size_t>(rg) * ep.ld_f16 + col) = o;
                         }
                     }
@@ -457,12 +462,8 @@ static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, 
     if (N % 128 != 0 || K % GEMM_KATOM != 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
     if ((out_f32 && (ld_f32 % 4)) || (out_f16 && (ld_f16 % 8)) || (residual && (ld_res % 4))) return GRIDMM_ERR_SHAPE;
     if (!a || !w || (!out_f32 && !out_f16 && !out_lanes && !cls_part)) return GRIDMM_ERR_ARG;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        GMM_CUDA_CHECK(cudaGetDevice(&dev));
-        GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sms = gridmm_sm_count();
+    if (sms <= 0) return GRIDMM_ERR_DRIVER;
     GemmEpilogue ep{bias, residual, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, act,
                     reinterpret_cast<__half*>(out_lanes), lanes_rows, grp, gw2, cls_part, cls_raw, m_dev, g_gemm_dbg};
     if (grp) {
@@ -511,7 +512,7 @@ extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw,
 // text_proj for gridmm_pool: out_lanes[b, N/8, 128] (16-byte units, lane-major) = a[M = batch*rows_per_b, K] . w[N, K]^T + bias
 extern "C" int gridmm_linear_f16_lanes(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                                        void* out_lanes, int rows_per_b, cudaStream_t stream) {
-    if (!out_lanes || rows_per_b < 1 || rows_per_b > 128 || (M % rows_per_b)) return GRIDMM_ERR_SHAPE;
+    if (!out_lanes || rows_per_b < 1 || rows_per_b > 256 || (M % rows_per_b)) return GRIDMM_ERR_SHAPE;
     return gemm_dispatch(a, lda, w, ldw, M, N, K, bias, nullptr, 0, nullptr, 0, nullptr, 0, 0, out_lanes, rows_per_b, stream);
 }
 

@@ -50,6 +50,20 @@ bool gridmm_use_pdl() {
     return v == 1;
 }
 
+int gridmm_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    if (dev < 64) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
+    return sms;
+}
+
 void gridmm_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" long long gridmm_launch_count() { return g_launches.load(std::memory_order_relaxed); }

@@ -13,6 +13,9 @@
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_pitch_bytes,
                      uint32_t box_inner, uint32_t box_outer);
 
+// SM count of the CURRENT device (cached per device ordinal); <= 0 on error
+int gridmm_sm_count();
+
 // counts kernel launches issued through the C ABI (bench.py reports it as gpu_launches)
 void gridmm_count_launch(int n);
 

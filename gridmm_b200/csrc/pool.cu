@@ -51,9 +51,11 @@ struct PoolParams {
     const int* cell_rank;    // [B, n_cells]
     const uint4* text_ws;    // [B, D/8, 128] lane-major copy of text_fts (16-byte units; positions < l_pad are read)
     __half* pooled;          // [B, n_cells, D]  compacted by cell rank
-    float* w_out;            // [B, cap] relevance weight per sorted position, or null (tests)
+    float* w_out;            // [B, cap] relevance weight per sorted position, or null (tests; the first pass of a long text)
+    const float* w_in;       // [B, cap] row maxima over the text positions an EARLIER launch covered (merged into w), or null
+    int max_only;            // 1: only w_out is produced (first pass over a text longer than 128 positions): no softmax, no sums
     int batch, t_cap, cap, n_cells;
-    int l_pad;               // text positions (<= 128)
+    int l_pad;               // text positions of THIS launch (<= 128: one per tensor-memory lane)
     int slot_rows, view_rows, tok_off;   // row = slot*slot_rows + view*view_rows + tok_off + patch
     long long* dbg;          // optional [grid][16] cycle counters (tools/microbench2.py), null in production
 };
@@ -171,10 +173,11 @@ struct PoolSmem {
 template <int D>
 __global__ void __launch_bounds__(128) text_to_lanes_kernel(const __half* text, uint4* ws, int l_pad) {
     pdl_wait();
-    const int b = blockIdx.y, c = blockIdx.x, t = threadIdx.x;
+    // positions 128 z .. 128 z + 127 go to the z-th [B, D/8, 128] block of the workspace (texts longer than 128 positions)
+    const int b = blockIdx.y, c = blockIdx.x, t = blockIdx.z * 128 + threadIdx.x;
     if (t >= l_pad) return;
     const uint4 v = *reinterpret_cast<const uint4*>(text + (static_cast<size_t>(b) * l_pad + t) * D + c * 8);
-    ws[(static_cast<size_t>(b) * (D / 8) + c) * 128 + t] = v;
+    ws[(static_cast<size_t>(blockIdx.z) * gridDim.y + b) * (D / 8) * 128 + static_cast<size_t>(c) * 128 + threadIdx.x] = v;
     pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
@@ -501,8 +504,17 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 // ---- softmax numerator of row e (one warp: 32 rows): exp(w - max over its cell), the cell max taken with
                 //      match.any + redux.max, merged with the carried max of a cell that an earlier tile opened (the pooling
                 //      warps rescale their accumulators by s_scal)
-                const float w = fmaxf(fmaxf(wmax, part[lane]), fmaxf(part[POOL_ROWS + lane], part[2 * POOL_ROWS + lane]));
+                float w = fmaxf(fmaxf(wmax, part[lane]), fmaxf(part[POOL_ROWS + lane], part[2 * POOL_ROWS + lane]));
                 const bool valid = lane < t.nrows;
+                // text longer than 128 positions: the maxima over the positions of the earlier launch are merged in here
+                if (valid && p.w_in) w = fmaxf(w, __ldg(p.w_in + static_cast<size_t>(t.b) * p.cap + t.pos + lane));
+                if (p.max_only) {
+                    if (valid) p.w_out[static_cast<size_t>(t.b) * p.cap + t.pos + lane] = w;
+                    mbar_arrive(&p_full[buf]);
+                    if (p.dbg) { w_a += c2 - c1; c_soft += clock64() - c2; }
+                    ++it;
+                    continue;
+                }
                 int cid = -1;
                 if (valid) {
                     const int P = t.pos + lane;
@@ -560,6 +572,12 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
             mbar_wait_guard(&p_full[buf], ph);
             mbar_wait_guard(&a_full[buf], ph);         // already complete; makes the TMA-written tile visible to this thread
             const long long c1 = p.dbg ? clock64() : 0;
+            if (p.max_only) {                          // first pass of a long text: only drain the ring
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_empty[buf]);
+                ++it;
+                continue;
+            }
             const uint32_t tile_s = smem_u32(sA) + buf * L::A_BYTES;
             const float* pp = s_p + buf * POOL_ROWS;
             const int* rk = s_cid + buf * POOL_ROWS;    // compact cell rank | (last row of its cell ? 0x10000 : 0); -1 = no row
@@ -689,17 +707,29 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
 
 template <int D>
 static int launch_pool(const void* fts, long long fts_rows, const void* text_fts, void* text_ws, int text_ws_ready, int grid,
-                       PoolParams& p, cudaStream_t stream) {
+                       PoolParams& p, float* w_scratch, cudaStream_t stream) {
     // gather4 tensor map: the slab as [fts_rows, D] fp16, box = 64 columns x 1 row (the instruction names 4 rows)
     CUtensorMap tm;
     const int rc = make_tmap_f16_2d(&tm, fts, static_cast<uint64_t>(D), static_cast<uint64_t>(fts_rows), static_cast<uint64_t>(D) * 2, 64, 1);
     if (rc) return rc;
     constexpr int smem = PoolSmem<D>::TOTAL;
     GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int l_total = p.l_pad;
     if (!text_ws_ready) {
-        GMM_CUDA_CHECK(launch_pdl(text_to_lanes_kernel<D>, dim3(D / 8, p.batch), dim3(128), 0, stream,
-                                  reinterpret_cast<const __half*>(text_fts), reinterpret_cast<uint4*>(text_ws), p.l_pad));
+        GMM_CUDA_CHECK(launch_pdl(text_to_lanes_kernel<D>, dim3(D / 8, p.batch, (l_total + 127) / 128), dim3(128), 0, stream,
+                                  reinterpret_cast<const __half*>(text_fts), reinterpret_cast<uint4*>(text_ws), l_total));
         gridmm_count_launch(1);
+    }
+    if (l_total > 128) {
+        // A text of 129..256 positions does not fit the 128 tensor-memory lanes: a first pass over positions 128.. (second block of
+        // the workspace) only produces the row maxima; the main pass over positions 0..127 merges them before the softmax
+        // (vilmodel.py:798 takes the max over ALL positions).  The features are streamed twice in this case.
+        PoolParams p1 = p;
+        p1.text_ws = p.text_ws + static_cast<size_t>(p.batch) * (D / 8) * 128;
+        p1.l_pad = l_total - 128; p1.max_only = 1; p1.w_out = w_scratch; p1.w_in = nullptr;
+        GMM_CUDA_CHECK(launch_pdl(pool_kernel<D>, dim3(grid), dim3(POOL_FIXED_THREADS + D / 4), smem, stream, tm, p1));
+        gridmm_count_launch(1);
+        p.l_pad = 128; p.w_in = w_scratch;
     }
     GMM_CUDA_CHECK(launch_pdl(pool_kernel<D>, dim3(grid), dim3(POOL_FIXED_THREADS + D / 4), smem, stream, tm, p));
     gridmm_count_launch(1);
@@ -715,24 +745,24 @@ extern "C" void gridmm_debug_set_pool_counters(long long* dbg) { g_pool_dbg = db
 extern "C" int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, const int* slots, int t_cap, int slot_rows,
                            int view_rows, int tok_off, const int* perm, int cap, const int* cell_start, const int* cell_rank,
                            int n_cells, const void* text_fts, int l_pad, int batch, void* text_ws, int text_ws_ready,
-                           void* pooled, float* w_out, int num_ctas, cudaStream_t stream) {
+                           void* pooled, float* w_out, float* w_scratch, int num_ctas, cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0) return 0;
     if (!fts || !slots || !perm || !cell_start || !cell_rank || !text_ws || !pooled) return GRIDMM_ERR_ARG;
     if (!text_ws_ready && !text_fts) return GRIDMM_ERR_ARG;
-    if (batch > POOL_MAX_BATCH || n_cells > POOL_MAX_CELLS || l_pad < 1 || l_pad > 128 || fts_rows <= 0) return GRIDMM_ERR_SHAPE;
+    if (batch > POOL_MAX_BATCH || n_cells > POOL_MAX_CELLS || l_pad < 1 || l_pad > 256 || fts_rows <= 0) return GRIDMM_ERR_SHAPE;
+    if (l_pad > 128 && !w_scratch) return GRIDMM_ERR_ARG;
     if (feat_dim != 768 && feat_dim != 512) return GRIDMM_ERR_SHAPE;
     if ((reinterpret_cast<uintptr_t>(text_fts) & 15) || (reinterpret_cast<uintptr_t>(text_ws) & 15)) return GRIDMM_ERR_SHAPE;
     PoolParams p;
     p.slots = slots; p.perm = perm; p.cell_start = cell_start; p.cell_rank = cell_rank;
     p.text_ws = reinterpret_cast<const uint4*>(text_ws);
-    p.pooled = reinterpret_cast<__half*>(pooled); p.w_out = w_out;
+    p.pooled = reinterpret_cast<__half*>(pooled); p.w_out = w_out; p.w_in = nullptr; p.max_only = 0;
     p.batch = batch; p.t_cap = t_cap; p.cap = cap; p.n_cells = n_cells; p.l_pad = l_pad;
     p.slot_rows = slot_rows; p.view_rows = view_rows; p.tok_off = tok_off; p.dbg = g_pool_dbg;
-    int dev = 0, sms = 0;
-    GMM_CUDA_CHECK(cudaGetDevice(&dev));
-    GMM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int sms = gridmm_sm_count();
+    if (sms <= 0) return GRIDMM_ERR_DRIVER;
     const int grid = num_ctas > 0 ? num_ctas : sms;
-    if (feat_dim == 768) return launch_pool<768>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, stream);
-    return launch_pool<512>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, stream);
+    if (feat_dim == 768) return launch_pool<768>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
+    return launch_pool<512>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
 }

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
 // ------------------------------------------------------------------------------------------- BERT text embeddings
 // LayerNorm(word[ids] + position[l] + token_type[0])   (BertEmbeddings.forward, vilmodel.py:77-93; one warp per token)
 __global__ void __launch_bounds__(256) text_embed_kernel(const long long* ids, const float* word, const float* pos,
-                                                         const float* type0, const float* gamma, const float* beta,
+                                                         const float* type0, const float* gamma, const float* beta, float eps,
                                                          float* o32, __half* o16, int L, int rows) {
     pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256) text_embed_kernel(const long long* ids, c
         const float4 c = *reinterpret_cast<const float4*>(type0 + col);
         v[i] = make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w);
     }
-    ln_row(v, gamma, beta, 1e-12f, lane);
+    ln_row(v, gamma, beta, eps, lane);
     store_row(v, o32 ? o32 + static_cast<size_t>(row) * HID : nullptr, o16 ? o16 + static_cast<size_t>(row) * HID : nullptr, lane);
     pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
@@ -633,15 +633,15 @@ extern "C" int gridmm_pos_embed(const float* feat, int kin, const float* w, cons
 }
 
 extern "C" int gridmm_text_embed(const long long* ids, const float* word, const float* pos, const float* type0,
-                                 const float* gamma, const float* beta, float* out_f32, void* out_f16, int batch, int L,
-                                 int hidden, cudaStream_t stream) {
+                                 const float* gamma, const float* beta, float eps, float* out_f32, void* out_f16, int batch,
+                                 int L, int hidden, cudaStream_t stream) {
     using namespace gmm;
     const int rows = batch * L;
     if (rows <= 0) return 0;
     if (hidden != HID) return GRIDMM_ERR_SHAPE;
     if (!ids || !word || !pos || !type0 || !gamma || !beta || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
     GMM_CUDA_CHECK(launch_pdl(text_embed_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, ids, word, pos, type0, gamma, beta,
-                              out_f32, reinterpret_cast<__half*>(out_f16), L, rows));
+                              eps, out_f32, reinterpret_cast<__half*>(out_f16), L, rows));
     gridmm_count_launch(1);
     return 0;
 }

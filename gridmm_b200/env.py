@@ -167,16 +167,35 @@ class GridMapBuilder:
         self.slab, self.wx, self.wy, self.valid = slab, wx, wy, valid
         self.cell = torch.full((B, cap), -1, dtype=torch.int16, device=dev)
         self.perm = torch.zeros(B, cap, dtype=torch.int32, device=dev)
-        # slot of (episode b, step t) = t * B + b  -> the B viewpoints of one step are one contiguous H2D copy
-        slots = (torch.arange(t_cap, dtype=torch.int32)[None, :] * B + torch.arange(B, dtype=torch.int32)[:, None])
-        self.slots = slots.contiguous().to(dev)
+        # slot of (episode b, step t) = t * B + b  -> the B viewpoints of one step are one contiguous H2D copy.  (With per-episode
+        # `active` masks an episode's t-th viewpoint is the one of the t'-th call, t' >= t: step() then rewrites its row of the table.)
+        slots = (torch.arange(t_cap, dtype=torch.int32)[None, :] * B + torch.arange(B, dtype=torch.int32)[:, None]).contiguous()
+        if old and getattr(self, "_slots_host", None) is not None:
+            slots[:, :old] = self._slots_host
+        self._slots_host = slots
+        self.slots = slots.to(dev)
         self.t_cap, self.cap = t_cap, cap
+
+    def _grow(self):
+        """Double the capacity, up to the 111 viewpoints (65 268 points) the 16-bit sort cursors allow."""
+        if self.t_cap >= 111:
+            raise ValueError("at most 111 viewpoints per episode (cell sort uses 16-bit cursors)")
+        self._alloc(min(self.t_cap * 2, 111))
 
     def new_episodes(self):
         """env.py:183-193."""
         self.bounds.copy_(torch.tensor([-10000.0, 10000.0, -10000.0, 10000.0]).repeat(self.batch, 1))
         self.n_pts.zero_()
-        self.n_steps = np.zeros(self.batch, dtype=np.int64)
+        self.n_steps = np.zeros(self.batch, dtype=np.int64)      # viewpoints accumulated per episode
+        self.n_calls = 0                                         # step() calls since the reset = next free slab row block
+        if getattr(self, "_lockstep", True) is False:
+            self._alloc_slots_reset()
+        self._lockstep = True
+
+    def _alloc_slots_reset(self):
+        B, t_cap = self.batch, self.t_cap
+        self._slots_host = (torch.arange(t_cap, dtype=torch.int32)[None, :] * B + torch.arange(B, dtype=torch.int32)[:, None]).contiguous()
+        self.slots.copy_(self._slots_host)
 
     # ------------------------------------------------------------------ one navigation step
     @staticmethod
@@ -213,10 +232,10 @@ class GridMapBuilder:
         after: optional CUDA event the copy must wait for (only needed when a slab slot is rewritten while an earlier step
         may still read it -- never the case in a real episode, where every step writes a new slot)."""
         grew = False
-        if int(self.n_steps.max()) + 1 > self.t_cap:
-            self._alloc(self.t_cap * 2)
+        if self.n_calls + 1 > self.t_cap:
+            self._grow()
             grew = True
-        t = int(self.n_steps[0])
+        t = self.n_calls
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             grew = True
@@ -253,12 +272,24 @@ class GridMapBuilder:
         Returns a GridBatch.
         """
         B, g = self.batch, self.geom
-        if int(self.n_steps.max()) + 1 > self.t_cap:
-            self._alloc(self.t_cap * 2)
+        if self.n_calls + 1 > self.t_cap:
+            self._grow()
+        t = self.n_calls                  # slab row block of this call (all B viewpoints, active or not, land in slab[t])
+        d_active = None
         if active is not None and not bool(np.all(active)):
-            raise NotImplementedError("per-episode `active` masks need per-episode step counters on the slab; "
-                                      "the reference re-adds the last viewpoint of ended episodes, so do that")
-        t = int(self.n_steps[0])
+            # Episodes with active[b] == 0 receive no viewpoint (the kernel leaves their points / bounds alone and only re-assigns
+            # cells); the others append theirs as viewpoint n_steps[b], which lives in slab row block t = this call's index.
+            # (The reference itself never skips: it re-adds the last viewpoint of ended episodes, r2r/env.py:392-398.)
+            act = np.asarray(active).astype(bool).reshape(B)
+            self._lockstep = False
+            idx = torch.from_numpy(np.nonzero(act)[0])
+            self._slots_host[idx, torch.from_numpy(self.n_steps[act])] = (t * B + idx).to(torch.int32)
+            self.slots.copy_(self._slots_host, non_blocking=False)
+            d_active = torch.from_numpy(act.astype(np.uint8)).to(self.device)
+        elif not self._lockstep:
+            idx = torch.arange(B)
+            self._slots_host[idx, torch.from_numpy(self.n_steps)] = (t * B + idx).to(torch.int32)
+            self.slots.copy_(self._slots_host, non_blocking=False)
         self._pinned_free(clip_too=clip is not None)      # a staged copy of THIS step is waited for on the device, below
         # features: one contiguous copy into slab[t]
         if clip is None:
@@ -290,10 +321,11 @@ class GridMapBuilder:
         self.d_view.copy_(self.h_view, non_blocking=True)
         self._h2d_evt = torch.cuda.Event()
         self._h2d_evt.record()
-        ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, None, g.off7, g.flip_y,
+        ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, d_active, g.off7, g.flip_y,
                         g.negate_map_x, g.pos_mode, g.max_dist, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
                         self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
-        self.n_steps += 1
+        self.n_steps += 1 if d_active is None else np.asarray(active).astype(np.int64).reshape(B)
+        self.n_calls += 1
         return GridBatch(self)
 
     def run_trajectory(self, depth_sub, clip, pos_xy, heading):

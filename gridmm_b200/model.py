@@ -46,6 +46,9 @@ class NavConfig:
         self.graph_sprels = True
         self.glocal_fuse = True
         self.grid_w = 14             # GLOBAL_WIDTH / GLOBAL_HEIGHT, map_nav_src/r2r/env.py:43-44 (hard-coded there)
+        # eps of the LayerNorms inside the BERT blocks (vilmodel.py:75, 163, 202, 282 read config.layer_norm_eps): 1e-12 for
+        # bert-base, 1e-5 for xlm-roberta-base (`--tokenizer xlm`, the RxR default: vlnbert_init.py:29-35, rxr/parser.py:13)
+        self.layer_norm_eps = 1e-12
         # pretraining trunk (pretrain_src/model/vilmodel.py:640-666): no action heads, no sprel_linear, and with
         # use_lang2visn_attn every GraphLXRTXLayer also owns the lang_* blocks that forward_mlm runs (:369-385)
         self.pretrain_trunk = False
@@ -423,7 +426,7 @@ class GlocalTextPathNavCMT(nn.Module):
         h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16)
         ops.linear(x16, self.W16(pre_i + ".dense.weight"), self.B32(pre_i + ".dense.bias"), out_f16=h, act=ops.ACT_GELU)
         ops.linear_ln(h, self.W16(pre_o + ".dense.weight"), self.B32(pre_o + ".dense.bias"), x32, self.P(pre_o + ".LayerNorm.weight"),
-                      self.P(pre_o + ".LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
+                      self.P(pre_o + ".LayerNorm.bias"), self.config.layer_norm_eps, out_f32=x32, out_f16=x16)
 
     def _self_post(self, x32, x16, pre, kmask, B, S, tag):
         """BertAttention (vilmodel.py:172-182): x = LN(Wo attn(x) + x), additive -10000 mask."""
@@ -432,7 +435,8 @@ class GlocalTextPathNavCMT(nn.Module):
                    self.B32(pre + ".self.query.bias", pre + ".self.key.bias", pre + ".self.value.bias"), out_f16=qkv)
         a = self._attention(qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:], kmask, NEG_BERT, B, S, S, "att16_" + tag)
         ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
-                      self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
+                      self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), self.config.layer_norm_eps,
+                      out_f32=x32, out_f16=x16)
 
     def _cross_post(self, x32, x16, pre, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None):
         """BertXAttention (vilmodel.py:317-379): x = LN(Wo attn(q = x, kv = ctx) + x).
@@ -445,7 +449,8 @@ class GlocalTextPathNavCMT(nn.Module):
         else:
             a = self._attention(q, ctx_k, ctx_v, ctx_mask, NEG_BERT, B, S, Sk, "att16_" + tag)
         ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
-                      self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), 1e-12, out_f32=x32, out_f16=x16)
+                      self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), self.config.layer_norm_eps,
+                      out_f32=x32, out_f16=x16)
 
     def _lxrt_layer(self, pre, x32, x16, x_mask, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None):
         """GraphLXRTXLayer.forward (vilmodel.py:399-414): cross-attention, self-attention, FFN (all post-norm)."""
@@ -506,7 +511,20 @@ class GlocalTextPathNavCMT(nn.Module):
         n = [int(x.shape[0]) for x in grid_fts]
         if any(v % 588 for v in n):
             raise ValueError("grid_fts rows must be a multiple of 588 (12 views x 49 patches, r2r/env.py:299)")
-        t_cap = max(max(n) // 588, 1)
+        # capacity in viewpoints: grows by doubling (as GridMapBuilder does), so an episode of T steps re-allocates the staging
+        # buffers O(log T) times instead of once per step (every size gets its own workspace entry and CUDA graph)
+        t_need = max(max(n) // 588, 1)
+        t_cap = max(getattr(self, "_compat_t_cap", 4), 4)
+        while t_cap < t_need:
+            t_cap *= 2
+        t_cap = min(t_cap, 111)
+        if t_need > t_cap:
+            raise ValueError("at most 111 viewpoints per episode (65535 points: the cell sort uses 16-bit cursors)")
+        if t_cap != getattr(self, "_compat_t_cap", None):
+            for key in [k for k in self._ws if isinstance(k[0], str) and k[0].startswith("compat_")]:
+                del self._ws[key]          # drop the smaller generation
+            self._graphs = {}
+            self._compat_t_cap = t_cap
         cap = t_cap * 588
         D = int(grid_fts[0].shape[1])
         nc = self.config.grid_w ** 2
@@ -621,9 +639,9 @@ class GlocalTextPathNavCMT(nn.Module):
         txt16 = self.buf("txt16", (B * L, HID), f16)
         ops.copy_rows(txt32, L, 0, L, B, L, 0, out_f16=txt16)
         # text_proj lands directly in the pooling kernel's lane-major operand layout (no fp16 [B, L, 768] round trip)
-        if L > 128:
-            raise ops._lib.GridmmError("gridmm_pool keeps one text position per TMEM lane: at most 128 text positions")
-        text_ws = ops.pool_text_ws(txt16.device, B, HID)
+        if L > 256:
+            raise ops._lib.GridmmError("gridmm_pool covers at most 256 text positions (two passes of 128 tensor-memory lanes)")
+        text_ws = ops.pool_text_ws(txt16.device, B, HID, L)
         ops.linear_lanes(txt16, self.W16("text_proj.weight"), self.B32("text_proj.bias"), text_ws, L)
         pooled16 = self.buf("pooled16", (B * NC, HID), f16, zero=True)
         w_out = self.buf("w_out", (B, grid.cap), f32, zero=True) if return_intermediates else None
@@ -757,7 +775,7 @@ class GlocalTextPathNavCMT(nn.Module):
         x16 = self.buf("lang_x16", (B * L, HID), torch.float16)
         ops.text_embed(ids, self.P("embeddings.word_embeddings.weight"), self.P("embeddings.position_embeddings.weight"),
                        self.P("embeddings.token_type_embeddings.weight"), self.P("embeddings.LayerNorm.weight"),
-                       self.P("embeddings.LayerNorm.bias"), x32, x16, B, L)
+                       self.P("embeddings.LayerNorm.bias"), x32, x16, B, L, eps=self.config.layer_norm_eps)
         for i in range(self.config.num_l_layers):
             p = "lang_encoder.layer.%d" % i
             self._self_post(x32, x16, p + ".attention", mask_u8, B, L, "lang")
@@ -932,8 +950,19 @@ class GlocalTextPathNavCMT(nn.Module):
             out[b, :n] = torch.cat((logits[b, 1:n], logits[b, 0:1]), 0)
         return out
 
+    def _require_eval(self):
+        """The kernels behind forward() are inference kernels: dropout is the identity and no autograd graph is recorded (the
+        outputs never require grad).  The reference's fine-tuning loop calls loss.backward() on these outputs
+        (map_nav_src/r2r/agent_base.py:203-208); rather than let that fail later with "does not require grad" -- or let
+        model.train() silently behave as eval -- training mode is refused here.  The training step of this package is
+        gridmm_b200.train (pretraining objectives), not this forward."""
+        if self.training:
+            raise RuntimeError("gridmm_b200 forward(mode, batch) is inference-only (eval semantics, no autograd): call model.eval() "
+                               "for test/eval rollouts; see gridmm_b200.train for the training step")
+
     def forward(self, mode, batch, **kwargs):
         """vilmodel.py:920-939.  A tuple batch selects the continuous-env calling convention (gridmap/vilmodel.py:802-817)."""
+        self._require_eval()
         if isinstance(batch, (tuple, list)):
             if mode == "language":
                 return self.forward_text(batch[0], batch[1])
@@ -974,6 +1003,9 @@ class VLNBert(nn.Module):
                         kw[c] = getattr(args, a)
                 if hasattr(args, "fusion"):
                     kw["glocal_fuse"] = args.fusion == "dynamic"
+                if getattr(args, "tokenizer", "bert") == "xlm":
+                    # PretrainedConfig.from_pretrained('xlm-roberta-base') + type_vocab_size = 2 (vlnbert_init.py:29-35)
+                    kw.update(vocab_size=250002, max_position_embeddings=514, type_vocab_size=2, layer_norm_eps=1e-5)
             config = NavConfig(**kw)
         self.args = args
         self.vln_bert = GlocalTextPathNavCMT(config)

@@ -154,10 +154,10 @@ def pos_embed(feat, w, bias, gamma, beta, eps, out_f32, out_f16, in_rows_per_b, 
               in_rows_per_b, out_rows_per_b, out_row_off, rows, HID, _lib.stream_ptr())
 
 
-def text_embed(ids, word, pos, type0, gamma, beta, out_f32, out_f16, batch, L):
+def text_embed(ids, word, pos, type0, gamma, beta, out_f32, out_f16, batch, L, eps=1e-12):
     _chk(ids, torch.int64, "ids"); _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
     _lib.call("gridmm_text_embed", ids.data_ptr(), word.data_ptr(), pos.data_ptr(), type0.data_ptr(), gamma.data_ptr(),
-              beta.data_ptr(), _lib.ptr(out_f32), _lib.ptr(out_f16), batch, L, HID, _lib.stream_ptr())
+              beta.data_ptr(), float(eps), _lib.ptr(out_f32), _lib.ptr(out_f16), batch, L, HID, _lib.stream_ptr())
 
 
 def grid_assemble(proj, pos_fts, cell_rank, n_nonempty, w, bias, gamma, beta, map_f32, map_mask, batch, n_cells, seq):
@@ -246,12 +246,23 @@ def grid_update(batch, depth, depth_is_f32, depth_scale, pose, view_cs, active, 
 _POOL_WS = {}
 
 
-def pool_text_ws(device, batch, feat_dim):
-    """Persistent (CUDA-graph safe) lane-major text workspace of gridmm_pool: [batch, feat_dim/8, 128] 16-byte units."""
-    key = (device, batch, feat_dim)
+def pool_text_ws(device, batch, feat_dim, l_pad=128):
+    """Persistent (CUDA-graph safe) lane-major text workspace of gridmm_pool: [ceil(l_pad/128)][batch, feat_dim/8, 128] 16-byte
+    units (a text of 129..256 positions takes a second block, see include/gridmm_b200.h)."""
+    blocks = (int(l_pad) + 127) // 128
+    key = (device, batch, feat_dim, blocks)
     ws = _POOL_WS.get(key)
     if ws is None:
-        ws = _POOL_WS[key] = torch.zeros(batch * 128 * feat_dim, dtype=torch.float16, device=device)
+        ws = _POOL_WS[key] = torch.zeros(blocks * batch * 128 * feat_dim, dtype=torch.float16, device=device)
+    return ws
+
+
+def pool_w_scratch(device, batch, cap):
+    """f32 [batch, cap] row maxima of the first pass over a text longer than 128 positions."""
+    key = ("w", device, batch, cap)
+    ws = _POOL_WS.get(key)
+    if ws is None:
+        ws = _POOL_WS[key] = torch.zeros(batch, cap, dtype=torch.float32, device=device)
     return ws
 
 
@@ -272,11 +283,15 @@ def pool(fts, feat_dim, slots, t_cap, slot_rows, view_rows, tok_off, perm, cap, 
     if text_ws is None:
         if text_ws_ready:
             raise _lib.GridmmError("text_ws_ready needs the workspace that linear_lanes filled")
-        text_ws = pool_text_ws(fts.device, batch, feat_dim)
+        text_ws = pool_text_ws(fts.device, batch, feat_dim, l_pad)
+    if text_ws.numel() < ((l_pad + 127) // 128) * batch * 128 * feat_dim:
+        raise _lib.GridmmError("text_ws too small for %d text positions" % l_pad)
+    w_scratch = pool_w_scratch(fts.device, batch, cap) if l_pad > 128 else None
     fts_rows = fts.numel() // feat_dim
     _lib.call("gridmm_pool", fts.data_ptr(), fts_rows, feat_dim, slots.data_ptr(), t_cap, slot_rows, view_rows, tok_off,
               perm.data_ptr(), cap, cell_start.data_ptr(), cell_rank.data_ptr(), n_cells, _lib.ptr(text_fts), l_pad, batch,
-              text_ws.data_ptr(), int(bool(text_ws_ready)), pooled.data_ptr(), _lib.ptr(w_out), num_ctas, _lib.stream_ptr())
+              text_ws.data_ptr(), int(bool(text_ws_ready)), pooled.data_ptr(), _lib.ptr(w_out), _lib.ptr(w_scratch), num_ctas,
+              _lib.stream_ptr())
 
 
 def cell_sort(batch, cell, n_pts, grid_w, cap, perm, cell_start, cell_rank, n_nonempty):

@@ -74,18 +74,23 @@ int gridmm_cell_sort(int batch, const short* cell, const int* n_pts, int grid_w,
  *   fts          fp16 feature slab [fts_rows, feat_dim], row r at fts + r*feat_dim; point (step t, view v, patch k) of episode
  *                b is row slots[b*t_cap+t]*slot_rows + v*view_rows + tok_off + k (CLS token skipped via tok_off,
  *                env.py:299); rows are fetched with TMA tile::gather4 through a tensor map over the whole slab
- *   text_fts     fp16 [batch, l_pad, feat_dim] = text_proj(txt_embeds), 16-byte aligned; l_pad <= 128 (the operand lives in
- *                tensor memory, one text position per TMEM lane; unused lanes replicate position 0); may be NULL when
+ *   text_fts     fp16 [batch, l_pad, feat_dim] = text_proj(txt_embeds), 16-byte aligned; l_pad <= 256 (the reference's launch
+ *                scripts use --max_instr_len 200, 250 for RxR: scripts/run_r2r.sh:38, run_rxr.sh:38).  The operand lives in
+ *                tensor memory, one text position per TMEM lane (unused lanes replicate a real position): up to 128 positions
+ *                are ONE pass over the features; 129..256 positions take two (the first only produces the row maxima over
+ *                positions 128.. into w_scratch, the second merges them before the softmax).  May be NULL when
  *                text_ws_ready != 0
- *   text_ws      workspace, batch * 128 * feat_dim * 2 bytes, 16-byte aligned: lane-major copy of text_fts -- written here
- *                (text_ws_ready = 0) or already produced by gridmm_linear_f16_lanes (text_ws_ready = 1)
+ *   text_ws      workspace, ceil(l_pad/128) * batch * 128 * feat_dim * 2 bytes, 16-byte aligned: lane-major copy of text_fts
+ *                as [ceil(l_pad/128)][batch][feat_dim/8][128] 16-byte units -- written here (text_ws_ready = 0) or already
+ *                produced by gridmm_linear_f16_lanes (text_ws_ready = 1)
  *   pooled       fp16 [batch, n_cells, feat_dim], rows >= n_nonempty[b] are not written
  *   w_out        optional f32 [batch,cap]: w per sorted position (tests), or NULL
+ *   w_scratch    f32 [batch,cap], required when l_pad > 128 (else may be NULL)
  *   num_ctas     0 = one CTA per SM */
 int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, const int* slots, int t_cap, int slot_rows, int view_rows,
                 int tok_off, const int* perm, int cap, const int* cell_start, const int* cell_rank, int n_cells,
                 const void* text_fts, int l_pad, int batch, void* text_ws, int text_ws_ready, void* pooled, float* w_out,
-                int num_ctas, cudaStream_t stream);
+                float* w_scratch, int num_ctas, cudaStream_t stream);
 
 /* ---- stage 3: cross-modal encoder blocks ------------------------------------------------------------------
  * nn.Linear on tcgen05: out = act(a[M,K] . w[N,K]^T + bias) + residual; fp16 operands, fp32 accumulate.
@@ -165,8 +170,8 @@ int gridmm_nav_logits2(const float* part, const float* fuse_raw, const float* fu
                        cudaStream_t stream);
 
 /* text_proj (vilmodel.py:702, 793-795) written straight into gridmm_pool's lane-major operand layout:
- * out_lanes[b][u][t] (16-byte units, 128 slots per unit row) = (a[b*rows_per_b + t, :] . w^T + bias)[8u .. 8u+7];
- * M = batch*rows_per_b, rows_per_b <= 128. */
+ * out_lanes[t / 128][b][u][t % 128] (16-byte units, 128 slots per unit row) = (a[b*rows_per_b + t, :] . w^T + bias)[8u .. 8u+7];
+ * M = batch*rows_per_b, rows_per_b <= 256 (a second [batch][N/8][128] block holds positions 128..). */
 int gridmm_linear_f16_lanes(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                             void* out_lanes, int rows_per_b, cudaStream_t stream);
 
@@ -198,10 +203,11 @@ int gridmm_pos_embed(const float* feat, int kin, const float* w, const float* bi
                      float eps, const float* base, const float* table, const long long* idx, float* out_f32, void* out_f16,
                      int in_rows_per_b, int out_rows_per_b, int out_row_off, int rows, int hidden, cudaStream_t stream);
 
-/* BERT text embeddings: LayerNorm(word[ids] + position[0..L) + token_type[0]), eps 1e-12 (BertEmbeddings.forward,
- * vilmodel.py:77-93); ids int64 [batch, L]. */
+/* BERT text embeddings: LayerNorm(word[ids] + position[0..L) + token_type[0]), eps = config.layer_norm_eps (1e-12 for
+ * bert-base, 1e-5 for xlm-roberta-base: BertEmbeddings.forward, vilmodel.py:75-93); ids int64 [batch, L]. */
 int gridmm_text_embed(const long long* ids, const float* word, const float* pos, const float* type0, const float* gamma,
-                      const float* beta, float* out_f32, void* out_f16, int batch, int L, int hidden, cudaStream_t stream);
+                      const float* beta, float eps, float* out_f32, void* out_f16, int batch, int L, int hidden,
+                      cudaStream_t stream);
 
 /* grid cells of the map sequence + validity mask incl. the reference's compaction quirk (vilmodel.py:813-823);
  * w is the TRANSPOSED grid_pos_embeddings.0 weight, [5, 768]. */

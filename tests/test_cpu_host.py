@@ -196,7 +196,7 @@ def _stub_ops(monkeypatch):
         fn = getattr(ops, name)
         if isinstance(fn, types.FunctionType) and not name.startswith("_") and name != "pool_text_ws":
             monkeypatch.setattr(ops, name, (lambda n: (lambda *a, **k: calls.append(n)))(name))
-    monkeypatch.setattr(ops, "pool_text_ws", lambda dev, B, D: torch.zeros(B * 128 * D, dtype=torch.float16))
+    monkeypatch.setattr(ops, "pool_text_ws", lambda dev, B, D, L=128: torch.zeros((L + 127) // 128 * B * 128 * D, dtype=torch.float16))
     return calls
 
 
@@ -306,3 +306,21 @@ def test_bench_flop_model_matches_the_survey():
     assert 13.0e9 < per_sample < 14.4e9
     packed = bench.gemm_flops_per_step(kv_rows=bench.B * 217)        # ~217 valid context rows per episode instead of 296
     assert packed < bench.gemm_flops_per_step() and packed > 0.9 * bench.gemm_flops_per_step()
+
+
+def test_subsample_depth_reads_the_reference_pixels():
+    """SURVEY 8a row 1 (host indexing, no GPU): views 12..23 and pixels 9 + 18 i of a [36,128,128] map (r2r/env.py:278-285);
+    19 + 36 i of the CE policy's [12,256,256] stack.  Everything else is noise here, so a wrong stride or view range fails."""
+    from gridmm_b200.env import GridMapBuilder
+    rng = np.random.default_rng(3)
+    full = rng.integers(1, 60000, size=(2, 36, 128, 128)).astype(np.uint16)
+    c = np.array([9 + 18 * i for i in range(7)])
+    want = np.stack([[full[b, 12 + v][c[:, None], c[None, :]].reshape(49) for v in range(12)] for b in range(2)])
+    got = GridMapBuilder.subsample_depth(full)
+    assert got.shape == (2, 12, 49) and np.array_equal(got, want)
+    assert np.array_equal(GridMapBuilder.subsample_depth(full[0]), want[0])              # one episode, no batch axis
+    ce = rng.random((2, 12, 256, 256)).astype(np.float32)
+    c = np.array([19 + 36 * i for i in range(7)])
+    want = np.stack([[ce[b, v][c[:, None], c[None, :]].reshape(49) for v in range(12)] for b in range(2)])
+    assert np.array_equal(GridMapBuilder.subsample_depth(ce, ce=True), want)
+    assert np.array_equal(GridMapBuilder.subsample_depth(synth.expand_depth(want[0].astype(np.uint16))), want[0].astype(np.uint16))

@@ -55,22 +55,26 @@ def test_linear_epilogues(act):
     assert (out - ref).abs().max().item() < 2e-3
 
 
-@pytest.mark.parametrize("B,L", [(32, 80), (3, 37), (1, 128)])
+@pytest.mark.parametrize("B,L", [(32, 80), (3, 37), (1, 128), (3, 136), (2, 200), (4, 250), (1, 256)])
 def test_linear_lanes_layout(B, L):
-    """text_proj epilogue that writes gridmm_pool's lane-major operand: unit u of (b, t) at ((b*96 + u)*128 + t) * 8 halves."""
+    """text_proj epilogue that writes gridmm_pool's lane-major operand: unit u of (b, t) at ((b*96 + u)*128 + t) * 8 halves;
+    positions 128.. of a long text (--max_instr_len 200 / 250) in a second [B, 96, 128] block."""
     from gridmm_b200 import ops
     g = torch.Generator().manual_seed(B * 131 + L)
     a = torch.randn(B * L, 768, generator=g).half().to(_dev())
     w = (torch.randn(768, 768, generator=g) * 0.05).half().to(_dev())
     bias = torch.randn(768, generator=g).to(_dev())
-    ws = torch.zeros(B * 128 * 768, dtype=torch.float16, device=_dev())
+    nblk = (L + 127) // 128
+    ws = torch.zeros(nblk * B * 128 * 768, dtype=torch.float16, device=_dev())
     ops.linear_lanes(a, w, bias, ws, L)
     ref16 = torch.empty(B * L, 768, device=_dev(), dtype=torch.float16)
     ops.linear(a, w, bias=bias, out_f16=ref16)
     torch.cuda.synchronize()
-    got = ws.view(B, 96, 128, 8)[:, :, :L].permute(0, 2, 1, 3).reshape(B * L, 768)
+    # [blk, b, u, t, 8] -> [b, blk * 128 + t, u * 8]
+    full = ws.view(nblk, B, 96, 128, 8).permute(1, 0, 3, 2, 4).reshape(B, nblk * 128, 768)
+    got = full[:, :L].reshape(B * L, 768)
     assert torch.equal(got, ref16)                                   # same kernel, same rounding: bitwise
-    assert ws.view(B, 96, 128, 8)[:, :, L:].abs().max().item() == 0 if L < 128 else True
+    assert full[:, L:].abs().max().item() == 0 if L < nblk * 128 else True
     ref = a.float() @ w.float().t() + bias
     assert (got.float() - ref).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
 
@@ -306,8 +310,12 @@ def _oracle_pool(fts, cell, tp16, n_cells=196):
     return out, w
 
 
-@pytest.mark.parametrize("B,T,L,D,gw", [(3, 2, 80, 768, 14), (8, 8, 80, 768, 14), (2, 15, 40, 768, 14), (1, 1, 16, 512, 8), (37, 3, 24, 768, 14)])
+@pytest.mark.parametrize("B,T,L,D,gw", [(3, 2, 80, 768, 14), (8, 8, 80, 768, 14), (2, 15, 40, 768, 14), (1, 1, 16, 512, 8), (37, 3, 24, 768, 14),
+                                        (3, 2, 128, 768, 14), (3, 2, 129, 768, 14), (3, 3, 136, 768, 14), (5, 4, 200, 768, 14),
+                                        (2, 8, 250, 768, 14), (2, 2, 256, 768, 14), (2, 2, 200, 512, 8)])
 def test_pool_vs_oracle(B, T, L, D, gw):
+    """L > 128 (the reference's --max_instr_len 200 / 250, vilmodel.py:798 takes the max over ALL positions): two passes of the
+    kernel, the first over positions 128.. only produces row maxima."""
     from gridmm_b200 import ops
     ep = synth.make_episodes(B, T, seed=B * 100 + T, dim=D)
     cells, fts, halfs, pos = H.oracle_grid(ep, grid_w=gw)
