@@ -31,11 +31,29 @@ sys.path.insert(0, ROOT)
 from gridmm_b200 import synth  # noqa: E402
 
 B, T, L, G, VIEWS = 32, 8, 80, 20, 36
+OBJS, CE = 0, False
 METRIC = "nav-steps/sec (grid build + cross-modal encode) R2R batch"
 CONFIG = {"workload": "configs[1]: R2R fine-tune forward, batch 32/GPU, 14x14 grid, 36-view pano, 80-tok instr, step T=8 "
                       "(N=4704 points/episode), eval mode",
           "batch_per_gpu": B, "T": T, "txt_len": L, "gmap_len": G, "views": VIEWS,
-          "l2": "inputs > L2: the pooling kernel streams ~208 MB of fp16 patch features per step; activations are L2-resident by nature"}
+          "l2": "inputs > L2 (126 MB): every step streams ~208 MB of fp16 patch features plus ~120 MB of fp16 weights from HBM, so "
+                "consecutive steps cannot reuse each other's cache lines; no explicit flush"}
+WORKLOADS = {
+    # name: (workload text, B, views, objs, continuous-env)
+    "r2r": ("configs[1]: R2R fine-tune forward, batch 32/GPU, 14x14 grid, 36-view pano, 80-tok instr", 32, 36, 0, False),
+    "reverie": ("configs[2]: REVERIE with object tokens (20 objects), batch 32/GPU, 14x14 grid", 32, 36, 20, False),
+    "ce": ("configs[3]: R2R-CE continuous-env forward (grid map + candidate head), batch 16/GPU, 12 views", 16, 12, 0, True),
+}
+
+
+def set_workload(name, t):
+    """Select a BASELINE config (headline = r2r, T = 8).  The other workloads are extra bench lines kept under profiles/."""
+    global B, T, VIEWS, OBJS, CE
+    text, B, VIEWS, OBJS, CE = WORKLOADS[name]
+    T = int(t)
+    CONFIG.update(workload="%s, step T=%d (N=%d points/episode), eval mode" % (text, T, 588 * T), batch_per_gpu=B, T=T, views=VIEWS)
+    if OBJS:
+        CONFIG["objects"] = OBJS
 
 
 def _dist_env():
@@ -64,32 +82,39 @@ def aggregate(ms_local, steps, world, device=None):
 
 def _inputs(seed):
     ep = synth.make_episodes(B, T, seed=seed, dim=768)
-    nav = synth.make_nav_inputs(B, seed=seed, txt_len=L, gmap_len=G, n_views=VIEWS)
+    if CE:
+        ep["depth_sub"] = (ep["depth_sub"].astype(np.float32) / 4000.0).astype(np.float32)      # the CE depth sensor: metres
+    nav = synth.make_nav_inputs(B, seed=seed, txt_len=L, gmap_len=G, n_views=VIEWS, n_objs=OBJS)
     return ep, nav
 
 
-def _weights(seed=0, obj=False):
+def _weights(seed=0, obj=None):
     from gridmm_b200.model import NavConfig, param_spec
-    cfg = NavConfig(num_l_layers=1, num_pano_layers=1, obj_feat_size=768 if obj else 0)   # lang/pano encoders are not on the path
+    obj = bool(OBJS) if obj is None else obj
+    cfg = NavConfig(num_l_layers=1, num_pano_layers=1, obj_feat_size=768 if obj else 0,   # lang/pano encoders are not on the path
+                    graph_sprels=not CE)
     w = synth.make_weights({k: v[0] for k, v in param_spec(cfg).items()}, seed=seed)
     return cfg, w
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline
-def cpu_reference_steps(ep, nav_np, cfg, w, n_steps, threads):
+def cpu_reference_steps(ep, nav_np, cfg, w, n_steps, threads, device="cpu"):
     """The reference algorithm on host cores: per-episode serial grid build (r2r/env.py:392-398) + forward('navigation')
-    (vilmodel.py:782-918) through the oracle port.  Returns seconds per step (best of n_steps after one warm-up)."""
+    (vilmodel.py:782-918) through the oracle port.  Returns seconds per step (best of n_steps after one warm-up).
+    device="cuda": the same torch code with its tensors on the GPU (stock torch eager: the `gpu_eager_baseline` leg; the grid
+    build stays numpy on the host, as in the reference, and the whole map is uploaded every step like r2r/agent.py:168)."""
     from oracle import grid_oracle as go
     from oracle import model_oracle as mo
     torch.set_num_threads(threads)
-    sd = {k: torch.from_numpy(v) for k, v in w.items()}
-    nav = synth.to_torch(nav_np)
+    geom = go.CEGeometry if CE else go.R2RGeometry
+    sd = {k: torch.from_numpy(v).to(device) for k, v in w.items()}
+    nav = synth.to_torch(nav_np, device)
     # state after T-1 viewpoints (not timed)
     states = []
     for b in range(B):
         st = go.GridState()
         for t in range(T - 1):
-            go.grid_step(st, ep["depth_sub"][b, t], ep["clip"][b, t], ep["pos"][b, t], float(ep["heading"][b, t]))
+            go.grid_step(st, ep["depth_sub"][b, t], ep["clip"][b, t], ep["pos"][b, t], float(ep["heading"][b, t]), geom=geom)
         states.append(st)
     times = []
     for it in range(n_steps + 1):
@@ -99,16 +124,20 @@ def cpu_reference_steps(ep, nav_np, cfg, w, n_steps, threads):
             st = states[b]
             keep = (len(st.wx), st.max_x, st.min_x, st.max_y, st.min_y)
             f, c, h = go.grid_step(st, ep["depth_sub"][b, T - 1], ep["clip"][b, T - 1], ep["pos"][b, T - 1],
-                                   float(ep["heading"][b, T - 1]))
-            pos.append(go.gridmap_pos_fts(h))
-            fts.append(torch.from_numpy(f)); cells.append(torch.from_numpy(c.astype(np.float64)))
+                                   float(ep["heading"][b, T - 1]), geom=geom)
+            pos.append(go.gridmap_pos_fts(h, 14, geom))
+            fts.append(torch.from_numpy(f).to(device)); cells.append(torch.from_numpy(c.astype(np.float64)).to(device))
             # roll the state back so every timed step is the same T-th step
             del st.wx[keep[0]:], st.wy[keep[0]:], st.mask[keep[0]:], st.fts[keep[0]:]
             st.max_x, st.min_x, st.max_y, st.min_y = keep[1:]
         nav["grid_fts"], nav["grid_map"] = fts, cells
-        nav["gridmap_pos_fts"] = torch.from_numpy(np.stack(pos).astype(np.float32))
+        nav["gridmap_pos_fts"] = torch.from_numpy(np.stack(pos).astype(np.float32)).to(device)
         with torch.no_grad():
-            out = mo.navigation(sd, nav, n_x_layers=cfg.num_x_layers)
+            if CE:
+                nav["candidate_lengths"] = [int(x) for x in nav["vp_nav_masks"].sum(1)]
+                out = {"fused_logits": mo.navigation_ce(sd, nav, n_x_layers=cfg.num_x_layers)}
+            else:
+                out = mo.navigation(sd, nav, n_x_layers=cfg.num_x_layers)
         float(out["fused_logits"][0, 0])
         dt = time.perf_counter() - t0
         if it > 0:
@@ -200,55 +229,63 @@ class Step:
             model = GlocalTextPathNavCMT(self.cfg)
             model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
             model.to(device).eval()
-            model.enable_cuda_graph(True)       # the device part of forward('navigation') replays from a CUDA graph
+            model.enable_cuda_graph(True)       # the device part of the step replays from a CUDA graph
         self.model = model
-        self.builder = GridMapBuilder(B, max_steps=T, device=device)
+        self.builder = GridMapBuilder(B, max_steps=T, device=device, geometry="r2r_ce" if CE else "r2r")
         ep = self.ep
         for t in range(T - 1):
             self.builder.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
-        # saved state of step T-1, restored before every step so each timed step is the same 8th step
+        # saved state of step T-1, restored before every step so each timed step is the same T-th step
         self.saved_bounds = self.builder.bounds.clone()
         self.saved_npts = self.builder.n_pts.clone()
         self.saved_steps = self.builder.n_steps.copy()
         self.saved_calls = self.builder.n_calls
         self.nav = {k: (v.to(device) if isinstance(v, torch.Tensor) else v) for k, v in synth.to_torch(self.nav_np).items()}
+        self.cand = [int(x) for x in self.nav_np["vp_nav_masks"].sum(1)]
         # host (pinned) and device copies of the step's new observation
-        self.h_depth = torch.from_numpy(ep["depth_sub"][:, T - 1].astype(np.int16)).pin_memory()
+        d = ep["depth_sub"][:, T - 1]
+        self.h_depth = torch.from_numpy(np.ascontiguousarray(d if CE else d.astype(np.int16))).pin_memory()
         self.h_clip = torch.from_numpy(np.ascontiguousarray(ep["clip"][:, T - 1])).pin_memory()
         self.d_depth = self.h_depth.to(device)
         self.d_clip = self.h_clip.to(device)
         # per-step host-originating nav inputs (ids, position features, masks); embeddings stay on the device, where the
         # reference's 'language' / 'panorama' modes leave them
         self.host_keys = ["gmap_step_ids", "gmap_pos_fts", "gmap_masks", "gmap_visited_masks", "vp_pos_fts", "vp_masks",
-                          "vp_nav_masks"]
+                          "vp_nav_masks"] + (["vp_obj_masks"] if OBJS else [])
         self.h_nav = {k: synth.to_torch(self.nav_np)[k].pin_memory() for k in self.host_keys}
 
     def restore(self):
-        self.builder.bounds.copy_(self.saved_bounds)
-        self.builder.n_pts.copy_(self.saved_npts)
+        from gridmm_b200 import ops
+        ops.copy_segments([(self.saved_bounds, self.builder.bounds), (self.saved_npts, self.builder.n_pts)])
         self.builder.n_steps = self.saved_steps.copy()
         self.builder.n_calls = self.saved_calls
+
+    def _forward(self, grid, batch):
+        if CE:
+            n = batch
+            tup = (n["txt_embeds"], n["txt_masks"], n["gmap_img_embeds"], n["gmap_step_ids"], n["gmap_pos_fts"], n["gmap_masks"],
+                   n["vp_img_embeds"], n["vp_pos_fts"], n["vp_masks"], n["vp_nav_masks"], None, None, None, self.cand)
+            return {"fused_logits": self.model("navigation", tup, grid=grid)}
+        batch["grid"] = grid
+        batch.update(grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        return self.model("navigation", batch)
 
     def run_resident(self):
         """inputs already in HBM"""
         self.restore()
         ep = self.ep
-        grid = self.builder.step(self.d_depth, self.d_clip, ep["pos"][:, T - 1], ep["heading"][:, T - 1])
-        batch = dict(self.nav); batch["grid"] = grid
-        batch.update(grid_fts=None, grid_map=None, gridmap_pos_fts=None)
-        return self.model("navigation", batch)
+        grid = self.builder.step(self.d_depth, self.d_clip, ep["pos"][:, T - 1], ep["heading"][:, T - 1], lazy=True)
+        return self._forward(grid, dict(self.nav))
 
     def run_e2e(self):
         """host buffers in, logits out: H2D of the new viewpoint (depth + CLIP tokens) and of the step's nav inputs,
         D2H of the fused logits."""
         self.restore()
         ep = self.ep
-        grid = self.builder.step(self.h_depth.numpy().view(np.uint16), self.h_clip, ep["pos"][:, T - 1], ep["heading"][:, T - 1])
-        batch = dict(self.nav); batch["grid"] = grid
-        batch.update(grid_fts=None, grid_map=None, gridmap_pos_fts=None)
-        for k in self.host_keys:
-            batch[k] = self.h_nav[k].to(self.dev, non_blocking=True)
-        out = self.model("navigation", batch)
+        grid = self.builder.step(self.h_depth, self.h_clip, ep["pos"][:, T - 1], ep["heading"][:, T - 1], lazy=True)
+        batch = dict(self.nav)
+        batch.update(self.h_nav)          # host tensors: the model packs them into one pinned buffer = one H2D copy
+        out = self._forward(grid, batch)
         return out["fused_logits"].cpu()
 
     # ---- pipelined end-to-end: two environment batches per GPU share one model; while one batch's kernels run, the other
@@ -262,12 +299,10 @@ class Step:
     def e2e_compute(self):
         """enqueue the step's kernels + the async D2H of the result"""
         ep = self.ep
-        grid = self.builder.step(self.h_depth.numpy().view(np.uint16), None, ep["pos"][:, T - 1], ep["heading"][:, T - 1])
-        batch = dict(self.nav); batch["grid"] = grid
-        batch.update(grid_fts=None, grid_map=None, gridmap_pos_fts=None)
-        for k in self.host_keys:
-            batch[k] = self.h_nav[k].to(self.dev, non_blocking=True)
-        out = self.model("navigation", batch)
+        grid = self.builder.step(self.h_depth, None, ep["pos"][:, T - 1], ep["heading"][:, T - 1], lazy=True)
+        batch = dict(self.nav)
+        batch.update(self.h_nav)
+        out = self._forward(grid, batch)
         if not hasattr(self, "h_out"):
             self.h_out = torch.empty(out["fused_logits"].shape, dtype=torch.float32).pin_memory()
         self.h_out.copy_(out["fused_logits"], non_blocking=True)
@@ -280,9 +315,9 @@ class Step:
         return float(self.h_out[0, 0])
 
     def e2e_bytes(self):
-        h2d = self.h_depth.numel() * 2 + self.h_clip.numel() * 2 + B * 28 * 4
-        h2d += sum(v.numel() * v.element_size() for v in self.h_nav.values()) + B * (G * 4 + (1 + VIEWS) * 1)
-        return int(h2d), int(B * G * 4)
+        h2d = self.h_depth.numel() * self.h_depth.element_size() + self.h_clip.numel() * 2 + B * 28 * 4
+        h2d += sum(v.numel() * v.element_size() for v in self.h_nav.values()) + B * (G * 4 + (1 + VIEWS + OBJS) * 4)
+        return int(h2d), int(self.nav_np["gmap_masks"].shape[1] * B * 4 if not CE else B * max(self.cand) * 4)
 
 
 def timed(fn, steps, warmup, world):
@@ -350,18 +385,20 @@ def kernel_breakdown(step, n=5):
     return {k: (t / n, c / n) for k, (t, c) in agg.items()}
 
 
-def gemm_flops_per_step(kv_rows=None):
+def gemm_flops_per_step(kv_rows=None, map_rows=None):
     """Algorithmic FLOPs (2mnk) of every tcgen05 GEMM launch of one step (padded shapes as launched: S = 196 + G; the fusion
-    encoder's K/V projection over the `kv_rows` packed context rows it actually processes)."""
+    encoder's K/V projection over the `kv_rows` packed context rows it actually processes).  map_rows: count the map-sized GEMMs
+    over that many rows instead of B * S (the VALID rows of the map sequence: what the reference's result depends on)."""
     H, I = 768, 3072
-    S, Q, KC = 196 + G, G + 1 + VIEWS, 196 + G + L
+    S, Q, KC = 196 + G, G + 1 + VIEWS + OBJS, 196 + G + L
     mm = lambda m, n, k: 2.0 * m * n * k   # noqa: E731
-    f = mm(B * L, H, H) + mm(B * 196, H, H)                                            # text_proj, grid_proj
-    f += mm(B * S, 3 * H, H) + mm(B * S, H, H) + mm(B * S, I, H) + mm(B * S, H, I)      # grid_encoder
-    f += mm(B * L, 2 * H, H) + mm(B * S, H, H) * 2 + mm(B * S, 3 * H, H) + mm(B * S, H, H) + mm(B * S, I, H) + mm(B * S, H, I)
+    BS = B * S if map_rows is None else map_rows
+    f = mm(B * L, H, H) + mm(B * 196 if map_rows is None else max(map_rows - B * G, 0), H, H)      # text_proj, grid_proj
+    f += mm(BS, 3 * H, H) + mm(BS, H, H) + mm(BS, I, H) + mm(BS, H, I)                              # grid_encoder
+    f += mm(B * L, 2 * H, H) + mm(BS, H, H) * 2 + mm(BS, 3 * H, H) + mm(BS, H, H) + mm(BS, I, H) + mm(BS, H, I)
     f += mm(kv_rows if kv_rows is not None else B * KC, 8 * H, H)                        # fusion K/V of 4 layers
     f += 4 * (mm(B * Q, H, H) * 2 + mm(B * Q, 3 * H, H) + mm(B * Q, H, H) + mm(B * Q, I, H) + mm(B * Q, H, I))
-    f += mm(B * G, H, H) * 2 + mm(B * (1 + VIEWS), H, H) + mm(B, H, 2 * H)               # heads (algorithmic: the 3-term fp16 split
+    f += mm(B * G, H, H) * 2 + mm(B * (1 + VIEWS + OBJS), H, H) * (2 if OBJS else 1) + mm(B, H, 2 * H)   # heads (algorithmic: the 3-term fp16 split
     #                                                                                      and the 128-row padding are not counted)
     return f
 
@@ -373,7 +410,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="r2r", choices=sorted(WORKLOADS), help="BASELINE config; the headline is r2r")
+    ap.add_argument("--T", type=int, default=8, help="viewpoints accumulated per episode at the timed step (1, 8 or 15)")
+    ap.add_argument("--gpu-eager-baseline", action="store_true",
+                    help="also time the reference algorithm in stock torch eager on this GPU (oracle code on CUDA tensors)")
     args = ap.parse_args()
+    set_workload(args.workload, args.T)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -464,6 +506,9 @@ def main():
         kv_rows = int(step.model.buf("kv_off", (B + 1,), torch.int32)[B].item())      # packed context rows of this batch
         flops = gemm_flops_per_step(kv_rows)
         tf = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        S_ = 196 + G
+        valid_map_rows = int(step.model.buf("map_mask", (B, S_), torch.uint8).sum().item())
+        flops_valid = gemm_flops_per_step(kv_rows, map_rows=valid_map_rows)
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
@@ -473,7 +518,9 @@ def main():
                     "bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
                     "traffic": traffic.get("gemm_bytes_per_step"),
                     "peak_source": peak_src + ", sustained bf16/fp16 dense", "share_of_step": g_ms / total_k if total_k else None,
-                    "algorithmic_flops_per_step": flops, "ms": g_ms, "packed_context_rows": kv_rows}
+                    "algorithmic_flops_per_step": flops, "ms": g_ms, "packed_context_rows": kv_rows,
+                    "valid_map_rows": valid_map_rows, "padded_map_rows": B * S_,
+                    "frac_valid_rows": flops_valid / (g_ms * 1e-3) / 1e12 / tf_peak if g_ms > 0 else None}
         # the HBM-bound pooling kernel (north_star's "grid scatter/pool"): bytes that must move / its duration
         p_ms, _ = br.get("gridmm_pool", (0.0, 0))
         gridb = step.builder
@@ -489,7 +536,15 @@ def main():
             threads = os.cpu_count() or 1
             best, mean = cpu_reference_steps(step.ep, step.nav_np, step.cfg, _weights()[1], 2, threads)
             cpu = {"value": B / mean, "unit": "nav-steps/s", "cores": threads, "kind": "port",
-                   "sample": "2 steps of the same B=32, T=8 workload after 1 warm-up (oracle/ port of the reference algorithm)"}
+                   "sample": "2 steps of the same B=%d, T=%d workload after 1 warm-up (oracle/ port of the reference algorithm)" % (B, T)}
+        eager = None
+        if args.gpu_eager_baseline:
+            # SURVEY 2.1's own bar: the reference algorithm in stock torch 2.11 eager on the same B200 (per-cell Python loop,
+            # whole-map upload per step), outside the timed region of this repo's path
+            best, mean = cpu_reference_steps(step.ep, step.nav_np, step.cfg, _weights()[1], 3, os.cpu_count() or 1, device="cuda")
+            eager = {"value": B / mean, "unit": "nav-steps/s", "ms_per_step": mean * 1e3,
+                     "what": "oracle/ restatement of the reference forward on CUDA tensors, torch eager fp32 (TF32 off), grid build in "
+                             "numpy on the host as in the reference; 3 steps after 1 warm-up"}
         line = {"metric": METRIC, "value": value, "unit": "nav-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 operands / f32 accumulate (grid cell ids: f32 + int, bit-exact)", "data": "synthetic",
@@ -501,6 +556,7 @@ def main():
                         "serial_value": world * B * args.steps / (ms_e2e_serial * 1e-3),
                         "serial_ms_per_step": ms_e2e_serial / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_pool": roofline_pool, "cpu_baseline": cpu,
+                "gpu_eager_baseline": eager,
                 "kernel_ms_per_step": {k: round(t, 4) for k, (t, _) in sorted(br.items(), key=lambda kv: -kv[1][0])}}
         print(json.dumps(line))
     if world > 1:

@@ -33,8 +33,9 @@ _SIGS = {
     "gridmm_head_rows": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
     "gridmm_cls_heads_f16": [c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p],
-    "gridmm_nav_logits2": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 11 +
+    "gridmm_nav_logits2": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 +
                           [c_int, c_int, c_int, c_void_p],
+    "gridmm_copy_segments": [c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_linear_f16_lanes": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                           c_void_p, c_int, c_int, c_void_p],

@@ -63,7 +63,12 @@ struct Logit2Params {
     const uint8_t* gmap_masks; const uint8_t* gmap_visited;   // [B, G]
     const uint8_t* vp_nav_masks; const uint8_t* vp_obj_masks; // [B, V]
     const int* fuse_src;       // [B, G]  >=0: add local[src]; -2: add the back-track sum; -1: nothing
-    const uint8_t* bw_mask;    // [B, V]  candidates that are already visited (their local logits are summed)
+    const uint8_t* bw_mask;    // [B, V]  candidates that are already visited (their local logits are summed); unused with cand_node
+    // mask-free form of the same tables (the host then never has to read gmap_visited back from the device): fuse_src[b, g] is
+    // computed from the vpid strings alone (>= 0: LAST candidate slot holding node g's viewpoint, -2: none, -1: g is [stop] or
+    // padding) and only applies to nodes that are not visited; cand_node[b, v] = gmap slot of candidate v's viewpoint (-1: none,
+    // [stop], padding) -- a candidate is "already visited" when that node's gmap_visited flag is set (vilmodel.py:884-891)
+    const int* cand_node;      // [B, V] or null
     float* global_logits; float* grid_logits; float* local_logits; float* fused_logits; float* obj_logits;
     int G, V;
 };
@@ -120,13 +125,22 @@ __global__ void __launch_bounds__(128) nav_logits2_kernel(Logit2Params p) {
     __syncthreads();
     if (tid == 0) {
         float bw = 0.0f;   // sequential, candidate order (the reference accumulates with `+=` in a Python loop)
-        for (int v = 1; v < p.V; ++v)
-            if (p.bw_mask[b * p.V + v]) bw += s_local[v];
+        for (int v = 1; v < p.V; ++v) {
+            bool back;
+            if (p.cand_node) {
+                const int node = p.cand_node[b * p.V + v];
+                back = node >= 0 && p.gmap_visited[b * p.G + node] != 0;
+            } else {
+                back = p.bw_mask[b * p.V + v] != 0;
+            }
+            if (back) bw += s_local[v];
+        }
         s_bw = bw;
     }
     __syncthreads();
     for (int g = tid; g < p.G; g += blockDim.x) {
-        const bool masked = p.gmap_visited[b * p.G + g] || !p.gmap_masks[b * p.G + g];
+        const bool visited = p.gmap_visited[b * p.G + g] != 0;
+        const bool masked = visited || !p.gmap_masks[b * p.G + g];
         float gl = finish_head(p.part + static_cast<size_t>(p.row_global + b * p.G + g) * 36, 12, p.consts[0], p.consts[1]) * fw;
         float gr = finish_head(p.part + static_cast<size_t>(p.row_grid + b * p.G + g) * 36, 12, p.consts[4], p.consts[5]);
         if (masked) { gl = ninf; gr = ninf; }
@@ -135,7 +149,8 @@ __global__ void __launch_bounds__(128) nav_logits2_kernel(Logit2Params p) {
         float f = gl;
         if (g == 0) f += s_local[0];
         else {
-            const int src = p.fuse_src[b * p.G + g];
+            int src = p.fuse_src[b * p.G + g];
+            if (p.cand_node && visited) src = -1;           // `vp not in visited_nodes` (vilmodel.py:893)
             if (src >= 0) f += s_local[src];
             else if (src == -2) f += s_bw;
         }
@@ -172,16 +187,17 @@ extern "C" int gridmm_nav_logits2(const float* part, const float* fuse_raw, cons
                                   int row_fuse_g, int row_fuse_v, const float* consts, int row_global, int row_local,
                                   int row_grid, int row_obj, const unsigned char* gmap_masks, const unsigned char* gmap_visited,
                                   const unsigned char* vp_nav_masks, const unsigned char* vp_obj_masks, const int* fuse_src,
-                                  const unsigned char* bw_mask, float* global_logits, float* grid_logits, float* local_logits,
-                                  float* fused_logits, float* obj_logits, int batch, int G, int V, cudaStream_t stream) {
+                                  const unsigned char* bw_mask, const int* cand_node, float* global_logits, float* grid_logits,
+                                  float* local_logits, float* fused_logits, float* obj_logits, int batch, int G, int V,
+                                  cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0) return 0;
-    if (!part || !consts || !gmap_masks || !gmap_visited || !vp_nav_masks || !fuse_src || !bw_mask || !global_logits ||
+    if (!part || !consts || !gmap_masks || !gmap_visited || !vp_nav_masks || !fuse_src || (!bw_mask && !cand_node) || !global_logits ||
         !grid_logits || !local_logits || !fused_logits || (row_obj >= 0 && (!vp_obj_masks || !obj_logits)))
         return GRIDMM_ERR_ARG;
     if (fuse_raw && (!fuse_bias || !fuse_gw2)) return GRIDMM_ERR_ARG;
     Logit2Params p{part, fuse_raw, fuse_bias, fuse_gw2, row_fuse_g, row_fuse_v, consts, row_global, row_local, row_grid, row_obj, gmap_masks, gmap_visited, vp_nav_masks,
-                   vp_obj_masks, fuse_src, bw_mask, global_logits, grid_logits, local_logits, fused_logits, obj_logits, G, V};
+                   vp_obj_masks, fuse_src, bw_mask, cand_node, global_logits, grid_logits, local_logits, fused_logits, obj_logits, G, V};
     GMM_CUDA_CHECK(launch_pdl(nav_logits2_kernel, dim3(batch), dim3(128), V * sizeof(float), stream, p));
     gridmm_count_launch(1);
     return 0;

@@ -223,6 +223,39 @@ __global__ void __launch_bounds__(256) fusion_inputs_kernel(FusionInParams p) {
     pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
+// ------------------------------------------------------------------------------------------- batched copies
+// One launch that copies up to 24 independent byte ranges (device or pinned-host sources -> device destinations): the
+// per-step inputs of forward('navigation') arrive as ~14 freshly allocated tensors (r2r/agent.py:163-205) and have to land in
+// the static buffers a CUDA graph replays from; 14 cudaMemcpyAsync / copy kernels cost more host and device time than the data.
+constexpr int SEG_MAX = 24;
+struct CopySegs {
+    const uint8_t* src[SEG_MAX];
+    uint8_t* dst[SEG_MAX];
+    long long units[SEG_MAX + 1];      // exclusive prefix of ceil(bytes / 16)
+    long long bytes[SEG_MAX];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) copy_segments_kernel(CopySegs p) {
+    pdl_wait();
+    const long long total = p.units[p.n];
+    for (long long u = blockIdx.x * 256LL + threadIdx.x; u < total; u += static_cast<long long>(gridDim.x) * 256) {
+        int s = 0;
+        while (u >= p.units[s + 1]) ++s;
+        const long long off = (u - p.units[s]) * 16;
+        const uint8_t* src = p.src[s] + off;
+        uint8_t* dst = p.dst[s] + off;
+        const long long left = p.bytes[s] - off;
+        if (left >= 16 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+        } else {
+            const int nb = left < 16 ? static_cast<int>(left) : 16;
+            for (int i = 0; i < nb; ++i) dst[i] = src[i];
+        }
+    }
+    pdl_launch_dependents();
+}
+
 // ------------------------------------------------------------------------------------------- fp32 -> (hi, lo) fp16 split
 // out[b, r] = [ hi | lo | hi ] at column blocks 0, k_total, 2*k_total (each 768 wide at the given column offset), where
 // hi = fp16(x), lo = fp16(x - hi).  Against weights laid out [Wh | Wh | Wl] a single K-concatenated GEMM then computes
@@ -723,6 +756,36 @@ extern "C" int gridmm_ce_logits(const float* raw_global, const float* raw_local,
     if (!raw_global || !raw_local || !raw_fuse || !vp_nav_masks || !fused) return GRIDMM_ERR_ARG;
     GMM_CUDA_CHECK(launch_pdl(ce_logits_kernel, dim3(batch), dim3(128), 0, stream, raw_global, raw_local, raw_fuse, vp_nav_masks,
                               fused, G, V, maxc));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+// dst[i][0 .. nbytes[i]) = src[i][0 .. nbytes[i]) for i < n (n <= 24), one launch.  src / dst / nbytes are HOST arrays; the
+// pointers in them must be device-accessible (device memory, or pinned host memory for sources).
+extern "C" int gridmm_copy_segments(int n, const void* const* src, void* const* dst, const long long* nbytes, cudaStream_t stream) {
+    using namespace gmm;
+    if (n <= 0) return 0;
+    if (n > SEG_MAX || !src || !dst || !nbytes) return GRIDMM_ERR_ARG;
+    CopySegs p;
+    p.n = 0;
+    p.units[0] = 0;
+    for (int i = 0; i < n; ++i) {
+        if (nbytes[i] < 0 || (nbytes[i] > 0 && (!src[i] || !dst[i]))) return GRIDMM_ERR_ARG;
+        if (nbytes[i] == 0) continue;
+        const int k = p.n++;
+        p.src[k] = reinterpret_cast<const uint8_t*>(src[i]);
+        p.dst[k] = reinterpret_cast<uint8_t*>(dst[i]);
+        p.bytes[k] = nbytes[i];
+        p.units[k + 1] = p.units[k] + (nbytes[i] + 15) / 16;
+    }
+    if (p.n == 0) return 0;
+    for (int i = p.n; i < SEG_MAX; ++i) { p.src[i] = nullptr; p.dst[i] = nullptr; p.bytes[i] = 0; p.units[i + 1] = p.units[p.n]; }
+    const long long total = p.units[p.n];
+    long long blocks = (total + 255) / 256;
+    const int sms = gridmm_sm_count();
+    const long long cap = static_cast<long long>(sms > 0 ? sms : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    GMM_CUDA_CHECK(launch_pdl(copy_segments_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, p));
     gridmm_count_launch(1);
     return 0;
 }

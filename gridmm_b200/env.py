@@ -26,6 +26,7 @@ VIEW_TOKENS = 50     # CLS + 49 patches (env.py:100)
 _OFF7 = [-6 / 7, -4 / 7, -2 / 7, 0., 2 / 7, 4 / 7, 6 / 7]
 PATCH_CENTRES = np.array([9 + 18 * i for i in range(7)])          # env.py:279
 PATCH_CENTRES_CE = np.array([19 + 36 * i for i in range(7)])      # Policy_ViewSelection_GridMap.py (256x256 depth)
+_VIEW_ANGLES = np.arange(12, dtype=np.float64) * math.pi / 6        # (ix - 12) * pi / 6 of the 12 horizon views, env.py:290
 
 
 class Geometry:
@@ -91,17 +92,33 @@ class GridBatch:
         self.cap = b.cap
         self.perm, self.cell_start, self.cell_rank, self.n_nonempty = b.perm, b.cell_start, b.cell_rank, b.n_nonempty
         self.cell, self.pos_fts, self.half_len, self.n_pts = b.cell, b.pos_fts, b.half_len, b.n_pts
-        self.n_steps = b.n_steps
+        self.n_steps = b.n_steps.copy()
+        self._builder = b
+        self.pending = False      # True: gridmm_grid_update of this step has not been launched yet (step(lazy=True))
+
+    def launch_update(self):
+        """Launch the deferred gridmm_grid_update of a `step(lazy=True)` on the current stream (the model does this as the first
+        kernel of its forward, so that the launch is part of the captured CUDA graph of the step); no-op otherwise."""
+        if self.pending:
+            self.pending = False
+            self._builder._launch_update(None)
+
+    def update_signature(self):
+        """What a CUDA graph that contains this step's grid update depends on (static addresses / sizes)."""
+        b = self._builder
+        return (id(b), b.cap, b._d_pack.data_ptr(), b.wx.data_ptr(), b.cell.data_ptr(), b.bounds.data_ptr())
 
     # ---- views in the reference's formats (tests / drop-in consumers; these DO copy) ----
     def grid_map_numpy(self):
         """list of float64[N] with values in {-1, 0..n_cells-1} -- env.py:300-306,366-369."""
+        self.launch_update()
         n = self.n_pts.cpu().numpy()
         cell = self.cell.cpu().numpy()
         return [cell[i, :n[i]].astype(np.float64) for i in range(self.batch)]
 
     def grid_fts_torch(self):
         """list of fp16[N, D] device tensors in point order (env.py:299-304)."""
+        self.launch_update()
         out = []
         slab = self.slab.view(-1, 12, VIEW_TOKENS, self.feat_dim)
         slots = self.slots.view(self.batch, self.t_cap).cpu().numpy()
@@ -134,20 +151,26 @@ class GridMapBuilder:
         self.cell_rank = torch.zeros(B, nc, dtype=torch.int32, device=dev)
         self.n_nonempty = torch.zeros(B, dtype=torch.int32, device=dev)
         self.pos_fts = torch.zeros(B, nc, 5, dtype=torch.float32, device=dev)
-        # per-step staging (pinned host -> device)
-        self.h_depth_u16 = torch.empty(B, PTS, dtype=torch.int16).pin_memory()
-        self.h_depth_f32 = torch.empty(B, PTS, dtype=torch.float32).pin_memory()
-        self.h_pose = torch.empty(B, 4, dtype=torch.float32).pin_memory()
-        self.h_view = torch.empty(B, 24, dtype=torch.float32).pin_memory()         # view_cs[12*2]
+        # per-step staging: ONE packed buffer [pose B x 4 f32 | view_cs B x 24 f32 | depth B x 588 (u16 or f32)] per step, written
+        # by the host into a ring of pinned buffers (so the host never waits for the previous step's copy) and moved with one
+        # H2D copy into a static device pack that gridmm_grid_update reads
+        self._depth_elt = 4 if self.geom.depth_is_f32 else 2
+        self._off_view = B * 4 * 4
+        self._off_depth = self._off_view + B * 24 * 4
+        self._pack_bytes = self._off_depth + B * PTS * self._depth_elt
+        self._h_packs = [torch.empty(self._pack_bytes, dtype=torch.uint8).pin_memory() for _ in range(3)]
+        self._h_evts = [None, None, None]
+        self._h_next = 0
+        self._d_pack = torch.empty(self._pack_bytes, dtype=torch.uint8, device=dev)
+        self.d_pose = self._d_pack[:self._off_view].view(torch.float32).view(B, 4)
+        self.d_view = self._d_pack[self._off_view:self._off_depth].view(torch.float32).view(B, 24)
+        self.d_depth = self._d_pack[self._off_depth:].view(torch.float32 if self.geom.depth_is_f32 else torch.int16).view(B, PTS)
         self.h_clip = torch.empty(B, 12, VIEW_TOKENS, self.feat_dim, dtype=torch.float16).pin_memory()
-        self.d_depth_u16 = torch.empty(B, PTS, dtype=torch.int16, device=dev)
-        self.d_depth_f32 = torch.empty(B, PTS, dtype=torch.float32, device=dev)
-        self.d_pose = torch.empty(B, 4, dtype=torch.float32, device=dev)
-        self.d_view = torch.empty(B, 24, dtype=torch.float32, device=dev)
         self._copy_stream = None
         self._staged_evt = None
         self._staged_step = -1
-        self._h2d_evt = None          # last asynchronous copy out of the pinned staging buffers above
+        self._clip_evt = None         # last asynchronous copy out of h_clip
+        self._last_grid = None
         self.new_episodes()
 
     # ------------------------------------------------------------------ buffers
@@ -207,22 +230,27 @@ class GridMapBuilder:
             d = d[..., 12:24, :, :]
         return d[..., c[:, None], c[None, :]].reshape(d.shape[:-2] + (49,))
 
-    def host_pose(self, pos_xy, heading):
+    def host_pose(self, pos_xy, heading, out=None):
         """pose / view trigonometry, evaluated in double and rounded to fp32 like the reference
-        (python float x np.float32 array, env.py:119-120, 290, 337, 347-348)."""
+        (python float x np.float32 array, env.py:119-120, 290, 337, 347-348).  Returns [B, 28] fp32: px, py, cos, sin of the map
+        angle, then (cos, sin) of the 12 view angles; `out` = (pose [B,4], view [B,24]) fp32 arrays to fill instead."""
         B, g = self.batch, self.geom
         pos_xy = np.asarray(pos_xy, dtype=np.float64).reshape(B, 2)
         heading = np.asarray(heading, dtype=np.float64).reshape(B)
-        out = np.empty((B, 28), dtype=np.float32)
-        out[:, 0:2] = pos_xy.astype(np.float32)
+        if out is None:
+            full = np.empty((B, 28), dtype=np.float32)
+            pose, view = full[:, :4], full[:, 4:]
+        else:
+            full, (pose, view) = None, out
+        pose[:, 0:2] = pos_xy                      # float64 -> float32 rounding on assignment
         ang = -heading + g.angle_offset
-        out[:, 2] = np.cos(ang).astype(np.float32)
-        out[:, 3] = np.sin(ang).astype(np.float32)
-        v = np.arange(12, dtype=np.float64) * math.pi / 6
+        pose[:, 2] = np.cos(ang)
+        pose[:, 3] = np.sin(ang)
+        v = _VIEW_ANGLES
         va = v[None, :] - heading[:, None] if g.view_minus_heading else np.broadcast_to(v[None, :], (B, 12))
-        out[:, 4::2] = np.cos(va).astype(np.float32)
-        out[:, 5::2] = np.sin(va).astype(np.float32)
-        return out
+        view[:, 0::2] = np.cos(va)
+        view[:, 1::2] = np.sin(va)
+        return full
 
     def stage_features(self, clip, after=None):
         """Start the host->device copy of the NEXT viewpoint's CLIP tokens on this builder's copy stream and return at once.
@@ -233,6 +261,7 @@ class GridMapBuilder:
         may still read it -- never the case in a real episode, where every step writes a new slot)."""
         grew = False
         if self.n_calls + 1 > self.t_cap:
+            self._flush_pending()
             self._grow()
             grew = True
         t = self.n_calls
@@ -240,7 +269,7 @@ class GridMapBuilder:
             self._copy_stream = torch.cuda.Stream(device=self.device)
             grew = True
         if not (isinstance(clip, torch.Tensor) and clip.is_pinned()):
-            self._pinned_free()
+            self._clip_free()
             self.h_clip.copy_(torch.as_tensor(clip).reshape(self.h_clip.shape))
             clip = self.h_clip
         cs = self._copy_stream
@@ -252,33 +281,51 @@ class GridMapBuilder:
             self.slab[t].copy_(clip.reshape(self.batch, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
             self._staged_evt = torch.cuda.Event()
             self._staged_evt.record(cs)
+        if clip is self.h_clip:
+            self._clip_evt = self._staged_evt
         self._staged_step = t
 
-    def _pinned_free(self, clip_too=True):
-        """The pinned staging buffers are reused every step: before the host rewrites them, the asynchronous copies that read
-        them last step must have run (they have, unless the caller queued steps faster than the GPU drains them).
-        clip_too: also the last staged feature copy, which may have read h_clip."""
-        for evt in (self._h2d_evt, self._staged_evt if clip_too else None):
-            if evt is not None:
-                evt.synchronize()
+    def _clip_free(self):
+        """h_clip (the pinned bounce buffer for pageable feature arrays) is reused every step: the asynchronous copy that read it
+        last must have run before the host rewrites it."""
+        if self._clip_evt is not None:
+            self._clip_evt.synchronize()
+            self._clip_evt = None
 
-    def step(self, depth_sub, clip, pos_xy, heading, active=None):
+    def _flush_pending(self):
+        """A step(lazy=True) whose grid update nobody launched yet must run before its inputs are overwritten."""
+        g = self._last_grid
+        if g is not None and g.pending:
+            g.launch_update()
+
+    def _launch_update(self, d_active):
+        g = self.geom
+        ops.grid_update(self.batch, self.d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, d_active, g.off7, g.flip_y,
+                        g.negate_map_x, g.pos_mode, g.max_dist, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
+                        self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
+
+    def step(self, depth_sub, clip, pos_xy, heading, active=None, lazy=False):
         """Append one viewpoint per episode and rebuild the grid assignment (getStates' grid half, env.py:392-398).
 
         depth_sub : [B,12,49] uint16 (0.25 mm) or float32 metres (CE); numpy (host) or a device tensor
         clip      : [B,12,50,D] fp16 CLIP tokens incl. CLS; numpy / host tensor (copied H2D) or a device tensor; None when the
                     copy was started earlier with stage_features()
         pos_xy    : [B,2] viewpoint x,y (python floats / float64);  heading : [B] radians
+        active    : optional [B] bools; episodes with 0 receive no viewpoint in this call
+        lazy      : stage the inputs now but leave the launch of gridmm_grid_update to the consumer of the returned GridBatch
+                    (forward('navigation') launches it as its first kernel, inside its CUDA graph when graphs are enabled)
         Returns a GridBatch.
         """
         B, g = self.batch, self.geom
+        self._flush_pending()
         if self.n_calls + 1 > self.t_cap:
             self._grow()
         t = self.n_calls                  # slab row block of this call (all B viewpoints, active or not, land in slab[t])
         d_active = None
         if active is not None and not bool(np.all(active)):
             # Episodes with active[b] == 0 receive no viewpoint (the kernel leaves their points / bounds alone and only re-assigns
-            # cells); the others append theirs as viewpoint n_steps[b], which lives in slab row block t = this call's index.
+            # cells to the window of the pose passed for them); the others append theirs as viewpoint n_steps[b], which lives in
+            # slab row block t = this call's index.
             # (The reference itself never skips: it re-adds the last viewpoint of ended episodes, r2r/env.py:392-398.)
             act = np.asarray(active).astype(bool).reshape(B)
             self._lockstep = False
@@ -290,7 +337,6 @@ class GridMapBuilder:
             idx = torch.arange(B)
             self._slots_host[idx, torch.from_numpy(self.n_steps)] = (t * B + idx).to(torch.int32)
             self.slots.copy_(self._slots_host, non_blocking=False)
-        self._pinned_free(clip_too=clip is not None)      # a staged copy of THIS step is waited for on the device, below
         # features: one contiguous copy into slab[t]
         if clip is None:
             if self._staged_step != t or self._staged_evt is None:
@@ -300,33 +346,45 @@ class GridMapBuilder:
         elif isinstance(clip, torch.Tensor) and (clip.is_cuda or clip.is_pinned()):
             self.slab[t].copy_(clip.reshape(B, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
         else:
+            self._clip_free()
             self.h_clip.copy_(torch.as_tensor(clip).reshape(self.h_clip.shape))
             self.slab[t].copy_(self.h_clip.view(B, 12 * VIEW_TOKENS, self.feat_dim), non_blocking=True)
-        # depth
-        if isinstance(depth_sub, torch.Tensor) and depth_sub.is_cuda:
-            d_depth = depth_sub.reshape(B, PTS).contiguous()
-        elif g.depth_is_f32:
-            self.h_depth_f32.copy_(torch.as_tensor(np.ascontiguousarray(depth_sub, dtype=np.float32)).reshape(B, PTS))
-            self.d_depth_f32.copy_(self.h_depth_f32, non_blocking=True)
-            d_depth = self.d_depth_f32
+            self._clip_evt = torch.cuda.Event()
+            self._clip_evt.record()
+        # pose, view trigonometry and depth: one packed pinned buffer (ring of three), one H2D copy
+        k = self._h_next
+        self._h_next = (k + 1) % len(self._h_packs)
+        if self._h_evts[k] is not None:
+            self._h_evts[k].synchronize()             # three steps old: long done unless the host runs that far ahead
+        hp = self._h_packs[k]
+        hp_np = hp.numpy()
+        pose = hp_np[:self._off_view].view(np.float32).reshape(B, 4)
+        view = hp_np[self._off_view:self._off_depth].view(np.float32).reshape(B, 24)
+        self.host_pose(pos_xy, heading, out=(pose, view))
+        depth_on_device = isinstance(depth_sub, torch.Tensor) and depth_sub.is_cuda
+        if depth_on_device:
+            n_h2d = self._off_depth
         else:
-            arr = np.ascontiguousarray(depth_sub).astype(np.uint16, copy=False).reshape(B, PTS)
-            self.h_depth_u16.copy_(torch.from_numpy(arr.view(np.int16)))
-            self.d_depth_u16.copy_(self.h_depth_u16, non_blocking=True)
-            d_depth = self.d_depth_u16
-        hp = self.host_pose(pos_xy, heading)
-        self.h_pose.copy_(torch.from_numpy(hp[:, :4]))
-        self.h_view.copy_(torch.from_numpy(hp[:, 4:]))
-        self.d_pose.copy_(self.h_pose, non_blocking=True)
-        self.d_view.copy_(self.h_view, non_blocking=True)
-        self._h2d_evt = torch.cuda.Event()
-        self._h2d_evt.record()
-        ops.grid_update(B, d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, d_active, g.off7, g.flip_y,
-                        g.negate_map_x, g.pos_mode, g.max_dist, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
-                        self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
+            n_h2d = self._pack_bytes
+            dst = hp_np[self._off_depth:].view(np.float32 if g.depth_is_f32 else np.uint16).reshape(B, PTS)
+            src = depth_sub.numpy() if isinstance(depth_sub, torch.Tensor) else np.asarray(depth_sub)
+            dst[...] = src.reshape(B, PTS).view(np.uint16) if (not g.depth_is_f32 and src.dtype == np.int16) else src.reshape(B, PTS)
+        self._d_pack[:n_h2d].copy_(hp[:n_h2d], non_blocking=True)
+        evt = torch.cuda.Event()
+        evt.record()
+        self._h_evts[k] = evt
+        if depth_on_device:
+            dd = depth_sub.reshape(B, PTS)
+            self.d_depth.copy_(dd.view(torch.int16) if (not g.depth_is_f32 and dd.dtype == torch.uint16) else dd, non_blocking=True)
         self.n_steps += 1 if d_active is None else np.asarray(active).astype(np.int64).reshape(B)
         self.n_calls += 1
-        return GridBatch(self)
+        grid = GridBatch(self)
+        if lazy and d_active is None:
+            grid.pending = True
+        else:
+            self._launch_update(d_active)
+        self._last_grid = grid
+        return grid
 
     def run_trajectory(self, depth_sub, clip, pos_xy, heading):
         """Whole ground-truth paths at once, as the pretraining dataset builds them (`get_traj_pano_fts`,

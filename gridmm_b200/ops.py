@@ -213,11 +213,12 @@ def cls_heads(a16, w16, groups, tiles_m, bias, gw2, grp, part, raw):
 
 def nav_logits2(part, fuse_raw, fuse_bias, fuse_gw2, row_fuse_g, row_fuse_v, consts, row_global, row_local, row_grid, row_obj,
                 gmap_masks, gmap_visited, vp_nav_masks, vp_obj_masks, fuse_src, bw_mask, global_logits, grid_logits, local_logits,
-                fused_logits, obj_logits, batch, G, V):
+                fused_logits, obj_logits, batch, G, V, cand_node=None):
     for t, n in ((gmap_masks, "gmap_masks"), (gmap_visited, "gmap_visited"), (vp_nav_masks, "vp_nav_masks"),
                  (vp_obj_masks, "vp_obj_masks"), (bw_mask, "bw_mask")):
         _chk(t, torch.uint8, n)
     _chk(fuse_src, torch.int32, "fuse_src"); _chk(part, torch.float32, "part"); _chk(consts, torch.float32, "consts")
+    _chk(cand_node, torch.int32, "cand_node")
     _lib.call("gridmm_nav_logits2", part.data_ptr(), _lib.ptr(fuse_raw), _lib.ptr(fuse_bias), _lib.ptr(fuse_gw2), row_fuse_g, row_fuse_v,
               consts.data_ptr(), row_global, row_local, row_grid, row_obj,
               gmap_masks.data_ptr(), gmap_visited.data_ptr(), vp_nav_masks.data_ptr(), _lib.ptr(vp_obj_masks), fuse_src.data_ptr(),
@@ -298,3 +299,23 @@ def cell_sort(batch, cell, n_pts, grid_w, cap, perm, cell_start, cell_rank, n_no
     _chk(cell, torch.int16, "cell"); _chk(n_pts, torch.int32, "n_pts")
     _lib.call("gridmm_cell_sort", batch, cell.data_ptr(), n_pts.data_ptr(), grid_w, cap, perm.data_ptr(), cell_start.data_ptr(),
               cell_rank.data_ptr(), n_nonempty.data_ptr(), _lib.stream_ptr())
+
+
+def copy_segments(pairs):
+    """pairs: list of (src, dst) tensors with equal byte counts (src: CUDA or pinned host, contiguous; dst: CUDA, contiguous).
+    One kernel launch for all of them."""
+    import ctypes
+    pairs = [(s_, d_) for s_, d_ in pairs if d_.numel() > 0]
+    for i0 in range(0, len(pairs), 24):
+        chunk = pairs[i0:i0 + 24]
+        n = len(chunk)
+        for s_, d_ in chunk:
+            if not d_.is_cuda or not (s_.is_cuda or s_.is_pinned()):
+                raise _lib.GridmmError("copy_segments: destinations must be CUDA tensors, sources CUDA or pinned host tensors")
+            if not (s_.is_contiguous() and d_.is_contiguous()) or s_.numel() * s_.element_size() != d_.numel() * d_.element_size():
+                raise _lib.GridmmError("copy_segments: contiguous tensors of equal byte size expected")
+        src = (ctypes.c_void_p * n)(*[s_.data_ptr() for s_, _ in chunk])
+        dst = (ctypes.c_void_p * n)(*[d_.data_ptr() for _, d_ in chunk])
+        nb = (ctypes.c_longlong * n)(*[d_.numel() * d_.element_size() for _, d_ in chunk])
+        cast = lambda a: ctypes.cast(a, ctypes.c_void_p)                   # noqa: E731
+        _lib.call("gridmm_copy_segments", n, cast(src), cast(dst), cast(nb), _lib.stream_ptr())

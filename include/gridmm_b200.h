@@ -165,9 +165,18 @@ int gridmm_cls_heads_f16(const void* a, int lda, long long a_rows, const void* w
 int gridmm_nav_logits2(const float* part, const float* fuse_raw, const float* fuse_bias, const float* fuse_gw2, int row_fuse_g,
                        int row_fuse_v, const float* consts, int row_global, int row_local, int row_grid, int row_obj,
                        const unsigned char* gmap_masks, const unsigned char* gmap_visited, const unsigned char* vp_nav_masks,
-                       const unsigned char* vp_obj_masks, const int* fuse_src, const unsigned char* bw_mask, float* global_logits,
-                       float* grid_logits, float* local_logits, float* fused_logits, float* obj_logits, int batch, int G, int V,
-                       cudaStream_t stream);
+                       const unsigned char* vp_obj_masks, const int* fuse_src, const unsigned char* bw_mask, const int* cand_node,
+                       float* global_logits, float* grid_logits, float* local_logits, float* fused_logits, float* obj_logits,
+                       int batch, int G, int V, cudaStream_t stream);
+/* cand_node != NULL selects the mask-free form of the vpid tables of vilmodel.py:881-899 (built from the vpid strings alone, so
+ * the host never reads gmap_visited back): fuse_src[b,g] = last candidate slot holding node g's viewpoint (-2 none, -1 [stop] /
+ * padding), applied only to unvisited nodes; cand_node[b,v] = gmap slot of candidate v's viewpoint (-1 none): candidate v
+ * counts as "already visited" when gmap_visited[b, cand_node[b,v]] is set.  bw_mask is then unused (may be NULL). */
+
+/* dst[i][0 .. nbytes[i]) = src[i][0 .. nbytes[i]) for i < n <= 24 in ONE launch (src / dst / nbytes: host arrays of device-
+ * accessible pointers; sources may be pinned host memory).  Lands the ~14 per-step input tensors of forward('navigation')
+ * (r2r/agent.py:163-205) in the static buffers the captured graph reads. */
+int gridmm_copy_segments(int n, const void* const* src, void* const* dst, const long long* nbytes, cudaStream_t stream);
 
 /* text_proj (vilmodel.py:702, 793-795) written straight into gridmm_pool's lane-major operand layout:
  * out_lanes[t / 128][b][u][t % 128] (16-byte units, 128 slots per unit row) = (a[b*rows_per_b + t, :] . w^T + bias)[8u .. 8u+7];

@@ -70,6 +70,25 @@ def test_fuse_index_equals_reference_loops():
                 elif src[i, j] == -2:
                     got[i, j] += s
         assert torch.equal(got, ref)
+        # the mask-free tables the product passes to gridmm_nav_logits2 (no D2H read of the visited mask) + the kernel's rule
+        # (heads.cu: a candidate is "already visited" when its node's flag is set; node_src only applies to unvisited nodes)
+        src2, bw2 = _fuse_index_from_maps(nav["gmap_vpids"], nav["gmap_visited_masks"].numpy(), nav["vp_cand_vpids"], G, V)
+        assert np.array_equal(src2, src) and np.array_equal(bw2, bw)
+
+
+def _fuse_index_from_maps(gmap_vpids, vis, vp_cand_vpids, G, V):
+    """numpy restatement of what nav_logits2_kernel derives from build_fuse_maps' tables and the device-side visited flags."""
+    from gridmm_b200.model import build_fuse_maps
+    node_src, cand_node = build_fuse_maps(gmap_vpids, vp_cand_vpids, G, V)
+    B = len(gmap_vpids)
+    fuse_src = np.full((B, G), -1, np.int32)
+    bw = np.zeros((B, V), np.uint8)
+    for i in range(B):
+        for v in range(1, V):
+            bw[i, v] = 1 if (cand_node[i, v] >= 0 and vis[i, cand_node[i, v]]) else 0
+        for j in range(1, G):
+            fuse_src[i, j] = -1 if vis[i, j] else node_src[i, j]
+    return fuse_src, bw
 
 
 def test_host_pose_rounding_contract():
@@ -230,7 +249,10 @@ def test_pretrain_sap_heads_glue_masks_and_candidates(monkeypatch):
     assert torch.equal(staged["in_gmap_visited"].bool(), batch["gmap_visited_masks"])
     cands = [[None] + list(c[-1]) for c in batch["traj_cand_vpids"]]
     src, bw = build_fuse_index(batch["gmap_vpids"], batch["gmap_visited_masks"], cands, G, V)
-    assert np.array_equal(staged["in_fuse_src"].numpy(), src) and np.array_equal(staged["in_bw_mask"].numpy(), bw)
+    vis = batch["gmap_visited_masks"].numpy()
+    node_src, cand_node = staged["in_fuse_src"].numpy(), staged["in_cand_node"].numpy()
+    assert np.array_equal(np.where(vis, -1, node_src), src)
+    assert np.array_equal((cand_node >= 0) & np.take_along_axis(vis, np.maximum(cand_node, 0), 1), bw.astype(bool))
     with pytest.raises(ValueError):
         GlocalTextPathNavCMT(H.make_config(pretrain_trunk=True, use_lang2visn_attn=True, **case["model"])).forward_pretrain(
             batch, task="sap", heads=True)

@@ -14,9 +14,10 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 LOGIT_TOL = 1e-3
-EMBED_TOL = 2e-2          # 768-d hidden states with |x| up to ~6 after LayerNorm
-MAP_TOL = 5e-2            # grid-cell tokens: the per-cell softmax over relevance (|w| ~ 40 with these weights) is nearly an
-                          # arg-max, so the fp16 rounding of text_fts can move a few cell vectors by ~1e-2 (numerics)
+EMBED_TOL = 4e-3          # 768-d hidden states with |x| up to ~6 after LayerNorm: measured <= 2.1e-3 over all cases below
+MAP_TOL = 3e-2            # grid-cell tokens after both map encoders: measured 0.7-2.3e-2.  The per-cell softmax over relevance
+                          # (|w| ~ 40 with these weights) is nearly an arg-max, so the fp16 rounding of text_fts moves a few
+                          # cell vectors by ~1e-2 (numerics); the logits, which are what is specified, stay < 1e-3
 LOGITS = ("global_logits", "local_logits", "fused_logits", "grid_logits", "obj_logits")
 
 
@@ -210,7 +211,7 @@ def test_pretrain_trunk_matches_reference_golden():
     valid_t = torch.arange(ref.shape[1])[None, :] < batch["txt_lens"][:, None]
     errs["mlm_txt_embeds"] = (txt.float().cpu() - ref).abs()[valid_t].max().item()
     print("pretrain trunk errors", errs)
-    assert max(errs.values()) <= 1e-2, errs
+    assert max(errs.values()) <= 4e-3, errs        # measured 2.0e-3 (the reference pools in fp16 here)
 
 
 def test_cuda_graph_replay_matches_eager():
@@ -461,8 +462,12 @@ def test_partial_active_masks_vs_oracle():
     gb = GridMapBuilder(B, max_steps=2)                 # also exercises growth with a rewritten slot table
     states = [go.GridState() for _ in range(B)]
     last = [None] * B
+    pos, heading = ep["pos"][:, 0].copy(), ep["heading"][:, 0].copy()
     for t in range(T):
-        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t], active=active[t])
+        # an episode that receives no viewpoint stays where it is: its points are re-assigned to the same window
+        pos[active[t]] = ep["pos"][active[t], t]
+        heading[active[t]] = ep["heading"][active[t], t]
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], pos, heading, active=active[t])
         got = grid.grid_map_numpy()
         fts = grid.grid_fts_torch()
         for b in range(B):
@@ -488,13 +493,12 @@ def test_partial_active_masks_vs_oracle():
 
 
 def test_trained_scale_activations():
-    """The parity cases above use N(0, 0.02) weights (|activations| <= ~6).  Trained checkpoints have much larger projections; the
-    fp16 operands of the next GEMM must neither overflow nor lose the result.  Here the Q/K/V, FFN1 and text/grid projection
-    weights are scaled so that |QKV| reaches ~50-100 and |FFN1| several hundred (LayerNorm keeps the residual stream bounded,
-    as in a trained model), and the forward must stay finite and within a RELATIVE tolerance of the fp32 oracle: fp16 has
-    11 bits, so errors scale with the activation magnitude (2e-2 of the largest hidden activation; logits: 2e-2 absolute here,
-    against 1e-3 at the N(0, 0.02) scale).  A second run with weights large enough to exceed 65504 in FFN1 checks that the
-    saturating fp16 stores (gemm_tc.cu sat_f16) keep every output finite instead of inf -> NaN."""
+    """The parity cases above use N(0, 0.02) weights (|activations| <= ~6).  Trained BERT-style checkpoints have outlier channels:
+    a few LayerNorm gains / biases put |x| ~ 50-200 into the QKV / FFN1 GEMMs, value and FFN1 projections are several times
+    larger.  The fp16 operands of the next GEMM must neither overflow nor lose the result: here 4 channels of every LayerNorm get
+    gain x30 and bias +-10, value weights x6, FFN1 weights x10; the forward must stay finite and within a RELATIVE tolerance of
+    the fp32 oracle (fp16 has 11 bits: errors scale with the activation magnitude).  A second run with FFN1 weights large enough
+    to exceed 65504 checks that the saturating fp16 stores (gemm_tc.cu sat_f16) keep every output finite instead of inf -> NaN."""
     B, T, L, G = 4, 3, 48, 12
     ep_kw = dict(batch=B, steps=T, seed=4242)
     nav_kw = dict(txt_len=L, gmap_len=G, n_views=36, n_objs=0)
@@ -503,32 +507,41 @@ def test_trained_scale_activations():
     cells, fts, _, pos = H.oracle_grid(ep)
     nav = H.nav_batch(ep_kw, nav_kw, cells, fts, pos)
 
-    def scaled(qkv, ffn1):
+    def scaled(value, ffn1):
         w = H.make_weights(cfg, 4242)
         for k in list(w):
-            if k.endswith("weight") and (".query." in k or ".key." in k or ".value." in k or "in_proj_weight" in k):
-                w[k] = (w[k] * qkv).astype(np.float32)
+            if "LayerNorm.weight" in k or ".norm1.weight" in k or ".norm2.weight" in k or k.endswith(".norm.weight"):
+                w[k] = w[k].copy(); w[k][[5, 77, 301, 640]] *= 30.0
+            elif "LayerNorm.bias" in k or ".norm1.bias" in k or ".norm2.bias" in k or k.endswith(".norm.bias"):
+                w[k] = w[k].copy(); w[k][[5, 301]] += 10.0; w[k][[77, 640]] -= 10.0
+            elif k.endswith("weight") and ".value." in k:
+                w[k] = (w[k] * value).astype(np.float32)
             elif k.endswith("weight") and (".visn_inter." in k or ".linear1." in k):
                 w[k] = (w[k] * ffn1).astype(np.float32)
         return w
 
     from gridmm_b200.model import GlocalTextPathNavCMT
-    w = scaled(12.0, 20.0)
+    w = scaled(6.0, 10.0)
     model = GlocalTextPathNavCMT(cfg)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
     model = model.cuda().eval()
     ref = _oracle_nav(cfg, w, nav)
     out = model("navigation", _to_cuda(nav), return_intermediates=True)
     torch.cuda.synchronize()
+    rels = {}
     for k in ("gmap_embeds", "vp_embeds"):
         a, r = out[k].float().cpu(), ref[k]
         assert torch.isfinite(a).all()
-        rel = (a - r).abs().max().item() / max(r.abs().max().item(), 1.0)
-        assert rel < 2e-2, (k, rel)
-    errs = {k: H.finite_close(out[k], ref[k], atol=2e-2) for k in ("global_logits", "local_logits", "fused_logits", "grid_logits")}
-    print("trained-scale errors", errs)
+        rels[k] = ((a - r).abs().max().item(), r.abs().max().item())
+    errs = {k: H.finite_close(out[k], ref[k], atol=1.0) for k in ("global_logits", "local_logits", "fused_logits", "grid_logits")}
+    mags = {k: ref[k][torch.isfinite(ref[k])].abs().max().item() for k in errs}
+    print("trained-scale errors: hidden (abs err, max |x|)", rels, "logits", errs, "logit magnitudes", mags)
+    for k, (e, m) in rels.items():
+        assert e / max(m, 1.0) < 1e-2, (k, e, m)
+    for k in errs:
+        assert errs[k] < 1e-2 * max(mags[k], 1.0), (k, errs[k], mags[k])
     # overflow guard: FFN1 pre-activations far beyond the fp16 range
-    w = scaled(12.0, 40000.0)
+    w = scaled(6.0, 40000.0)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
     out = model("navigation", _to_cuda(nav))
     torch.cuda.synchronize()
@@ -536,3 +549,48 @@ def test_trained_scale_activations():
         a = out[k].float().cpu()
         assert not torch.isnan(a).any(), k
         assert torch.isfinite(a[torch.isfinite(ref[k])]).all(), k
+
+
+def test_lazy_grid_update_inside_the_step_graph_and_host_inputs():
+    """The serving path of bench.py: GridMapBuilder.step(lazy=True) leaves the launch of gridmm_grid_update to
+    forward('navigation'), which records it as the first node of the step's CUDA graph (parallel to the text branch on a side
+    stream); per-step inputs may be HOST tensors (one pinned pack, one H2D, one gridmm_copy_segments launch).  Every step must
+    give bitwise the results of the plain path (eager update, eager forward, CUDA inputs), the viewpoint must be appended
+    exactly once per step (also on the step that captures the graph), and cell ids stay bit-exact."""
+    from gridmm_b200.env import GridMapBuilder
+    B, T, L, G = 6, 5, 40, 12
+    cfg = H.make_config()
+    plain, _ = _model(cfg, 9)
+    served, _ = _model(cfg, 9)
+    served.enable_cuda_graph(True)
+    ep = synth.make_episodes(B, T, seed=9)
+    cells, _, _, _ = H.oracle_grid(ep)
+    nav_cpu = synth.to_torch(synth.make_nav_inputs(B, seed=9, txt_len=L, gmap_len=G))
+    nav = _to_cuda(nav_cpu)
+    host_keys = ("gmap_step_ids", "gmap_pos_fts", "gmap_masks", "gmap_visited_masks", "vp_pos_fts", "vp_masks", "vp_nav_masks")
+    gb_a, gb_b = GridMapBuilder(B, max_steps=2), GridMapBuilder(B, max_steps=2)      # max_steps=2: the buffers grow twice on the way
+    for t in range(T):
+        ga = gb_a.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+        ba = dict(nav); ba.update(grid=ga, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        want = {k: v.clone() for k, v in plain("navigation", ba).items() if v is not None}
+        g2 = gb_b.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t], lazy=True)
+        assert g2.pending
+        bb = dict(nav); bb.update(grid=g2, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        for k in host_keys:
+            bb[k] = nav_cpu[k]                        # host tensors (pageable): packed + one H2D inside the model
+        got = served("navigation", bb)
+        torch.cuda.synchronize()
+        assert not g2.pending
+        for k in LOGITS[:4] + ("gmap_embeds", "vp_embeds"):
+            assert torch.equal(got[k], want[k]), "step %d: %s" % (t, k)
+        assert torch.equal(gb_a.n_pts, gb_b.n_pts) and int(gb_b.n_pts[0]) == 588 * (t + 1)
+        got_cells = g2.grid_map_numpy()
+        for b in range(B):
+            assert np.array_equal(got_cells[b].astype(np.int32), cells[b][t])
+    # a lazy step nobody consumed is flushed by the next step() (its inputs would otherwise be overwritten)
+    gb_c = GridMapBuilder(B, max_steps=4)
+    for t in range(3):
+        gc = gb_c.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t], lazy=True)
+    got_cells = gc.grid_map_numpy()
+    for b in range(B):
+        assert np.array_equal(got_cells[b].astype(np.int32), cells[b][2])
