@@ -222,7 +222,7 @@ def nav_logits2(part, fuse_raw, fuse_bias, fuse_gw2, row_fuse_g, row_fuse_v, con
     _lib.call("gridmm_nav_logits2", part.data_ptr(), _lib.ptr(fuse_raw), _lib.ptr(fuse_bias), _lib.ptr(fuse_gw2), row_fuse_g, row_fuse_v,
               consts.data_ptr(), row_global, row_local, row_grid, row_obj,
               gmap_masks.data_ptr(), gmap_visited.data_ptr(), vp_nav_masks.data_ptr(), _lib.ptr(vp_obj_masks), fuse_src.data_ptr(),
-              bw_mask.data_ptr(), global_logits.data_ptr(), grid_logits.data_ptr(), local_logits.data_ptr(),
+              _lib.ptr(bw_mask), _lib.ptr(cand_node), global_logits.data_ptr(), grid_logits.data_ptr(), local_logits.data_ptr(),
               fused_logits.data_ptr(), _lib.ptr(obj_logits), batch, G, V, _lib.stream_ptr())
 
 

@@ -346,3 +346,29 @@ def test_subsample_depth_reads_the_reference_pixels():
     want = np.stack([[ce[b, v][c[:, None], c[None, :]].reshape(49) for v in range(12)] for b in range(2)])
     assert np.array_equal(GridMapBuilder.subsample_depth(ce, ce=True), want)
     assert np.array_equal(GridMapBuilder.subsample_depth(synth.expand_depth(want[0].astype(np.uint16))), want[0].astype(np.uint16))
+
+
+def test_wrappers_and_ctypes_table_agree_with_the_header():
+    """Three statements of every entry point must agree without a GPU: the prototype in include/gridmm_b200.h, the ctypes
+    signature table (_lib._SIGS) and the number of arguments the tensor-level wrapper in ops.py passes."""
+    import ast
+    import re
+    from gridmm_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "gridmm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\bint\s+(gridmm_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S))
+    for name, sig in _lib._SIGS.items():
+        assert name in protos, name
+        n_hdr = len([a for a in protos[name].split(",") if a.strip() and a.strip() != "void"])
+        assert n_hdr == len(sig), "%s: header has %d parameters, ctypes table %d" % (name, n_hdr, len(sig))
+    tree = ast.parse(open(os.path.join(root, "gridmm_b200", "ops.py")).read())
+    seen = set()
+    for node in ast.walk(tree):
+        if (isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr == "call" and node.args
+                and isinstance(node.args[0], ast.Constant)):
+            name = node.args[0].value
+            seen.add(name)
+            assert len(node.args) - 1 == len(_lib._SIGS[name]), "%s: ops.py passes %d arguments, ctypes table has %d" % (
+                name, len(node.args) - 1, len(_lib._SIGS[name]))
+    assert seen == set(_lib._SIGS), set(_lib._SIGS) ^ seen

@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2, run B: GPU suite after the host-path rework, host enqueue time, bench lines for every workload
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread -p no:cacheprovider -s > gpurun_out/r2b_tests.log 2>&1; echo "gpu tests exit=$?"
+grep -E "passed|failed" gpurun_out/r2b_tests.log | tail -3
+grep -E "^(FAILED|ERROR)|^E  " gpurun_out/r2b_tests.log | head -40
+grep -E "trained-scale" gpurun_out/r2b_tests.log | cut -c1-900
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2b_smoke.log 2>&1; echo "smoke exit=$?"; tail -1 gpurun_out/r2b_smoke.log
+timeout 600 python bench.py --steps 200 --warmup 5 --no-cpu-baseline > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; echo "bench exit=$?"; tail -3 gpurun_out/r2b_bench.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/r2b_bench.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, 'e2e', d['e2e']['value'], 'serial', d['e2e']['serial_value'], d['e2e']['serial_ms_per_step'])
+print('gemm', d['roofline']['achieved'], d['roofline']['frac'], d['roofline'].get('frac_valid_rows'), 'pool', d['roofline_pool']['achieved'], d['roofline_pool']['frac']); print(d['kernel_ms_per_step'])
+PY
+timeout 300 python tools/host_time.py > gpurun_out/r2b_host_time.txt 2>&1; head -3 gpurun_out/r2b_host_time.txt
+for w in "reverie 8" "ce 8" "r2r 1" "r2r 15"; do set -- $w; timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --workload $1 --T $2 > gpurun_out/r2b_bench_$1_T$2.json 2> gpurun_out/r2b_bench_$1_T$2.err; echo "bench $1 T=$2 exit=$?"; python -c "
+import json,sys
+d=json.loads(open('gpurun_out/r2b_bench_$1_T$2.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['serial_value'])"; done

@@ -1,5 +1,9 @@
-"""Host-side time of one resident step (enqueue only) vs device time: is the loop host-bound?"""
-import os, sys, time
+"""Host-side cost of one step (enqueue only) next to the device time of the same step: is the loop host-bound?
+
+Every step is timed on the host from call to return with the GPU IDLE at the start (a synchronize before each call), so no launch
+ever blocks on a full queue or on the pinned-buffer ring: the number is the pure host cost of GridMapBuilder.step(lazy=True) +
+forward('navigation') (input staging, vpid tables, one graph launch).  The device time is the graph-replay loop of bench.py."""
+import os, sys, time, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from bench import Step
@@ -8,18 +12,32 @@ step = Step(dev, seed=0)
 for _ in range(5):
     step.run_resident()
 torch.cuda.synchronize()
-import cProfile, pstats
+
+
+def host_cost(fn, n=100):
+    ts = []
+    for _ in range(n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    torch.cuda.synchronize()
+    return statistics.median(ts) * 1e3, min(ts) * 1e3
+
+
+for name, fn in (("resident (inputs in HBM)", step.run_resident), ("serial e2e (host inputs, incl. the blocking .cpu() of the logits)", step.run_e2e)):
+    med, best = host_cost(fn)
+    print("host time per step, %s: median %.3f ms, min %.3f ms" % (name, med, best))
 n = 200
-torch.cuda._sleep(2_000_000_000 // 4)          # park the GPU ~0.25 s so that the host runs ahead
-t0 = time.perf_counter()
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize(); s.record()
 for _ in range(n):
     step.run_resident()
-t1 = time.perf_counter()
-torch.cuda.synchronize()
-t2 = time.perf_counter()
-print("host enqueue per step: %.3f ms; total incl. drain %.3f ms/step" % ((t1 - t0) / n * 1e3, (t2 - t0) / n * 1e3))
-pr = cProfile.Profile(); pr.enable()
+e.record(); torch.cuda.synchronize()
+print("device-bound loop: %.3f ms/step" % (s.elapsed_time(e) / n))
+import cProfile, pstats
+pr = cProfile.Profile()
 for _ in range(50):
-    step.run_resident()
-pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+    torch.cuda.synchronize()
+    pr.enable(); step.run_resident(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
