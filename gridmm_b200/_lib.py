@@ -29,8 +29,16 @@ _SIGS = {
     "gridmm_pool": [c_void_p, c_longlong, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                     c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_ln_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                             c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
-    "gridmm_head_rows": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p],
+                             c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "gridmm_head_rows": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                         c_void_p],
+    "gridmm_map_index": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "gridmm_map_inputs_packed": [c_void_p] * 11 + [c_int] + [c_void_p] * 10 + [c_float] + [c_void_p] * 4 + [c_int] * 4 + [c_void_p],
+    "gridmm_attention_ragged_f16": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_int, c_int, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int,
+                                    c_float, c_void_p],
+    "gridmm_kv_index_packed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "gridmm_fusion_inputs_packed": [c_void_p] * 12 + [c_int] + [c_void_p] * 5 + [c_int] * 6 + [c_void_p],
     "gridmm_cls_heads_f16": [c_void_p, c_int, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p],
     "gridmm_nav_logits2": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 +
@@ -38,7 +46,7 @@ _SIGS = {
     "gridmm_copy_segments": [c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_linear_f16_lanes": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                          c_void_p, c_int, c_int, c_void_p],
+                          c_void_p, c_int, c_int, c_void_p, c_void_p],
     "gridmm_attention_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_float,
                              c_int, c_int, c_int, c_int, c_float, c_void_p],
     "gridmm_layernorm": [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
@@ -48,8 +56,8 @@ _SIGS = {
     "gridmm_fusion_inputs": [c_void_p] * 13 + [c_int] + [c_void_p] * 5 + [c_int] * 6 + [c_void_p],
     "gridmm_kv_index": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_linear_f16_rows": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
-    "gridmm_attention_varlen_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                    c_int, c_int, c_int, c_float, c_void_p],
+    "gridmm_attention_varlen_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_int, c_float, c_void_p],
     "gridmm_split_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "gridmm_pos_embed": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -29,6 +29,7 @@ struct AttnParams {
     float scale;
     const int* k_off;                  // optional packed context: keys of episode b are rows k_off[b] .. k_off[b] + k_cnt[b] - 1,
     const int* k_cnt;                  // all valid (kmask unused); sk is then the maximum over the batch (shared-memory sizing)
+    const float* k_bias;               // optional additive score bias per packed key row (log of a key's multiplicity), or null
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
     for (int kt = 0; kt < n_kt && kt < ATT_NSTG; ++kt) issue_tile(kt);
     for (int j = tid; j < sk_pad; j += ATT_THREADS) {
         float m = -INFINITY;                                   // keys past Sk never contribute
-        if (j < sk) m = p.k_off ? 0.0f : (p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg);
+        if (j < sk) m = p.k_off ? (p.k_bias ? p.k_bias[krow0 + j] : 0.0f) : (p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg);
         sM[j] = m;
     }
     // first group (Q + key tile 0) must have landed before the Q fragments are read
@@ -228,7 +229,8 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnParams p) {
 
 int gridmm_attention_tc(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv, int k_rows, void* o,
                         int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk, float scale,
-                        cudaStream_t stream);      // attn_tc.cu
+                        cudaStream_t stream, const int* q_off, const int* q_cnt, const int* k_off, const int* k_cnt,
+                        const float* kbias, long long q_total, long long k_total);      // attn_tc.cu
 static int g_attn_legacy = 0;
 // Debug hook: 1 forces the mma.sync kernel, 2 the tcgen05 kernel (A/B timing and parity of the two paths); 0 = by shape.
 extern "C" void gridmm_debug_set_attn_legacy(int on) { g_attn_legacy = on; }
@@ -246,7 +248,8 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     // mma.sync, 2 forces tcgen05 (tests).
     if (g_attn_legacy != 1 && (sq > 64 || g_attn_legacy == 2) && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
         // tcgen05 path (attn_tc.cu); shapes it does not cover (Sk > 320, unaligned output) fall through to mma.sync
-        const int rc = gridmm_attention_tc(q, ldq, q_rows, k, ldk, v, ldv, k_rows, o, ldo, kmask, mask_neg, batch, heads, sq, sk, scale, stream);
+        const int rc = gridmm_attention_tc(q, ldq, q_rows, k, ldk, v, ldv, k_rows, o, ldo, kmask, mask_neg, batch, heads, sq, sk, scale, stream,
+                                           nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0);
         if (rc != GRIDMM_ERR_SHAPE) {
             if (rc == 0) gridmm_count_launch(1);
             return rc;
@@ -257,6 +260,7 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     p.v = reinterpret_cast<const __half*>(v); p.o = reinterpret_cast<__half*>(o);
     p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.q_rows = q_rows; p.k_rows = k_rows;
     p.kmask = kmask; p.mask_neg = mask_neg; p.sq = sq; p.sk = sk; p.scale = scale; p.k_off = nullptr; p.k_cnt = nullptr;
+    p.k_bias = nullptr;
     const int sk_pad = (sk + 63) & ~63;
     // 8 warps (128 query rows per CTA) halve the K/V re-reads of long query sequences; 4 warps otherwise
     const int nw = (sq > 64) ? 8 : 4;
@@ -279,8 +283,8 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
 // k / v and all of them are valid, so no key mask is applied (a masked key contributes exp(-10000) = 0 in fp32: dropping it is
 // exact).  max_sk >= max_b k_cnt[b] sizes the shared memory.  Always the mma.sync kernel (query tiles of 64 / 128 rows).
 extern "C" int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
-                                           const int* k_off, const int* k_cnt, int max_sk, void* o, int ldo, int batch, int heads,
-                                           int sq, float scale, cudaStream_t stream) {
+                                           const int* k_off, const int* k_cnt, int max_sk, const float* k_bias, void* o, int ldo,
+                                           int batch, int heads, int sq, float scale, cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0 || sq <= 0) return 0;
     if (!q || !k || !v || !o || !k_off || !k_cnt) return GRIDMM_ERR_ARG;
@@ -290,6 +294,7 @@ extern "C" int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, c
     p.v = reinterpret_cast<const __half*>(v); p.o = reinterpret_cast<__half*>(o);
     p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.q_rows = q_rows; p.k_rows = 0;
     p.kmask = nullptr; p.mask_neg = 0.0f; p.sq = sq; p.sk = max_sk; p.scale = scale; p.k_off = k_off; p.k_cnt = k_cnt;
+    p.k_bias = k_bias;
     const int sk_pad = (max_sk + 63) & ~63;
     const int nw = (sq > 64) ? 8 : 4;
     const int qt = nw * 16;
@@ -304,4 +309,23 @@ extern "C" int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, c
     }
     gridmm_count_launch(1);
     return 0;
+}
+
+// Attention over RAGGED (packed) query sequences on the tcgen05 kernel: the queries of episode b are rows q_off[b] .. q_off[b] +
+// q_cnt[b] - 1 of q (and of o); the keys are either ragged too (k_off / k_cnt given: rows of k / v, with kmask / kbias indexed by
+// packed key row) or regular (k_off = NULL: rows b * k_rows .. + sk - 1, kmask [batch, sk]).  max_sq / max_sk bound the per-episode
+// counts (launch and shared-memory sizing), q_total / k_total are the row counts of the buffers (tensor-map extents).  Valid keys get
+// kbias added to their score when kbias != NULL (log-multiplicity of de-duplicated keys), masked keys mask_neg.
+extern "C" int gridmm_attention_ragged_f16(const void* q, int ldq, const int* q_off, const int* q_cnt, int max_sq, long long q_total,
+                                           const void* k, int ldk, const void* v, int ldv, const int* k_off, const int* k_cnt,
+                                           int k_rows, int max_sk, long long k_total, const unsigned char* kmask, const float* kbias,
+                                           float mask_neg, void* o, int ldo, int batch, int heads, float scale, cudaStream_t stream) {
+    if (batch <= 0 || max_sq <= 0) return 0;
+    if (!q || !k || !v || !o || !kmask || !q_off || !q_cnt || ((k_off == nullptr) != (k_cnt == nullptr))) return GRIDMM_ERR_ARG;
+    if (max_sk <= 0 || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8) || heads * 64 > ldq || heads * 64 > ldk || heads * 64 > ldv)
+        return GRIDMM_ERR_SHAPE;
+    const int rc = gridmm_attention_tc(q, ldq, 0, k, ldk, v, ldv, k_rows, o, ldo, kmask, mask_neg, batch, heads, max_sq, max_sk, scale,
+                                       stream, q_off, q_cnt, k_off, k_cnt, kbias, q_total, k_total);
+    if (rc == 0) gridmm_count_launch(1);
+    return rc;
 }

@@ -26,6 +26,10 @@ struct AttnTcParams {
     int sq, sk, nkey;                  // nkey = sk rounded up to 16
     int o_col, tmem_cols;              // TMEM column of O, allocation size (power of two)
     float scale;
+    // ragged ("packed") sequences: rows of episode b start at q_off[b] / k_off[b] and number q_cnt[b] / k_cnt[b] (<= sq / sk, which
+    // then only size the launch and the shared memory); kmask / kbias are indexed by packed key row when k_off is given
+    const int* q_off; const int* q_cnt; const int* k_off; const int* k_cnt;
+    const float* kbias;                // optional additive score bias per VALID key (log of a key's multiplicity), or null
 };
 
 // MN-major shared-memory operand (V as [key][dim]: 64 dims = 128 contiguous bytes per key, SWIZZLE_128B, 8-key groups 1024 B
@@ -65,6 +69,12 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    pdl_wait();
+    const int q_base = p.q_off ? __ldg(p.q_off + b) : b * p.q_rows;
+    const int q_n = p.q_cnt ? __ldg(p.q_cnt + b) : p.sq;
+    const int k_base = p.k_off ? __ldg(p.k_off + b) : b * p.k_rows;
+    const int k_n = p.k_cnt ? __ldg(p.k_cnt + b) : p.sk;
+    if (q0 >= q_n) return;                              // ragged batch: this query tile lies past the episode's rows (whole CTA)
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -72,26 +82,29 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
         fence_mbar_init();
     }
     if (warp == 4) tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-    pdl_wait();
-    for (int j = threadIdx.x; j < p.nkey; j += blockDim.x) {
+    const int nkey = max((k_n + 15) & ~15, 16);          // keys of THIS episode, rounded to the MMA's K step (<= p.nkey)
+    const size_t m_base = p.k_off ? static_cast<size_t>(k_base) : static_cast<size_t>(b) * p.sk;
+    for (int j = threadIdx.x; j < nkey; j += blockDim.x) {
         float m = -INFINITY;                               // keys past Sk never contribute
-        if (j < p.sk) m = p.kmask[static_cast<size_t>(b) * p.sk + j] ? 0.0f : p.mask_neg;
+        if (j < k_n) {
+            m = p.kmask[m_base + j] ? 0.0f : p.mask_neg;
+            if (p.kbias && m == 0.0f) m = p.kbias[m_base + j];
+        }
         sM[j] = m;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
-    const int nkey = p.nkey;
 
     if (warp == 4) {
         // ---------------------------------------------------------------- loads + both MMA phases
         if (elect_one()) {
             mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(128 * 128 + 2 * nkey * 128));
-            tma_load_2d(sQ, &tmQ, h * 64, b * p.q_rows + q0, &bars[0]);
+            tma_load_2d(sQ, &tmQ, h * 64, q_base + q0, &bars[0]);
             for (int j = 0; j < nkey; j += 16) {
-                tma_load_2d(sK + j * 128, &tmK, h * 64, b * p.k_rows + j, &bars[0]);
-                tma_load_2d(sV + j * 128, &tmV, h * 64, b * p.k_rows + j, &bars[0]);
+                tma_load_2d(sK + j * 128, &tmK, h * 64, k_base + j, &bars[0]);
+                tma_load_2d(sV + j * 128, &tmV, h * 64, k_base + j, &bars[0]);
             }
         }
         __syncwarp();
@@ -137,7 +150,10 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
             tmem_ld_32x32b_x16(t_row + c, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), sc, sM[c + j] * LOG2E));
+            for (int j = 0; j < 16; ++j) {
+                const float mj = sM[c + j];
+                if (mj != -INFINITY) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), sc, mj * LOG2E));
+            }
         }
         const float m_use = (mx == -INFINITY) ? 0.0f : mx;
         float l = 0.f;
@@ -148,8 +164,10 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
             uint32_t pk[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
-                const float p0 = ex2f(fmaf(__uint_as_float(v[j]), sc, sM[c + j] * LOG2E) - m_use);
-                const float p1 = ex2f(fmaf(__uint_as_float(v[j + 1]), sc, sM[c + j + 1] * LOG2E) - m_use);
+                // keys past the episode's end / -inf masked keys get probability exactly 0 whatever the (stale) score is
+                const float m0 = sM[c + j], m1 = sM[c + j + 1];
+                const float p0 = (m0 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[j]), sc, m0 * LOG2E) - m_use);
+                const float p1 = (m1 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[j + 1]), sc, m1 * LOG2E) - m_use);
                 const __half2 hp = __floats2half2_rn(p0, p1);
                 const float2 fp = __half22float2(hp);      // the normaliser uses the rounded probabilities the MMA will see
                 l += fp.x + fp.y;
@@ -179,8 +197,8 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
             ov[2 * c] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
             ov[2 * c + 1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
         }
-        if (row < p.sq) {
-            uint4* dst = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(b) * p.q_rows + row) * p.ldo + h * 64);
+        if (row < q_n) {
+            uint4* dst = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(q_base) + row) * p.ldo + h * 64);
 #pragma unroll
             for (int c = 0; c < 8; ++c) dst[c] = ov[c];
         }
@@ -200,22 +218,26 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
 // returns GRIDMM_ERR_SHAPE when the shape is outside this kernel's range (the caller then uses the mma.sync kernel)
 int gridmm_attention_tc(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv, int k_rows, void* o,
                         int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk, float scale,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const int* q_off, const int* q_cnt, const int* k_off, const int* k_cnt,
+                        const float* kbias, long long q_total, long long k_total) {
     using namespace gmm;
     const int nkey = (sk + 15) & ~15;
     if (nkey > 320 || (ldo % 8) || (reinterpret_cast<uintptr_t>(o) & 15)) return GRIDMM_ERR_SHAPE;
     AttnTcParams p;
     p.o = reinterpret_cast<__half*>(o); p.ldo = ldo; p.q_rows = q_rows; p.k_rows = k_rows; p.kmask = kmask; p.mask_neg = mask_neg;
     p.sq = sq; p.sk = sk; p.nkey = nkey; p.scale = scale;
+    p.q_off = q_off; p.q_cnt = q_cnt; p.k_off = k_off; p.k_cnt = k_cnt; p.kbias = kbias;
     p.o_col = ((nkey / 2) + 31) & ~31;
     const int need = nkey > p.o_col + 64 ? nkey : p.o_col + 64;
     p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    const uint64_t q_outer = q_total > 0 ? static_cast<uint64_t>(q_total) : static_cast<uint64_t>(batch) * q_rows;
+    const uint64_t k_outer = k_total > 0 ? static_cast<uint64_t>(k_total) : static_cast<uint64_t>(batch) * k_rows;
     CUtensorMap tmQ, tmK, tmV;
-    int rc = make_tmap_f16_2d(&tmQ, q, static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(batch) * q_rows, static_cast<uint64_t>(ldq) * 2, 64, 128);
+    int rc = make_tmap_f16_2d(&tmQ, q, static_cast<uint64_t>(heads) * 64, q_outer, static_cast<uint64_t>(ldq) * 2, 64, 128);
     if (rc) return rc;
-    rc = make_tmap_f16_2d(&tmK, k, static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(batch) * k_rows, static_cast<uint64_t>(ldk) * 2, 64, 16);
+    rc = make_tmap_f16_2d(&tmK, k, static_cast<uint64_t>(heads) * 64, k_outer, static_cast<uint64_t>(ldk) * 2, 64, 16);
     if (rc) return rc;
-    rc = make_tmap_f16_2d(&tmV, v, static_cast<uint64_t>(heads) * 64, static_cast<uint64_t>(batch) * k_rows, static_cast<uint64_t>(ldv) * 2, 64, 16);
+    rc = make_tmap_f16_2d(&tmV, v, static_cast<uint64_t>(heads) * 64, k_outer, static_cast<uint64_t>(ldv) * 2, 64, 16);
     if (rc) return rc;
     const int smem = 1024 + 128 * 128 + 2 * nkey * 128 + nkey * 4 + 64;
     GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -41,6 +41,7 @@ struct LnEpilogue {
     __half* out_f16;         // [M, ld_f16] or null
     int ld_res, ld_f32, ld_f16;
     int f32_raw;             // 1: out_f32 receives v (pre-norm residual stream), 0: the normalised y
+    const int* m_dev;        // optional device-side row count (<= M): packed / ragged operands whose size only the GPU knows
 };
 
 // PAIR: the cluster is 4 CTAs = two cta_group::2 pairs.  A pair owns 256 rows x 384 columns (each CTA: its 128 rows of A, HALF of
@@ -138,8 +139,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     pdl_wait();
+    if (ep.m_dev) M = min(M, __ldg(ep.m_dev));
+    // ragged operand: row tiles past the device-side row count have nothing to do.  The whole cluster shares one row tile (one
+    // 256-row tile in pair mode), so the decision is cluster-uniform and the cluster barriers below stay matched.
+    const bool tile_active = (static_cast<int>(blockIdx.x / CL) * (PAIR ? 2 * LN_BM : LN_BM)) < M;
 
-    if (warp == 0) {
+    if (!tile_active) {
+        // fall through to the barriers / TMEM release
+    } else if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer (converged warp, elected issue)
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % STAGES;
@@ -303,7 +310,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---- every column slice of the tile has published its partial statistics
     cluster_sync_all();
 
-    if (warp >= 2) {
+    if (warp >= 2 && tile_active) {
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int trow = q * 32 + lane;
@@ -425,7 +432,8 @@ extern "C" void gridmm_debug_set_ln_cluster(int cl) { g_ln_cluster = cl; }
 
 extern "C" int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                                     const float* residual, int ld_res, const float* gamma, const float* beta, float eps,
-                                    float* out_f32, int ld_f32, void* out_f16, int ld_f16, int f32_raw, cudaStream_t stream) {
+                                    float* out_f32, int ld_f32, void* out_f16, int ld_f16, int f32_raw, const int* m_dev,
+                                    cudaStream_t stream) {
     using namespace gmm;
     if (M <= 0) return 0;
     if (N != LN_N || K % 64 != 0 || K <= 0 || (lda % 8) || (ldw % 8)) return GRIDMM_ERR_SHAPE;
@@ -433,7 +441,7 @@ extern "C" int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int l
     if (!a || !w || !gamma || !beta || (!out_f32 && !out_f16)) return GRIDMM_ERR_ARG;
     const int sms = gridmm_sm_count();
     if (sms <= 0) return GRIDMM_ERR_DRIVER;
-    LnEpilogue ep{bias, residual, gamma, beta, eps, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, f32_raw};
+    LnEpilogue ep{bias, residual, gamma, beta, eps, out_f32, reinterpret_cast<__half*>(out_f16), ld_res, ld_f32, ld_f16, f32_raw, m_dev};
     // cluster size: waves x (per-CTA work ~ slice width + fixed epilogue/launch part)
     const int tiles_m = (M + LN_BM - 1) / LN_BM;
     const long long t2 = static_cast<long long>((tiles_m * 2 + sms - 1) / sms) * (384 + 128);

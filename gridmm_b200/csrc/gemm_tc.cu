@@ -505,8 +505,9 @@ static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, 
 
 extern "C" int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                                  const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16,
-                                 int act, cudaStream_t stream) {
-    return gemm_dispatch(a, lda, w, ldw, M, N, K, bias, residual, ld_res, out_f32, ld_f32, out_f16, ld_f16, act, nullptr, 0, stream);
+                                 int act, const int* m_dev, cudaStream_t stream) {
+    return gemm_dispatch(a, lda, w, ldw, M, N, K, bias, residual, ld_res, out_f32, ld_f32, out_f16, ld_f16, act, nullptr, 0, stream,
+                         nullptr, nullptr, nullptr, 0, 0, nullptr, m_dev);
 }
 
 // text_proj for gridmm_pool: out_lanes[b, N/8, 128] (16-byte units, lane-major) = a[M = batch*rows_per_b, K] . w[N, K]^T + bias

@@ -15,6 +15,7 @@ constexpr int HD = 768;
 
 struct HeadSeg {
     const float* x; int ldx, in_rows_per_b, in_off, rows_per_b, rows, out_row0;
+    const int* row_off;      // optional [batch] first input row of every episode (ragged / packed source), replaces b * in_rows_per_b
 };
 struct HeadRowsParams {
     HeadSeg seg[6];
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(256) head_rows_kernel(HeadRowsParams p) {
         if (si < p.nseg - 1 && row >= p.seg[si].rows) { row -= p.seg[si].rows; ++si; }
     const HeadSeg sg = p.seg[si];
     const int b = row / sg.rows_per_b, r = row - b * sg.rows_per_b;
-    const size_t irow = static_cast<size_t>(b) * sg.in_rows_per_b + sg.in_off + r;
+    const size_t irow = (sg.row_off ? static_cast<size_t>(sg.row_off[b]) : static_cast<size_t>(b) * sg.in_rows_per_b) + sg.in_off + r;
     __half* o = p.out + static_cast<size_t>(sg.out_row0 + row) * p.ld_out;
 #pragma unroll
     for (int i = 0; i < HD / 128; ++i) {
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(128) nav_logits2_kernel(Logit2Params p) {
 // segs: HOST array of nseg x 7 ints is awkward across a C ABI with pointers inside, so the (at most 4) segments are passed flat:
 // x[i], ldx[i], in_rows_per_b[i], in_off[i], rows_per_b[i], out_row0[i]; rows = rows_per_b * batch.
 extern "C" int gridmm_head_rows(int nseg, const float* const* x, const int* ldx, const int* in_rows_per_b, const int* in_off,
-                                const int* rows_per_b, const int* out_row0, int batch, void* out_f16, int ld_f16, int hidden,
-                                cudaStream_t stream) {
+                                const int* rows_per_b, const int* out_row0, const int* const* row_off, int batch, void* out_f16,
+                                int ld_f16, int hidden, cudaStream_t stream) {
     using namespace gmm;
     if (nseg < 1 || nseg > 6 || batch <= 0) return GRIDMM_ERR_SHAPE;
     if (hidden != HD || (ld_f16 % 4) || ld_f16 < 3 * HD || !out_f16) return GRIDMM_ERR_SHAPE;
@@ -173,7 +174,8 @@ extern "C" int gridmm_head_rows(int nseg, const float* const* x, const int* ldx,
     p.nseg = nseg; p.total = 0; p.out = reinterpret_cast<__half*>(out_f16); p.ld_out = ld_f16;
     for (int i = 0; i < nseg; ++i) {
         if (!x[i] || (ldx[i] % 4)) return GRIDMM_ERR_ARG;
-        p.seg[i] = HeadSeg{x[i], ldx[i], in_rows_per_b[i], in_off[i], rows_per_b[i], rows_per_b[i] * batch, out_row0[i]};
+        p.seg[i] = HeadSeg{x[i], ldx[i], in_rows_per_b[i], in_off[i], rows_per_b[i], rows_per_b[i] * batch, out_row0[i],
+                           row_off ? row_off[i] : nullptr};
         p.total += rows_per_b[i] * batch;
     }
     for (int i = nseg; i < 6; ++i) p.seg[i] = p.seg[nseg - 1];

@@ -473,6 +473,264 @@ __global__ void __launch_bounds__(256) grid_assemble_kernel(AssembleParams p) {
     pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
+// ------------------------------------------------------------------------------------------- ragged ("packed") map sequence
+// The reference pads every episode's map sequence [grid cells ; gmap nodes] to the batch maximum (vilmodel.py:813-838); here the
+// rows that matter are PACKED back to back, so that every map-sized GEMM / attention / LayerNorm launch only touches them:
+//   episode b owns rows m_off[b] .. m_off[b+1]-1 =  [ k_b non-empty cells (rank order) | q_b | G gmap nodes ]
+// q_b (0 or 1) stands for the z_b zero-vector slots that the reference's mask-aliasing quirk flags valid (grid_assemble above:
+// valid = [0,k) u (S n [k,k')) truncated to C).  Those z_b rows are IDENTICAL at every layer (same input, permutation-equivariant
+// blocks), so one representative row is computed and, wherever it acts as an attention KEY, its score gets + log(z_b):
+// sum_j exp(s_j) v_j over z identical keys = exp(s + log z) v -- exact.  Masked (invalid) cell slots are dropped: as keys they have
+// weight 0, as queries nobody reads them.  All G gmap rows stay (the reference returns their outputs, masked or not).
+__global__ void __launch_bounds__(1024) map_index_kernel(const int* cell_rank, const int* n_nonempty, int B, int NC, int G,
+                                                         int* m_off, int* m_info, float* m_logz, int* cell_of_rank, int* m_goff) {
+    extern __shared__ int s_n[];            // [B + 1] rows per episode, then their exclusive prefix
+    __shared__ int s_red[32];
+    __shared__ int s_c;
+    pdl_wait();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    int mx = 0;
+    for (int i = tid; i < B; i += blockDim.x) mx = max(mx, n_nonempty[i]);
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int i = 0; i < nwarps; ++i) m = max(m, s_red[i]);
+        s_c = m;                            // C = max_b k_b: the reference truncates the cell slots to C columns
+    }
+    __syncthreads();
+    const int C = s_c;
+    for (int b = warp; b < B; b += nwarps) {
+        const int k = n_nonempty[b];
+        int above = 0;
+        for (int c = lane; c < NC; c += 32) {
+            const int r = cell_rank[b * NC + c];
+            if (r >= 0) { cell_of_rank[b * NC + r] = c; above += (c >= k) ? 1 : 0; }
+        }
+        above = __reduce_add_sync(0xffffffffu, above);
+        const int k2 = min(k + above, C);
+        int z = 0;
+        for (int c = k + lane; c < k2; c += 32) z += (cell_rank[b * NC + c] >= 0) ? 1 : 0;
+        z = __reduce_add_sync(0xffffffffu, z);
+        if (lane == 0) {
+            const int v = k + (z > 0 ? 1 : 0);
+            m_info[b] = k; m_info[B + b] = v; m_info[2 * B + b] = v + G; m_info[3 * B + b] = z;      // [4][B]: each row is a contiguous per-episode array
+            m_logz[b] = z > 0 ? logf(static_cast<float>(z)) : 0.0f;
+            s_n[b] = v + G;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int b = b0 + lane;
+            const int c = b < B ? s_n[b] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (b < B) { m_off[b] = run + incl - c; m_goff[b] = run + incl - G; }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) m_off[B] = run;
+    }
+    pdl_launch_dependents();
+}
+
+struct MapPackedParams {
+    const float* proj;        // [B, n_cells, 768] grid_proj output in rank order
+    const float* pos_fts;     // [B, n_cells, 5]
+    const int* cell_of_rank;  // [B, n_cells]
+    const int* m_off; const int* m_info; const float* m_logz;
+    const float* w; const float* bias; const float* gamma; const float* beta;   // grid_pos_embeddings (w TRANSPOSED: [5, 768])
+    const float* g_feat; int g_kin; const float* g_w; const float* g_bias; const float* g_gamma; const float* g_beta;
+    const float* g_base; const float* g_table; const long long* g_idx; const uint8_t* g_mask;
+    const float* n_gamma; const float* n_beta; float n_eps;
+    float* map32; __half* map16;          // packed rows
+    uint8_t* kvalid; float* kbias;        // per packed row: valid as a key, additive score bias (log multiplicity)
+    int batch, n_cells, G;
+};
+
+__global__ void __launch_bounds__(256) map_inputs_packed_kernel(MapPackedParams p) {
+    extern __shared__ int s_off[];         // [B + 1]
+    pdl_wait();
+    for (int i = threadIdx.x; i <= p.batch; i += 256) s_off[i] = p.m_off[i];
+    __syncthreads();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= s_off[p.batch]) return;
+    int lo = 0, hi = p.batch;              // largest b with m_off[b] <= row
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= row) lo = mid; else hi = mid;
+    }
+    const int b = lo, r = row - s_off[b];
+    const int k = p.m_info[b], vcells = p.m_info[p.batch + b];
+    float4 v[HV];
+    uint8_t valid = 1;
+    float kb = 0.0f;
+    if (r >= vcells) {
+        // gmap token (vilmodel.py:828-831): gmap_img + step embedding + LN(Linear(gmap_pos))
+        const size_t gr = static_cast<size_t>(b) * p.G + (r - vcells);
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = (j < p.g_kin) ? p.g_feat[gr * p.g_kin + j] : 0.0f;
+        small_linear(v, f, p.g_kin, p.g_w, p.g_bias, lane);
+        ln_row(v, p.g_gamma, p.g_beta, 1e-12f, lane);
+        const float* tr = p.g_table + static_cast<size_t>(p.g_idx[gr]) * HID;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const float4 t1 = *reinterpret_cast<const float4*>(p.g_base + gr * HID + (i * 32 + lane) * 4);
+            const float4 t2 = *reinterpret_cast<const float4*>(tr + (i * 32 + lane) * 4);
+            v[i].x += t1.x + t2.x; v[i].y += t1.y + t2.y; v[i].z += t1.z + t2.z; v[i].w += t1.w + t2.w;
+        }
+        valid = p.g_mask[gr];
+    } else if (r < k) {
+        // non-empty cell of rank r: grid_proj(pooled) + grid_pos_embeddings(cell-centre features) (vilmodel.py:813-816)
+        const int cellid = p.cell_of_rank[b * p.n_cells + r];
+        float f[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) f[j] = p.pos_fts[(static_cast<size_t>(b) * p.n_cells + cellid) * 5 + j];
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const int col = (i * 32 + lane) * 4;
+            float4 a = *reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(p.w + j * HID + col);
+                a.x = fmaf(f[j], w4.x, a.x); a.y = fmaf(f[j], w4.y, a.y); a.z = fmaf(f[j], w4.z, a.z); a.w = fmaf(f[j], w4.w, a.w);
+            }
+            v[i] = a;
+        }
+        ln_row(v, p.gamma, p.beta, 1e-12f, lane);
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(p.proj + (static_cast<size_t>(b) * p.n_cells + r) * HID + (i * 32 + lane) * 4);
+            v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+        }
+    } else {
+        // the representative of the z_b zero-vector slots the compaction quirk flags valid
+#pragma unroll
+        for (int i = 0; i < HV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        kb = p.m_logz[b];
+    }
+    store_row(v, p.map32 + static_cast<size_t>(row) * HID, nullptr, lane);
+    if (lane == 0) { p.kvalid[row] = valid; p.kbias[row] = kb; }
+    ln_row(v, p.n_gamma, p.n_beta, p.n_eps, lane);
+    store_row(v, nullptr, p.map16 + static_cast<size_t>(row) * HID, lane);
+    pdl_launch_dependents();
+}
+
+// Packed context of the fusion encoder over the PACKED map: context of episode b = its valid map rows + its valid text rows.
+//   kv_src[r]  source of packed context row r: >= 0 packed map row, < 0: -1 - (b * L + l) text row
+//   kv_bias[r] additive score bias of that key (log multiplicity of the quirk representative, else 0)
+__global__ void __launch_bounds__(1024) kv_index_packed_kernel(const int* m_off, const uint8_t* kvalid, const float* kbias,
+                                                               const uint8_t* txt_mask, int B, int L, int* kv_src, float* kv_bias,
+                                                               int* kv_off, int* kv_cnt) {
+    extern __shared__ int s_cnt[];          // [B + 1]
+    pdl_wait();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < B; b += nwarps) {
+        const int r0 = m_off[b], n = m_off[b + 1] - r0;
+        int cnt = 0;
+        for (int i0 = 0; i0 < n + L; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < n + L && ((i < n) ? kvalid[r0 + i] : txt_mask[b * L + (i - n)]) != 0;
+            cnt += __popc(__ballot_sync(0xffffffffu, valid));
+        }
+        if (lane == 0) s_cnt[b] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int b = b0 + lane;
+            const int c = b < B ? s_cnt[b] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (b < B) { kv_off[b] = run + incl - c; kv_cnt[b] = c; s_cnt[b] = run + incl - c; }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) kv_off[B] = run;
+    }
+    __syncthreads();
+    for (int b = warp; b < B; b += nwarps) {
+        const int r0 = m_off[b], n = m_off[b + 1] - r0;
+        int rank = s_cnt[b];
+        for (int i0 = 0; i0 < n + L; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < n + L && ((i < n) ? kvalid[r0 + i] : txt_mask[b * L + (i - n)]) != 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const int dst = rank + __popc(bal & ((1u << lane) - 1u));
+                kv_src[dst] = (i < n) ? (r0 + i) : (-1 - (b * L + (i - n)));
+                kv_bias[dst] = (i < n) ? kbias[r0 + i] : 0.0f;
+            }
+            rank += __popc(bal);
+        }
+    }
+    pdl_launch_dependents();
+}
+
+struct FusionPackedParams {
+    const float* map32; const float* txt32;     // packed map rows, [B, L, 768]
+    const int* kv_src; const int* kv_off;       // packed context index (kv_off[B] = number of context rows)
+    const int* m_goff;                          // [B] first gmap row of every episode in the packed map
+    const uint8_t* gmap_mask; const uint8_t* vp_mask;
+    float* x32; __half* x16; __half* kv16; uint8_t* q_mask;
+    int B, L, G, V, kv_rows_max;
+    const float* v_feat; int v_kin; const float* v_w; const float* v_bias; const float* v_gamma; const float* v_beta; const float* v_base;
+};
+
+__global__ void __launch_bounds__(256) fusion_inputs_packed_kernel(FusionPackedParams p) {
+    pdl_wait();
+    const int Q = p.G + p.V;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= p.kv_rows_max + p.B * Q) return;
+    float4 v[HV];
+    if (row < p.kv_rows_max) {
+        if (row >= p.kv_off[p.B]) return;
+        const int src = p.kv_src[row];
+        const float* sp = (src >= 0) ? p.map32 + static_cast<size_t>(src) * HID : p.txt32 + static_cast<size_t>(-1 - src) * HID;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(sp + (i * 32 + lane) * 4);
+        store_row(v, nullptr, p.kv16 + static_cast<size_t>(row) * HID, lane);
+    } else if (row < p.kv_rows_max + p.B * p.G) {
+        const int rr = row - p.kv_rows_max;
+        const int b = rr / p.G, g = rr - b * p.G;
+        const float* src = p.map32 + (static_cast<size_t>(p.m_goff[b]) + g) * HID;
+#pragma unroll
+        for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+        const size_t orow = static_cast<size_t>(b) * Q + g;
+        store_row(v, p.x32 + orow * HID, p.x16 + orow * HID, lane);
+        if (lane == 0) p.q_mask[b * Q + g] = p.gmap_mask[b * p.G + g];
+    } else {
+        // vp token j of episode b: vp_img + LN(Linear(vp_pos)) (vilmodel.py:832-833)
+        const int vr = row - p.kv_rows_max - p.B * p.G;
+        const int b = vr / p.V, j = vr - b * p.V;
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = (k < p.v_kin) ? p.v_feat[static_cast<size_t>(vr) * p.v_kin + k] : 0.0f;
+        small_linear(v, f, p.v_kin, p.v_w, p.v_bias, lane);
+        ln_row(v, p.v_gamma, p.v_beta, 1e-12f, lane);
+#pragma unroll
+        for (int i = 0; i < HV; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(p.v_base + static_cast<size_t>(vr) * HID + (i * 32 + lane) * 4);
+            v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+        }
+        const size_t orow = static_cast<size_t>(b) * Q + p.G + j;
+        store_row(v, p.x32 + orow * HID, p.x16 + orow * HID, lane);
+        if (lane == 0) p.q_mask[b * Q + p.G + j] = p.vp_mask[b * p.V + j];
+    }
+    pdl_launch_dependents();
+}
+
 // ------------------------------------------------------------------------------------------- ClsPrediction tail
 // logit[row] = w2 . LN(h[row]) + b2      (h = ReLU(Linear(x)) comes from the GEMM epilogue)
 __global__ void __launch_bounds__(256) cls_tail_kernel(const float* h, const float* gamma, const float* beta, const float* w2,
@@ -786,6 +1044,74 @@ extern "C" int gridmm_copy_segments(int n, const void* const* src, void* const* 
     const long long cap = static_cast<long long>(sms > 0 ? sms : 148) * 8;
     if (blocks > cap) blocks = cap;
     GMM_CUDA_CHECK(launch_pdl(copy_segments_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, p));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+// ---- ragged ("packed") map sequence: see the comment above map_index_kernel
+extern "C" int gridmm_map_index(const int* cell_rank, const int* n_nonempty, int batch, int n_cells, int G, int* m_off, int* m_info,
+                                float* m_logz, int* cell_of_rank, int* m_goff, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (batch > 8192 || n_cells < 1 || n_cells > 256 || G < 1) return GRIDMM_ERR_SHAPE;
+    if (!cell_rank || !n_nonempty || !m_off || !m_info || !m_logz || !cell_of_rank || !m_goff) return GRIDMM_ERR_ARG;
+    GMM_CUDA_CHECK(launch_pdl(map_index_kernel, dim3(1), dim3(1024), (batch + 1) * sizeof(int), stream, cell_rank, n_nonempty, batch, n_cells,
+                              G, m_off, m_info, m_logz, cell_of_rank, m_goff));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+extern "C" int gridmm_map_inputs_packed(const float* proj, const float* pos_fts, const int* cell_of_rank, const int* m_off,
+                                        const int* m_info, const float* m_logz, const float* w, const float* bias, const float* gamma,
+                                        const float* beta, const float* gmap_pos, int gmap_kin, const float* gw, const float* gbias,
+                                        const float* ggamma, const float* gbeta, const float* gmap_img, const float* step_table,
+                                        const long long* step_ids, const unsigned char* gmap_mask, const float* norm_gamma,
+                                        const float* norm_beta, float norm_eps, float* map_f32, void* map_f16, unsigned char* kvalid,
+                                        float* kbias, int batch, int n_cells, int G, int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (hidden != HID || n_cells > 256 || G < 1 || gmap_kin < 1 || gmap_kin > 16 || batch > 8192) return GRIDMM_ERR_SHAPE;
+    if (!proj || !pos_fts || !cell_of_rank || !m_off || !m_info || !m_logz || !w || !bias || !gamma || !beta || !gmap_pos || !gw ||
+        !gbias || !ggamma || !gbeta || !gmap_img || !step_table || !step_ids || !gmap_mask || !norm_gamma || !norm_beta || !map_f32 ||
+        !map_f16 || !kvalid || !kbias)
+        return GRIDMM_ERR_ARG;
+    MapPackedParams p{proj, pos_fts, cell_of_rank, m_off, m_info, m_logz, w, bias, gamma, beta, gmap_pos, gmap_kin, gw, gbias, ggamma,
+                      gbeta, gmap_img, step_table, step_ids, gmap_mask, norm_gamma, norm_beta, norm_eps, map_f32,
+                      reinterpret_cast<__half*>(map_f16), kvalid, kbias, batch, n_cells, G};
+    const int rows = batch * (n_cells + G);      // upper bound; warps past m_off[batch] exit
+    GMM_CUDA_CHECK(launch_pdl(map_inputs_packed_kernel, dim3((rows + 7) / 8), dim3(256), (batch + 1) * sizeof(int), stream, p));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+extern "C" int gridmm_kv_index_packed(const int* m_off, const unsigned char* kvalid, const float* kbias, const unsigned char* txt_mask,
+                                      int batch, int L, int* kv_src, float* kv_bias, int* kv_off, int* kv_cnt, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (L < 1 || batch > 8192) return GRIDMM_ERR_SHAPE;
+    if (!m_off || !kvalid || !kbias || !txt_mask || !kv_src || !kv_bias || !kv_off || !kv_cnt) return GRIDMM_ERR_ARG;
+    GMM_CUDA_CHECK(launch_pdl(kv_index_packed_kernel, dim3(1), dim3(1024), (batch + 1) * sizeof(int), stream, m_off, kvalid, kbias, txt_mask,
+                              batch, L, kv_src, kv_bias, kv_off, kv_cnt));
+    gridmm_count_launch(1);
+    return 0;
+}
+
+extern "C" int gridmm_fusion_inputs_packed(const float* map32, const float* txt32, const int* kv_src, const int* kv_off, const int* m_goff,
+                                           const unsigned char* gmap_mask, const unsigned char* vp_mask, float* x32, void* x16, void* kv16,
+                                           unsigned char* q_mask, const float* vp_pos, int vp_kin, const float* vp_w, const float* vp_bias,
+                                           const float* vp_gamma, const float* vp_beta, const float* vp_img, int batch, int L, int G, int V,
+                                           int kv_rows_max, int hidden, cudaStream_t stream) {
+    using namespace gmm;
+    if (batch <= 0) return 0;
+    if (hidden != HID || L < 1 || G < 1 || V < 1 || kv_rows_max < 1 || vp_kin < 1 || vp_kin > 16) return GRIDMM_ERR_SHAPE;
+    if (!map32 || !txt32 || !kv_src || !kv_off || !m_goff || !gmap_mask || !vp_mask || !x32 || !x16 || !kv16 || !q_mask || !vp_pos ||
+        !vp_w || !vp_bias || !vp_gamma || !vp_beta || !vp_img)
+        return GRIDMM_ERR_ARG;
+    FusionPackedParams p{map32, txt32, kv_src, kv_off, m_goff, gmap_mask, vp_mask, x32, reinterpret_cast<__half*>(x16),
+                         reinterpret_cast<__half*>(kv16), q_mask, batch, L, G, V, kv_rows_max, vp_pos, vp_kin, vp_w, vp_bias, vp_gamma,
+                         vp_beta, vp_img};
+    const int rows = kv_rows_max + batch * (G + V);
+    GMM_CUDA_CHECK(launch_pdl(fusion_inputs_packed_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, p));
     gridmm_count_launch(1);
     return 0;
 }

@@ -485,66 +485,85 @@ class GlocalTextPathNavCMT(nn.Module):
     def _ln(self, x32, pre, eps, out32, out16):
         ops.layernorm(x32, self.P(pre + ".weight"), self.P(pre + ".bias"), eps, out_f32=out32, out_f16=out16)
 
-    def _ffn_post(self, x32, x16, pre_i, pre_o, rows, tag):
+    def _ffn_post(self, x32, x16, pre_i, pre_o, rows, tag, rag=None):
         """BertIntermediate + BertOutput (vilmodel.py:184-209): x = LN(W2 gelu(W1 x) + x)."""
-        h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16)
-        ops.linear(x16, self.W16(pre_i + ".dense.weight"), self.B32(pre_i + ".dense.bias"), out_f16=h, act=ops.ACT_GELU)
+        md = rag["m_dev"] if rag else None
+        h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16, zero=True)
+        ops.linear(x16, self.W16(pre_i + ".dense.weight"), self.B32(pre_i + ".dense.bias"), out_f16=h, act=ops.ACT_GELU, m_dev=md)
         ops.linear_ln(h, self.W16(pre_o + ".dense.weight"), self.B32(pre_o + ".dense.bias"), x32, self.P(pre_o + ".LayerNorm.weight"),
-                      self.P(pre_o + ".LayerNorm.bias"), self.config.layer_norm_eps, out_f32=x32, out_f16=x16)
+                      self.P(pre_o + ".LayerNorm.bias"), self.config.layer_norm_eps, out_f32=x32, out_f16=x16, m_dev=md)
 
-    def _self_post(self, x32, x16, pre, kmask, B, S, tag):
+    def _self_attention(self, qkv, kmask, neg, B, S, tag, rag):
+        """softmax(q k^T / 8 + mask) v over the fused projection buffer; `rag`: the rows are a packed (ragged) batch."""
+        q, k, v = qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:]
+        if rag is None:
+            return self._attention(q, k, v, kmask, neg, B, S, S, tag)
+        out = self.buf(tag, (qkv.shape[0], HID), torch.float16, zero=True)
+        ops.attention_ragged(q, k, v, out, rag["off"], rag["cnt"], S, rag["kvalid"], neg, B, HEADS, S, k_off=rag["off"],
+                             k_cnt=rag["cnt"], kbias=rag["kbias"])
+        return out
+
+    def _self_post(self, x32, x16, pre, kmask, B, S, tag, rag=None):
         """BertAttention (vilmodel.py:172-182): x = LN(Wo attn(x) + x), additive -10000 mask."""
-        qkv = self.buf("qkv16_" + tag, (B * S, 3 * HID), torch.float16)
+        md = rag["m_dev"] if rag else None
+        qkv = self.buf("qkv16_" + tag, (x16.shape[0], 3 * HID), torch.float16, zero=True)
         ops.linear(x16, self.W16(pre + ".self.query.weight", pre + ".self.key.weight", pre + ".self.value.weight"),
-                   self.B32(pre + ".self.query.bias", pre + ".self.key.bias", pre + ".self.value.bias"), out_f16=qkv)
-        a = self._attention(qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:], kmask, NEG_BERT, B, S, S, "att16_" + tag)
+                   self.B32(pre + ".self.query.bias", pre + ".self.key.bias", pre + ".self.value.bias"), out_f16=qkv, m_dev=md)
+        a = self._self_attention(qkv, kmask, NEG_BERT, B, S, "att16_" + tag, rag)
         ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
                       self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), self.config.layer_norm_eps,
-                      out_f32=x32, out_f16=x16)
+                      out_f32=x32, out_f16=x16, m_dev=md)
 
-    def _cross_post(self, x32, x16, pre, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None):
+    def _cross_post(self, x32, x16, pre, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None, rag=None):
         """BertXAttention (vilmodel.py:317-379): x = LN(Wo attn(q = x, kv = ctx) + x).
-        ctx_var = (k_off, k_cnt): the context is packed (masked rows removed, gridmm_kv_index), no key mask is needed."""
-        q = self.buf("q16_" + tag, (B * S, HID), torch.float16)
-        ops.linear(x16, self.W16(pre + ".att.query.weight"), self.B32(pre + ".att.query.bias"), out_f16=q)
-        if ctx_var is not None:
+        ctx_var = (k_off, k_cnt[, k_bias]): the context is packed (masked rows removed, gridmm_kv_index), no key mask is needed.
+        rag: the QUERY rows are a packed (ragged) batch; the context is regular ([B, Sk] rows with ctx_mask)."""
+        md = rag["m_dev"] if rag else None
+        q = self.buf("q16_" + tag, (x16.shape[0], HID), torch.float16, zero=True)
+        ops.linear(x16, self.W16(pre + ".att.query.weight"), self.B32(pre + ".att.query.bias"), out_f16=q, m_dev=md)
+        if rag is not None:
+            a = self.buf("att16_" + tag, (x16.shape[0], HID), torch.float16, zero=True)
+            ops.attention_ragged(q, ctx_k, ctx_v, a, rag["off"], rag["cnt"], S, ctx_mask, NEG_BERT, B, HEADS, Sk, k_rows=Sk)
+        elif ctx_var is not None:
             a = self.buf("att16_" + tag, (B * S, HID), torch.float16)
-            ops.attention_varlen(q, ctx_k, ctx_v, a, ctx_var[0], ctx_var[1], Sk, B, HEADS, S)
+            ops.attention_varlen(q, ctx_k, ctx_v, a, ctx_var[0], ctx_var[1], Sk, B, HEADS, S,
+                                 k_bias=ctx_var[2] if len(ctx_var) > 2 else None)
         else:
             a = self._attention(q, ctx_k, ctx_v, ctx_mask, NEG_BERT, B, S, Sk, "att16_" + tag)
         ops.linear_ln(a, self.W16(pre + ".output.dense.weight"), self.B32(pre + ".output.dense.bias"), x32,
                       self.P(pre + ".output.LayerNorm.weight"), self.P(pre + ".output.LayerNorm.bias"), self.config.layer_norm_eps,
-                      out_f32=x32, out_f16=x16)
+                      out_f32=x32, out_f16=x16, m_dev=md)
 
-    def _lxrt_layer(self, pre, x32, x16, x_mask, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None):
+    def _lxrt_layer(self, pre, x32, x16, x_mask, ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=None, rag=None):
         """GraphLXRTXLayer.forward (vilmodel.py:399-414): cross-attention, self-attention, FFN (all post-norm)."""
-        self._cross_post(x32, x16, pre + ".visual_attention", ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=ctx_var)
-        self._self_post(x32, x16, pre + ".visn_self_att", x_mask, B, S, tag)
-        self._ffn_post(x32, x16, pre + ".visn_inter", pre + ".visn_output", B * S, tag)
+        self._cross_post(x32, x16, pre + ".visual_attention", ctx_k, ctx_v, ctx_mask, B, S, Sk, tag, ctx_var=ctx_var, rag=rag)
+        self._self_post(x32, x16, pre + ".visn_self_att", x_mask, B, S, tag, rag=rag)
+        self._ffn_post(x32, x16, pre + ".visn_inter", pre + ".visn_output", x16.shape[0], tag, rag=rag)
 
-    def _prenorm_encoder(self, pre, n_layers, x32, x16, kmask, B, S, tag, first_norm_done=False):
+    def _prenorm_encoder(self, pre, n_layers, x32, x16, kmask, B, S, tag, first_norm_done=False, rag=None):
         """TransformerEncoder of forward_pre layers + final norm (models/transformer.py:60-87, 170-182).
         first_norm_done: x16 already holds layers.0.norm1(x32) (written by the kernel that produced x32)."""
-        rows = B * S
+        rows = x16.shape[0]
+        md = rag["m_dev"] if rag else None
         if not first_norm_done:
             self._ln(x32, "%s.layers.0.norm1" % pre, 1e-5, None, x16)
         for i in range(n_layers):
             q = "%s.layers.%d" % (pre, i)
-            qkv = self.buf("qkv16_" + tag, (rows, 3 * HID), torch.float16)
-            ops.linear(x16, self.W16(q + ".self_attn.in_proj_weight"), self.B32(q + ".self_attn.in_proj_bias"), out_f16=qkv)
-            a = self._attention(qkv[:, :HID], qkv[:, HID:2 * HID], qkv[:, 2 * HID:], kmask, NEG_INF, B, S, S, "att16_" + tag)
+            qkv = self.buf("qkv16_" + tag, (rows, 3 * HID), torch.float16, zero=True)
+            ops.linear(x16, self.W16(q + ".self_attn.in_proj_weight"), self.B32(q + ".self_attn.in_proj_bias"), out_f16=qkv, m_dev=md)
+            a = self._self_attention(qkv, kmask, NEG_INF, B, S, "att16_" + tag, rag)
             # x += out_proj(a); x16 = norm2(x)   (residual stream stays un-normalised: f32_raw)
             ops.linear_ln(a, self.W16(q + ".self_attn.out_proj.weight"), self.B32(q + ".self_attn.out_proj.bias"), x32,
-                          self.P(q + ".norm2.weight"), self.P(q + ".norm2.bias"), 1e-5, out_f32=x32, out_f16=x16, f32_raw=True)
-            h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16)
-            ops.linear(x16, self.W16(q + ".linear1.weight"), self.B32(q + ".linear1.bias"), out_f16=h, act=ops.ACT_GELU)
+                          self.P(q + ".norm2.weight"), self.P(q + ".norm2.bias"), 1e-5, out_f32=x32, out_f16=x16, f32_raw=True, m_dev=md)
+            h = self.buf("ffn16_" + tag, (rows, self.config.intermediate_size), torch.float16, zero=True)
+            ops.linear(x16, self.W16(q + ".linear1.weight"), self.B32(q + ".linear1.bias"), out_f16=h, act=ops.ACT_GELU, m_dev=md)
             if i + 1 < n_layers:      # x += linear2(h); x16 = norm1 of the next layer
                 nq = "%s.layers.%d" % (pre, i + 1)
                 ops.linear_ln(h, self.W16(q + ".linear2.weight"), self.B32(q + ".linear2.bias"), x32, self.P(nq + ".norm1.weight"),
-                              self.P(nq + ".norm1.bias"), 1e-5, out_f32=x32, out_f16=x16, f32_raw=True)
+                              self.P(nq + ".norm1.bias"), 1e-5, out_f32=x32, out_f16=x16, f32_raw=True, m_dev=md)
             else:                     # x = norm(x + linear2(h))  (the encoder's final LayerNorm, eps 1e-12)
                 ops.linear_ln(h, self.W16(q + ".linear2.weight"), self.B32(q + ".linear2.bias"), x32, self.P(pre + ".norm.weight"),
-                              self.P(pre + ".norm.bias"), 1e-12, out_f32=x32, out_f16=x16)
+                              self.P(pre + ".norm.bias"), 1e-12, out_f32=x32, out_f16=x16, m_dev=md)
 
     def _cls_head(self, pre, xs16, rows, tag):
         """ClsPrediction (vilmodel.py:663-674) -> raw logit per row.  `xs16` is the [hi | lo | hi] split of the fp32 input
@@ -755,6 +774,32 @@ class GlocalTextPathNavCMT(nn.Module):
             return dict(entry[1]) if isinstance(entry[1], dict) else entry[1]
         return self._device_forward(st, grid, dims, return_intermediates, False)
 
+    def _unpack_map(self, map32, m_off, m_info, cell_rank, gmap_mask, B, NC, G):
+        """Test / inspection only (host synchronisation): the packed map sequence scattered back to the reference's padded layout
+        [B, NC + G, 768] with its validity mask (vilmodel.py:813-838, quirk included: every flagged zero-vector slot receives the
+        representative row's result)."""
+        S = NC + G
+        off = m_off.cpu().numpy()
+        info = m_info.cpu().numpy()
+        cr = cell_rank.view(B, NC).cpu().numpy()
+        gm = gmap_mask.view(B, G).cpu().numpy()
+        C = int(info[0].max()) if B else 0
+        out = torch.zeros(B, S, HID, dtype=torch.float32, device=map32.device)
+        mask = torch.zeros(B, S, dtype=torch.uint8)
+        for b in range(B):
+            k, v = int(info[0, b]), int(info[1, b])
+            out[b, :k] = map32[off[b]: off[b] + k]
+            mask[b, :k] = 1
+            if v > k:
+                in_s = cr[b] >= 0
+                k2 = min(k + int(in_s[k:].sum()), C)
+                slots = [r for r in range(k, k2) if in_s[r]]
+                out[b, slots] = map32[off[b] + k]
+                mask[b, slots] = 1
+            out[b, NC:] = map32[off[b] + v: off[b] + v + G]
+            mask[b, NC:] = torch.from_numpy(gm[b].astype("uint8"))
+        return {"map_embeds": out, "map_masks": mask.to(map32.device)}
+
     def _fork_side(self, device):
         """Context manager that runs its body on this model's side stream, forked from the current stream (works eagerly and
         under CUDA-graph capture, where it becomes a parallel branch of the graph); `.join()` makes the current stream wait for
@@ -805,48 +850,88 @@ class GlocalTextPathNavCMT(nn.Module):
         ops.linear(pooled16, self.W16("grid_proj.weight"), self.B32("grid_proj.bias"), out_f32=proj32)
 
         # ---- map sequence = [grid cells ; gmap nodes]  (vilmodel.py:813-838)
-        map32 = self.buf("map32", (B * S, HID), f32)
-        map16 = self.buf("map16", (B * S, HID), f16)
-        map_mask = self.buf("map_mask", (B, S), u8)
-        # one launch: grid-cell rows (+ position embedding, compaction quirk), gmap rows (img + step + position embedding), both
-        # masks, and grid_encoder's first pre-norm LayerNorm (-> map16)
         ge = "global_encoder.gmap_pos_embeddings"
-        ops.map_inputs(proj32, grid.pos_fts, grid.cell_rank, grid.n_nonempty, self.Wt32("grid_pos_embeddings.0.weight"),
-                       self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
-                       self.P("grid_pos_embeddings.1.bias"), st["gmap_pos"], self.Wt32(ge + ".0.weight"), self.P(ge + ".0.bias"),
-                       self.P(ge + ".1.weight"), self.P(ge + ".1.bias"), st["gmap_img"],
-                       self.P("global_encoder.gmap_step_embeddings.weight"), st["gmap_step"], gmap_mask_u8,
-                       self.P("grid_encoder.layers.0.norm1.weight"), self.P("grid_encoder.layers.0.norm1.bias"), 1e-5,
-                       map32, map16, map_mask, B, NC, S)
+        ve = "local_encoder.vp_pos_embeddings"      # the vp tokens of x are computed by gridmm_fusion_inputs* below
+        gt = "grid_txt_encoder.x_layers.0"
         x32 = self._out("x32", (B * Q, HID), static_out)       # escapes as gmap_embeds / vp_embeds
         x16 = self.buf("x16", (B * Q, HID), f16)
-        ve = "local_encoder.vp_pos_embeddings"      # the vp tokens of x are computed by gridmm_fusion_inputs below
-        # the packed-context index of the fusion encoder only needs the masks: side stream, concurrent with the map encoders
-        kv_mask = self.buf("kv_mask", (B, KC), u8)
         q_mask = self.buf("q_mask", (B, Q), u8)
-        kv_pos = self.buf("kv_pos", (B * KC,), torch.int32)
         kv_off = self.buf("kv_off", (B + 1,), torch.int32)
         kv_cnt = self.buf("kv_cnt", (B,), torch.int32)
-        side = self._fork_side(map32.device)
-        with side:
-            ops.kv_index(map_mask, txt_mask_u8, kv_pos, kv_off, kv_cnt, B, S, L)
-
-        # ---- grid_encoder (pre-norm, key_padding_mask) and grid_txt_encoder (vilmodel.py:840-841)
-        self._prenorm_encoder("grid_encoder", 1, map32, map16, map_mask, B, S, "map", first_norm_done=True)
-        self._lxrt_layer(gt, map32, map16, map_mask, kv_txt[:, :HID], kv_txt[:, HID:], txt_mask_u8, B, S, L, "map")
+        kv16 = self.buf("kv16", (B * KC, HID), f16, zero=True)
+        map32 = self.buf("map32", (B * S, HID), f32, zero=True)
+        map16 = self.buf("map16", (B * S, HID), f16, zero=True)
         inter = {}
-        if return_intermediates:
-            inter["map_embeds"] = map32.view(B, S, HID).clone()
-            inter["map_masks"] = map_mask.clone()
+        vp_args = (st["vp_pos"], self.Wt32(ve + ".0.weight"), self.P(ve + ".0.bias"), self.P(ve + ".1.weight"), self.P(ve + ".1.bias"),
+                   st["vp_img"])
+        ragged = bool(getattr(self, "ragged_map", True)) and S <= 320      # gridmm_attention_ragged_f16 covers <= 320 keys
+        if ragged:
+            # PACKED map sequence (include/gridmm_b200.h): only the rows that matter -- the non-empty cells, ONE representative of the
+            # zero-vector slots the compaction quirk flags valid (key bias log z), all G gmap nodes -- back to back; every map-sized
+            # GEMM / attention launch below runs over m_off[B] rows (a device-side count) instead of B * S
+            m_off = self.buf("m_off", (B + 1,), torch.int32, zero=True)
+            m_info = self.buf("m_info", (4, B), torch.int32, zero=True)        # rows: k_b, k_b + q_b, rows per episode, z_b
+            m_logz = self.buf("m_logz", (B,), f32, zero=True)
+            m_goff = self.buf("m_goff", (B,), torch.int32, zero=True)
+            cell_of_rank = self.buf("cell_of_rank", (B, NC), torch.int32, zero=True)
+            m_kvalid = self.buf("m_kvalid", (B * S,), u8, zero=True)
+            m_kbias = self.buf("m_kbias", (B * S,), f32, zero=True)
+            kv_src = self.buf("kv_src", (B * KC,), torch.int32, zero=True)
+            kv_bias = self.buf("kv_bias", (B * KC,), f32, zero=True)
+            ops.map_index(grid.cell_rank, grid.n_nonempty, B, NC, G, m_off, m_info, m_logz, cell_of_rank, m_goff)
+            ops.map_inputs_packed(proj32, grid.pos_fts, cell_of_rank, m_off, m_info, m_logz, self.Wt32("grid_pos_embeddings.0.weight"),
+                                  self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
+                                  self.P("grid_pos_embeddings.1.bias"), st["gmap_pos"], self.Wt32(ge + ".0.weight"),
+                                  self.P(ge + ".0.bias"), self.P(ge + ".1.weight"), self.P(ge + ".1.bias"), st["gmap_img"],
+                                  self.P("global_encoder.gmap_step_embeddings.weight"), st["gmap_step"], gmap_mask_u8,
+                                  self.P("grid_encoder.layers.0.norm1.weight"), self.P("grid_encoder.layers.0.norm1.bias"), 1e-5,
+                                  map32, map16, m_kvalid, m_kbias, B, NC, G)
+            rag = {"m_dev": m_off[B:], "off": m_off, "cnt": m_info[2], "kvalid": m_kvalid, "kbias": m_kbias}
+            # the packed-context index of the fusion encoder only needs masks: side stream, concurrent with the map encoders
+            side = self._fork_side(map32.device)
+            with side:
+                ops.kv_index_packed(m_off, m_kvalid, m_kbias, txt_mask_u8, B, L, kv_src, kv_bias, kv_off, kv_cnt)
+            # ---- grid_encoder (pre-norm, key_padding_mask) and grid_txt_encoder (vilmodel.py:840-841)
+            self._prenorm_encoder("grid_encoder", 1, map32, map16, None, B, S, "map", first_norm_done=True, rag=rag)
+            self._lxrt_layer(gt, map32, map16, None, kv_txt[:, :HID], kv_txt[:, HID:], txt_mask_u8, B, S, L, "map", rag=rag)
+            if return_intermediates:
+                inter.update(self._unpack_map(map32, m_off, m_info, grid.cell_rank, gmap_mask_u8, B, NC, G))
+            # ---- fusion encoder inputs: queries [gmap'; vp], packed context [valid map rows ; valid text rows]
+            side.join()
+            ops.fusion_inputs_packed(map32, txt32, kv_src, kv_off, m_goff, gmap_mask_u8, vp_mask_u8, x32, x16, kv16, q_mask, vp_args,
+                                     B, L, G, V, B * KC)
+            ctx_var = (kv_off, kv_cnt, kv_bias)
+            grid_seg = (map32, 0, 0, G, None, m_goff)          # gmap rows of the packed map: first row of episode b = m_goff[b]
+        else:
+            map_mask = self.buf("map_mask", (B, S), u8)
+            # one launch: grid-cell rows (+ position embedding, compaction quirk), gmap rows (img + step + position embedding), both
+            # masks, and grid_encoder's first pre-norm LayerNorm (-> map16)
+            ops.map_inputs(proj32, grid.pos_fts, grid.cell_rank, grid.n_nonempty, self.Wt32("grid_pos_embeddings.0.weight"),
+                           self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
+                           self.P("grid_pos_embeddings.1.bias"), st["gmap_pos"], self.Wt32(ge + ".0.weight"), self.P(ge + ".0.bias"),
+                           self.P(ge + ".1.weight"), self.P(ge + ".1.bias"), st["gmap_img"],
+                           self.P("global_encoder.gmap_step_embeddings.weight"), st["gmap_step"], gmap_mask_u8,
+                           self.P("grid_encoder.layers.0.norm1.weight"), self.P("grid_encoder.layers.0.norm1.bias"), 1e-5,
+                           map32, map16, map_mask, B, NC, S)
+            kv_mask = self.buf("kv_mask", (B, KC), u8)
+            kv_pos = self.buf("kv_pos", (B * KC,), torch.int32)
+            side = self._fork_side(map32.device)
+            with side:
+                ops.kv_index(map_mask, txt_mask_u8, kv_pos, kv_off, kv_cnt, B, S, L)
+            self._prenorm_encoder("grid_encoder", 1, map32, map16, map_mask, B, S, "map", first_norm_done=True)
+            self._lxrt_layer(gt, map32, map16, map_mask, kv_txt[:, :HID], kv_txt[:, HID:], txt_mask_u8, B, S, L, "map")
+            if return_intermediates:
+                inter["map_embeds"] = map32.view(B, S, HID).clone()
+                inter["map_masks"] = map_mask.clone()
+            # The context is PACKED: masked rows (empty grid-cell slots, padded text: ~1/3 of the 296 rows per episode) get no K/V
+            # projection and no attention work; their attention weight would be exp(-10000) = 0 anyway.
+            side.join()
+            ops.fusion_inputs(map32, txt32, map_mask, txt_mask_u8, gmap_mask_u8, vp_mask_u8, x32, x16, kv16, kv_mask, q_mask, B, S, L, G,
+                              V, kv_pos=kv_pos, vp=vp_args)
+            ctx_var = (kv_off, kv_cnt)
+            grid_seg = (map32, S, NC, G, None)
 
         # ---- fusion encoder: queries [gmap'; vp], context [map; txt]  (vilmodel.py:843-856)
-        # The context is PACKED: masked rows (empty grid-cell slots, padded text: ~1/3 of the 296 rows per episode) get no K/V
-        # projection and no attention work; their attention weight would be exp(-10000) = 0 anyway.
-        kv16 = self.buf("kv16", (B * KC, HID), f16, zero=True)
-        side.join()
-        ops.fusion_inputs(map32, txt32, map_mask, txt_mask_u8, gmap_mask_u8, vp_mask_u8, x32, x16, kv16, kv_mask, q_mask, B, S, L, G, V,
-                          kv_pos=kv_pos, vp=(st["vp_pos"], self.Wt32(ve + ".0.weight"), self.P(ve + ".0.bias"),
-                                             self.P(ve + ".1.weight"), self.P(ve + ".1.bias"), st["vp_img"]))
         nx = cfg.num_x_layers
         le = "local_encoder.encoder.x_layers.%d"
         if mode == "mlm":
@@ -859,11 +944,16 @@ class GlocalTextPathNavCMT(nn.Module):
         ops.linear_rows(kv16, self.W16(*names_w), self.B32(*names_b), kvp, kv_off[B:])
         for i in range(nx):
             self._lxrt_layer(le % i, x32, x16, q_mask, kvp[:, 2 * HID * i: 2 * HID * i + HID],
-                             kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], kv_mask, B, Q, KC, "x", ctx_var=(kv_off, kv_cnt))
+                             kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], None, B, Q, KC, "x", ctx_var=ctx_var)
 
         if mode == "trunk":
             x3 = x32.view(B, Q, HID)
-            return {"gmap_embeds": x3[:, :G], "vp_embeds": x3[:, G:], "grid_gmap_embeds": map32.view(B, S, HID)[:, NC:].clone()}
+            if ragged:
+                rows = (m_goff.long()[:, None] + torch.arange(G, device=m_goff.device)[None, :]).reshape(-1)
+                grid_g = map32.index_select(0, rows).view(B, G, HID)
+            else:
+                grid_g = map32.view(B, S, HID)[:, NC:].clone()
+            return {"gmap_embeds": x3[:, :G], "vp_embeds": x3[:, G:], "grid_gmap_embeds": grid_g}
         # ---- heads and logit fusion (vilmodel.py:859-907)
         if ce_maxc:
             hg16 = self.buf("hg16", (B * G, 3 * HID), f16)
@@ -886,7 +976,8 @@ class GlocalTextPathNavCMT(nn.Module):
         hA = self.buf("heads_a16", (a_rows, 3 * HID), f16, zero=True)
         part = self.buf("heads_part", (out_rows, 36), f32)
         raw = self.buf("heads_raw", (out_rows, HID), f32)
-        segs = [(x32, Q, 0, G, a0["global"]), (x32, Q, G, V, a0["local"]), (map32, S, NC, G, a0["grid"])]
+        segs = [(x32, Q, 0, G, a0["global"]), (x32, Q, G, V, a0["local"]),
+                grid_seg[:4] + (a0["grid"],) + grid_seg[5:]]
         if cfg.glocal_fuse:
             segs += [(x32, Q, 0, 1, a0["fuse_g"]), (x32, Q, G, 1, a0["fuse_v"])]
         ops.head_rows(segs, B, hA)

@@ -21,8 +21,10 @@ def _chk(t, dtype, name):
         raise _lib.GridmmError("%s must be contiguous in its last dimension" % name)
 
 
-def linear(a16, w16, bias=None, residual=None, out_f32=None, out_f16=None, act=ACT_NONE):
-    """act(a16 @ w16.T + bias) + residual.  a16 [M,K] fp16 (row pitch = stride(0)), w16 [N,K] fp16."""
+def linear(a16, w16, bias=None, residual=None, out_f32=None, out_f16=None, act=ACT_NONE, m_dev=None):
+    """act(a16 @ w16.T + bias) + residual.  a16 [M,K] fp16 (row pitch = stride(0)), w16 [N,K] fp16.
+    m_dev: optional device int32 tensor, the number of rows to process (packed / ragged operand)."""
+    _chk(m_dev, torch.int32, "m_dev")
     _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w")
     _chk(bias, torch.float32, "bias"); _chk(residual, torch.float32, "residual")
     _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
@@ -32,11 +34,12 @@ def linear(a16, w16, bias=None, residual=None, out_f32=None, out_f16=None, act=A
     _lib.call("gridmm_linear_f16", a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, N, K,
               _lib.ptr(bias), _lib.ptr(residual), residual.stride(0) if residual is not None else 0,
               _lib.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
-              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, act, _lib.stream_ptr())
+              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, act, _lib.ptr(m_dev), _lib.stream_ptr())
 
 
-def linear_ln(a16, w16, bias, residual, gamma, beta, eps, out_f32=None, out_f16=None, f32_raw=False):
+def linear_ln(a16, w16, bias, residual, gamma, beta, eps, out_f32=None, out_f16=None, f32_raw=False, m_dev=None):
     """LayerNorm(a16 @ w16.T + bias + residual) in one kernel; out_f32 gets the un-normalised sum when f32_raw (pre-norm blocks)."""
+    _chk(m_dev, torch.int32, "m_dev")
     _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w"); _chk(bias, torch.float32, "bias")
     _chk(residual, torch.float32, "residual"); _chk(gamma, torch.float32, "gamma"); _chk(beta, torch.float32, "beta")
     _chk(out_f32, torch.float32, "out_f32"); _chk(out_f16, torch.float16, "out_f16")
@@ -46,7 +49,8 @@ def linear_ln(a16, w16, bias, residual, gamma, beta, eps, out_f32=None, out_f16=
     _lib.call("gridmm_linear_ln_f16", a16.data_ptr(), a16.stride(0), w16.data_ptr(), w16.stride(0), M, N, K, _lib.ptr(bias),
               _lib.ptr(residual), residual.stride(0) if residual is not None else 0, gamma.data_ptr(), beta.data_ptr(), float(eps),
               _lib.ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
-              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, int(bool(f32_raw)), _lib.stream_ptr())
+              _lib.ptr(out_f16), out_f16.stride(0) if out_f16 is not None else 0, int(bool(f32_raw)), _lib.ptr(m_dev),
+              _lib.stream_ptr())
 
 
 def attention(q, k, v, out, kmask, mask_neg, batch, heads, sq, sk, q_rows=None, k_rows=None):
@@ -108,13 +112,82 @@ def linear_rows(a16, w16, bias, out_f16, m_dev):
               out_f16.data_ptr(), out_f16.stride(0), m_dev.data_ptr(), _lib.stream_ptr())
 
 
-def attention_varlen(q, k, v, out, k_off, k_cnt, max_sk, batch, heads, sq, q_rows=None):
+def attention_varlen(q, k, v, out, k_off, k_cnt, max_sk, batch, heads, sq, q_rows=None, k_bias=None):
     for t_, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
         _chk(t_, torch.float16, n)
-    _chk(k_off, torch.int32, "k_off"); _chk(k_cnt, torch.int32, "k_cnt")
+    _chk(k_off, torch.int32, "k_off"); _chk(k_cnt, torch.int32, "k_cnt"); _chk(k_bias, torch.float32, "k_bias")
     _lib.call("gridmm_attention_varlen_f16", q.data_ptr(), q.stride(0), q_rows or sq, k.data_ptr(), k.stride(0), v.data_ptr(),
-              v.stride(0), k_off.data_ptr(), k_cnt.data_ptr(), max_sk, out.data_ptr(), out.stride(0), batch, heads, sq,
-              1.0 / math.sqrt(64.0), _lib.stream_ptr())
+              v.stride(0), k_off.data_ptr(), k_cnt.data_ptr(), max_sk, _lib.ptr(k_bias), out.data_ptr(), out.stride(0), batch, heads,
+              sq, 1.0 / math.sqrt(64.0), _lib.stream_ptr())
+
+
+def attention_ragged(q, k, v, out, q_off, q_cnt, max_sq, kmask, mask_neg, batch, heads, max_sk, k_off=None, k_cnt=None, k_rows=0,
+                     kbias=None):
+    """tcgen05 attention over packed query rows (rows q_off[b] .. + q_cnt[b] of q / out); keys packed too (k_off / k_cnt, kmask and
+    kbias indexed by packed row) or regular (k_rows rows per episode, kmask [batch, max_sk])."""
+    for t_, n in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _chk(t_, torch.float16, n)
+    for t_, n in ((q_off, "q_off"), (q_cnt, "q_cnt"), (k_off, "k_off"), (k_cnt, "k_cnt")):
+        _chk(t_, torch.int32, n)
+    _chk(kmask, torch.uint8, "kmask"); _chk(kbias, torch.float32, "kbias")
+    _lib.call("gridmm_attention_ragged_f16", q.data_ptr(), q.stride(0), q_off.data_ptr(), q_cnt.data_ptr(), max_sq, q.shape[0],
+              k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _lib.ptr(k_off), _lib.ptr(k_cnt), k_rows, max_sk, k.shape[0],
+              kmask.data_ptr(), _lib.ptr(kbias), float(mask_neg), out.data_ptr(), out.stride(0), batch, heads, 1.0 / math.sqrt(64.0),
+              _lib.stream_ptr())
+
+
+def map_index(cell_rank, n_nonempty, batch, n_cells, G, m_off, m_info, m_logz, cell_of_rank, m_goff):
+    for t_, n in ((cell_rank, "cell_rank"), (n_nonempty, "n_nonempty"), (m_off, "m_off"), (m_info, "m_info"),
+                  (cell_of_rank, "cell_of_rank"), (m_goff, "m_goff")):
+        _chk(t_, torch.int32, n)
+    _chk(m_logz, torch.float32, "m_logz")
+    _lib.call("gridmm_map_index", cell_rank.data_ptr(), n_nonempty.data_ptr(), batch, n_cells, G, m_off.data_ptr(), m_info.data_ptr(),
+              m_logz.data_ptr(), cell_of_rank.data_ptr(), m_goff.data_ptr(), _lib.stream_ptr())
+
+
+def map_inputs_packed(proj, pos_fts, cell_of_rank, m_off, m_info, m_logz, w, bias, gamma, beta, gmap_pos, gw, gbias, ggamma, gbeta,
+                      gmap_img, step_table, step_ids, gmap_mask, norm_gamma, norm_beta, norm_eps, map_f32, map_f16, kvalid, kbias,
+                      batch, n_cells, G):
+    _chk(proj, torch.float32, "proj"); _chk(pos_fts, torch.float32, "pos_fts"); _chk(gmap_pos, torch.float32, "gmap_pos")
+    _chk(gmap_img, torch.float32, "gmap_img"); _chk(step_ids, torch.int64, "step_ids"); _chk(gmap_mask, torch.uint8, "gmap_mask")
+    _chk(map_f32, torch.float32, "map_f32"); _chk(map_f16, torch.float16, "map_f16"); _chk(kvalid, torch.uint8, "kvalid")
+    _chk(kbias, torch.float32, "kbias")
+    for t_ in (cell_of_rank, m_off, m_info):
+        _chk(t_, torch.int32, "map index")
+    for t_ in (gmap_pos, gmap_img, gw, map_f32, map_f16):
+        assert t_.is_contiguous()
+    _lib.call("gridmm_map_inputs_packed", proj.data_ptr(), pos_fts.data_ptr(), cell_of_rank.data_ptr(), m_off.data_ptr(),
+              m_info.data_ptr(), m_logz.data_ptr(), w.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+              gmap_pos.data_ptr(), gmap_pos.shape[1], gw.data_ptr(), gbias.data_ptr(), ggamma.data_ptr(), gbeta.data_ptr(),
+              gmap_img.data_ptr(), step_table.data_ptr(), step_ids.data_ptr(), gmap_mask.data_ptr(), norm_gamma.data_ptr(),
+              norm_beta.data_ptr(), float(norm_eps), map_f32.data_ptr(), map_f16.data_ptr(), kvalid.data_ptr(), kbias.data_ptr(),
+              batch, n_cells, G, HID, _lib.stream_ptr())
+
+
+def kv_index_packed(m_off, kvalid, kbias, txt_mask, batch, L, kv_src, kv_bias, kv_off, kv_cnt):
+    for t_ in (m_off, kv_src, kv_off, kv_cnt):
+        _chk(t_, torch.int32, "kv index")
+    _chk(kvalid, torch.uint8, "kvalid"); _chk(txt_mask, torch.uint8, "txt_mask"); _chk(kbias, torch.float32, "kbias")
+    _chk(kv_bias, torch.float32, "kv_bias")
+    _lib.call("gridmm_kv_index_packed", m_off.data_ptr(), kvalid.data_ptr(), kbias.data_ptr(), txt_mask.data_ptr(), batch, L,
+              kv_src.data_ptr(), kv_bias.data_ptr(), kv_off.data_ptr(), kv_cnt.data_ptr(), _lib.stream_ptr())
+
+
+def fusion_inputs_packed(map32, txt32, kv_src, kv_off, m_goff, gmap_mask, vp_mask, x32, x16, kv16, q_mask, vp, batch, L, G, V,
+                         kv_rows_max):
+    """vp = (vp_pos [B*V, kin], w_t [kin, 768], bias, gamma, beta, vp_img [B*V, 768])."""
+    for t_, n in ((gmap_mask, "gmap_mask"), (vp_mask, "vp_mask"), (q_mask, "q_mask")):
+        _chk(t_, torch.uint8, n)
+    _chk(map32, torch.float32, "map32"); _chk(txt32, torch.float32, "txt32"); _chk(x32, torch.float32, "x32")
+    _chk(x16, torch.float16, "x16"); _chk(kv16, torch.float16, "kv16")
+    for t_ in (kv_src, kv_off, m_goff):
+        _chk(t_, torch.int32, "index")
+    for t_ in (map32, txt32, x32, x16, kv16, vp[0], vp[5]):
+        assert t_.is_contiguous()
+    _lib.call("gridmm_fusion_inputs_packed", map32.data_ptr(), txt32.data_ptr(), kv_src.data_ptr(), kv_off.data_ptr(), m_goff.data_ptr(),
+              gmap_mask.data_ptr(), vp_mask.data_ptr(), x32.data_ptr(), x16.data_ptr(), kv16.data_ptr(), q_mask.data_ptr(),
+              vp[0].data_ptr(), vp[0].shape[1], vp[1].data_ptr(), vp[2].data_ptr(), vp[3].data_ptr(), vp[4].data_ptr(), vp[5].data_ptr(),
+              batch, L, G, V, kv_rows_max, HID, _lib.stream_ptr())
 
 
 def fusion_inputs(map32, txt32, map_mask, txt_mask, gmap_mask, vp_mask, x32, x16, kv16, kv_mask, q_mask, batch, S, L, G, V, kv_pos=None,
@@ -189,7 +262,8 @@ def nav_logits(raw_global, raw_grid, raw_local, raw_obj, raw_fuse, gmap_masks, g
 
 
 def head_rows(segs, batch, out_f16):
-    """segs: list of (x fp32 [*, 768], in_rows_per_b, in_off, rows_per_b, out_row0) -> [hi | lo | hi] rows of out_f16 [*, 2304]."""
+    """segs: list of (x fp32 [*, 768], in_rows_per_b, in_off, rows_per_b, out_row0[, row_off]) -> [hi | lo | hi] rows of out_f16
+    [*, 2304]; row_off: optional int32 device tensor [batch], first input row of every episode (packed source)."""
     import ctypes
     n = len(segs)
     _chk(out_f16, torch.float16, "out_f16")
@@ -200,8 +274,13 @@ def head_rows(segs, batch, out_f16):
     ldx, irb, ioff, rpb, or0 = (mk([sgm[0].stride(0) for sgm in segs]), mk([sgm[1] for sgm in segs]), mk([sgm[2] for sgm in segs]),
                                 mk([sgm[3] for sgm in segs]), mk([sgm[4] for sgm in segs]))
     cast = lambda a: ctypes.cast(a, ctypes.c_void_p)                   # noqa: E731
-    _lib.call("gridmm_head_rows", n, cast(xs), cast(ldx), cast(irb), cast(ioff), cast(rpb), cast(or0), batch, out_f16.data_ptr(),
-              out_f16.stride(0), HID, _lib.stream_ptr())
+    offs = [(sgm[5] if len(sgm) > 5 else None) for sgm in segs]
+    for o_ in offs:
+        _chk(o_, torch.int32, "row_off")
+    roff = (ctypes.c_void_p * n)(*[(o_.data_ptr() if o_ is not None else None) for o_ in offs])
+    _lib.call("gridmm_head_rows", n, cast(xs), cast(ldx), cast(irb), cast(ioff), cast(rpb), cast(or0),
+              cast(roff) if any(o_ is not None for o_ in offs) else None, batch, out_f16.data_ptr(), out_f16.stride(0), HID,
+              _lib.stream_ptr())
 
 
 def cls_heads(a16, w16, groups, tiles_m, bias, gw2, grp, part, raw):

@@ -98,7 +98,9 @@ int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, const int* sl
  * N % 128 == 0, K % 64 == 0; act: 0 none, 1 GELU(erf), 2 ReLU; either output may be NULL. */
 int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                       const float* residual, int ld_res, float* out_f32, int ld_f32, void* out_f16, int ld_f16, int act,
-                      cudaStream_t stream);
+                      const int* m_dev, cudaStream_t stream);
+/* m_dev (here and in gridmm_linear_ln_f16): optional DEVICE int, the number of rows to process (<= M) when only the GPU knows it
+ * (packed / ragged operands); the launch is sized for M, row tiles past *m_dev do nothing.  NULL = M rows. */
 
 /* nn.Linear(K -> 768) + residual + LayerNorm in one kernel (a cluster of 2 or 6 CTAs per 128-row tile, row statistics merged
  * through distributed shared memory):  v = a . w^T + bias + residual;  y = LayerNorm(v; gamma, beta, eps).
@@ -107,7 +109,7 @@ int gridmm_linear_f16(const void* a, int lda, const void* w, int ldw, int M, int
  * out_f16 = y).  N must be 768, K % 64 == 0; out_f32 may alias residual. */
 int gridmm_linear_ln_f16(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias,
                          const float* residual, int ld_res, const float* gamma, const float* beta, float eps, float* out_f32,
-                         int ld_f32, void* out_f16, int ld_f16, int f32_raw, cudaStream_t stream);
+                         int ld_f32, void* out_f16, int ld_f16, int f32_raw, const int* m_dev, cudaStream_t stream);
 
 /* gridmm_grid_assemble + the gmap tokens (rows [n_cells, seq) of the map sequence: gmap_img + step_table[step_ids] +
  * LN(Linear(gmap_pos)), vilmodel.py:828-831; mask from gmap_mask) + the first pre-norm LayerNorm of grid_encoder
@@ -132,8 +134,47 @@ int gridmm_kv_index(const unsigned char* map_mask, const unsigned char* txt_mask
 int gridmm_linear_f16_rows(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, void* out_f16,
                            int ld_f16, const int* m_dev, cudaStream_t stream);
 int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
-                                const int* k_off, const int* k_cnt, int max_sk, void* o, int ldo, int batch, int heads, int sq,
-                                float scale, cudaStream_t stream);
+                                const int* k_off, const int* k_cnt, int max_sk, const float* k_bias, void* o, int ldo, int batch,
+                                int heads, int sq, float scale, cudaStream_t stream);
+/* k_bias: optional f32 per packed key row, added to that key's scores (log multiplicity of a de-duplicated key), or NULL. */
+
+/* ---- packed ("ragged") MAP sequence ---------------------------------------------------------------------------
+ * The reference pads every episode's map sequence [grid cells ; gmap nodes] to the batch maximum (vilmodel.py:813-838: on
+ * BASELINE config 2 about 40 % of the padded rows are masked).  Here the rows that matter are packed back to back and every
+ * map-sized launch (grid_encoder, grid_txt_encoder: transformer.py:170-182, vilmodel.py:399-414) runs over them only:
+ *   episode b owns packed rows m_off[b] .. m_off[b+1]-1 = [ k_b non-empty cells (rank order) | q_b | G gmap nodes ]
+ * q_b in {0,1} is ONE representative of the z_b zero-vector slots that the reference's mask-aliasing quirk flags valid
+ * (gridmm_grid_assemble); wherever it acts as an attention key its score gets + log(z_b) (z identical keys: exact).
+ * gridmm_map_index (one CTA): m_off [batch+1], m_info [4][batch] = rows of k_b, k_b + q_b, rows per episode, z_b, m_logz [batch],
+ *   cell_of_rank [batch][n_cells] (inverse of cell_rank), m_goff [batch] = first gmap row of every episode.
+ * gridmm_map_inputs_packed: gridmm_map_inputs over the packed rows; kvalid [rows] u8 (1 = valid key: cells, valid gmap nodes),
+ *   kbias [rows] f32 (log z_b on the representative row, else 0).
+ * gridmm_attention_ragged_f16: tcgen05 attention with per-episode query rows q_off[b] .. + q_cnt[b] (also the rows of o); keys
+ *   ragged too (k_off / k_cnt; kmask / kbias indexed by packed key row) or regular (k_off = k_cnt = NULL: rows b * k_rows .. + max_sk,
+ *   kmask [batch, max_sk]); max_sq / max_sk bound the per-episode counts (<= 320 keys), q_total / k_total = rows of the buffers.
+ * gridmm_kv_index_packed / gridmm_fusion_inputs_packed: the fusion encoder's packed context [valid map rows ; valid text rows] and
+ *   its queries [gmap' ; vp] read from the packed map (kv_src[r] >= 0: packed map row, < 0: text row -1 - (b * L + l);
+ *   kv_bias[r] = that key's score bias). */
+int gridmm_map_index(const int* cell_rank, const int* n_nonempty, int batch, int n_cells, int G, int* m_off, int* m_info,
+                     float* m_logz, int* cell_of_rank, int* m_goff, cudaStream_t stream);
+int gridmm_map_inputs_packed(const float* proj, const float* pos_fts, const int* cell_of_rank, const int* m_off, const int* m_info,
+                             const float* m_logz, const float* w, const float* bias, const float* gamma, const float* beta,
+                             const float* gmap_pos, int gmap_kin, const float* gw, const float* gbias, const float* ggamma,
+                             const float* gbeta, const float* gmap_img, const float* step_table, const long long* step_ids,
+                             const unsigned char* gmap_mask, const float* norm_gamma, const float* norm_beta, float norm_eps,
+                             float* map_f32, void* map_f16, unsigned char* kvalid, float* kbias, int batch, int n_cells, int G,
+                             int hidden, cudaStream_t stream);
+int gridmm_attention_ragged_f16(const void* q, int ldq, const int* q_off, const int* q_cnt, int max_sq, long long q_total,
+                                const void* k, int ldk, const void* v, int ldv, const int* k_off, const int* k_cnt, int k_rows,
+                                int max_sk, long long k_total, const unsigned char* kmask, const float* kbias, float mask_neg,
+                                void* o, int ldo, int batch, int heads, float scale, cudaStream_t stream);
+int gridmm_kv_index_packed(const int* m_off, const unsigned char* kvalid, const float* kbias, const unsigned char* txt_mask, int batch,
+                           int L, int* kv_src, float* kv_bias, int* kv_off, int* kv_cnt, cudaStream_t stream);
+int gridmm_fusion_inputs_packed(const float* map32, const float* txt32, const int* kv_src, const int* kv_off, const int* m_goff,
+                                const unsigned char* gmap_mask, const unsigned char* vp_mask, float* x32, void* x16, void* kv16,
+                                unsigned char* q_mask, const float* vp_pos, int vp_kin, const float* vp_w, const float* vp_bias,
+                                const float* vp_gamma, const float* vp_beta, const float* vp_img, int batch, int L, int G, int V,
+                                int kv_rows_max, int hidden, cudaStream_t stream);
 
 /* Inputs of the fusion encoder (vilmodel.py:828-833, 843-850) in one launch: x[b, :G] = map[b, S-G:] (fp32 + fp16),
  * x[b, G:] = vp_img + LN(Linear(vp_pos)) when vp_pos is given (vp_w = TRANSPOSED weight [vp_kin, 768]; with vp_pos NULL rows G..
@@ -157,8 +198,10 @@ int gridmm_fusion_inputs(const float* map32, const float* txt32, const unsigned 
  *   head from fuse_raw rows row_fuse_g + b, row_fuse_v + b) and fuses the logits exactly like gridmm_nav_logits;
  *   row_obj < 0 / fuse_raw NULL disable the object head / dynamic fusion. */
 int gridmm_head_rows(int nseg, const float* const* x, const int* ldx, const int* in_rows_per_b, const int* in_off,
-                     const int* rows_per_b, const int* out_row0, int batch, void* out_f16, int ld_f16, int hidden,
-                     cudaStream_t stream);
+                     const int* rows_per_b, const int* out_row0, const int* const* row_off, int batch, void* out_f16, int ld_f16,
+                     int hidden, cudaStream_t stream);
+/* row_off: NULL, or a host array of nseg device pointers (each NULL or int[batch]): first input row of every episode of that
+ * segment (a packed / ragged source: the gmap rows of the packed map sequence), replacing b * in_rows_per_b[i]. */
 int gridmm_cls_heads_f16(const void* a, int lda, long long a_rows, const void* w, int ldw, int groups, int tiles_m, int N, int K,
                          const float* bias, const float* gw2, const int* grp, float* cls_part, float* cls_raw,
                          cudaStream_t stream);

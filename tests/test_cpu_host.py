@@ -273,8 +273,15 @@ def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
     B, G, V = ep_kw["batch"], nav_kw["gmap_len"], 1 + nav_kw["n_views"]
     assert out["fused_logits"].shape == (B, G) and out["local_logits"].shape == (B, V) and out["obj_logits"] is None
     assert out["gmap_embeds"].shape == (B, G, 768) and out["vp_embeds"].shape == (B, V, 768)
-    # cell_sort (list path only) + the 57 launches after the grid build = the 58-launch step of bench.py, where grid_update replaces cell_sort
-    assert calls.count("cell_sort") == 1 and len(calls) == 58, (len(calls), calls)
+    # cell_sort (list path only) + the 58 launches after the grid build = the 59-launch step of bench.py, where grid_update replaces
+    # cell_sort (+ one gridmm_copy_segments staging launch there); gridmm_map_index is the launch the packed map sequence adds
+    assert calls.count("cell_sort") == 1 and len(calls) == 59, (len(calls), calls)
+    assert calls.count("map_index") == 1 and calls.count("map_inputs_packed") == 1 and calls.count("attention_ragged") == 3
+    model.ragged_map = False                    # the padded layout (used for map sequences longer than 320 rows) stays available
+    calls.clear()
+    model("navigation", nav)
+    assert len(calls) == 58 and calls.count("map_inputs") == 1 and "map_index" not in calls
+    model.ragged_map = True
     assert calls.count("linear_ln") == 17 and calls.count("pool") == 1 and calls.count("cls_heads") == 1
     calls.clear()
     inter = model("navigation", nav, return_intermediates=True)

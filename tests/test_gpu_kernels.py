@@ -439,3 +439,169 @@ def test_kv_index_and_varlen_attention():
     assert (o[:n].float() - want).abs().max().item() < 4e-3 * max(1.0, want.abs().max().item())
     tail = ((n + 255) // 256) * 256           # rows of tiles that hold no valid row stay untouched
     assert (o[tail:] == 7.0).all()
+
+
+@pytest.mark.parametrize("B,S,L,keys", [(5, 216, 80, "self"), (5, 216, 80, "text"), (32, 216, 80, "self"), (3, 300, 250, "self"),
+                                        (3, 300, 250, "text"), (2, 40, 24, "self")])
+def test_attention_ragged(B, S, L, keys):
+    """gridmm_attention_ragged_f16: packed query rows (and, for self-attention, packed keys with a validity mask and a per-key
+    score bias = log multiplicity of a de-duplicated key) against plain fp32 attention per episode."""
+    from gridmm_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 1000 + S + L)
+    cnt = torch.randint(max(1, S // 3), S + 1, (B,), generator=g).int()
+    cnt[0] = S
+    off = torch.zeros(B + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(cnt, 0)
+    total = int(off[-1])
+    rows = B * S
+    q = torch.zeros(rows, 768, dtype=torch.float16); q[:total] = torch.randn(total, 768, generator=g).half()
+    out = torch.full((rows, 768), 3.0, dtype=torch.float16, device=dev)
+    for neg in (-10000.0, float("-inf")):
+        if keys == "self":
+            kv = torch.zeros(rows, 1536, dtype=torch.float16); kv[:total] = torch.randn(total, 1536, generator=g).half()
+            kvalid = (torch.rand(rows, generator=g) < 0.8).to(torch.uint8)
+            kvalid[off[:-1].long()] = 1                                          # at least one valid key per episode
+            kbias = torch.where(torch.rand(rows, generator=g) < 0.1, torch.rand(rows, generator=g) * 3.0, torch.zeros(rows))
+            ops.attention_ragged(q.to(dev), kv[:, :768].to(dev), kv[:, 768:].to(dev), out, off.to(dev), cnt.to(dev), S, kvalid.to(dev), neg,
+                                 B, 12, S, k_off=off.to(dev), k_cnt=cnt.to(dev), kbias=kbias.to(dev))
+        else:
+            kv = torch.randn(B * L, 1536, generator=g).half()
+            lens = torch.randint(1, L + 1, (B,), generator=g); lens[0] = L
+            tmask = (torch.arange(L)[None, :] < lens[:, None]).to(torch.uint8)
+            ops.attention_ragged(q.to(dev), kv[:, :768].to(dev), kv[:, 768:].to(dev), out, off.to(dev), cnt.to(dev), S, tmask.to(dev), neg,
+                                 B, 12, L, k_rows=L)
+        torch.cuda.synchronize()
+        got = out.float().cpu()
+        for b in range(B):
+            r0, n = int(off[b]), int(cnt[b])
+            qh = q[r0:r0 + n].float().view(n, 12, 64).permute(1, 0, 2)
+            if keys == "self":
+                kk, vv = kv[r0:r0 + n, :768], kv[r0:r0 + n, 768:]
+                add = torch.where(kvalid[r0:r0 + n] > 0, kbias[r0:r0 + n], torch.full((n,), neg))
+            else:
+                kk, vv = kv[b * L:(b + 1) * L, :768], kv[b * L:(b + 1) * L, 768:]
+                add = torch.zeros(L).masked_fill(tmask[b] == 0, neg)
+            kh = kk.float().view(-1, 12, 64).permute(1, 0, 2)
+            vh = vv.float().view(-1, 12, 64).permute(1, 0, 2)
+            ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0 + add[None, None, :], -1) @ vh).permute(1, 0, 2).reshape(n, 768)
+            err = (got[r0:r0 + n] - ref).abs().max().item()
+            assert err < 4e-3, "b=%d neg=%s err=%.3e" % (b, neg, err)
+        assert (got[total:] == 3.0).all()                # rows past the packed batch are never written
+
+
+def test_linear_device_row_count():
+    """m_dev: the GEMM kernels process the first *m_dev rows only (packed operand whose size only the GPU knows); every epilogue
+    variant of gridmm_linear_f16 and both cluster shapes of gridmm_linear_ln_f16."""
+    from gridmm_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(77)
+    M, K = 6912, 768
+    a = torch.randn(M, K, generator=g).half().to(dev)
+    res = torch.randn(M, 768, generator=g).to(dev)
+    gamma, beta = (torch.rand(768, generator=g) + 0.5).to(dev), torch.randn(768, generator=g).to(dev)
+    for n_rows in (4500, 129, 1, 6912, 1800):
+        md = torch.tensor([n_rows], dtype=torch.int32, device=dev)
+        for N, act in ((2304, ops.ACT_NONE), (3072, ops.ACT_GELU), (768, ops.ACT_NONE)):
+            w = (torch.randn(N, K, generator=g) * 0.03).half().to(dev)
+            bias = torch.randn(N, generator=g).to(dev)
+            o = torch.full((M, N), 5.0, device=dev, dtype=torch.float16)
+            full = torch.empty(M, N, device=dev, dtype=torch.float16)
+            ops.linear(a, w, bias, out_f16=o, act=act, m_dev=md)
+            ops.linear(a, w, bias, out_f16=full, act=act)
+            torch.cuda.synchronize()
+            assert torch.equal(o[:n_rows], full[:n_rows])                      # row results do not depend on the row count
+            assert (o[n_rows:] == 5.0).all()
+        w = (torch.randn(768, K, generator=g) * 0.03).half().to(dev)
+        bias = torch.randn(768, generator=g).to(dev)
+        o32 = torch.full((M, 768), 5.0, device=dev); o16 = torch.full((M, 768), 5.0, device=dev, dtype=torch.float16)
+        f32 = torch.empty(M, 768, device=dev); f16 = torch.empty(M, 768, device=dev, dtype=torch.float16)
+        ops.linear_ln(a, w, bias, res, gamma, beta, 1e-12, out_f32=o32, out_f16=o16, m_dev=md)
+        ops.linear_ln(a, w, bias, res, gamma, beta, 1e-12, out_f32=f32, out_f16=f16)
+        torch.cuda.synchronize()
+        assert torch.equal(o32[:n_rows], f32[:n_rows]) and torch.equal(o16[:n_rows], f16[:n_rows])
+        assert (o32[n_rows:] == 5.0).all() and (o16[n_rows:] == 5.0).all()
+
+
+def test_packed_map_inputs_equal_padded():
+    """gridmm_map_index + gridmm_map_inputs_packed against gridmm_map_inputs (the padded layout with the reference's compaction quirk):
+    same rows, the quirk's zero-vector slots represented once with key bias log z, all gmap rows kept; and the packed fusion context
+    (gridmm_kv_index_packed / gridmm_fusion_inputs_packed) holds the rows of the padded one up to that de-duplication."""
+    from gridmm_b200 import ops
+    dev = _dev()
+    B, T, G, L, V = 9, 4, 11, 30, 37
+    NC, S = 196, 196 + 11
+    ep = synth.make_episodes(B, T, seed=321, dim=768)
+    ep["depth_sub"][3] = 0                                    # an episode without any valid point
+    gb, grid, _ = _run_builder(ep)
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dev)      # noqa: E731
+    proj = rnd(B * NC, 768)
+    gw, gb_, gg, gbt = rnd(5, 768), rnd(768), rnd(768), rnd(768)
+    mw, mb, mg, mbt = rnd(7, 768), rnd(768), rnd(768), rnd(768)
+    ng, nb = rnd(768), rnd(768)
+    gmap_pos, gmap_img, table = rnd(B * G, 7), rnd(B * G, 768), rnd(100, 768)
+    step_ids = torch.randint(0, 100, (B * G,), generator=g).to(dev)
+    gmask = (torch.rand(B, G, generator=g) < 0.7).to(torch.uint8).to(dev); gmask[:, 0] = 1
+    map32 = torch.zeros(B * S, 768, device=dev); map16 = torch.zeros(B * S, 768, device=dev, dtype=torch.float16)
+    map_mask = torch.zeros(B, S, dtype=torch.uint8, device=dev)
+    ops.map_inputs(proj, grid.pos_fts, grid.cell_rank, grid.n_nonempty, gw, gb_, gg, gbt, gmap_pos, mw, mb, mg, mbt, gmap_img, table,
+                   step_ids, gmask, ng, nb, 1e-5, map32, map16, map_mask, B, NC, S)
+    i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)      # noqa: E731
+    m_off, m_info, m_goff, cor = i32(B + 1), i32(4, B), i32(B), i32(B, NC)
+    m_logz = torch.zeros(B, device=dev)
+    p32 = torch.zeros(B * S, 768, device=dev); p16 = torch.zeros(B * S, 768, device=dev, dtype=torch.float16)
+    kvalid = torch.zeros(B * S, dtype=torch.uint8, device=dev); kbias = torch.zeros(B * S, device=dev)
+    ops.map_index(grid.cell_rank, grid.n_nonempty, B, NC, G, m_off, m_info, m_logz, cor, m_goff)
+    ops.map_inputs_packed(proj, grid.pos_fts, cor, m_off, m_info, m_logz, gw, gb_, gg, gbt, gmap_pos, mw, mb, mg, mbt, gmap_img, table,
+                          step_ids, gmask, ng, nb, 1e-5, p32, p16, kvalid, kbias, B, NC, G)
+    torch.cuda.synchronize()
+    off, info = m_off.cpu().numpy(), m_info.cpu().numpy()
+    mm = map_mask.cpu().numpy().astype(bool)
+    k_all = grid.n_nonempty.cpu().numpy()
+    pad32, pad16 = map32.view(B, S, 768), map16.view(B, S, 768)
+    for b in range(B):
+        k, v, n, z = info[:, b]
+        assert k == k_all[b] and n == v + G and off[b + 1] - off[b] == n and int(m_goff[b]) == off[b] + v
+        assert z == mm[b, k:NC].sum() and v == k + (1 if z > 0 else 0)
+        r0 = off[b]
+        assert torch.equal(p32[r0:r0 + k], pad32[b, :k]) and torch.equal(p16[r0:r0 + k], pad16[b, :k])
+        assert torch.equal(p32[r0 + v:r0 + n], pad32[b, NC:]) and torch.equal(p16[r0 + v:r0 + n], pad16[b, NC:])
+        assert (kvalid[r0:r0 + v] == 1).all() and torch.equal(kvalid[r0 + v:r0 + n], gmask[b])
+        if z > 0:
+            slot = k + int(np.argmax(mm[b, k:NC]))           # any flagged zero-vector slot of the padded layout
+            assert p32[r0 + k].abs().max().item() == 0 and torch.equal(p16[r0 + k], pad16[b, slot])
+            assert abs(float(kbias[r0 + k]) - np.log(z)) < 1e-6
+        assert float(kbias[r0:r0 + k].abs().max()) == 0 if k else True
+    # packed fusion context
+    KC = S + L
+    txt32 = rnd(B * L, 768)
+    tmask = (torch.arange(L)[None, :] < torch.randint(5, L + 1, (B, 1), generator=g)).to(torch.uint8).to(dev)
+    vmask = torch.ones(B, V, dtype=torch.uint8, device=dev)
+    kv_src, kv_off, kv_cnt = i32(B * KC), i32(B + 1), i32(B)
+    kv_bias = torch.zeros(B * KC, device=dev)
+    ops.kv_index_packed(m_off, kvalid, kbias, tmask, B, L, kv_src, kv_bias, kv_off, kv_cnt)
+    x32 = torch.zeros(B * (G + V), 768, device=dev); x16 = torch.zeros(B * (G + V), 768, device=dev, dtype=torch.float16)
+    kv16 = torch.zeros(B * KC, 768, device=dev, dtype=torch.float16)
+    qm = torch.zeros(B, G + V, dtype=torch.uint8, device=dev)
+    vp = (rnd(B * V, 14), rnd(14, 768), rnd(768), rnd(768), rnd(768), rnd(B * V, 768))
+    ops.fusion_inputs_packed(p32, txt32, kv_src, kv_off, m_goff, gmask, vmask, x32, x16, kv16, qm, vp, B, L, G, V, B * KC)
+    # padded reference of the same inputs
+    kv_pos, kv_off2, kv_cnt2 = i32(B * KC), i32(B + 1), i32(B)
+    ops.kv_index(map_mask, tmask, kv_pos, kv_off2, kv_cnt2, B, S, L)
+    x32b = torch.zeros_like(x32); x16b = torch.zeros_like(x16); kv16b = torch.zeros_like(kv16)
+    kvm = torch.zeros(B, KC, dtype=torch.uint8, device=dev); qmb = torch.zeros_like(qm)
+    ops.fusion_inputs(map32, txt32, map_mask, tmask, gmask, vmask, x32b, x16b, kv16b, kvm, qmb, B, S, L, G, V, kv_pos=kv_pos, vp=vp)
+    torch.cuda.synchronize()
+    assert torch.equal(x32, x32b) and torch.equal(x16, x16b) and torch.equal(qm, qmb)
+    o1, c1, o2, c2 = kv_off.cpu().numpy(), kv_cnt.cpu().numpy(), kv_off2.cpu().numpy(), kv_cnt2.cpu().numpy()
+    for b in range(B):
+        k, v, n, z = info[:, b]
+        assert c1[b] == c2[b] - max(z - 1, 0)
+        a = kv16[o1[b]:o1[b] + c1[b]]; ref = kv16b[o2[b]:o2[b] + c2[b]]
+        assert torch.equal(a[:k], ref[:k])
+        assert torch.equal(a[v:], ref[k + z:])               # valid gmap rows, then the valid text rows
+        bias = kv_bias[o1[b]:o1[b] + c1[b]]
+        if z > 0:
+            assert a[k].abs().max().item() == 0 and abs(float(bias[k]) - np.log(z)) < 1e-6
+        assert float(bias.abs().sum()) == (np.log(z) if z > 1 else 0.0) or abs(float(bias.abs().sum()) - np.log(max(z, 1))) < 1e-6

@@ -600,3 +600,31 @@ def test_lazy_grid_update_inside_the_step_graph_and_host_inputs():
     got_cells = gc.grid_map_numpy()
     for b in range(B):
         assert np.array_equal(got_cells[b].astype(np.int32), cells[b][2])
+
+
+def test_packed_map_sequence_equals_padded_layout():
+    """The packed (ragged) map sequence -- masked cell slots dropped, the quirk's zero-vector slots represented once with key bias
+    log z -- must give the results of the padded layout the reference uses (config 2 and REVERIE shapes): same masks, hidden
+    states and logits up to fp16 summation order."""
+    from gridmm_b200.env import GridMapBuilder
+    for B, T, L, G, objs in ((32, 8, 80, 20, 0), (7, 3, 48, 9, 6)):
+        cfg = H.make_config(obj_feat_size=768 if objs else 0)
+        model, _ = _model(cfg, 100 + B)
+        ep = synth.make_episodes(B, T, seed=100 + B)
+        gb = GridMapBuilder(B, max_steps=T)
+        for t in range(T):
+            grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+        nav = _to_cuda(synth.to_torch(synth.make_nav_inputs(B, seed=100 + B, txt_len=L, gmap_len=G, n_objs=objs)))
+        nav.update(grid=grid, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        model.ragged_map = True
+        a = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in model("navigation", nav, return_intermediates=True).items()}
+        model.ragged_map = False
+        b = model("navigation", nav, return_intermediates=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a["map_masks"].cpu(), b["map_masks"].cpu())
+        valid = b["map_masks"].bool()
+        err_map = (a["map_embeds"] - b["map_embeds"])[valid].abs().max().item()
+        errs = {k: H.finite_close(a[k], b[k], atol=5e-4) for k in LOGITS if b[k] is not None}
+        errs.update({k: H.finite_close(a[k], b[k], atol=4e-3) for k in ("gmap_embeds", "vp_embeds")})
+        print("packed vs padded B=%d" % B, "map", err_map, errs)
+        assert err_map < 2e-2, err_map
