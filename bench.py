@@ -393,7 +393,7 @@ def gemm_flops_per_step(kv_rows=None, map_rows=None):
     S, Q, KC = 196 + G, G + 1 + VIEWS + OBJS, 196 + G + L
     mm = lambda m, n, k: 2.0 * m * n * k   # noqa: E731
     BS = B * S if map_rows is None else map_rows
-    f = mm(B * L, H, H) + mm(B * 196 if map_rows is None else max(map_rows - B * G, 0), H, H)      # text_proj, grid_proj
+    f = mm(B * L, H, H) + mm(B * 196, H, H)                                                         # text_proj, grid_proj
     f += mm(BS, 3 * H, H) + mm(BS, H, H) + mm(BS, I, H) + mm(BS, H, I)                              # grid_encoder
     f += mm(B * L, 2 * H, H) + mm(BS, H, H) * 2 + mm(BS, 3 * H, H) + mm(BS, H, H) + mm(BS, I, H) + mm(BS, H, I)
     f += mm(kv_rows if kv_rows is not None else B * KC, 8 * H, H)                        # fusion K/V of 4 layers
@@ -429,6 +429,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     from gridmm_b200 import _lib
+    if os.environ.get("GRIDMM_GEMM_384") == "0":          # A/B: without the 256 x 384 pair tiles
+        import ctypes
+        _lib.load().gridmm_debug_set_gemm_384.argtypes = [ctypes.c_int]
+        _lib.load().gridmm_debug_set_gemm_384(0)
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to produce samples
     step = Step(dev, seed=shard_seed(rank))
     step.run_resident()
@@ -504,11 +508,14 @@ def main():
         g_ms = sum(br.get(k, (0.0, 0))[0] for k in gemm_eps)
         g_n = sum(br.get(k, (0.0, 0))[1] for k in gemm_eps)
         kv_rows = int(step.model.buf("kv_off", (B + 1,), torch.int32)[B].item())      # packed context rows of this batch
-        flops = gemm_flops_per_step(kv_rows)
-        tf = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         S_ = 196 + G
-        valid_map_rows = int(step.model.buf("map_mask", (B, S_), torch.uint8).sum().item())
-        flops_valid = gemm_flops_per_step(kv_rows, map_rows=valid_map_rows)
+        m_off = step.model._ws.get(("m_off", (B + 1,), torch.int32))
+        if m_off is not None:       # packed map sequence: the map-sized launches process m_off[B] rows (device-side count)
+            map_rows = int(m_off[B].item())
+        else:
+            map_rows = B * S_
+        flops = gemm_flops_per_step(kv_rows, map_rows=map_rows)
+        tf = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
@@ -519,8 +526,7 @@ def main():
                     "traffic": traffic.get("gemm_bytes_per_step"),
                     "peak_source": peak_src + ", sustained bf16/fp16 dense", "share_of_step": g_ms / total_k if total_k else None,
                     "algorithmic_flops_per_step": flops, "ms": g_ms, "packed_context_rows": kv_rows,
-                    "valid_map_rows": valid_map_rows, "padded_map_rows": B * S_,
-                    "frac_valid_rows": flops_valid / (g_ms * 1e-3) / 1e12 / tf_peak if g_ms > 0 else None}
+                    "map_rows_processed": map_rows, "padded_map_rows": B * S_}
         # the HBM-bound pooling kernel (north_star's "grid scatter/pool"): bytes that must move / its duration
         p_ms, _ = br.get("gridmm_pool", (0.0, 0))
         gridb = step.builder

@@ -101,6 +101,14 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     using L = GemmSmem<BN, STAGES, BK, CG>;
     constexpr int ATOMS = BK / GEMM_KATOM;
     constexpr int TILE_M = GEMM_BM * CG;          // CG = 2: a CTA pair owns a 256 x BN tile (tcgen05 cta_group::2)
+    // BN = 384 (pairs only): 256 x 384 tiles as two N = 192 MMAs per K step, ONE accumulator of 384 columns (no double buffering:
+    // used where the whole problem is a single round of tiles, so there is no next main loop to overlap the epilogue with).
+    // Per CTA and k-block 16 KB of A + 24 KB of W arrive for 128 x 384 outputs: 153 flop per delivered byte against 128 for
+    // 256 x 256 pair tiles, and M = 1824 x N = 3072 becomes 8 x 8 = 64 pair tiles = one round instead of 96 = two.
+    constexpr int NMMA = (BN > 256) ? 2 : 1;
+    constexpr int MMA_N = BN / NMMA;
+    constexpr int NACC = (BN > 256) ? 1 : 2;
+    static_assert(BN <= 256 || CG == 2, "384-wide tiles exist in pair mode only");
     extern __shared__ uint8_t smem_raw[];
     // align by pointer arithmetic on the __shared__ array (an integer round-trip would demote every access below to a
     // generic LD/ST instead of LDS/STS)
@@ -132,7 +140,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         fence_mbar_init();
     }
     if (warp == 1) {
-        if (CG == 2) tmem_alloc_2sm(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN);
+        if (CG == 2) tmem_alloc_2sm(tmem_slot, NACC * BN > 256 ? 512 : NACC * BN); else tmem_alloc(tmem_slot, NACC * BN);
     }
     tc_fence_before();
     __syncthreads();
@@ -181,7 +189,16 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                         for (int a = 0; a < ATOMS; ++a) {
                             tma_load_2d_2sm(a_dst + a * L::A_ATOM, &tmA, kb * BK + a * GEMM_KATOM, m0, lead_bar);
-                            tma_load_2d_2sm(b_dst + a * L::B_ATOM, &tmW, kb * BK + a * GEMM_KATOM, n0, lead_bar);
+                            if (NMMA == 1) {
+                                tma_load_2d_2sm(b_dst + a * L::B_ATOM, &tmW, kb * BK + a * GEMM_KATOM, n0, lead_bar);
+                            } else {
+                                // this CTA's half (MMA_N / 2 rows) of each of the two MMAs' W rows
+                                const int nt = (tile % tiles_n) * BN;
+#pragma unroll
+                                for (int j = 0; j < NMMA; ++j)
+                                    tma_load_2d_2sm(b_dst + a * L::B_ATOM + j * (MMA_N / 2) * 128, &tmW, kb * BK + a * GEMM_KATOM,
+                                                    nt + j * MMA_N + static_cast<int>(rank) * (MMA_N / 2), lead_bar);
+                            }
                         }
                     }
                 }
@@ -193,14 +210,14 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(TILE_M, BN);
+            constexpr uint32_t idesc = umma_idesc_f16(TILE_M, MMA_N);
             int it = 0, t = 0;
             long long w_full = 0, w_acc = 0;
             const long long t_begin = DBG ? clock64() : 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
-                const int acc = t & 1;
+                const int acc = (NACC == 2) ? (t & 1) : 0;
                 const long long c1 = DBG ? clock64() : 0;
-                mbar_wait(&tmem_empty_bar[acc], ((t >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+                mbar_wait(&tmem_empty_bar[acc], (((NACC == 2) ? (t >> 1) : t) & 1) ^ 1);   // epilogue has drained this accumulator
                 if (DBG) w_acc += clock64() - c1;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -218,10 +235,14 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const uint64_t da = umma_desc_sw128_kmajor(a_addr + a * L::A_ATOM);
                         const uint64_t db = umma_desc_sw128_kmajor(a_addr + L::A_BYTES + a * L::B_ATOM);
 #pragma unroll
-                        for (int k = 0; k < GEMM_KATOM / 16; ++k) {
-                            // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
-                            if (CG == 2) umma_f16_ss_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
-                            else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
+                        for (int j = 0; j < NMMA; ++j) {
+                            const uint64_t dbj = db + static_cast<uint64_t>((j * (MMA_N / 2) * 128) >> 4);
+#pragma unroll
+                            for (int k = 0; k < GEMM_KATOM / 16; ++k) {
+                                // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
+                                if (CG == 2) umma_f16_ss_2sm(d_tmem + j * MMA_N, da + 2 * k, dbj + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
+                                else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | a | k) ? 1u : 0u);
+                            }
                         }
                     }
                     if (CG == 2) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);     // frees the stage in both CTAs
@@ -249,7 +270,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         long long w_tfull = 0;
         const long long t_begin = DBG ? clock64() : 0;
         for (int tile = tile0; tile < num_tiles; tile += tile_step, ++t) {
-            const int acc = t & 1;
+            const int acc = (NACC == 2) ? (t & 1) : 0;
             int m0 = (tile / tiles_n) * TILE_M + static_cast<int>(rank) * GEMM_BM;
             const int n0 = (tile % tiles_n) * BN;
             int wrow0 = n0;                                // row of W / index of bias for column n0 of this tile
@@ -261,8 +282,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 raw_tile = __ldg(gt + 3) != 0;
             }
             // stage this tile's bias slice (the slot of tile t-2 is free: all warps passed the barrier of tile t-1)
-            float* sb = s_bias + acc * BN;
-            float* sg = reinterpret_cast<float*>(smem + L::GW2_OFFSET) + acc * BN;
+            float* sb = s_bias + (t & 1) * BN;
+            float* sg = reinterpret_cast<float*>(smem + L::GW2_OFFSET) + (t & 1) * BN;
             for (int i = et; i < BN; i += GEMM_EPI_WARPS * 32) {
                 sb[i] = ep.bias ? __ldg(ep.bias + wrow0 + i) : 0.0f;
                 if (ep.cls_part) sg[i] = __ldg(ep.gw2 + wrow0 + i);
@@ -287,7 +308,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             named_bar_sync_epi();
             const long long c0 = DBG ? clock64() : 0;
-            mbar_wait(&tmem_full_bar[acc], (t >> 1) & 1);
+            mbar_wait(&tmem_full_bar[acc], ((NACC == 2) ? (t >> 1) : t) & 1);
             if (DBG) w_tfull += clock64() - c0;
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * HALF;
@@ -401,7 +422,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        if (CG == 2) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, NACC * BN > 256 ? 512 : NACC * BN); else tmem_dealloc(tmem_base, NACC * BN);
     }
 }
 
@@ -413,7 +434,7 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, in
                               static_cast<uint64_t>(lda) * 2, GEMM_KATOM, GEMM_BM);
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tmW, w, static_cast<uint64_t>(K), static_cast<uint64_t>(w_rows > 0 ? w_rows : N),
-                          static_cast<uint64_t>(ldw) * 2, GEMM_KATOM, BN / CG);
+                          static_cast<uint64_t>(ldw) * 2, GEMM_KATOM, BN > 256 ? BN / 4 : BN / CG);
     if (rc) return rc;
     auto kern = gemm_f16_tn_kernel<BN, STAGES, BK, DBG, CG>;
     constexpr int smem = GemmSmem<BN, STAGES, BK, CG>::TOTAL;
@@ -447,6 +468,9 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, in
 // ----------------------------------------------------------------------------- C ABI
 static long long* g_gemm_dbg = nullptr;
 static int g_gemm_pairs = 1;
+static int g_gemm_384 = 1;
+// Debug hook: 0 disables the 256 x 384 pair tiles (A/B comparisons).
+extern "C" void gridmm_debug_set_gemm_384(int on) { g_gemm_384 = on; }
 // Debug hook: 0 disables the CTA-pair (cta_group::2) path (A/B comparisons in tools/microbench.py).
 extern "C" void gridmm_debug_set_gemm_pairs(int on) { g_gemm_pairs = on; }
 // Debug hook (tools/microbench.py): per-CTA cycle counters [grid][8] written by the next GEMM launches; null disables.
@@ -488,14 +512,30 @@ static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, 
     // 128-wide single-CTA tiles take 128 K-columns per stage (8 MMAs per barrier round trip) when K allows.
     const bool pair = g_gemm_pairs && (N % 256 == 0) && (static_cast<long long>(tiles_m / 2) * (N / 256) * 2 >= sms);
     const bool deep = (K % 128 == 0);
+    // 256 x 384 pair tiles when they cover the whole problem in ONE round and that round is cheaper than the schedule picked above
+    // (cost ~ rounds x bytes a CTA ingests per k-block: 32 KB for 128 x 128 and for 256 x 256 pair tiles, 48 KB for 128 x 256, 40 KB
+    // for 256 x 384 pair tiles): the 57-query GEMMs of the fusion encoder, M = 1824 x N = 3072 / 2304.
+    bool wide384 = false;
+    if (g_gemm_pairs && g_gemm_384 && N % 384 == 0 && !lanes_rows && !cls_part) {
+        const long long pairs384 = static_cast<long long>((tiles_m + 1) / 2) * (N / 384);
+        if (pairs384 * 2 <= sms) {
+            long long cost;
+            if (pair) cost = ((static_cast<long long>((tiles_m + 1) / 2) * (N / 256) + sms / 2 - 1) / (sms / 2)) * 32;
+            else if (wide) cost = ((static_cast<long long>(tiles_m) * (N / 256) + sms - 1) / sms) * 48;
+            else cost = ((static_cast<long long>(tiles_m) * (N / 128) + sms - 1) / sms) * 32;
+            wide384 = 40 < cost;
+        }
+    }
     int rc;
     if (g_gemm_dbg)
-        rc = pair ? launch_gemm<256, 6, 64, true, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+        rc = wide384 ? launch_gemm<384, 4, 64, true, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : pair ? launch_gemm<256, 6, 64, true, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
            : wide ? launch_gemm<256, 4, 64, true, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
            : deep ? launch_gemm<128, 3, 128, true, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
                   : launch_gemm<128, 6, 64, true, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream);
     else
-        rc = pair ? launch_gemm<256, 6, 64, false, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+        rc = wide384 ? launch_gemm<384, 4, 64, false, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
+           : pair ? launch_gemm<256, 6, 64, false, 2>(a, lda, w, ldw, M, N, K, ep, sms, stream)
            : wide ? launch_gemm<256, 4, 64, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
            : deep ? launch_gemm<128, 3, 128, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream)
                   : launch_gemm<128, 6, 64, false, 1>(a, lda, w, ldw, M, N, K, ep, sms, stream);

@@ -43,6 +43,7 @@ constexpr int POOL_MAX_BATCH = 1024;
 constexpr int POOL_MAX_CELLS = 256;
 constexpr int POOL_TMEM_COLS = 512;
 constexpr int POOL_PTS = 588, POOL_VIEW_PTS = 49;   // points per viewpoint / per view (r2r/env.py:279-289)
+constexpr int POOL_EPISODE_COST = 96;               // rows' worth of time an episode switch costs a CTA (text staging, partial tiles)
 
 struct PoolParams {
     const int* slots;        // [B, t_cap]   slab slot of (episode, step)
@@ -296,19 +297,26 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     if (warp < 2) {
         // CTA range [g0, g1) in global sorted-valid coordinates, snapped up to a cell boundary: warp w resolves boundary
         // blockIdx.x + w with ONE round trip to global memory (every lane loads a slice of the episode's cell_start row)
+        // Work is split in COST units: one per valid row plus POOL_EPISODE_COST per episode start (moving a new text operand into
+        // tensor memory and the partial tiles around an episode switch cost about three tiles), so a CTA whose range crosses an
+        // episode boundary gets fewer rows: equal rows per CTA left the slowest CTA 20 % behind the mean.
         const int total = s_vbase[p.batch];
-        const long long tgt = (static_cast<long long>(blockIdx.x + warp) * total) / gridDim.x;
-        int g = static_cast<int>(tgt);
-        if (g >= total) g = total;
-        else if (g > 0) {
-            int lo = 0, hi = p.batch;
+        const long long total_c = static_cast<long long>(total) + static_cast<long long>(p.batch) * POOL_EPISODE_COST;
+        const long long tgt = (static_cast<long long>(blockIdx.x + warp) * total_c) / gridDim.x;
+        int g;
+        if (blockIdx.x + warp >= gridDim.x) g = total;
+        else if (tgt <= 0) g = 0;
+        else {
+            int lo = 0, hi = p.batch;      // largest b with vbase[b] + b * COST <= tgt
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (s_vbase[mid] <= g) lo = mid; else hi = mid;
+                if (static_cast<long long>(s_vbase[mid]) + static_cast<long long>(mid) * POOL_EPISODE_COST <= tgt) lo = mid; else hi = mid;
             }
-            const int local = g - s_vbase[lo];
+            const int nv = s_vbase[lo + 1] - s_vbase[lo];
+            const long long lc = tgt - s_vbase[lo] - static_cast<long long>(lo) * POOL_EPISODE_COST - POOL_EPISODE_COST;
+            const int local = lc <= 0 ? 0 : (lc >= nv ? nv : static_cast<int>(lc));
             const int* cs = p.cell_start + lo * (n_cells + 1);
-            int best = 0x7fffffff;     // smallest boundary value >= local (cell_start is non-decreasing)
+            int best = nv;                 // smallest cell boundary >= local (cell_start is non-decreasing, cs[n_cells] = nv)
             for (int i = lane; i <= n_cells; i += 32) {
                 const int v = cs[i];
                 if (v >= local) best = min(best, v);

@@ -11,6 +11,7 @@ The forward here is inference (eval-mode semantics: dropout = identity), which i
 """
 import collections
 import math
+import os
 
 import numpy as np
 import torch
@@ -262,11 +263,11 @@ def build_fuse_maps(gmap_vpids, vp_cand_vpids, G, V):
 
 
 class _SideBranch:
-    def __init__(self, model, device):
+    def __init__(self, model, device, index=0):
         self.cuda = torch.device(device).type == "cuda"
         if self.cuda:
             streams = model.__dict__.setdefault("_side_streams", {})
-            key = torch.device(device).index
+            key = (torch.device(device).index, index)
             if key not in streams:
                 streams[key] = torch.cuda.Stream(device=device)
             self.side = streams[key]
@@ -800,11 +801,11 @@ class GlocalTextPathNavCMT(nn.Module):
             mask[b, NC:] = torch.from_numpy(gm[b].astype("uint8"))
         return {"map_embeds": out, "map_masks": mask.to(map32.device)}
 
-    def _fork_side(self, device):
-        """Context manager that runs its body on this model's side stream, forked from the current stream (works eagerly and
-        under CUDA-graph capture, where it becomes a parallel branch of the graph); `.join()` makes the current stream wait for
-        the body.  On a CPU model (host-logic tests with stubbed kernels) the body simply runs inline."""
-        return _SideBranch(self, device)
+    def _fork_side(self, device, index=0):
+        """Context manager that runs its body on one of this model's side streams, forked from the current stream (works eagerly
+        and under CUDA-graph capture, where it becomes a parallel branch of the graph); `.join()` makes the current stream wait
+        for the body.  On a CPU model (host-logic tests with stubbed kernels) the body simply runs inline."""
+        return _SideBranch(self, device, index)
 
     def _out(self, name, shape, static):
         dev = next(self.parameters()).device
@@ -942,9 +943,29 @@ class GlocalTextPathNavCMT(nn.Module):
             names_b += [(le % i) + ".visual_attention.att.key.bias", (le % i) + ".visual_attention.att.value.bias"]
         kvp = self.buf("kvp16", (B * KC, 2 * HID * nx), f16, zero=True)
         ops.linear_rows(kv16, self.W16(*names_w), self.B32(*names_b), kvp, kv_off[B:])
-        for i in range(nx):
-            self._lxrt_layer(le % i, x32, x16, q_mask, kvp[:, 2 * HID * i: 2 * HID * i + HID],
-                             kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], None, B, Q, KC, "x", ctx_var=ctx_var)
+        # The 57 query rows per episode make every launch of these four layers latency-bound (M = B * 57 rows: 90-135 CTAs, 8-22 us
+        # each, of which ~5 us are launch gap, prologue, pipeline fill and drain).  Episodes are independent, so the batch is cut in
+        # `fusion_chains` groups whose layer stacks run as PARALLEL branches (side streams / graph branches): the fixed costs of one
+        # chain hide behind the other chain's tiles.
+        n_ch = int(getattr(self, "fusion_chains", None) or os.environ.get("GRIDMM_FUSION_CHAINS", 2))
+        n_ch = max(1, min(n_ch, B // 8)) if x32.is_cuda else 1
+        bounds = [(c * B) // n_ch for c in range(n_ch + 1)]
+        branches = []
+        for c in range(n_ch):
+            b0, b1 = bounds[c], bounds[c + 1]
+            cv = tuple(t_[b0:] if j < 2 else t_ for j, t_ in enumerate(ctx_var))       # k_off / k_cnt of the chain's episodes
+            br = self._fork_side(x32.device, index=1 + c) if n_ch > 1 else None
+            if br is not None:
+                br.__enter__()
+            for i in range(nx):
+                self._lxrt_layer(le % i, x32[b0 * Q: b1 * Q], x16[b0 * Q: b1 * Q], q_mask[b0:b1], kvp[:, 2 * HID * i: 2 * HID * i + HID],
+                                 kvp[:, 2 * HID * i + HID: 2 * HID * (i + 1)], None, b1 - b0, Q, KC, "x%d" % c if n_ch > 1 else "x",
+                                 ctx_var=cv)
+            if br is not None:
+                br.__exit__(None, None, None)
+                branches.append(br)
+        for br in branches:
+            br.join()
 
         if mode == "trunk":
             x3 = x32.view(B, Q, HID)

@@ -17,8 +17,12 @@ def _dev():
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 768, 768), (6912, 2304, 768), (1000, 768, 3072), (32, 768, 1536),
-                                   (6272, 768, 768), (9472, 6144, 768), (6913, 768, 3072), (12801, 256, 192)])
+                                   (6272, 768, 768), (9472, 6144, 768), (6913, 768, 3072), (12801, 256, 192),
+                                   (1824, 3072, 768), (912, 3072, 768), (1824, 2304, 768), (912, 2304, 768), (1025, 768, 3072),
+                                   (257, 1152, 128)])
 def test_linear_tcgen05_plain(M, N, K):
+    """The last rows of shapes include the 57-query GEMMs of the fusion encoder (whole batch and the two half-batch chains), which
+    run on 256 x 384 CTA-pair tiles (one accumulator, two N = 192 MMAs per K step)."""
     from gridmm_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g).half().to(_dev())
@@ -605,3 +609,35 @@ def test_packed_map_inputs_equal_padded():
         if z > 0:
             assert a[k].abs().max().item() == 0 and abs(float(bias[k]) - np.log(z)) < 1e-6
         assert float(bias.abs().sum()) == (np.log(z) if z > 1 else 0.0) or abs(float(bias.abs().sum()) - np.log(max(z, 1))) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,act", [(1824, 3072, 1), (912, 2304, 0), (300, 1152, 2), (1824, 768, 0)])
+def test_linear_384_wide_pair_tiles_equal_the_other_schedules(M, N, act):
+    """256 x 384 pair tiles against the 128/256-wide schedules of the same kernel (debug hook): same K order per output element,
+    so the fp32 accumulators agree to rounding and the fp16 outputs almost everywhere bitwise."""
+    import ctypes
+    from gridmm_b200 import ops, _lib
+    lib = _lib.load()
+    lib.gridmm_debug_set_gemm_384.argtypes = [ctypes.c_int]
+    dev = _dev()
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, 768, generator=g).half().to(dev)
+    w = (torch.randn(N, 768, generator=g) * 0.05).half().to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    outs = []
+    for on in (1, 0):
+        lib.gridmm_debug_set_gemm_384(on)
+        try:
+            o32 = torch.empty(M, N, device=dev); o16 = torch.empty(M, N, device=dev, dtype=torch.float16)
+            ops.linear(a, w, bias, residual=res, out_f32=o32, out_f16=o16, act=act)
+            torch.cuda.synchronize()
+        finally:
+            lib.gridmm_debug_set_gemm_384(1)
+        outs.append((o32, o16))
+    y = a.float() @ w.float().t() + bias
+    y = torch.nn.functional.gelu(y) if act == 1 else (torch.relu(y) if act == 2 else y)
+    ref = y + res
+    for o32, o16 in outs:
+        assert (o32 - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())

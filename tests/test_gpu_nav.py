@@ -543,9 +543,9 @@ def test_trained_scale_activations():
     mags = {k: ref[k][torch.isfinite(ref[k])].abs().max().item() for k in errs}
     print("trained-scale errors: hidden (abs err, max |x|)", rels, "logits", errs, "logit magnitudes", mags)
     for k, (e, m) in rels.items():
-        assert e / max(m, 1.0) < 1e-2, (k, e, m)
+        assert e / max(m, 1.0) < 4e-3, (k, e, m)           # measured 1.5e-3 of the largest activation (0.3 at |x| = 200)
     for k in errs:
-        assert errs[k] < 1e-2 * max(mags[k], 1.0), (k, errs[k], mags[k])
+        assert errs[k] < 3e-3 * max(mags[k], 1.0), (k, errs[k], mags[k])      # measured <= 1.4e-3 (grid logits of magnitude 1.5)
     # overflow guard: FFN1 pre-activations far beyond the fp16 range
     w = scaled(6.0, 40000.0)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
@@ -624,7 +624,9 @@ def test_packed_map_sequence_equals_padded_layout():
         assert torch.equal(a["map_masks"].cpu(), b["map_masks"].cpu())
         valid = b["map_masks"].bool()
         err_map = (a["map_embeds"] - b["map_embeds"])[valid].abs().max().item()
-        errs = {k: H.finite_close(a[k], b[k], atol=5e-4) for k in LOGITS if b[k] is not None}
+        # two fp16 realisations of the same computation (different summation order in attention, z keys vs one key + log z): their
+        # difference is bounded by the sum of their distances to the fp32 result, i.e. by the logit tolerance itself
+        errs = {k: H.finite_close(a[k], b[k], atol=LOGIT_TOL) for k in LOGITS if b[k] is not None}
         errs.update({k: H.finite_close(a[k], b[k], atol=4e-3) for k in ("gmap_embeds", "vp_embeds")})
         print("packed vs padded B=%d" % B, "map", err_map, errs)
         assert err_map < 2e-2, err_map
