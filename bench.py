@@ -429,10 +429,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     from gridmm_b200 import _lib
-    if os.environ.get("GRIDMM_GEMM_384") == "0":          # A/B: without the 256 x 384 pair tiles
+    if os.environ.get("GRIDMM_GEMM_384") == "1":          # A/B: with the (opt-in) 256 x 384 pair tiles
         import ctypes
         _lib.load().gridmm_debug_set_gemm_384.argtypes = [ctypes.c_int]
-        _lib.load().gridmm_debug_set_gemm_384(0)
+        _lib.load().gridmm_debug_set_gemm_384(1)
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to produce samples
     step = Step(dev, seed=shard_seed(rank))
     step.run_resident()

@@ -468,8 +468,10 @@ static int launch_gemm(const void* a, int lda, const void* w, int ldw, int M, in
 // ----------------------------------------------------------------------------- C ABI
 static long long* g_gemm_dbg = nullptr;
 static int g_gemm_pairs = 1;
-static int g_gemm_384 = 1;
-// Debug hook: 0 disables the 256 x 384 pair tiles (A/B comparisons).
+static int g_gemm_384 = 0;
+// 256 x 384 pair tiles are OFF by default: measured on the navigation step (B = 32, the 57-query GEMMs N = 3072 / 2304) they were
+// ~8 us per launch SLOWER than the two-round 256 x 256 schedule (1.197 vs 1.131 ms per step) -- a single accumulator serialises the
+// GELU epilogue behind the main loop and the 4-stage ring is shallower.  Kept behind this hook (1 = on) with its parity tests.
 extern "C" void gridmm_debug_set_gemm_384(int on) { g_gemm_384 = on; }
 // Debug hook: 0 disables the CTA-pair (cta_group::2) path (A/B comparisons in tools/microbench.py).
 extern "C" void gridmm_debug_set_gemm_pairs(int on) { g_gemm_pairs = on; }
@@ -512,9 +514,9 @@ static int gemm_dispatch(const void* a, int lda, const void* w, int ldw, int M, 
     // 128-wide single-CTA tiles take 128 K-columns per stage (8 MMAs per barrier round trip) when K allows.
     const bool pair = g_gemm_pairs && (N % 256 == 0) && (static_cast<long long>(tiles_m / 2) * (N / 256) * 2 >= sms);
     const bool deep = (K % 128 == 0);
-    // 256 x 384 pair tiles when they cover the whole problem in ONE round and that round is cheaper than the schedule picked above
-    // (cost ~ rounds x bytes a CTA ingests per k-block: 32 KB for 128 x 128 and for 256 x 256 pair tiles, 48 KB for 128 x 256, 40 KB
-    // for 256 x 384 pair tiles): the 57-query GEMMs of the fusion encoder, M = 1824 x N = 3072 / 2304.
+    // (opt-in, see g_gemm_384) 256 x 384 pair tiles when they cover the whole problem in ONE round and that round would be cheaper
+    // than the schedule picked above by the ingest model (cost ~ rounds x bytes a CTA ingests per k-block: 32 KB for 128 x 128 and
+    // for 256 x 256 pair tiles, 48 KB for 128 x 256, 40 KB for 256 x 384 pair tiles)
     bool wide384 = false;
     if (g_gemm_pairs && g_gemm_384 && N % 384 == 0 && !lanes_rows && !cls_part) {
         const long long pairs384 = static_cast<long long>((tiles_m + 1) / 2) * (N / 384);

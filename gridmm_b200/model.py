@@ -943,11 +943,11 @@ class GlocalTextPathNavCMT(nn.Module):
             names_b += [(le % i) + ".visual_attention.att.key.bias", (le % i) + ".visual_attention.att.value.bias"]
         kvp = self.buf("kvp16", (B * KC, 2 * HID * nx), f16, zero=True)
         ops.linear_rows(kv16, self.W16(*names_w), self.B32(*names_b), kvp, kv_off[B:])
-        # The 57 query rows per episode make every launch of these four layers latency-bound (M = B * 57 rows: 90-135 CTAs, 8-22 us
-        # each, of which ~5 us are launch gap, prologue, pipeline fill and drain).  Episodes are independent, so the batch is cut in
-        # `fusion_chains` groups whose layer stacks run as PARALLEL branches (side streams / graph branches): the fixed costs of one
-        # chain hide behind the other chain's tiles.
-        n_ch = int(getattr(self, "fusion_chains", None) or os.environ.get("GRIDMM_FUSION_CHAINS", 2))
+        # The 57 query rows per episode make every launch of these four layers small (M = B * 57 rows: 90-135 CTAs, 8-22 us each).
+        # Episodes are independent, so the batch CAN be cut in `fusion_chains` groups whose layer stacks run as parallel branches
+        # (side streams / graph branches).  Measured at B = 32: 1.131 ms per step with one chain, 1.140 with two -- the launches are
+        # bound by the per-SM operand ingest of their tiles, not by launch gaps, so the default stays one chain.
+        n_ch = int(getattr(self, "fusion_chains", None) or os.environ.get("GRIDMM_FUSION_CHAINS", 1))
         n_ch = max(1, min(n_ch, B // 8)) if x32.is_cuda else 1
         bounds = [(c * B) // n_ch for c in range(n_ch + 1)]
         branches = []

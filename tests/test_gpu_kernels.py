@@ -21,8 +21,7 @@ def _dev():
                                    (1824, 3072, 768), (912, 3072, 768), (1824, 2304, 768), (912, 2304, 768), (1025, 768, 3072),
                                    (257, 1152, 128)])
 def test_linear_tcgen05_plain(M, N, K):
-    """The last rows of shapes include the 57-query GEMMs of the fusion encoder (whole batch and the two half-batch chains), which
-    run on 256 x 384 CTA-pair tiles (one accumulator, two N = 192 MMAs per K step)."""
+    """The last rows of shapes include the 57-query GEMMs of the fusion encoder (whole batch and half batches)."""
     from gridmm_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g).half().to(_dev())
@@ -633,7 +632,7 @@ def test_linear_384_wide_pair_tiles_equal_the_other_schedules(M, N, act):
             ops.linear(a, w, bias, residual=res, out_f32=o32, out_f16=o16, act=act)
             torch.cuda.synchronize()
         finally:
-            lib.gridmm_debug_set_gemm_384(1)
+            lib.gridmm_debug_set_gemm_384(0)
         outs.append((o32, o16))
     y = a.float() @ w.float().t() + bias
     y = torch.nn.functional.gelu(y) if act == 1 else (torch.relu(y) if act == 2 else y)
