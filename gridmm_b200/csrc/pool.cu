@@ -37,8 +37,12 @@ constexpr int POOL_NBUF = 4;           // tile buffers / TMEM accumulators in fl
 constexpr int POOL_PROD_WARPS = 4;     // warps 0..3: TMA gather producers (8 rows of every tile each) + text staging, first half
 constexpr int POOL_RED_WARP0 = 4;      // warps 4..7: relevance max (TMEM lane quadrant = warp % 4), softmax weights, text staging
 constexpr int POOL_MMA_WARP = 8;       // tcgen05.mma issuer, owns the TMEM allocation
-constexpr int POOL_POOL_WARP0 = 9;     // warps 9.. (D / 128 of them): weighted sums
+constexpr int POOL_POOL_WARP0 = 9;     // warps 9.. : weighted sums.  TC mode: warp 9 issues the pooling MMAs, warps 10..13 are the
+                                       // accumulator epilogue (one per tensor-memory lane quadrant); HMMA mode: D / 128 mma.sync warps
 constexpr int POOL_FIXED_THREADS = POOL_POOL_WARP0 * 32;
+constexpr int POOL_TC_THREADS = (POOL_POOL_WARP0 + 5) * 32;
+constexpr int POOL_MAXPASS = 4;        // a 32-row tile holds at most 32 cells = 4 passes of 8 cell slots
+constexpr int POOL_W_BYTES = 16 * 32 * 2;      // one pass of the weight operand: [16 = 8 slots x (hi, lo)] x [32 rows] fp16
 constexpr int POOL_MAX_BATCH = 1024;
 constexpr int POOL_MAX_CELLS = 256;
 constexpr int POOL_TMEM_COLS = 512;
@@ -152,6 +156,32 @@ __device__ __forceinline__ float ord2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// MN-major shared-memory operand of the pooling MMA: A[M = 128 feature dims, K = 16 tile rows] read straight out of the K-major
+// feature tile the relevance MMA uses (chunk = 64 dims: 32 rows x 128 B, SWIZZLE_128B).  Seen MN-major, a swizzle atom is
+// 64 dims (128 B) x 8 rows; atoms repeat every `chunk_bytes` along M (LBO) and every 1024 B along K (SBO).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
+    return d;
+}
+// K-major operand WITHOUT swizzle: 8 x 8 core matrices of 128 contiguous bytes (row r of a core matrix = 16 B at r * 16);
+// lbo = byte distance between core matrices adjacent in K, sbo = between core matrices adjacent in M/N.
+__device__ __forceinline__ uint64_t umma_desc_noswizzle_kmajor(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
+}
+// kind::f16 instruction descriptor with an MN-major A operand (bit 15), K-major B, fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_f16_amn(int m, int n) {
+    return (1u << 4) | (1u << 15) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 template <int D>
 struct PoolSmem {
     static constexpr int CH = D / 64;
@@ -164,7 +194,8 @@ struct PoolSmem {
                                       + 128                       // scalars
                                       + 2 * (POOL_MAX_CELLS + 1) * 4 + POOL_MAX_CELLS * 4   // cell_start (reducers / poolers), cell_rank
                                       + (POOL_MAX_BATCH + 1) * 4; // vbase
-    static constexpr int TOTAL = 1024 + POOL_NBUF * A_BYTES + MISC_BYTES;
+    static constexpr int W_BYTES = POOL_NBUF * POOL_MAXPASS * POOL_W_BYTES;      // weight operands of the pooling MMAs (TC mode)
+    static constexpr int TOTAL = 1024 + POOL_NBUF * A_BYTES + W_BYTES + MISC_BYTES + 64;
 };
 
 // text_fts [B, l_pad, D] -> lane-major copy [B, D/8, 128] of 16-byte units: unit c of text position t sits at
@@ -210,14 +241,17 @@ __device__ __forceinline__ void stage_text(const uint4* ws_b, int tlane, int l_p
     tmem_st_wait();
 }
 
-template <int D>
-__global__ void __launch_bounds__(POOL_FIXED_THREADS + D / 4, 1)
+template <int D, bool TC>
+__global__ void __launch_bounds__(TC ? POOL_TC_THREADS : POOL_FIXED_THREADS + D / 4, 1)
 pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     using L = PoolSmem<D>;
     constexpr int CH = L::CH;
-    constexpr int NPW = D / 128;                  // pooling warps
+    constexpr int NPW = D / 128;                  // pooling warps (HMMA mode) = 128-dim blocks of a feature row
     constexpr int A_COLS = D / 2;                 // TMEM columns of the text operand (two fp16 per column)
-    constexpr int D_COL0 = A_COLS;                // accumulators behind it: one of 32 columns per tile buffer
+    constexpr int D_COL0 = A_COLS;                // relevance accumulators behind it: 32 columns per tile buffer (TC mode: ONE buffer)
+    constexpr int NDBUF = TC ? 1 : POOL_NBUF;     // relevance accumulators in flight
+    constexpr int P_COL0 = D_COL0 + POOL_ROWS;    // TC mode: pooling accumulators, 16 columns (8 slots x (hi, lo)) per 128-dim block
+    static_assert(!TC || P_COL0 + NPW * 16 <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
     constexpr int UNITS = D / 8;                  // 16-byte units per text position
     constexpr int BU = UNITS / 16;                // units per staging batch (16 batches: 8 per half)
     constexpr float LOG2E = 1.4426950408889634f;
@@ -228,7 +262,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     // generic LD/ST instead of LDS/STS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;                            // [NBUF][CH][32 x 128 B]
-    uint8_t* misc = sA + POOL_NBUF * L::A_BYTES;
+    uint8_t* sW = sA + POOL_NBUF * L::A_BYTES;     // [NBUF][MAXPASS][2 n-cores][4 k-cores][8 x 16 B]: weights of the pooling MMAs (TC mode)
+    uint8_t* misc = sW + L::W_BYTES;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);          // [NBUF] tile landed (producer arrivals + TMA transaction bytes)
     uint64_t* a_empty = a_full + POOL_NBUF;                        // [NBUF] tile buffer drained by the pooling warps
     uint64_t* d_full = a_empty + POOL_NBUF;                        // [NBUF] accumulator written (tcgen05.commit)
@@ -237,6 +272,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     uint64_t* m_full = p_full + POOL_NBUF;                         // [NBUF] partial maxima of reducer warps 1..3 are in s_part
     uint64_t* t_ready = m_full + POOL_NBUF;                              // [1] text operand of the episode is in TMEM
     uint64_t* ep_done = t_ready + 1;                               // [1] every MMA of the previous episode has retired
+    uint64_t* pacc_full = ep_done + 1;                             // [1] TC mode: the pooling MMAs of a pass have retired
+    uint64_t* pacc_empty = pacc_full + 1;                          // [1] TC mode: the epilogue warps have read the pooling accumulators
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 60);
     float* s_p = reinterpret_cast<float*>(misc + 64 * 8);          // [NBUF][32] exp(w - cell max) per row
     int* s_cid = reinterpret_cast<int*>(s_p + POOL_NBUF * POOL_ROWS);      // [NBUF][32] compact cell rank (+ last-row flag) of every row
@@ -245,6 +282,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     float* s_carry_m = s_scal + POOL_NBUF;         // [1] running max of the cell left open by the previous tile
     int* s_carry_c = reinterpret_cast<int*>(s_carry_m + 1);        // [1] its (episode << 16 | cell) key (-1: none)
     int* s_range = s_carry_c + 1;                                  // [0] g_start, [1] g_end
+    int* s_meta = s_range + 2;                                     // [NBUF][2] first / last compact cell rank of the tile (TC mode)
     int* s_csr = reinterpret_cast<int*>(misc + 64 * 8 + 2 * POOL_NBUF * POOL_ROWS * 4 + POOL_NBUF * 4 * POOL_ROWS * 4 + 128);   // reducers' cell_start
     int* s_cs = s_csr + POOL_MAX_CELLS + 1;                        // (spare table slot)
     int* s_cr = s_cs + POOL_MAX_CELLS + 1;                         // reducers' cell_rank [n_cells]
@@ -259,7 +297,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
         tma_prefetch_desc(&tm_fts);
         for (int i = 0; i < POOL_NBUF; ++i) {
             mbar_init(&a_full[i], POOL_PROD_WARPS);
-            mbar_init(&a_empty[i], NPW);
+            mbar_init(&a_empty[i], TC ? 1 : NPW);
             mbar_init(&d_full[i], 1);
             mbar_init(&d_empty[i], 4);
             mbar_init(&p_full[i], 32);
@@ -267,6 +305,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
         }
         mbar_init(t_ready, 256);
         mbar_init(ep_done, 1);
+        mbar_init(pacc_full, 1);
+        mbar_init(pacc_empty, 4);
         *s_carry_c = -1;
         fence_mbar_init();
     }
@@ -419,13 +459,15 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                     cur_b = t.b;
                     ++visits;
                 }
+                const int dbuf = TC ? 0 : buf;                    // TC mode: one relevance accumulator, phases advance per tile
+                const uint32_t dph = TC ? (it & 1) : ph;
                 const long long c0 = p.dbg ? clock64() : 0;
-                mbar_wait_guard(&d_empty[buf], ph ^ 1);
+                mbar_wait_guard(&d_empty[dbuf], dph ^ 1);
                 const long long c1 = p.dbg ? clock64() : 0;
                 mbar_wait_relaxed(&a_full[buf], ph);
                 if (p.dbg) { w_b += c1 - c0; w_a += clock64() - c1; }
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + D_COL0 + buf * POOL_ROWS;
+                const uint32_t d_tmem = tmem_base + D_COL0 + dbuf * POOL_ROWS;
                 const uint32_t tile_s = smem_u32(sA) + buf * L::A_BYTES;
                 if (elect_one()) {
 #pragma unroll
@@ -435,7 +477,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                         for (int kk = 0; kk < 4; ++kk)   // K = 16 per instruction = 8 TMEM columns of A, 32 bytes of B
                             umma_f16_ts(d_tmem, tmem_base + k * 32 + kk * 8, db + 2 * kk, idesc, (k | kk) ? 1u : 0u);
                     }
-                    umma_commit(&d_full[buf]);
+                    umma_commit(&d_full[dbuf]);
                 }
                 __syncwarp();
                 ++it;
@@ -468,8 +510,10 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 mbar_arrive(t_ready);
                 if (p.dbg) c_text += clock64() - c0;
             }
+            const int dbuf = TC ? 0 : buf;
+            const uint32_t dph = TC ? (it & 1) : ph;
             const long long c1 = p.dbg ? clock64() : 0;
-            mbar_wait_guard(&d_full[buf], ph);
+            mbar_wait_guard(&d_full[dbuf], dph);
             const long long c2 = p.dbg ? clock64() : 0;
             tc_fence_after();
             float* part = s_part + buf * 4 * POOL_ROWS;
@@ -478,10 +522,10 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
             if (!has_text) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[buf]);
+                if (lane == 0) mbar_arrive(&d_empty[dbuf]);
             } else {
                 float v[32];
-                const uint32_t ta = taddr_lane + D_COL0 + buf * POOL_ROWS;
+                const uint32_t ta = taddr_lane + D_COL0 + dbuf * POOL_ROWS;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t r0[16];
@@ -492,7 +536,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[buf]);      // the accumulator may be overwritten
+                if (lane == 0) mbar_arrive(&d_empty[dbuf]);     // the accumulator may be overwritten
                 lane_max_level<32>(v, lane, 16);
                 lane_max_level<16>(v, lane, 8);
                 lane_max_level<8>(v, lane, 4);
@@ -542,11 +586,34 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 __syncwarp();                       // every lane has read the carry before the last row's lane replaces it
                 const bool cont = valid && (key == carry_c);
                 if (cont) m = fmaxf(m, carry_m);
-                s_p[buf * POOL_ROWS + lane] = valid ? ex2_approx((w - m) * LOG2E) : 0.0f;
+                const float pnum = valid ? ex2_approx((w - m) * LOG2E) : 0.0f;
+                s_p[buf * POOL_ROWS + lane] = pnum;
                 // compact rank of the row's cell (= its row in `pooled`), flagged when this is the cell's last row
-                s_cid[buf * POOL_ROWS + lane] = valid ? (s_cr[cid] | ((t.pos + lane + 1 == s_csr[cid + 1]) ? 0x10000 : 0)) : -1;
+                const int rank = valid ? s_cr[cid] : -1;
+                s_cid[buf * POOL_ROWS + lane] = valid ? (rank | ((t.pos + lane + 1 == s_csr[cid + 1]) ? 0x10000 : 0)) : -1;
                 if (lane == 0) s_scal[buf] = cont ? ex2_approx((carry_m - m) * LOG2E) : 1.0f;
                 if (lane == t.nrows - 1) { *s_carry_m = m; *s_carry_c = key; }
+                if constexpr (TC) {
+                    // B operand of the pooling MMAs: W^T[16 = 8 cell slots x (hi, lo)][32 rows] per pass of 8 consecutive cell ranks,
+                    // row r of the tile has weight p_r in the slot of its cell (slot = rank & 7, so an open cell keeps its slot
+                    // from tile to tile) as fp16 value (n-core 0) + fp16 rounding residual (n-core 1): K-major without swizzle,
+                    // 8 x 8 core matrices [n-core][k-core][slot][row & 7]
+                    const int rank0 = __shfl_sync(0xffffffffu, rank, 0);
+                    const int rank_last = __shfl_sync(0xffffffffu, rank, t.nrows - 1);
+                    const int npass = ((rank_last - rank0) >> 3) + 1;
+                    uint8_t* wb = sW + buf * (POOL_MAXPASS * POOL_W_BYTES);
+                    for (int i = lane; i < npass * (POOL_W_BYTES / 16); i += 32) reinterpret_cast<uint4*>(wb)[i] = make_uint4(0, 0, 0, 0);
+                    __syncwarp();
+                    if (valid) {
+                        const __half hi = __float2half_rn(pnum);
+                        const __half lo = __float2half_rn(pnum - __half2float(hi));
+                        __half* dst = reinterpret_cast<__half*>(wb + ((rank - rank0) >> 3) * POOL_W_BYTES + (lane >> 3) * 128 + (rank & 7) * 16) + (lane & 7);
+                        dst[0] = hi;
+                        dst[256] = lo;                  // n-core 1 (512 B further)
+                    }
+                    if (lane == 0) { s_meta[buf * 2] = rank0; s_meta[buf * 2 + 1] = rank_last; }
+                    fence_proxy_async_smem();           // generic-proxy stores -> visible to the tensor core's operand reads
+                }
                 mbar_arrive(&p_full[buf]);          // release: s_p[buf] / s_scal[buf] are visible to the pooling warps
             }
             if (p.dbg) { w_a += c2 - c1; c_soft += clock64() - c2; }
@@ -556,7 +623,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
             long long* d = p.dbg + blockIdx.x * 16 + 6;
             d[0] = clock64() - t_begin; d[1] = w_a; d[2] = c_text; d[3] = c_soft;
         }
-    } else {
+    } else if constexpr (!TC) {
         // ------------------------------------------------------------ weighted sums from the resident tile (warp-level HMMA)
         // out[cell, :] = sum_r p[r] x[r, :] is a matrix product  X^T[D, 32 rows] . W[32 rows, 8 cell slots]  with W[r, slot] = p[r]
         // when row r belongs to the cell in that slot (slot = compact cell rank & 7; ranks are consecutive along the sorted
@@ -701,6 +768,138 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
             long long* d = p.dbg + blockIdx.x * 16 + 10;
             d[0] = clock64() - t_begin; d[1] = w_a; d[2] = c_loop;
         }
+    } else if (warp == POOL_POOL_WARP0) {
+        // ------------------------------------------------------------ TC mode: issuer of the pooling MMAs
+        // out[cell, :] = sum_r p[r] x[r, :] as  D[128 dims, 16] (+)= X^T[128 dims, 16 rows] . W[16 rows, 16 = 8 slots x (hi, lo)]
+        // per 128-dim block and 16-row half of the tile: the A operand is the resident feature tile read MN-major (no transpose,
+        // no second copy), the accumulators (NPW x 16 tensor-memory columns) are read back by the epilogue warps after every pass.
+        constexpr uint32_t idesc_p = umma_idesc_f16_amn(128, 16);
+        int it = 0;
+        uint32_t pc = 0;                                  // passes issued so far (phase of pacc_empty / pacc_full)
+        while (wk.next(t)) {
+            const int buf = uniform_i32(it % POOL_NBUF);
+            const uint32_t ph = (it / POOL_NBUF) & 1;
+            mbar_wait_guard(&p_full[buf], ph);
+            if (p.max_only) {                              // first pass of a long text: only drain the ring
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_empty[buf]);
+                ++it;
+                continue;
+            }
+            const int npass = uniform_i32(((s_meta[buf * 2 + 1] - s_meta[buf * 2]) >> 3) + 1);
+            const uint32_t tile_s = smem_u32(sA) + buf * L::A_BYTES;
+            const uint32_t w_s = smem_u32(sW) + buf * (POOL_MAXPASS * POOL_W_BYTES);
+            for (int ps = 0; ps < npass; ++ps, ++pc) {
+                mbar_wait_guard(pacc_empty, (pc & 1) ^ 1);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {       // 16 tile rows per instruction
+                        const uint64_t db = umma_desc_noswizzle_kmajor(w_s + ps * POOL_W_BYTES + kk * 256, 128, 512);
+#pragma unroll
+                        for (int mb = 0; mb < NPW; ++mb) {
+                            const uint64_t da = umma_desc_sw128_mnmajor_lbo(tile_s + mb * 2 * L::A_CHUNK + kk * 2048, L::A_CHUNK);
+                            umma_f16_ss(tmem_base + P_COL0 + mb * 16, da, db, idesc_p, kk ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(pacc_full);
+                    if (ps == npass - 1) umma_commit(&a_empty[buf]);     // the tile buffer is free once these MMAs have read it
+                }
+                __syncwarp();
+            }
+            ++it;
+        }
+    } else if (warp > POOL_POOL_WARP0 && warp <= POOL_POOL_WARP0 + 4) {
+        // ------------------------------------------------------------ TC mode: accumulator epilogue, one warp per TMEM lane quadrant
+        // thread (quadrant q, lane) owns feature dims mb * 128 + q * 32 + lane of every 128-dim block; the fp32 sums of the (up to
+        // 8) open cell slots stay in registers across tiles, rescaled when a later tile raises the open cell's max
+        const int q = warp & 3;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + P_COL0;
+        float acc[NPW][8];
+        float ssum[8];                                     // sum of the weights of every slot (replicated in all threads)
+#pragma unroll
+        for (int s_ = 0; s_ < 8; ++s_) {
+            ssum[s_] = 0.f;
+#pragma unroll
+            for (int mb = 0; mb < NPW; ++mb) acc[mb][s_] = 0.f;
+        }
+        int it = 0;
+        uint32_t pc = 0;
+        long long c_loop = 0;
+        while (!p.max_only && wk.next(t)) {
+            const int buf = it % POOL_NBUF;
+            const uint32_t ph = (it / POOL_NBUF) & 1;
+            const long long c0 = p.dbg ? clock64() : 0;
+            mbar_wait_guard(&p_full[buf], ph);             // s_p / s_cid / s_scal of the tile are visible
+            const long long c1 = p.dbg ? clock64() : 0;
+            const float my_p = s_p[buf * POOL_ROWS + lane];
+            const int my_rk = s_cid[buf * POOL_ROWS + lane];      // compact cell rank | (last row of its cell ? 0x10000 : 0); -1 = no row
+            const int rank0 = __shfl_sync(0xffffffffu, my_rk, 0) & 0xffff;
+            const int rank_last = __shfl_sync(0xffffffffu, my_rk, t.nrows - 1) & 0xffff;
+            {
+                const float sc = s_scal[buf];              // a later tile raised the open cell's max (1 otherwise): its slot is rank0 & 7
+                if (sc != 1.0f) {
+                    const int s0 = rank0 & 7;
+#pragma unroll
+                    for (int s_ = 0; s_ < 8; ++s_)
+                        if (s_ == s0) {
+                            ssum[s_] *= sc;
+#pragma unroll
+                            for (int mb = 0; mb < NPW; ++mb) acc[mb][s_] *= sc;
+                        }
+                }
+            }
+            for (int base = rank0; base <= rank_last; base += 8, ++pc) {
+                const int rel = (my_rk & 0xffff) - base;
+                const bool in_pass = my_rk >= 0 && rel >= 0 && rel < 8;
+                const int my_slot = my_rk & 7;
+#pragma unroll
+                for (int s_ = 0; s_ < 8; ++s_) ssum[s_] += warp_sum((in_pass && my_slot == s_) ? my_p : 0.0f);
+                const unsigned done = __reduce_or_sync(0xffffffffu, (in_pass && (my_rk & 0x10000)) ? (1u << my_slot) : 0u);
+                mbar_wait_guard(pacc_full, pc & 1);
+                tc_fence_after();
+                constexpr int HB = NPW / 2;                 // two batches of 128-dim blocks: 48 registers in flight instead of 96
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    uint32_t raw[HB][16];
+#pragma unroll
+                    for (int mb = 0; mb < HB; ++mb) tmem_ld_32x32b_x16(t_lane + (hb * HB + mb) * 16, raw[mb]);
+                    tmem_ld_wait();
+                    if (hb == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(pacc_empty);     // the accumulators may be overwritten by the next pass
+                    }
+#pragma unroll
+                    for (int mb = 0; mb < HB; ++mb)
+#pragma unroll
+                        for (int s_ = 0; s_ < 8; ++s_)
+                            acc[hb * HB + mb][s_] += __uint_as_float(raw[mb][s_]) + __uint_as_float(raw[mb][8 + s_]);
+                }
+                if (done) {
+                    // cells of this pass whose last row lies in this tile: normalise, store (rows of `pooled` are the compact ranks), reset
+                    __half* out_b = p.pooled + static_cast<size_t>(t.b) * n_cells * D + q * 32 + lane;
+#pragma unroll
+                    for (int s_ = 0; s_ < 8; ++s_)
+                        if ((done >> s_) & 1u) {
+                            const float fin = 1.0f / ssum[s_];
+                            __half* orow = out_b + static_cast<size_t>(base + ((s_ - base) & 7)) * D;
+#pragma unroll
+                            for (int mb = 0; mb < NPW; ++mb) {
+                                orow[mb * 128] = __float2half_rn(acc[mb][s_] * fin);
+                                acc[mb][s_] = 0.f;
+                            }
+                            ssum[s_] = 0.f;
+                        }
+                }
+            }
+            if (p.dbg) { w_a += c1 - c0; c_loop += clock64() - c1; }
+            ++it;
+        }
+        if (p.dbg && warp == POOL_POOL_WARP0 + 1 && lane == 0) {
+            long long* d = p.dbg + blockIdx.x * 16 + 10;
+            d[0] = clock64() - t_begin; d[1] = w_a; d[2] = c_loop;
+        }
     }
 
     tc_fence_before();
@@ -713,7 +912,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
-template <int D>
+template <int D, bool TC>
 static int launch_pool(const void* fts, long long fts_rows, const void* text_fts, void* text_ws, int text_ws_ready, int grid,
                        PoolParams& p, float* w_scratch, cudaStream_t stream) {
     // gather4 tensor map: the slab as [fts_rows, D] fp16, box = 64 columns x 1 row (the instruction names 4 rows)
@@ -721,7 +920,8 @@ static int launch_pool(const void* fts, long long fts_rows, const void* text_fts
     const int rc = make_tmap_f16_2d(&tm, fts, static_cast<uint64_t>(D), static_cast<uint64_t>(fts_rows), static_cast<uint64_t>(D) * 2, 64, 1);
     if (rc) return rc;
     constexpr int smem = PoolSmem<D>::TOTAL;
-    GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    constexpr int threads = TC ? POOL_TC_THREADS : POOL_FIXED_THREADS + D / 4;
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(pool_kernel<D, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int l_total = p.l_pad;
     if (!text_ws_ready) {
         GMM_CUDA_CHECK(launch_pdl(text_to_lanes_kernel<D>, dim3(D / 8, p.batch, (l_total + 127) / 128), dim3(128), 0, stream,
@@ -735,11 +935,11 @@ static int launch_pool(const void* fts, long long fts_rows, const void* text_fts
         PoolParams p1 = p;
         p1.text_ws = p.text_ws + static_cast<size_t>(p.batch) * (D / 8) * 128;
         p1.l_pad = l_total - 128; p1.max_only = 1; p1.w_out = w_scratch; p1.w_in = nullptr;
-        GMM_CUDA_CHECK(launch_pdl(pool_kernel<D>, dim3(grid), dim3(POOL_FIXED_THREADS + D / 4), smem, stream, tm, p1));
+        GMM_CUDA_CHECK(launch_pdl(pool_kernel<D, TC>, dim3(grid), dim3(threads), smem, stream, tm, p1));
         gridmm_count_launch(1);
         p.l_pad = 128; p.w_in = w_scratch;
     }
-    GMM_CUDA_CHECK(launch_pdl(pool_kernel<D>, dim3(grid), dim3(POOL_FIXED_THREADS + D / 4), smem, stream, tm, p));
+    GMM_CUDA_CHECK(launch_pdl(pool_kernel<D, TC>, dim3(grid), dim3(threads), smem, stream, tm, p));
     gridmm_count_launch(1);
     return 0;
 }
@@ -747,6 +947,9 @@ static int launch_pool(const void* fts, long long fts_rows, const void* text_fts
 }  // namespace gmm
 
 static long long* g_pool_dbg = nullptr;
+static int g_pool_hmma = 0;
+// Debug hook: 1 selects the previous weighted-sum stage (warp-level mma.sync from registers) instead of the tcgen05 one (A/B timing).
+extern "C" void gridmm_debug_set_pool_hmma(int on) { g_pool_hmma = on; }
 // Debug hook (tools/microbench2.py): per-CTA cycle counters [grid][16] written by the next pool launches; null disables.
 extern "C" void gridmm_debug_set_pool_counters(long long* dbg) { g_pool_dbg = dbg; }
 
@@ -771,6 +974,10 @@ extern "C" int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, co
     const int sms = gridmm_sm_count();
     if (sms <= 0) return GRIDMM_ERR_DRIVER;
     const int grid = num_ctas > 0 ? num_ctas : sms;
-    if (feat_dim == 768) return launch_pool<768>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
-    return launch_pool<512>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
+    if (g_pool_hmma) {
+        if (feat_dim == 768) return launch_pool<768, false>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
+        return launch_pool<512, false>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
+    }
+    if (feat_dim == 768) return launch_pool<768, true>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
+    return launch_pool<512, true>(fts, fts_rows, text_fts, text_ws, text_ws_ready, grid, p, w_scratch, stream);
 }

@@ -300,6 +300,14 @@ def test_grid_update_ce_geometry():
             assert np.array_equal(per_step[t][b].astype(np.int32), cells[b][t]), "b=%d t=%d" % (b, t)
 
 
+def _pool_mode(hmma):
+    import ctypes
+    from gridmm_b200 import _lib
+    lib = _lib.load()
+    lib.gridmm_debug_set_pool_hmma.argtypes = [ctypes.c_int]
+    lib.gridmm_debug_set_pool_hmma(int(hmma))
+
+
 def _oracle_pool(fts, cell, tp16, n_cells=196):
     """float64 statement of vilmodel.py:797-807 in feature space, with the SAME fp16-rounded text_fts the kernel sees."""
     x = torch.from_numpy(np.ascontiguousarray(fts)).double()
@@ -316,10 +324,13 @@ def _oracle_pool(fts, cell, tp16, n_cells=196):
 @pytest.mark.parametrize("B,T,L,D,gw", [(3, 2, 80, 768, 14), (8, 8, 80, 768, 14), (2, 15, 40, 768, 14), (1, 1, 16, 512, 8), (37, 3, 24, 768, 14),
                                         (3, 2, 128, 768, 14), (3, 2, 129, 768, 14), (3, 3, 136, 768, 14), (5, 4, 200, 768, 14),
                                         (2, 8, 250, 768, 14), (2, 2, 256, 768, 14), (2, 2, 200, 512, 8)])
-def test_pool_vs_oracle(B, T, L, D, gw):
+@pytest.mark.parametrize("hmma", [0, 1], ids=["tcgen05_sums", "mma_sync_sums"])
+def test_pool_vs_oracle(B, T, L, D, gw, hmma):
     """L > 128 (the reference's --max_instr_len 200 / 250, vilmodel.py:798 takes the max over ALL positions): two passes of the
-    kernel, the first over positions 128.. only produces row maxima."""
+    kernel, the first over positions 128.. only produces row maxima.  hmma: the weighted-sum stage on tcgen05 (default) or on
+    warp-level mma.sync (debug hook)."""
     from gridmm_b200 import ops
+    _pool_mode(hmma)
     ep = synth.make_episodes(B, T, seed=B * 100 + T, dim=D)
     cells, fts, halfs, pos = H.oracle_grid(ep, grid_w=gw)
     gb, grid, _ = _run_builder(ep, grid_w=gw)
@@ -328,9 +339,12 @@ def test_pool_vs_oracle(B, T, L, D, gw):
     tp = (torch.randn(B, L, D, generator=g) * 0.55).half()
     pooled = torch.zeros(B * nc, D, device=_dev(), dtype=torch.float16)
     w_out = torch.zeros(B, grid.cap, device=_dev())
-    ops.pool(grid.slab, D, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
-             grid.cell_start, grid.cell_rank, nc, tp.to(_dev()).view(B * L, D), L, B, pooled, w_out=w_out)
-    torch.cuda.synchronize()
+    try:
+        ops.pool(grid.slab, D, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
+                 grid.cell_start, grid.cell_rank, nc, tp.to(_dev()).view(B * L, D), L, B, pooled, w_out=w_out)
+        torch.cuda.synchronize()
+    finally:
+        _pool_mode(0)
     pooled = pooled.view(B, nc, D).float().cpu(); w_out = w_out.cpu()
     perm = grid.perm.cpu().numpy(); cr = grid.cell_rank.cpu().numpy(); cs = grid.cell_start.cpu().numpy()
     for b in range(B):
@@ -344,8 +358,9 @@ def test_pool_vs_oracle(B, T, L, D, gw):
                 assert err < 6e-3, "b=%d cell=%d err=%.3e" % (b, c, err)   # fp16 output (ulp 4e-3 at |x|~4) + exp rounding
 
 
+@pytest.mark.parametrize("hmma", [0, 1], ids=["tcgen05_sums", "mma_sync_sums"])
 @pytest.mark.parametrize("sizes", ["tiny", "mixed", "one_big"])
-def test_pool_handmade_cells(sizes):
+def test_pool_handmade_cells(sizes, hmma):
     """gridmm_pool on a hand-made layout (no grid builder): tiny cells (> 8 cells per 32-row tile -> several passes of the
     8-slot HMMA pooling), a cell spanning many tiles, an episode without any valid point, ragged text length."""
     from gridmm_b200 import ops
@@ -385,9 +400,13 @@ def test_pool_handmade_cells(sizes):
     dev = _dev()
     pooled = torch.zeros(B * nc, D, device=dev, dtype=torch.float16)
     w_out = torch.zeros(B, cap, device=dev)
-    ops.pool(slab.to(dev), D, slots.to(dev), t_cap, 588, 49, 0, perm.to(dev), cap, cell_start.to(dev), cell_rank.to(dev), nc,
-             tp.to(dev).view(B * L, D), L, B, pooled, w_out=w_out)
-    torch.cuda.synchronize()
+    _pool_mode(hmma)
+    try:
+        ops.pool(slab.to(dev), D, slots.to(dev), t_cap, 588, 49, 0, perm.to(dev), cap, cell_start.to(dev), cell_rank.to(dev), nc,
+                 tp.to(dev).view(B * L, D), L, B, pooled, w_out=w_out)
+        torch.cuda.synchronize()
+    finally:
+        _pool_mode(0)
     pooled = pooled.view(B, nc, D).float().cpu()
     for b in range(B):
         x_b = slab[b * cap:(b + 1) * cap].double()

@@ -126,16 +126,23 @@ if "ln" in want:
         print("LN rows=%5d: %6.1f us  (%.0f GB/s of 10 B/elt)" % (rows, us, rows * 768 * 10 / us / 1e3), flush=True)
 
 if "pool" in want:
+    if os.environ.get("GRIDMM_POOL_HMMA") == "1":       # A/B: the previous weighted-sum stage (warp-level mma.sync)
+        lib.gridmm_debug_set_pool_hmma.argtypes = [ctypes.c_int]
+        lib.gridmm_debug_set_pool_hmma(1)
+        print("pool: weighted sums on mma.sync (debug hook)")
     step = Step(dev, seed=0)
     step.model.use_cuda_graph = False
     step.run_resident(); torch.cuda.synchronize()
     m = step.model; g = step.builder
     from gridmm_b200.env import GridBatch
     grid = GridBatch(g)
+    ref_pooled = m.buf("pooled16", (B * 196, 768), torch.float16, zero=True).clone()
     pooled = m.buf("pooled16", (B * 196, 768), torch.float16, zero=True)
     text_ws = ops.pool_text_ws(dev, B, 768)          # filled by the step above (text_proj epilogue)
     fn = lambda: ops.pool(grid.slab, 768, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
                           grid.cell_start, grid.cell_rank, 196, None, 80, B, pooled, text_ws=text_ws, text_ws_ready=True)
+    fn(); torch.cuda.synchronize()
+    print("pool: re-run equals the step's result:", bool(torch.equal(pooled, ref_pooled)))
     nv = int(grid.cell_start[:, -1].sum().item())
     cs = grid.cell_start.cpu()
     sizes = (cs[:, 1:] - cs[:, :-1]).flatten()
