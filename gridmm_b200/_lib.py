@@ -44,6 +44,9 @@ _SIGS = {
     "gridmm_nav_logits2": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 12 +
                           [c_int, c_int, c_int, c_void_p],
     "gridmm_copy_segments": [c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "gridmm_grad_sumsq": [c_void_p, c_longlong, c_void_p, c_void_p],
+    "gridmm_adamw_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, c_float,
+                          c_void_p, c_float, c_void_p],
     "gridmm_linear_f16_lanes": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_linear_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
                           c_void_p, c_int, c_int, c_void_p, c_void_p],

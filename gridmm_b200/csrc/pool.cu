@@ -128,6 +128,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// warp-wide maximum of a float, returned to every lane (sm_100a: CREDUX.MAX.F32)
+__device__ __forceinline__ float redux_max_f32(float x) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -248,10 +255,12 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     constexpr int CH = L::CH;
     constexpr int NPW = D / 128;                  // pooling warps (HMMA mode) = 128-dim blocks of a feature row
     constexpr int A_COLS = D / 2;                 // TMEM columns of the text operand (two fp16 per column)
-    constexpr int D_COL0 = A_COLS;                // relevance accumulators behind it: 32 columns per tile buffer (TC mode: ONE buffer)
-    constexpr int NDBUF = TC ? 1 : POOL_NBUF;     // relevance accumulators in flight
-    constexpr int P_COL0 = D_COL0 + POOL_ROWS;    // TC mode: pooling accumulators, 16 columns (8 slots x (hi, lo)) per 128-dim block
-    static_assert(!TC || P_COL0 + NPW * 16 <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
+    constexpr int D_COL0 = A_COLS;                // relevance accumulators behind it: 32 columns per tile buffer (TC mode: TWO buffers)
+    constexpr int NDBUF = TC ? 2 : POOL_NBUF;     // relevance accumulators in flight
+    constexpr int HB = NPW / 2;                   // TC mode: 128-dim blocks per sub-pass of the pooling MMAs
+    constexpr int P_COL0 = D_COL0 + NDBUF * POOL_ROWS;   // TC mode: pooling accumulators, 16 columns (8 slots x (hi, lo)) per 128-dim
+                                                  // block of a SUB-PASS (half of the blocks: all of them do not fit next to the text)
+    static_assert(!TC || P_COL0 + HB * 16 <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
     constexpr int UNITS = D / 8;                  // 16-byte units per text position
     constexpr int BU = UNITS / 16;                // units per staging batch (16 batches: 8 per half)
     constexpr float LOG2E = 1.4426950408889634f;
@@ -459,8 +468,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                     cur_b = t.b;
                     ++visits;
                 }
-                const int dbuf = TC ? 0 : buf;                    // TC mode: one relevance accumulator, phases advance per tile
-                const uint32_t dph = TC ? (it & 1) : ph;
+                const int dbuf = TC ? (it & 1) : buf;             // TC mode: two relevance accumulators
+                const uint32_t dph = TC ? ((it >> 1) & 1) : ph;
                 const long long c0 = p.dbg ? clock64() : 0;
                 mbar_wait_guard(&d_empty[dbuf], dph ^ 1);
                 const long long c1 = p.dbg ? clock64() : 0;
@@ -508,10 +517,27 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 stage_text<D, BU>(p.text_ws + static_cast<size_t>(t.b) * UNITS * 128, tlane, p.l_pad, taddr_lane, UNITS / 2);
                 tc_fence_before();
                 mbar_arrive(t_ready);
+                named_bar_sync(4, 128);             // the new tables are visible to every reducer warp
                 if (p.dbg) c_text += clock64() - c0;
             }
-            const int dbuf = TC ? 0 : buf;
-            const uint32_t dph = TC ? (it & 1) : ph;
+            // The softmax warp resolves the cell of its row (binary search over the episode's cell_start, ~300 cycles) BEFORE it
+            // waits for the tile's relevance: this lookup only depends on the tile's position, and the wait -> numerators chain of
+            // this single warp is what paces the whole kernel.
+            const bool sm_valid = lane < t.nrows;
+            int sm_cid = -1, sm_rank = -1, sm_last = 0;
+            if (warp == POOL_RED_WARP0 + 3 && sm_valid && !p.max_only) {
+                const int P = t.pos + lane;
+                int a = 0, c = n_cells;             // last cell with cs[cell] <= P
+                while (c - a > 1) {
+                    const int mid = (a + c) >> 1;
+                    if (s_csr[mid] <= P) a = mid; else c = mid;
+                }
+                sm_cid = a;
+                sm_rank = s_cr[a];
+                sm_last = (P + 1 == s_csr[a + 1]) ? 0x10000 : 0;
+            }
+            const int dbuf = TC ? (it & 1) : buf;
+            const uint32_t dph = TC ? ((it >> 1) & 1) : ph;
             const long long c1 = p.dbg ? clock64() : 0;
             mbar_wait_guard(&d_full[dbuf], dph);
             const long long c2 = p.dbg ? clock64() : 0;
@@ -537,12 +563,14 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[dbuf]);     // the accumulator may be overwritten
-                lane_max_level<32>(v, lane, 16);
-                lane_max_level<16>(v, lane, 8);
-                lane_max_level<8>(v, lane, 4);
-                lane_max_level<4>(v, lane, 2);
-                lane_max_level<2>(v, lane, 1);
-                wmax = v[0];
+                // max over the 32 lanes (= text positions) of every column (= tile row): one warp-wide redux.sync.max.f32 per column
+                // (CREDUX, result in a uniform register; 32 independent instructions instead of a 5-level dependent shuffle
+                // butterfly), lane c keeps column c
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float r = redux_max_f32(v[c]);
+                    if (lane == c) wmax = r;
+                }
             }
             if (warp != POOL_RED_WARP0 + 3) {
                 // reducer warps 0..2 hand their partial maxima to warp 3 through shared memory + an mbarrier and move on to the next
@@ -567,17 +595,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                     ++it;
                     continue;
                 }
-                int cid = -1;
-                if (valid) {
-                    const int P = t.pos + lane;
-                    int a = 0, c = n_cells;        // last cell with cs[cell] <= P
-                    while (c - a > 1) {
-                        const int mid = (a + c) >> 1;
-                        if (s_csr[mid] <= P) a = mid; else c = mid;
-                    }
-                    cid = a;
-                    if (p.w_out) p.w_out[static_cast<size_t>(t.b) * p.cap + P] = w;
-                }
+                const int cid = sm_cid;
+                if (valid && p.w_out) p.w_out[static_cast<size_t>(t.b) * p.cap + t.pos + lane] = w;
                 const unsigned same = __match_any_sync(0xffffffffu, cid);
                 float m = ord2f(__reduce_max_sync(same, f2ord(w)));
                 const float carry_m = *s_carry_m;
@@ -589,8 +608,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 const float pnum = valid ? ex2_approx((w - m) * LOG2E) : 0.0f;
                 s_p[buf * POOL_ROWS + lane] = pnum;
                 // compact rank of the row's cell (= its row in `pooled`), flagged when this is the cell's last row
-                const int rank = valid ? s_cr[cid] : -1;
-                s_cid[buf * POOL_ROWS + lane] = valid ? (rank | ((t.pos + lane + 1 == s_csr[cid + 1]) ? 0x10000 : 0)) : -1;
+                const int rank = sm_rank;
+                s_cid[buf * POOL_ROWS + lane] = valid ? (rank | sm_last) : -1;
                 if (lane == 0) s_scal[buf] = cont ? ex2_approx((carry_m - m) * LOG2E) : 1.0f;
                 if (lane == t.nrows - 1) { *s_carry_m = m; *s_carry_c = key; }
                 if constexpr (TC) {
@@ -789,7 +808,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
             const int npass = uniform_i32(((s_meta[buf * 2 + 1] - s_meta[buf * 2]) >> 3) + 1);
             const uint32_t tile_s = smem_u32(sA) + buf * L::A_BYTES;
             const uint32_t w_s = smem_u32(sW) + buf * (POOL_MAXPASS * POOL_W_BYTES);
-            for (int ps = 0; ps < npass; ++ps, ++pc) {
+            for (int sp = 0; sp < 2 * npass; ++sp, ++pc) {       // sub-pass = (pass of 8 cell ranks, half of the 128-dim blocks)
+                const int ps = sp >> 1, mb0 = (sp & 1) * HB;
                 mbar_wait_guard(pacc_empty, (pc & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -797,13 +817,13 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                     for (int kk = 0; kk < 2; ++kk) {       // 16 tile rows per instruction
                         const uint64_t db = umma_desc_noswizzle_kmajor(w_s + ps * POOL_W_BYTES + kk * 256, 128, 512);
 #pragma unroll
-                        for (int mb = 0; mb < NPW; ++mb) {
-                            const uint64_t da = umma_desc_sw128_mnmajor_lbo(tile_s + mb * 2 * L::A_CHUNK + kk * 2048, L::A_CHUNK);
+                        for (int mb = 0; mb < HB; ++mb) {
+                            const uint64_t da = umma_desc_sw128_mnmajor_lbo(tile_s + (mb0 + mb) * 2 * L::A_CHUNK + kk * 2048, L::A_CHUNK);
                             umma_f16_ss(tmem_base + P_COL0 + mb * 16, da, db, idesc_p, kk ? 1u : 0u);
                         }
                     }
                     umma_commit(pacc_full);
-                    if (ps == npass - 1) umma_commit(&a_empty[buf]);     // the tile buffer is free once these MMAs have read it
+                    if (sp == 2 * npass - 1) umma_commit(&a_empty[buf]);     // the tile buffer is free once these MMAs have read it
                 }
                 __syncwarp();
             }
@@ -849,27 +869,24 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                         }
                 }
             }
-            for (int base = rank0; base <= rank_last; base += 8, ++pc) {
+            for (int base = rank0; base <= rank_last; base += 8) {
                 const int rel = (my_rk & 0xffff) - base;
                 const bool in_pass = my_rk >= 0 && rel >= 0 && rel < 8;
                 const int my_slot = my_rk & 7;
 #pragma unroll
                 for (int s_ = 0; s_ < 8; ++s_) ssum[s_] += warp_sum((in_pass && my_slot == s_) ? my_p : 0.0f);
                 const unsigned done = __reduce_or_sync(0xffffffffu, (in_pass && (my_rk & 0x10000)) ? (1u << my_slot) : 0u);
-                mbar_wait_guard(pacc_full, pc & 1);
-                tc_fence_after();
-                constexpr int HB = NPW / 2;                 // two batches of 128-dim blocks: 48 registers in flight instead of 96
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
+                for (int hb = 0; hb < 2; ++hb, ++pc) {
+                    mbar_wait_guard(pacc_full, pc & 1);
+                    tc_fence_after();
                     uint32_t raw[HB][16];
 #pragma unroll
-                    for (int mb = 0; mb < HB; ++mb) tmem_ld_32x32b_x16(t_lane + (hb * HB + mb) * 16, raw[mb]);
+                    for (int mb = 0; mb < HB; ++mb) tmem_ld_32x32b_x16(t_lane + mb * 16, raw[mb]);
                     tmem_ld_wait();
-                    if (hb == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(pacc_empty);     // the accumulators may be overwritten by the next pass
-                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pacc_empty);         // the accumulators may be overwritten by the next sub-pass
 #pragma unroll
                     for (int mb = 0; mb < HB; ++mb)
 #pragma unroll

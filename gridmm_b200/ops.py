@@ -398,3 +398,18 @@ def copy_segments(pairs):
         nb = (ctypes.c_longlong * n)(*[d_.numel() * d_.element_size() for _, d_ in chunk])
         cast = lambda a: ctypes.cast(a, ctypes.c_void_p)                   # noqa: E731
         _lib.call("gridmm_copy_segments", n, cast(src), cast(dst), cast(nb), _lib.stream_ptr())
+
+
+def grad_sumsq(g, out):
+    """out[0] += sum(g ** 2) for a flat fp32 CUDA tensor (zero `out` first)."""
+    _chk(g, torch.float32, "g"); _chk(out, torch.float32, "out")
+    _lib.call("gridmm_grad_sumsq", g.data_ptr(), g.numel(), out.data_ptr(), _lib.stream_ptr())
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, sumsq=None, max_norm=0.0):
+    """In-place AdamW step over flat fp32 CUDA tensors (pretrain_src/optim/adamw.py:57-104)."""
+    for t_, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v"), (sumsq, "sumsq")):
+        _chk(t_, torch.float32, n)
+    assert p.numel() == g.numel() == m.numel() == v.numel() and p.is_contiguous() and g.is_contiguous()
+    _lib.call("gridmm_adamw_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2),
+              float(eps), float(weight_decay), int(step), float(grad_scale), _lib.ptr(sumsq), float(max_norm), _lib.stream_ptr())

@@ -284,6 +284,17 @@ int gridmm_nav_logits(const float* raw_global, const float* raw_grid, const floa
 int gridmm_ce_logits(const float* raw_global, const float* raw_local, const float* raw_fuse, const unsigned char* vp_nav_masks,
                      float* fused, int batch, int G, int V, int maxc, cudaStream_t stream);
 
+/* ---- optimizer half of the pretraining step (BASELINE config 5) -------------------------------------------
+ * After the NCCL all-reduce of the flat gradient buffer (gridmm_b200/train.py) every rank applies the same update:
+ * torch.nn.utils.clip_grad_norm_ (pretrain_src/train_r2r.py:281-285) + AdamW with decoupled weight decay and bias correction
+ * (pretrain_src/optim/adamw.py:57-104), one flat fp32 range per parameter group (weight decay 0.01 / 0: optim/misc.py:12-22).
+ * gridmm_grad_sumsq: out[0] += sum g[i]^2 (zero `out` first; ranges may be accumulated).
+ * gridmm_adamw_step: p, m, v updated in place from g * grad_scale (1 / world size, 1 / loss scale); sumsq != NULL clips by the
+ *   global norm sqrt(*sumsq) * grad_scale against max_norm on the device (no host synchronisation); step >= 1. */
+int gridmm_grad_sumsq(const float* g, long long n, float* out, cudaStream_t stream);
+int gridmm_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, float grad_scale, const float* sumsq, float max_norm, cudaStream_t stream);
+
 /* Debug hooks (tools/microbench.py only): per-CTA clock64 counters written by the following launches ([grid][8] for the
  * GEMM, [grid][16] for the pooling kernel: role totals and time spent waiting on each mbarrier).  NULL disables. */
 void gridmm_debug_set_gemm_counters(long long* dbg);
