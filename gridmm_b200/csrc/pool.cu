@@ -200,7 +200,8 @@ struct PoolSmem {
                                       + POOL_NBUF * 4 * POOL_ROWS * 4   // per-quadrant partial maxima (per buffer)
                                       + 128                       // scalars
                                       + 2 * (POOL_MAX_CELLS + 1) * 4 + POOL_MAX_CELLS * 4   // cell_start (reducers / poolers), cell_rank
-                                      + (POOL_MAX_BATCH + 1) * 4; // vbase
+                                      + (POOL_MAX_BATCH + 1) * 4  // vbase
+                                      + POOL_NBUF * POOL_MAXPASS * 8 * 4;   // weight sum per cell slot (TC mode)
     static constexpr int W_BYTES = POOL_NBUF * POOL_MAXPASS * POOL_W_BYTES;      // weight operands of the pooling MMAs (TC mode)
     static constexpr int TOTAL = 1024 + POOL_NBUF * A_BYTES + W_BYTES + MISC_BYTES + 64;
 };
@@ -255,12 +256,12 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     constexpr int CH = L::CH;
     constexpr int NPW = D / 128;                  // pooling warps (HMMA mode) = 128-dim blocks of a feature row
     constexpr int A_COLS = D / 2;                 // TMEM columns of the text operand (two fp16 per column)
-    constexpr int D_COL0 = A_COLS;                // relevance accumulators behind it: 32 columns per tile buffer (TC mode: TWO buffers)
-    constexpr int NDBUF = TC ? 2 : POOL_NBUF;     // relevance accumulators in flight
-    constexpr int HB = NPW / 2;                   // TC mode: 128-dim blocks per sub-pass of the pooling MMAs
-    constexpr int P_COL0 = D_COL0 + NDBUF * POOL_ROWS;   // TC mode: pooling accumulators, 16 columns (8 slots x (hi, lo)) per 128-dim
-                                                  // block of a SUB-PASS (half of the blocks: all of them do not fit next to the text)
-    static_assert(!TC || P_COL0 + HB * 16 <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
+    constexpr int D_COL0 = A_COLS;                // relevance accumulators behind it: 32 columns per tile buffer (TC mode: ONE buffer --
+                                                  // the pooling accumulators take the rest of tensor memory; the reducers read a
+                                                  // relevance tile back within ~300 cycles, well inside the HBM time of a tile)
+    constexpr int NDBUF = TC ? 1 : POOL_NBUF;     // relevance accumulators in flight
+    constexpr int P_COL0 = D_COL0 + NDBUF * POOL_ROWS;   // TC mode: pooling accumulators, 16 columns (8 slots x (hi, lo)) per 128-dim block
+    static_assert(!TC || P_COL0 + NPW * 16 <= POOL_TMEM_COLS, "text operand + accumulators must fit in tensor memory");
     constexpr int UNITS = D / 8;                  // 16-byte units per text position
     constexpr int BU = UNITS / 16;                // units per staging batch (16 batches: 8 per half)
     constexpr float LOG2E = 1.4426950408889634f;
@@ -296,6 +297,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
     int* s_cs = s_csr + POOL_MAX_CELLS + 1;                        // (spare table slot)
     int* s_cr = s_cs + POOL_MAX_CELLS + 1;                         // reducers' cell_rank [n_cells]
     int* s_vbase = s_cr + POOL_MAX_CELLS;                          // [batch + 1]
+    float* s_wsum = reinterpret_cast<float*>(s_vbase + POOL_MAX_BATCH + 1);     // [NBUF][MAXPASS][8] weight sum per cell slot (TC mode)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -468,8 +470,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                     cur_b = t.b;
                     ++visits;
                 }
-                const int dbuf = TC ? (it & 1) : buf;             // TC mode: two relevance accumulators
-                const uint32_t dph = TC ? ((it >> 1) & 1) : ph;
+                const int dbuf = TC ? 0 : buf;                    // TC mode: one relevance accumulator, phases advance per tile
+                const uint32_t dph = TC ? (it & 1) : ph;
                 const long long c0 = p.dbg ? clock64() : 0;
                 mbar_wait_guard(&d_empty[dbuf], dph ^ 1);
                 const long long c1 = p.dbg ? clock64() : 0;
@@ -536,8 +538,8 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                 sm_rank = s_cr[a];
                 sm_last = (P + 1 == s_csr[a + 1]) ? 0x10000 : 0;
             }
-            const int dbuf = TC ? (it & 1) : buf;
-            const uint32_t dph = TC ? ((it >> 1) & 1) : ph;
+            const int dbuf = TC ? 0 : buf;
+            const uint32_t dph = TC ? (it & 1) : ph;
             const long long c1 = p.dbg ? clock64() : 0;
             mbar_wait_guard(&d_full[dbuf], dph);
             const long long c2 = p.dbg ? clock64() : 0;
@@ -631,6 +633,13 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                         dst[256] = lo;                  // n-core 1 (512 B further)
                     }
                     if (lane == 0) { s_meta[buf * 2] = rank0; s_meta[buf * 2 + 1] = rank_last; }
+                    // sum of the weights of every cell slot of every pass (the epilogue warps normalise with it): one integer
+                    // redux over the lanes of a cell (24-bit fixed point: p <= 1, at most 32 rows -> exact to 2^-24)
+                    float* ws = s_wsum + buf * (POOL_MAXPASS * 8);
+                    ws[lane] = 0.0f;
+                    __syncwarp();
+                    const int qsum = __reduce_add_sync(same, __float2int_rn(pnum * 16777216.0f));
+                    if (valid && lane == __ffs(same) - 1) ws[((rank - rank0) >> 3) * 8 + (rank & 7)] = static_cast<float>(qsum) * (1.0f / 16777216.0f);
                     fence_proxy_async_smem();           // generic-proxy stores -> visible to the tensor core's operand reads
                 }
                 mbar_arrive(&p_full[buf]);          // release: s_p[buf] / s_scal[buf] are visible to the pooling warps
@@ -808,8 +817,7 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
             const int npass = uniform_i32(((s_meta[buf * 2 + 1] - s_meta[buf * 2]) >> 3) + 1);
             const uint32_t tile_s = smem_u32(sA) + buf * L::A_BYTES;
             const uint32_t w_s = smem_u32(sW) + buf * (POOL_MAXPASS * POOL_W_BYTES);
-            for (int sp = 0; sp < 2 * npass; ++sp, ++pc) {       // sub-pass = (pass of 8 cell ranks, half of the 128-dim blocks)
-                const int ps = sp >> 1, mb0 = (sp & 1) * HB;
+            for (int ps = 0; ps < npass; ++ps, ++pc) {     // pass = 8 consecutive cell ranks (normally one per tile)
                 mbar_wait_guard(pacc_empty, (pc & 1) ^ 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -817,13 +825,13 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                     for (int kk = 0; kk < 2; ++kk) {       // 16 tile rows per instruction
                         const uint64_t db = umma_desc_noswizzle_kmajor(w_s + ps * POOL_W_BYTES + kk * 256, 128, 512);
 #pragma unroll
-                        for (int mb = 0; mb < HB; ++mb) {
-                            const uint64_t da = umma_desc_sw128_mnmajor_lbo(tile_s + (mb0 + mb) * 2 * L::A_CHUNK + kk * 2048, L::A_CHUNK);
+                        for (int mb = 0; mb < NPW; ++mb) {
+                            const uint64_t da = umma_desc_sw128_mnmajor_lbo(tile_s + mb * 2 * L::A_CHUNK + kk * 2048, L::A_CHUNK);
                             umma_f16_ss(tmem_base + P_COL0 + mb * 16, da, db, idesc_p, kk ? 1u : 0u);
                         }
                     }
                     umma_commit(pacc_full);
-                    if (sp == 2 * npass - 1) umma_commit(&a_empty[buf]);     // the tile buffer is free once these MMAs have read it
+                    if (ps == npass - 1) umma_commit(&a_empty[buf]);     // the tile buffer is free once these MMAs have read it
                 }
                 __syncwarp();
             }
@@ -852,7 +860,6 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
             const long long c0 = p.dbg ? clock64() : 0;
             mbar_wait_guard(&p_full[buf], ph);             // s_p / s_cid / s_scal of the tile are visible
             const long long c1 = p.dbg ? clock64() : 0;
-            const float my_p = s_p[buf * POOL_ROWS + lane];
             const int my_rk = s_cid[buf * POOL_ROWS + lane];      // compact cell rank | (last row of its cell ? 0x10000 : 0); -1 = no row
             const int rank0 = __shfl_sync(0xffffffffu, my_rk, 0) & 0xffff;
             const int rank_last = __shfl_sync(0xffffffffu, my_rk, t.nrows - 1) & 0xffff;
@@ -869,30 +876,35 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                         }
                 }
             }
-            for (int base = rank0; base <= rank_last; base += 8) {
+            const float* wsum = s_wsum + buf * (POOL_MAXPASS * 8);
+            int ps = 0;
+            for (int base = rank0; base <= rank_last; base += 8, ++ps, ++pc) {
                 const int rel = (my_rk & 0xffff) - base;
                 const bool in_pass = my_rk >= 0 && rel >= 0 && rel < 8;
                 const int my_slot = my_rk & 7;
-#pragma unroll
-                for (int s_ = 0; s_ < 8; ++s_) ssum[s_] += warp_sum((in_pass && my_slot == s_) ? my_p : 0.0f);
                 const unsigned done = __reduce_or_sync(0xffffffffu, (in_pass && (my_rk & 0x10000)) ? (1u << my_slot) : 0u);
+                mbar_wait_guard(pacc_full, pc & 1);
+                tc_fence_after();
+                constexpr int HB = NPW / 2;                 // two batches of 128-dim blocks: 48 registers in flight instead of 96
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb, ++pc) {
-                    mbar_wait_guard(pacc_full, pc & 1);
-                    tc_fence_after();
+                for (int hb = 0; hb < 2; ++hb) {
                     uint32_t raw[HB][16];
 #pragma unroll
-                    for (int mb = 0; mb < HB; ++mb) tmem_ld_32x32b_x16(t_lane + mb * 16, raw[mb]);
+                    for (int mb = 0; mb < HB; ++mb) tmem_ld_32x32b_x16(t_lane + (hb * HB + mb) * 16, raw[mb]);
                     tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(pacc_empty);         // the accumulators may be overwritten by the next sub-pass
+                    if (hb == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(pacc_empty);     // the accumulators may be overwritten by the next pass
+                    }
 #pragma unroll
                     for (int mb = 0; mb < HB; ++mb)
 #pragma unroll
                         for (int s_ = 0; s_ < 8; ++s_)
                             acc[hb * HB + mb][s_] += __uint_as_float(raw[mb][s_]) + __uint_as_float(raw[mb][8 + s_]);
                 }
+#pragma unroll
+                for (int s_ = 0; s_ < 8; ++s_) ssum[s_] += wsum[ps * 8 + s_];      // weight sums per slot, from the softmax warp
                 if (done) {
                     // cells of this pass whose last row lies in this tile: normalise, store (rows of `pooled` are the compact ranks), reset
                     __half* out_b = p.pooled + static_cast<size_t>(t.b) * n_cells * D + q * 32 + lane;
