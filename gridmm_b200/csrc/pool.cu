@@ -976,8 +976,14 @@ static int launch_pool(const void* fts, long long fts_rows, const void* text_fts
 }  // namespace gmm
 
 static long long* g_pool_dbg = nullptr;
-static int g_pool_hmma = 0;
-// Debug hook: 1 selects the previous weighted-sum stage (warp-level mma.sync from registers) instead of the tcgen05 one (A/B timing).
+static int g_pool_hmma = 1;
+// Weighted-sum stage: 1 (default) = warp-level mma.sync from the resident tile, accumulators in registers; 0 = tcgen05 (MN-major A
+// operand out of the same tile, weight operand built by the softmax warp, accumulators in tensor memory read back by four epilogue
+// warps).  Both are parity-tested.  Measured at B = 32, T = 8 (profiles/r2_pool_modes.md): mma.sync 67.8-68.4 us; tcgen05 72.0-77.2 us
+// in three layouts -- next to the 384 columns of the text operand tensor memory only holds EITHER all six pooling accumulators and
+// one relevance accumulator (the relevance MMA then waits for the reducers 35 % of the time) OR two relevance accumulators and half
+// of the pooling blocks (two MMA -> epilogue round trips per tile), and the per-tile weight operand adds ~500 cycles to the softmax
+// warp, which paces the kernel.
 extern "C" void gridmm_debug_set_pool_hmma(int on) { g_pool_hmma = on; }
 // Debug hook (tools/microbench2.py): per-CTA cycle counters [grid][16] written by the next pool launches; null disables.
 extern "C" void gridmm_debug_set_pool_counters(long long* dbg) { g_pool_dbg = dbg; }

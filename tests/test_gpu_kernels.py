@@ -327,8 +327,8 @@ def _oracle_pool(fts, cell, tp16, n_cells=196):
 @pytest.mark.parametrize("hmma", [0, 1], ids=["tcgen05_sums", "mma_sync_sums"])
 def test_pool_vs_oracle(B, T, L, D, gw, hmma):
     """L > 128 (the reference's --max_instr_len 200 / 250, vilmodel.py:798 takes the max over ALL positions): two passes of the
-    kernel, the first over positions 128.. only produces row maxima.  hmma: the weighted-sum stage on tcgen05 (default) or on
-    warp-level mma.sync (debug hook)."""
+    kernel, the first over positions 128.. only produces row maxima.  hmma: the weighted-sum stage on warp-level mma.sync (default)
+    or on tcgen05 (debug hook)."""
     from gridmm_b200 import ops
     _pool_mode(hmma)
     ep = synth.make_episodes(B, T, seed=B * 100 + T, dim=D)
@@ -344,7 +344,7 @@ def test_pool_vs_oracle(B, T, L, D, gw, hmma):
                  grid.cell_start, grid.cell_rank, nc, tp.to(_dev()).view(B * L, D), L, B, pooled, w_out=w_out)
         torch.cuda.synchronize()
     finally:
-        _pool_mode(0)
+        _pool_mode(1)
     pooled = pooled.view(B, nc, D).float().cpu(); w_out = w_out.cpu()
     perm = grid.perm.cpu().numpy(); cr = grid.cell_rank.cpu().numpy(); cs = grid.cell_start.cpu().numpy()
     for b in range(B):
@@ -406,7 +406,7 @@ def test_pool_handmade_cells(sizes, hmma):
                  tp.to(dev).view(B * L, D), L, B, pooled, w_out=w_out)
         torch.cuda.synchronize()
     finally:
-        _pool_mode(0)
+        _pool_mode(1)
     pooled = pooled.view(B, nc, D).float().cpu()
     for b in range(B):
         x_b = slab[b * cap:(b + 1) * cap].double()
@@ -659,3 +659,45 @@ def test_linear_384_wide_pair_tiles_equal_the_other_schedules(M, N, act):
     for o32, o16 in outs:
         assert (o32 - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_adamw_and_grad_clip_match_the_reference_optimizer():
+    """gridmm_grad_sumsq + gridmm_adamw_step against the reference's update rule restated in float64: clip_grad_norm_
+    (pretrain_src/train_r2r.py:281-285) followed by AdamW with decoupled weight decay and bias correction
+    (pretrain_src/optim/adamw.py:57-104), several steps, both parameter groups, gradients pre-summed over `world` ranks."""
+    from gridmm_b200 import ops
+    dev = _dev()
+    g_ = torch.Generator().manual_seed(3)
+    n = 1_000_003
+    p0 = torch.randn(n, generator=g_)
+    lr, b1, b2, eps, world, max_norm = 5e-5, 0.9, 0.98, 1e-6, 8, 5.0
+    for wd in (0.01, 0.0):
+        p = torch.zeros(n + 1, device=dev)[:n]           # odd length: the scalar tail of the vectorised kernels
+        p.copy_(p0)
+        m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+        rp, rm, rv = p0.double(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+        sumsq = torch.zeros(1, device=dev)
+        for step in range(1, 4):
+            g = torch.randn(n, generator=g_) * (40.0 if step == 2 else 0.002) * world      # step 2 is clipped
+            gd = g.to(dev)
+            sumsq.zero_()
+            ops.grad_sumsq(gd[: n // 2], sumsq); ops.grad_sumsq(gd[n // 2:][:0], sumsq)      # empty range: no-op
+            ops.grad_sumsq(gd[n // 2:].clone(), sumsq)                                       # accumulates over ranges
+            ops.adamw_step(p, gd, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0 / world, sumsq=sumsq, max_norm=max_norm)
+            # reference
+            ga = g.double() / world
+            norm = ga.norm()
+            coef = max_norm / (norm + 1e-6)
+            if coef < 1:
+                ga = ga * coef
+            rm = b1 * rm + (1 - b1) * ga
+            rv = b2 * rv + (1 - b2) * ga * ga
+            step_size = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+            rp = rp - step_size * rm / (rv.sqrt() + eps)
+            if wd > 0:
+                rp = rp - lr * wd * rp
+            torch.cuda.synchronize()
+            assert abs(float(sumsq.sqrt()) / world - float(norm)) < 1e-3 * float(norm)
+        assert (p.cpu().double() - rp).abs().max().item() < 2e-6
+        assert (m.cpu().double() - rm).abs().max().item() < 1e-6 * max(1.0, float(rm.abs().max()))
+        assert (v.cpu().double() - rv).abs().max().item() < 1e-5 * max(1.0, float(rv.abs().max()))

@@ -126,10 +126,10 @@ if "ln" in want:
         print("LN rows=%5d: %6.1f us  (%.0f GB/s of 10 B/elt)" % (rows, us, rows * 768 * 10 / us / 1e3), flush=True)
 
 if "pool" in want:
-    if os.environ.get("GRIDMM_POOL_HMMA") == "1":       # A/B: the previous weighted-sum stage (warp-level mma.sync)
+    if os.environ.get("GRIDMM_POOL_HMMA") == "0":       # A/B: the weighted-sum stage on tcgen05 (opt-in; measured slower)
         lib.gridmm_debug_set_pool_hmma.argtypes = [ctypes.c_int]
-        lib.gridmm_debug_set_pool_hmma(1)
-        print("pool: weighted sums on mma.sync (debug hook)")
+        lib.gridmm_debug_set_pool_hmma(0)
+        print("pool: weighted sums on tcgen05 (debug hook)")
     step = Step(dev, seed=0)
     step.model.use_cuda_graph = False
     step.run_resident(); torch.cuda.synchronize()
