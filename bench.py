@@ -429,6 +429,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     from gridmm_b200 import _lib
+    if os.environ.get("GRIDMM_POOL_SPLIT") in ("0", "1"):   # A/B: softmax weights of the pooling sums as one fp16 / value + residual
+        import ctypes
+        _lib.load().gridmm_debug_set_pool_split.argtypes = [ctypes.c_int]
+        _lib.load().gridmm_debug_set_pool_split(int(os.environ["GRIDMM_POOL_SPLIT"]))
     if os.environ.get("GRIDMM_GEMM_384") == "1":          # A/B: with the (opt-in) 256 x 384 pair tiles
         import ctypes
         _lib.load().gridmm_debug_set_gemm_384.argtypes = [ctypes.c_int]

@@ -59,6 +59,7 @@ struct PoolParams {
     float* w_out;            // [B, cap] relevance weight per sorted position, or null (tests; the first pass of a long text)
     const float* w_in;       // [B, cap] row maxima over the text positions an EARLIER launch covered (merged into w), or null
     int max_only;            // 1: only w_out is produced (first pass over a text longer than 128 positions): no softmax, no sums
+    int split_weights;       // mma.sync sums: 1 = every softmax weight enters as fp16 value + fp16 residual (two MMAs), 0 = fp16 value only
     int batch, t_cap, cap, n_cells;
     int l_pad;               // text positions of THIS launch (<= 128: one per tensor-memory lane)
     int slot_rows, view_rows, tok_off;   // row = slot*slot_rows + view*view_rows + tok_off + patch
@@ -727,7 +728,9 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                         const __half2 lo = __floats2half2_rn(w.x - fhi.x, w.y - fhi.y);
                         bh[ks][h] = *reinterpret_cast<const uint32_t*>(&hi);
                         bl[ks][h] = *reinterpret_cast<const uint32_t*>(&lo);
-                        add += w.x + w.y;
+                        // the normaliser is the sum of the weights the MMAs actually apply: with single fp16 weights the
+                        // result is an exactly normalised convex combination with weights perturbed by <= 2^-12 relative
+                        add += p.split_weights ? (w.x + w.y) : (fhi.x + fhi.y);
                     }
                 add += __shfl_xor_sync(0xffffffffu, add, 1);
                 add += __shfl_xor_sync(0xffffffffu, add, 2);
@@ -747,9 +750,10 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                             asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                          : "+f"(cacc[ct][0]), "+f"(cacc[ct][1]), "+f"(cacc[ct][2]), "+f"(cacc[ct][3])
                                          : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bh[ks][0]), "r"(bh[ks][1]));
-                            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                         : "+f"(cacc[ct][0]), "+f"(cacc[ct][1]), "+f"(cacc[ct][2]), "+f"(cacc[ct][3])
-                                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bl[ks][0]), "r"(bl[ks][1]));
+                            if (p.split_weights)
+                                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                             : "+f"(cacc[ct][0]), "+f"(cacc[ct][1]), "+f"(cacc[ct][2]), "+f"(cacc[ct][3])
+                                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bl[ks][0]), "r"(bl[ks][1]));
                         }
                     }
                 }
@@ -976,6 +980,9 @@ static int launch_pool(const void* fts, long long fts_rows, const void* text_fts
 }  // namespace gmm
 
 static long long* g_pool_dbg = nullptr;
+static int g_pool_split = 1;
+// Debug hook: 0 = single fp16 softmax weights in the mma.sync weighted sums (half the HMMA count), 1 = value + residual.
+extern "C" void gridmm_debug_set_pool_split(int on) { g_pool_split = on; }
 static int g_pool_hmma = 1;
 // Weighted-sum stage: 1 (default) = warp-level mma.sync from the resident tile, accumulators in registers; 0 = tcgen05 (MN-major A
 // operand out of the same tile, weight operand built by the softmax warp, accumulators in tensor memory read back by four epilogue
@@ -1003,7 +1010,7 @@ extern "C" int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, co
     PoolParams p;
     p.slots = slots; p.perm = perm; p.cell_start = cell_start; p.cell_rank = cell_rank;
     p.text_ws = reinterpret_cast<const uint4*>(text_ws);
-    p.pooled = reinterpret_cast<__half*>(pooled); p.w_out = w_out; p.w_in = nullptr; p.max_only = 0;
+    p.pooled = reinterpret_cast<__half*>(pooled); p.w_out = w_out; p.w_in = nullptr; p.max_only = 0; p.split_weights = g_pool_split;
     p.batch = batch; p.t_cap = t_cap; p.cap = cap; p.n_cells = n_cells; p.l_pad = l_pad;
     p.slot_rows = slot_rows; p.view_rows = view_rows; p.tok_off = tok_off; p.dbg = g_pool_dbg;
     const int sms = gridmm_sm_count();

@@ -303,6 +303,7 @@ void gridmm_debug_set_attn_legacy(int on);    /* gridmm_attention_f16: 1 forces 
 void gridmm_debug_set_ln_cluster(int cl);     /* force the cluster size (2 / 6) of gridmm_linear_ln_f16; 0 = automatic */
 void gridmm_debug_set_gemm_pairs(int on);    /* 0: disable the cta_group::2 GEMM path (A/B timing) */
 void gridmm_debug_set_pool_hmma(int on);     /* gridmm_pool's weighted-sum stage: 1 (default) mma.sync from the resident tile, 0 tcgen05 (measured slower) */
+void gridmm_debug_set_pool_split(int on);    /* gridmm_pool (mma.sync sums): 0 = single fp16 softmax weights, 1 = value + residual */
 void gridmm_debug_set_gemm_384(int on);      /* 1: enable the 256 x 384 pair tiles of gridmm_linear_f16 (off by default: measured slower) */
 
 #ifdef __cplusplus

@@ -24,3 +24,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionstart(session):
+    """GRIDMM_POOL_SPLIT=0/1 runs the whole GPU suite with single / value + residual softmax weights in gridmm_pool (A/B of the
+    accuracy cost of halving the pooling kernel's HMMA count)."""
+    v = os.environ.get("GRIDMM_POOL_SPLIT")
+    if v in ("0", "1"):
+        try:
+            import ctypes
+            from gridmm_b200 import _lib
+            lib = _lib.load()
+            lib.gridmm_debug_set_pool_split.argtypes = [ctypes.c_int]
+            lib.gridmm_debug_set_pool_split(int(v))
+        except Exception:
+            pass

@@ -130,6 +130,10 @@ if "pool" in want:
         lib.gridmm_debug_set_pool_hmma.argtypes = [ctypes.c_int]
         lib.gridmm_debug_set_pool_hmma(0)
         print("pool: weighted sums on tcgen05 (debug hook)")
+    if os.environ.get("GRIDMM_POOL_SPLIT") in ("0", "1"):
+        lib.gridmm_debug_set_pool_split.argtypes = [ctypes.c_int]
+        lib.gridmm_debug_set_pool_split(int(os.environ["GRIDMM_POOL_SPLIT"]))
+        print("pool: split weights =", os.environ["GRIDMM_POOL_SPLIT"])
     step = Step(dev, seed=0)
     step.model.use_cuda_graph = False
     step.run_resident(); torch.cuda.synchronize()
