@@ -1144,11 +1144,14 @@ class GlocalTextPathNavCMT(nn.Module):
         B, L = int(txt_ids.shape[0]), int(txt_ids.shape[1])
         txt_masks = torch.arange(L, device=dev)[None, :] < txt_lens[:, None]
         txt = self.forward_text(txt_ids, txt_masks)
-        if batch.get("traj_obj_img_fts") is not None:
-            raise NotImplementedError("object tokens in pretraining batches (REVERIE / SOON) are not wired yet")
-        pano, _ = self.forward_panorama_per_step(batch["traj_view_img_fts"], None, batch["traj_loc_fts"], batch["traj_nav_types"],
-                                                 batch["traj_vp_view_lens"], None)
+        # every panorama of every path through the image embeddings + pano encoder; REVERIE / SOON batches carry object tokens
+        # behind the views (pretrain_src/model/vilmodel.py:496-512), which forward_panorama_per_step already packs
+        obj = batch.get("traj_obj_img_fts")
+        pano, _ = self.forward_panorama_per_step(batch["traj_view_img_fts"], obj, batch["traj_loc_fts"], batch["traj_nav_types"],
+                                                 batch["traj_vp_view_lens"], batch["traj_vp_obj_lens"] if obj is not None else None)
         lens = torch.as_tensor(batch["traj_vp_view_lens"]).to(dev)
+        if obj is not None:
+            lens = lens + torch.as_tensor(batch["traj_vp_obj_lens"]).to(dev)
         step_lens = [int(x) for x in batch["traj_step_lens"]]
         gmap_img = self._aggregate_gmap(pano, lens, step_lens, batch["traj_vpids"], batch["traj_cand_vpids"], batch["gmap_vpids"])
         gmap_lens = torch.as_tensor(batch["gmap_lens"]).to(dev)

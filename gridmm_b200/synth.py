@@ -182,8 +182,9 @@ def make_pano_inputs(batch, seed=0, n_views=36, n_objs=0, dim=768, loc_dim=7):
     return out
 
 
-def make_pretrain_batch(batch, seed=0, txt_len=40, max_steps=4, n_views=36, n_cands=3, dim=768, vocab=30522, min_txt=8):
-    """One collated pretraining batch without objects, in the layout pretrain_src/data/tasks.py's collate functions hand to
+def make_pretrain_batch(batch, seed=0, txt_len=40, max_steps=4, n_views=36, n_cands=3, dim=768, vocab=30522, min_txt=8, n_objs=0):
+    """One collated pretraining batch (n_objs > 0: with REVERIE / SOON object tokens: `traj_obj_img_fts`, `traj_vp_obj_lens`, nav
+    type 2, pretrain_src/model/vilmodel.py:487-512), in the layout pretrain_src/data/tasks.py's collate functions hand to
     `GlocalTextPathCMT.forward` / `forward_mlm` (pretrain_src/model/vilmodel.py:668-674, 767-771), minus the grid tensors
     (those come from the grid build over the same paths).  Episode b walks steps[b] viewpoints "v{b}_{t}"; each panorama has
     n_views views of which the first n_cands are navigable candidates: the next viewpoint of the path, the previous one, and
@@ -229,7 +230,7 @@ def make_pretrain_batch(batch, seed=0, txt_len=40, max_steps=4, n_views=36, n_ca
         gmap_step_ids[b, :gmap_lens[b]] = gmap_step[b]
     gmap_pos_fts = rng.standard_normal((B, G, 7), dtype=f32) * gmap_masks[:, :, None]
     vp_pos_fts = rng.standard_normal((B, 1 + n_views, 14), dtype=f32)
-    return {
+    out = {
         "txt_ids": txt_ids, "txt_lens": txt_lens.astype(np.int64),
         "traj_view_img_fts": traj_view_img_fts, "traj_loc_fts": traj_loc_fts, "traj_nav_types": traj_nav_types,
         "traj_step_lens": [int(x) for x in steps], "traj_vp_view_lens": np.full(n_tot, n_views, dtype=np.int64),
@@ -237,6 +238,17 @@ def make_pretrain_batch(batch, seed=0, txt_len=40, max_steps=4, n_views=36, n_ca
         "gmap_lens": gmap_lens, "gmap_step_ids": gmap_step_ids, "gmap_pos_fts": gmap_pos_fts,
         "gmap_pair_dists": np.zeros((B, G, G), dtype=f32), "gmap_vpids": gmap_vpids, "vp_pos_fts": vp_pos_fts,
     }
+    if n_objs > 0:
+        # drawn AFTER everything above, so that the object-free batch of the same seed is unchanged
+        obj_lens = rng.integers(0, n_objs + 1, size=n_tot).astype(np.int64)
+        obj_lens[0] = n_objs                                  # the padded panorama length is n_views + n_objs
+        obj_valid = np.arange(n_objs)[None, :] < obj_lens[:, None]
+        out["traj_obj_img_fts"] = rng.standard_normal((n_tot, n_objs, dim), dtype=f32) * obj_valid[:, :, None]
+        out["traj_vp_obj_lens"] = obj_lens
+        out["traj_loc_fts"] = np.concatenate([traj_loc_fts, rng.standard_normal((n_tot, n_objs, 7), dtype=f32) * obj_valid[:, :, None]], 1)
+        out["traj_nav_types"] = np.concatenate([traj_nav_types, 2 * obj_valid.astype(np.int64)], 1)
+        out["vp_pos_fts"] = np.concatenate([vp_pos_fts, rng.standard_normal((B, n_objs, 14), dtype=f32)], 1)
+    return out
 
 
 def make_pretrain_labels(pb, seed=0, n_masked=2):

@@ -252,11 +252,11 @@ def ref_pretrain_traj(ds, scan, headings, depth_u16, clip_f32, pos_xy):
     return cells, pos_fts, targets, grid_fts.reshape((-1, clip_f32[0].shape[-1]))
 
 
-def make_pretrain_config(num_l_layers=9, num_pano_layers=2, num_x_layers=4):
-    """BertConfig + the keys of pretrain_src/config/r2r_model_config.json."""
+def make_pretrain_config(num_l_layers=9, num_pano_layers=2, num_x_layers=4, obj_feat_size=0):
+    """BertConfig + the keys of pretrain_src/config/r2r_model_config.json (obj_feat_size > 0: the REVERIE / SOON configs)."""
     from transformers import BertConfig
     c = BertConfig()
-    for k, v in dict(pred_head_dropout_prob=0.1, image_feat_size=768, image_prob_size=1000, angle_feat_size=4, obj_feat_size=0,
+    for k, v in dict(pred_head_dropout_prob=0.1, image_feat_size=768, image_prob_size=1000, angle_feat_size=4, obj_feat_size=obj_feat_size,
                      obj_prob_size=0, num_l_layers=num_l_layers, num_x_layers=num_x_layers, num_pano_layers=num_pano_layers,
                      max_action_steps=100, update_lang_bert=True, use_lang2visn_attn=True, graph_sprels=True,
                      glocal_fuse=True).items():

@@ -132,6 +132,47 @@ def make_pretrain_model():
     print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()})
 
 
+PRETRAIN_OBJ_CASE = dict(seed=62, batch=3, max_steps=3, txt_len=32, n_objs=6,
+                         model=dict(num_l_layers=1, num_pano_layers=2, num_x_layers=2, obj_feat_size=768))
+
+
+def make_pretrain_obj():
+    """pretrain_obj_small.npz: the pretraining trunk's `forward` on a REVERIE-style batch WITH object tokens
+    (`traj_obj_img_fts` / `traj_vp_obj_lens`, pretrain_src/model/vilmodel.py:496-512, 722-731)."""
+    import json
+    case = PRETRAIN_OBJ_CASE
+    B, seed = case["batch"], case["seed"]
+    model = _refshim.load_reference_pretrain_model(**case["model"])
+    shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
+    w = synth.make_weights(shapes, seed=seed)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    pb = synth.make_pretrain_batch(B, seed=seed, txt_len=case["txt_len"], max_steps=case["max_steps"], n_objs=case["n_objs"])
+    ep = synth.make_episodes(B, case["max_steps"], seed=seed, dim=768)
+    heads = synth.pretrain_headings(ep)
+    ds = _refshim.load_reference_pretrain_data()
+    gfts, gmap, gpos = [], [], []
+    for b in range(B):
+        T = pb["traj_step_lens"][b]
+        cells, pos_fts, _, fts = _refshim.ref_pretrain_traj(
+            ds, "scan%d" % b, [float(x) for x in heads[b, :T]], [synth.expand_depth(ep["depth_sub"][b, t]) for t in range(T)],
+            [ep["clip"][b, t].astype(np.float32) for t in range(T)], ep["pos"][b, :T])
+        gfts.append(torch.from_numpy(fts).to(torch.float16))
+        gmap.append(torch.from_numpy(cells[-1]).to(torch.int64))
+        gpos.append(pos_fts[-1])
+    t = lambda k: torch.from_numpy(pb[k])
+    args = (t("txt_ids"), t("txt_lens"), t("traj_view_img_fts"), t("traj_obj_img_fts"), t("traj_loc_fts"), t("traj_nav_types"),
+            pb["traj_step_lens"], t("traj_vp_view_lens"), t("traj_vp_obj_lens"), pb["traj_vpids"], pb["traj_cand_vpids"], t("gmap_lens"),
+            t("gmap_step_ids"), t("gmap_pos_fts"), t("gmap_pair_dists"), pb["gmap_vpids"], t("vp_pos_fts"), gfts, gmap)
+    gp = torch.from_numpy(np.stack(gpos).astype(np.float32))
+    with torch.no_grad():
+        gmap_e, vp_e, grid_g = model.forward(*args, None, gp)
+    save = {"gmap_embeds": gmap_e.numpy(), "vp_embeds": vp_e.numpy(), "grid_gmap_embeds": grid_g.numpy()}
+    path = os.path.join(GOLD, "pretrain_obj_small.npz")
+    np.savez_compressed(path, **save)
+    json.dump(shapes, open(os.path.join(GOLD, "pretrain_obj_small_spec.json"), "w"), indent=0)
+    print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()})
+
+
 def make_pretrain_heads():
     """pretrain_heads_small.npz: `GlocalTextPathCMTPreTraining.forward_sap` (logits and per-sample losses) and `.forward_mlm`
     (vocabulary scores at the masked positions) on the batch of pretrain_small.npz (pretrain_src/model/pretrain_cmt.py:128-292);
@@ -300,7 +341,7 @@ if __name__ == "__main__":
         raise SystemExit("reference not available at %s" % _refshim.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain", "pretrain_model", "pretrain_heads"]
+    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain", "pretrain_model", "pretrain_heads", "pretrain_obj"]
     if "grid" in which:
         make_grid()
     if "nav" in which:
@@ -315,3 +356,5 @@ if __name__ == "__main__":
         make_pretrain_model()
     if "pretrain_heads" in which:
         make_pretrain_heads()
+    if "pretrain_obj" in which:
+        make_pretrain_obj()

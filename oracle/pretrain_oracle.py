@@ -25,13 +25,16 @@ from oracle import model_oracle as mo
 
 
 def trajectory_embeddings(sd, batch, n_pano_layers=2):
-    """ImageEmbeddings.forward without objects (vilmodel.py:487-530) over all panoramas of all paths: [sum_T, V, 768] -> per
-    episode a [T_b, V, 768] block and its view counts."""
-    pano = {"view_img_fts": batch["traj_view_img_fts"], "view_lens": batch["traj_vp_view_lens"], "obj_img_fts": None,
+    """ImageEmbeddings.forward (vilmodel.py:487-530; object tokens :496-512 when the batch carries `traj_obj_img_fts`) over all
+    panoramas of all paths: [sum_T, V, 768] -> per episode a [T_b, V, 768] block and its token counts (views + objects)."""
+    obj = batch.get("traj_obj_img_fts")
+    pano = {"view_img_fts": batch["traj_view_img_fts"], "view_lens": batch["traj_vp_view_lens"], "obj_img_fts": obj,
+            "obj_lens": batch.get("traj_vp_obj_lens") if obj is not None else None,
             "loc_fts": batch["traj_loc_fts"], "nav_types": batch["traj_nav_types"]}
     x, _ = mo.panorama(sd, pano, n_layers=n_pano_layers)            # same arithmetic as forward('panorama')
     steps = list(batch["traj_step_lens"])
-    return list(torch.split(x, steps, 0)), list(torch.split(batch["traj_vp_view_lens"], steps, 0))
+    lens = batch["traj_vp_view_lens"] + (batch["traj_vp_obj_lens"] if obj is not None else 0)
+    return list(torch.split(x, steps, 0)), list(torch.split(lens, steps, 0))
 
 
 def aggregate_gmap_features(split_embeds, split_lens, traj_vpids, traj_cand_vpids, gmap_vpids):

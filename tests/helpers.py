@@ -27,6 +27,8 @@ AUX_CASES = {
 
 PRETRAIN_GRID_CASE = dict(seed=51, batch=3, steps=7)      # mirrors oracle/make_golden.py
 PRETRAIN_MODEL_CASE = dict(seed=61, batch=3, max_steps=4, txt_len=40, model=dict(num_l_layers=2, num_pano_layers=2, num_x_layers=4))
+PRETRAIN_OBJ_CASE = dict(seed=62, batch=3, max_steps=3, txt_len=32, n_objs=6,
+                         model=dict(num_l_layers=1, num_pano_layers=2, num_x_layers=2, obj_feat_size=768))     # mirrors make_golden.py
 CE_GRID_CASE = dict(seed=41, batch=3, steps=6)
 CE_NAV_CASE = (dict(batch=3, steps=3, seed=42), dict(txt_len=24, gmap_len=10, n_views=12, n_objs=0))
 
@@ -106,7 +108,7 @@ def pretrain_batch(case):
     build over each path (bit-identical to the pretraining dataset's, see test_grid_oracle_matches_pretraining_dataset)."""
     from oracle import grid_oracle as go
     B = case["batch"]
-    pb = synth.make_pretrain_batch(B, seed=case["seed"], txt_len=case["txt_len"], max_steps=case["max_steps"])
+    pb = synth.make_pretrain_batch(B, seed=case["seed"], txt_len=case["txt_len"], max_steps=case["max_steps"], n_objs=case.get("n_objs", 0))
     ep = synth.make_episodes(B, case["max_steps"], seed=case["seed"], dim=768)
     heads = synth.pretrain_headings(ep)
     batch = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in pb.items()}

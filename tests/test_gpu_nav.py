@@ -214,6 +214,29 @@ def test_pretrain_trunk_matches_reference_golden():
     assert max(errs.values()) <= 4e-3, errs        # measured 2.0e-3 (the reference pools in fp16 here)
 
 
+def test_pretrain_trunk_with_object_tokens_matches_reference_golden():
+    """SURVEY 8a row 19 with REVERIE / SOON object tokens in the pretraining batch (pretrain_src/model/vilmodel.py:496-512,
+    722-731), against the reference's own trunk (tests/golden/pretrain_obj_small.npz)."""
+    case = H.PRETRAIN_OBJ_CASE
+    gold = np.load(os.path.join(H.GOLD, "pretrain_obj_small.npz"))
+    cfg = H.make_config(pretrain_trunk=True, use_lang2visn_attn=True, **case["model"])
+    model, _ = _model(cfg, case["seed"])
+    batch = H.pretrain_batch(case)
+    gmap_e, vp_e, grid_g = model.forward_pretrain(batch, task="sap")
+    torch.cuda.synchronize()
+    valid_g = (torch.arange(gmap_e.shape[1])[None, :] < batch["gmap_lens"][:, None])
+    last = torch.tensor(np.cumsum(batch["traj_step_lens"]) - 1)
+    vp_lens = (batch["traj_vp_view_lens"] + batch["traj_vp_obj_lens"])[last] + 1
+    valid_v = torch.arange(vp_e.shape[1])[None, :] < vp_lens[:, None]
+    errs = {}
+    for got, key, valid in ((gmap_e, "gmap_embeds", valid_g), (vp_e, "vp_embeds", valid_v), (grid_g, "grid_gmap_embeds", valid_g)):
+        ref = torch.from_numpy(gold[key])
+        assert tuple(got.shape) == tuple(ref.shape), key
+        errs[key] = (got.float().cpu() - ref).abs()[valid].max().item()
+    print("pretrain trunk with objects: errors", errs)
+    assert max(errs.values()) <= 4e-3, errs
+
+
 def test_cuda_graph_replay_matches_eager():
     B, T, L, G = 8, 3, 40, 12
     from gridmm_b200.env import GridMapBuilder

@@ -114,6 +114,28 @@ def test_pretrain_oracle_matches_reference_trunk():
         assert err <= 5e-5, "%s: max abs error %.3e" % (key, err)
 
 
+def test_pretrain_oracle_matches_reference_trunk_with_object_tokens():
+    """REVERIE / SOON pretraining batches carry object tokens behind the views of every panorama (`traj_obj_img_fts`,
+    `traj_vp_obj_lens`: pretrain_src/model/vilmodel.py:496-512): the oracle against the reference's own trunk on such a batch
+    (tests/golden/pretrain_obj_small.npz)."""
+    import json
+    from oracle import pretrain_oracle as po
+    case = H.PRETRAIN_OBJ_CASE
+    gold = np.load(os.path.join(H.GOLD, "pretrain_obj_small.npz"))
+    shapes = json.load(open(os.path.join(H.GOLD, "pretrain_obj_small_spec.json")))
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_weights(shapes, seed=case["seed"]).items()}
+    batch = H.pretrain_batch(case)
+    assert int(batch["traj_vp_obj_lens"].max()) == case["n_objs"] and int(batch["traj_vp_obj_lens"].min()) < case["n_objs"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        gmap_e, vp_e, grid_g = po.forward(sd, batch, n_l_layers=case["model"]["num_l_layers"],
+                                          n_pano_layers=case["model"]["num_pano_layers"], n_x_layers=case["model"]["num_x_layers"])
+    for got, key in ((gmap_e, "gmap_embeds"), (vp_e, "vp_embeds"), (grid_g, "grid_gmap_embeds")):
+        assert tuple(got.shape) == gold[key].shape, key
+        err = (got - torch.from_numpy(gold[key])).abs().max().item()
+        assert err <= 5e-5, "%s: max abs error %.3e" % (key, err)
+
+
 def test_pretrain_oracle_matches_reference_task_heads():
     """oracle/pretrain_oracle.py `sap` / `mlm_scores` against the reference's own GlocalTextPathCMTPreTraining.forward_sap
     (logits + per-sample losses, which also cover the grid head) and .forward_mlm (scores at the masked positions) --
