@@ -299,8 +299,13 @@ def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
     txt = pm.forward_pretrain(batch, task="mlm")
     assert txt.shape == (case["batch"], case["txt_len"], 768)
     assert "linear_rows" not in calls                                       # the MLM exit leaves before the fusion encoder's K/V projection
-    with pytest.raises(NotImplementedError):
-        pm.forward_pretrain(dict(batch, traj_obj_img_fts=torch.zeros(1)), task="sap")
+    # REVERIE / SOON batches: object tokens behind the views of every panorama (host glue: packed panorama rows, lens = views + objects)
+    ocase = H.PRETRAIN_OBJ_CASE
+    om = GlocalTextPathNavCMT(H.make_config(pretrain_trunk=True, use_lang2visn_attn=True, **ocase["model"])).eval()
+    obatch = H.pretrain_batch(ocase)
+    calls.clear()
+    gmap_e, vp_e, grid_g = om.forward_pretrain(obatch, task="sap")
+    assert vp_e.shape == (ocase["batch"], 1 + 36 + ocase["n_objs"], 768) and gmap_e.shape[1] == int(obatch["gmap_lens"].max())
 
 
 def test_bench_reference_arm_prints_the_contract_line():
