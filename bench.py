@@ -14,6 +14,7 @@ N > 1: launched by torchrun, one rank per GPU, episodes sharded (weak scaling, n
 Prints ONE JSON line (rank 0).
 """
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -132,7 +133,8 @@ def cpu_reference_steps(ep, nav_np, cfg, w, n_steps, threads, device="cpu"):
             st.max_x, st.min_x, st.max_y, st.min_y = keep[1:]
         nav["grid_fts"], nav["grid_map"] = fts, cells
         nav["gridmap_pos_fts"] = torch.from_numpy(np.stack(pos).astype(np.float32)).to(device)
-        with torch.no_grad():
+        # device="cuda": the oracle's factory calls (torch.zeros / arange without a device) must land on the GPU too
+        with torch.no_grad(), (torch.device(device) if device != "cpu" else contextlib.nullcontext()):
             if CE:
                 nav["candidate_lengths"] = [int(x) for x in nav["vp_nav_masks"].sum(1)]
                 out = {"fused_logits": mo.navigation_ce(sd, nav, n_x_layers=cfg.num_x_layers)}
@@ -522,7 +524,7 @@ def main():
         tf = flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
         traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         except Exception:
             pass
         roofline = {"kernel": "tcgen05 GEMM kernels (gemm_f16_tn_kernel / gemm_ln_kernel, %d launches/step)" % round(g_n),

@@ -84,6 +84,17 @@ if "gemm" in want:
         gemm_case(B * Q, 3072, 768, act=1, tag="x ffn1"); gemm_case(B * Q, 2304, 768, tag="x qkv")
         gemm_case(B * S, 768, 768, tag="map xattn q"); gemm_case(B * L, 1536, 768, tag="txt kv")
 
+    # 256 x 384 pair tiles (opt-in) on the two shapes they were written for
+    lib.gridmm_debug_set_gemm_384.argtypes = [ctypes.c_int]
+    for on in (1, 0):
+        lib.gridmm_debug_set_gemm_384(on)
+        print("--- 256x384 pair tiles %s" % ("on" if on else "off"), flush=True)
+        gemm_case(B * Q, 3072, 768, act=1, tag="x ffn1"); gemm_case(B * Q, 2304, 768, tag="x qkv")
+    # the packed map sequence at this workload's row count (~4500 of 6912 padded rows)
+    print("--- map-sized GEMMs over 4480 rows (packed map sequence)", flush=True)
+    gemm_case(4480, 2304, 768, tag="map qkv (packed)"); gemm_case(4480, 3072, 768, act=1, tag="map ffn1 (packed)")
+    gemm_case(4480, 768, 768, tag="map xattn q (packed)")
+
 if "gemmln" in want:
     def ln_case(M, K, tag):
         a = torch.randn(M, K, device=dev).half(); w = (torch.randn(768, K, device=dev) * 0.02).half()

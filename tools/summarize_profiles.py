@@ -100,7 +100,7 @@ def step(src_csv, dst, traffic_json=None, pool_rep=None):
         pr = list(csv.reader(raw.splitlines()))
         pix = {h: i for i, h in enumerate(pr[0])}
         pb = sum(_bytes(pr[2][pix[m]], pr[1][pix[m]]) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-        json.dump({"source": "ncu --set full --clock-control none (tools/gpu_evidence.sh, B=32 T=8 step): dram__bytes_read.sum + dram__bytes_write.sum",
+        json.dump({"source": "ncu --set full --clock-control none (tools/gpu_r2_final.sh, B=32 T=8 step): dram__bytes_read.sum + dram__bytes_write.sum",
                    "pool_bytes_per_launch": pb, "gemm_bytes_per_step": gem}, open(traffic_json, "w"), indent=1)
 
 
