@@ -316,6 +316,34 @@ class Step:
         self.done_evt.synchronize()
         return float(self.h_out[0, 0])
 
+    # ---- end to end with a device-resident feature DB: the CLIP tokens of every viewpoint already live in HBM (uploaded once per
+    #      viewpoint; the whole Matterport DB is ~10 GB of 180), so a step's host inputs are the depth samples, poses, viewpoint
+    #      keys and the small nav tensors.  Reported as e2e.cached_* NEXT to the contract's e2e (which uploads the features).
+    def setup_cached(self):
+        from gridmm_b200.env import DeviceFeatureDB, GridMapBuilder
+        ep = self.ep
+        self.db = DeviceFeatureDB(capacity=B * T, device=self.dev)
+        self.keys = [["b%d_t%d" % (b, t) for b in range(B)] for t in range(T)]
+        for t in range(T):
+            for b in range(B):
+                self.db.put(self.keys[t][b], ep["clip"][b, t])
+        self.cbuilder = GridMapBuilder(B, max_steps=T, device=self.dev, geometry="r2r_ce" if CE else "r2r", feature_db=self.db)
+        for t in range(T - 1):
+            self.cbuilder.step(ep["depth_sub"][:, t], None, ep["pos"][:, t], ep["heading"][:, t], keys=self.keys[t])
+        self.c_saved = (self.cbuilder.bounds.clone(), self.cbuilder.n_pts.clone(), self.cbuilder.n_steps.copy(), self.cbuilder.n_calls)
+
+    def run_e2e_cached(self):
+        from gridmm_b200 import ops
+        cb = self.cbuilder
+        ops.copy_segments([(self.c_saved[0], cb.bounds), (self.c_saved[1], cb.n_pts)])
+        cb.n_steps = self.c_saved[2].copy(); cb.n_calls = self.c_saved[3]
+        ep = self.ep
+        grid = cb.step(self.h_depth, None, ep["pos"][:, T - 1], ep["heading"][:, T - 1], lazy=True, keys=self.keys[T - 1])
+        batch = dict(self.nav)
+        batch.update(self.h_nav)
+        out = self._forward(grid, batch)
+        return out["fused_logits"].cpu()
+
     def e2e_bytes(self):
         h2d = self.h_depth.numel() * self.h_depth.element_size() + self.h_clip.numel() * 2 + B * 28 * 4
         h2d += sum(v.numel() * v.element_size() for v in self.h_nav.values()) + B * (G * 4 + (1 + VIEWS + OBJS) * 4)
@@ -479,6 +507,8 @@ def main():
                 sp.e2e_result()
     ms_e2e = timed(e2e_step, args.steps, warmup, world)
     e2e_drain()
+    step.setup_cached()
+    ms_e2e_cached = timed(step.run_e2e_cached, args.steps, warmup, world)
     clocks = None
     if sampler:
         window = "timed region"
@@ -566,7 +596,11 @@ def main():
                         "mode": "two environment batches per GPU ping-pong on one model: each step's H2D (pinned host -> HBM, copy "
                                 "stream) overlaps the other batch's kernels; every step copies its own inputs in and its logits out",
                         "serial_value": world * B * args.steps / (ms_e2e_serial * 1e-3),
-                        "serial_ms_per_step": ms_e2e_serial / args.steps},
+                        "serial_ms_per_step": ms_e2e_serial / args.steps,
+                        "cached_value": world * B * args.steps / (ms_e2e_cached * 1e-3),
+                        "cached_ms_per_step": ms_e2e_cached / args.steps,
+                        "cached_mode": "serial loop with a device-resident feature DB (gridmm_b200.env.DeviceFeatureDB): the step names "
+                                       "viewpoint keys, its H2D is depth + poses + ids / masks (%d bytes), logits D2H" % (h2d - step.h_clip.numel() * 2)},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_pool": roofline_pool, "cpu_baseline": cpu,
                 "gpu_eager_baseline": eager,
                 "kernel_ms_per_step": {k: round(t, 4) for k, (t, _) in sorted(br.items(), key=lambda kv: -kv[1][0])}}

@@ -30,6 +30,8 @@ struct GridParams {
     const float* pose;         // [B, 4]  px, py, cos(map angle), sin(map angle)      (fp32-rounded on host)
     const float* view_cs;      // [B, 12, 2] cos/sin of every view's heading            (fp32-rounded on host)
     const uint8_t* active;     // [B] or null: 0 = episode receives no new viewpoint this step (cells are still re-assigned)
+    const int* new_slot;       // [B] or null: feature-slab slot of this step's viewpoint (device-resident feature DB): written
+    int* slots; int t_cap;     //   into slots[b, n_pts / 588], the table gridmm_pool resolves rows through
     // persistent per-episode state
     float* wx;                 // [B, cap]
     float* wy;                 // [B, cap]
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 1) grid_update_kernel(GridParams
             p.bounds[b * 4 + 0] = max_x; p.bounds[b * 4 + 1] = min_x;
             p.bounds[b * 4 + 2] = max_y; p.bounds[b * 4 + 3] = min_y;
             p.n_pts[b] = n;
+            if (p.new_slot && n_old / PTS_PER_VP < p.t_cap) p.slots[b * p.t_cap + n_old / PTS_PER_VP] = p.new_slot[b];
         }
         // window (env.py:322-331)
         const float ax = __fsub_rn(px, min_x), bx = __fsub_rn(max_x, px);
@@ -268,15 +271,18 @@ extern "C" int gridmm_grid_update(int batch, const void* depth, int depth_is_f32
                                   const float* view_cs, const unsigned char* active, const float* off7, int flip_y,
                                   int negate_map_x, int pos_mode, float max_dist, int grid_w, int cap, float* wx, float* wy, unsigned char* valid,
                                   float* bounds, int* n_pts, short* cell, float* half_len, int* perm, int* cell_start,
-                                  int* cell_rank, int* n_nonempty, float* pos_fts, cudaStream_t stream) {
+                                  int* cell_rank, int* n_nonempty, float* pos_fts, const int* new_slot, int* slots, int t_cap,
+                                  cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0) return 0;
     if (grid_w < 2 || grid_w * grid_w > MAX_CELLS || cap < PTS_PER_VP || cap > 65535) return GRIDMM_ERR_SHAPE;
+    if (new_slot && (!slots || t_cap < 1)) return GRIDMM_ERR_ARG;
     if (!depth || !pose || !view_cs || !off7 || !wx || !wy || !valid || !bounds || !n_pts || !cell || !half_len || !perm ||
         !cell_start || !cell_rank || !n_nonempty || !pos_fts)
         return GRIDMM_ERR_ARG;
     GridParams p;
     p.depth = depth; p.pose = pose; p.view_cs = view_cs; p.active = active;
+    p.new_slot = new_slot; p.slots = slots; p.t_cap = t_cap;
     p.wx = wx; p.wy = wy; p.valid = valid; p.bounds = bounds; p.n_pts = n_pts;
     p.cell = cell; p.half_len = half_len; p.perm = perm; p.cell_start = cell_start; p.cell_rank = cell_rank;
     p.n_nonempty = n_nonempty; p.pos_fts = pos_fts;

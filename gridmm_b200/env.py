@@ -129,12 +129,57 @@ class GridBatch:
         return out
 
 
+class DeviceFeatureDB:
+    """Device-resident counterpart of the reference's `SemanticFeaturesDB` (map_nav_src/r2r/env.py:98-113: an HDF5 file cached in a
+    host dict, from which every step's [12,50,768] tokens are re-uploaded inside the growing map, r2r/agent.py:168).  The CLIP patch
+    tokens of the 12 horizon views of every viewpoint are kept in HBM, uploaded ONCE per viewpoint -- the whole Matterport feature
+    DB is ~10 GB, a B200 has 180 -- and a navigation step only names slots: GridMapBuilder(feature_db=db).step(depth, None, pos,
+    heading, keys=[...]) moves no features at all (the pooling kernel gathers rows straight out of this buffer through its TMA
+    gather4 tensor map)."""
+
+    def __init__(self, capacity, feat_dim=768, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gridmm_b200.DeviceFeatureDB needs a CUDA device (there is no CPU path)")
+        self.capacity, self.feat_dim, self.device = int(capacity), int(feat_dim), torch.device(device)
+        self.buffer = torch.empty(self.capacity, 12 * VIEW_TOKENS, self.feat_dim, dtype=torch.float16, device=self.device)
+        self.index = {}
+
+    def __contains__(self, key):
+        return key in self.index
+
+    def __len__(self):
+        return len(self.index)
+
+    def put(self, key, fts):
+        """fts: [12,50,D] fp16 tokens of the 12 horizon views (CLS first), or the reference's [36,50,D] (views 12..23 are taken,
+        r2r/env.py:296); numpy / host tensor / device tensor.  Returns the slot; a key already present keeps its slot."""
+        slot = self.index.get(key)
+        if slot is not None:
+            return slot
+        if len(self.index) >= self.capacity:
+            raise RuntimeError("DeviceFeatureDB is full (%d viewpoints)" % self.capacity)
+        t = torch.as_tensor(fts)
+        if t.shape[0] == 36:
+            t = t[12:24]
+        slot = len(self.index)
+        self.buffer[slot].copy_(t.reshape(12 * VIEW_TOKENS, self.feat_dim).to(torch.float16), non_blocking=True)
+        self.index[key] = slot
+        return slot
+
+    def slots(self, keys):
+        try:
+            return np.fromiter((self.index[k] for k in keys), dtype=np.int32, count=len(keys))
+        except KeyError as e:
+            raise KeyError("viewpoint %r is not in the device feature DB: put() it first" % (e.args[0],))
+
+
 class GridMapBuilder:
     """`EnvBatch`-side replacement: persistent device buffers + one launch per step for the whole batch."""
 
-    def __init__(self, batch_size, feat_dim=768, grid_w=14, geometry="r2r", max_steps=16, device="cuda"):
+    def __init__(self, batch_size, feat_dim=768, grid_w=14, geometry="r2r", max_steps=16, device="cuda", feature_db=None):
         if not torch.cuda.is_available():
             raise RuntimeError("gridmm_b200.GridMapBuilder needs a CUDA device (there is no CPU path)")
+        self.feature_db = feature_db           # DeviceFeatureDB: the feature slab IS the DB, steps only name slots
         self.batch = int(batch_size)
         self.feat_dim = int(feat_dim)
         self.grid_w = int(grid_w)
@@ -157,14 +202,16 @@ class GridMapBuilder:
         self._depth_elt = 4 if self.geom.depth_is_f32 else 2
         self._off_view = B * 4 * 4
         self._off_depth = self._off_view + B * 24 * 4
-        self._pack_bytes = self._off_depth + B * PTS * self._depth_elt
+        self._off_slot = self._off_depth + B * PTS * self._depth_elt
+        self._pack_bytes = self._off_slot + B * 4
         self._h_packs = [torch.empty(self._pack_bytes, dtype=torch.uint8).pin_memory() for _ in range(3)]
         self._h_evts = [None, None, None]
         self._h_next = 0
         self._d_pack = torch.empty(self._pack_bytes, dtype=torch.uint8, device=dev)
         self.d_pose = self._d_pack[:self._off_view].view(torch.float32).view(B, 4)
         self.d_view = self._d_pack[self._off_view:self._off_depth].view(torch.float32).view(B, 24)
-        self.d_depth = self._d_pack[self._off_depth:].view(torch.float32 if self.geom.depth_is_f32 else torch.int16).view(B, PTS)
+        self.d_depth = self._d_pack[self._off_depth:self._off_slot].view(torch.float32 if self.geom.depth_is_f32 else torch.int16).view(B, PTS)
+        self.d_new_slot = self._d_pack[self._off_slot:].view(torch.int32)
         self.h_clip = torch.empty(B, 12, VIEW_TOKENS, self.feat_dim, dtype=torch.float16).pin_memory()
         self._copy_stream = None
         self._staged_evt = None
@@ -180,12 +227,14 @@ class GridMapBuilder:
         cap = t_cap * PTS
         if cap > 65535:
             raise ValueError("at most 111 viewpoints per episode (cell sort uses 16-bit cursors)")
-        slab = torch.empty(t_cap, B, 12 * VIEW_TOKENS, D, dtype=torch.float16, device=dev)
+        db = getattr(self, "feature_db", None)
+        slab = db.buffer if db is not None else torch.empty(t_cap, B, 12 * VIEW_TOKENS, D, dtype=torch.float16, device=dev)
         wx = torch.zeros(B, cap, dtype=torch.float32, device=dev)
         wy = torch.zeros(B, cap, dtype=torch.float32, device=dev)
         valid = torch.zeros(B, cap, dtype=torch.uint8, device=dev)
         if old:
-            slab[:old].copy_(self.slab)
+            if db is None:
+                slab[:old].copy_(self.slab)
             wx[:, :old * PTS].copy_(self.wx); wy[:, :old * PTS].copy_(self.wy); valid[:, :old * PTS].copy_(self.valid)
         self.slab, self.wx, self.wy, self.valid = slab, wx, wy, valid
         self.cell = torch.full((B, cap), -1, dtype=torch.int16, device=dev)
@@ -196,7 +245,10 @@ class GridMapBuilder:
         if old and getattr(self, "_slots_host", None) is not None:
             slots[:, :old] = self._slots_host
         self._slots_host = slots
-        self.slots = slots.to(dev)
+        new_slots = slots.to(dev)
+        if old and db is not None:
+            new_slots[:, :old].copy_(self.slots)          # feature-DB mode: the table is written on the device (gridmm_grid_update)
+        self.slots = new_slots
         self.t_cap, self.cap = t_cap, cap
 
     def _grow(self):
@@ -300,17 +352,21 @@ class GridMapBuilder:
 
     def _launch_update(self, d_active):
         g = self.geom
+        db = self.feature_db is not None
         ops.grid_update(self.batch, self.d_depth, g.depth_is_f32, g.depth_scale, self.d_pose, self.d_view, d_active, g.off7, g.flip_y,
                         g.negate_map_x, g.pos_mode, g.max_dist, self.grid_w, self.cap, self.wx, self.wy, self.valid, self.bounds, self.n_pts,
-                        self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts)
+                        self.cell, self.half_len, self.perm, self.cell_start, self.cell_rank, self.n_nonempty, self.pos_fts,
+                        new_slot=self.d_new_slot if db else None, slots=self.slots if db else None, t_cap=self.t_cap)
 
-    def step(self, depth_sub, clip, pos_xy, heading, active=None, lazy=False):
+    def step(self, depth_sub, clip, pos_xy, heading, active=None, lazy=False, keys=None):
         """Append one viewpoint per episode and rebuild the grid assignment (getStates' grid half, env.py:392-398).
 
         depth_sub : [B,12,49] uint16 (0.25 mm) or float32 metres (CE); numpy (host) or a device tensor
         clip      : [B,12,50,D] fp16 CLIP tokens incl. CLS; numpy / host tensor (copied H2D) or a device tensor; None when the
                     copy was started earlier with stage_features()
         pos_xy    : [B,2] viewpoint x,y (python floats / float64);  heading : [B] radians
+        keys      : feature-DB mode (GridMapBuilder(feature_db=...)): the B viewpoint keys (or int slots) of this step; `clip` is
+                    ignored -- no feature bytes move, the step only names where they already are in HBM
         active    : optional [B] bools; episodes with 0 receive no viewpoint in this call
         lazy      : stage the inputs now but leave the launch of gridmm_grid_update to the consumer of the returned GridBatch
                     (forward('navigation') launches it as its first kernel, inside its CUDA graph when graphs are enabled)
@@ -322,7 +378,15 @@ class GridMapBuilder:
             self._grow()
         t = self.n_calls                  # slab row block of this call (all B viewpoints, active or not, land in slab[t])
         d_active = None
-        if active is not None and not bool(np.all(active)):
+        db = self.feature_db
+        if db is not None:
+            if keys is None:
+                raise ValueError("GridMapBuilder(feature_db=...) steps by viewpoint key: pass keys=[...]")
+            new_slots = np.asarray(keys, dtype=np.int32) if isinstance(keys, np.ndarray) or isinstance(keys[0], (int, np.integer)) \
+                else db.slots(keys)
+            if active is not None and not bool(np.all(active)):
+                d_active = torch.from_numpy(np.asarray(active).astype(np.uint8).reshape(B)).to(self.device)
+        elif active is not None and not bool(np.all(active)):
             # Episodes with active[b] == 0 receive no viewpoint (the kernel leaves their points / bounds alone and only re-assigns
             # cells to the window of the pose passed for them); the others append theirs as viewpoint n_steps[b], which lives in
             # slab row block t = this call's index.
@@ -337,8 +401,10 @@ class GridMapBuilder:
             idx = torch.arange(B)
             self._slots_host[idx, torch.from_numpy(self.n_steps)] = (t * B + idx).to(torch.int32)
             self.slots.copy_(self._slots_host, non_blocking=False)
-        # features: one contiguous copy into slab[t]
-        if clip is None:
+        # features: one contiguous copy into slab[t] (feature-DB mode: nothing to copy)
+        if db is not None:
+            pass
+        elif clip is None:
             if self._staged_step != t or self._staged_evt is None:
                 raise RuntimeError("step(clip=None) needs stage_features() for this step first")
             torch.cuda.current_stream(self.device).wait_event(self._staged_evt)
@@ -361,9 +427,13 @@ class GridMapBuilder:
         pose = hp_np[:self._off_view].view(np.float32).reshape(B, 4)
         view = hp_np[self._off_view:self._off_depth].view(np.float32).reshape(B, 24)
         self.host_pose(pos_xy, heading, out=(pose, view))
+        if db is not None:
+            hp_np[self._off_slot:].view(np.int32)[:] = new_slots
         depth_on_device = isinstance(depth_sub, torch.Tensor) and depth_sub.is_cuda
         if depth_on_device:
             n_h2d = self._off_depth
+            if db is not None:
+                self.d_new_slot.copy_(torch.from_numpy(new_slots), non_blocking=False)
         else:
             n_h2d = self._pack_bytes
             dst = hp_np[self._off_depth:].view(np.float32 if g.depth_is_f32 else np.uint16).reshape(B, PTS)

@@ -1218,6 +1218,13 @@ class GlocalTextPathNavCMT(nn.Module):
             out[b, :n] = torch.cat((logits[b, 1:n], logits[b, 0:1]), 0)
         return out
 
+    def _plist_device(self):
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = list(self.parameters())
+            self.__dict__["_plist"] = plist
+        return plist[0].device
+
     def _require_eval(self):
         """The kernels behind forward() are inference kernels: dropout is the identity and no autograd graph is recorded (the
         outputs never require grad).  The reference's fine-tuning loop calls loss.backward() on these outputs
@@ -1231,6 +1238,11 @@ class GlocalTextPathNavCMT(nn.Module):
     def forward(self, mode, batch, **kwargs):
         """vilmodel.py:920-939.  A tuple batch selects the continuous-env calling convention (gridmap/vilmodel.py:802-817)."""
         self._require_eval()
+        dev = self._plist_device()
+        if dev.type == "cuda" and torch.cuda.current_device() != dev.index:
+            # the kernels launch on the CURRENT device and on its current stream: make that the model's device
+            with torch.cuda.device(dev):
+                return self.forward(mode, batch, **kwargs)
         if isinstance(batch, (tuple, list)):
             if mode == "language":
                 return self.forward_text(batch[0], batch[1])

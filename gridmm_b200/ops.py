@@ -313,14 +313,15 @@ def ce_logits(raw_global, raw_local, raw_fuse, vp_nav_masks, fused, batch, G, V,
 
 def grid_update(batch, depth, depth_is_f32, depth_scale, pose, view_cs, active, off7_host, flip_y, negate_map_x, pos_mode,
                 max_dist, grid_w, cap,
-                wx, wy, valid, bounds, n_pts, cell, half_len, perm, cell_start, cell_rank, n_nonempty, pos_fts):
+                wx, wy, valid, bounds, n_pts, cell, half_len, perm, cell_start, cell_rank, n_nonempty, pos_fts,
+                new_slot=None, slots=None, t_cap=0):
     import ctypes
     off = (ctypes.c_float * 7)(*[float(x) for x in off7_host])
     _lib.call("gridmm_grid_update", batch, depth.data_ptr(), int(depth_is_f32), float(depth_scale), pose.data_ptr(),
               view_cs.data_ptr(), _lib.ptr(active), ctypes.cast(off, ctypes.c_void_p), int(flip_y), int(negate_map_x),
               int(pos_mode), float(max_dist), grid_w, cap, wx.data_ptr(), wy.data_ptr(), valid.data_ptr(), bounds.data_ptr(), n_pts.data_ptr(), cell.data_ptr(),
               half_len.data_ptr(), perm.data_ptr(), cell_start.data_ptr(), cell_rank.data_ptr(), n_nonempty.data_ptr(),
-              pos_fts.data_ptr(), _lib.stream_ptr())
+              pos_fts.data_ptr(), _lib.ptr(new_slot), _lib.ptr(slots), int(t_cap), _lib.stream_ptr())
 
 
 _POOL_WS = {}

@@ -57,7 +57,10 @@ int gridmm_grid_update(int batch, const void* depth, int depth_is_f32, float dep
                        const float* view_cs, const unsigned char* active, const float* off7, int flip_y, int negate_map_x,
                        int pos_mode, float max_dist, int grid_w, int cap, float* wx, float* wy, unsigned char* valid, float* bounds, int* n_pts,
                        short* cell, float* half_len, int* perm, int* cell_start, int* cell_rank, int* n_nonempty,
-                       float* pos_fts, cudaStream_t stream);
+                       float* pos_fts, const int* new_slot, int* slots, int t_cap, cudaStream_t stream);
+/* new_slot (optional, device int[batch]) + slots (device int[batch, t_cap]): device-resident feature DB -- the CLIP tokens of every
+ * viewpoint already live in HBM (the whole Matterport feature DB is ~10 GB of 180), the step only names the slab slot of each
+ * episode's new viewpoint; the kernel records it as slots[b, (viewpoints so far)], the table gridmm_pool resolves rows through. */
 
 /* Sort-only variant for callers that already hold the reference's `grid_map` tensors (cell id per point, -1 = masked,
  * r2r/env.py:611): cell [batch,cap] int16 and n_pts [batch] are INPUTS; outputs as above. */

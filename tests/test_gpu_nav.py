@@ -80,9 +80,9 @@ def _oracle_nav(cfg, w, nav):
 
 @pytest.mark.parametrize("B,T,L,G,objs", [(4, 2, 37, 9, 0), (32, 8, 80, 20, 0), (32, 4, 80, 20, 20), (5, 15, 80, 20, 0),
                                           (32, 1, 80, 20, 0), (32, 15, 80, 20, 0), (4, 3, 200, 14, 0), (3, 2, 250, 10, 6),
-                                          (2, 2, 136, 8, 0)],
+                                          (2, 2, 136, 8, 0), (2, 3, 40, 130, 0), (1, 4, 30, 5, 0), (64, 2, 48, 12, 0)],
                          ids=["ragged_L37", "cfg2_b32_t8", "cfg3_reverie_b32", "t15", "cfg2_b32_t1", "cfg2_b32_t15",
-                              "instr200", "instr250_objs", "instr136"])
+                              "instr200", "instr250_objs", "instr136", "gmap130_padded_fallback", "batch1", "batch64"])
 def test_nav_matches_oracle(B, T, L, G, objs):
     ep_kw = dict(batch=B, steps=T, seed=1000 + B + T)
     nav_kw = dict(txt_len=L, gmap_len=G, n_views=36, n_objs=objs)
@@ -653,3 +653,52 @@ def test_packed_map_sequence_equals_padded_layout():
         errs.update({k: H.finite_close(a[k], b[k], atol=4e-3) for k in ("gmap_embeds", "vp_embeds")})
         print("packed vs padded B=%d" % B, "map", err_map, errs)
         assert err_map < 2e-2, err_map
+
+
+def test_device_feature_db_steps_by_key():
+    """DeviceFeatureDB: the CLIP tokens of every viewpoint live in HBM (uploaded once per viewpoint, reference:
+    SemanticFeaturesDB's host dict, r2r/env.py:98-113); a step names viewpoint keys and moves no feature bytes.  Cell ids, the
+    reference-format feature view and the logits must equal the per-step upload path bit for bit, also when a viewpoint is
+    revisited, when buffers grow, with partial `active` masks, and through the lazy / graphed path."""
+    from gridmm_b200.env import DeviceFeatureDB, GridMapBuilder
+    B, T, L, G = 5, 5, 32, 9
+    cfg = H.make_config()
+    model, _ = _model(cfg, 12)
+    model.enable_cuda_graph(True)
+    ep = synth.make_episodes(B, T, seed=12)
+    # episode b revisits its first viewpoint at step 3 (same features, new pose / depth)
+    keys = [["s%d_v%d" % (b, t if t != 3 else 0) for t in range(T)] for b in range(B)]
+    clip = ep["clip"].copy()
+    clip[:, 3] = clip[:, 0]
+    db = DeviceFeatureDB(capacity=B * T)
+    for b in range(B):
+        for t in range(T):
+            full = np.zeros((36, 50, 768), np.float16)
+            full[12:24] = clip[b, t]
+            db.put(keys[b][t], full if t % 2 else clip[b, t])            # both accepted layouts
+    assert len(db) == B * (T - 1)
+    rng = np.random.default_rng(1)
+    active = rng.random((T, B)) < 0.7
+    active[0] = True
+    nav = _to_cuda(synth.to_torch(synth.make_nav_inputs(B, seed=12, txt_len=L, gmap_len=G)))
+    gb_a = GridMapBuilder(B, max_steps=2)
+    gb_b = GridMapBuilder(B, max_steps=2, feature_db=db)
+    pos, heading = ep["pos"][:, 0].copy(), ep["heading"][:, 0].copy()
+    for t in range(T):
+        pos[active[t]] = ep["pos"][active[t], t]; heading[active[t]] = ep["heading"][active[t], t]
+        ga = gb_a.step(ep["depth_sub"][:, t], clip[:, t], pos, heading, active=active[t])
+        ba = dict(nav); ba.update(grid=ga, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        want = {k: v.clone() for k, v in model("navigation", ba).items() if v is not None}
+        gbt = gb_b.step(ep["depth_sub"][:, t], None, pos, heading, active=active[t], keys=[keys[b][t] for b in range(B)],
+                        lazy=bool(active[t].all()))
+        bb = dict(nav); bb.update(grid=gbt, grid_fts=None, grid_map=None, gridmap_pos_fts=None)
+        got = model("navigation", bb)
+        torch.cuda.synchronize()
+        for k in LOGITS[:4] + ("gmap_embeds", "vp_embeds"):
+            assert torch.equal(got[k], want[k]), "step %d: %s" % (t, k)
+        ca, cb = ga.grid_map_numpy(), gbt.grid_map_numpy()
+        fa, fb = ga.grid_fts_torch(), gbt.grid_fts_torch()
+        for b in range(B):
+            assert np.array_equal(ca[b], cb[b]) and torch.equal(fa[b], fb[b]), "step %d episode %d" % (t, b)
+    with pytest.raises(KeyError):
+        gb_b.step(ep["depth_sub"][:, 0], None, pos, heading, keys=["nope"] * B)
