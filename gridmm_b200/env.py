@@ -436,7 +436,7 @@ class GridMapBuilder:
                 self.d_new_slot.copy_(torch.from_numpy(new_slots), non_blocking=False)
         else:
             n_h2d = self._pack_bytes
-            dst = hp_np[self._off_depth:].view(np.float32 if g.depth_is_f32 else np.uint16).reshape(B, PTS)
+            dst = hp_np[self._off_depth:self._off_slot].view(np.float32 if g.depth_is_f32 else np.uint16).reshape(B, PTS)
             src = depth_sub.numpy() if isinstance(depth_sub, torch.Tensor) else np.asarray(depth_sub)
             dst[...] = src.reshape(B, PTS).view(np.uint16) if (not g.depth_is_f32 and src.dtype == np.int16) else src.reshape(B, PTS)
         self._d_pack[:n_h2d].copy_(hp[:n_h2d], non_blocking=True)
