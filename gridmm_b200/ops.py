@@ -414,3 +414,20 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale
     assert p.numel() == g.numel() == m.numel() == v.numel() and p.is_contiguous() and g.is_contiguous()
     _lib.call("gridmm_adamw_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr), float(beta1), float(beta2),
               float(eps), float(weight_decay), int(step), float(grad_scale), _lib.ptr(sumsq), float(max_norm), _lib.stream_ptr())
+
+
+def cast_transpose(src, dst=None, dst_t=None):
+    """src [R, C] fp32 / fp16 -> dst [R, C] fp16 and / or dst_t [C, r_pad >= R] fp16 (columns past R zero-filled)."""
+    if src.dtype not in (torch.float32, torch.float16):
+        raise _lib.GridmmError("cast_transpose: fp32 or fp16 source expected")
+    _chk(src, src.dtype, "src"); _chk(dst, torch.float16, "dst"); _chk(dst_t, torch.float16, "dst_t")
+    R, C = src.shape
+    _lib.call("gridmm_cast_transpose_f16", src.data_ptr(), int(src.dtype == torch.float16), src.stride(0), R, C, _lib.ptr(dst),
+              dst.stride(0) if dst is not None else 0, _lib.ptr(dst_t), dst_t.stride(0) if dst_t is not None else 0,
+              dst_t.shape[1] if dst_t is not None else R, _lib.stream_ptr())
+
+
+def colsum(dy, out):
+    """out[n] += sum_m dy[m, n] (fp32)."""
+    _chk(dy, torch.float32, "dy"); _chk(out, torch.float32, "out")
+    _lib.call("gridmm_colsum_f32", dy.data_ptr(), dy.stride(0), dy.shape[0], dy.shape[1], out.data_ptr(), _lib.stream_ptr())

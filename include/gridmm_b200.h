@@ -298,6 +298,15 @@ int gridmm_grad_sumsq(const float* g, long long n, float* out, cudaStream_t stre
 int gridmm_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                       float weight_decay, int step, float grad_scale, const float* sumsq, float max_norm, cudaStream_t stream);
 
+/* ---- training path helpers (BASELINE config 5): operands of the dgrad / wgrad GEMMs of nn.Linear ------------------------------
+ * dx = dy . W and dW = dy^T . x run on gridmm_linear_f16 (A[M,K] . W[N,K]^T, both K-contiguous) with transposed fp16 operands:
+ * gridmm_cast_transpose_f16: src [R, C] fp32 / fp16 -> dst [R, C] fp16 and / or dst_t [C, r_pad] fp16 (zero padded beyond R: the wgrad
+ *   contraction runs over the rows, padded to the GEMM's K granularity of 64); pitches in elements.
+ * gridmm_colsum_f32: out[n] += sum_m dy[m, n], the bias gradient.  (loss.backward() through nn.Linear, pretrain_src/train_r2r.py:258) */
+int gridmm_cast_transpose_f16(const void* src, int src_is_f16, long long lds, int R, int C, void* dst, long long ldd, void* dst_t,
+                              long long ldt, int r_pad, cudaStream_t stream);
+int gridmm_colsum_f32(const float* dy, long long ld, int M, int N, float* out, cudaStream_t stream);
+
 /* Debug hooks (tools/microbench.py only): per-CTA clock64 counters written by the following launches ([grid][8] for the
  * GEMM, [grid][16] for the pooling kernel: role totals and time spent waiting on each mbarrier).  NULL disables. */
 void gridmm_debug_set_gemm_counters(long long* dbg);
