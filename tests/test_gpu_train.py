@@ -1,0 +1,140 @@
+"""GPU: the training path of BASELINE config 5 (gridmm_b200/train_model.py + train.py).
+
+  * LinearFn: forward / dgrad / wgrad on the tcgen05 GEMM kernel against torch autograd of F.linear;
+  * PretrainModel (MLM and SAP proxy tasks): logits and losses against the reference's own outputs
+    (tests/golden/pretrain_heads_small.npz) and GRADIENTS of every parameter against CPU autograd through the oracle
+    (oracle/pretrain_oracle.py, pinned on the reference's forward), relative error per tensor;
+  * one optimizer step through FlatParams + GradientStep equals the reference update rule applied to those gradients.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gridmm_b200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_linear_fn_matches_torch_autograd():
+    from gridmm_b200.train_model import LinearFn, _WeightCache
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    cache = _WeightCache()
+    for lead, K, N in (((3, 57), 768, 2304), ((130,), 3072, 768), ((2,), 1536, 768), ((4, 9), 768, 768)):
+        x = torch.randn(*lead, K, generator=g).to(dev).requires_grad_(True)
+        w = (torch.randn(N, K, generator=g) * 0.05).to(dev).requires_grad_(True)
+        b = torch.randn(N, generator=g).to(dev).requires_grad_(True)
+        dy = torch.randn(*lead, N, generator=g).to(dev)
+        y = LinearFn.apply(x, w, b, cache)
+        y.backward(dy)
+        x2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+        y2 = torch.nn.functional.linear(x2, w2, b2)
+        y2.backward(dy)
+        for got, ref, name in ((y, y2, "y"), (x.grad, x2.grad, "dx"), (w.grad, w2.grad, "dW"), (b.grad, b2.grad, "db")):
+            rel = (got.detach() - ref.detach()).norm().item() / max(ref.detach().norm().item(), 1e-12)
+            assert rel < 2e-3, (lead, K, N, name, rel)               # fp16 operands (2^-11), fp32 accumulate
+
+
+def _setup(case):
+    from gridmm_b200.model import NavConfig
+    from gridmm_b200.train_model import PretrainModel
+    shapes = json.load(open(os.path.join(H.GOLD, "pretrain_heads_small_spec.json")))
+    w = synth.make_weights(shapes, seed=case["seed"])
+    w["mlm_head.predictions.decoder.weight"] = w["bert.embeddings.word_embeddings.weight"]       # tie_weights, pretrain_cmt.py:68-71
+    model = PretrainModel(NavConfig(pretrain_trunk=True, use_lang2visn_attn=True, graph_sprels=False, **case["model"]))
+    res = model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    batch = H.pretrain_batch(case)
+    pb = synth.make_pretrain_batch(case["batch"], seed=case["seed"], txt_len=case["txt_len"], max_steps=case["max_steps"])
+    for k, v in synth.make_pretrain_labels(pb, seed=case["seed"]).items():
+        batch[k] = torch.from_numpy(v)
+    return model, w, batch
+
+
+def _oracle_grads(w, batch, task, case):
+    """d mean(loss) / d parameter by CPU autograd through the oracle restatement of the reference's wrapper."""
+    from oracle import pretrain_oracle as po
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in w.items() if k != "mlm_head.predictions.decoder.weight"}
+    sd["mlm_head.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]
+    kw = dict(n_l_layers=case["model"]["num_l_layers"], n_pano_layers=case["model"]["num_pano_layers"],
+              n_x_layers=case["model"]["num_x_layers"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    if task == "sap":
+        labels = {k: batch[k] for k in ("gmap_visited_masks", "global_act_labels", "local_act_labels")}
+        loss = po.sap(sd, batch, labels, **kw)[3].mean()
+    else:
+        scores = po.mlm_scores(sd, batch, batch["txt_labels"], **kw)
+        loss = torch.nn.functional.cross_entropy(scores, batch["txt_labels"][batch["txt_labels"] != -1], reduction="none").mean()
+    loss.backward()
+    return float(loss), {k: v.grad for k, v in sd.items() if v.grad is not None and k != "mlm_head.predictions.decoder.weight"}
+
+
+@pytest.mark.parametrize("task", ["sap", "mlm"])
+def test_pretrain_model_losses_and_gradients(task):
+    case = H.PRETRAIN_MODEL_CASE
+    model, w, batch = _setup(case)
+    gold = np.load(os.path.join(H.GOLD, "pretrain_heads_small.npz"))
+    ref_loss, ref_grads = _oracle_grads(w, batch, task, case)
+    model = model.cuda().train()
+    scale = 1024.0                                            # the data gradients pass through fp16 GEMM operands
+    losses = model(batch, task)
+    if task == "sap":
+        err = (losses.detach().cpu() - torch.from_numpy(gold["sap_losses"])).abs().max().item()
+        assert err < 5e-3, err                                # the reference's own per-sample losses
+        gl, ll, fused = model(batch, task, compute_loss=False)
+        for k, t in (("global_logits", gl), ("local_logits", ll), ("fused_logits", fused)):
+            H.finite_close(t.detach(), gold[k], atol=2e-3)
+    else:
+        scores = model(batch, task, compute_loss=False)
+        assert (scores.detach().cpu() - torch.from_numpy(gold["mlm_scores"])).abs().max().item() < 5e-3
+    (losses.mean() * scale).backward()
+    torch.cuda.synchronize()
+    assert abs(float(losses.mean()) - ref_loss) < 2e-3 * max(1.0, abs(ref_loss))
+    worst = {}
+    for name, p in model.named_parameters():
+        rg = ref_grads.get(name)
+        if rg is None or float(rg.norm()) == 0.0:
+            assert p.grad is None or float(p.grad.norm()) < 1e-6 * scale, name
+            continue
+        assert p.grad is not None, name
+        got = p.grad.detach().cpu() / scale
+        rel = (got - rg).norm().item() / rg.norm().item()
+        worst[name] = rel
+    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+    print("gradient parity (%s): %d tensors, worst relative errors %s" % (task, len(worst), top))
+    assert len(worst) > 100
+    assert top[0][1] < 1e-2, top
+
+
+def test_one_training_step_through_flat_buffers():
+    """FlatParams + GradientStep on the trainable model: after backward, one step must equal the reference update rule
+    (clip_grad_norm_ + AdamW, pretrain_src/train_r2r.py:281-296, optim/adamw.py) applied to the same gradients."""
+    from gridmm_b200.train import FlatParams, GradientStep
+    case = H.PRETRAIN_MODEL_CASE
+    model, w, batch = _setup(case)
+    model = model.cuda().train()
+    flat = FlatParams(model)
+    gs = GradientStep(flat, lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_norm=0.5)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    scale = 1024.0
+    gs.arm()
+    (model(batch, "sap").mean() * scale).backward()
+    grads = {n: p.grad.detach().clone() / scale for n, p in model.named_parameters()}
+    gs.step(loss_scale=scale)
+    torch.cuda.synchronize()
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
+    coef = min(1.0, 0.5 / (float(total) + 1e-6))
+    assert abs(gs.grad_norm() - float(total)) < 1e-3 * float(total)
+    for n, p in model.named_parameters():
+        g = grads[n].double() * coef
+        m, v = 0.1 * g, 0.02 * g * g
+        step = 1e-4 * (1 - 0.98) ** 0.5 / (1 - 0.9)
+        want = before[n].double() - step * m / (v.sqrt() + 1e-6)
+        if not any(nd in n for nd in ("bias", "LayerNorm.bias", "LayerNorm.weight")):
+            want = want - 1e-4 * 0.01 * want
+        assert (p.detach().double() - want).abs().max().item() < 2e-6, n
+        assert float(p.grad.abs().max()) == 0.0                # zero_grad on the flat buffer
