@@ -440,11 +440,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="r2r", choices=sorted(WORKLOADS), help="BASELINE config; the headline is r2r")
+    ap.add_argument("--workload", default="r2r", choices=sorted(WORKLOADS) + ["pretrain"],
+                    help="BASELINE config; the headline is r2r.  pretrain = config 5 (training step), see tools/bench_pretrain.py")
     ap.add_argument("--T", type=int, default=8, help="viewpoints accumulated per episode at the timed step (1, 8 or 15)")
     ap.add_argument("--gpu-eager-baseline", action="store_true",
                     help="also time the reference algorithm in stock torch eager on this GPU (oracle code on CUDA tensors)")
     args = ap.parse_args()
+    if args.workload == "pretrain":
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import bench_pretrain
+        return bench_pretrain.main(sys.argv[1:])
     set_workload(args.workload, args.T)
     if args.impl == "reference":
         return run_reference(args)

@@ -67,9 +67,11 @@ class GradientStep:
         gs.arm(); loss.backward(); gs.step()          # every iteration
     """
 
-    def __init__(self, flat, lr, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_norm=-1.0, bucket_elems=32 << 20, group=None):
+    def __init__(self, flat, lr, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_norm=-1.0, bucket_elems=32 << 20, group=None, after_step=()):
         self.flat, self.lr, self.betas, self.eps, self.wd, self.max_norm = flat, lr, betas, eps, weight_decay, max_norm
         self.group = group
+        self.after_step = list(after_step)      # callables run after every update (e.g. a weight cache's invalidate)
+        self._last_scale = 1.0
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.m = torch.zeros_like(flat.params)
         self.v = torch.zeros_like(flat.params)
@@ -148,7 +150,10 @@ class GradientStep:
             ops.adamw_step(f.params[nd:], f.grads[nd:], self.m[nd:], self.v[nd:], lr, self.betas[0], self.betas[1], self.eps, 0.0,
                            self.t, grad_scale=scale, sumsq=sumsq, max_norm=self.max_norm or 0.0)
         f.zero_grad()
+        self._last_scale = scale
+        for cb in self.after_step:
+            cb()
 
     def grad_norm(self):
         """Global gradient norm of the last step (after averaging), as clip_grad_norm_ returns it.  Host synchronisation."""
-        return float(self.sumsq.sqrt().item()) / self.world
+        return float(self.sumsq.sqrt().item()) * self._last_scale

@@ -25,23 +25,31 @@ from .model import HID, HEADS, NavConfig, _Holder, _cls, param_spec
 
 # ----------------------------------------------------------------------------------------------- Linear on the tcgen05 GEMM
 class _WeightCache:
-    """fp16 copy and fp16 transpose of every weight LinearFn touches, refreshed when the parameter's version counter changes
-    (i.e. after every optimizer step)."""
+    """fp16 copy and fp16 transpose of every weight LinearFn touches, refreshed when the parameter's version counter or storage changes
+    (torch optimizers) or after invalidate() (this package's fused update)."""
 
     def __init__(self):
         self.c = {}
+        self.generation = 0
+
+    def invalidate(self):
+        """The parameters changed behind autograd's back (gridmm_adamw_step writes the flat buffer through a raw pointer):
+        GradientStep calls this after every update (`after_step`)."""
+        self.generation += 1
 
     def get(self, w):
         key = id(w)
         e = self.c.get(key)
-        if e is None or e[0] != w._version or e[1].device != w.device:
+        stamp = (w._version, w.data_ptr(), self.generation)
+        if e is None or e[0] is not w or e[1] != stamp:
             N, K = w.shape
-            w16 = torch.empty(N, K, dtype=torch.float16, device=w.device)
-            w16t = torch.empty(K, N, dtype=torch.float16, device=w.device)
+            fresh = e is None or e[0] is not w or e[2].device != w.device
+            w16 = torch.empty(N, K, dtype=torch.float16, device=w.device) if fresh else e[2]
+            w16t = torch.empty(K, N, dtype=torch.float16, device=w.device) if fresh else e[3]
             ops.cast_transpose(w.detach(), dst=w16, dst_t=w16t)
-            e = (w._version, w16, w16t)
+            e = (w, stamp, w16, w16t)             # holding w keeps id(w) from being reused by another tensor
             self.c[key] = e
-        return e[1], e[2]
+        return e[2], e[3]
 
 
 class LinearFn(torch.autograd.Function):
@@ -99,8 +107,10 @@ def _bool_masks(lens, n):
 class PretrainModel(nn.Module):
     """`GlocalTextPathCMTPreTraining(config)` with pretrain_tasks = ['mlm', 'sap'] (pretrain_cmt.py:37-66)."""
 
-    def __init__(self, config=None, **kw):
+    def __init__(self, config=None, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, **kw):
         super().__init__()
+        # dropout sites of the reference in training mode (pretrain_src/config/r2r_model_config.json: both 0.1)
+        self.p_hid, self.p_att = float(hidden_dropout_prob), float(attention_probs_dropout_prob)
         kw.setdefault("pretrain_trunk", True)
         kw.setdefault("use_lang2visn_attn", True)
         self.config = config if config is not None else NavConfig(**kw)
@@ -126,6 +136,7 @@ class PretrainModel(nn.Module):
                 mod = getattr(mod, p)
             mod.register_parameter(parts[-1], nn.Parameter(t))
         self._cache = _WeightCache()
+        self.weights_updated = self._cache.invalidate        # GradientStep(..., after_step=[model.weights_updated])
         self.use_native_linear = True
 
     # ---- reference checkpoints carry the tied decoder weight as its own key (pretrain_cmt.py:68-71)
@@ -153,6 +164,9 @@ class PretrainModel(nn.Module):
             return LinearFn.apply(x, w, b, self._cache)
         return F.linear(x, w, b)
 
+    def drop(self, x, p):
+        return F.dropout(x, p, True) if (self.training and p > 0.0) else x
+
     def ln(self, pre, x, eps):
         return F.layer_norm(x, (HID,), self.P(pre + ".weight"), self.P(pre + ".bias"), eps)
 
@@ -161,12 +175,12 @@ class PretrainModel(nn.Module):
         B, S, _ = x.shape
         return x.view(B, S, HEADS, HID // HEADS).permute(0, 2, 1, 3)
 
-    def attend(self, q, k, v, add_mask):
-        """softmax(q k^T / sqrt(64) + mask) v (vilmodel.py:95-153, 317-368)."""
+    def attend(self, q, k, v, add_mask, p_drop=None):
+        """softmax(q k^T / sqrt(64) + mask) v, dropout on the probabilities in training mode (vilmodel.py:95-153, 317-368)."""
         s = torch.matmul(self._heads(q), self._heads(k).transpose(-1, -2)) / math.sqrt(HID // HEADS)
         if add_mask is not None:
             s = s + add_mask
-        o = torch.matmul(torch.softmax(s, -1), self._heads(v))
+        o = torch.matmul(self.drop(torch.softmax(s, -1), self.p_att if p_drop is None else p_drop), self._heads(v))
         B, H, S, Dh = o.shape
         return o.permute(0, 2, 1, 3).reshape(B, S, H * Dh)
 
@@ -179,15 +193,15 @@ class PretrainModel(nn.Module):
 
     def bert_self(self, pre, x, add):
         a = self.attend(self.lin(pre + ".self.query", x), self.lin(pre + ".self.key", x), self.lin(pre + ".self.value", x), add)
-        return self.ln(pre + ".output.LayerNorm", self.lin(pre + ".output.dense", a) + x, self.config.layer_norm_eps)
+        return self.ln(pre + ".output.LayerNorm", self.drop(self.lin(pre + ".output.dense", a), self.p_hid) + x, self.config.layer_norm_eps)
 
     def bert_ffn(self, pi, po, x):
         h = self.gelu(self.lin(pi + ".dense", x))
-        return self.ln(po + ".LayerNorm", self.lin(po + ".dense", h) + x, self.config.layer_norm_eps)
+        return self.ln(po + ".LayerNorm", self.drop(self.lin(po + ".dense", h), self.p_hid) + x, self.config.layer_norm_eps)
 
     def cross(self, pre, x, ctx, ctx_add):
         a = self.attend(self.lin(pre + ".att.query", x), self.lin(pre + ".att.key", ctx), self.lin(pre + ".att.value", ctx), ctx_add)
-        return self.ln(pre + ".output.LayerNorm", self.lin(pre + ".output.dense", a) + x, self.config.layer_norm_eps)
+        return self.ln(pre + ".output.LayerNorm", self.drop(self.lin(pre + ".output.dense", a), self.p_hid) + x, self.config.layer_norm_eps)
 
     def lxrt(self, pre, ctx, ctx_add, x, x_add):
         """GraphLXRTXLayer.forward (vilmodel.py:387-402)."""
@@ -203,9 +217,9 @@ class PretrainModel(nn.Module):
             h = self.ln(q + ".norm1", x, 1e-5)
             qkv = self.lin(None, h, self.P(q + ".self_attn.in_proj_weight"), self.P(q + ".self_attn.in_proj_bias"))
             qq, kk, vv = qkv.chunk(3, -1)
-            x = x + self.lin(q + ".self_attn.out_proj", self.attend(qq, kk, vv, add))
+            x = x + self.drop(self.lin(q + ".self_attn.out_proj", self.attend(qq, kk, vv, add, self.p_hid)), self.p_hid)
             h = self.ln(q + ".norm2", x, 1e-5)
-            x = x + self.lin(q + ".linear2", F.gelu(self.lin(q + ".linear1", h)))
+            x = x + self.drop(self.lin(q + ".linear2", self.drop(F.gelu(self.lin(q + ".linear1", h)), self.p_hid)), self.p_hid)
         return self.ln(pre + ".norm", x, 1e-12)
 
     def cls_head(self, pre, x):
@@ -220,7 +234,7 @@ class PretrainModel(nn.Module):
         e = "bert.embeddings"
         x = self.P(e + ".word_embeddings.weight")[txt_ids] + self.P(e + ".position_embeddings.weight")[:L][None] + \
             self.P(e + ".token_type_embeddings.weight")[0]
-        x = self.ln(e + ".LayerNorm", x, self.config.layer_norm_eps)
+        x = self.drop(self.ln(e + ".LayerNorm", x, self.config.layer_norm_eps), self.p_hid)
         add = self.neg_mask(txt_masks)
         for i in range(self.config.num_l_layers):
             p = "bert.lang_encoder.layer.%d" % i
@@ -249,7 +263,7 @@ class PretrainModel(nn.Module):
                                                        self.P(ie + ".loc_linear.bias")), 1e-12)
         x = img + loc + self.P(ie + ".nav_type_embedding.weight")[batch["traj_nav_types"].to(dev)] + \
             self.P("bert.embeddings.token_type_embeddings.weight")[1]
-        x = self.ln(ie + ".layer_norm", x, 1e-12)
+        x = self.drop(self.ln(ie + ".layer_norm", x, 1e-12), self.p_hid)
         masks = _bool_masks(lens, x.shape[1])
         if self.config.num_pano_layers > 0:
             x = self.prenorm(ie + ".pano_encoder", self.config.num_pano_layers, x, masks)

@@ -45,7 +45,8 @@ def _setup(case):
     shapes = json.load(open(os.path.join(H.GOLD, "pretrain_heads_small_spec.json")))
     w = synth.make_weights(shapes, seed=case["seed"])
     w["mlm_head.predictions.decoder.weight"] = w["bert.embeddings.word_embeddings.weight"]       # tie_weights, pretrain_cmt.py:68-71
-    model = PretrainModel(NavConfig(pretrain_trunk=True, use_lang2visn_attn=True, graph_sprels=False, **case["model"]))
+    model = PretrainModel(NavConfig(pretrain_trunk=True, use_lang2visn_attn=True, graph_sprels=False, **case["model"]),
+                          hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)      # parity needs a deterministic forward
     res = model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     batch = H.pretrain_batch(case)
@@ -94,20 +95,32 @@ def test_pretrain_model_losses_and_gradients(task):
     (losses.mean() * scale).backward()
     torch.cuda.synchronize()
     assert abs(float(losses.mean()) - ref_loss) < 2e-3 * max(1.0, abs(ref_loss))
-    worst = {}
+    # Per tensor: ||g - g_ref|| <= 1e-2 ||g_ref|| + 2e-3 * (RMS gradient element of the whole model) * sqrt(numel).  The absolute
+    # term is for tensors whose gradient is analytically zero (key biases: softmax is shift-invariant; the last bias and LayerNorm
+    # bias of a ClsPrediction head under a softmax over its rows), where both sides hold rounding noise only.
+    tot_sq = sum(float(g.double().pow(2).sum()) for g in ref_grads.values())
+    tot_n = sum(g.numel() for g in ref_grads.values())
+    rms = (tot_sq / tot_n) ** 0.5
+    worst, bad, err_sq = {}, [], 0.0
     for name, p in model.named_parameters():
         rg = ref_grads.get(name)
-        if rg is None or float(rg.norm()) == 0.0:
-            assert p.grad is None or float(p.grad.norm()) < 1e-6 * scale, name
+        if rg is None:
+            assert p.grad is None or float(p.grad.norm()) / scale <= 2e-3 * rms * p.numel() ** 0.5, name
             continue
         assert p.grad is not None, name
         got = p.grad.detach().cpu() / scale
-        rel = (got - rg).norm().item() / rg.norm().item()
-        worst[name] = rel
-    top = sorted(worst.items(), key=lambda kv: -kv[1])[:5]
-    print("gradient parity (%s): %d tensors, worst relative errors %s" % (task, len(worst), top))
+        err, ref = (got - rg).norm().item(), rg.norm().item()
+        err_sq += err * err
+        worst[name] = err / max(ref, 1e-30)
+        if err > 1e-2 * ref + 2e-3 * rms * rg.numel() ** 0.5:
+            bad.append((name, err, ref, rg.numel()))
+    top = sorted(worst.items(), key=lambda kv: -kv[1])
+    sig = [kv for kv in top if float(ref_grads[kv[0]].norm()) > 0.05 * rms * ref_grads[kv[0]].numel() ** 0.5]
+    print("gradient parity (%s): %d tensors, whole-model relative error %.2e, worst tensors with a significant gradient %s"
+          % (task, len(worst), (err_sq / tot_sq) ** 0.5, sig[:4]))
     assert len(worst) > 100
-    assert top[0][1] < 1e-2, top
+    assert not bad, bad
+    assert (err_sq / tot_sq) ** 0.5 < 5e-3
 
 
 def test_one_training_step_through_flat_buffers():
@@ -118,7 +131,7 @@ def test_one_training_step_through_flat_buffers():
     model, w, batch = _setup(case)
     model = model.cuda().train()
     flat = FlatParams(model)
-    gs = GradientStep(flat, lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_norm=0.5)
+    gs = GradientStep(flat, lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01, max_norm=0.5, after_step=[model.weights_updated])
     before = {n: p.detach().clone() for n, p in model.named_parameters()}
     scale = 1024.0
     gs.arm()
@@ -138,3 +151,12 @@ def test_one_training_step_through_flat_buffers():
             want = want - 1e-4 * 0.01 * want
         assert (p.detach().double() - want).abs().max().item() < 2e-6, n
         assert float(p.grad.abs().max()) == 0.0                # zero_grad on the flat buffer
+    # the next forward must see the updated weights (fp16 operand cache invalidated by the step)
+    with torch.no_grad():
+        after = float(model(batch, "sap").mean())
+        ref_model, _, _ = _setup(case)
+        ref_model = ref_model.cuda()
+        ref_model.load_state_dict(model.state_dict())
+        assert abs(after - float(ref_model(batch, "sap").mean())) < 1e-4    # index_add atomics reorder sums; a stale cache is off by 1.6e-3
+        stale = {n: p.detach().clone() for n, p in model.named_parameters()}
+    assert any(float((stale[n] - before[n]).abs().max()) > 0 for n in before)
