@@ -47,6 +47,9 @@ _SIGS = {
     "gridmm_grad_sumsq": [c_void_p, c_longlong, c_void_p, c_void_p],
     "gridmm_cast_transpose_f16": [c_void_p, c_int, c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p],
     "gridmm_colsum_f32": [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p],
+    "gridmm_linear_train_fwd": [c_void_p, c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "gridmm_linear_train_bwd": [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p],
     "gridmm_adamw_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_float, c_int, c_float,
                           c_void_p, c_float, c_void_p],
     "gridmm_linear_f16_lanes": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],

@@ -427,6 +427,33 @@ def cast_transpose(src, dst=None, dst_t=None):
               dst_t.shape[1] if dst_t is not None else R, _lib.stream_ptr())
 
 
+def linear_train_fwd(x, w16, bias, y, x16, x16t):
+    """Forward of a trainable nn.Linear: x fp32 [M, K] -> y fp32 [M, N] = x . w16^T + bias; fills x16 (scratch, >= M*K fp16 elements)
+    and x16t [K, m_pad] (kept for linear_train_bwd)."""
+    _chk(x, torch.float32, "x"); _chk(w16, torch.float16, "w16"); _chk(bias, torch.float32, "bias"); _chk(y, torch.float32, "y")
+    _chk(x16, torch.float16, "x16"); _chk(x16t, torch.float16, "x16t")
+    M, K = x.shape
+    N = w16.shape[0]
+    if x16.numel() < M * K or x16t.shape[0] != K or not (w16.is_contiguous() and y.is_contiguous() and x16t.is_contiguous()):
+        raise _lib.GridmmError("linear_train_fwd: operand shapes")
+    _lib.call("gridmm_linear_train_fwd", x.data_ptr(), x.stride(0), M, K, w16.data_ptr(), N, _lib.ptr(bias), y.data_ptr(), x16.data_ptr(),
+              x16t.data_ptr(), x16t.shape[1], _lib.stream_ptr())
+
+
+def linear_train_bwd(dy, w16t, x16t, dy16, dy16t, dx=None, dw=None, db=None):
+    """Backward of the same layer: dy fp32 [M, N]; dx [M, K] = dy . W (needs w16t [K, N]), dw [N, K] = dy^T . x (needs x16t [K, m_pad]),
+    db [N] = column sums of dy; dy16 / dy16t are scratch (>= M*N and N*m_pad fp16 elements)."""
+    _chk(dy, torch.float32, "dy"); _chk(w16t, torch.float16, "w16t"); _chk(x16t, torch.float16, "x16t")
+    _chk(dy16, torch.float16, "dy16"); _chk(dy16t, torch.float16, "dy16t")
+    _chk(dx, torch.float32, "dx"); _chk(dw, torch.float32, "dw"); _chk(db, torch.float32, "db")
+    M, N = dy.shape
+    K, m_pad = x16t.shape
+    if dy16.numel() < M * N or dy16t.numel() < N * m_pad or not x16t.is_contiguous() or (w16t is not None and tuple(w16t.shape) != (K, N)):
+        raise _lib.GridmmError("linear_train_bwd: operand shapes")
+    _lib.call("gridmm_linear_train_bwd", dy.data_ptr(), dy.stride(0), M, N, K, _lib.ptr(w16t), x16t.data_ptr(), m_pad, dy16.data_ptr(),
+              dy16t.data_ptr(), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.stream_ptr())
+
+
 def colsum(dy, out):
     """out[n] += sum_m dy[m, n] (fp32)."""
     _chk(dy, torch.float32, "dy"); _chk(out, torch.float32, "out")

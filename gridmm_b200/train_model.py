@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 from .model import HID, HEADS, NavConfig, _Holder, _cls, param_spec
 
 
@@ -30,6 +30,7 @@ class _WeightCache:
 
     def __init__(self):
         self.c = {}
+        self.lo = {}
         self.generation = 0
 
     def invalidate(self):
@@ -49,26 +50,78 @@ class _WeightCache:
             ops.cast_transpose(w.detach(), dst=w16, dst_t=w16t)
             e = (w, stamp, w16, w16t)             # holding w keeps id(w) from being reused by another tensor
             self.c[key] = e
+            self.lo.pop(key, None)
         return e[2], e[3]
+
+    def get_lo(self, w):
+        """fp16 of the rounding residual w - fp16(w) (split-precision forward)."""
+        w16, _ = self.get(w)
+        key = id(w)
+        lo = self.lo.get(key)
+        if lo is None:
+            lo = (w.detach() - w16.float()).half()
+            self.lo[key] = lo
+        return lo
+
+
+class _Scratch:
+    """One growing fp16 scratch buffer per (device, role) for the operands that live only inside a call (x16, dy16, dy16t).  Every
+    kernel of the training path is enqueued on the device's current stream, so the next call's writes are ordered behind this
+    call's reads."""
+    bufs = {}
+
+    @classmethod
+    def get(cls, device, role, numel):
+        key = (device, role)
+        b = cls.bufs.get(key)
+        if b is None or b.numel() < numel:
+            b = torch.empty(max(numel, 1 << 20), dtype=torch.float16, device=device)
+            cls.bufs[key] = b
+        return b
+
+
+_FN = {}
+
+
+def _native(name, *args):
+    """Direct call of a C entry (the argument checks of gridmm_b200.ops are skipped: LinearFn builds every operand itself)."""
+    f = _FN.get(name)
+    if f is None:
+        f = _FN[name] = getattr(_lib.load(), name)
+    rc = f(*args)
+    if rc != 0:
+        raise _lib.GridmmError("%s failed: %d" % (name, rc))
 
 
 class LinearFn(torch.autograd.Function):
-    """y = x W^T + b with all three GEMMs (forward, dx = dy W, dW = dy^T x) on gridmm_linear_f16."""
+    """y = x W^T + b with all three GEMMs (forward, dx = dy W, dW = dy^T x) on gridmm_linear_f16 (one C call per direction:
+    gridmm_linear_train_fwd / gridmm_linear_train_bwd, the casts, transposes and the bias gradient fused around the GEMMs)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache):
+    def forward(ctx, x, weight, bias, cache, split=False):
         N, K = weight.shape
         x2 = x.reshape(-1, K)
-        if x2.dtype != torch.float32 or not x2.is_contiguous():
+        if x2.dtype != torch.float32 or x2.stride(-1) != 1:
             x2 = x2.float().contiguous()
         M = x2.shape[0]
         m_pad = (M + 63) // 64 * 64
-        x16 = torch.empty(M, K, dtype=torch.float16, device=x.device)
         x16t = torch.empty(K, m_pad, dtype=torch.float16, device=x.device)      # operand of the weight gradient
-        ops.cast_transpose(x2, dst=x16, dst_t=x16t)
         w16, _ = cache.get(weight)
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
-        ops.linear(x16, w16, bias.detach() if bias is not None else None, out_f32=y)
+        b = bias.detach() if bias is not None else None
+        if split:
+            # split-precision forward: x = xh + xl, W = Wh + Wl in fp16 pairs, y = xh Wh^T + xl Wh^T + xh Wl^T (fp32 accumulate, the
+            # dropped xl Wl^T term is 2^-22 relative): for the few layers whose rounding error is amplified downstream
+            xh = x2.half()
+            xl = (x2 - xh.float()).half()
+            ops.cast_transpose(xh, dst_t=x16t)
+            ops.linear(xh, w16, b, out_f32=y)
+            ops.linear(xl, w16, None, residual=y, out_f32=y)
+            ops.linear(xh, cache.get_lo(weight), None, residual=y, out_f32=y)
+        else:
+            _native("gridmm_linear_train_fwd", x2.data_ptr(), x2.stride(0), M, K, w16.data_ptr(), N, b.data_ptr() if b is not None else None,
+                    y.data_ptr(), _Scratch.get(x.device, "x16", M * K).data_ptr(), x16t.data_ptr(), m_pad,
+                    torch.cuda.current_stream().cuda_stream)
         ctx.save_for_backward(x16t, weight)
         ctx.cache, ctx.has_bias, ctx.in_shape, ctx.M = cache, bias is not None, x.shape, M
         return y.view(*x.shape[:-1], N)
@@ -79,25 +132,102 @@ class LinearFn(torch.autograd.Function):
         N, K = weight.shape
         M = ctx.M
         dy2 = dy.reshape(M, N)
-        if dy2.dtype != torch.float32 or not dy2.is_contiguous():
+        if dy2.dtype != torch.float32 or dy2.stride(-1) != 1:
             dy2 = dy2.float().contiguous()
         m_pad = x16t.shape[1]
-        dy16 = torch.empty(M, N, dtype=torch.float16, device=dy.device)
-        dy16t = torch.empty(N, m_pad, dtype=torch.float16, device=dy.device)
-        ops.cast_transpose(dy2, dst=dy16, dst_t=dy16t)
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            _, w16t = ctx.cache.get(weight)                         # [K, N]: dx[M, K] = dy16[M, N] . (W^T)[K, N]^T
-            dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
-            ops.linear(dy16, w16t, None, out_f32=dx)
-            dx = dx.view(ctx.in_shape)
-        if ctx.needs_input_grad[1]:
-            dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
-            ops.linear(dy16t, x16t, None, out_f32=dw)               # dW[N, K] = dy^T[N, M] . (x^T)[K, M]^T
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = torch.zeros(N, dtype=torch.float32, device=dy.device)
-            ops.colsum(dy2, db)
-        return dx, dw, db, None
+        dev = dy.device
+        dx = torch.empty(M, K, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(N, K, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        db = torch.empty(N, dtype=torch.float32, device=dev) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        w16t = ctx.cache.get(weight)[1] if dx is not None else None           # [K, N]: dx[M, K] = dy16[M, N] . (W^T)[K, N]^T
+        _native("gridmm_linear_train_bwd", dy2.data_ptr(), dy2.stride(0), M, N, K, w16t.data_ptr() if w16t is not None else None,
+                x16t.data_ptr(), m_pad, _Scratch.get(dev, "dy16", M * N).data_ptr(), _Scratch.get(dev, "dy16t", N * m_pad).data_ptr(),
+                dx.data_ptr() if dx is not None else None, dw.data_ptr() if dw is not None else None,
+                db.data_ptr() if db is not None else None, torch.cuda.current_stream().cuda_stream)
+        return (dx.view(ctx.in_shape) if dx is not None else None), dw, db, None, None
+
+
+def collate_plan(batch):
+    """Index tensors (host) that turn the per-episode Python bookkeeping of the reference into a few gathers / index_adds:
+
+      * gmap aggregation (GlobalMapEncoder._aggregate_gmap_features, vilmodel.py:578-612): node g of episode b is either the mean of
+        the valid tokens of the (last) panorama taken at that viewpoint, or the mean of every candidate-view token that points at it;
+        emitted as COO triplets (destination node, flat source token, weight);
+      * logit fusion (pretrain_cmt.py:256-273): per unvisited node the local logit that points at it (the LAST such candidate, the
+        reference fills a dict) or else the summed logits of the candidates that lead back to visited nodes;
+      * the row of the last panorama of every path.
+
+    Depends only on the batch's ids / lengths: it belongs to collation (the reference's DataLoader workers) and is cached in the batch
+    under '_plan'."""
+    steps = [int(x) for x in batch["traj_step_lens"]]
+    B = len(steps)
+    vlen = torch.as_tensor(batch["traj_vp_view_lens"]).cpu()
+    olen = batch.get("traj_vp_obj_lens")
+    lens = (vlen + torch.as_tensor(olen).cpu()) if olen is not None and batch.get("traj_obj_img_fts") is not None else vlen
+    lens = [int(x) for x in lens]
+    n_tok = int(max(lens)) if lens else 0
+    G = 1 + max(len(g) - 1 for g in batch["gmap_vpids"])
+    dst, src, wgt = [], [], []
+    row0 = 0
+    for b, T in enumerate(steps):
+        own_t = {}
+        for t in range(T):
+            own_t[batch["traj_vpids"][b][t]] = t
+        seen = {}
+        for t in range(T):
+            for j, vp in enumerate(batch["traj_cand_vpids"][b][t]):
+                if vp not in own_t:
+                    seen.setdefault(vp, []).append((row0 + t) * n_tok + j)
+        for g, vp in enumerate(batch["gmap_vpids"][b]):
+            if g == 0:
+                continue
+            if vp in own_t:
+                t = own_t[vp]
+                n = lens[row0 + t]
+                base = (row0 + t) * n_tok
+                dst.extend([b * G + g] * n); src.extend(range(base, base + n)); wgt.extend([1.0 / n] * n)
+            else:
+                toks = seen[vp]
+                dst.extend([b * G + g] * len(toks)); src.extend(toks); wgt.extend([1.0 / len(toks)] * len(toks))
+        row0 += T
+    last = [sum(steps[:i + 1]) - 1 for i in range(B)]
+    plan = {"G": G, "n_tok": n_tok, "agg_dst": torch.tensor(dst, dtype=torch.long), "agg_src": torch.tensor(src, dtype=torch.long),
+            "agg_w": torch.tensor(wgt, dtype=torch.float32), "last": torch.tensor(last, dtype=torch.long), "steps": steps}
+    n_per = [int(f.shape[0]) for f in batch["grid_fts"]] if "grid_fts" in batch else []
+    if n_per:
+        plan["pt_ep"] = torch.repeat_interleave(torch.arange(B), torch.tensor(n_per))
+        plan["pt_slot"] = torch.cat([torch.arange(n) for n in n_per])
+        plan["pt_max"] = max(n_per)
+    labels = batch.get("txt_labels")
+    if labels is not None:
+        lab = torch.as_tensor(labels).cpu().reshape(-1)
+        plan["mlm_pos"] = torch.nonzero(lab != -1).reshape(-1)
+        plan["mlm_tgt"] = lab[plan["mlm_pos"]]
+    vis = batch.get("gmap_visited_masks")
+    if vis is not None:
+        vis = torch.as_tensor(vis).cpu()
+        V1 = 1 + n_tok                                   # local logits: [stop] + the tokens of the last panorama
+        src_idx = torch.zeros(B, G, dtype=torch.long)
+        use_src = torch.zeros(B, G, dtype=torch.bool)
+        use_bw = torch.zeros(B, G, dtype=torch.bool)
+        bw_mask = torch.zeros(B, V1, dtype=torch.bool)
+        for b in range(B):
+            vp_b = batch["gmap_vpids"][b]
+            done = set(vp for vp, m in zip(vp_b, vis[b].tolist()) if m)
+            tmp = {}
+            for j, cand in enumerate(batch["traj_cand_vpids"][b][-1], start=1):
+                if cand in done:
+                    bw_mask[b, j] = True
+                else:
+                    tmp[cand] = j
+            for g, vp in enumerate(vp_b):
+                if g > 0 and vp not in done:
+                    if vp in tmp:
+                        src_idx[b, g], use_src[b, g] = tmp[vp], True
+                    else:
+                        use_bw[b, g] = True
+        plan.update(fuse_src=src_idx, fuse_use_src=use_src, fuse_use_bw=use_bw, fuse_bw_mask=bw_mask)
+    return plan
 
 
 def _bool_masks(lens, n):
@@ -138,6 +268,10 @@ class PretrainModel(nn.Module):
         self._cache = _WeightCache()
         self.weights_updated = self._cache.invalidate        # GradientStep(..., after_step=[model.weights_updated])
         self.use_native_linear = True
+        # optional split-precision forward (3 GEMMs, ~fp32 accuracy) of text_proj, whose output feeds the per-cell softmax.  Off by
+        # default: on the parity batch it does not change the gradient error, which comes from ReLU units of the ClsPrediction heads
+        # changing side under the fp16 rounding of ANY upstream operand (tools/diag_train_grad.py)
+        self.split_precision = False
 
     # ---- reference checkpoints carry the tied decoder weight as its own key (pretrain_cmt.py:68-71)
     def load_state_dict(self, state_dict, strict=True):
@@ -156,12 +290,12 @@ class PretrainModel(nn.Module):
             mod = getattr(mod, p)
         return mod
 
-    def lin(self, pre, x, weight=None, bias=None):
+    def lin(self, pre, x, weight=None, bias=None, split=False):
         w = self.P(pre + ".weight") if weight is None else weight
         b = (self.P(pre + ".bias") if weight is None else bias)
         N, K = w.shape
         if self.use_native_linear and x.is_cuda and K % 128 == 0 and N % 128 == 0:
-            return LinearFn.apply(x, w, b, self._cache)
+            return LinearFn.apply(x, w, b, self._cache, split and self.split_precision)
         return F.linear(x, w, b)
 
     def drop(self, x, p):
@@ -232,7 +366,7 @@ class PretrainModel(nn.Module):
         """BertEmbeddings + lang_encoder (vilmodel.py:62-93, 416-440)."""
         B, L = txt_ids.shape
         e = "bert.embeddings"
-        x = self.P(e + ".word_embeddings.weight")[txt_ids] + self.P(e + ".position_embeddings.weight")[:L][None] + \
+        x = F.embedding(txt_ids, self.P(e + ".word_embeddings.weight")) + self.P(e + ".position_embeddings.weight")[:L][None] + \
             self.P(e + ".token_type_embeddings.weight")[0]
         x = self.drop(self.ln(e + ".LayerNorm", x, self.config.layer_norm_eps), self.p_hid)
         add = self.neg_mask(txt_masks)
@@ -261,7 +395,7 @@ class PretrainModel(nn.Module):
             img, lens = view, vlen
         loc = self.ln(ie + ".loc_layer_norm", F.linear(batch["traj_loc_fts"].to(dev), self.P(ie + ".loc_linear.weight"),
                                                        self.P(ie + ".loc_linear.bias")), 1e-12)
-        x = img + loc + self.P(ie + ".nav_type_embedding.weight")[batch["traj_nav_types"].to(dev)] + \
+        x = img + loc + F.embedding(batch["traj_nav_types"].to(dev), self.P(ie + ".nav_type_embedding.weight")) + \
             self.P("bert.embeddings.token_type_embeddings.weight")[1]
         x = self.drop(self.ln(ie + ".layer_norm", x, 1e-12), self.p_hid)
         masks = _bool_masks(lens, x.shape[1])
@@ -270,43 +404,33 @@ class PretrainModel(nn.Module):
         return x, lens
 
     @staticmethod
-    def aggregate_gmap(pano, lens, step_lens, traj_vpids, traj_cand_vpids, gmap_vpids):
-        """GlobalMapEncoder._aggregate_gmap_features (vilmodel.py:578-612)."""
-        rows, row0 = [], 0
-        for i, T in enumerate(step_lens):
-            e, n = pano[row0:row0 + T], lens[row0:row0 + T]
-            row0 += T
-            e = e * _bool_masks(n, e.shape[1])[:, :, None]
-            own, seen = {}, {}
-            for t in range(T):
-                own[traj_vpids[i][t]] = e[t].sum(0) / n[t]
-                for j, vp in enumerate(traj_cand_vpids[i][t]):
-                    if vp not in own:
-                        seen.setdefault(vp, []).append(e[t, j])
-            rows.append(torch.stack([own[vp] if vp in own else torch.stack(seen[vp], 0).mean(0) for vp in gmap_vpids[i][1:]], 0))
-        G = 1 + max(r.shape[0] for r in rows)
-        return torch.stack([F.pad(r, (0, 0, 1, G - 1 - r.shape[0])) for r in rows], 0)
+    def aggregate_gmap(pano, plan):
+        """GlobalMapEncoder._aggregate_gmap_features (vilmodel.py:578-612) as one gather + one index_add (collate_plan)."""
+        dev = pano.device
+        B = len(plan["steps"])
+        vals = pano.reshape(-1, HID).index_select(0, plan["agg_src"]) * plan["agg_w"][:, None]
+        return torch.zeros(B * plan["G"], HID, device=dev).index_add(0, plan["agg_dst"], vals).view(B, plan["G"], HID)
 
-    def grid_pool(self, txt, batch, dev):
+    def grid_pool(self, txt, batch, plan, dev):
         """vilmodel.py:685-700 (fp32 here; the reference pools in fp16): per episode w = max_l <x, text_proj(txt)_l>, per cell a
-        softmax over its points; grid_proj applied after the convex combination (it commutes with it)."""
+        softmax over its points; grid_proj applied after the convex combination (it commutes with it).  One padded bmm for the
+        relevance, segment softmax by scatter / index_add over (episode, cell) bins; masked points go to a spare bin."""
         B = txt.shape[0]
-        tp = self.lin("bert.text_proj", txt)                                       # [B, L, 768]
-        xs, ws, ids = [], [], []
-        for b in range(B):
-            cell = torch.as_tensor(batch["grid_map"][b]).to(dev).long()
-            keep = cell >= 0
-            x = torch.as_tensor(batch["grid_fts"][b]).to(dev)[keep].float()
-            xs.append(x)
-            ws.append((x @ tp[b].t()).max(-1)[0])
-            ids.append(cell[keep] + b * 196)
-        x, w, ids = torch.cat(xs, 0), torch.cat(ws, 0), torch.cat(ids, 0)
-        m = torch.full((B * 196,), float("-inf"), device=dev).scatter_reduce(0, ids, w.detach(), "amax", include_self=True)
+        tp = self.lin("bert.text_proj", txt, split=True)                           # [B, L, 768]
+        x = torch.cat([torch.as_tensor(f).to(dev, non_blocking=True) for f in batch["grid_fts"]], 0).float()      # [n, 768]
+        cell = torch.cat([torch.as_tensor(c).to(dev, non_blocking=True) for c in batch["grid_map"]], 0).long()
+        ep, slot = plan["pt_ep"], plan["pt_slot"]
+        xpad = torch.zeros(B, plan["pt_max"], HID, device=dev).index_put((ep, slot), x)
+        w = torch.bmm(xpad, tp.transpose(1, 2)).max(-1)[0][ep, slot]               # [n]
+        nb = B * 196
+        ids = torch.where(cell >= 0, cell + ep * 196, torch.full_like(cell, nb))
+        m = torch.full((nb + 1,), float("-inf"), device=dev).scatter_reduce(0, ids, w.detach(), "amax", include_self=True)
         e = torch.exp(w - m[ids])
-        z = torch.zeros(B * 196, device=dev).index_add(0, ids, e)
-        pooled = torch.zeros(B * 196, HID, device=dev).index_add(0, ids, (e / z[ids])[:, None] * x)
-        nonempty = torch.zeros(B * 196, dtype=torch.bool, device=dev)
+        z = torch.zeros(nb + 1, device=dev).index_add(0, ids, e)
+        pooled = torch.zeros(nb + 1, HID, device=dev).index_add(0, ids, (e / z[ids])[:, None] * x)[:nb]
+        nonempty = torch.zeros(nb + 1, dtype=torch.bool, device=dev)
         nonempty[ids] = True
+        nonempty = nonempty[:nb]
         proj = self.lin("bert.grid_proj", pooled) * nonempty[:, None]
         return proj.view(B, 196, HID), nonempty.view(B, 196)
 
@@ -314,18 +438,14 @@ class PretrainModel(nn.Module):
         """vilmodel.py:701-711 with the mask-aliasing quirk (valid = [0,k) u (S n [k,k')), truncated to C = max k)."""
         B = cells.shape[0]
         k = nonempty.sum(1)
-        C = int(k.max()) if B else 0
-        embeds = torch.zeros(B, C, HID, device=cells.device)
-        masks = torch.zeros(B, C, dtype=torch.bool, device=cells.device)
-        for b in range(B):
-            kb = int(k[b])
-            embeds[b, :kb] = cells[b][nonempty[b]]
-            k2 = kb + int(nonempty[b, kb:].sum())
-            row = nonempty[b].clone()
-            row[:kb] = True
-            row[k2:] = False
-            masks[b] = row[:C]
-        return embeds, masks, C
+        C = int(k.max()) if B else 0                                             # the one host read (it sizes the sequence)
+        order = torch.sort((~nonempty).to(torch.int8), dim=1, stable=True)[1][:, :C]        # non-empty cells first, in cell order
+        pos = torch.arange(196, device=cells.device)[None, :]
+        embeds = cells.gather(1, order[:, :, None].expand(B, C, HID)) * (pos[:, :C] < k[:, None])[:, :, None]
+        tail = nonempty & (pos >= k[:, None])
+        k2 = k + tail.sum(1)
+        masks = ((pos < k[:, None]) | tail) & (pos < k2[:, None])
+        return embeds, masks[:, :C], C
 
     def trunk(self, batch, dev, stop_before_fusion=False):
         """GlocalTextPathCMT.forward up to the fused [gmap'; vp] embeddings (vilmodel.py:668-764)."""
@@ -334,24 +454,28 @@ class PretrainModel(nn.Module):
         txt_masks = _bool_masks(batch["txt_lens"].to(dev), txt_ids.shape[1])
         txt = self.text(txt_ids, txt_masks)
         pano, lens = self.panoramas(batch, dev)
-        step_lens = [int(x) for x in batch["traj_step_lens"]]
-        gmap_img = self.aggregate_gmap(pano, lens, step_lens, batch["traj_vpids"], batch["traj_cand_vpids"], batch["gmap_vpids"])
+        plan = batch.get("_plan")
+        if plan is None or plan["agg_w"].device != dev:
+            plan = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in (plan or collate_plan(batch)).items()}
+            batch["_plan"] = plan
+        assert plan["n_tok"] == pano.shape[1]
+        gmap_img = self.aggregate_gmap(pano, plan)
         G = gmap_img.shape[1]
         gmap_masks = _bool_masks(batch["gmap_lens"].to(dev), G)
         ge = "bert.global_encoder"
-        gmap = gmap_img + self.P(ge + ".gmap_step_embeddings.weight")[batch["gmap_step_ids"].to(dev)] + \
+        gmap = gmap_img + F.embedding(batch["gmap_step_ids"].to(dev), self.P(ge + ".gmap_step_embeddings.weight")) + \
             self.ln(ge + ".gmap_pos_embeddings.1", F.linear(batch["gmap_pos_fts"].to(dev), self.P(ge + ".gmap_pos_embeddings.0.weight"),
                                                             self.P(ge + ".gmap_pos_embeddings.0.bias")), 1e-12)
-        last = torch.tensor([sum(step_lens[:i + 1]) - 1 for i in range(len(step_lens))], device=dev)
+        last = plan["last"]
         vp_lens = lens[last] + 1
         V = int(vp_lens.max())
-        vp_img = torch.cat([torch.zeros(len(step_lens), 1, HID, device=dev), pano[last]], 1)[:, :V]
+        vp_img = torch.cat([torch.zeros(len(plan["steps"]), 1, HID, device=dev), pano.index_select(0, last)], 1)[:, :V]
         vp_masks = _bool_masks(vp_lens, V)
         le = "bert.local_encoder"
         vp = vp_img + self.ln(le + ".vp_pos_embeddings.1", F.linear(batch["vp_pos_fts"].to(dev)[:, :V], self.P(le + ".vp_pos_embeddings.0.weight"),
                                                                     self.P(le + ".vp_pos_embeddings.0.bias")), 1e-12)
         # grid map: pooled cells + position embedding, compacted; map sequence = [cells ; gmap]
-        cells, nonempty = self.grid_pool(txt, batch, dev)
+        cells, nonempty = self.grid_pool(txt, batch, plan, dev)
         pos = self.ln("bert.grid_pos_embeddings.1", F.linear(batch["gridmap_pos_fts"].to(dev), self.P("bert.grid_pos_embeddings.0.weight"),
                                                              self.P("bert.grid_pos_embeddings.0.bias")), 1e-12)
         cell_embeds, cell_masks, C = self.compact(cells + pos, nonempty)
@@ -391,14 +515,14 @@ class PretrainModel(nn.Module):
             txt = self.cross(p + ".visual_attention", txt, ctx, ctx_add)
             txt = self.bert_self(p + ".lang_self_att", txt, t_add)
             txt = self.bert_ffn(p + ".lang_inter", p + ".lang_output", txt)
-        labels = batch["txt_labels"].to(dev)
-        h = txt[labels != -1]
+        plan = batch["_plan"]
+        h = txt.reshape(-1, HID).index_select(0, plan["mlm_pos"])
         mp = "mlm_head.predictions"
         h = self.ln(mp + ".transform.LayerNorm", self.gelu(self.lin(mp + ".transform.dense", h)), self.config.layer_norm_eps)
         scores = self.lin(None, h, self.P("bert.embeddings.word_embeddings.weight"), None) + self.P(mp + ".bias")
         if not compute_loss:
             return scores
-        return F.cross_entropy(scores, labels[labels != -1], reduction="none")
+        return F.cross_entropy(scores, plan["mlm_tgt"], reduction="none")
 
     def forward_sap(self, batch, dev, compute_loss=True):
         """pretrain_cmt.py:214-292."""
@@ -410,27 +534,18 @@ class PretrainModel(nn.Module):
         gl = (self.cls_head("global_sap_head", gmap_e).squeeze(2) * fw).masked_fill(visited, ninf).masked_fill(~gmap_masks, ninf)
         gr = self.cls_head("grid_sap_head", gmap2).squeeze(2).masked_fill(visited, ninf).masked_fill(~gmap_masks, ninf)
         ll = self.cls_head("local_sap_head", vp_e).squeeze(2) * (1 - fw)
-        steps = [int(x) for x in batch["traj_step_lens"]]
-        last = torch.tensor([sum(steps[:i + 1]) - 1 for i in range(B)])
-        not_nav = batch["traj_nav_types"][last][:, :ll.shape[1] - 1].to(dev) != 1
+        plan = batch["_plan"]
+        not_nav = batch["traj_nav_types"].to(dev)[plan["last"]][:, :ll.shape[1] - 1] != 1
         ll = ll.masked_fill(torch.cat([torch.zeros(B, 1, dtype=torch.bool, device=dev), not_nav], 1), ninf)
-        # logit fusion (pretrain_cmt.py:256-273): candidates of the last panorama
-        fused = gl.clone()
-        fused[:, 0] = fused[:, 0] + ll[:, 0]
-        vis_host = visited.cpu()
-        for i in range(B):
-            vp_i = batch["gmap_vpids"][i]
-            done = set(vp for vp, m in zip(vp_i, vis_host[i]) if m)
-            tmp, bw = {}, 0
-            for j, cand in enumerate([None] + list(batch["traj_cand_vpids"][i][-1])):
-                if j > 0:
-                    if cand in done:
-                        bw = bw + ll[i, j]
-                    else:
-                        tmp[cand] = ll[i, j]
-            for j, vp in enumerate(vp_i):
-                if j > 0 and vp not in done:
-                    fused[i, j] = fused[i, j] + (tmp[vp] if vp in tmp else bw)
+        # logit fusion (pretrain_cmt.py:256-273) through collate_plan's index tensors
+        V1 = ll.shape[1]
+        llz = torch.where(torch.isfinite(ll), ll, torch.zeros_like(ll))              # masked views are never sources
+        bw = (llz * plan["fuse_bw_mask"][:, :V1]).sum(1, keepdim=True)
+        add = torch.where(plan["fuse_use_src"], llz.gather(1, plan["fuse_src"].clamp(max=V1 - 1)), torch.zeros_like(gl)) + \
+            torch.where(plan["fuse_use_bw"], bw.expand_as(gl), torch.zeros_like(gl))
+        first = torch.zeros_like(gl)
+        first[:, 0] = 1.0
+        fused = gl + add + first * ll[:, :1]
         if not compute_loss:
             return gl, ll, fused
         ga, la = batch["global_act_labels"].to(dev), batch["local_act_labels"].to(dev)

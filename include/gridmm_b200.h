@@ -307,6 +307,17 @@ int gridmm_cast_transpose_f16(const void* src, int src_is_f16, long long lds, in
                               long long ldt, int r_pad, cudaStream_t stream);
 int gridmm_colsum_f32(const float* dy, long long ld, int M, int N, float* out, cudaStream_t stream);
 
+/* A trainable nn.Linear(K -> N) (K, N multiples of 128) in one call per direction, what torch.nn.functional.linear and its autograd
+ * node do in the reference's training loop (pretrain_src/train_r2r.py:244-258):
+ * forward:  x fp32 [M, K] (pitch ldx) -> x16 [M, K] (scratch) and x16t [K, m_pad] (the caller keeps it for backward; m_pad = M rounded
+ *           up to 64), y[M, N] = x16 . w16[N, K]^T + bias (fp32 out, bias may be NULL);
+ * backward: dy fp32 [M, N] (pitch lddy) -> dy16 [M, N] and dy16t [N, m_pad] (scratch); db[N] = column sums of dy, fused into the cast
+ *           (overwritten; NULL = skip); dx[M, K] = dy16 . w16t[K, N]^T (NULL = skip); dw[N, K] = dy16t . x16t^T (NULL = skip). */
+int gridmm_linear_train_fwd(const float* x, long long ldx, int M, int K, const void* w16, int N, const float* bias, float* y,
+                            void* x16, void* x16t, int m_pad, cudaStream_t stream);
+int gridmm_linear_train_bwd(const float* dy, long long lddy, int M, int N, int K, const void* w16t, const void* x16t, int m_pad,
+                            void* dy16, void* dy16t, float* dx, float* dw, float* db, cudaStream_t stream);
+
 /* Debug hooks (tools/microbench.py only): per-CTA clock64 counters written by the following launches ([grid][8] for the
  * GEMM, [grid][16] for the pooling kernel: role totals and time spent waiting on each mbarrier).  NULL disables. */
 void gridmm_debug_set_gemm_counters(long long* dbg);

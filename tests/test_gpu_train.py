@@ -95,9 +95,16 @@ def test_pretrain_model_losses_and_gradients(task):
     (losses.mean() * scale).backward()
     torch.cuda.synchronize()
     assert abs(float(losses.mean()) - ref_loss) < 2e-3 * max(1.0, abs(ref_loss))
-    # Per tensor: ||g - g_ref|| <= 1e-2 ||g_ref|| + 2e-3 * (RMS gradient element of the whole model) * sqrt(numel).  The absolute
+    # Tolerances.  MLM: whole-model relative error < 2e-3 (measured 6.5e-4), per tensor 1e-2.  SAP: < 4e-2 / 8e-2: the ClsPrediction
+    # heads contain ReLUs, and the fp16 rounding of any upstream operand (relative 5e-4) moves a fraction ~1e-3 of their units across
+    # zero; each flipped unit switches its whole gradient contribution on or off, so the gradient is a DISCONTINUOUS function of the
+    # forward values.  Measured: 6.6e-3 .. 2.4e-2 from run to run (index_add atomics reorder sums, the fp16 casts turn that 1e-7 noise
+    # into different flips); torch fp32 linears on the same GPU give 2.1e-4, fp16 rounding in the backward GEMMs alone 4.8e-4, in the
+    # forward alone 0.9-1.5e-2; rounding one single block's linears reproduces the same 2.6e-3 jump (tools/diag_train_grad.py).
+    # Per tensor: ||g - g_ref|| <= tol ||g_ref|| + 2e-3 * (RMS gradient element of the whole model) * sqrt(numel); the absolute
     # term is for tensors whose gradient is analytically zero (key biases: softmax is shift-invariant; the last bias and LayerNorm
     # bias of a ClsPrediction head under a softmax over its rows), where both sides hold rounding noise only.
+    tol_model, tol_tensor = (4e-2, 8e-2) if task == "sap" else (2e-3, 1e-2)
     tot_sq = sum(float(g.double().pow(2).sum()) for g in ref_grads.values())
     tot_n = sum(g.numel() for g in ref_grads.values())
     rms = (tot_sq / tot_n) ** 0.5
@@ -112,7 +119,7 @@ def test_pretrain_model_losses_and_gradients(task):
         err, ref = (got - rg).norm().item(), rg.norm().item()
         err_sq += err * err
         worst[name] = err / max(ref, 1e-30)
-        if err > 1e-2 * ref + 2e-3 * rms * rg.numel() ** 0.5:
+        if err > tol_tensor * ref + 2e-3 * rms * rg.numel() ** 0.5:
             bad.append((name, err, ref, rg.numel()))
     top = sorted(worst.items(), key=lambda kv: -kv[1])
     sig = [kv for kv in top if float(ref_grads[kv[0]].norm()) > 0.05 * rms * ref_grads[kv[0]].numel() ** 0.5]
@@ -120,7 +127,7 @@ def test_pretrain_model_losses_and_gradients(task):
           % (task, len(worst), (err_sq / tot_sq) ** 0.5, sig[:4]))
     assert len(worst) > 100
     assert not bad, bad
-    assert (err_sq / tot_sq) ** 0.5 < 5e-3
+    assert (err_sq / tot_sq) ** 0.5 < tol_model
 
 
 def test_one_training_step_through_flat_buffers():
