@@ -64,7 +64,7 @@ _SIGS = {
     "gridmm_fusion_inputs": [c_void_p] * 13 + [c_int] + [c_void_p] * 5 + [c_int] * 6 + [c_void_p],
     "gridmm_kv_index": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_linear_f16_rows": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
-    "gridmm_attention_varlen_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+    "gridmm_attention_varlen_f16": [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p,
                                     c_int, c_int, c_int, c_int, c_float, c_void_p],
     "gridmm_split_rows": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "gridmm_pos_embed": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -231,6 +231,10 @@ int gridmm_attention_tc(const void* q, int ldq, int q_rows, const void* k, int l
                         int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk, float scale,
                         cudaStream_t stream, const int* q_off, const int* q_cnt, const int* k_off, const int* k_cnt,
                         const float* kbias, long long q_total, long long k_total);      // attn_tc.cu
+int gridmm_attention_tc_pair(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv, int k_rows, void* o,
+                             int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk, float scale,
+                             cudaStream_t stream, const int* q_off, const int* q_cnt, const int* k_off, const int* k_cnt,
+                             const float* kbias, long long q_total, long long k_total);      // attn_tc.cu
 static int g_attn_legacy = 0;
 // Debug hook: 1 forces the mma.sync kernel, 2 the tcgen05 kernel (A/B timing and parity of the two paths); 0 = by shape.
 extern "C" void gridmm_debug_set_attn_legacy(int on) { g_attn_legacy = on; }
@@ -246,6 +250,15 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     // threads is padding and the mma.sync kernel (64-row tiles, 4 warps) is faster -- measured at B=32: Sq=57/Sk=296 18.4 vs
     // 22.5 us, Sq=57/Sk=57 5.3 vs 6.8 us; Sq=216/Sk=216 35.8 vs 24.6 us, Sq=216/Sk=80 21.6 vs 13.6 us.  g_attn_legacy: 1 forces
     // mma.sync, 2 forces tcgen05 (tests).
+    if (g_attn_legacy == 0 && sq <= 64 && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
+        // <= 64 queries: two heads per CTA on the tcgen05 head-pair kernel (Sk <= 256), else mma.sync below
+        const int rc = gridmm_attention_tc_pair(q, ldq, q_rows, k, ldk, v, ldv, k_rows, o, ldo, kmask, mask_neg, batch, heads, sq, sk, scale,
+                                                stream, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0);
+        if (rc != GRIDMM_ERR_SHAPE) {
+            if (rc == 0) gridmm_count_launch(1);
+            return rc;
+        }
+    }
     if (g_attn_legacy != 1 && (sq > 64 || g_attn_legacy == 2) && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
         // tcgen05 path (attn_tc.cu); shapes it does not cover (Sk > 320, unaligned output) fall through to mma.sync
         const int rc = gridmm_attention_tc(q, ldq, q_rows, k, ldk, v, ldv, k_rows, o, ldo, kmask, mask_neg, batch, heads, sq, sk, scale, stream,
@@ -283,12 +296,20 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
 // k / v and all of them are valid, so no key mask is applied (a masked key contributes exp(-10000) = 0 in fp32: dropping it is
 // exact).  max_sk >= max_b k_cnt[b] sizes the shared memory.  Always the mma.sync kernel (query tiles of 64 / 128 rows).
 extern "C" int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
-                                           const int* k_off, const int* k_cnt, int max_sk, const float* k_bias, void* o, int ldo,
-                                           int batch, int heads, int sq, float scale, cudaStream_t stream) {
+                                           const int* k_off, const int* k_cnt, int max_sk, long long k_total, const float* k_bias,
+                                           void* o, int ldo, int batch, int heads, int sq, float scale, cudaStream_t stream) {
     using namespace gmm;
     if (batch <= 0 || sq <= 0) return 0;
     if (!q || !k || !v || !o || !k_off || !k_cnt) return GRIDMM_ERR_ARG;
     if (max_sk <= 0 || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return GRIDMM_ERR_SHAPE;
+    if (g_attn_legacy == 0 && sq <= 64 && k_total > 0 && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
+        const int rc = gridmm_attention_tc_pair(q, ldq, q_rows, k, ldk, v, ldv, 0, o, ldo, nullptr, 0.0f, batch, heads, sq, max_sk, scale, stream,
+                                                nullptr, nullptr, k_off, k_cnt, k_bias, 0, k_total);
+        if (rc != GRIDMM_ERR_SHAPE) {
+            if (rc == 0) gridmm_count_launch(1);
+            return rc;
+        }
+    }
     AttnParams p;
     p.q = reinterpret_cast<const __half*>(q); p.k = reinterpret_cast<const __half*>(k);
     p.v = reinterpret_cast<const __half*>(v); p.o = reinterpret_cast<__half*>(o);

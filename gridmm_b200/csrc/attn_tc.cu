@@ -213,6 +213,174 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
     pdl_launch_dependents();      // at the very end: only the next launch's latency and prologue overlap this kernel's tail
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Head-PAIR variant for short query sequences (<= 64 rows per (episode, head): the 57-query fusion-encoder shapes).  One CTA per
+// (two heads, episode): the 128 TMEM lanes hold the queries of head h0 (lanes 0..63) and of head h0+1 (lanes 64..127), so every
+// softmax thread owns a real row instead of half of them idling on padding.
+//   S1[128, Sk] = Qpair . K(h0)^T   (lanes 0..63 meaningful)      S2[128, Sk] = Qpair . K(h0+1)^T   (lanes 64..127 meaningful)
+//   P (fp16, written by each lane over the first half of ITS OWN S1 columns; lanes 64..127 read S2, their S1 columns are dead)
+//   O1[128, 64] = P . V(h0), O2[128, 64] = P . V(h0+1) over the dead S2 columns; lanes 0..63 store O1, lanes 64..127 store O2.
+// The tensor pipe does twice the useful flops (it is 10 % busy in this kernel); the per-row softmax latency, which is what the
+// kernel is made of, is spent on 114 rows per CTA instead of 57.  Sk <= 256 (S1 + S2 fit 512 TMEM columns).
+__global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                           const __grid_constant__ CUtensorMap tmV, AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;                                  // 2 x 64 rows x 128 B
+    uint8_t* sK0 = sQ + 128 * 128;                       // nkey x 128 B each
+    uint8_t* sK1 = sK0 + p.nkey * 128;
+    uint8_t* sV0 = sK1 + p.nkey * 128;
+    uint8_t* sV1 = sV0 + p.nkey * 128;
+    float* sM = reinterpret_cast<float*>(sV1 + p.nkey * 128);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sM + p.nkey);        // [0] loads, [1] S ready, [2] P ready, [3] O ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h0 = blockIdx.x * 2, b = blockIdx.y;
+    pdl_wait();
+    const int q_base = p.q_off ? __ldg(p.q_off + b) : b * p.q_rows;
+    const int q_n = p.q_cnt ? __ldg(p.q_cnt + b) : p.sq;
+    const int k_base = p.k_off ? __ldg(p.k_off + b) : b * p.k_rows;
+    const int k_n = p.k_cnt ? __ldg(p.k_cnt + b) : p.sk;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 128); mbar_init(&bars[3], 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    const int nkey = max((k_n + 15) & ~15, 16);
+    const size_t m_base = p.k_off ? static_cast<size_t>(k_base) : static_cast<size_t>(b) * p.sk;
+    for (int j = threadIdx.x; j < nkey; j += blockDim.x) {
+        float m = -INFINITY;
+        if (j < k_n) {
+            m = (!p.kmask || p.kmask[m_base + j]) ? 0.0f : p.mask_neg;
+            if (p.kbias && m == 0.0f) m = p.kbias[m_base + j];
+        }
+        sM[j] = m;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
+    const uint32_t oc = static_cast<uint32_t>(p.o_col);      // column of S2, later of O1 | O2
+
+    if (warp == 4) {
+        if (elect_one()) {
+            mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(128 * 128 + 4 * nkey * 128));
+            tma_load_2d(sQ, &tmQ, h0 * 64, q_base, &bars[0]);
+            tma_load_2d(sQ + 64 * 128, &tmQ, (h0 + 1) * 64, q_base, &bars[0]);
+            for (int j = 0; j < nkey; j += 16) {
+                tma_load_2d(sK0 + j * 128, &tmK, h0 * 64, k_base + j, &bars[0]);
+                tma_load_2d(sK1 + j * 128, &tmK, (h0 + 1) * 64, k_base + j, &bars[0]);
+                tma_load_2d(sV0 + j * 128, &tmV, h0 * 64, k_base + j, &bars[0]);
+                tma_load_2d(sV1 + j * 128, &tmV, (h0 + 1) * 64, k_base + j, &bars[0]);
+            }
+        }
+        __syncwarp();
+        mbar_wait(&bars[0], 0);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t id_s = umma_idesc_f16_rt(128, nkey, 0);
+            const uint64_t dq = umma_desc_sw128_kmajor(smem_u32(sQ));
+            const uint64_t dk0 = umma_desc_sw128_kmajor(smem_u32(sK0));
+            const uint64_t dk1 = umma_desc_sw128_kmajor(smem_u32(sK1));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base, dq + 2 * k, dk0 + 2 * k, id_s, k ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + oc, dq + 2 * k, dk1 + 2 * k, id_s, k ? 1u : 0u);
+            umma_commit(&bars[1]);
+        }
+        __syncwarp();
+        mbar_wait(&bars[2], 0);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t id_o = umma_idesc_f16_rt(128, 64, 1);
+            const uint32_t v0 = smem_u32(sV0), v1 = smem_u32(sV1);
+            for (int j = 0; j < nkey / 16; ++j)
+                umma_f16_ts(tmem_base + oc, tmem_base + j * 8, umma_desc_sw128_mnmajor(v0 + j * 2048), id_o, j ? 1u : 0u);
+            for (int j = 0; j < nkey / 16; ++j)
+                umma_f16_ts(tmem_base + oc + 64, tmem_base + j * 8, umma_desc_sw128_mnmajor(v1 + j * 2048), id_o, j ? 1u : 0u);
+            umma_commit(&bars[3]);
+        }
+        __syncwarp();
+    } else {
+        const int half = warp >> 1;                         // 0: head h0 (lanes 0..63), 1: head h0 + 1 (lanes 64..127)
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const uint32_t t_s = t_lane + (half ? oc : 0u);
+        constexpr float LOG2E = 1.4426950408889634f;
+        const float sc = p.scale * LOG2E;
+        mbar_wait(&bars[1], 0);
+        tc_fence_after();
+        float mx = -INFINITY;
+        for (int c = 0; c < nkey; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_s + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float mj = sM[c + j];
+                if (mj != -INFINITY) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), sc, mj * LOG2E));
+            }
+        }
+        const float m_use = (mx == -INFINITY) ? 0.0f : mx;
+        float l = 0.f;
+        for (int c = 0; c < nkey; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_s + c, v);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const float m0 = sM[c + j], m1 = sM[c + j + 1];
+                const float p0 = (m0 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[j]), sc, m0 * LOG2E) - m_use);
+                const float p1 = (m1 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[j + 1]), sc, m1 * LOG2E) - m_use);
+                const __half2 hp = __floats2half2_rn(p0, p1);
+                const float2 fp = __half22float2(hp);
+                l += fp.x + fp.y;
+                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+            }
+            tmem_st_32x32b_x8(t_lane + (c >> 1), pk);     // P always at column 0 of the lane (lanes >= 64: over their dead S1 part)
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars[2]);
+        mbar_wait(&bars[3], 0);
+        tc_fence_after();
+        const float inv = l > 0.f ? 1.0f / l : 0.0f;
+        const int row = (warp & 1) * 32 + lane;
+        uint4 ov[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_lane + oc + half * 64 + c * 16, v);
+            tmem_ld_wait();
+            uint32_t hh[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const __half2 h2 = __floats2half2_rn(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
+                hh[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            ov[2 * c] = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            ov[2 * c + 1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+        }
+        if (row < q_n) {
+            uint4* dst = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(q_base) + row) * p.ldo + (h0 + half) * 64);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dst[c] = ov[c];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    }
+    pdl_launch_dependents();
+}
+
 }  // namespace gmm
 
 // returns GRIDMM_ERR_SHAPE when the shape is outside this kernel's range (the caller then uses the mma.sync kernel)
@@ -243,5 +411,37 @@ int gridmm_attention_tc(const void* q, int ldq, int q_rows, const void* k, int l
     GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((sq + 127) / 128, heads, batch);
     GMM_CUDA_CHECK(launch_pdl(attn_tc_kernel, grid, dim3(160), smem, stream, tmQ, tmK, tmV, p));
+    return 0;
+}
+
+// Head-pair kernel for <= 64 queries per (episode, head) and <= 256 keys; kmask may be NULL (every key of the k_cnt[b] rows valid).
+// Returns GRIDMM_ERR_SHAPE outside its range (the caller falls back to the mma.sync kernel).
+int gridmm_attention_tc_pair(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv, int k_rows, void* o,
+                             int ldo, const unsigned char* kmask, float mask_neg, int batch, int heads, int sq, int sk, float scale,
+                             cudaStream_t stream, const int* q_off, const int* q_cnt, const int* k_off, const int* k_cnt,
+                             const float* kbias, long long q_total, long long k_total) {
+    using namespace gmm;
+    const int nkey = max((sk + 15) & ~15, 16);
+    if (sq > 64 || nkey > 256 || (heads & 1) || (ldo % 8) || (reinterpret_cast<uintptr_t>(o) & 15)) return GRIDMM_ERR_SHAPE;
+    AttnTcParams p;
+    p.o = reinterpret_cast<__half*>(o); p.ldo = ldo; p.q_rows = q_rows; p.k_rows = k_rows; p.kmask = kmask; p.mask_neg = mask_neg;
+    p.sq = sq; p.sk = sk; p.nkey = nkey; p.scale = scale;
+    p.q_off = q_off; p.q_cnt = q_cnt; p.k_off = k_off; p.k_cnt = k_cnt; p.kbias = kbias;
+    p.o_col = (nkey + 31) & ~31;
+    const int need = p.o_col + (nkey > 128 ? nkey : 128);
+    p.tmem_cols = need <= 256 ? 256 : 512;
+    const uint64_t q_outer = q_total > 0 ? static_cast<uint64_t>(q_total) : static_cast<uint64_t>(batch) * q_rows;
+    const uint64_t k_outer = k_total > 0 ? static_cast<uint64_t>(k_total) : static_cast<uint64_t>(batch) * k_rows;
+    CUtensorMap tmQ, tmK, tmV;
+    int rc = make_tmap_f16_2d(&tmQ, q, static_cast<uint64_t>(heads) * 64, q_outer, static_cast<uint64_t>(ldq) * 2, 64, 64);
+    if (rc) return rc;
+    rc = make_tmap_f16_2d(&tmK, k, static_cast<uint64_t>(heads) * 64, k_outer, static_cast<uint64_t>(ldk) * 2, 64, 16);
+    if (rc) return rc;
+    rc = make_tmap_f16_2d(&tmV, v, static_cast<uint64_t>(heads) * 64, k_outer, static_cast<uint64_t>(ldv) * 2, 64, 16);
+    if (rc) return rc;
+    const int smem = 1024 + 128 * 128 + 4 * nkey * 128 + nkey * 4 + 64;
+    GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    dim3 grid(heads / 2, batch);
+    GMM_CUDA_CHECK(launch_pdl(attn_tc_pair_kernel, grid, dim3(160), smem, stream, tmQ, tmK, tmV, p));
     return 0;
 }

@@ -117,7 +117,8 @@ def attention_varlen(q, k, v, out, k_off, k_cnt, max_sk, batch, heads, sq, q_row
         _chk(t_, torch.float16, n)
     _chk(k_off, torch.int32, "k_off"); _chk(k_cnt, torch.int32, "k_cnt"); _chk(k_bias, torch.float32, "k_bias")
     _lib.call("gridmm_attention_varlen_f16", q.data_ptr(), q.stride(0), q_rows or sq, k.data_ptr(), k.stride(0), v.data_ptr(),
-              v.stride(0), k_off.data_ptr(), k_cnt.data_ptr(), max_sk, _lib.ptr(k_bias), out.data_ptr(), out.stride(0), batch, heads,
+              v.stride(0), k_off.data_ptr(), k_cnt.data_ptr(), max_sk, min(k.shape[0], v.shape[0]), _lib.ptr(k_bias), out.data_ptr(),
+              out.stride(0), batch, heads,
               sq, 1.0 / math.sqrt(64.0), _lib.stream_ptr())
 
 

@@ -323,7 +323,7 @@ class PretrainModel(nn.Module):
         return (1.0 - masks[:, None, None, :].float()) * -10000.0              # extend_neg_masks, ops.py:25-34
 
     def gelu(self, h):
-        return h * 0.5 * (1.0 + torch.erf(h / math.sqrt(2.0)))
+        return F.gelu(h)                                                        # erf form, as the reference's `gelu` (vilmodel.py:32-40)
 
     def bert_self(self, pre, x, add):
         a = self.attend(self.lin(pre + ".self.query", x), self.lin(pre + ".self.key", x), self.lin(pre + ".self.value", x), add)

@@ -137,9 +137,11 @@ int gridmm_kv_index(const unsigned char* map_mask, const unsigned char* txt_mask
 int gridmm_linear_f16_rows(const void* a, int lda, const void* w, int ldw, int M, int N, int K, const float* bias, void* out_f16,
                            int ld_f16, const int* m_dev, cudaStream_t stream);
 int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
-                                const int* k_off, const int* k_cnt, int max_sk, const float* k_bias, void* o, int ldo, int batch,
-                                int heads, int sq, float scale, cudaStream_t stream);
-/* k_bias: optional f32 per packed key row, added to that key's scores (log multiplicity of a de-duplicated key), or NULL. */
+                                const int* k_off, const int* k_cnt, int max_sk, long long k_total, const float* k_bias, void* o,
+                                int ldo, int batch, int heads, int sq, float scale, cudaStream_t stream);
+/* k_bias: optional f32 per packed key row, added to that key's scores (log multiplicity of a de-duplicated key), or NULL.
+ * k_total: rows of the k / v buffers (extent of the TMA tensor maps of the tcgen05 head-pair kernel, which serves sq <= 64 and
+ * max_sk <= 256: two heads of one episode share the 128 TMEM lanes); 0 = unknown (mma.sync kernel). */
 
 /* ---- packed ("ragged") MAP sequence ---------------------------------------------------------------------------
  * The reference pads every episode's map sequence [grid cells ; gmap nodes] to the batch maximum (vilmodel.py:813-838: on

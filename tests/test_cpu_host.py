@@ -20,7 +20,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), "include/gridmm_b200.h declares %s but the library does not export it" % n
     assert set(_lib._SIGS) <= set(names)
-    assert _lib.load().gridmm_abi_version() == 2
+    assert _lib.load().gridmm_abi_version() == 3
 
 
 def test_param_spec_matches_reference_layout():

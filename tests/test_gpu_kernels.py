@@ -127,9 +127,11 @@ def test_linear_strided_views():
 
 @pytest.mark.parametrize("legacy", [2, 1, 0])
 @pytest.mark.parametrize("B,Sq,Sk,neg", [(2, 216, 216, float("-inf")), (3, 57, 296, -10000.0), (2, 64, 80, -10000.0), (1, 5, 7, -10000.0),
-                                         (2, 130, 320, -10000.0), (1, 40, 400, float("-inf"))])
+                                         (2, 130, 320, -10000.0), (1, 40, 400, float("-inf")), (4, 57, 57, -10000.0),
+                                         (3, 57, 221, -10000.0), (2, 64, 256, float("-inf")), (2, 33, 250, -10000.0)])
 def test_attention(B, Sq, Sk, neg, legacy):
-    """legacy = 2: the tcgen05 kernel (Sk <= 320; Sk = 400 exercises its fall-back), 1: the mma.sync kernel, 0: dispatch by shape."""
+    """legacy = 2: the tcgen05 kernel (Sk <= 320; Sk = 400 exercises its fall-back), 1: the mma.sync kernel, 0: dispatch by shape
+    (Sq <= 64 and Sk <= 256: the tcgen05 head-pair kernel)."""
     import ctypes
     from gridmm_b200 import ops, _lib
     lib = _lib.load()
@@ -420,10 +422,12 @@ def test_pool_handmade_cells(sizes, hmma):
 
 
 
-def test_kv_index_and_varlen_attention():
-    """Packed fusion context: gridmm_kv_index positions, and attention over the packed keys == masked attention over the padded ones."""
+@pytest.mark.parametrize("S", [216, 150])
+def test_kv_index_and_varlen_attention(S):
+    """Packed fusion context: gridmm_kv_index positions, and attention over the packed keys == masked attention over the padded ones
+    (S = 150: <= 256 keys per episode, the tcgen05 head-pair kernel; S = 216: 296 keys, the mma.sync kernel)."""
     from gridmm_b200 import ops
-    B, S, L, Sq = 5, 216, 80, 57
+    B, L, Sq = 5, 80, 57
     KC = S + L
     g = torch.Generator().manual_seed(9)
     map_mask = (torch.rand(B, S, generator=g) < 0.6).to(torch.uint8); map_mask[:, -3:] = 1
