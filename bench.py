@@ -472,6 +472,10 @@ def main():
         import ctypes
         _lib.load().gridmm_debug_set_gemm_384.argtypes = [ctypes.c_int]
         _lib.load().gridmm_debug_set_gemm_384(1)
+    if os.environ.get("GRIDMM_ATTN_PAIR") == "1":         # A/B: tcgen05 head-pair attention for the 57-query shapes (opt-in, measured slower)
+        import ctypes
+        _lib.load().gridmm_debug_set_attn_legacy.argtypes = [ctypes.c_int]
+        _lib.load().gridmm_debug_set_attn_legacy(3)
     sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to produce samples
     step = Step(dev, seed=shard_seed(rank))
     step.run_resident()

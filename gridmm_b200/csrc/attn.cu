@@ -236,7 +236,8 @@ int gridmm_attention_tc_pair(const void* q, int ldq, int q_rows, const void* k, 
                              cudaStream_t stream, const int* q_off, const int* q_cnt, const int* k_off, const int* k_cnt,
                              const float* kbias, long long q_total, long long k_total);      // attn_tc.cu
 static int g_attn_legacy = 0;
-// Debug hook: 1 forces the mma.sync kernel, 2 the tcgen05 kernel (A/B timing and parity of the two paths); 0 = by shape.
+// Debug hook: 1 forces the mma.sync kernel, 2 the tcgen05 kernel (A/B timing and parity of the two paths), 3 = by shape but with the
+// tcgen05 head-pair kernel for <= 64 queries; 0 = by shape with the measured-fastest kernel per shape.
 extern "C" void gridmm_debug_set_attn_legacy(int on) { g_attn_legacy = on; }
 
 extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const void* k, int ldk, const void* v, int ldv,
@@ -250,8 +251,10 @@ extern "C" int gridmm_attention_f16(const void* q, int ldq, int q_rows, const vo
     // threads is padding and the mma.sync kernel (64-row tiles, 4 warps) is faster -- measured at B=32: Sq=57/Sk=296 18.4 vs
     // 22.5 us, Sq=57/Sk=57 5.3 vs 6.8 us; Sq=216/Sk=216 35.8 vs 24.6 us, Sq=216/Sk=80 21.6 vs 13.6 us.  g_attn_legacy: 1 forces
     // mma.sync, 2 forces tcgen05 (tests).
-    if (g_attn_legacy == 0 && sq <= 64 && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
-        // <= 64 queries: two heads per CTA on the tcgen05 head-pair kernel (Sk <= 256), else mma.sync below
+    if (g_attn_legacy == 3 && sq <= 64 && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
+        // <= 64 queries: two heads per CTA on the tcgen05 head-pair kernel (Sk <= 256).  Opt-in: measured at B=32 against the
+        // mma.sync kernel below, Sq=57/Sk=208 14.8 vs 12.0 us, Sq=57/Sk=57 7.0 vs 5.5 us (profiles/r2_microbench.txt): both are at
+        // the latency floor of one (load -> S -> softmax -> O -> store) chain per CTA and the tcgen05 chain has more hand-offs
         const int rc = gridmm_attention_tc_pair(q, ldq, q_rows, k, ldk, v, ldv, k_rows, o, ldo, kmask, mask_neg, batch, heads, sq, sk, scale,
                                                 stream, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0);
         if (rc != GRIDMM_ERR_SHAPE) {
@@ -302,7 +305,7 @@ extern "C" int gridmm_attention_varlen_f16(const void* q, int ldq, int q_rows, c
     if (batch <= 0 || sq <= 0) return 0;
     if (!q || !k || !v || !o || !k_off || !k_cnt) return GRIDMM_ERR_ARG;
     if (max_sk <= 0 || (ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return GRIDMM_ERR_SHAPE;
-    if (g_attn_legacy == 0 && sq <= 64 && k_total > 0 && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
+    if (g_attn_legacy == 3 && sq <= 64 && k_total > 0 && heads * 64 <= ldq && heads * 64 <= ldk && heads * 64 <= ldv) {
         const int rc = gridmm_attention_tc_pair(q, ldq, q_rows, k, ldk, v, ldv, 0, o, ldo, nullptr, 0.0f, batch, heads, sq, max_sk, scale, stream,
                                                 nullptr, nullptr, k_off, k_cnt, k_bias, 0, k_total);
         if (rc != GRIDMM_ERR_SHAPE) {

@@ -144,8 +144,11 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
         const float sc = p.scale * LOG2E;                  // scores are compared / exponentiated in the log2 domain
         mbar_wait(&bars[1], 0);
         tc_fence_after();
+        // a warp whose 32 rows all lie past the episode's queries (the ragged tail tile) skips both passes: its lanes of P stay
+        // whatever they were, rows are independent and its output rows are never stored
+        const int nk_w = (q0 + warp * 32 < q_n) ? nkey : 0;
         float mx = -INFINITY;
-        for (int c = 0; c < nkey; c += 16) {
+        for (int c = 0; c < nk_w; c += 16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(t_row + c, v);
             tmem_ld_wait();
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
         }
         const float m_use = (mx == -INFINITY) ? 0.0f : mx;
         float l = 0.f;
-        for (int c = 0; c < nkey; c += 16) {
+        for (int c = 0; c < nk_w; c += 16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(t_row + c, v);
             tmem_ld_wait();
@@ -217,13 +220,19 @@ __global__ void __launch_bounds__(160) attn_tc_kernel(const __grid_constant__ CU
 // ---------------------------------------------------------------------------------------------------------------------------------
 // Head-PAIR variant for short query sequences (<= 64 rows per (episode, head): the 57-query fusion-encoder shapes).  One CTA per
 // (two heads, episode): the 128 TMEM lanes hold the queries of head h0 (lanes 0..63) and of head h0+1 (lanes 64..127), so every
-// softmax thread owns a real row instead of half of them idling on padding.
+// lane owns a real row instead of half of them idling on padding.
 //   S1[128, Sk] = Qpair . K(h0)^T   (lanes 0..63 meaningful)      S2[128, Sk] = Qpair . K(h0+1)^T   (lanes 64..127 meaningful)
-//   P (fp16, written by each lane over the first half of ITS OWN S1 columns; lanes 64..127 read S2, their S1 columns are dead)
+//   P (fp16) written by each lane over consumed S1 columns of ITS OWN lane (lanes 64..127 read S2, their S1 columns are dead)
 //   O1[128, 64] = P . V(h0), O2[128, 64] = P . V(h0+1) over the dead S2 columns; lanes 0..63 store O1, lanes 64..127 store O2.
-// The tensor pipe does twice the useful flops (it is 10 % busy in this kernel); the per-row softmax latency, which is what the
-// kernel is made of, is spent on 114 rows per CTA instead of 57.  Sk <= 256 (S1 + S2 fit 512 TMEM columns).
-__global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+// S1 + S2 need up to 512 TMEM columns, i.e. one CTA per SM, so the row softmax (the bulk of this kernel) is spread over EIGHT warps:
+// warps w and w + 4 share TMEM lane quadrant w (a warp may only touch lanes 32 (warp % 4) ..) and split the row's keys in two
+// column ranges; row maxima and sums meet in shared memory.  The tensor pipe does twice the useful flops (it is ~10 % busy here).
+// Sk <= 256.
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(288) attn_tc_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                            const __grid_constant__ CUtensorMap tmV, AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -232,8 +241,9 @@ __global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant
     uint8_t* sK1 = sK0 + p.nkey * 128;
     uint8_t* sV0 = sK1 + p.nkey * 128;
     uint8_t* sV1 = sV0 + p.nkey * 128;
-    float* sM = reinterpret_cast<float*>(sV1 + p.nkey * 128);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sM + p.nkey);        // [0] loads, [1] S ready, [2] P ready, [3] O ready
+    float* sM = reinterpret_cast<float*>(sV1 + p.nkey * 128);         // [nkey] additive mask, log2 domain
+    float* sX = sM + p.nkey;                                          // [2][128] partial row maxima, then partial row sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 256);           // [0] loads, [1] S ready, [2] P ready, [3] O ready
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -243,13 +253,14 @@ __global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant
     const int q_n = p.q_cnt ? __ldg(p.q_cnt + b) : p.sq;
     const int k_base = p.k_off ? __ldg(p.k_off + b) : b * p.k_rows;
     const int k_n = p.k_cnt ? __ldg(p.k_cnt + b) : p.sk;
+    constexpr float LOG2E = 1.4426950408889634f;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 128); mbar_init(&bars[3], 1);
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 256); mbar_init(&bars[3], 1);
         fence_mbar_init();
     }
-    if (warp == 4) tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    if (warp == 8) tmem_alloc_rt(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
     const int nkey = max((k_n + 15) & ~15, 16);
     const size_t m_base = p.k_off ? static_cast<size_t>(k_base) : static_cast<size_t>(b) * p.sk;
     for (int j = threadIdx.x; j < nkey; j += blockDim.x) {
@@ -258,15 +269,17 @@ __global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant
             m = (!p.kmask || p.kmask[m_base + j]) ? 0.0f : p.mask_neg;
             if (p.kbias && m == 0.0f) m = p.kbias[m_base + j];
         }
-        sM[j] = m;
+        sM[j] = m * LOG2E;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     const uint32_t oc = static_cast<uint32_t>(p.o_col);      // column of S2, later of O1 | O2
+    const int n_chunks = nkey >> 4;                          // 16 keys per chunk
+    const int c_split = (n_chunks + 1) >> 1;                 // part 0: chunks [0, c_split), part 1: [c_split, n_chunks)
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             mbar_arrive_expect_tx(&bars[0], static_cast<uint32_t>(128 * 128 + 4 * nkey * 128));
             tma_load_2d(sQ, &tmQ, h0 * 64, q_base, &bars[0]);
@@ -274,6 +287,8 @@ __global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant
             for (int j = 0; j < nkey; j += 16) {
                 tma_load_2d(sK0 + j * 128, &tmK, h0 * 64, k_base + j, &bars[0]);
                 tma_load_2d(sK1 + j * 128, &tmK, (h0 + 1) * 64, k_base + j, &bars[0]);
+            }
+            for (int j = 0; j < nkey; j += 16) {
                 tma_load_2d(sV0 + j * 128, &tmV, h0 * 64, k_base + j, &bars[0]);
                 tma_load_2d(sV1 + j * 128, &tmV, (h0 + 1) * 64, k_base + j, &bars[0]);
             }
@@ -298,63 +313,90 @@ __global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant
         if (elect_one()) {
             const uint32_t id_o = umma_idesc_f16_rt(128, 64, 1);
             const uint32_t v0 = smem_u32(sV0), v1 = smem_u32(sV1);
-            for (int j = 0; j < nkey / 16; ++j)
-                umma_f16_ts(tmem_base + oc, tmem_base + j * 8, umma_desc_sw128_mnmajor(v0 + j * 2048), id_o, j ? 1u : 0u);
-            for (int j = 0; j < nkey / 16; ++j)
-                umma_f16_ts(tmem_base + oc + 64, tmem_base + j * 8, umma_desc_sw128_mnmajor(v1 + j * 2048), id_o, j ? 1u : 0u);
+            // chunk j of P lives at column 8 j (part 0) or 16 c_split + 8 (j - c_split) (part 1: over that part's own S columns)
+            for (int j = 0; j < n_chunks; ++j) {
+                const uint32_t pc = j < c_split ? j * 8 : c_split * 16 + (j - c_split) * 8;
+                umma_f16_ts(tmem_base + oc, tmem_base + pc, umma_desc_sw128_mnmajor(v0 + j * 2048), id_o, j ? 1u : 0u);
+            }
+            for (int j = 0; j < n_chunks; ++j) {
+                const uint32_t pc = j < c_split ? j * 8 : c_split * 16 + (j - c_split) * 8;
+                umma_f16_ts(tmem_base + oc + 64, tmem_base + pc, umma_desc_sw128_mnmajor(v1 + j * 2048), id_o, j ? 1u : 0u);
+            }
             umma_commit(&bars[3]);
         }
         __syncwarp();
     } else {
-        const int half = warp >> 1;                         // 0: head h0 (lanes 0..63), 1: head h0 + 1 (lanes 64..127)
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const int quad = warp & 3, part = warp >> 2;        // TMEM lane quadrant, column half
+        const int half = quad >> 1;                         // 0: head h0 (lanes 0..63), 1: head h0 + 1 (lanes 64..127)
+        const int row128 = quad * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
         const uint32_t t_s = t_lane + (half ? oc : 0u);
-        constexpr float LOG2E = 1.4426950408889634f;
         const float sc = p.scale * LOG2E;
+        const int c_lo = part ? c_split : 0, c_hi = part ? n_chunks : c_split;
         mbar_wait(&bars[1], 0);
         tc_fence_after();
         float mx = -INFINITY;
-        for (int c = 0; c < nkey; c += 16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_s + c, v);
+        for (int c = c_lo; c < c_hi; c += 2) {
+            uint32_t v[2][16];
+            const bool two = c + 1 < c_hi;
+            tmem_ld_32x32b_x16(t_s + c * 16, v[0]);
+            if (two) tmem_ld_32x32b_x16(t_s + c * 16 + 16, v[1]);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float mj = sM[c + j];
-                if (mj != -INFINITY) mx = fmaxf(mx, fmaf(__uint_as_float(v[j]), sc, mj * LOG2E));
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(v[u][j]), sc, sM[(c + u) * 16 + j]));
             }
         }
+        sX[part * 128 + row128] = mx;
+        bar_sync_named(1 + quad, 64);
+        mx = fmaxf(mx, sX[(part ^ 1) * 128 + row128]);
         const float m_use = (mx == -INFINITY) ? 0.0f : mx;
+        bar_sync_named(1 + quad, 64);                      // both partial maxima are read before the slots are reused for the sums
         float l = 0.f;
-        for (int c = 0; c < nkey; c += 16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_s + c, v);
+        for (int c = c_lo; c < c_hi; c += 2) {
+            uint32_t v[2][16];
+            const bool two = c + 1 < c_hi;
+            tmem_ld_32x32b_x16(t_s + c * 16, v[0]);
+            if (two) tmem_ld_32x32b_x16(t_s + c * 16 + 16, v[1]);
             tmem_ld_wait();
-            uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-                const float m0 = sM[c + j], m1 = sM[c + j + 1];
-                const float p0 = (m0 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[j]), sc, m0 * LOG2E) - m_use);
-                const float p1 = (m1 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[j + 1]), sc, m1 * LOG2E) - m_use);
-                const __half2 hp = __floats2half2_rn(p0, p1);
-                const float2 fp = __half22float2(hp);
-                l += fp.x + fp.y;
-                pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    // -inf masks (keys past the episode's end, key_padding_mask) give exactly 0 through ex2(-inf); the guard keeps a
+                    // stale non-finite score out
+                    const float m0 = sM[(c + u) * 16 + j], m1 = sM[(c + u) * 16 + j + 1];
+                    const float p0 = (m0 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[u][j]), sc, m0) - m_use);
+                    const float p1 = (m1 == -INFINITY) ? 0.0f : ex2f(fmaf(__uint_as_float(v[u][j + 1]), sc, m1) - m_use);
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    const float2 fp = __half22float2(hp);
+                    l += fp.x + fp.y;
+                    pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+                }
+                const int cc = c + u;
+                tmem_st_32x32b_x8(t_lane + (part ? c_split * 16 + (cc - c_split) * 8 : cc * 8), pk);
             }
-            tmem_st_32x32b_x8(t_lane + (c >> 1), pk);     // P always at column 0 of the lane (lanes >= 64: over their dead S1 part)
         }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bars[2]);
+        sX[part * 128 + row128] = l;
+        bar_sync_named(1 + quad, 64);
+        l += sX[(part ^ 1) * 128 + row128];
         mbar_wait(&bars[3], 0);
         tc_fence_after();
         const float inv = l > 0.f ? 1.0f / l : 0.0f;
-        const int row = (warp & 1) * 32 + lane;
-        uint4 ov[8];
+        const int row = (quad & 1) * 32 + lane;
+        // each of the row's two threads stores 32 of the 64 output columns
+        uint4 ov[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
             uint32_t v[16];
-            tmem_ld_32x32b_x16(t_lane + oc + half * 64 + c * 16, v);
+            tmem_ld_32x32b_x16(t_lane + oc + half * 64 + part * 32 + c * 16, v);
             tmem_ld_wait();
             uint32_t hh[8];
 #pragma unroll
@@ -366,14 +408,14 @@ __global__ void __launch_bounds__(160) attn_tc_pair_kernel(const __grid_constant
             ov[2 * c + 1] = make_uint4(hh[4], hh[5], hh[6], hh[7]);
         }
         if (row < q_n) {
-            uint4* dst = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(q_base) + row) * p.ldo + (h0 + half) * 64);
+            uint4* dst = reinterpret_cast<uint4*>(p.o + (static_cast<size_t>(q_base) + row) * p.ldo + (h0 + half) * 64 + part * 32);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) dst[c] = ov[c];
+            for (int c = 0; c < 4; ++c) dst[c] = ov[c];
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         __syncwarp();
         tc_fence_after();
         tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
@@ -439,9 +481,9 @@ int gridmm_attention_tc_pair(const void* q, int ldq, int q_rows, const void* k, 
     if (rc) return rc;
     rc = make_tmap_f16_2d(&tmV, v, static_cast<uint64_t>(heads) * 64, k_outer, static_cast<uint64_t>(ldv) * 2, 64, 16);
     if (rc) return rc;
-    const int smem = 1024 + 128 * 128 + 4 * nkey * 128 + nkey * 4 + 64;
+    const int smem = 1024 + 128 * 128 + 4 * nkey * 128 + nkey * 4 + 256 * 4 + 64;
     GMM_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid(heads / 2, batch);
-    GMM_CUDA_CHECK(launch_pdl(attn_tc_pair_kernel, grid, dim3(160), smem, stream, tmQ, tmK, tmV, p));
+    GMM_CUDA_CHECK(launch_pdl(attn_tc_pair_kernel, grid, dim3(288), smem, stream, tmQ, tmK, tmV, p));
     return 0;
 }

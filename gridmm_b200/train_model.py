@@ -270,7 +270,7 @@ class PretrainModel(nn.Module):
         self.use_native_linear = True
         # optional split-precision forward (3 GEMMs, ~fp32 accuracy) of text_proj, whose output feeds the per-cell softmax.  Off by
         # default: on the parity batch it does not change the gradient error, which comes from ReLU units of the ClsPrediction heads
-        # changing side under the fp16 rounding of ANY upstream operand (tools/diag_train_grad.py, DESIGN.md section 9)
+        # changing side under the fp16 rounding of ANY upstream operand (tools/diag_train_grad.py, DESIGN.md section 8)
         self.split_precision = False
 
     # ---- reference checkpoints carry the tied decoder weight as its own key (pretrain_cmt.py:68-71)

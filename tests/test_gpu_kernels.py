@@ -125,13 +125,13 @@ def test_linear_strided_views():
     assert out[:, :768].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("legacy", [2, 1, 0])
+@pytest.mark.parametrize("legacy", [2, 1, 0, 3])
 @pytest.mark.parametrize("B,Sq,Sk,neg", [(2, 216, 216, float("-inf")), (3, 57, 296, -10000.0), (2, 64, 80, -10000.0), (1, 5, 7, -10000.0),
                                          (2, 130, 320, -10000.0), (1, 40, 400, float("-inf")), (4, 57, 57, -10000.0),
                                          (3, 57, 221, -10000.0), (2, 64, 256, float("-inf")), (2, 33, 250, -10000.0)])
 def test_attention(B, Sq, Sk, neg, legacy):
-    """legacy = 2: the tcgen05 kernel (Sk <= 320; Sk = 400 exercises its fall-back), 1: the mma.sync kernel, 0: dispatch by shape
-    (Sq <= 64 and Sk <= 256: the tcgen05 head-pair kernel)."""
+    """legacy = 2: the tcgen05 kernel (Sk <= 320; Sk = 400 exercises its fall-back), 1: the mma.sync kernel, 0: dispatch by shape,
+    3: dispatch by shape with the tcgen05 head-pair kernel for Sq <= 64 and Sk <= 256."""
     import ctypes
     from gridmm_b200 import ops, _lib
     lib = _lib.load()
@@ -422,11 +422,14 @@ def test_pool_handmade_cells(sizes, hmma):
 
 
 
-@pytest.mark.parametrize("S", [216, 150])
-def test_kv_index_and_varlen_attention(S):
+@pytest.mark.parametrize("S,pair", [(216, 0), (150, 0), (150, 3), (216, 3)])
+def test_kv_index_and_varlen_attention(S, pair):
     """Packed fusion context: gridmm_kv_index positions, and attention over the packed keys == masked attention over the padded ones
-    (S = 150: <= 256 keys per episode, the tcgen05 head-pair kernel; S = 216: 296 keys, the mma.sync kernel)."""
-    from gridmm_b200 import ops
+    (pair = 3 and S = 150: <= 256 keys per episode, the tcgen05 head-pair kernel; otherwise the mma.sync kernel)."""
+    import ctypes
+    from gridmm_b200 import ops, _lib
+    lib = _lib.load()
+    lib.gridmm_debug_set_attn_legacy.argtypes = [ctypes.c_int]
     B, L, Sq = 5, 80, 57
     KC = S + L
     g = torch.Generator().manual_seed(9)
@@ -451,7 +454,11 @@ def test_kv_index_and_varlen_attention(S):
     packed = torch.zeros_like(kv)
     packed[: int(cnt.sum())] = kv[full.to(dev)]
     out = torch.empty_like(ref)
-    ops.attention_varlen(q, packed[:, :768], packed[:, 768:], out, kv_off, kv_cnt, KC, B, 12, Sq)
+    lib.gridmm_debug_set_attn_legacy(pair)
+    try:
+        ops.attention_varlen(q, packed[:, :768], packed[:, 768:], out, kv_off, kv_cnt, KC, B, 12, Sq)
+    finally:
+        lib.gridmm_debug_set_attn_legacy(0)
     torch.cuda.synchronize()
     assert (out.float() - ref.float()).abs().max().item() < 2e-3
     # GEMM over the first kv_off[B] rows only

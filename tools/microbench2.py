@@ -123,9 +123,11 @@ if "attn" in want:
         print("ATTN %-14s Sq=%3d Sk=%3d: %6.1f us  %6.1f TF" % (tag, Sq, Sk, us, fl / us / 1e6), flush=True)
         return us
     lib.gridmm_debug_set_attn_legacy.argtypes = [ctypes.c_int]
-    for legacy in (1, 2, 0):
+    for legacy in (1, 2, 3, 0):
         lib.gridmm_debug_set_attn_legacy(legacy)
-        print("--- attention kernel:", {1: "mma.sync", 2: "tcgen05", 0: "dispatch by shape"}[legacy], flush=True)
+        print("--- attention kernel:", {1: "mma.sync", 2: "tcgen05", 3: "dispatch by shape, tcgen05 head-pair kernel for <= 64 queries",
+                                        0: "dispatch by shape (default)"}[legacy], flush=True)
+        attn_case(57, 208, "x cross packed")           # the step's packed context averages 193 keys: head-pair kernel when dispatched by shape
         tot = attn_case(216, 216, "map self") * 2 + attn_case(216, 80, "map x txt") + attn_case(57, 296, "x cross") * 4 + attn_case(57, 57, "x self") * 4
         print("ATTN sum over the step's 11 launches: %.1f us" % tot, flush=True)
 
