@@ -9,6 +9,8 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${ta
 timeout 900 python bench.py --steps 200 --warmup 5 --gpu-eager-baseline > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench exit=$?"; cut -c1-1200 gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err; echo "ref exit=$?"; cut -c1-500 gpurun_out/${tag}_bench_ref.json
 for w in "reverie 8" "ce 8" "r2r 1" "r2r 15"; do set -- $w; timeout 300 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --workload $1 --T $2 > gpurun_out/${tag}_bench_$1_T$2.json 2> gpurun_out/${tag}_bench_$1_T$2.err; echo "bench $1 T=$2 exit=$?"; done
+timeout 600 python bench.py --workload pretrain --steps 20 --warmup 4 > gpurun_out/${tag}_bench_pretrain.json 2> gpurun_out/${tag}_bench_pretrain.err; echo "bench pretrain exit=$?"; cut -c1-400 gpurun_out/${tag}_bench_pretrain.json
+timeout 600 python bench.py --workload pretrain --impl reference --steps 2 --warmup 0 > gpurun_out/${tag}_bench_pretrain_ref.json 2> gpurun_out/${tag}_bench_pretrain_ref.err; echo "pretrain ref exit=$?"; cut -c1-300 gpurun_out/${tag}_bench_pretrain_ref.json
 timeout 300 python tools/host_time.py > gpurun_out/${tag}_host_time.txt 2>&1; head -4 gpurun_out/${tag}_host_time.txt
 timeout 600 python tools/microbench2.py > gpurun_out/${tag}_microbench.txt 2>&1; echo "micro exit=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/${tag}_launches.csv python tools/prof_pool.py > gpurun_out/${tag}_ncu_l.log 2>&1; echo "ncu launches exit=$?"
