@@ -27,7 +27,8 @@ _SIGS = {
                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "gridmm_cell_sort": [c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "gridmm_pool": [c_void_p, c_longlong, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
-                    c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+                    c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "gridmm_pool_plan": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "gridmm_linear_ln_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                              c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "gridmm_head_rows": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
@@ -102,6 +103,8 @@ def load():
         fn.argtypes = args
         fn.restype = c_int
     lib.gridmm_abi_version.restype = c_int
+    lib.gridmm_pool_ws_bytes.argtypes = [c_int, c_int, c_int]
+    lib.gridmm_pool_ws_bytes.restype = c_longlong
     lib.gridmm_launch_count.restype = c_longlong
     lib.gridmm_launch_count_reset.restype = None
     _lib = lib

@@ -68,4 +68,4 @@ void gridmm_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_rela
 
 extern "C" long long gridmm_launch_count() { return g_launches.load(std::memory_order_relaxed); }
 extern "C" void gridmm_launch_count_reset() { g_launches.store(0, std::memory_order_relaxed); }
-extern "C" int gridmm_abi_version() { return 3; }
+extern "C" int gridmm_abi_version() { return 4; }

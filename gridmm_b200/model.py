@@ -839,6 +839,8 @@ class GlocalTextPathNavCMT(nn.Module):
                        self.B32(gt + ".visual_attention.att.key.bias", gt + ".visual_attention.att.value.bias"), out_f16=kv_txt)
         if getattr(grid, "pending", False):
             grid.launch_update()          # gridmm_grid_update of a step(lazy=True): first kernel of the step's graph
+        # the pooling kernel's work plan only needs the sorted cells: it runs behind the grid update, concurrently with the text branch
+        plan_ws = ops.pool_plan(grid.cell_start, NC, B, grid.feat_dim)
         side.join()
 
         # ---- relevance pooling + grid_proj (vilmodel.py:796-807)
@@ -846,7 +848,7 @@ class GlocalTextPathNavCMT(nn.Module):
         w_out = self.buf("w_out", (B, grid.cap), f32, zero=True) if return_intermediates else None
         ops.pool(grid.slab, grid.feat_dim, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm,
                  grid.cap, grid.cell_start, grid.cell_rank, NC, None, L, B, pooled16, w_out=w_out, text_ws=text_ws,
-                 text_ws_ready=True)
+                 text_ws_ready=True, pool_ws_buf=plan_ws, plan_ready=True)
         proj32 = self.buf("proj32", (B * NC, HID), f32)
         ops.linear(pooled16, self.W16("grid_proj.weight"), self.B32("grid_proj.bias"), out_f32=proj32)
 

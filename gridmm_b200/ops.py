@@ -348,6 +348,29 @@ def pool_w_scratch(device, batch, cap):
     return ws
 
 
+def pool_ws(device, batch, feat_dim, num_ctas=0):
+    """Persistent workspace of gridmm_pool / gridmm_pool_plan: the work plan (one row range per CTA) and the partials of cells
+    that several CTAs pool in pieces (include/gridmm_b200.h)."""
+    key = ("ws", device, batch, feat_dim, num_ctas)
+    ws = _POOL_WS.get(key)
+    if ws is None:
+        with torch.cuda.device(device):
+            n = int(_lib.load().gridmm_pool_ws_bytes(batch, feat_dim, num_ctas))
+        if n <= 0:
+            raise _lib.GridmmError("gridmm_pool_ws_bytes(%d, %d, %d) failed" % (batch, feat_dim, num_ctas))
+        ws = _POOL_WS[key] = torch.zeros((n + 15) // 16 * 16, dtype=torch.uint8, device=device)
+    return ws
+
+
+def pool_plan(cell_start, n_cells, batch, feat_dim, num_ctas=0, ws=None):
+    """gridmm_pool_plan on the current stream; returns the workspace to hand to pool(..., pool_ws=ws, plan_ready=True)."""
+    _chk(cell_start, torch.int32, "cell_start")
+    if ws is None:
+        ws = pool_ws(cell_start.device, batch, feat_dim, num_ctas)
+    _lib.call("gridmm_pool_plan", cell_start.data_ptr(), n_cells, batch, feat_dim, num_ctas, ws.data_ptr(), _lib.stream_ptr())
+    return ws
+
+
 def linear_lanes(a16, w16, bias, out_lanes, rows_per_b):
     """text_proj written directly in gridmm_pool's lane-major layout (see include/gridmm_b200.h)."""
     _chk(a16, torch.float16, "a"); _chk(w16, torch.float16, "w"); _chk(bias, torch.float32, "bias")
@@ -358,8 +381,9 @@ def linear_lanes(a16, w16, bias, out_lanes, rows_per_b):
 
 
 def pool(fts, feat_dim, slots, t_cap, slot_rows, view_rows, tok_off, perm, cap, cell_start, cell_rank, n_cells, text_fts, l_pad,
-         batch, pooled, w_out=None, num_ctas=0, text_ws=None, text_ws_ready=False):
-    """text_fts [batch*l_pad, D] fp16, or None with text_ws_ready=True when `text_ws` was filled by linear_lanes."""
+         batch, pooled, w_out=None, num_ctas=0, text_ws=None, text_ws_ready=False, pool_ws_buf=None, plan_ready=False):
+    """text_fts [batch*l_pad, D] fp16, or None with text_ws_ready=True when `text_ws` was filled by linear_lanes.
+    pool_ws_buf / plan_ready: the workspace pool_plan() already filled for this cell_start and num_ctas."""
     _chk(fts, torch.float16, "fts"); _chk(text_fts, torch.float16, "text_fts"); _chk(pooled, torch.float16, "pooled")
     _chk(slots, torch.int32, "slots"); _chk(perm, torch.int32, "perm")
     if text_ws is None:
@@ -369,11 +393,15 @@ def pool(fts, feat_dim, slots, t_cap, slot_rows, view_rows, tok_off, perm, cap, 
     if text_ws.numel() < ((l_pad + 127) // 128) * batch * 128 * feat_dim:
         raise _lib.GridmmError("text_ws too small for %d text positions" % l_pad)
     w_scratch = pool_w_scratch(fts.device, batch, cap) if l_pad > 128 else None
+    if pool_ws_buf is None:
+        if plan_ready:
+            raise _lib.GridmmError("plan_ready needs the workspace that pool_plan filled")
+        pool_ws_buf = pool_ws(fts.device, batch, feat_dim, num_ctas)
     fts_rows = fts.numel() // feat_dim
     _lib.call("gridmm_pool", fts.data_ptr(), fts_rows, feat_dim, slots.data_ptr(), t_cap, slot_rows, view_rows, tok_off,
               perm.data_ptr(), cap, cell_start.data_ptr(), cell_rank.data_ptr(), n_cells, _lib.ptr(text_fts), l_pad, batch,
-              text_ws.data_ptr(), int(bool(text_ws_ready)), pooled.data_ptr(), _lib.ptr(w_out), _lib.ptr(w_scratch), num_ctas,
-              _lib.stream_ptr())
+              text_ws.data_ptr(), int(bool(text_ws_ready)), pooled.data_ptr(), _lib.ptr(w_out), _lib.ptr(w_scratch),
+              pool_ws_buf.data_ptr(), int(bool(plan_ready)), num_ctas, _lib.stream_ptr())
 
 
 def cell_sort(batch, cell, n_pts, grid_w, cap, perm, cell_start, cell_rank, n_nonempty):

@@ -89,11 +89,21 @@ int gridmm_cell_sort(int batch, const short* cell, const int* n_pts, int grid_w,
  *   pooled       fp16 [batch, n_cells, feat_dim], rows >= n_nonempty[b] are not written
  *   w_out        optional f32 [batch,cap]: w per sorted position (tests), or NULL
  *   w_scratch    f32 [batch,cap], required when l_pad > 128 (else may be NULL)
+ *   pool_ws      workspace of gridmm_pool_ws_bytes(batch, feat_dim, num_ctas) bytes, 16-byte aligned: the work plan (one
+ *                contiguous range of the batch's sorted valid rows per CTA, equal in cost; a range may end in the middle of a
+ *                large cell) and the un-normalised partials of cells that are pooled in pieces by several CTAs (merged by the
+ *                last piece to arrive, in CTA order: the result is deterministic).  plan_ready = 0: the plan is computed here
+ *                (one extra small launch); 1: gridmm_pool_plan already ran for this cell_start / num_ctas (e.g. on the stream
+ *                of gridmm_grid_update, concurrently with the text branch)
  *   num_ctas     0 = one CTA per SM */
 int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, const int* slots, int t_cap, int slot_rows, int view_rows,
                 int tok_off, const int* perm, int cap, const int* cell_start, const int* cell_rank, int n_cells,
                 const void* text_fts, int l_pad, int batch, void* text_ws, int text_ws_ready, void* pooled, float* w_out,
-                float* w_scratch, int num_ctas, cudaStream_t stream);
+                float* w_scratch, void* pool_ws, int plan_ready, int num_ctas, cudaStream_t stream);
+/* Work plan of gridmm_pool (replaces nothing in the reference: the reference loops over episodes and cells serially,
+ * vilmodel.py:796-807; this is the load balancing of that loop over the SMs).  Returns the byte size / fills the workspace. */
+long long gridmm_pool_ws_bytes(int batch, int feat_dim, int num_ctas);
+int gridmm_pool_plan(const int* cell_start, int n_cells, int batch, int feat_dim, int num_ctas, void* pool_ws, cudaStream_t stream);
 
 /* ---- stage 3: cross-modal encoder blocks ------------------------------------------------------------------
  * nn.Linear on tcgen05: out = act(a[M,K] . w[N,K]^T + bias) + residual; fp16 operands, fp32 accumulate.
@@ -327,7 +337,9 @@ void gridmm_debug_set_pool_counters(long long* dbg);
 void gridmm_debug_set_attn_legacy(int on);    /* gridmm_attention_f16: 1 forces the mma.sync kernel, 2 the tcgen05 one, 0 by shape */
 void gridmm_debug_set_ln_cluster(int cl);     /* force the cluster size (2 / 6) of gridmm_linear_ln_f16; 0 = automatic */
 void gridmm_debug_set_gemm_pairs(int on);    /* 0: disable the cta_group::2 GEMM path (A/B timing) */
-void gridmm_debug_set_pool_hmma(int on);     /* gridmm_pool's weighted-sum stage: 1 (default) mma.sync from the resident tile, 0 tcgen05 (measured slower) */
+void gridmm_debug_set_pool_trace(long long* t);   /* gridmm_pool: [4][64][8] clock64 stamps of the first tiles' stage hand-overs (CTAs 0..3) */
+void gridmm_debug_set_pool_exp(int e);        /* gridmm_pool timing experiments (1: half rows, 2: L2-resident rows); results are garbage when != 0 */
+void gridmm_debug_set_pool_plan(int episode_cost, int snap);   /* gridmm_pool_plan: rows an episode start costs, snap distance of a cut (< 0 keeps) */
 void gridmm_debug_set_pool_split(int on);    /* gridmm_pool (mma.sync sums): 0 = single fp16 softmax weights, 1 = value + residual */
 void gridmm_debug_set_gemm_384(int on);      /* 1: enable the 256 x 384 pair tiles of gridmm_linear_f16 (off by default: measured slower) */
 

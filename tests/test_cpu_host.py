@@ -20,7 +20,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for n in names:
         assert hasattr(lib, n), "include/gridmm_b200.h declares %s but the library does not export it" % n
     assert set(_lib._SIGS) <= set(names)
-    assert _lib.load().gridmm_abi_version() == 3
+    assert _lib.load().gridmm_abi_version() == 4
 
 
 def test_param_spec_matches_reference_layout():
@@ -261,7 +261,7 @@ def test_pretrain_sap_heads_glue_masks_and_candidates(monkeypatch):
 def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
     """Host logic without a GPU: every `ops.*` kernel wrapper is replaced by a recorder, the model lives on the CPU, and the
     Python glue of forward('navigation'), its intermediates path and forward_pretrain (both tasks) must run to the end with
-    consistent shapes.  Pins the launch budget of the navigation step: 58 kernel launches at one launch per wrapper call."""
+    consistent shapes.  Pins the launch budget of the navigation step: 59 kernel launches at one launch per wrapper call."""
     from gridmm_b200.model import GlocalTextPathNavCMT
     calls = _stub_ops(monkeypatch)
     ep_kw, nav_kw, model_kw = H.NAV_CASES["r2r_small"]
@@ -273,14 +273,16 @@ def test_host_glue_launch_sequence_with_stubbed_kernels(monkeypatch):
     B, G, V = ep_kw["batch"], nav_kw["gmap_len"], 1 + nav_kw["n_views"]
     assert out["fused_logits"].shape == (B, G) and out["local_logits"].shape == (B, V) and out["obj_logits"] is None
     assert out["gmap_embeds"].shape == (B, G, 768) and out["vp_embeds"].shape == (B, V, 768)
-    # cell_sort (list path only) + the 58 launches after the grid build = the 59-launch step of bench.py, where grid_update replaces
-    # cell_sort (+ one gridmm_copy_segments staging launch there); gridmm_map_index is the launch the packed map sequence adds
-    assert calls.count("cell_sort") == 1 and len(calls) == 59, (len(calls), calls)
+    # cell_sort (list path only) + the 59 launches after the grid build = the 60-launch step of bench.py, where grid_update replaces
+    # cell_sort (+ one gridmm_copy_segments staging launch there); gridmm_map_index is the launch the packed map sequence adds,
+    # gridmm_pool_plan the one the pooling kernel's work plan adds (behind the grid update, beside the text branch)
+    assert calls.count("cell_sort") == 1 and len(calls) == 60, (len(calls), calls)
+    assert calls.count("pool_plan") == 1
     assert calls.count("map_index") == 1 and calls.count("map_inputs_packed") == 1 and calls.count("attention_ragged") == 3
     model.ragged_map = False                    # the padded layout (used for map sequences longer than 320 rows) stays available
     calls.clear()
     model("navigation", nav)
-    assert len(calls) == 58 and calls.count("map_inputs") == 1 and "map_index" not in calls
+    assert len(calls) == 59 and calls.count("map_inputs") == 1 and "map_index" not in calls
     model.ragged_map = True
     assert calls.count("linear_ln") == 17 and calls.count("pool") == 1 and calls.count("cls_heads") == 1
     calls.clear()

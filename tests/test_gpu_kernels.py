@@ -302,14 +302,6 @@ def test_grid_update_ce_geometry():
             assert np.array_equal(per_step[t][b].astype(np.int32), cells[b][t]), "b=%d t=%d" % (b, t)
 
 
-def _pool_mode(hmma):
-    import ctypes
-    from gridmm_b200 import _lib
-    lib = _lib.load()
-    lib.gridmm_debug_set_pool_hmma.argtypes = [ctypes.c_int]
-    lib.gridmm_debug_set_pool_hmma(int(hmma))
-
-
 def _oracle_pool(fts, cell, tp16, n_cells=196):
     """float64 statement of vilmodel.py:797-807 in feature space, with the SAME fp16-rounded text_fts the kernel sees."""
     x = torch.from_numpy(np.ascontiguousarray(fts)).double()
@@ -326,13 +318,12 @@ def _oracle_pool(fts, cell, tp16, n_cells=196):
 @pytest.mark.parametrize("B,T,L,D,gw", [(3, 2, 80, 768, 14), (8, 8, 80, 768, 14), (2, 15, 40, 768, 14), (1, 1, 16, 512, 8), (37, 3, 24, 768, 14),
                                         (3, 2, 128, 768, 14), (3, 2, 129, 768, 14), (3, 3, 136, 768, 14), (5, 4, 200, 768, 14),
                                         (2, 8, 250, 768, 14), (2, 2, 256, 768, 14), (2, 2, 200, 512, 8)])
-@pytest.mark.parametrize("hmma", [0, 1], ids=["tcgen05_sums", "mma_sync_sums"])
-def test_pool_vs_oracle(B, T, L, D, gw, hmma):
+@pytest.mark.parametrize("ctas", [0, 13], ids=["cta_per_sm", "13_ctas"])
+def test_pool_vs_oracle(B, T, L, D, gw, ctas):
     """L > 128 (the reference's --max_instr_len 200 / 250, vilmodel.py:798 takes the max over ALL positions): two passes of the
-    kernel, the first over positions 128.. only produces row maxima.  hmma: the weighted-sum stage on warp-level mma.sync (default)
-    or on tcgen05 (debug hook)."""
+    kernel, the first over positions 128.. only produces row maxima.  ctas: the work plan cuts the sorted rows into one range per
+    CTA; with one CTA per SM on these small batches nearly every cell is pooled in pieces by several CTAs and merged."""
     from gridmm_b200 import ops
-    _pool_mode(hmma)
     ep = synth.make_episodes(B, T, seed=B * 100 + T, dim=D)
     cells, fts, halfs, pos = H.oracle_grid(ep, grid_w=gw)
     gb, grid, _ = _run_builder(ep, grid_w=gw)
@@ -341,12 +332,9 @@ def test_pool_vs_oracle(B, T, L, D, gw, hmma):
     tp = (torch.randn(B, L, D, generator=g) * 0.55).half()
     pooled = torch.zeros(B * nc, D, device=_dev(), dtype=torch.float16)
     w_out = torch.zeros(B, grid.cap, device=_dev())
-    try:
-        ops.pool(grid.slab, D, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
-                 grid.cell_start, grid.cell_rank, nc, tp.to(_dev()).view(B * L, D), L, B, pooled, w_out=w_out)
-        torch.cuda.synchronize()
-    finally:
-        _pool_mode(1)
+    ops.pool(grid.slab, D, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
+             grid.cell_start, grid.cell_rank, nc, tp.to(_dev()).view(B * L, D), L, B, pooled, w_out=w_out, num_ctas=ctas)
+    torch.cuda.synchronize()
     pooled = pooled.view(B, nc, D).float().cpu(); w_out = w_out.cpu()
     perm = grid.perm.cpu().numpy(); cr = grid.cell_rank.cpu().numpy(); cs = grid.cell_start.cpu().numpy()
     for b in range(B):
@@ -360,11 +348,13 @@ def test_pool_vs_oracle(B, T, L, D, gw, hmma):
                 assert err < 6e-3, "b=%d cell=%d err=%.3e" % (b, c, err)   # fp16 output (ulp 4e-3 at |x|~4) + exp rounding
 
 
-@pytest.mark.parametrize("hmma", [0, 1], ids=["tcgen05_sums", "mma_sync_sums"])
+@pytest.mark.parametrize("ctas", [0, 3, 40, 300], ids=["cta_per_sm", "3_ctas", "40_ctas", "300_ctas"])
 @pytest.mark.parametrize("sizes", ["tiny", "mixed", "one_big"])
-def test_pool_handmade_cells(sizes, hmma):
+def test_pool_handmade_cells(sizes, ctas):
     """gridmm_pool on a hand-made layout (no grid builder): tiny cells (> 8 cells per 32-row tile -> several passes of the
-    8-slot HMMA pooling), a cell spanning many tiles, an episode without any valid point, ragged text length."""
+    8-slot HMMA pooling), a cell spanning many tiles (and, cut by the work plan, many CTAs: the pieces are merged by the last one
+    to arrive -- 300 CTAs are more than the SMs hold at once, so no piece may wait for another), an episode without any valid
+    point, ragged text length."""
     from gridmm_b200 import ops
     rng = np.random.default_rng({"tiny": 1, "mixed": 2, "one_big": 3}[sizes])
     B, nc, D, L, t_cap = 3, 196, 768, 37, 2
@@ -402,13 +392,15 @@ def test_pool_handmade_cells(sizes, hmma):
     dev = _dev()
     pooled = torch.zeros(B * nc, D, device=dev, dtype=torch.float16)
     w_out = torch.zeros(B, cap, device=dev)
-    _pool_mode(hmma)
-    try:
-        ops.pool(slab.to(dev), D, slots.to(dev), t_cap, 588, 49, 0, perm.to(dev), cap, cell_start.to(dev), cell_rank.to(dev), nc,
-                 tp.to(dev).view(B * L, D), L, B, pooled, w_out=w_out)
-        torch.cuda.synchronize()
-    finally:
-        _pool_mode(1)
+    ops.pool(slab.to(dev), D, slots.to(dev), t_cap, 588, 49, 0, perm.to(dev), cap, cell_start.to(dev), cell_rank.to(dev), nc,
+             tp.to(dev).view(B * L, D), L, B, pooled, w_out=w_out, num_ctas=ctas)
+    torch.cuda.synchronize()
+    # a second launch on the same workspace (the arrival counters must be back at zero) gives the same bits
+    again = torch.zeros_like(pooled)
+    ops.pool(slab.to(dev), D, slots.to(dev), t_cap, 588, 49, 0, perm.to(dev), cap, cell_start.to(dev), cell_rank.to(dev), nc,
+             tp.to(dev).view(B * L, D), L, B, again, num_ctas=ctas)
+    torch.cuda.synchronize()
+    assert torch.equal(again, pooled)
     pooled = pooled.view(B, nc, D).float().cpu()
     for b in range(B):
         x_b = slab[b * cap:(b + 1) * cap].double()
@@ -419,6 +411,55 @@ def test_pool_handmade_cells(sizes, hmma):
             err = (pooled[b, int(cell_rank[b, c])].double() - ref).abs().max().item()
             assert err < 6e-3, "b=%d cell=%d n=%d err=%.3e" % (b, c, len(idx), err)
     assert pooled[1].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("ctas", [0, 7, 300])
+def test_pool_plan_invariants(ctas):
+    """gridmm_pool_plan: the ranges tile the sorted valid rows in order, a cut is either on a cell boundary or further than the
+    snap distance from both neighbours, and the chain records of a cut cell name exactly the CTAs that hold a piece of it."""
+    from gridmm_b200 import ops, _lib
+    rng = np.random.default_rng(5)
+    B, nc = 5, 196
+    counts = rng.integers(0, 60, (B, nc)); counts[2] = 0; counts[3, 50] = 2500; counts[4, :] = 0; counts[4, 9] = 4000
+    cs = np.zeros((B, nc + 1), dtype=np.int32); cs[:, 1:] = np.cumsum(counts, 1)
+    dev = _dev()
+    ws = ops.pool_plan(torch.from_numpy(cs).to(dev), nc, B, 768, num_ctas=ctas)
+    torch.cuda.synchronize()
+    G = ctas or torch.cuda.get_device_properties(dev).multi_processor_count
+    w = ws.cpu().numpy().view(np.int32)
+    rec = w[:G * 8].reshape(G, 8); vb = w[G * 8:G * 8 + B + 1]; cnt = w[G * 8 + B + 1:G * 8 + B + 1 + G]
+    assert np.array_equal(vb, np.concatenate([[0], np.cumsum(cs[:, -1])])) and not cnt.any()
+    g0, g1 = rec[:, 0], rec[:, 1]
+    assert g0[0] == 0 and g1[-1] == vb[-1] and np.array_equal(g0[1:], g1[:-1]) and (g1 >= g0).all()
+    bounds = np.unique(np.concatenate([vb[b] + cs[b] for b in range(B)]))
+    def cell_of(row):      # [lo, hi) of the cell that holds global row `row`
+        i = np.searchsorted(bounds, row, side="right")
+        return int(bounds[i - 1]), int(bounds[i])
+    for c in range(G):
+        first, last, n, tlast, tn, fl = rec[c, 2], rec[c, 3], rec[c, 4], rec[c, 5], rec[c, 6], rec[c, 7]
+        if g1[c] == g0[c]:
+            assert fl == 0
+            continue
+        head = g0[c] not in bounds
+        tail = g1[c] not in bounds
+        if head:
+            lo, hi = cell_of(g0[c])
+            assert min(g0[c] - lo, hi - g0[c]) > 16      # closer than the snap distance: the cut would sit on the boundary
+            pieces = [k for k in range(G) if g1[k] > g0[k] and g0[k] < hi and g1[k] > lo]
+            assert (fl & 1) and first == pieces[0] and last == pieces[-1] and n == len(pieces)
+        else:
+            assert not (fl & 1)
+        if tail:
+            lo, hi = cell_of(g1[c] - 1)
+            if head and cell_of(g0[c]) == (lo, hi):
+                assert fl & 4 and not (fl & 2)
+            else:
+                pieces = [k for k in range(G) if g1[k] > g0[k] and g0[k] < hi and g1[k] > lo]
+                assert (fl & 2) and pieces[0] == c and tlast == pieces[-1] and tn == len(pieces)
+        else:
+            assert not (fl & 6)
+
+
 
 
 

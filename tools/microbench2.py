@@ -139,10 +139,6 @@ if "ln" in want:
         print("LN rows=%5d: %6.1f us  (%.0f GB/s of 10 B/elt)" % (rows, us, rows * 768 * 10 / us / 1e3), flush=True)
 
 if "pool" in want:
-    if os.environ.get("GRIDMM_POOL_HMMA") == "0":       # A/B: the weighted-sum stage on tcgen05 (opt-in; measured slower)
-        lib.gridmm_debug_set_pool_hmma.argtypes = [ctypes.c_int]
-        lib.gridmm_debug_set_pool_hmma(0)
-        print("pool: weighted sums on tcgen05 (debug hook)")
     if os.environ.get("GRIDMM_POOL_SPLIT") in ("0", "1"):
         lib.gridmm_debug_set_pool_split.argtypes = [ctypes.c_int]
         lib.gridmm_debug_set_pool_split(int(os.environ["GRIDMM_POOL_SPLIT"]))
@@ -156,8 +152,10 @@ if "pool" in want:
     ref_pooled = m.buf("pooled16", (B * 196, 768), torch.float16, zero=True).clone()
     pooled = m.buf("pooled16", (B * 196, 768), torch.float16, zero=True)
     text_ws = ops.pool_text_ws(dev, B, 768)          # filled by the step above (text_proj epilogue)
+    plan_ws = ops.pool_plan(grid.cell_start, 196, B, 768)      # the step runs it behind the grid update, off the critical path
     fn = lambda: ops.pool(grid.slab, 768, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
-                          grid.cell_start, grid.cell_rank, 196, None, 80, B, pooled, text_ws=text_ws, text_ws_ready=True)
+                          grid.cell_start, grid.cell_rank, 196, None, 80, B, pooled, text_ws=text_ws, text_ws_ready=True,
+                          pool_ws_buf=plan_ws, plan_ready=True)
     fn(); torch.cuda.synchronize()
     print("pool: re-run equals the step's result:", bool(torch.equal(pooled, ref_pooled)))
     nv = int(grid.cell_start[:, -1].sum().item())
