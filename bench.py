@@ -415,6 +415,37 @@ def kernel_breakdown(step, n=5):
     return {k: (t / n, c / n) for k, (t, c) in agg.items()}
 
 
+def pool_launch_ms(step, n=10, reps=3):
+    """Duration of ONE gridmm_pool launch on the step's own state: `n` launches back to back on the launch stream between two
+    CUDA events (the per-launch event pairs of kernel_breakdown add the launch gap of an isolated kernel, 3-5 us on a ~55 us
+    kernel).  Every launch streams the batch's 208 MB of features again -- more than the 126 MB L2 holds, so each launch reads
+    them from HBM like the launch inside a step does -- while the text operand and the cell tables stay L2-resident, as they are
+    in the step (the text_proj GEMM and gridmm_grid_update wrote them just before).  The work plan (gridmm_pool_plan) is not
+    part of it: in the step it runs behind the grid update, beside the text branch."""
+    from gridmm_b200 import ops
+    from gridmm_b200.env import GridBatch
+    m = step.model
+    grid = GridBatch(step.builder)
+    pooled = torch.empty(B * 196, 768, dtype=torch.float16, device=step.dev)
+    text_ws = ops.pool_text_ws(step.dev, B, 768, L)
+    plan_ws = ops.pool_plan(grid.cell_start, 196, B, 768)
+    fn = lambda: ops.pool(grid.slab, 768, grid.slots, grid.t_cap, grid.slot_rows, grid.view_rows, grid.tok_off, grid.perm, grid.cap,
+                          grid.cell_start, grid.cell_rank, 196, None, L, B, pooled, text_ws=text_ws, text_ws_ready=True,
+                          pool_ws_buf=plan_ws, plan_ready=True)
+    fn(); torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(2_000_000)          # the host queues all n launches behind a ~1 ms spin
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record(); torch.cuda.synchronize()
+        t = s.elapsed_time(e) / n
+        best = t if best is None else min(best, t)
+    return best
+
+
 def gemm_flops_per_step(kv_rows=None, map_rows=None):
     """Algorithmic FLOPs (2mnk) of every tcgen05 GEMM launch of one step (padded shapes as launched: S = 196 + G; the fusion
     encoder's K/V projection over the `kv_rows` packed context rows it actually processes).  map_rows: count the map-sized GEMMs
@@ -574,6 +605,7 @@ def main():
                     "map_rows_processed": map_rows, "padded_map_rows": B * S_}
         # the HBM-bound pooling kernel (north_star's "grid scatter/pool"): bytes that must move / its duration
         p_ms, _ = br.get("gridmm_pool", (0.0, 0))
+        p_ms_b2b = pool_launch_ms(step) if (L <= 128 and not CE) else None
         gridb = step.builder
         nv = int(gridb.cell_start[:, -1].sum().item()); ne = int(gridb.n_nonempty.sum().item())
         pbytes = nv * 768 * 2 + B * L * 768 * 2 + ne * 768 * 2 + nv * 4
@@ -581,7 +613,11 @@ def main():
         roofline_pool = {"kernel": "pool_kernel<768> (gridmm_pool)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic.get("pool_bytes_per_launch"),
                          "algorithmic_bytes": pbytes,
-                         "valid_rows": nv, "ms": p_ms, "peak_source": peak_src}
+                         "valid_rows": nv, "ms": p_ms, "peak_source": peak_src,
+                         "timing": "CUDA events around the launch inside the instrumented step (mean of 5 steps)",
+                         "ms_back_to_back": p_ms_b2b,
+                         "back_to_back": "10 launches of the same kernel on the step's state between two CUDA events, per launch (features "
+                                         "re-read from HBM by every launch: 208 MB > L2; includes the launch gaps between them)"}
         cpu = None
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -29,6 +29,8 @@ _SIGS = {
     "gridmm_pool": [c_void_p, c_longlong, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                     c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "gridmm_pool_plan": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "gridmm_gmap_update": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "gridmm_gmap_gather": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "gridmm_linear_ln_f16": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                              c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
     "gridmm_head_rows": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libgridmm_b200.so"
-SOURCES = ["host_util.cu", "grid.cu", "pool.cu", "gemm_tc.cu", "gemm_ln.cu", "attn.cu", "attn_tc.cu", "rowops.cu", "heads.cu", "optim.cu", "train.cu"]
+SOURCES = ["host_util.cu", "grid.cu", "pool.cu", "gemm_tc.cu", "gemm_ln.cu", "attn.cu", "attn_tc.cu", "rowops.cu", "heads.cu", "optim.cu", "train.cu", "graph.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177",

@@ -3,25 +3,29 @@
 //   for i in range(196): softmax over the points of cell i, weighted sum   vilmodel.py:801-807
 // as ONE persistent kernel that reads every valid patch-feature row from HBM exactly once.
 //
+//   * pool_plan_kernel (one small launch, off the critical path: it only needs the sorted cells) cuts the batch's sorted valid
+//     rows into one contiguous range per CTA, equal in cost (a row = 1, an episode switch = POOL_EPISODE_COST).  A cut may fall
+//     inside a large cell: such a cell is pooled in pieces, each piece leaves (max, weight sum, fp32 sums) in a workspace and the
+//     last piece to arrive merges them in CTA order, per 128-column slice (no atomics on data, deterministic result);
 //   * rows are streamed in cell-sorted order (gridmm_grid_update produced `perm`), 32 rows per tile, through a ring of
-//     four 48 KB shared-memory tiles.  Four producer warps resolve the tile's slab rows (perm -> slot -> row) and fetch
-//     them with TMA tile::gather4 (cp.async.bulk.tensor.2d...tile::gather4: four arbitrary rows x 64 fp16 columns per
-//     instruction, hardware SWIZZLE_128B, completion on an mbarrier) straight into a K-major operand tile (D/64 chunks
-//     of 32 x 128 B).  Row indices are made warp-uniform with shuffles and one elected lane issues the copies back to back
-//     (elect_one(), common.cuh: per-lane operands cost a ~100-cycle R2UR waterfall per gather4);
+//     four 48 KB shared-memory tiles.  Four producer warps resolve the tile's slab rows (perm entry requested two tiles ahead,
+//     the episode's slot table in registers) and fetch them with TMA tile::gather4 (cp.async.bulk.tensor.2d...tile::gather4:
+//     four arbitrary rows x 64 fp16 columns per instruction, hardware SWIZZLE_128B, completion on an mbarrier) straight into a
+//     K-major operand tile (D/64 chunks of 32 x 128 B).  Row indices are made warp-uniform with shuffles and one elected lane
+//     issues the copies back to back (elect_one(), common.cuh: per-lane operands cost a ~100-cycle R2UR waterfall per gather4);
 //   * relevance  S^T[L, 32] = text_fts[L, D] . X_tile^T  on tcgen05 with the A operand (text_fts of the current
-//     episode, up to 128 positions) held in TENSOR MEMORY for the whole episode (tcgen05.st by 8 warps, software
-//     pipelined), B operand = the feature tile in shared memory, one TMEM accumulator per ring slot;
-//     w = max over ALL text positions (padding included -- vilmodel.py:798) = max over TMEM lanes, taken with a
-//     warp butterfly (31 shuffles per thread) by the reducer warps whose lane quadrant holds real text positions, merged
-//     across quadrants through shared memory + an mbarrier by the reducer warp that owns the padding quadrant;
-//   * that warp also turns w into per-cell softmax numerators exp(w - cell max) (binary search of the row's cell,
-//     match.any + redux.max inside the warp, running max carried across tiles) and publishes each row's compact cell rank;
+//     episode, up to 128 positions) held in TENSOR MEMORY for the whole episode (tcgen05.st by 8 warps, 12-16 loads in flight
+//     per thread), B operand = the feature tile in shared memory, one TMEM accumulator per ring slot;
+//     w = max over ALL text positions (padding included -- vilmodel.py:798) = max over TMEM lanes, taken with
+//     redux.sync.max.f32 (32 independent warp-wide maxima) by the reducer warps whose lane quadrant holds real text positions,
+//     merged across quadrants through shared memory + an mbarrier by the reducer warp that owns the padding quadrant;
+//   * that warp also turns w into per-cell softmax numerators exp(w - cell max) (binary search of the row's cell ahead of the
+//     relevance wait, match.any + redux.max inside the warp, running max carried across tiles);
+//   * a builder warp turns the numerators into the mma.sync B fragments of the pooling warps, keeps the running weight sum of
+//     the open cells and publishes which cells complete and their normalisers (once, instead of once per pooling warp);
 //   * weighted sums as warp-level HMMA from the resident tile: out[cell, :] = sum_r p[r] x[r, :] is the product
 //     X^T[D, 32 rows] . W[32 rows, 8 cell slots] (slot = rank & 7; an open cell keeps its slot across tiles), A through
-//     ldmatrix.trans, weights as fp16 value + fp16 residual (two MMAs), fp32 accumulators in registers across tiles,
-//     rescaled when a later tile raises the open cell's max.  CTA ranges are cut at cell boundaries, so no atomics and no
-//     cross-CTA merge exist and the result is deterministic;
+//     ldmatrix.trans, fp32 accumulators in registers across tiles, rescaled when a later tile raises the open cell's max;
 //   * grid_proj is applied AFTER pooling by the GEMM kernel (sum_j p_j (W x_j + b) = W (sum_j p_j x_j) + b), so this
 //     kernel emits the pooled raw feature per non-empty cell, compacted in ascending cell order (the order
 //     vilmodel.py:819 gathers them in), as fp16 GEMM input.
@@ -90,7 +94,7 @@ struct PoolParams {
     int slot_rows, view_rows, tok_off;   // row = slot*slot_rows + view*view_rows + tok_off + patch
     long long* dbg;          // optional [grid][16] cycle counters (tools/microbench2.py), null in production
     long long* trace;        // optional [4 CTAs][64 tiles][8] clock64 stamps of the first tiles' stage hand-overs (tools/pool_probe.py)
-    int exp;                 // timing experiments (tools/pool_probe.py; results are garbage): 1 = fetch half of every row, 2 = always the same 32 rows (L2 hits)
+    int exp;                 // timing experiments (tools/pool_probe.py; results are garbage): 1 = fetch half of every row, 2 = always the same 32 rows (L2 hits), 3 / 4 = half / a twelfth of the relevance contraction
 };
 
 struct Tile {
@@ -240,8 +244,8 @@ __device__ __forceinline__ void stage_text(const uint4* ws_b, int tlane, int l_p
 }
 
 // ---------------------------------------------------------------------------------------------------- work plan
-// One CTA of 1024 threads: prefix of the valid-row counts, the G + 1 cuts (warp per cut: every lane loads a slice of the
-// episode's cell_start row, one round trip), then per CTA the chains of its first / last cell (see PoolPlanCta).
+// One CTA of 1024 threads: prefix of the valid-row counts, the G + 1 cuts (four lanes per cut, each loads a quarter of the
+// episode's cell_start row), then per CTA the chains of its first / last cell (see PoolPlanCta).
 __global__ void __launch_bounds__(1024) pool_plan_kernel(const int* __restrict__ cell_start, int n_cells, int batch, int G,
                                                          int episode_cost, int snap, int* __restrict__ ws) {
     __shared__ int s_vb[POOL_MAX_BATCH + 1];
@@ -268,33 +272,39 @@ __global__ void __launch_bounds__(1024) pool_plan_kernel(const int* __restrict__
     __syncthreads();
     const int total = s_vb[batch];
     const long long total_c = static_cast<long long>(total) + static_cast<long long>(batch) * episode_cost;
-    for (int c = warp; c <= G; c += 32) {
+    // Four lanes per cut (256 cuts per pass of the block): every lane requests its quarter of the episode's cell_start row at once,
+    // so a pass costs ONE round trip to L2 (a warp per cut took five dependent passes for 149 cuts, ~10 us in the step).
+    for (int c0 = 0; c0 <= G; c0 += 256) {
+        const int c = c0 + (tid >> 2), sub = tid & 3;
         // cut c in COST units: one per valid row plus `episode_cost` per episode start (moving a new text operand into tensor
         // memory and the partial tiles around an episode switch), so a CTA whose range crosses an episode boundary gets fewer rows
-        const long long tgt = (static_cast<long long>(c) * total_c) / G;
+        const long long tgt = (static_cast<long long>(min(c, G)) * total_c) / G;
+        const bool interior = c < G && tgt > 0;
+        int lo = 0, hi = batch;            // largest b with vbase[b] + b * COST <= tgt
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (static_cast<long long>(s_vb[mid]) + static_cast<long long>(mid) * episode_cost <= tgt) lo = mid; else hi = mid;
+        }
+        const int nv = s_vb[lo + 1] - s_vb[lo];
+        const long long lc = tgt - s_vb[lo] - static_cast<long long>(lo) * episode_cost - episode_cost;
+        const int local = lc <= 0 ? 0 : (lc >= nv ? nv : static_cast<int>(lc));
+        const int* cs = cell_start + lo * (n_cells + 1);
+        int lb = 0, ub = nv;               // cell boundaries around the cut: lb = largest <= local, ub = smallest > local
+        if (interior) {
+            for (int i = sub; i <= n_cells; i += 4) {
+                const int v = __ldg(cs + i);
+                if (v <= local) lb = max(lb, v); else ub = min(ub, v);
+            }
+        }
+#pragma unroll
+        for (int o = 2; o > 0; o >>= 1) {
+            lb = max(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+            ub = min(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+        }
         int g, clo = -1, chi = -1;
         if (c >= G) g = total;
         else if (tgt <= 0) g = 0;
         else {
-            int lo = 0, hi = batch;        // largest b with vbase[b] + b * COST <= tgt
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (static_cast<long long>(s_vb[mid]) + static_cast<long long>(mid) * episode_cost <= tgt) lo = mid; else hi = mid;
-            }
-            const int nv = s_vb[lo + 1] - s_vb[lo];
-            const long long lc = tgt - s_vb[lo] - static_cast<long long>(lo) * episode_cost - episode_cost;
-            const int local = lc <= 0 ? 0 : (lc >= nv ? nv : static_cast<int>(lc));
-            const int* cs = cell_start + lo * (n_cells + 1);
-            int lb = 0, ub = nv;           // cell boundaries around the cut: lb = largest <= local, ub = smallest > local
-            for (int i = lane; i <= n_cells; i += 32) {
-                const int v = cs[i];
-                if (v <= local) lb = max(lb, v); else ub = min(ub, v);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lb = max(lb, __shfl_xor_sync(0xffffffffu, lb, o));
-                ub = min(ub, __shfl_xor_sync(0xffffffffu, ub, o));
-            }
             int cut = local;
             if (local >= nv) cut = nv;
             else if (local - lb <= snap && local - lb <= ub - local) cut = lb;
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__(1024) pool_plan_kernel(const int* __restrict__
             if (cut > lb && cut < ub) { clo = s_vb[lo] + lb; chi = s_vb[lo] + ub; }      // mid-cell: the cell is rows [clo, chi)
             g = s_vb[lo] + cut;
         }
-        if (lane == 0) { s_g[c] = g; s_clo[c] = clo; s_chi[c] = chi; }
+        if (sub == 0 && c <= G) { s_g[c] = g; s_clo[c] = clo; s_chi[c] = chi; }
     }
     __syncthreads();
     int* vb_out = ws + G * 8;
@@ -580,8 +590,9 @@ pool_kernel(const __grid_constant__ CUtensorMap tm_fts, PoolParams p) {
                     // unrolled loop moved 48 operand addresses from vector to uniform registers, ~20 cycles per instruction
                     uint64_t db = umma_desc_sw128_kmajor(tile_s);
                     uint32_t ta = tmem_base;
+                    const int kend = p.exp == 3 ? CH / 2 : (p.exp == 4 ? 1 : CH);      // (timing experiments: half / a twelfth of the contraction)
 #pragma unroll 1
-                    for (int k = 0; k < CH; ++k) {
+                    for (int k = 0; k < kend; ++k) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)   // K = 16 per instruction = 8 TMEM columns of A, 32 bytes of B
                             umma_f16_ts(d_tmem, ta + kk * 8, db + 2 * kk, idesc, (k | kk) ? 1u : 0u);

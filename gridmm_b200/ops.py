@@ -404,6 +404,27 @@ def pool(fts, feat_dim, slots, t_cap, slot_rows, view_rows, tok_off, perm, cap, 
               pool_ws_buf.data_ptr(), int(bool(plan_ready)), num_ctas, _lib.stream_ptr())
 
 
+def gmap_update(pano_embeds, pano_masks, cur_slot, cand_slot, node_sum, node_cnt):
+    """pano_embeds f32 [B, V, D], pano_masks u8/bool [B, V], cur_slot i32 [B], cand_slot i32 [B, V], node_sum f32 [B, N, D], node_cnt f32 [B, N]."""
+    _chk(pano_embeds, torch.float32, "pano_embeds"); _chk(cur_slot, torch.int32, "cur_slot"); _chk(cand_slot, torch.int32, "cand_slot")
+    _chk(node_sum, torch.float32, "node_sum"); _chk(node_cnt, torch.float32, "node_cnt")
+    if pano_masks.dtype == torch.bool:
+        pano_masks = pano_masks.view(torch.uint8)
+    _chk(pano_masks, torch.uint8, "pano_masks")
+    B, V, D = pano_embeds.shape
+    _lib.call("gridmm_gmap_update", pano_embeds.data_ptr(), pano_masks.data_ptr(), V, D, cur_slot.data_ptr(), cand_slot.data_ptr(),
+              node_sum.data_ptr(), node_cnt.data_ptr(), node_sum.shape[1], B, _lib.stream_ptr())
+
+
+def gmap_gather(node_sum, node_cnt, slots, out):
+    """slots i32 [B, G] -> out f32 [B, G, D] = sum / count (zero rows for slots < 0)."""
+    _chk(node_sum, torch.float32, "node_sum"); _chk(node_cnt, torch.float32, "node_cnt"); _chk(slots, torch.int32, "slots")
+    _chk(out, torch.float32, "out")
+    B, N, D = node_sum.shape
+    _lib.call("gridmm_gmap_gather", node_sum.data_ptr(), node_cnt.data_ptr(), N, D, slots.data_ptr(), slots.shape[1], B, out.data_ptr(),
+              _lib.stream_ptr())
+
+
 def cell_sort(batch, cell, n_pts, grid_w, cap, perm, cell_start, cell_rank, n_nonempty):
     _chk(cell, torch.int16, "cell"); _chk(n_pts, torch.int32, "n_pts")
     _lib.call("gridmm_cell_sort", batch, cell.data_ptr(), n_pts.data_ptr(), grid_w, cap, perm.data_ptr(), cell_start.data_ptr(),

@@ -105,6 +105,19 @@ int gridmm_pool(const void* fts, long long fts_rows, int feat_dim, const int* sl
 long long gridmm_pool_ws_bytes(int batch, int feat_dim, int num_ctas);
 int gridmm_pool_plan(const int* cell_start, int n_cells, int batch, int feat_dim, int num_ctas, void* pool_ws, cudaStream_t stream);
 
+/* ---- caller side of the step: node embeddings of the episodes' topological maps ------------------------
+ * Replaces GraphMap.update_node_embed / get_node_embed (map_nav_src/models/graph_utils.py:114-125) and the per-episode loops
+ * around them (map_nav_src/r2r/agent.py:306-320, 126-129): sums [batch, n_nodes, dim] and counts [batch, n_nodes] stay on the
+ * device (zero-initialised by the caller at the start of an episode batch), the host keeps the viewpoint -> slot maps.
+ *   gridmm_gmap_update: avg = masked mean of pano_embeds[b] over its n_views tokens; node cur_slot[b] = (avg, 1) (rewrite);
+ *                       for every token j with cand_slot[b, j] >= 0: node cand_slot[b, j] += (pano_embeds[b, j], 1), in token
+ *                       order.  cur_slot[b] < 0: the episode has ended, nothing changes.
+ *   gridmm_gmap_gather: out[b, g] = sum / count of node slots[b, g], or a zero row for slots[b, g] < 0 (stop node, padding). */
+int gridmm_gmap_update(const float* pano_embeds, const unsigned char* pano_masks, int n_views, int dim, const int* cur_slot,
+                       const int* cand_slot, float* node_sum, float* node_cnt, int n_nodes, int batch, cudaStream_t stream);
+int gridmm_gmap_gather(const float* node_sum, const float* node_cnt, int n_nodes, int dim, const int* slots, int gmap_len,
+                       int batch, float* out, cudaStream_t stream);
+
 /* ---- stage 3: cross-modal encoder blocks ------------------------------------------------------------------
  * nn.Linear on tcgen05: out = act(a[M,K] . w[N,K]^T + bias) + residual; fp16 operands, fp32 accumulate.
  * Replaces every nn.Linear of vilmodel.py:95-209, 317-379, 663-674, 702-703 and transformer.py:133-182.
