@@ -688,15 +688,19 @@ struct FusionPackedParams {
     const float* v_feat; int v_kin; const float* v_w; const float* v_bias; const float* v_gamma; const float* v_beta; const float* v_base;
 };
 
-__global__ void __launch_bounds__(256) fusion_inputs_packed_kernel(FusionPackedParams p) {
+__global__ void __launch_bounds__(256, 4) fusion_inputs_packed_kernel(FusionPackedParams p) {
     pdl_wait();
     const int Q = p.G + p.V;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= p.kv_rows_max + p.B * Q) return;
+    // warp per output row; the grid is ordered [vp tokens | gmap tokens | context rows]: the vp rows (a 768 x K linear + LayerNorm
+    // each) are the expensive ones and must not be the tail of the launch (as its last blocks they ran alone, one block per SM)
+    const int wrow = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wrow >= p.kv_rows_max + p.B * Q) return;
+    const int row = wrow < p.B * p.V ? p.kv_rows_max + p.B * p.G + wrow
+                                     : (wrow < p.B * Q ? p.kv_rows_max + (wrow - p.B * p.V) : wrow - p.B * Q);
     float4 v[HV];
     if (row < p.kv_rows_max) {
-        if (row >= p.kv_off[p.B]) return;
-        const int src = p.kv_src[row];
+        const int n_kv = p.kv_off[p.B], src = p.kv_src[row];      // both requested at once (kv_src has kv_rows_max entries)
+        if (row >= n_kv) return;
         const float* sp = (src >= 0) ? p.map32 + static_cast<size_t>(src) * HID : p.txt32 + static_cast<size_t>(-1 - src) * HID;
 #pragma unroll
         for (int i = 0; i < HV; ++i) v[i] = *reinterpret_cast<const float4*>(sp + (i * 32 + lane) * 4);
