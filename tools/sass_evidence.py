@@ -3,7 +3,7 @@
 UTC*MMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor copies, LDTM / STTM = tcgen05.ld / st (tensor memory), HMMA = mma.sync,
 LDGSTS = cp.async, SYNCS = mbarrier ops, UCGABAR / CGA = cluster barriers.
 
-    python tools/sass_evidence.py > profiles/r1_sass_evidence.md
+    python tools/sass_evidence.py > profiles/r2_sass_evidence.md
 """
 import collections
 import os
