@@ -839,6 +839,19 @@ class GlocalTextPathNavCMT(nn.Module):
                        self.B32(gt + ".visual_attention.att.key.bias", gt + ".visual_attention.att.value.bias"), out_f16=kv_txt)
         if getattr(grid, "pending", False):
             grid.launch_update()          # gridmm_grid_update of a step(lazy=True): first kernel of the step's graph
+        # the packed map sequence's index (gridmm_map_index, one CTA) only needs the cells too: a third branch behind the grid
+        # update, joined before gridmm_map_inputs_packed (it used to sit between grid_proj and the map encoders)
+        ragged = bool(getattr(self, "ragged_map", True)) and S <= 320      # gridmm_attention_ragged_f16 covers <= 320 keys
+        idx_branch = None
+        if ragged:
+            m_off = self.buf("m_off", (B + 1,), torch.int32, zero=True)
+            m_info = self.buf("m_info", (4, B), torch.int32, zero=True)        # rows: k_b, k_b + q_b, rows per episode, z_b
+            m_logz = self.buf("m_logz", (B,), f32, zero=True)
+            m_goff = self.buf("m_goff", (B,), torch.int32, zero=True)
+            cell_of_rank = self.buf("cell_of_rank", (B, NC), torch.int32, zero=True)
+            idx_branch = self._fork_side(txt16.device, index=5)
+            with idx_branch:
+                ops.map_index(grid.cell_rank, grid.n_nonempty, B, NC, G, m_off, m_info, m_logz, cell_of_rank, m_goff)
         # the pooling kernel's work plan only needs the sorted cells: it runs behind the grid update, concurrently with the text branch
         plan_ws = ops.pool_plan(grid.cell_start, NC, B, grid.feat_dim)
         side.join()
@@ -867,21 +880,15 @@ class GlocalTextPathNavCMT(nn.Module):
         inter = {}
         vp_args = (st["vp_pos"], self.Wt32(ve + ".0.weight"), self.P(ve + ".0.bias"), self.P(ve + ".1.weight"), self.P(ve + ".1.bias"),
                    st["vp_img"])
-        ragged = bool(getattr(self, "ragged_map", True)) and S <= 320      # gridmm_attention_ragged_f16 covers <= 320 keys
         if ragged:
             # PACKED map sequence (include/gridmm_b200.h): only the rows that matter -- the non-empty cells, ONE representative of the
             # zero-vector slots the compaction quirk flags valid (key bias log z), all G gmap nodes -- back to back; every map-sized
             # GEMM / attention launch below runs over m_off[B] rows (a device-side count) instead of B * S
-            m_off = self.buf("m_off", (B + 1,), torch.int32, zero=True)
-            m_info = self.buf("m_info", (4, B), torch.int32, zero=True)        # rows: k_b, k_b + q_b, rows per episode, z_b
-            m_logz = self.buf("m_logz", (B,), f32, zero=True)
-            m_goff = self.buf("m_goff", (B,), torch.int32, zero=True)
-            cell_of_rank = self.buf("cell_of_rank", (B, NC), torch.int32, zero=True)
             m_kvalid = self.buf("m_kvalid", (B * S,), u8, zero=True)
             m_kbias = self.buf("m_kbias", (B * S,), f32, zero=True)
             kv_src = self.buf("kv_src", (B * KC,), torch.int32, zero=True)
             kv_bias = self.buf("kv_bias", (B * KC,), f32, zero=True)
-            ops.map_index(grid.cell_rank, grid.n_nonempty, B, NC, G, m_off, m_info, m_logz, cell_of_rank, m_goff)
+            idx_branch.join()
             ops.map_inputs_packed(proj32, grid.pos_fts, cell_of_rank, m_off, m_info, m_logz, self.Wt32("grid_pos_embeddings.0.weight"),
                                   self.P("grid_pos_embeddings.0.bias"), self.P("grid_pos_embeddings.1.weight"),
                                   self.P("grid_pos_embeddings.1.bias"), st["gmap_pos"], self.Wt32(ge + ".0.weight"),

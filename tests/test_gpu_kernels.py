@@ -413,6 +413,24 @@ def test_pool_handmade_cells(sizes, ctas):
     assert pooled[1].abs().max().item() == 0
 
 
+def test_pool_batch_without_any_valid_point():
+    """Every episode empty (no valid depth at all): the plan hands out empty ranges, nothing is written, nothing hangs."""
+    from gridmm_b200 import ops
+    B, nc, D, L, t_cap = 2, 196, 768, 20, 1
+    cap = t_cap * 588
+    dev = _dev()
+    slab = torch.randn(B * cap, D, device=dev).half()
+    slots = torch.arange(B * t_cap, dtype=torch.int32, device=dev).view(B, t_cap)
+    perm = torch.zeros(B, cap, dtype=torch.int32, device=dev)
+    cell_start = torch.zeros(B, nc + 1, dtype=torch.int32, device=dev)
+    cell_rank = torch.full((B, nc), -1, dtype=torch.int32, device=dev)
+    tp = torch.randn(B * L, D, device=dev).half()
+    pooled = torch.full((B * nc, D), 7.0, device=dev, dtype=torch.float16)
+    ops.pool(slab, D, slots, t_cap, 588, 49, 0, perm, cap, cell_start, cell_rank, nc, tp, L, B, pooled)
+    torch.cuda.synchronize()
+    assert bool((pooled == 7.0).all())
+
+
 @pytest.mark.parametrize("ctas", [0, 7, 300])
 def test_pool_plan_invariants(ctas):
     """gridmm_pool_plan: the ranges tile the sorted valid rows in order, a cut is either on a cell boundary or further than the

@@ -710,3 +710,39 @@ def test_device_feature_db_steps_by_key():
             assert np.array_equal(ca[b], cb[b]) and torch.equal(fa[b], fb[b]), "step %d episode %d" % (t, b)
     with pytest.raises(KeyError):
         gb_b.step(ep["depth_sub"][:, 0], None, pos, heading, keys=["nope"] * B)
+
+
+@pytest.mark.gpu
+def test_programmatic_dependent_launch_does_not_change_results():
+    """Every kernel is launched with programmatic stream serialization by default (GRIDMM_PDL, csrc/host_util.cu): the same
+    forward in a process with GRIDMM_PDL=0 (plain stream order) must give bitwise identical outputs."""
+    import subprocess
+    import sys
+    import tempfile
+    name = "r2r_small"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import os, sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from gridmm_b200 import synth\n"
+        "from tests import helpers as H\n"
+        "from tests.test_gpu_nav import _model, _to_cuda\n"
+        "ep_kw, nav_kw, model_kw = H.NAV_CASES[%r]\n"
+        "model, _ = _model(H.make_config(**model_kw), ep_kw['seed'])\n"
+        "ep = synth.make_episodes(dim=768, **ep_kw)\n"
+        "cells, fts, _, pos = H.oracle_grid(ep)\n"
+        "out = model('navigation', _to_cuda(H.nav_batch(ep_kw, nav_kw, cells, fts, pos)))\n"
+        "torch.cuda.synchronize()\n"
+        "np.savez(sys.argv[1], **{k: v.float().cpu().numpy() for k, v in out.items() if torch.is_tensor(v)})\n" % (root, name))
+    outs = {}
+    with tempfile.TemporaryDirectory() as d:
+        for pdl in ("0", "1"):
+            path = os.path.join(d, "out%s.npz" % pdl)
+            env = dict(os.environ, GRIDMM_PDL=pdl)
+            r = subprocess.run([sys.executable, "-c", script, path], env=env, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=280)
+            assert r.returncode == 0, r.stdout.decode()[-2000:]
+            z = np.load(path)
+            outs[pdl] = {k: z[k] for k in z.files}
+    assert set(outs["0"]) == set(outs["1"]) and "fused_logits" in outs["0"]
+    for k in outs["0"]:
+        assert np.array_equal(outs["0"][k], outs["1"][k], equal_nan=True), k
