@@ -386,3 +386,46 @@ def test_wrappers_and_ctypes_table_agree_with_the_header():
             assert len(node.args) - 1 == len(_lib._SIGS[name]), "%s: ops.py passes %d arguments, ctypes table has %d" % (
                 name, len(node.args) - 1, len(_lib._SIGS[name]))
     assert seen == set(_lib._SIGS), set(_lib._SIGS) ^ seen
+
+
+def test_feature_files_read_the_reference_formats(tmp_path):
+    """gridmm_b200/io.py against what the reference's DepthFeaturesDB / SemanticFeaturesDB (map_nav_src/r2r/env.py:80-113) and the
+    depth sub-sampling of getGlobalMap (:279-285) would produce from the same stored arrays (an in-memory store stands in for
+    h5py.File: this image has no h5py)."""
+    import json
+    from gridmm_b200.io import FeatureFiles
+    from gridmm_b200.env import GridMapBuilder
+    rng = np.random.default_rng(3)
+    keys = [("scanA", "vp1"), ("scanA", "vp2"), ("scanB", "vp9")]
+    clip_store, depth_store, info = {}, {}, {}
+    for i, (s, v) in enumerate(keys):
+        k = "%s_%s" % (s, v)
+        clip_store[k] = rng.standard_normal((12, 50 + i, 768))                     # written as "float" (float64), >= 50 tokens
+        d = rng.integers(0, 40000, (36, 128, 128)).astype(np.float64)
+        depth_store[k] = d[..., None] if i == 1 else (d.reshape(36, -1) if i == 2 else d)      # the three layouts seen in the wild
+        info[k] = {"x": float(i), "y": 2.0 * i, "z": 0.5}
+    vinfo = tmp_path / "viewpoint_info.json"
+    vinfo.write_text(json.dumps(info))
+    stores = {"clip.h5": clip_store, "depth.h5": depth_store}
+    ff = FeatureFiles("clip.h5", "depth.h5", str(vinfo), open_fn=lambda path: stores[path])
+    for i, (s, v) in enumerate(keys):
+        k = "%s_%s" % (s, v)
+        # SemanticFeaturesDB: f[key][...][:, :50].astype(float16)
+        assert np.array_equal(ff.clip_tokens(s, v), clip_store[k][:, :50].astype(np.float16))
+        # DepthFeaturesDB + getGlobalMap's sub-sampling: depth[:, idx][:, :, idx].reshape(36, -1), rows 12..23 are used
+        full = np.asarray(depth_store[k]).reshape(36, 128, 128).astype(np.uint16)
+        idx = np.array([9 + 18 * j for j in range(7)])
+        ref = full[:, idx][:, :, idx].reshape(36, -1)[12:24]
+        assert np.array_equal(GridMapBuilder.subsample_depth(ff.depth_map(s, v)), ref)
+        assert ff.position(s, v) == (float(i), 2.0 * i)
+    depth, clip, pos = ff.step_inputs(keys)
+    assert depth.shape == (3, 12, 49) and depth.dtype == np.uint16 and clip.shape == (3, 12, 50, 768) and clip.dtype == np.float16
+    assert pos.shape == (3, 2) and ff.step_inputs(keys, with_clip=False)[1] is None
+
+    class FakeDB(dict):
+        def put(self, k, fts):
+            self[k] = fts
+    db = FakeDB()
+    assert ff.preload(db, keys) == 3 and ff.preload(db, keys) == 0 and db["scanB_vp9"].shape == (12, 50, 768)
+    with pytest.raises(ValueError):
+        FeatureFiles("clip.h5", "depth.h5", open_fn=lambda path: {"a_b": np.zeros((12, 50, 512))}).clip_tokens("a", "b")
