@@ -14,6 +14,7 @@ What runs where (and what does not run on this package's kernels yet):
 """
 import collections
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -268,6 +269,7 @@ class PretrainModel(nn.Module):
         self._cache = _WeightCache()
         self.weights_updated = self._cache.invalidate        # GradientStep(..., after_step=[model.weights_updated])
         self.use_native_linear = True
+        self.use_fused_attention = os.environ.get("GRIDMM_TRAIN_SDPA", "1") != "0"      # torch SDPA for the attention cores (A/B switch)
         # optional split-precision forward (3 GEMMs, ~fp32 accuracy) of text_proj, whose output feeds the per-cell softmax.  Off by
         # default: on the parity batch it does not change the gradient error, which comes from ReLU units of the ClsPrediction heads
         # changing side under the fp16 rounding of ANY upstream operand (tools/diag_train_grad.py)
@@ -311,10 +313,18 @@ class PretrainModel(nn.Module):
 
     def attend(self, q, k, v, add_mask, p_drop=None):
         """softmax(q k^T / sqrt(64) + mask) v, dropout on the probabilities in training mode (vilmodel.py:95-153, 317-368)."""
-        s = torch.matmul(self._heads(q), self._heads(k).transpose(-1, -2)) / math.sqrt(HID // HEADS)
-        if add_mask is not None:
-            s = s + add_mask
-        o = torch.matmul(self.drop(torch.softmax(s, -1), self.p_att if p_drop is None else p_drop), self._heads(v))
+        p = self.p_att if p_drop is None else p_drop
+        if self.use_fused_attention and q.is_cuda:
+            # torch's fused fp32 attention (library kernel: one launch forward, one backward, instead of ~6 + ~10 eager ones in a
+            # launch-bound step); same mathematics, dropout on the probabilities inside the kernel
+            m = None if add_mask is None else add_mask.to(q.dtype).expand(q.shape[0], HEADS, q.shape[1], k.shape[1])
+            o = F.scaled_dot_product_attention(self._heads(q), self._heads(k), self._heads(v), attn_mask=m,
+                                               dropout_p=p if (self.training and p > 0.0) else 0.0)
+        else:
+            s = torch.matmul(self._heads(q), self._heads(k).transpose(-1, -2)) / math.sqrt(HID // HEADS)
+            if add_mask is not None:
+                s = s + add_mask
+            o = torch.matmul(self.drop(torch.softmax(s, -1), p), self._heads(v))
         B, H, S, Dh = o.shape
         return o.permute(0, 2, 1, 3).reshape(B, S, H * Dh)
 
