@@ -1238,11 +1238,12 @@ class GlocalTextPathNavCMT(nn.Module):
         """The kernels behind forward() are inference kernels: dropout is the identity and no autograd graph is recorded (the
         outputs never require grad).  The reference's fine-tuning loop calls loss.backward() on these outputs
         (map_nav_src/r2r/agent_base.py:203-208); rather than let that fail later with "does not require grad" -- or let
-        model.train() silently behave as eval -- training mode is refused here.  The training step of this package is
-        gridmm_b200.train (pretraining objectives), not this forward."""
+        model.train() silently behave as eval -- training mode is refused here.  The trainable counterpart of this forward is
+        gridmm_b200.train_nav (same modes, same state_dict keys); the pretraining step is gridmm_b200.train_model / train."""
         if self.training:
             raise RuntimeError("gridmm_b200 forward(mode, batch) is inference-only (eval semantics, no autograd): call model.eval() "
-                               "for test/eval rollouts; see gridmm_b200.train for the training step")
+                               "for test/eval rollouts, or fine-tune with gridmm_b200.train_nav.VLNBertTrainable (same interface and "
+                               "state_dict keys, autograd enabled)")
 
     def forward(self, mode, batch, **kwargs):
         """vilmodel.py:920-939.  A tuple batch selects the continuous-env calling convention (gridmap/vilmodel.py:802-817)."""

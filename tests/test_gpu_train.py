@@ -167,3 +167,46 @@ def test_one_training_step_through_flat_buffers():
         assert abs(after - float(ref_model(batch, "sap").mean())) < 1e-4    # index_add atomics reorder sums; a stale cache is off by 1.6e-3
         stale = {n: p.detach().clone() for n, p in model.named_parameters()}
     assert any(float((stale[n] - before[n]).abs().max()) > 0 for n in before)
+
+
+def test_trainable_nav_on_the_gpu():
+    """gridmm_b200/train_nav.py with its linears on the tcgen05 GEMM: forward('navigation') in train() mode against the
+    reference's own outputs, loss.backward() against CPU autograd through the oracle, and the weights handed to the inference
+    model give the same logits (the fine-tuning loop the reference runs around this model: r2r/agent_base.py:203-208)."""
+    from oracle import model_oracle as mo
+    from gridmm_b200.model import GlocalTextPathNavCMT
+    from tests.test_cpu_train_nav import _nav_setup
+    name = "reverie_small"
+    model, cfg, w, nav = _nav_setup(name)
+    gold = np.load(os.path.join(H.GOLD, "nav_%s.npz" % name))
+    dev = torch.device("cuda:0")
+    model.to(dev).train()
+    nav_d = {k: (v.to(dev) if torch.is_tensor(v) else ([t.to(dev) for t in v] if isinstance(v, list) and v and torch.is_tensor(v[0]) else v))
+             for k, v in nav.items()}
+    out = model("navigation", nav_d)
+    for k in ("global_logits", "local_logits", "fused_logits", "obj_logits", "grid_logits"):
+        H.finite_close(out[k].detach(), gold[k], atol=2e-3)          # fp16 GEMM operands, fp32 accumulate
+    B = nav["gmap_masks"].shape[0]
+    finite = torch.isfinite(out["fused_logits"].detach().cpu())
+    target = torch.tensor([int(torch.nonzero(finite[b])[-1]) for b in range(B)])
+    loss = torch.nn.functional.cross_entropy(out["fused_logits"], target.to(dev), reduction="sum")
+    loss.backward()
+    sd = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in w.items()}
+    ref_loss = torch.nn.functional.cross_entropy(mo.navigation(sd, nav, n_x_layers=cfg.num_x_layers)["fused_logits"], target, reduction="sum")
+    ref_loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) < 5e-3
+    tot = err = 0.0
+    for n, p in model.named_parameters():
+        if sd[n].grad is not None:
+            tot += float(sd[n].grad.double().pow(2).sum())
+            err += float((p.grad.cpu() - sd[n].grad).double().pow(2).sum())
+    rel = (err / tot) ** 0.5
+    print("trainable nav: whole-model relative gradient error %.3e" % rel)
+    assert rel < 4e-2            # ReLU units of the ClsPrediction heads flip under fp16 operand rounding (DESIGN.md section 8)
+    # the trained weights drop into the inference model
+    inf = GlocalTextPathNavCMT(cfg)
+    inf.load_state_dict(model.state_dict(), strict=True)
+    inf.to(dev).eval()
+    out_i = inf("navigation", nav_d)
+    torch.cuda.synchronize()
+    H.finite_close(out_i["fused_logits"], out["fused_logits"].detach(), atol=2e-3)
