@@ -146,8 +146,16 @@ class TrainableNavCMT(PretrainModel):
         txt, txt_masks = batch["txt_embeds"], batch["txt_masks"].bool()
         dev = txt.device
         gmap_masks, vp_masks = batch["gmap_masks"].bool(), batch["vp_masks"].bool()
-        cells, nonempty = self.nav_grid_pool(txt, batch["grid_fts"], batch["grid_map"])
-        pos = self.ln("grid_pos_embeddings.1", F.linear(batch["gridmap_pos_fts"].to(dev), self.P("grid_pos_embeddings.0.weight"),
+        grid_fts, grid_map, grid_pos = batch["grid_fts"], batch["grid_map"], batch["gridmap_pos_fts"]
+        if batch["grid"] is not None:
+            # a device-built grid (GridMapBuilder.step): the reference's per-episode views of it, all on the device
+            g = batch["grid"]
+            grid_fts = g.grid_fts_torch()
+            n = g.n_pts.cpu().numpy()
+            grid_map = [g.cell[i, :int(n[i])] for i in range(g.batch)]
+            grid_pos = g.pos_fts
+        cells, nonempty = self.nav_grid_pool(txt, grid_fts, grid_map)
+        pos = self.ln("grid_pos_embeddings.1", F.linear(grid_pos.to(dev), self.P("grid_pos_embeddings.0.weight"),
                                                         self.P("grid_pos_embeddings.0.bias")), 1e-12)
         cell_embeds, cell_masks, C = self.compact(cells + pos, nonempty)
         ge, le = "global_encoder", "local_encoder"

@@ -210,3 +210,15 @@ def test_trainable_nav_on_the_gpu():
     out_i = inf("navigation", nav_d)
     torch.cuda.synchronize()
     H.finite_close(out_i["fused_logits"], out["fused_logits"].detach(), atol=2e-3)
+    # a device-built grid (GridMapBuilder) instead of the reference's lists gives the same logits
+    from gridmm_b200.env import GridMapBuilder
+    ep_kw = H.NAV_CASES[name][0]
+    ep = synth.make_episodes(dim=768, **ep_kw)
+    gb = GridMapBuilder(ep_kw["batch"], max_steps=ep_kw["steps"])
+    for t in range(ep_kw["steps"]):
+        grid = gb.step(ep["depth_sub"][:, t], ep["clip"][:, t], ep["pos"][:, t], ep["heading"][:, t])
+    nav_g = {k: v for k, v in nav_d.items() if k not in ("grid_fts", "grid_map", "gridmap_pos_fts")}
+    nav_g["grid"] = grid
+    with torch.no_grad():
+        out_g = model("navigation", nav_g)
+    H.finite_close(out_g["fused_logits"], out["fused_logits"].detach(), atol=1e-4)
