@@ -164,7 +164,9 @@ def test_one_training_step_through_flat_buffers():
         ref_model, _, _ = _setup(case)
         ref_model = ref_model.cuda()
         ref_model.load_state_dict(model.state_dict())
-        assert abs(after - float(ref_model(batch, "sap").mean())) < 1e-4    # index_add atomics reorder sums; a stale cache is off by 1.6e-3
+        # index_add atomics reorder sums by ~1e-7 and the fp16 operand casts can turn that into a flipped ReLU unit of a head
+        # (DESIGN.md section 8): two forwards of the same weights agree to a few 1e-5, rarely 1e-4; a stale cache is off by 1.6e-3
+        assert abs(after - float(ref_model(batch, "sap").mean())) < 5e-4
         stale = {n: p.detach().clone() for n, p in model.named_parameters()}
     assert any(float((stale[n] - before[n]).abs().max()) > 0 for n in before)
 
@@ -221,4 +223,5 @@ def test_trainable_nav_on_the_gpu():
     nav_g["grid"] = grid
     with torch.no_grad():
         out_g = model("navigation", nav_g)
-    H.finite_close(out_g["fused_logits"], out["fused_logits"].detach(), atol=1e-4)
+    # (the device-built position features differ from the oracle's by <= 2e-6, which the fp16 operand rounding can amplify)
+    H.finite_close(out_g["fused_logits"], out["fused_logits"].detach(), atol=2e-3)
