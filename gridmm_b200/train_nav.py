@@ -54,7 +54,13 @@ class TrainableNavCMT(PretrainModel):
         return nn.Module.state_dict(self, *a, **k)
 
     # ------------------------------------------------------------------ modes
+    CE_KEYS = ("txt_embeds", "txt_masks", "gmap_img_embeds", "gmap_step_ids", "gmap_pos_fts", "gmap_masks", "vp_img_embeds",
+               "vp_pos_fts", "vp_masks", "vp_nav_masks", "grid_fts", "grid_map", "gridmap_pos_fts", "candidate_lengths")
+
     def forward(self, mode, batch):
+        if mode == "navigation" and isinstance(batch, (tuple, list)):
+            # continuous-env calling convention: the 14-tuple of Policy_ViewSelection_GridMap.py:622-623
+            return self.forward_navigation_ce(dict(zip(self.CE_KEYS, batch)))
         batch = collections.defaultdict(lambda: None, batch)
         if mode == "language":
             return self.forward_text(batch["txt_ids"], batch["txt_masks"])
@@ -140,8 +146,29 @@ class TrainableNavCMT(PretrainModel):
         masks = ((pos < k[:, None]) | tail) & (pos < k2[:, None])
         return embeds, masks[:, :C], C
 
+    def forward_navigation_ce(self, batch):
+        """VLN_CE/vlnce_baselines/models/gridmap/vilmodel.py:710-800: same trunk, the action logits are global * w + local * (1 - w)
+        on the first max(candidate_lengths) slots, masked by vp_nav_masks (:791-800)."""
+        batch = collections.defaultdict(lambda: None, batch)
+        gmap_e, vp_e, _, _ = self._nav_trunk(batch)
+        fw = torch.sigmoid(self.cls_head("sap_fuse_linear", torch.cat([gmap_e[:, 0], vp_e[:, 0]], 1)))
+        maxc = int(max(batch["candidate_lengths"]))
+        nav = ~batch["vp_nav_masks"].bool()[:, :maxc]
+        ninf = float("-inf")
+        gl = (self.cls_head("global_sap_head", gmap_e).squeeze(2) * fw)[:, :maxc].masked_fill(nav, ninf)
+        ll = (self.cls_head("local_sap_head", vp_e).squeeze(2) * (1 - fw))[:, :maxc].masked_fill(nav, ninf)
+        return gl + ll
+
     def forward_navigation(self, batch):
         """vilmodel.py:782-918 (forward_navigation_per_step)."""
+        cfg = self.config
+        gmap_e, vp_e, gmap2, gmap_masks = self._nav_trunk(batch)
+        dev = gmap_e.device
+        G, V = gmap_e.shape[1], vp_e.shape[1]
+        return self._nav_heads(batch, gmap_e, vp_e, gmap2, gmap_masks, G, V, dev)
+
+    def _nav_trunk(self, batch):
+        """Everything of forward_navigation_per_step up to the fused [gmap; vp] embeddings (vilmodel.py:788-856)."""
         cfg = self.config
         txt, txt_masks = batch["txt_embeds"], batch["txt_masks"].bool()
         dev = txt.device
@@ -175,9 +202,12 @@ class TrainableNavCMT(PretrainModel):
         q_add = self.neg_mask(torch.cat([gmap_masks, vp_masks], 1))
         for i in range(cfg.num_x_layers):
             q = self.lxrt(le + ".encoder.x_layers.%d" % i, ctx, ctx_add, q, q_add)
-        G, V = gmap.shape[1], vp.shape[1]
-        gmap_e, vp_e = q[:, :G], q[:, G:]
-        # ---- heads and logit fusion (vilmodel.py:859-907)
+        G = gmap.shape[1]
+        return q[:, :G], q[:, G:], gmap2, gmap_masks
+
+    def _nav_heads(self, batch, gmap_e, vp_e, gmap2, gmap_masks, G, V, dev):
+        """Heads and logit fusion (vilmodel.py:859-907)."""
+        cfg = self.config
         ninf = float("-inf")
         fw = torch.sigmoid(self.cls_head("sap_fuse_linear", torch.cat([gmap_e[:, 0], vp_e[:, 0]], 1))) if cfg.glocal_fuse else 0.5
         visited = batch["gmap_visited_masks"].bool()

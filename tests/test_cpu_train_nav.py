@@ -83,6 +83,23 @@ def test_trainable_nav_gradients_match_autograd_through_the_oracle():
     assert n_grad > 150 and (err / tot) ** 0.5 < 1e-4
 
 
+def test_trainable_continuous_env_variant_matches_reference_golden():
+    """The 14-tuple calling convention of the continuous-env policy (BASELINE config 4) against the reference's CE model."""
+    from oracle import grid_oracle as go
+    from gridmm_b200.train_nav import TrainableNavCMT
+    ep_kw, nav_kw = H.CE_NAV_CASE
+    gold = np.load(os.path.join(H.GOLD, "nav_ce_small.npz"))
+    cfg = H.make_config(graph_sprels=False)
+    model = TrainableNavCMT(cfg, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in H.make_weights(cfg, ep_kw["seed"]).items()})
+    cells, fts, _, pos = H.oracle_grid(H.ce_episodes(ep_kw), geom=go.CEGeometry)
+    tup = H.ce_nav_tuple(ep_kw, nav_kw, cells, fts, pos)
+    out = model("navigation", tup)
+    H.finite_close(out.detach(), gold["fused_logits"], atol=5e-5)
+    out[torch.isfinite(out)].sum().backward()
+    assert sum(1 for p in model.parameters() if p.grad is not None and float(p.grad.abs().max()) > 0) > 100
+
+
 def test_wrapper_applies_feature_dropout_only_in_training():
     from types import SimpleNamespace
     from gridmm_b200.train_nav import VLNBertTrainable
