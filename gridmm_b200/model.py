@@ -1277,26 +1277,28 @@ class GlocalTextPathNavCMT(nn.Module):
         raise NotImplementedError("wrong mode: %s" % mode)
 
 
+def nav_config_from_args(args=None):
+    """The NavConfig the reference builds from its command-line arguments (models/vlnbert_init.py:29-56)."""
+    kw = {}
+    if args is not None:
+        for a in ("image_feat_size", "angle_feat_size", "obj_feat_size", "num_l_layers", "num_pano_layers", "num_x_layers", "graph_sprels"):
+            if hasattr(args, a):
+                kw[a] = getattr(args, a)
+        if hasattr(args, "fusion"):
+            kw["glocal_fuse"] = args.fusion == "dynamic"
+        if getattr(args, "tokenizer", "bert") == "xlm":
+            # PretrainedConfig.from_pretrained('xlm-roberta-base') + type_vocab_size = 2 (vlnbert_init.py:29-35)
+            kw.update(vocab_size=250002, max_position_embeddings=514, type_vocab_size=2, layer_norm_eps=1e-5)
+    return NavConfig(**kw)
+
+
 class VLNBert(nn.Module):
     """map_nav_src/models/model.py:12-40 -- the object the agents hold (`self.vln_bert`)."""
 
     def __init__(self, args=None, config=None):
         super().__init__()
         if config is None:
-            kw = {}
-            if args is not None:
-                for a, c in (("image_feat_size", "image_feat_size"), ("angle_feat_size", "angle_feat_size"),
-                             ("obj_feat_size", "obj_feat_size"), ("num_l_layers", "num_l_layers"),
-                             ("num_pano_layers", "num_pano_layers"), ("num_x_layers", "num_x_layers"),
-                             ("graph_sprels", "graph_sprels"), ("max_action_len", None)):
-                    if c and hasattr(args, a):
-                        kw[c] = getattr(args, a)
-                if hasattr(args, "fusion"):
-                    kw["glocal_fuse"] = args.fusion == "dynamic"
-                if getattr(args, "tokenizer", "bert") == "xlm":
-                    # PretrainedConfig.from_pretrained('xlm-roberta-base') + type_vocab_size = 2 (vlnbert_init.py:29-35)
-                    kw.update(vocab_size=250002, max_position_embeddings=514, type_vocab_size=2, layer_norm_eps=1e-5)
-            config = NavConfig(**kw)
+            config = nav_config_from_args(args)
         self.args = args
         self.vln_bert = GlocalTextPathNavCMT(config)
 

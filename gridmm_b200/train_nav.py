@@ -237,9 +237,9 @@ class VLNBertTrainable(nn.Module):
 
     def __init__(self, args=None, config=None):
         super().__init__()
-        from .model import VLNBert
+        from .model import nav_config_from_args
         if config is None:
-            config = VLNBert(args).vln_bert.config if args is not None else NavConfig()
+            config = nav_config_from_args(args)
         self.args = args
         kw = {}
         if args is not None:
