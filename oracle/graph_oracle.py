@@ -12,22 +12,26 @@ import torch
 
 
 class NodeEmbeds:
-    """node_embeds of one GraphMap (graph_utils.py:114-125)."""
+    """Per-viewpoint running sums of one episode's map (graph_utils.py:114-125): `rewrite` replaces a node's sum by the new
+    embedding with count 1 (the agent does that for the viewpoint it stands on), otherwise the embedding is added to the node's
+    sum and its count grows by one (a viewpoint seen as a candidate from several places); the read-out is the mean."""
 
     def __init__(self):
-        self.node_embeds = {}
+        self.sums, self.counts = {}, {}
+
+    @property
+    def node_embeds(self):                       # same view as the reference's dict: vp -> [sum, count]
+        return {vp: [self.sums[vp], self.counts[vp]] for vp in self.sums}
 
     def update_node_embed(self, vp, embed, rewrite=False):
-        if rewrite:
-            self.node_embeds[vp] = [embed, 1]
-        elif vp in self.node_embeds:
-            self.node_embeds[vp][0] = embed + self.node_embeds[vp][0]
-            self.node_embeds[vp][1] += 1
+        if rewrite or vp not in self.sums:
+            self.sums[vp], self.counts[vp] = embed, 1
         else:
-            self.node_embeds[vp] = [embed, 1]
+            self.sums[vp] = embed + self.sums[vp]
+            self.counts[vp] += 1
 
     def get_node_embed(self, vp):
-        return self.node_embeds[vp][0] / self.node_embeds[vp][1]
+        return self.sums[vp] / self.counts[vp]
 
 
 def step_update(maps, visited, pano_embeds, pano_masks, cur_vpids, cand_vpids, ended):
