@@ -66,6 +66,12 @@ class CEGeometry:
         return v * math.pi / 6 - heading      # :731
 
 
+class RxRCEGeometry(CEGeometry):
+    """RxR-CE: the same conventions with the 79-degree camera (Policy_ViewSelection_GridMap.py:637-638) and MAX_DIST 40 (:282-285)."""
+    tan_half_fov = math.tan(math.pi * 79. / 360.)
+    max_dist = 40.0
+
+
 _OFF7 = [-6 / 7, -4 / 7, -2 / 7, 0., 2 / 7, 4 / 7, 6 / 7]
 
 

@@ -291,15 +291,20 @@ def test_grid_update_8x8_config1():
     np.testing.assert_allclose(grid.pos_fts.cpu().numpy()[0], pos[0], atol=2e-6, rtol=0)
 
 
-def test_grid_update_ce_geometry():
+@pytest.mark.parametrize("geometry", ["r2r_ce", "rxr_ce"])
+def test_grid_update_ce_geometry(geometry):
+    """Continuous-env conventions (Policy_ViewSelection_GridMap.py:632-641, 689-825): R2R-CE (90-degree camera, MAX_DIST 25) and
+    RxR-CE (79 degrees, MAX_DIST 40)."""
     from oracle import grid_oracle as go
+    geom = go.CEGeometry if geometry == "r2r_ce" else go.RxRCEGeometry
     ep = synth.make_episodes(4, 5, seed=4, dim=768)
     ep["depth_sub"] = (ep["depth_sub"].astype(np.float32) / 4000.0).astype(np.float32)       # CE depth is metres
-    cells, fts, halfs, pos = H.oracle_grid(ep, geom=go.CEGeometry)
-    gb, grid, per_step = _run_builder(ep, geometry="r2r_ce")
+    cells, fts, halfs, pos = H.oracle_grid(ep, geom=geom)
+    gb, grid, per_step = _run_builder(ep, geometry=geometry)
     for t in range(5):
         for b in range(4):
             assert np.array_equal(per_step[t][b].astype(np.int32), cells[b][t]), "b=%d t=%d" % (b, t)
+    np.testing.assert_allclose(grid.pos_fts.cpu().numpy(), np.stack(pos), atol=2e-6, rtol=0)
 
 
 def _oracle_pool(fts, cell, tp16, n_cells=196):
