@@ -272,9 +272,9 @@ CE_GRID_CASE = dict(seed=41, batch=3, steps=6)
 CE_NAV_CASE = (dict(batch=3, steps=3, seed=42), dict(txt_len=24, gmap_len=10, n_views=12, n_objs=0))
 
 
-def reference_ce_grid(ep):
+def reference_ce_grid(ep, dataset="R2R", max_dist=25):
     B, T = ep["pos"].shape[:2]
-    g = _refshim.load_reference_ce_grid(B)
+    g = _refshim.load_reference_ce_grid(B, dataset=dataset, max_dist=max_dist)
     dep = (ep["depth_sub"].astype(np.float32) / 4000.0).astype(np.float32)          # CE depth is float32 metres
     cells = [[None] * T for _ in range(B)]
     fts, pos_fts = [None] * B, [None] * B
@@ -336,12 +336,30 @@ def make_nav():
         print("wrote", path, os.path.getsize(path), {k: tuple(v.shape) for k, v in save.items()})
 
 
+RXR_CE_GRID_CASE = dict(seed=43, batch=3, steps=4)
+
+
+def make_rxr_ce():
+    """RxR-CE conventions of the same source (DATASET = 'RxR': 79-degree camera, Policy_ViewSelection_GridMap.py:635-638; MAX_DIST
+    40, :282-285): cell ids per step and gridmap_pos_fts of the last step."""
+    case = RXR_CE_GRID_CASE
+    ep = synth.make_episodes(case["batch"], case["steps"], seed=case["seed"], dim=768)
+    cells, _, pos_fts = reference_ce_grid(ep, dataset="RxR", max_dist=40)
+    out = {"pos_fts_last": np.stack(pos_fts).astype(np.float32)}
+    for b in range(case["batch"]):
+        for t in range(case["steps"]):
+            out["cell_b%d_t%d" % (b, t)] = cells[b][t]
+    path = os.path.join(GOLD, "grid_rxrce_s%d.npz" % case["seed"])
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
     if not _refshim.available():
         raise SystemExit("reference not available at %s" % _refshim.REF_ROOT)
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
-    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "pretrain", "pretrain_model", "pretrain_heads", "pretrain_obj"]
+    which = sys.argv[1:] or ["grid", "nav", "aux", "ce", "rxr_ce", "pretrain", "pretrain_model", "pretrain_heads", "pretrain_obj"]
     if "grid" in which:
         make_grid()
     if "nav" in which:
@@ -350,6 +368,8 @@ if __name__ == "__main__":
         make_aux()
     if "ce" in which:
         make_ce()
+    if "rxr_ce" in which:
+        make_rxr_ce()
     if "pretrain" in which:
         make_pretrain_grid()
     if "pretrain_model" in which:

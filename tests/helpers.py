@@ -30,6 +30,7 @@ PRETRAIN_MODEL_CASE = dict(seed=61, batch=3, max_steps=4, txt_len=40, model=dict
 PRETRAIN_OBJ_CASE = dict(seed=62, batch=3, max_steps=3, txt_len=32, n_objs=6,
                          model=dict(num_l_layers=1, num_pano_layers=2, num_x_layers=2, obj_feat_size=768))     # mirrors make_golden.py
 CE_GRID_CASE = dict(seed=41, batch=3, steps=6)
+RXR_CE_GRID_CASE = dict(seed=43, batch=3, steps=4)         # mirrors oracle/make_golden.py
 CE_NAV_CASE = (dict(batch=3, steps=3, seed=42), dict(txt_len=24, gmap_len=10, n_views=12, n_objs=0))
 
 

@@ -243,6 +243,22 @@ def test_ce_oracle_matches_reference():
     H.finite_close(out, gold["fused_logits"], atol=2e-5)
 
 
+def test_rxr_ce_oracle_matches_reference():
+    """RxR-CE conventions (DATASET = 'RxR' in Policy_ViewSelection_GridMap.py: 79-degree camera :635-638, MAX_DIST 40 :282-285):
+    cell ids bit-exact and cell-centre features against the reference's own getGlobalMap (oracle/make_golden.py rxr_ce)."""
+    from oracle import grid_oracle as go
+    case = H.RXR_CE_GRID_CASE
+    gold = np.load(os.path.join(H.GOLD, "grid_rxrce_s%d.npz" % case["seed"]))
+    cells, _, _, pos = H.oracle_grid(H.ce_episodes(case), geom=go.RxRCEGeometry)
+    for b in range(case["batch"]):
+        for t in range(case["steps"]):
+            assert np.array_equal(gold["cell_b%d_t%d" % (b, t)].astype(np.int32), cells[b][t])
+    np.testing.assert_allclose(np.stack(pos), gold["pos_fts_last"], atol=1e-6, rtol=0)
+    # and it is not the R2R-CE geometry in disguise
+    cells_r2r, _, _, _ = H.oracle_grid(H.ce_episodes(case), geom=go.CEGeometry)
+    assert any(not np.array_equal(cells_r2r[b][-1], cells[b][-1]) for b in range(case["batch"]))
+
+
 def test_graph_oracle_matches_reference_graphmap():
     """oracle/graph_oracle.NodeEmbeds against the reference's own GraphMap.update_node_embed / get_node_embed
     (map_nav_src/models/graph_utils.py:114-125), imported from /root/reference when present (the authoring container);
