@@ -51,7 +51,7 @@ constexpr int POOL_MAX_CTAS = 1024;
 constexpr int POOL_MAX_CELLS = 256;
 constexpr int POOL_TMEM_COLS = 512;
 constexpr int POOL_PTS = 588, POOL_VIEW_PTS = 49;   // points per viewpoint / per view (r2r/env.py:279-289)
-constexpr int POOL_EPISODE_COST = 160;              // rows' worth of time an episode switch costs a CTA (text staging, partial tiles)
+constexpr int POOL_EPISODE_COST = 200;              // rows' worth of time an episode switch costs a CTA (text staging, partial tiles)
 constexpr int POOL_SNAP = 16;                       // a CTA boundary within this many rows of a cell boundary moves onto it
 
 // Work plan of one launch (gridmm_pool_plan -> workspace, read by every CTA of pool_kernel): the sorted valid rows of the whole
