@@ -83,3 +83,34 @@ class DeviceGraphMaps:
             out = torch.empty(B, G, self.dim, dtype=torch.float32, device=self.device)
         ops.gmap_gather(self.node_sum, self.node_cnt, slots, out)
         return out
+
+
+def teacher_actions(obs, gmap_vpids, ended, shortest_distances, visited_masks=None, ignoreid=-100):
+    """Imitation-learning targets of one step (map_nav_src/r2r/agent.py:207-237), as one masked arg-min per episode:
+    an ended episode -> `ignoreid`; standing on the goal (last viewpoint of `gt_path`) -> 0 ([stop]); otherwise the map node j >= 1
+    that is not visited and minimises  d(node_j, goal) + d(current, node_j)  over the scan's shortest-path table (the first such
+    node on ties); no eligible node -> `ignoreid`.  obs[i] needs 'scan', 'viewpoint', 'gt_path'; gmap_vpids[i][0] is the stop slot.
+    Returns int64 [B] (host array: the caller moves it where its loss lives)."""
+    out = np.full(len(obs), ignoreid, dtype=np.int64)
+    for i, ob in enumerate(obs):
+        if ended[i]:
+            continue
+        cur, goal = ob["viewpoint"], ob["gt_path"][-1]
+        if cur == goal:
+            out[i] = 0
+            continue
+        table = shortest_distances[ob["scan"]]
+        from_cur = table[cur]
+        nodes = gmap_vpids[i]
+        cost = np.full(len(nodes), np.inf)
+        eligible = np.ones(len(nodes), dtype=bool)
+        eligible[0] = False
+        if visited_masks is not None:
+            eligible &= ~np.asarray(visited_masks[i], dtype=bool)[:len(nodes)]
+        idx = np.nonzero(eligible)[0]
+        if idx.size:
+            cost[idx] = [table[nodes[j]][goal] + from_cur[nodes[j]] for j in idx]
+            j = int(np.argmin(cost))                      # first minimum, like the reference's strict `<`
+            if np.isfinite(cost[j]):
+                out[i] = j
+    return out

@@ -63,3 +63,43 @@ def test_device_graph_maps_match_the_reference_bookkeeping(B, steps, V, D):
         got = dg.node_embeds(vpids).cpu()
         assert got.shape == ref.shape
         assert (got - ref).abs().max().item() < 2e-6
+
+
+def test_teacher_actions_equal_the_reference_loop():
+    """graph.teacher_actions against a literal restatement of the selection loop of map_nav_src/r2r/agent.py:207-237 on random
+    maps (ties, visited masks, ended episodes, episodes standing on their goal, maps without any eligible node)."""
+    from gridmm_b200.graph import teacher_actions
+    rng = np.random.default_rng(11)
+    vps = ["v%d" % i for i in range(9)]
+    d = rng.integers(1, 5, (9, 9)).astype(float)          # small integers: ties are common
+    d = np.minimum(d, d.T); np.fill_diagonal(d, 0.0)
+    table = {"s": {a: {b: d[i, j] for j, b in enumerate(vps)} for i, a in enumerate(vps)}}
+    for trial in range(200):
+        B = 4
+        obs, vpids, vis, ended = [], [], [], []
+        for b in range(B):
+            n = int(rng.integers(1, 7))
+            nodes = [None] + list(rng.choice(vps, size=n, replace=False))
+            cur = str(rng.choice(vps)); goal = cur if rng.random() < 0.2 else str(rng.choice(vps))
+            obs.append({"scan": "s", "viewpoint": cur, "gt_path": ["x", goal]})
+            vpids.append(nodes)
+            m = rng.random(len(nodes)) < (1.0 if rng.random() < 0.1 else 0.4)
+            vis.append(m.tolist())
+            ended.append(bool(rng.random() < 0.2))
+        masks = None if trial % 3 == 0 else vis
+        want = np.zeros(B, dtype=np.int64)
+        for i, ob in enumerate(obs):                      # the reference's loop, restated
+            if ended[i]:
+                want[i] = -100
+            elif ob["viewpoint"] == ob["gt_path"][-1]:
+                want[i] = 0
+            else:
+                best, best_d = -100, float("inf")
+                for j, vp in enumerate(vpids[i]):
+                    if j > 0 and (masks is None or not masks[i][j]):
+                        dist = table["s"][vp][ob["gt_path"][-1]] + table["s"][ob["viewpoint"]][vp]
+                        if dist < best_d:
+                            best_d, best = dist, j
+                want[i] = best
+        got = teacher_actions(obs, vpids, ended, table, visited_masks=masks)
+        assert np.array_equal(got, want), (trial, got, want)
